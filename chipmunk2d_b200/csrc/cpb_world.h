@@ -1,0 +1,162 @@
+// cpb_world.h -- SoA device layout of a world (the replacement for the reference's
+// cpBody / cpShape / cpArbiter / cpContact / cpConstraint AoS structs,
+// chipmunk_structs.h:35-382).  All views are plain structs of device pointers that are
+// passed to kernels by value.
+#pragma once
+#include "cpb_math.h"
+#include "../../include/cpb200.h"
+
+// ---- per-space step constants (host computes the pow()s with libm: SURVEY.md 8c) ----
+struct DSpace {
+	V2 gravity;
+	double damping_dt;      // pow(space->damping, dt)              cpSpaceStep.c:399
+	double bias_coef;       // 1 - pow(collisionBias, dt)            cpSpaceStep.c:384
+	double slop;
+	double idle_speed;      // idleSpeedThreshold
+	double sleep_threshold; // sleepTimeThreshold
+	uint32_t persistence;
+	int32_t iterations;
+};
+
+// ---- bodies (cpBody, chipmunk_structs.h:35-81) ----
+struct DBodies {
+	int n;
+	V2 *pos;        // p
+	double *ang;    // a
+	V2 *rot;        // (cos a, sin a)  = transform.a, transform.b
+	V2 *txy;        // transform.tx, transform.ty
+	V2 *cog;
+	double4 *V;     // (v.x, v.y, w, unused)          solver-hot: one 32-byte sector
+	double4 *VB;    // (v_bias.x, v_bias.y, w_bias, unused)
+	V2 *MI;         // (m_inv, i_inv)
+	V2 *M;          // (m, i)
+	V2 *force;      // f
+	double *torque; // t
+	double *idle;   // sleeping.idleTime
+	int *type;      // CPB200_BODY_*
+	int *space;
+	int *sleeping;  // 0 awake, 1 asleep
+	int *sgroup;    // sleeping component id (root body index) or -1
+};
+
+// ---- shapes (cpShape + cpCircleShape/cpSegmentShape/cpPolyShape) ----
+struct DShapes {
+	int n, nv;
+	int *type, *body;
+	uint32_t *hashid;
+	int *sensor;
+	uint32_t *cat, *mask;
+	uint64_t *group, *ctype;
+	double *e, *u, *r;
+	V2 *surfv;
+	V2 *la, *lb, *ln;     // body-local: circle c | segment a, b, n
+	V2 *atan, *btan;      // segment neighbour tangents
+	int *pcount, *poff;   // poly vertex range
+	V2 *lpv, *lpn;        // [nv] body-local hull vertices / edge normals (planes[count+i], cpPolyShape.c:147-165)
+	// world-space cache written by k_shape_cache (cacheData, cpShape.c:291-296,378-405; cpPolyShape.c:39-64)
+	V2 *wa, *wb, *wn;     // circle tc | segment ta, tb, tn
+	V2 *wpv, *wpn;        // [nv]
+	double4 *bb;          // (l, b, r, t)
+};
+
+// ---- arbiters + contacts (cpArbiter / cpContact, chipmunk_structs.h:101-145) ----
+// Double buffered: the previous step's records stay readable for warm starting
+// (the role of the reference's contact-buffer ring, cpSpaceStep.c:109-183).
+struct DArbs {
+	int cap;
+	int *count_ptr;        // device counter: number of records
+	uint64_t *key;         // (min hashid)<<32 | (max hashid): the unordered shape pair (cpSpaceStep.c:249-251)
+	int *sa, *sb;          // shape indices in cpCollide order (a.type <= b.type)
+	int *ba, *bb;          // body indices
+	int *cnt;              // contact count (kept while CACHED so hashes can still be matched)
+	int *state;            // CPB200_ARB_*
+	uint32_t *stamp;
+	int *active;           // solved this step
+	int *seen;             // touched by the following step's collision phase
+	uint32_t *gjkid;       // cpCollisionID warm start for GJK
+	V2 *n;
+	double *e, *u;
+	V2 *svr;               // surface_vr
+	// contacts, index = 2*arb + k
+	V2 *r1, *r2;
+	double *nmass, *tmass, *bounce, *bias;
+	double *jn, *jt, *jb;  // jnAcc, jtAcc, jBias
+	uint64_t *hash;
+	int *colour;           // colour assigned this step (-1 = not in the solver)
+};
+
+// open-addressing table: shape-pair key -> arbiter record index (replaces cpHashSet cachedArbiters)
+struct DTable {
+	uint32_t mask;         // capacity - 1 (capacity is a power of two)
+	uint64_t *keys;        // 0 = empty
+	int *vals;
+};
+
+// ---- colour-sorted solver rows (one per active arbiter), rebuilt every step ----
+struct DRows {
+	int cap;
+	int *arb;              // back pointer to the arbiter record
+	int *ba, *bb;
+	int *cnt;
+	V2 *n, *svr;
+	double *u;
+	// contact k of row r at [k*cap + r]
+	V2 *r1, *r2;
+	double *nmass, *tmass, *bounce, *bias;
+	double *jn, *jt, *jb;
+};
+
+// ---- joints (cpConstraint + joint structs, chipmunk_structs.h:250-382) ----
+struct DJoints {
+	int n;
+	int *type, *a, *b;
+	double *max_force, *max_bias, *bias_coef;   // bias_coef = 1 - pow(errorBias, dt), host libm (chipmunk_private.h:264-268)
+	V2 *anchor_a, *anchor_b;
+	double4 *prm;
+	// solver state
+	V2 *r1, *r2, *nrm;     // nrm doubles as grv_tn for groove joints
+	double *nmass;         // nMass | iSum | clamp (groove)
+	double4 *k;            // pivot / groove mass tensor (k11 k12 k21 k22 as cpMat2x2 a b c d)
+	V2 *bias;              // scalar joints use .x
+	V2 *acc;               // jnAcc / jAcc
+	double *aux0, *aux1;   // spring: target_vrn, v_coef | ratchet: angle
+	V2 *jspring;           // impulse applied by damped springs in preStep (cpDampedSpring.c:49-52)
+	int *colour;
+	int *row;              // colour-sorted order: row -> joint index
+};
+
+// ---- broadphase scratch (LBVH over all shapes, rebuilt every step) ----
+struct DBvh {
+	int n;                 // number of leaves (= shapes)
+	uint64_t *keys;        // sorted morton keys
+	int *leaf_shape;       // sorted position -> shape index
+	int *left, *right;     // [n-1] children; >= n-1 means leaf (value - (n-1))
+	int *parent;           // [2n-1]
+	double4 *nbb;          // [2n-1] node bounds; leaves at n-1+i
+	int2 *nsp;             // [2n-1] node space-id range
+	int *flags;            // [n-1] refit arrival counters
+	double *bounds;        // [4] world bounds l b r t
+};
+
+// pair lists by class: 0 circle-circle, 1 circle-segment, 2 everything that needs GJK
+struct DPairs {
+	int cap;
+	int *count;            // [3]
+	int *a[3], *b[3];      // shape indices, a.type <= b.type
+};
+
+// device-side step counters / flags
+struct DCounters {
+	int n_pairs[3];
+	int n_contacts;
+	int n_active;          // active arbiters
+	int n_colours;
+	int overflow;          // bit 0 pairs, 1 arbiters, 2 table, 3 bvh stack, 4 colours
+	int colour_remaining[2];
+	int colour_rounds;
+	int n_overflow_colour;
+	int n_cached;
+	int pad[4];
+};
+
+#define CPB_MAX_COLOURS 64

@@ -1,0 +1,251 @@
+// k_arb.cuh -- K5 wrapper + K6 (arbiter cache) + K8 (contact prestep).
+//
+// The reference handles one candidate pair at a time inside the broadphase callback
+// cpSpaceCollideShapes (cpSpaceStep.c:235-289): narrowphase, find-or-create the arbiter in
+// the cpHashSet keyed by the shape pair, cpArbiterUpdate (warm-start matching by contact
+// hash, cpArbiter.c:356-414), push to space->arbiters.  Here one thread does the same for one
+// pair against a device hash table:
+//   * prev table/records: last step's arbiters (double buffer = the reference's contact
+//     buffer ring, cpSpaceStep.c:109-183);
+//   * cur table/records: filled this step; unmatched prev records are aged or carried over by
+//     k_arb_carry (= cpSpaceArbiterSetFilter, cpSpaceStep.c:292-325).
+#pragma once
+#include "cpb_world.h"
+#include "k_narrow.cuh"
+#include "prims.cuh"
+
+CPB_DEVICE NShape load_nshape(const DShapes &S, const DBodies &B, int s){
+	NShape o;
+	o.type = S.type[s];
+	o.hashid = S.hashid[s];
+	o.r = S.r[s];
+	double4 bb = S.bb[s];
+	o.bbc = vlerp(v2(bb.x, bb.y), v2(bb.z, bb.w), 0.5);
+	o.count = 0; o.pv = 0; o.pn = 0;
+	o.a = v2(0, 0); o.b = v2(0, 0); o.n = v2(0, 0);
+	o.rot = v2(1, 0); o.atan = v2(0, 0); o.btan = v2(0, 0);
+	if(o.type == CPB200_SHAPE_CIRCLE){
+		o.a = S.wa[s];
+	} else if(o.type == CPB200_SHAPE_SEGMENT){
+		o.a = S.wa[s]; o.b = S.wb[s]; o.n = S.wn[s];
+		o.rot = B.rot[S.body[s]];
+		o.atan = S.atan[s]; o.btan = S.btan[s];
+	} else {
+		o.count = S.pcount[s];
+		o.pv = S.wpv + S.poff[s];
+		o.pn = S.wpn + S.poff[s];
+	}
+	return o;
+}
+
+CPB_DEVICE uint64_t arb_key(uint32_t ha, uint32_t hb){
+	uint64_t lo = (ha < hb ? ha : hb), hi = (ha < hb ? hb : ha);
+	return (lo << 32) | hi;
+}
+
+CPB_DEVICE int table_find(const DTable &T, uint64_t key){
+	uint32_t slot = (uint32_t)mix64(key) & T.mask;
+	for(uint32_t probe = 0; probe <= T.mask; probe++){
+		uint64_t k = T.keys[slot];
+		if(k == key) return T.vals[slot];
+		if(k == 0) return -1;
+		slot = (slot + 1) & T.mask;
+	}
+	return -1;
+}
+
+CPB_DEVICE bool table_insert(const DTable &T, uint64_t key, int val){
+	uint32_t slot = (uint32_t)mix64(key) & T.mask;
+	for(uint32_t probe = 0; probe <= T.mask; probe++){
+		unsigned long long old = atomicCAS((unsigned long long *)&T.keys[slot], 0ull, (unsigned long long)key);
+		if(old == 0ull || old == (unsigned long long)key){ T.vals[slot] = val; return true; }
+		slot = (slot + 1) & T.mask;
+	}
+	return false;
+}
+
+// K5 + K6 for one pair class (CLS 0 circle-circle, 1 circle-segment, 2 GJK family).
+// P lists shape pairs with a.type <= b.type.  Block-stride loop over a device-side count.
+template <int CLS>
+__global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int *__restrict__ pa, const int *__restrict__ pb, const int *__restrict__ pcount, int pcap,
+	DArbs prev, DTable prev_table, DArbs cur, DTable cur_table, uint32_t stamp, DCounters *C)
+{
+	int np = *pcount; if(np > pcap) np = pcap;
+	for(int base = blockIdx.x*blockDim.x; base < np; base += gridDim.x*blockDim.x){
+		int i = base + threadIdx.x;
+		bool have = false;
+		Manifold m; m.count = 0; m.id = 0; m.n = v2(0, 0);
+		int sa = 0, sb = 0, pi = -1;
+		uint64_t key = 0;
+		if(i < np){
+			sa = pa[i]; sb = pb[i];
+			key = arb_key(S.hashid[sa], S.hashid[sb]);
+			pi = table_find(prev_table, key);
+			m.id = (pi >= 0 ? prev.gjkid[pi] : 0u);
+			NShape a = load_nshape(S, B, sa), b = load_nshape(S, B, sb);
+			if(CLS == 0) circle_to_circle(a, b, m);
+			else if(CLS == 1) circle_to_segment(a, b, m);
+			else collide_shapes(a, b, m);
+			have = (m.count > 0);
+		}
+		int slot = cpb_warp_append(cur.count_ptr, have);
+		if(!have) continue;
+		if(slot >= cur.cap){ atomicOr((unsigned *)&C->overflow, 2u); continue; }
+
+		int ba = S.body[sa], bb = S.body[sb];
+		// cpArbiterUpdate (cpArbiter.c:356-414)
+		int state = CPB200_ARB_FIRST_COLLISION;
+		int pcnt = 0;
+		if(pi >= 0){
+			prev.seen[pi] = 1;
+			int ps = prev.state[pi];
+			pcnt = prev.cnt[pi];
+			// CACHED -> FIRST_COLLISION (cpArbiter.c:412-413); IGNORE is sticky until separation
+			state = (ps == CPB200_ARB_CACHED ? CPB200_ARB_FIRST_COLLISION : (ps == CPB200_ARB_IGNORE ? CPB200_ARB_IGNORE : CPB200_ARB_NORMAL));
+		}
+		V2 pa_ = B.pos[ba], pb_ = B.pos[bb];
+		for(int k = 0; k < m.count; k++){
+			double jn = 0.0, jt = 0.0;
+			for(int j = 0; j < pcnt; j++){
+				if(m.hash[k] == prev.hash[2*pi + j]){ jn = prev.jn[2*pi + j]; jt = prev.jt[2*pi + j]; }
+			}
+			int c = 2*slot + k;
+			cur.r1[c] = vsub(m.p1[k], pa_);
+			cur.r2[c] = vsub(m.p2[k], pb_);
+			cur.jn[c] = jn; cur.jt[c] = jt; cur.jb[c] = 0.0;
+			cur.hash[c] = m.hash[k];
+			cur.nmass[c] = 0.0; cur.tmass[c] = 0.0; cur.bounce[c] = 0.0; cur.bias[c] = 0.0;
+		}
+		cur.key[slot] = key;
+		cur.sa[slot] = sa; cur.sb[slot] = sb; cur.ba[slot] = ba; cur.bb[slot] = bb;
+		cur.cnt[slot] = m.count;
+		cur.n[slot] = m.n;
+		cur.gjkid[slot] = m.id;
+		cur.e[slot] = S.e[sa]*S.e[sb];
+		cur.u[slot] = S.u[sa]*S.u[sb];
+		V2 svr = vsub(S.surfv[sb], S.surfv[sa]);
+		cur.svr[slot] = vsub(svr, vmul(m.n, vdot(svr, m.n)));
+		cur.stamp[slot] = stamp;
+		cur.seen[slot] = 0;
+		cur.colour[slot] = -1;
+		// active <=> pushed to space->arbiters (cpSpaceStep.c:261-274); the default handler accepts everything
+		bool both_inf = (B.type[ba] != CPB200_BODY_DYNAMIC) && (B.type[bb] != CPB200_BODY_DYNAMIC);
+		bool active = (state != CPB200_ARB_IGNORE) && !(S.sensor[sa] || S.sensor[sb]) && !both_inf;
+		cur.active[slot] = active ? 1 : 0;
+		if(!active && state != CPB200_ARB_IGNORE) state = CPB200_ARB_NORMAL; // cpSpaceStep.c:283
+		cur.state[slot] = state;
+		if(active){ atomicAdd(&C->n_active, 1); atomicAdd(&C->n_contacts, m.count); }
+		if(!table_insert(cur_table, key, slot)) atomicOr((unsigned *)&C->overflow, 4u);
+	}
+}
+
+// cpSpaceArbiterSetFilter (cpSpaceStep.c:292-325) over the previous step's records that the
+// collision phase did not touch.
+__global__ void k_arb_carry(DBodies B, DArbs prev, DArbs cur, DTable cur_table, const DSpace *__restrict__ spaces, uint32_t stamp, DCounters *C)
+{
+	int n_prev = *prev.count_ptr; if(n_prev > prev.cap) n_prev = prev.cap;
+	for(int base = blockIdx.x*blockDim.x; base < n_prev; base += gridDim.x*blockDim.x){
+		int i = base + threadIdx.x;
+		bool keep = false;
+		int new_state = 0, new_active = 0;
+		if(i < n_prev && !prev.seen[i]){
+			int ba = prev.ba[i], bb = prev.bb[i];
+			bool a_rest = (B.type[ba] == CPB200_BODY_STATIC) || B.sleeping[ba];
+			bool b_rest = (B.type[bb] == CPB200_BODY_STATIC) || B.sleeping[bb];
+			new_state = prev.state[i];
+			new_active = (prev.active[i] == 2 ? 2 : 0);
+			if(a_rest && b_rest){
+				keep = true; // preserved untouched (cpSpaceStep.c:302-307)
+			} else if(prev.active[i] == 2){
+				// a body of a dormant arbiter woke up: back into the solver with its saved contacts
+				// and a fresh stamp (cpSpaceActivateBody, cpSpaceComponent.c:45-73)
+				keep = true; new_active = 1;
+			} else {
+				uint32_t ticks = stamp - prev.stamp[i];
+				if(ticks >= 1 && new_state != CPB200_ARB_CACHED) new_state = CPB200_ARB_CACHED;
+				keep = (ticks < spaces[B.space[ba]].persistence);
+			}
+		}
+		int slot = cpb_warp_append(cur.count_ptr, keep);
+		if(!keep) continue;
+		if(slot >= cur.cap){ atomicOr((unsigned *)&C->overflow, 2u); continue; }
+		cur.key[slot] = prev.key[i];
+		cur.sa[slot] = prev.sa[i]; cur.sb[slot] = prev.sb[i]; cur.ba[slot] = prev.ba[i]; cur.bb[slot] = prev.bb[i];
+		cur.cnt[slot] = prev.cnt[i];
+		cur.state[slot] = new_state;
+		cur.stamp[slot] = (new_active == 1 ? stamp : prev.stamp[i]);
+		cur.active[slot] = new_active;
+		cur.seen[slot] = 0;
+		cur.gjkid[slot] = prev.gjkid[i];
+		cur.n[slot] = prev.n[i]; cur.e[slot] = prev.e[i]; cur.u[slot] = prev.u[i]; cur.svr[slot] = prev.svr[i];
+		cur.colour[slot] = -1;
+		for(int k = 0; k < 2; k++){
+			int c = 2*slot + k, p = 2*i + k;
+			cur.r1[c] = prev.r1[p]; cur.r2[c] = prev.r2[p];
+			cur.nmass[c] = prev.nmass[p]; cur.tmass[c] = prev.tmass[p]; cur.bounce[c] = prev.bounce[p]; cur.bias[c] = prev.bias[p];
+			cur.jn[c] = prev.jn[p]; cur.jt[c] = prev.jt[p]; cur.jb[c] = prev.jb[p];
+			cur.hash[c] = prev.hash[p];
+		}
+		if(new_active == 1){ atomicAdd(&C->n_active, 1); atomicAdd(&C->n_contacts, prev.cnt[i]); }
+		else atomicAdd(&C->n_cached, 1);
+		if(!table_insert(cur_table, prev.key[i], slot)) atomicOr((unsigned *)&C->overflow, 4u);
+	}
+}
+
+// K8: cpArbiterPreStep (cpArbiter.c:416-439) with k_scalar (chipmunk_private.h:205-226).
+CPB_DEVICE double k_scalar_body(V2 mi, V2 r, V2 n){
+	double rcn = vcross(r, n);
+	return mi.x + mi.y*rcn*rcn;
+}
+
+__global__ void k_arb_prestep(DBodies B, DArbs A, const DSpace *__restrict__ spaces, double dt, DCounters *C, double *max_pen)
+{
+	int n = *A.count_ptr; if(n > A.cap) n = A.cap;
+	for(int i = CPB_TID; i < n; i += CPB_NTHREADS){
+	if(A.active[i] != 1) continue;
+	int ba = A.ba[i], bb = A.bb[i];
+	DSpace sp = spaces[B.space[ba]];
+	V2 n_ = A.n[i];
+	V2 mia = B.MI[ba], mib = B.MI[bb];
+	double4 Va = B.V[ba], Vb = B.V[bb];
+	V2 body_delta = vsub(B.pos[bb], B.pos[ba]);
+	double e = A.e[i];
+	int cnt = A.cnt[i];
+	for(int k = 0; k < cnt; k++){
+		int c = 2*i + k;
+		V2 r1 = A.r1[c], r2 = A.r2[c];
+		A.nmass[c] = 1.0/(k_scalar_body(mia, r1, n_) + k_scalar_body(mib, r2, n_));
+		V2 t = vperp(n_);
+		A.tmass[c] = 1.0/(k_scalar_body(mia, r1, t) + k_scalar_body(mib, r2, t));
+		double dist = vdot(vadd(vsub(r2, r1), body_delta), n_);
+		A.bias[c] = -sp.bias_coef*fmin_cp(0.0, dist + sp.slop)/dt;
+		A.jb[c] = 0.0;
+		// normal_relative_velocity (chipmunk_private.h:172-183)
+		V2 v1 = vadd(v2(Va.x, Va.y), vmul(vperp(r1), Va.z));
+		V2 v2_ = vadd(v2(Vb.x, Vb.y), vmul(vperp(r2), Vb.z));
+		A.bounce[c] = vdot(vsub(v2_, v1), n_)*e;
+	}
+	}
+	(void)C; (void)max_pen;
+}
+
+// validation hook: narrowphase of one pair (cpShapesCollide, cpShape.c:259-283)
+__global__ void k_collide_one(DShapes S, DBodies B, int sa, int sb, double *out)
+{
+	if(CPB_TID != 0) return;
+	bool swapped = false;
+	if(S.type[sa] > S.type[sb]){ int t = sa; sa = sb; sb = t; swapped = true; }
+	NShape a = load_nshape(S, B, sa), b = load_nshape(S, B, sb);
+	Manifold m; m.id = 0;
+	collide_shapes(a, b, m);
+	for(int k = 0; k < 13; k++) out[k] = 0.0;
+	out[0] = m.count;
+	V2 n = swapped ? vneg(m.n) : m.n;
+	out[1] = n.x; out[2] = n.y;
+	for(int k = 0; k < m.count; k++){
+		V2 p1 = m.p1[k], p2 = m.p2[k];
+		V2 A_ = swapped ? p2 : p1, B_ = swapped ? p1 : p2;
+		out[3 + 5*k + 0] = A_.x; out[3 + 5*k + 1] = A_.y; out[3 + 5*k + 2] = B_.x; out[3 + 5*k + 3] = B_.y;
+		out[3 + 5*k + 4] = vdot(vsub(p2, p1), n);
+	}
+}

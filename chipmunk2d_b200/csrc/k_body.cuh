@@ -1,0 +1,92 @@
+// k_body.cuh -- K1 (integrate position + transform), K2 (shape world cache + AABB),
+// K9 (integrate velocity).  One thread per body / per shape; SoA fp64; -fmad=false.
+#pragma once
+#include "cpb_world.h"
+
+// K1: cpBodyUpdatePosition + SetTransform (cpBody.c:511-522, 347-357) for every body of the
+// reference's dynamicBodies array: awake dynamic AND kinematic bodies (cpSpace.c:447).
+__global__ void k_integrate_pos(DBodies B, double dt)
+{
+	int i = CPB_TID;
+	if(i >= B.n) return;
+	if(B.type[i] == CPB200_BODY_STATIC || B.sleeping[i]) return;
+	double4 V = B.V[i], VB = B.VB[i];
+	V2 p = vadd(B.pos[i], vmul(vadd(v2(V.x, V.y), v2(VB.x, VB.y)), dt));
+	double a = B.ang[i] + (V.z + VB.z)*dt;
+	double s, c;
+	sincos(a, &s, &c);
+	V2 rot = v2(c, s);
+	V2 cg = B.cog[i];
+	B.pos[i] = p;
+	B.ang[i] = a;
+	B.rot[i] = rot;
+	B.txy[i] = v2(p.x - (cg.x*rot.x - cg.y*rot.y), p.y - (cg.x*rot.y + cg.y*rot.x));
+	B.VB[i] = make_double4(0.0, 0.0, 0.0, 0.0);
+}
+
+// Translation part of SetTransform for bodies whose rotation came from the host
+// (initial upload: the host's libm cos/sin are kept so static geometry is bit-identical).
+__global__ void k_body_transform(DBodies B, int first, int n)
+{
+	int i = first + CPB_TID;
+	if(i >= first + n || i >= B.n) return;
+	V2 p = B.pos[i], rot = B.rot[i], cg = B.cog[i];
+	B.txy[i] = v2(p.x - (cg.x*rot.x - cg.y*rot.y), p.y - (cg.x*rot.y + cg.y*rot.x));
+}
+
+// K2: cpShapeUpdateFunc -> cacheData (cpSpaceStep.c:329-333; cpShape.c:291-296, 378-405;
+// cpPolyShape.c:39-64).  all != 0 recaches every shape (upload); otherwise only shapes in
+// the reference's dynamic index: those on awake, non-static bodies.
+__global__ void k_shape_cache(DShapes S, DBodies B, int all)
+{
+	int s = CPB_TID;
+	if(s >= S.n) return;
+	int b = S.body[s];
+	if(!all && (B.type[b] == CPB200_BODY_STATIC || B.sleeping[b])) return;
+	Xf T; T.rot = B.rot[b]; T.t = B.txy[b];
+	double rad = S.r[s];
+	int type = S.type[s];
+	if(type == CPB200_SHAPE_CIRCLE){
+		V2 c = xf_point(T, S.la[s]);
+		S.wa[s] = c;
+		S.bb[s] = make_double4(c.x - rad, c.y - rad, c.x + rad, c.y + rad);
+	} else if(type == CPB200_SHAPE_SEGMENT){
+		V2 ta = xf_point(T, S.la[s]);
+		V2 tb = xf_point(T, S.lb[s]);
+		S.wa[s] = ta; S.wb[s] = tb; S.wn[s] = xf_vect(T, S.ln[s]);
+		double l, r, bt, t;
+		if(ta.x < tb.x){ l = ta.x; r = tb.x; } else { l = tb.x; r = ta.x; }
+		if(ta.y < tb.y){ bt = ta.y; t = tb.y; } else { bt = tb.y; t = ta.y; }
+		S.bb[s] = make_double4(l - rad, bt - rad, r + rad, t + rad);
+	} else {
+		int off = S.poff[s], cnt = S.pcount[s];
+		double l = INFINITY, r = -INFINITY, bt = INFINITY, t = -INFINITY;
+		for(int k = 0; k < cnt; k++){
+			V2 v = xf_point(T, S.lpv[off + k]);
+			V2 n = xf_vect(T, S.lpn[off + k]);
+			S.wpv[off + k] = v;
+			S.wpn[off + k] = n;
+			l = fmin_cp(l, v.x); r = fmax_cp(r, v.x);
+			bt = fmin_cp(bt, v.y); t = fmax_cp(t, v.y);
+		}
+		S.bb[s] = make_double4(l - rad, bt - rad, r + rad, t + rad);
+	}
+}
+
+// K9: cpBodyUpdateVelocity (cpBody.c:493-509); kinematic bodies are skipped, forces reset.
+__global__ void k_integrate_vel(DBodies B, const DSpace *__restrict__ spaces, double dt)
+{
+	int i = CPB_TID;
+	if(i >= B.n) return;
+	if(B.type[i] != CPB200_BODY_DYNAMIC || B.sleeping[i]) return;
+	DSpace sp = spaces[B.space[i]];
+	double4 V = B.V[i];
+	V2 mi = B.MI[i];
+	V2 f = B.force[i];
+	double damping = sp.damping_dt;
+	V2 v = vadd(vmul(v2(V.x, V.y), damping), vmul(vadd(sp.gravity, vmul(f, mi.x)), dt));
+	double w = V.z*damping + B.torque[i]*mi.y*dt;
+	B.V[i] = make_double4(v.x, v.y, w, 0.0);
+	B.force[i] = v2(0.0, 0.0);
+	B.torque[i] = 0.0;
+}

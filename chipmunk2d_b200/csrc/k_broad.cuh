@@ -1,0 +1,266 @@
+// k_broad.cuh -- K3 + K4: broadphase and pair filter.
+//
+// Replaces cpBBTreeReindexQuery / cpSpaceHashReindexQuery / cpSweep1DReindexQuery
+// (cpBBTree.c:638-654, cpSpaceHash.c:448-457, cpSweep1D.c:211-233) with a linear BVH
+// that is rebuilt from scratch every step:
+//   world bounds -> 32-bit Morton code of each AABB centre (space id in the high key
+//   bits so batched spaces never mix) -> radix sort (prims.cuh) -> Karras radix tree
+//   -> bottom-up AABB refit -> one stack traversal per active leaf.
+// Candidate leaves go straight through the QueryReject rules (cpSpaceStep.c:204-232):
+// closed-interval AABB test (exact: leaf boxes ARE the cached shape->bb), same body,
+// cpShapeFilterReject, no-collide joints.  Membership follows SURVEY.md 8a a6/a7: A ranges
+// over shapes of awake non-static bodies, B over everything; each unordered pair is
+// emitted exactly once, binned by narrowphase class.
+#pragma once
+#include "cpb_world.h"
+#include "prims.cuh"
+
+#define CPB_BVH_STACK 96
+
+CPB_DEVICE bool shape_is_active(const DBodies &B, int body){
+	return B.type[body] != CPB200_BODY_STATIC && !B.sleeping[body];
+}
+
+// ---- world bounds: min/max over every shape AABB ----
+#ifndef CPB_EMU
+__device__ __forceinline__ void atomic_min_double(double *addr, double v){
+	// order-preserving for IEEE doubles through a signed/unsigned split
+	if(v >= 0.0) atomicMin((long long *)addr, __double_as_longlong(v));
+	else atomicMax((unsigned long long *)addr, (unsigned long long)__double_as_longlong(v));
+}
+__device__ __forceinline__ void atomic_max_double(double *addr, double v){
+	if(v >= 0.0) atomicMax((long long *)addr, __double_as_longlong(v));
+	else atomicMin((unsigned long long *)addr, (unsigned long long)__double_as_longlong(v));
+}
+#else
+static inline void atomic_min_double(double *addr, double v){ if(v < *addr) *addr = v; }
+static inline void atomic_max_double(double *addr, double v){ if(v > *addr) *addr = v; }
+#endif
+
+__global__ void k_bounds_init(double *bounds)
+{
+	if(CPB_TID == 0){ bounds[0] = INFINITY; bounds[1] = INFINITY; bounds[2] = -INFINITY; bounds[3] = -INFINITY; }
+}
+
+__global__ void k_bounds(DShapes S, double *bounds)
+{
+	int i = CPB_TID;
+	double l = INFINITY, b = INFINITY, r = -INFINITY, t = -INFINITY;
+	for(int s = i; s < S.n; s += CPB_NTHREADS){
+		double4 bb = S.bb[s];
+		V2 c = v2((bb.x + bb.z)*0.5, (bb.y + bb.w)*0.5);
+		if(c.x == c.x && c.y == c.y && fabs(c.x) != INFINITY && fabs(c.y) != INFINITY){
+			l = fmin(l, c.x); r = fmax(r, c.x); b = fmin(b, c.y); t = fmax(t, c.y);
+		}
+	}
+#ifndef CPB_EMU
+	for(int d = 16; d > 0; d >>= 1){
+		l = fmin(l, __shfl_xor_sync(0xffffffffu, l, d)); b = fmin(b, __shfl_xor_sync(0xffffffffu, b, d));
+		r = fmax(r, __shfl_xor_sync(0xffffffffu, r, d)); t = fmax(t, __shfl_xor_sync(0xffffffffu, t, d));
+	}
+	if((threadIdx.x & 31) != 0) return;
+#endif
+	if(l <= r){
+		atomic_min_double(&bounds[0], l); atomic_min_double(&bounds[1], b);
+		atomic_max_double(&bounds[2], r); atomic_max_double(&bounds[3], t);
+	}
+}
+
+CPB_DEVICE uint32_t spread16(uint32_t x){
+	x &= 0xffffu;
+	x = (x | (x << 8)) & 0x00ff00ffu;
+	x = (x | (x << 4)) & 0x0f0f0f0fu;
+	x = (x | (x << 2)) & 0x33333333u;
+	x = (x | (x << 1)) & 0x55555555u;
+	return x;
+}
+
+__global__ void k_morton(DShapes S, DBodies B, const double *__restrict__ bounds, uint64_t *keys, int *vals)
+{
+	int s = CPB_TID;
+	if(s >= S.n) return;
+	double4 bb = S.bb[s];
+	double cx = (bb.x + bb.z)*0.5, cy = (bb.y + bb.w)*0.5;
+	double w = bounds[2] - bounds[0], h = bounds[3] - bounds[1];
+	double fx = (w > 0.0 ? (cx - bounds[0])/w : 0.0), fy = (h > 0.0 ? (cy - bounds[1])/h : 0.0);
+	fx = fmin(fmax(fx, 0.0), 1.0); fy = fmin(fmax(fy, 0.0), 1.0);
+	if(!(fx == fx)) fx = 0.0;
+	if(!(fy == fy)) fy = 0.0;
+	uint32_t qx = (uint32_t)(fx*65535.0), qy = (uint32_t)(fy*65535.0);
+	uint32_t m = spread16(qx) | (spread16(qy) << 1);
+	keys[s] = ((uint64_t)(uint32_t)B.space[S.body[s]] << 32) | (uint64_t)m;
+	vals[s] = s;
+}
+
+// ---- Karras 2012 radix tree over the sorted keys ----
+CPB_DEVICE int bvh_delta(const uint64_t *__restrict__ keys, int n, int i, int j){
+	if(j < 0 || j >= n) return -1;
+	uint64_t a = keys[i], b = keys[j];
+	if(a == b) return 64 + __clz(i ^ j);
+	return __clzll((long long)(a ^ b));
+}
+
+__global__ void k_bvh_build(DBvh T)
+{
+	int i = CPB_TID;
+	int n = T.n;
+	if(i >= n - 1) return;
+	const uint64_t *keys = T.keys;
+	int d = (bvh_delta(keys, n, i, i + 1) - bvh_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+	int dmin = bvh_delta(keys, n, i, i - d);
+	int lmax = 2;
+	while(bvh_delta(keys, n, i, i + lmax*d) > dmin) lmax *= 2;
+	int l = 0;
+	for(int t = lmax/2; t >= 1; t /= 2){
+		if(bvh_delta(keys, n, i, i + (l + t)*d) > dmin) l += t;
+	}
+	int j = i + l*d;
+	int dnode = bvh_delta(keys, n, i, j);
+	int s = 0;
+	int t = l;
+	do {
+		t = (t + 1)/2;
+		if(bvh_delta(keys, n, i, i + (s + t)*d) > dnode) s += t;
+	} while(t > 1);
+	int gamma = i + s*d + (d < 0 ? d : 0);
+	int lo = (i < j ? i : j), hi = (i < j ? j : i);
+	int left = (lo == gamma ? (n - 1) + gamma : gamma);
+	int right = (hi == gamma + 1 ? (n - 1) + gamma + 1 : gamma + 1);
+	T.left[i] = left; T.right[i] = right;
+	T.parent[left] = i; T.parent[right] = i;
+	if(i == 0) T.parent[0] = -1;
+}
+
+__global__ void k_bvh_leaves(DBvh T, DShapes S, DBodies B)
+{
+	int i = CPB_TID;
+	if(i >= T.n) return;
+	int s = T.leaf_shape[i];
+	T.nbb[(T.n - 1) + i] = S.bb[s];
+	int sp = B.space[S.body[s]];
+	T.nsp[(T.n - 1) + i] = make_int2(sp, sp);
+}
+
+#ifndef CPB_EMU
+__device__ __forceinline__ double4 ld_cg4(const double4 *p){
+	double2 lo = __ldcg((const double2 *)p), hi = __ldcg((const double2 *)p + 1);
+	return make_double4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ int2 ld_cg_i2(const int2 *p){ return __ldcg(p); }
+#else
+static inline double4 ld_cg4(const double4 *p){ return *p; }
+static inline int2 ld_cg_i2(const int2 *p){ return *p; }
+#endif
+
+__global__ void k_bvh_refit(DBvh T)
+{
+	int i = CPB_TID;
+	int n = T.n;
+	if(i >= n || n < 2) return;
+	int cur = T.parent[(n - 1) + i];
+	while(cur >= 0){
+		__threadfence();
+		int old = atomicAdd(&T.flags[cur], 1);
+		if(old == 0) return; // first child to arrive: the sibling's thread finishes this node
+		__threadfence();
+		int l = T.left[cur], r = T.right[cur];
+		// children were written by other threads (possibly other SMs): read through L2
+		double4 a = ld_cg4(&T.nbb[l]);
+		double4 b = ld_cg4(&T.nbb[r]);
+		T.nbb[cur] = make_double4(fmin(a.x, b.x), fmin(a.y, b.y), fmax(a.z, b.z), fmax(a.w, b.w));
+		int2 sa = ld_cg_i2(&T.nsp[l]), sb = ld_cg_i2(&T.nsp[r]);
+		T.nsp[cur] = make_int2(sa.x < sb.x ? sa.x : sb.x, sa.y > sb.y ? sa.y : sb.y);
+		cur = T.parent[cur];
+	}
+}
+
+// ---- K4 rules ----
+CPB_DEVICE bool bb_intersects(double4 a, double4 b){
+	// cpBBIntersects (cpBB.h:58-61): closed intervals
+	return (a.x <= b.z && b.x <= a.z && a.y <= b.w && b.y <= a.w);
+}
+
+CPB_DEVICE bool nocollide_lookup(const uint64_t *__restrict__ keys, int n, int ba, int bb){
+	uint64_t lo = (uint64_t)(uint32_t)(ba < bb ? ba : bb), hi = (uint64_t)(uint32_t)(ba < bb ? bb : ba);
+	uint64_t key = (lo << 32) | hi;
+	int a = 0, b = n - 1;
+	while(a <= b){
+		int m = (a + b) >> 1;
+		uint64_t k = keys[m];
+		if(k == key) return true;
+		if(k < key) a = m + 1; else b = m - 1;
+	}
+	return false;
+}
+
+CPB_DEVICE bool query_reject(const DShapes &S, int sa, int sb, const uint64_t *nocollide, int n_nocollide){
+	int ba = S.body[sa], bb = S.body[sb];
+	if(ba == bb) return true;
+	// cpShapeFilterReject (chipmunk_private.h:144-155)
+	uint64_t ga = S.group[sa], gb = S.group[sb];
+	if(ga != 0 && ga == gb) return true;
+	if((S.cat[sa] & S.mask[sb]) == 0 || (S.cat[sb] & S.mask[sa]) == 0) return true;
+	// QueryRejectConstraint (cpSpaceStep.c:204-217)
+	if(n_nocollide > 0 && nocollide_lookup(nocollide, n_nocollide, ba, bb)) return true;
+	return false;
+}
+
+CPB_DEVICE void emit_pair(const DShapes &S, const DPairs &P, int *overflow, int sa, int sb){
+	int ta = S.type[sa], tb = S.type[sb];
+	// cpCollide orders by shape type (cpCollision.c:706-710); equal types: lower index first
+	if(ta > tb || (ta == tb && sa > sb)){ int t = sa; sa = sb; sb = t; t = ta; ta = tb; tb = t; }
+	int cls = (tb == 0 ? 0 : (ta == 0 && tb == 1 ? 1 : 2));
+	// warp-ballot compaction: one atomic per class per converged warp
+	int slot = -1;
+	for(int c = 0; c < 3; c++){
+		int sl = cpb_warp_append(&P.count[c], cls == c);
+		if(cls == c) slot = sl;
+	}
+	if(slot < P.cap){ P.a[cls][slot] = sa; P.b[cls][slot] = sb; }
+	else atomicOr((unsigned *)overflow, 1u);
+}
+
+// One thread per leaf in Morton order (neighbouring threads walk neighbouring paths).
+__global__ void k_bvh_pairs(DBvh T, DShapes S, DBodies B, DPairs P, const uint64_t *__restrict__ nocollide, int n_nocollide, int multi_space, int *overflow)
+{
+	int i = CPB_TID;
+	int n = T.n;
+	if(i >= n) return;
+	int si = T.leaf_shape[i];
+	int bi = S.body[si];
+	if(!shape_is_active(B, bi)) return;
+	double4 q = S.bb[si];
+	int qsp = B.space[bi];
+	if(n < 2) return;
+	int stack[CPB_BVH_STACK];
+	int sp = 0;
+	int node = 0;
+	for(;;){
+		int child[2] = {T.left[node], T.right[node]};
+		int next = -1;
+#pragma unroll
+		for(int c = 0; c < 2; c++){
+			int ch = child[c];
+			double4 cb = T.nbb[ch];
+			bool hit = bb_intersects(q, cb);
+			if(hit && multi_space){ int2 r = T.nsp[ch]; hit = (r.x <= qsp && qsp <= r.y); }
+			if(!hit) continue;
+			if(ch >= n - 1){
+				int j = ch - (n - 1);
+				if(j == i) continue;
+				int sj = T.leaf_shape[j];
+				// both active: the lower Morton position reports the pair
+				if(j < i && shape_is_active(B, S.body[sj])) continue;
+				if(query_reject(S, si, sj, nocollide, n_nocollide)) continue;
+				emit_pair(S, P, overflow, si, sj);
+			} else {
+				if(next < 0) next = ch;
+				else if(sp < CPB_BVH_STACK) stack[sp++] = ch;
+				else atomicOr((unsigned *)overflow, 8u);
+			}
+		}
+		if(next >= 0){ node = next; continue; }
+		if(sp == 0) break;
+		node = stack[--sp];
+	}
+}

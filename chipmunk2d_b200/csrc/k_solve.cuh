@@ -1,0 +1,330 @@
+// k_solve.cuh -- K10 (graph colouring) + K11 (warm start + Gauss-Seidel iterations).
+//
+// The reference walks space->arbiters then space->constraints sequentially, `iterations` times
+// (cpSpaceStep.c:406-427), every constraint reading and writing the velocities of its two
+// bodies in place.  Here the constraint graph (nodes = bodies with finite mass, edges = active
+// arbiters and joints) is edge-coloured every step so that constraints of one colour touch
+// disjoint dynamic bodies; a colour is then solved by independent threads and colours are
+// separated by grid-wide barriers inside ONE persistent cooperative kernel.
+//
+// Colouring: Jones-Plassmann rounds.  Every uncoloured constraint bids for its dynamic bodies
+// with atomicMax(round | hash(stable key)); a constraint that holds both bodies takes the lowest
+// colour free in both bodies' 64-bit colour masks.  Priorities depend only on the shape-pair key
+// / joint index, so the colouring (and therefore the solve) is deterministic run to run.
+// Static and kinematic bodies (m_inv = i_inv = 0) are never written and impose no conflict
+// (SURVEY.md hard part 8).  Colour 63 is an overflow bucket solved by a single thread.
+//
+// Serial mode (validation): one thread replays the reference's exact sequential order.
+#pragma once
+#include "cpb_world.h"
+#include "k_joint.cuh"
+
+#define CPB_OVERFLOW_COLOUR (CPB_MAX_COLOURS - 1)
+#define CPB_MAX_COLOUR_ROUNDS 200
+
+struct DColour {
+	unsigned long long *claim;   // [n_bodies]
+	unsigned long long *bmask;   // [n_bodies]
+	int *ccount, *cstart, *ccursor;   // [CPB_MAX_COLOURS + 1] arbiters per colour
+	int *jcount, *jstart, *jcursor;   // [CPB_MAX_COLOURS + 1] joints per colour
+	int *remaining;              // [CPB_MAX_COLOUR_ROUNDS + 1]
+};
+
+CPB_DEVICE bool body_is_dynamic(const DBodies &B, int b){ V2 mi = B.MI[b]; return mi.x != 0.0 || mi.y != 0.0; }
+
+// unified constraint index c: [0, nA) arbiter records, [nA, nA + nJ) joints
+CPB_DEVICE bool cons_fetch(const DArbs &A, const DJoints &J, int nA, int c, int &a, int &b, uint64_t &pri, int &col){
+	if(c < nA){
+		if(A.active[c] != 1) return false;
+		a = A.ba[c]; b = A.bb[c]; col = A.colour[c];
+		pri = mix64(A.key[c]) >> 8;
+	} else {
+		int j = c - nA;
+		col = J.colour[j];
+		if(col == -2) return false;
+		a = J.a[j]; b = J.b[j];
+		pri = mix64(0x9e3779b97f4a7c15ull ^ (uint64_t)j) >> 8;
+	}
+	return true;
+}
+
+CPB_DEVICE void colour_phase_a(const DBodies &B, const DArbs &A, const DJoints &J, const DColour &K, int nA, int round, int tid, int nth){
+	int total = nA + J.n;
+	for(int c = tid; c < total; c += nth){
+		int a, b, col; uint64_t pri;
+		if(!cons_fetch(A, J, nA, c, a, b, pri, col) || col >= 0) continue;
+		unsigned long long bid = ((unsigned long long)(round + 1) << 56) | pri;
+		if(body_is_dynamic(B, a)) atomicMax(&K.claim[a], bid);
+		if(body_is_dynamic(B, b)) atomicMax(&K.claim[b], bid);
+	}
+}
+
+CPB_DEVICE void colour_phase_b(const DBodies &B, const DArbs &A, const DJoints &J, const DColour &K, DCounters *C, int nA, int round, int tid, int nth){
+	int total = nA + J.n;
+	int lost = 0;
+	for(int c = tid; c < total; c += nth){
+		int a, b, col; uint64_t pri;
+		if(!cons_fetch(A, J, nA, c, a, b, pri, col) || col >= 0) continue;
+		unsigned long long bid = ((unsigned long long)(round + 1) << 56) | pri;
+		bool da = body_is_dynamic(B, a), db = body_is_dynamic(B, b);
+		bool win = (!da || K.claim[a] == bid) && (!db || K.claim[b] == bid);
+		if(!win){ lost++; continue; }
+		unsigned long long m = (da ? K.bmask[a] : 0ull) | (db ? K.bmask[b] : 0ull);
+		unsigned long long freebits = ~m & ((1ull << CPB_OVERFLOW_COLOUR) - 1ull);
+		int colour = (freebits ? __ffsll((long long)freebits) - 1 : CPB_OVERFLOW_COLOUR);
+		if(colour != CPB_OVERFLOW_COLOUR){
+			unsigned long long bit = 1ull << colour;
+			if(da) K.bmask[a] |= bit;
+			if(db) K.bmask[b] |= bit;
+		}
+		if(c < nA){ A.colour[c] = colour; atomicAdd(&K.ccount[colour], 1); }
+		else { J.colour[c - nA] = colour; atomicAdd(&K.jcount[colour], 1); }
+		atomicMax(&C->n_colours, colour + 1);
+	}
+	if(lost) atomicAdd(&K.remaining[round], lost);
+}
+
+// exclusive prefix of the per-colour counts (single thread; 64 entries)
+CPB_DEVICE void colour_starts(const DColour &K){
+	int ra = 0, rj = 0;
+	for(int c = 0; c <= CPB_MAX_COLOURS; c++){
+		int na = (c < CPB_MAX_COLOURS ? K.ccount[c] : 0), nj = (c < CPB_MAX_COLOURS ? K.jcount[c] : 0);
+		K.cstart[c] = ra; K.jstart[c] = rj;
+		K.ccursor[c] = 0; K.jcursor[c] = 0;
+		ra += na; rj += nj;
+	}
+}
+
+// scatter arbiter records into colour-sorted SoA rows (the solver's coalesced working set)
+CPB_DEVICE void build_rows(const DArbs &A, const DJoints &J, const DRows &R, const DColour &K, int nA, int tid, int nth){
+	for(int i = tid; i < nA; i += nth){
+		if(A.active[i] != 1) continue;
+		int col = A.colour[i];
+		if(col < 0) continue;
+		int r = K.cstart[col] + atomicAdd(&K.ccursor[col], 1);
+		if(r >= R.cap) continue;
+		R.arb[r] = i; R.ba[r] = A.ba[i]; R.bb[r] = A.bb[i];
+		int cnt = A.cnt[i];
+		// first-collision arbiters skip the warm start (cpArbiter.c:444): flag in the sign of cnt
+		R.cnt[r] = (A.state[i] == CPB200_ARB_FIRST_COLLISION ? -cnt : cnt);
+		R.n[r] = A.n[i]; R.svr[r] = A.svr[i]; R.u[r] = A.u[i];
+		for(int k = 0; k < cnt; k++){
+			int s = 2*i + k, d = k*R.cap + r;
+			R.r1[d] = A.r1[s]; R.r2[d] = A.r2[s];
+			R.nmass[d] = A.nmass[s]; R.tmass[d] = A.tmass[s]; R.bounce[d] = A.bounce[s]; R.bias[d] = A.bias[s];
+			R.jn[d] = A.jn[s]; R.jt[d] = A.jt[s]; R.jb[d] = A.jb[s];
+		}
+	}
+	for(int j = tid; j < J.n; j += nth){
+		int col = J.colour[j];
+		if(col < 0) continue;
+		J.row[K.jstart[col] + atomicAdd(&K.jcursor[col], 1)] = j;
+	}
+}
+
+// ---- contact math shared by the coloured and the serial solver ----
+// cpArbiterApplyCachedImpulse for one contact (cpArbiter.c:441-455)
+CPB_DEVICE void contact_apply_cached(double4 &Va, double4 &Vb, V2 mia, V2 mib, V2 n, V2 r1, V2 r2, double jn, double jt, double dt_coef){
+	V2 j = vrotate(n, v2(jn, jt));
+	apply_impulses(Va, Vb, mia, mib, r1, r2, vmul(j, dt_coef));
+}
+
+// cpArbiterApplyImpulse for one contact (cpArbiter.c:459-498)
+CPB_DEVICE void contact_apply(double4 &Va, double4 &Vb, double4 &VBa, double4 &VBb, V2 mia, V2 mib,
+	V2 n, V2 surface_vr, double friction, V2 r1, V2 r2, double nMass, double tMass, double bias, double bounce,
+	double &jnAcc, double &jtAcc, double &jBias)
+{
+	V2 vb1 = vadd(v2(VBa.x, VBa.y), vmul(vperp(r1), VBa.z));
+	V2 vb2 = vadd(v2(VBb.x, VBb.y), vmul(vperp(r2), VBb.z));
+	V2 vr = vadd(relative_velocity(Va, Vb, r1, r2), surface_vr);
+
+	double vbn = vdot(vsub(vb2, vb1), n);
+	double vrn = vdot(vr, n);
+	double vrt = vdot(vr, vperp(n));
+
+	double jbn = (bias - vbn)*nMass;
+	double jbnOld = jBias;
+	jBias = fmax_cp(jbnOld + jbn, 0.0);
+
+	double jn = -(bounce + vrn)*nMass;
+	double jnOld = jnAcc;
+	jnAcc = fmax_cp(jnOld + jn, 0.0);
+
+	double jtMax = friction*jnAcc;
+	double jt = -vrt*tMass;
+	double jtOld = jtAcc;
+	jtAcc = fclamp_cp(jtOld + jt, -jtMax, jtMax);
+
+	apply_impulses(VBa, VBb, mia, mib, r1, r2, vmul(n, jBias - jbnOld));
+	apply_impulses(Va, Vb, mia, mib, r1, r2, vrotate(n, v2(jnAcc - jnOld, jtAcc - jtOld)));
+}
+
+// one colour-sorted row: mode 0 = warm start, 1 = iteration
+CPB_DEVICE void solve_row(const DBodies &B, const DRows &R, int r, int mode, double dt_coef){
+	int ba = R.ba[r], bb = R.bb[r];
+	int cnt = R.cnt[r];
+	bool first = (cnt < 0);
+	if(first) cnt = -cnt;
+	if(mode == 0 && first) return;
+	V2 mia = B.MI[ba], mib = B.MI[bb];
+	double4 Va = B.V[ba], Vb = B.V[bb];
+	V2 n = R.n[r];
+	bool dyn_a = (mia.x != 0.0 || mia.y != 0.0), dyn_b = (mib.x != 0.0 || mib.y != 0.0);
+	if(mode == 0){
+		for(int k = 0; k < cnt; k++){
+			int d = k*R.cap + r;
+			contact_apply_cached(Va, Vb, mia, mib, n, R.r1[d], R.r2[d], R.jn[d], R.jt[d], dt_coef);
+		}
+		if(dyn_a) B.V[ba] = Va;
+		if(dyn_b) B.V[bb] = Vb;
+		return;
+	}
+	double4 VBa = B.VB[ba], VBb = B.VB[bb];
+	V2 svr = R.svr[r];
+	double u = R.u[r];
+	for(int k = 0; k < cnt; k++){
+		int d = k*R.cap + r;
+		double jn = R.jn[d], jt = R.jt[d], jb = R.jb[d];
+		contact_apply(Va, Vb, VBa, VBb, mia, mib, n, svr, u, R.r1[d], R.r2[d], R.nmass[d], R.tmass[d], R.bias[d], R.bounce[d], jn, jt, jb);
+		R.jn[d] = jn; R.jt[d] = jt; R.jb[d] = jb;
+	}
+	if(dyn_a){ B.V[ba] = Va; B.VB[ba] = VBa; }
+	if(dyn_b){ B.V[bb] = Vb; B.VB[bb] = VBb; }
+}
+
+CPB_DEVICE void solve_joint(const DBodies &B, const DJoints &J, int j, int mode, double dt, double dt_coef){
+	int a = J.a[j], b = J.b[j];
+	V2 mia = B.MI[a], mib = B.MI[b];
+	double4 Va = B.V[a], Vb = B.V[b];
+	if(mode == 0) joint_apply_cached(J, j, Va, Vb, mia, mib, dt_coef);
+	else joint_apply(J, j, Va, Vb, mia, mib, dt);
+	if(mia.x != 0.0 || mia.y != 0.0) B.V[a] = Va;
+	if(mib.x != 0.0 || mib.y != 0.0) B.V[b] = Vb;
+}
+
+// all rows + joints of one colour
+CPB_DEVICE void solve_colour(const DBodies &B, const DRows &R, const DJoints &J, const DColour &K, int colour, int mode, double dt, double dt_coef, int tid, int nth){
+	int r0 = K.cstart[colour], r1 = K.cstart[colour + 1];
+	for(int r = r0 + tid; r < r1; r += nth) solve_row(B, R, r, mode, dt_coef);
+	int j0 = K.jstart[colour], j1 = K.jstart[colour + 1];
+	for(int q = j0 + tid; q < j1; q += nth) solve_joint(B, J, J.row[q], mode, dt, dt_coef);
+}
+
+// overflow bucket: sequential, one thread
+CPB_DEVICE void solve_overflow(const DBodies &B, const DRows &R, const DJoints &J, const DColour &K, int mode, double dt, double dt_coef){
+	int r0 = K.cstart[CPB_OVERFLOW_COLOUR], r1 = K.cstart[CPB_OVERFLOW_COLOUR + 1];
+	for(int r = r0; r < r1; r++) solve_row(B, R, r, mode, dt_coef);
+	int j0 = K.jstart[CPB_OVERFLOW_COLOUR], j1 = K.jstart[CPB_OVERFLOW_COLOUR + 1];
+	for(int q = j0; q < j1; q++) solve_joint(B, J, J.row[q], mode, dt, dt_coef);
+}
+
+// copy the accumulated impulses back into the persistent arbiter records
+CPB_DEVICE void rows_writeback(const DArbs &A, const DRows &R, int n_rows, int tid, int nth){
+	for(int r = tid; r < n_rows; r += nth){
+		int i = R.arb[r];
+		int cnt = R.cnt[r]; if(cnt < 0) cnt = -cnt;
+		for(int k = 0; k < cnt; k++){
+			int s = 2*i + k, d = k*R.cap + r;
+			A.jn[s] = R.jn[d]; A.jt[s] = R.jt[d]; A.jb[s] = R.jb[d];
+		}
+	}
+}
+
+#ifndef CPB_EMU
+namespace cg = cooperative_groups;
+
+// K10 + K11 in one persistent launch.
+__global__ void __launch_bounds__(256) k_colour_solve(DBodies B, DArbs A, DJoints J, DRows R, DColour K, DCounters *C, int iterations, double dt, double dt_coef)
+{
+	cg::grid_group grid = cg::this_grid();
+	const int tid = CPB_TID, nth = CPB_NTHREADS;
+	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
+
+	// K10: colouring rounds
+	for(int round = 0; round < CPB_MAX_COLOUR_ROUNDS; round++){
+		colour_phase_a(B, A, J, K, nA, round, tid, nth);
+		grid.sync();
+		colour_phase_b(B, A, J, K, C, nA, round, tid, nth);
+		grid.sync();
+		if(*((volatile int *)&K.remaining[round]) == 0) break;
+	}
+	if(tid == 0) colour_starts(K);
+	grid.sync();
+	build_rows(A, J, R, K, nA, tid, nth);
+	grid.sync();
+
+	// K11: warm start then iterations, colour by colour
+	int ncol = *((volatile int *)&C->n_colours);
+	int nreg = (ncol > CPB_OVERFLOW_COLOUR ? CPB_OVERFLOW_COLOUR : ncol);
+	bool has_overflow = (ncol > CPB_OVERFLOW_COLOUR);
+	for(int pass = 0; pass <= iterations; pass++){
+		int mode = (pass == 0 ? 0 : 1);
+		for(int c = 0; c < nreg; c++){
+			solve_colour(B, R, J, K, c, mode, dt, dt_coef, tid, nth);
+			grid.sync();
+		}
+		if(has_overflow){
+			if(tid == 0) solve_overflow(B, R, J, K, mode, dt, dt_coef);
+			grid.sync();
+		}
+	}
+	int n_rows = K.cstart[CPB_MAX_COLOURS];
+	rows_writeback(A, R, n_rows, tid, nth);
+}
+#endif
+
+// kernels used by the emulation build (and available as a multi-launch variant)
+__global__ void k_colour_a(DBodies B, DArbs A, DJoints J, DColour K, int round){
+	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
+	colour_phase_a(B, A, J, K, nA, round, CPB_TID, CPB_NTHREADS);
+}
+__global__ void k_colour_b(DBodies B, DArbs A, DJoints J, DColour K, DCounters *C, int round){
+	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
+	colour_phase_b(B, A, J, K, C, nA, round, CPB_TID, CPB_NTHREADS);
+}
+__global__ void k_colour_finish(DArbs A, DJoints J, DRows R, DColour K, int stage){
+	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
+	if(stage == 0){ if(CPB_TID == 0) colour_starts(K); }
+	else build_rows(A, J, R, K, nA, CPB_TID, CPB_NTHREADS);
+}
+__global__ void k_solve_colour(DBodies B, DRows R, DJoints J, DColour K, int colour, int mode, double dt, double dt_coef){
+	if(colour == CPB_OVERFLOW_COLOUR){ if(CPB_TID == 0) solve_overflow(B, R, J, K, mode, dt, dt_coef); }
+	else solve_colour(B, R, J, K, colour, mode, dt, dt_coef, CPB_TID, CPB_NTHREADS);
+}
+__global__ void k_rows_writeback(DArbs A, DRows R, DColour K){
+	rows_writeback(A, R, K.cstart[CPB_MAX_COLOURS], CPB_TID, CPB_NTHREADS);
+}
+
+// ---- serial validation mode: the reference's exact order (cpSpaceStep.c:406-427) ----
+// order[n_order] lists arbiter record indices; joints follow in upload order.
+__global__ void k_solve_serial(DBodies B, DArbs A, DJoints J, const int *__restrict__ order, int n_order, int iterations, double dt, double dt_coef)
+{
+	if(CPB_TID != 0) return;
+	for(int pass = 0; pass <= iterations; pass++){
+		for(int q = 0; q < n_order; q++){
+			int i = order[q];
+			if(i < 0) continue;
+			bool reversed = (i & 0x40000000) != 0;
+			i &= 0x3fffffff;
+			if(A.active[i] != 1) continue;
+			if(pass == 0 && A.state[i] == CPB200_ARB_FIRST_COLLISION) continue;
+			int ba = A.ba[i], bb = A.bb[i];
+			V2 mia = B.MI[ba], mib = B.MI[bb];
+			double4 Va = B.V[ba], Vb = B.V[bb], VBa = B.VB[ba], VBb = B.VB[bb];
+			V2 n = A.n[i];
+			int cnt = A.cnt[i];
+			for(int kk = 0; kk < cnt; kk++){
+				int k = (reversed ? cnt - 1 - kk : kk);
+				int s = 2*i + k;
+				if(pass == 0) contact_apply_cached(Va, Vb, mia, mib, n, A.r1[s], A.r2[s], A.jn[s], A.jt[s], dt_coef);
+				else contact_apply(Va, Vb, VBa, VBb, mia, mib, n, A.svr[i], A.u[i], A.r1[s], A.r2[s], A.nmass[s], A.tmass[s], A.bias[s], A.bounce[s], A.jn[s], A.jt[s], A.jb[s]);
+			}
+			if(mia.x != 0.0 || mia.y != 0.0){ B.V[ba] = Va; B.VB[ba] = VBa; }
+			if(mib.x != 0.0 || mib.y != 0.0){ B.V[bb] = Vb; B.VB[bb] = VBb; }
+		}
+		for(int j = 0; j < J.n; j++){
+			if(J.colour[j] == -2) continue;
+			solve_joint(B, J, j, (pass == 0 ? 0 : 1), dt, dt_coef);
+		}
+	}
+}

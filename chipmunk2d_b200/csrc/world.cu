@@ -1,0 +1,945 @@
+// world.cu -- the C ABI of include/cpb200.h: device memory management, uploads, the step
+// schedule (one CUDA stream; K1..K11 in the order of cpSpaceStep, cpSpaceStep.c:335-445) and
+// read-back.  See DESIGN.md for the data layout and per-kernel roofline notes.
+#include <stdarg.h>
+#include <vector>
+#include <algorithm>
+
+#include "cpb_rt.h"
+#include "cpb_math.h"
+#include "cpb_world.h"
+#include "prims.cuh"
+#include "k_body.cuh"
+#include "k_broad.cuh"
+#include "k_arb.cuh"
+#include "k_joint.cuh"
+#include "k_solve.cuh"
+#include "k_island.cuh"
+
+#ifdef CPB_EMU
+emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+#endif
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_error[512] = "";
+
+void cpb_set_error(const char *fmt, ...)
+{
+	va_list ap; va_start(ap, fmt);
+	vsnprintf(g_error, sizeof(g_error), fmt, ap);
+	va_end(ap);
+}
+
+extern "C" const char *cpb200_last_error(void){ return g_error; }
+
+extern "C" int cpb200_device_available(void)
+{
+#ifdef CPB_EMU
+	return 1;
+#else
+	int n = 0;
+	if(cudaGetDeviceCount(&n) != cudaSuccess){ cudaGetLastError(); return 0; }
+	return n > 0;
+#endif
+}
+
+// ------------------------------------------------------------------ stages (profiling)
+enum {
+	ST_INTEGRATE_POS, ST_SHAPE_CACHE, ST_BVH_KEYS, ST_BVH_SORT, ST_BVH_BUILD, ST_BVH_PAIRS,
+	ST_COLLIDE, ST_ISLANDS, ST_CARRY, ST_PRESTEP, ST_INTEGRATE_VEL, ST_SOLVE, ST_COUNT
+};
+static const char *g_stage_names[ST_COUNT] = {
+	"integrate_pos", "shape_cache", "bvh_keys", "bvh_sort", "bvh_build", "bvh_pairs",
+	"collide", "islands", "arbiter_carry", "prestep", "integrate_vel", "colour_solve"
+};
+extern "C" const char *cpb200_stage_name(int i){ return (i >= 0 && i < ST_COUNT) ? g_stage_names[i] : ""; }
+
+// ------------------------------------------------------------------ world
+struct AllocGroup {
+	std::vector<void *> ptrs;
+	void release(){ for(void *p : ptrs) cudaFree(p); ptrs.clear(); }
+};
+
+struct cpb200_world {
+	int device;
+	cudaStream_t stream;
+	int n_spaces;
+	int sm_count;
+	int coop_blocks;
+
+	std::vector<cpb200_space_params> sp;
+	DSpace *d_spaces;
+	bool spaces_dirty;
+	double spaces_dt;
+
+	DBodies B; AllocGroup gB;
+	DShapes S; AllocGroup gS;
+	DJoints J; AllocGroup gJ;
+	std::vector<double> joint_error_bias;
+	double joints_dt;
+	uint64_t *d_nocollide; int n_nocollide;
+
+	DArbs A[2]; DTable T[2]; AllocGroup gA;
+	int cur;
+	DRows R;
+	DColour K; AllocGroup gK;
+	DBvh bvh; AllocGroup gV;
+	uint64_t *keys_b; int *vals_b; uint32_t *sort_tmp;
+	DPairs P; AllocGroup gP;
+	DIslands I; AllocGroup gI;
+	DCounters *C;
+	DCounters *hC;          // pinned
+	int cap_pairs, cap_arbs;
+	int user_cap_pairs, user_cap_arbs;
+
+	uint32_t stamp;
+	double curr_dt;
+	uint64_t steps;
+	bool cache_dirty;
+	bool any_sleep_enabled;
+
+	int solver_mode;
+	int *d_order; int order_cap;
+	uint64_t *d_user_order; int n_user_order; int user_order_cap;
+
+	bool profiling;
+	cudaEvent_t ev[ST_COUNT + 1];
+	float stage_us[ST_COUNT];
+
+	double *d_scratch;      // small scratch (collide_one output, stats)
+	double *h_scratch;      // pinned
+};
+
+template <typename T>
+static int dalloc(AllocGroup &g, T *&p, size_t n)
+{
+	void *q = NULL;
+	if(n == 0) n = 1;
+	cudaError_t e = cudaMalloc(&q, sizeof(T)*n);
+	if(e != cudaSuccess){ cpb_set_error("cudaMalloc(%zu bytes) failed: %s", sizeof(T)*n, cudaGetErrorString(e)); p = NULL; return -1; }
+	cudaMemsetAsync(q, 0, sizeof(T)*n, 0);
+	g.ptrs.push_back(q);
+	p = (T *)q;
+	return 0;
+}
+#define DA(g, p, n) do { if(dalloc(g, p, (size_t)(n))) return -1; } while(0)
+
+template <typename T>
+static int upload(cpb200_world *w, T *dst, const std::vector<T> &src)
+{
+	if(src.empty()) return 0;
+	CPB_CHECK(cudaMemcpyAsync(dst, src.data(), sizeof(T)*src.size(), cudaMemcpyHostToDevice, w->stream));
+	CPB_CHECK(cudaStreamSynchronize(w->stream));
+	return 0;
+}
+
+static inline int grid_for(int n, int block){ int g = cpb_div_up(n > 0 ? n : 1, block); return g; }
+
+static int world_sync(cpb200_world *w)
+{
+	CPB_CHECK(cudaStreamSynchronize(w->stream));
+	CPB_CHECK(cudaGetLastError());
+	return 0;
+}
+
+static int alloc_arbs(cpb200_world *w, int cap);
+static int alloc_pairs(cpb200_world *w, int cap);
+
+extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
+{
+	if(n_spaces < 1){ cpb_set_error("n_spaces must be >= 1"); return NULL; }
+#ifndef CPB_EMU
+	int ndev = 0;
+	if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0){
+		cudaGetLastError();
+		cpb_set_error("no CUDA device available: libcpb200 has no CPU fallback");
+		return NULL;
+	}
+	if(device < 0 || device >= ndev){ cpb_set_error("CUDA device %d out of range (%d present)", device, ndev); return NULL; }
+	if(cudaSetDevice(device) != cudaSuccess){ cpb_set_error("cudaSetDevice(%d) failed", device); return NULL; }
+#endif
+	cpb200_world *w = new cpb200_world();
+	w->device = device;
+	w->n_spaces = n_spaces;
+	w->stream = 0;
+	cudaStreamCreate(&w->stream);
+	w->sm_count = 148;
+	w->coop_blocks = 148;
+#ifndef CPB_EMU
+	{
+		cudaDeviceProp prop;
+		if(cudaGetDeviceProperties(&prop, device) == cudaSuccess) w->sm_count = prop.multiProcessorCount;
+		int per_sm = 1;
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colour_solve, 256, 0);
+		if(per_sm < 1) per_sm = 1;
+		if(per_sm > 4) per_sm = 4;
+		w->coop_blocks = w->sm_count*per_sm;
+	}
+#endif
+	cpb200_space_params def;
+	memset(&def, 0, sizeof(def));
+	def.damping = 1.0; def.sleep_time_threshold = INFINITY; def.collision_slop = 0.1;
+	def.collision_bias = pow(1.0 - 0.1, 60.0); def.collision_persistence = 3; def.iterations = 10;
+	w->sp.assign((size_t)n_spaces, def);
+	w->d_spaces = NULL; w->spaces_dirty = true; w->spaces_dt = 0.0;
+	memset(&w->B, 0, sizeof(w->B)); memset(&w->S, 0, sizeof(w->S)); memset(&w->J, 0, sizeof(w->J));
+	memset(w->A, 0, sizeof(w->A)); memset(w->T, 0, sizeof(w->T)); memset(&w->R, 0, sizeof(w->R));
+	memset(&w->K, 0, sizeof(w->K)); memset(&w->bvh, 0, sizeof(w->bvh)); memset(&w->P, 0, sizeof(w->P));
+	memset(&w->I, 0, sizeof(w->I));
+	w->joints_dt = 0.0; w->d_nocollide = NULL; w->n_nocollide = 0;
+	w->cur = 0; w->keys_b = NULL; w->vals_b = NULL; w->sort_tmp = NULL;
+	w->cap_pairs = 0; w->cap_arbs = 0; w->user_cap_pairs = 0; w->user_cap_arbs = 0;
+	w->stamp = 0; w->curr_dt = 0.0; w->steps = 0; w->cache_dirty = true; w->any_sleep_enabled = false;
+	w->solver_mode = 0; w->d_order = NULL; w->order_cap = 0; w->d_user_order = NULL; w->n_user_order = 0; w->user_order_cap = 0;
+	w->profiling = false;
+	for(int i = 0; i <= ST_COUNT; i++) cudaEventCreate(&w->ev[i]);
+	memset(w->stage_us, 0, sizeof(w->stage_us));
+	void *p = NULL;
+	cudaMalloc(&p, sizeof(DSpace)*(size_t)n_spaces); w->d_spaces = (DSpace *)p;
+	cudaMalloc(&p, sizeof(DCounters)); w->C = (DCounters *)p; cudaMemsetAsync(w->C, 0, sizeof(DCounters), w->stream);
+	cudaMallocHost(&p, sizeof(DCounters)); w->hC = (DCounters *)p; memset(w->hC, 0, sizeof(DCounters));
+	cudaMalloc(&p, sizeof(double)*64); w->d_scratch = (double *)p;
+	cudaMallocHost(&p, sizeof(double)*64); w->h_scratch = (double *)p;
+	if(!w->d_spaces || !w->C || !w->hC){ cpb_set_error("device allocation failed"); delete w; return NULL; }
+	return w;
+}
+
+extern "C" void cpb200_world_destroy(cpb200_world *w)
+{
+	if(!w) return;
+	cudaSetDevice(w->device);
+	cudaStreamSynchronize(w->stream);
+	w->gB.release(); w->gS.release(); w->gJ.release(); w->gA.release(); w->gK.release(); w->gV.release(); w->gP.release(); w->gI.release();
+	cudaFree(w->d_spaces); cudaFree(w->C); cudaFreeHost(w->hC); cudaFree(w->d_scratch); cudaFreeHost(w->h_scratch);
+	if(w->d_order) cudaFree(w->d_order);
+	if(w->d_user_order) cudaFree(w->d_user_order);
+	if(w->d_nocollide) cudaFree(w->d_nocollide);
+	for(int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(w->ev[i]);
+	cudaStreamDestroy(w->stream);
+	delete w;
+}
+
+extern "C" int cpb200_world_set_space_params(cpb200_world *w, int space, const cpb200_space_params *p)
+{
+	if(!w || space < 0 || space >= w->n_spaces){ cpb_set_error("bad space index"); return -1; }
+	w->sp[(size_t)space] = *p;
+	w->spaces_dirty = true;
+	return 0;
+}
+
+static int refresh_spaces(cpb200_world *w, double dt)
+{
+	if(!w->spaces_dirty && w->spaces_dt == dt) return 0;
+	std::vector<DSpace> h((size_t)w->n_spaces);
+	w->any_sleep_enabled = false;
+	for(int i = 0; i < w->n_spaces; i++){
+		const cpb200_space_params &p = w->sp[(size_t)i];
+		DSpace &d = h[(size_t)i];
+		d.gravity = v2(p.gravity[0], p.gravity[1]);
+		d.damping_dt = pow(p.damping, dt);                 // cpSpaceStep.c:399
+		d.bias_coef = 1.0 - pow(p.collision_bias, dt);     // cpSpaceStep.c:384
+		d.slop = p.collision_slop;
+		d.idle_speed = p.idle_speed_threshold;
+		d.sleep_threshold = p.sleep_time_threshold;
+		d.persistence = p.collision_persistence;
+		d.iterations = p.iterations;
+		if(p.sleep_time_threshold != INFINITY) w->any_sleep_enabled = true;
+	}
+	CPB_CHECK(cudaMemcpyAsync(w->d_spaces, h.data(), sizeof(DSpace)*h.size(), cudaMemcpyHostToDevice, w->stream));
+	CPB_CHECK(cudaStreamSynchronize(w->stream));
+	w->spaces_dirty = false; w->spaces_dt = dt;
+	return 0;
+}
+
+// ------------------------------------------------------------------ uploads
+static void fill_body(const cpb200_body_desc &d, V2 &pos, double &ang, V2 &rot, V2 &cog, double4 &V, double4 &VB, V2 &MI, V2 &M, V2 &force, double &torque, double &idle, int &type, int &space, int &sleeping, int &sgroup)
+{
+	pos = v2(d.p[0], d.p[1]); ang = d.a; rot = v2(d.rot[0], d.rot[1]); cog = v2(d.cog[0], d.cog[1]);
+	V = make_double4(d.v[0], d.v[1], d.w, 0.0); VB = make_double4(d.v_bias[0], d.v_bias[1], d.w_bias, 0.0);
+	bool dyn = (d.type == CPB200_BODY_DYNAMIC);
+	// m_inv/i_inv exactly as cpBodySetMass/SetMoment compute them (cpBody.c:246-270): 1/m, 0 for infinite
+	MI = v2(dyn ? 1.0/d.m : 0.0, dyn ? 1.0/d.i : 0.0);
+	M = v2(d.m, d.i);
+	force = v2(d.f[0], d.f[1]); torque = d.t; idle = d.idle_time;
+	type = d.type; space = d.space; sleeping = d.sleeping; sgroup = d.sleep_group;
+}
+
+extern "C" int cpb200_world_set_bodies(cpb200_world *w, int n, const cpb200_body_desc *bodies)
+{
+	if(!w || n < 0){ cpb_set_error("bad arguments"); return -1; }
+	cudaSetDevice(w->device);
+	if(world_sync(w)) return -1;
+	w->gB.release();
+	DBodies &B = w->B;
+	B.n = n;
+	DA(w->gB, B.pos, n); DA(w->gB, B.ang, n); DA(w->gB, B.rot, n); DA(w->gB, B.txy, n); DA(w->gB, B.cog, n);
+	DA(w->gB, B.V, n); DA(w->gB, B.VB, n); DA(w->gB, B.MI, n); DA(w->gB, B.M, n); DA(w->gB, B.force, n);
+	DA(w->gB, B.torque, n); DA(w->gB, B.idle, n); DA(w->gB, B.type, n); DA(w->gB, B.space, n);
+	DA(w->gB, B.sleeping, n); DA(w->gB, B.sgroup, n);
+	w->gK.release();
+	DA(w->gK, w->K.claim, n); DA(w->gK, w->K.bmask, n);
+	DA(w->gK, w->K.ccount, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.cstart, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.ccursor, CPB_MAX_COLOURS + 1);
+	DA(w->gK, w->K.jcount, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.jstart, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.jcursor, CPB_MAX_COLOURS + 1);
+	DA(w->gK, w->K.remaining, CPB_MAX_COLOUR_ROUNDS + 1);
+	w->gI.release();
+	DA(w->gI, w->I.parent, n); DA(w->gI, w->I.wake, n); DA(w->gI, w->I.comp_active, n); DA(w->gI, w->I.woken, n);
+	int r = cpb200_world_update_bodies(w, 0, n, bodies);
+	w->cache_dirty = true;
+	return r;
+}
+
+extern "C" int cpb200_world_update_bodies(cpb200_world *w, int first, int n, const cpb200_body_desc *bodies)
+{
+	if(!w || first < 0 || n < 0 || first + n > w->B.n){ cpb_set_error("body range out of bounds"); return -1; }
+	if(n == 0) return 0;
+	cudaSetDevice(w->device);
+	size_t N = (size_t)n;
+	std::vector<V2> pos(N), rot(N), cog(N), MI(N), M(N), force(N);
+	std::vector<double> ang(N), torque(N), idle(N);
+	std::vector<double4> V(N), VB(N);
+	std::vector<int> type(N), space(N), sleeping(N), sgroup(N);
+	for(size_t i = 0; i < N; i++){
+		fill_body(bodies[i], pos[i], ang[i], rot[i], cog[i], V[i], VB[i], MI[i], M[i], force[i], torque[i], idle[i], type[i], space[i], sleeping[i], sgroup[i]);
+		if(space[i] < 0 || space[i] >= w->n_spaces){ cpb_set_error("body %zu: space index %d out of range", i, space[i]); return -1; }
+	}
+	DBodies &B = w->B;
+	if(upload(w, B.pos + first, pos) || upload(w, B.ang + first, ang) || upload(w, B.rot + first, rot) || upload(w, B.cog + first, cog) ||
+	   upload(w, B.V + first, V) || upload(w, B.VB + first, VB) || upload(w, B.MI + first, MI) || upload(w, B.M + first, M) ||
+	   upload(w, B.force + first, force) || upload(w, B.torque + first, torque) || upload(w, B.idle + first, idle) ||
+	   upload(w, B.type + first, type) || upload(w, B.space + first, space) || upload(w, B.sleeping + first, sleeping) || upload(w, B.sgroup + first, sgroup)) return -1;
+	LAUNCH(k_body_transform, grid_for(n, 256), 256, w->stream, B, first, n);
+	w->cache_dirty = true;
+	return world_sync(w);
+}
+
+extern "C" int cpb200_world_reserve(cpb200_world *w, int max_pairs, int max_arbiters)
+{
+	if(!w) return -1;
+	w->user_cap_pairs = max_pairs; w->user_cap_arbs = max_arbiters;
+	return 0;
+}
+
+static int alloc_pairs(cpb200_world *w, int cap)
+{
+	w->gP.release();
+	w->P.cap = cap;
+	DA(w->gP, w->P.count, 4);
+	for(int c = 0; c < 3; c++){ DA(w->gP, w->P.a[c], cap); DA(w->gP, w->P.b[c], cap); }
+	w->cap_pairs = cap;
+	return 0;
+}
+
+static int alloc_arbs(cpb200_world *w, int cap)
+{
+	w->gA.release();
+	uint32_t tcap = 64;
+	while(tcap < (uint32_t)cap*2u) tcap <<= 1;
+	for(int k = 0; k < 2; k++){
+		DArbs &A = w->A[k];
+		A.cap = cap;
+		DA(w->gA, A.count_ptr, 4);
+		DA(w->gA, A.key, cap); DA(w->gA, A.sa, cap); DA(w->gA, A.sb, cap); DA(w->gA, A.ba, cap); DA(w->gA, A.bb, cap);
+		DA(w->gA, A.cnt, cap); DA(w->gA, A.state, cap); DA(w->gA, A.stamp, cap); DA(w->gA, A.active, cap); DA(w->gA, A.seen, cap);
+		DA(w->gA, A.gjkid, cap); DA(w->gA, A.n, cap); DA(w->gA, A.e, cap); DA(w->gA, A.u, cap); DA(w->gA, A.svr, cap);
+		DA(w->gA, A.r1, 2*(size_t)cap); DA(w->gA, A.r2, 2*(size_t)cap);
+		DA(w->gA, A.nmass, 2*(size_t)cap); DA(w->gA, A.tmass, 2*(size_t)cap); DA(w->gA, A.bounce, 2*(size_t)cap); DA(w->gA, A.bias, 2*(size_t)cap);
+		DA(w->gA, A.jn, 2*(size_t)cap); DA(w->gA, A.jt, 2*(size_t)cap); DA(w->gA, A.jb, 2*(size_t)cap); DA(w->gA, A.hash, 2*(size_t)cap);
+		DA(w->gA, A.colour, cap);
+		DTable &T = w->T[k];
+		T.mask = tcap - 1;
+		DA(w->gA, T.keys, tcap); DA(w->gA, T.vals, tcap);
+	}
+	DRows &R = w->R;
+	R.cap = cap;
+	DA(w->gA, R.arb, cap); DA(w->gA, R.ba, cap); DA(w->gA, R.bb, cap); DA(w->gA, R.cnt, cap);
+	DA(w->gA, R.n, cap); DA(w->gA, R.svr, cap); DA(w->gA, R.u, cap);
+	DA(w->gA, R.r1, 2*(size_t)cap); DA(w->gA, R.r2, 2*(size_t)cap);
+	DA(w->gA, R.nmass, 2*(size_t)cap); DA(w->gA, R.tmass, 2*(size_t)cap); DA(w->gA, R.bounce, 2*(size_t)cap); DA(w->gA, R.bias, 2*(size_t)cap);
+	DA(w->gA, R.jn, 2*(size_t)cap); DA(w->gA, R.jt, 2*(size_t)cap); DA(w->gA, R.jb, 2*(size_t)cap);
+	w->cap_arbs = cap;
+	w->cur = 0;
+	return 0;
+}
+
+extern "C" int cpb200_world_set_shapes(cpb200_world *w, int n, const cpb200_shape_desc *shapes, int n_verts, const double *verts_xy)
+{
+	if(!w || n < 0 || n_verts < 0){ cpb_set_error("bad arguments"); return -1; }
+	cudaSetDevice(w->device);
+	if(world_sync(w)) return -1;
+	size_t N = (size_t)n, NV = (size_t)n_verts;
+	std::vector<int> type(N), body(N), sensor(N), pcount(N), poff(N);
+	std::vector<uint32_t> hashid(N), cat(N), mask(N);
+	std::vector<uint64_t> group(N), ctype(N);
+	std::vector<double> e(N), u(N), r(N);
+	std::vector<V2> surfv(N), la(N), lb(N), ln(N), atan_(N), btan_(N), lpv(NV), lpn(NV);
+	for(size_t i = 0; i < N; i++){
+		const cpb200_shape_desc &d = shapes[i];
+		if(d.body < 0 || d.body >= w->B.n){ cpb_set_error("shape %zu: body index %d out of range (upload bodies first)", i, d.body); return -1; }
+		type[i] = d.type; body[i] = d.body; sensor[i] = d.sensor; hashid[i] = d.hashid; cat[i] = d.categories; mask[i] = d.mask;
+		group[i] = d.group; ctype[i] = d.collision_type; e[i] = d.e; u[i] = d.u; r[i] = d.r;
+		surfv[i] = v2(d.surface_v[0], d.surface_v[1]);
+		la[i] = v2(d.a[0], d.a[1]); lb[i] = v2(d.b[0], d.b[1]);
+		atan_[i] = v2(d.a_tangent[0], d.a_tangent[1]); btan_[i] = v2(d.b_tangent[0], d.b_tangent[1]);
+		ln[i] = v2(0, 0); pcount[i] = 0; poff[i] = 0;
+		if(d.type == CPB200_SHAPE_SEGMENT){
+			// cpSegmentShapeInit: n = cpvrperp(cpvnormalize(cpvsub(b, a))) (cpShape.c:498)
+			ln[i] = vrperp(vnormalize(vsub(lb[i], la[i])));
+		} else if(d.type == CPB200_SHAPE_POLY){
+			if(d.n_verts < 1 || d.vert_offset < 0 || d.vert_offset + d.n_verts > n_verts){ cpb_set_error("shape %zu: vertex range out of bounds", i); return -1; }
+			if(d.n_verts > 255){ cpb_set_error("shape %zu: polygons are limited to 255 vertices (GJK vertex ids are 8 bit, cpCollision.c:129-134)", i); return -1; }
+			pcount[i] = d.n_verts; poff[i] = d.vert_offset;
+			// SetVerts (cpPolyShape.c:147-165): plane i holds vertex i and the normal of edge (i-1 -> i)
+			for(int k = 0; k < d.n_verts; k++){
+				const double *va = verts_xy + 2*(size_t)(d.vert_offset + (k - 1 + d.n_verts)%d.n_verts);
+				const double *vb = verts_xy + 2*(size_t)(d.vert_offset + k);
+				V2 a = v2(va[0], va[1]), b = v2(vb[0], vb[1]);
+				lpv[(size_t)d.vert_offset + k] = b;
+				lpn[(size_t)d.vert_offset + k] = vnormalize(vrperp(vsub(b, a)));
+			}
+		}
+	}
+	w->gS.release();
+	DShapes &S = w->S;
+	S.n = n; S.nv = n_verts;
+	DA(w->gS, S.type, n); DA(w->gS, S.body, n); DA(w->gS, S.hashid, n); DA(w->gS, S.sensor, n); DA(w->gS, S.cat, n); DA(w->gS, S.mask, n);
+	DA(w->gS, S.group, n); DA(w->gS, S.ctype, n); DA(w->gS, S.e, n); DA(w->gS, S.u, n); DA(w->gS, S.r, n); DA(w->gS, S.surfv, n);
+	DA(w->gS, S.la, n); DA(w->gS, S.lb, n); DA(w->gS, S.ln, n); DA(w->gS, S.atan, n); DA(w->gS, S.btan, n);
+	DA(w->gS, S.pcount, n); DA(w->gS, S.poff, n); DA(w->gS, S.lpv, n_verts); DA(w->gS, S.lpn, n_verts);
+	DA(w->gS, S.wa, n); DA(w->gS, S.wb, n); DA(w->gS, S.wn, n); DA(w->gS, S.wpv, n_verts); DA(w->gS, S.wpn, n_verts); DA(w->gS, S.bb, n);
+	if(upload(w, S.type, type) || upload(w, S.body, body) || upload(w, S.hashid, hashid) || upload(w, S.sensor, sensor) || upload(w, S.cat, cat) ||
+	   upload(w, S.mask, mask) || upload(w, S.group, group) || upload(w, S.ctype, ctype) || upload(w, S.e, e) || upload(w, S.u, u) || upload(w, S.r, r) ||
+	   upload(w, S.surfv, surfv) || upload(w, S.la, la) || upload(w, S.lb, lb) || upload(w, S.ln, ln) || upload(w, S.atan, atan_) || upload(w, S.btan, btan_) ||
+	   upload(w, S.pcount, pcount) || upload(w, S.poff, poff) || upload(w, S.lpv, lpv) || upload(w, S.lpn, lpn)) return -1;
+
+	// broadphase scratch
+	w->gV.release();
+	DBvh &T = w->bvh;
+	T.n = n;
+	int nn = (n > 0 ? n : 1);
+	DA(w->gV, T.keys, nn); DA(w->gV, T.leaf_shape, nn); DA(w->gV, T.left, nn); DA(w->gV, T.right, nn); DA(w->gV, T.parent, 2*nn);
+	DA(w->gV, T.nbb, 2*nn); DA(w->gV, T.nsp, 2*nn); DA(w->gV, T.flags, nn); DA(w->gV, T.bounds, 4);
+	DA(w->gV, w->keys_b, nn); DA(w->gV, w->vals_b, nn);
+	DA(w->gV, w->sort_tmp, cpb_sort_tmp_elems(nn) + 16);
+
+	int want_pairs = std::max(w->user_cap_pairs, 16*n + 1024);
+	int want_arbs = std::max(w->user_cap_arbs, 8*n + 1024);
+	if(want_pairs > w->cap_pairs){ if(alloc_pairs(w, want_pairs)) return -1; }
+	if(want_arbs > w->cap_arbs){
+		// growing drops the cached arbiters (warm-start data); callers that care reserve up front
+		if(alloc_arbs(w, want_arbs)) return -1;
+	}
+	w->cache_dirty = true;
+	return world_sync(w);
+}
+
+extern "C" int cpb200_world_set_joints(cpb200_world *w, int n, const cpb200_joint_desc *joints)
+{
+	if(!w || n < 0){ cpb_set_error("bad arguments"); return -1; }
+	cudaSetDevice(w->device);
+	if(world_sync(w)) return -1;
+	size_t N = (size_t)n;
+	std::vector<int> type(N), a(N), b(N);
+	std::vector<double> max_force(N), max_bias(N), aux0(N, 0.0);
+	std::vector<V2> anchor_a(N), anchor_b(N), acc(N);
+	std::vector<double4> prm(N);
+	std::vector<uint64_t> nocollide;
+	w->joint_error_bias.resize(N);
+	for(size_t i = 0; i < N; i++){
+		const cpb200_joint_desc &d = joints[i];
+		if(d.a < 0 || d.a >= w->B.n || d.b < 0 || d.b >= w->B.n){ cpb_set_error("joint %zu: body index out of range", i); return -1; }
+		type[i] = d.type; a[i] = d.a; b[i] = d.b;
+		max_force[i] = d.max_force; max_bias[i] = d.max_bias; w->joint_error_bias[i] = d.error_bias;
+		anchor_a[i] = v2(d.anchor_a[0], d.anchor_a[1]); anchor_b[i] = v2(d.anchor_b[0], d.anchor_b[1]);
+		prm[i] = make_double4(d.prm[0], d.prm[1], d.prm[2], d.prm[3]);
+		acc[i] = v2(d.acc[0], d.acc[1]);
+		if(d.type == CPB200_JOINT_RATCHET) aux0[i] = d.prm[0];
+		if(d.type == CPB200_JOINT_GROOVE){
+			// cpGrooveJointInit: grv_n = cpvperp(cpvnormalize(cpvsub(groove_b, groove_a))) (cpGrooveJoint.c:128)
+			V2 gn = vperp(vnormalize(vsub(v2(d.prm[0], d.prm[1]), anchor_a[i])));
+			prm[i].z = gn.x; prm[i].w = gn.y;
+		}
+		if(!d.collide_bodies){
+			uint64_t lo = (uint64_t)(uint32_t)std::min(d.a, d.b), hi = (uint64_t)(uint32_t)std::max(d.a, d.b);
+			nocollide.push_back((lo << 32) | hi);
+		}
+	}
+	std::sort(nocollide.begin(), nocollide.end());
+	nocollide.erase(std::unique(nocollide.begin(), nocollide.end()), nocollide.end());
+	w->gJ.release();
+	DJoints &J = w->J;
+	J.n = n;
+	DA(w->gJ, J.type, n); DA(w->gJ, J.a, n); DA(w->gJ, J.b, n); DA(w->gJ, J.max_force, n); DA(w->gJ, J.max_bias, n); DA(w->gJ, J.bias_coef, n);
+	DA(w->gJ, J.anchor_a, n); DA(w->gJ, J.anchor_b, n); DA(w->gJ, J.prm, n);
+	DA(w->gJ, J.r1, n); DA(w->gJ, J.r2, n); DA(w->gJ, J.nrm, n); DA(w->gJ, J.nmass, n); DA(w->gJ, J.k, n); DA(w->gJ, J.bias, n); DA(w->gJ, J.acc, n);
+	DA(w->gJ, J.aux0, n); DA(w->gJ, J.aux1, n); DA(w->gJ, J.jspring, n); DA(w->gJ, J.colour, n); DA(w->gJ, J.row, n);
+	if(upload(w, J.type, type) || upload(w, J.a, a) || upload(w, J.b, b) || upload(w, J.max_force, max_force) || upload(w, J.max_bias, max_bias) ||
+	   upload(w, J.anchor_a, anchor_a) || upload(w, J.anchor_b, anchor_b) || upload(w, J.prm, prm) || upload(w, J.acc, acc) || upload(w, J.aux0, aux0)) return -1;
+	if(w->d_nocollide){ cudaFree(w->d_nocollide); w->d_nocollide = NULL; }
+	w->n_nocollide = (int)nocollide.size();
+	if(w->n_nocollide){
+		void *p = NULL;
+		CPB_CHECK(cudaMalloc(&p, sizeof(uint64_t)*nocollide.size()));
+		w->d_nocollide = (uint64_t *)p;
+		CPB_CHECK(cudaMemcpyAsync(w->d_nocollide, nocollide.data(), sizeof(uint64_t)*nocollide.size(), cudaMemcpyHostToDevice, w->stream));
+	}
+	w->joints_dt = 0.0; // force bias_coef refresh
+	return world_sync(w);
+}
+
+static int refresh_joint_bias(cpb200_world *w, double dt)
+{
+	if(w->J.n == 0 || w->joints_dt == dt) return 0;
+	std::vector<double> bc(w->joint_error_bias.size());
+	double last_eb = NAN, last = 0.0;
+	for(size_t i = 0; i < bc.size(); i++){
+		double eb = w->joint_error_bias[i];
+		if(!(eb == last_eb)){ last_eb = eb; last = 1.0 - pow(eb, dt); } // bias_coef (chipmunk_private.h:264-268)
+		bc[i] = last;
+	}
+	if(upload(w, w->J.bias_coef, bc)) return -1;
+	w->joints_dt = dt;
+	return 0;
+}
+
+// ------------------------------------------------------------------ the step
+#define STAGE_BEGIN(w) do { if((w)->profiling) cudaEventRecord((w)->ev[0], (w)->stream); } while(0)
+#define STAGE_END(w, id) do { if((w)->profiling){ cudaEventRecord((w)->ev[(id) + 1], (w)->stream); } } while(0)
+
+__global__ void k_reset_step(DCounters *C, int *pair_count, int *cur_count)
+{
+	if(CPB_TID != 0) return;
+	C->n_pairs[0] = C->n_pairs[1] = C->n_pairs[2] = 0;
+	C->n_contacts = 0; C->n_active = 0; C->n_colours = 0; C->n_cached = 0;
+	C->colour_remaining[0] = C->colour_remaining[1] = 0; C->colour_rounds = 0; C->n_overflow_colour = 0;
+	pair_count[0] = pair_count[1] = pair_count[2] = 0;
+	*cur_count = 0;
+}
+
+__global__ void k_finish_step(DCounters *C, const int *pair_count)
+{
+	if(CPB_TID != 0) return;
+	C->n_pairs[0] = pair_count[0]; C->n_pairs[1] = pair_count[1]; C->n_pairs[2] = pair_count[2];
+}
+
+// map the user's (shape a, shape b) order list onto arbiter record indices
+__global__ void k_build_order(DShapes S, DArbs A, DTable T, const uint64_t *__restrict__ user, int n_user, int *order, int *n_order_out)
+{
+	if(CPB_TID != 0) return;
+	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
+	for(int i = 0; i < nA; i++) A.seen[i] = 0;
+	int n = 0;
+	for(int q = 0; q < n_user; q++){
+		int sa = (int)(user[q] >> 32), sb = (int)(user[q] & 0xffffffffu);
+		if(sa < 0 || sa >= S.n || sb < 0 || sb >= S.n) continue;
+		int idx = table_find(T, arb_key(S.hashid[sa], S.hashid[sb]));
+		if(idx >= 0 && A.active[idx] == 1 && !A.seen[idx]){
+			// bit 30 = the caller's a/b orientation is the reverse of ours: contacts are then visited in
+			// reverse, which is the order the reference's ContactPoints produced them in (cpCollision.c:477-518)
+			order[n++] = idx | (A.sa[idx] != sa ? 0x40000000 : 0); A.seen[idx] = 1;
+		}
+	}
+	for(int i = 0; i < nA; i++){
+		if(A.active[i] == 1 && !A.seen[i]) order[n++] = i;
+		A.seen[i] = 0;
+	}
+	*n_order_out = n;
+}
+
+extern "C" int cpb200_world_step(cpb200_world *w, double dt)
+{
+	if(!w){ cpb_set_error("null world"); return -1; }
+	if(dt == 0.0) return 0; // cpSpaceStep.c:339
+	cudaSetDevice(w->device);
+	cudaStream_t st = w->stream;
+	DBodies &B = w->B; DShapes &S = w->S; DJoints &J = w->J;
+	if(S.n > 0 && w->cap_arbs == 0){ cpb_set_error("internal: arbiter buffers missing"); return -1; }
+	if(w->cap_arbs == 0){ if(alloc_arbs(w, 1024) || alloc_pairs(w, 1024)) return -1; }
+
+	w->stamp++;
+	double prev_dt = w->curr_dt;
+	w->curr_dt = dt;
+	double dt_coef = (prev_dt == 0.0 ? 0.0 : dt/prev_dt); // cpSpaceStep.c:407
+	if(refresh_spaces(w, dt) || refresh_joint_bias(w, dt)) return -1;
+
+	int iterations = 0;
+	for(int i = 0; i < w->n_spaces; i++) iterations = std::max(iterations, w->sp[(size_t)i].iterations);
+
+	if(w->cache_dirty){
+		if(S.n) LAUNCH(k_shape_cache, grid_for(S.n, 128), 128, st, S, B, 1);
+		w->cache_dirty = false;
+	}
+
+	// swap arbiter buffers: last step's records become "prev"
+	int prv = w->cur; w->cur ^= 1;
+	DArbs &Ap = w->A[prv]; DArbs &Ac = w->A[w->cur];
+	DTable &Tp = w->T[prv]; DTable &Tc = w->T[w->cur];
+	LAUNCH(k_reset_step, 1, 32, st, w->C, w->P.count, Ac.count_ptr);
+	cudaMemsetAsync(Tc.keys, 0, sizeof(uint64_t)*((size_t)Tc.mask + 1), st);
+
+	const int nb = B.n, ns = S.n;
+	const int wide = w->sm_count*8;
+
+	STAGE_BEGIN(w);
+	if(nb) LAUNCH(k_integrate_pos, grid_for(nb, 256), 256, st, B, dt);
+	STAGE_END(w, ST_INTEGRATE_POS);
+	if(ns) LAUNCH(k_shape_cache, grid_for(ns, 128), 128, st, S, B, 0);
+	STAGE_END(w, ST_SHAPE_CACHE);
+
+	// K3: LBVH
+	if(ns >= 2){
+		DBvh &T = w->bvh;
+		LAUNCH(k_bounds_init, 1, 32, st, T.bounds);
+		LAUNCH(k_bounds, std::min(grid_for(ns, 256), wide), 256, st, S, T.bounds);
+		LAUNCH(k_morton, grid_for(ns, 256), 256, st, S, B, (const double *)T.bounds, T.keys, T.leaf_shape);
+		STAGE_END(w, ST_BVH_KEYS);
+		int space_bits = 0; while((1 << space_bits) < w->n_spaces) space_bits++;
+		int bits = 32 + space_bits;
+		int where = cpb_radix_sort(T.keys, T.leaf_shape, w->keys_b, w->vals_b, ns, bits, w->sort_tmp, st);
+		if(where){ std::swap(T.keys, w->keys_b); std::swap(T.leaf_shape, w->vals_b); }
+		STAGE_END(w, ST_BVH_SORT);
+		cudaMemsetAsync(T.flags, 0, sizeof(int)*(size_t)ns, st);
+		LAUNCH(k_bvh_build, grid_for(ns - 1, 256), 256, st, T);
+		LAUNCH(k_bvh_leaves, grid_for(ns, 256), 256, st, T, S, B);
+		LAUNCH(k_bvh_refit, grid_for(ns, 256), 256, st, T);
+		STAGE_END(w, ST_BVH_BUILD);
+		LAUNCH(k_bvh_pairs, grid_for(ns, 128), 128, st, T, S, B, w->P, (const uint64_t *)w->d_nocollide, w->n_nocollide, (int)(w->n_spaces > 1), &w->C->overflow);
+		STAGE_END(w, ST_BVH_PAIRS);
+	} else {
+		STAGE_END(w, ST_BVH_KEYS); STAGE_END(w, ST_BVH_SORT); STAGE_END(w, ST_BVH_BUILD); STAGE_END(w, ST_BVH_PAIRS);
+	}
+
+	// K5 + K6
+	{
+		int g = std::min(grid_for(w->P.cap, 128), wide);
+		LAUNCH(k_collide<0>, g, 128, st, S, B, (const int *)w->P.a[0], (const int *)w->P.b[0], (const int *)&w->P.count[0], w->P.cap, Ap, Tp, Ac, Tc, w->stamp, w->C);
+		LAUNCH(k_collide<1>, g, 128, st, S, B, (const int *)w->P.a[1], (const int *)w->P.b[1], (const int *)&w->P.count[1], w->P.cap, Ap, Tp, Ac, Tc, w->stamp, w->C);
+		LAUNCH(k_collide<2>, g, 128, st, S, B, (const int *)w->P.a[2], (const int *)w->P.b[2], (const int *)&w->P.count[2], w->P.cap, Ap, Tp, Ac, Tc, w->stamp, w->C);
+	}
+	STAGE_END(w, ST_COLLIDE);
+
+	// K7: islands / sleeping (cpSpaceProcessComponents) -- before the cache filter, like the reference
+	if(w->any_sleep_enabled){
+		if(islands_step(w->I, B, S, J, Ap, Ac, Tc, w->d_spaces, dt, w->stamp, w->C, w->sm_count, st)) return -1;
+	}
+	STAGE_END(w, ST_ISLANDS);
+
+	{
+		int g = std::min(grid_for(Ap.cap, 128), wide);
+		LAUNCH(k_arb_carry, g, 128, st, B, Ap, Ac, Tc, (const DSpace *)w->d_spaces, w->stamp, w->C);
+	}
+	STAGE_END(w, ST_CARRY);
+
+	// K8
+	{
+		int g = std::min(grid_for(Ac.cap, 128), wide);
+		LAUNCH(k_arb_prestep, g, 128, st, B, Ac, (const DSpace *)w->d_spaces, dt, w->C, (double *)NULL);
+		if(J.n) LAUNCH(k_joint_prestep, grid_for(J.n, 128), 128, st, J, B, dt);
+	}
+	STAGE_END(w, ST_PRESTEP);
+
+	// K9
+	if(nb) LAUNCH(k_integrate_vel, grid_for(nb, 256), 256, st, B, (const DSpace *)w->d_spaces, dt);
+	STAGE_END(w, ST_INTEGRATE_VEL);
+
+	// K10 + K11
+	if(w->solver_mode == 1){
+		int need = Ac.cap;
+		if(w->order_cap < need){
+			if(w->d_order) cudaFree(w->d_order);
+			void *p = NULL; CPB_CHECK(cudaMalloc(&p, sizeof(int)*(size_t)(need + 4))); w->d_order = (int *)p; w->order_cap = need;
+		}
+		LAUNCH(k_build_order, 1, 32, st, S, Ac, Tc, (const uint64_t *)w->d_user_order, w->n_user_order, w->d_order, w->d_order + need);
+		CPB_CHECK(cudaMemcpyAsync(w->h_scratch, w->d_order + need, sizeof(int), cudaMemcpyDeviceToHost, st));
+		CPB_CHECK(cudaStreamSynchronize(st));
+		int n_order = *(int *)w->h_scratch;
+		LAUNCH(k_solve_serial, 1, 32, st, B, Ac, J, (const int *)w->d_order, n_order, iterations, dt, dt_coef);
+		w->n_user_order = 0;
+	} else {
+		DColour &K = w->K;
+		if(nb){ cudaMemsetAsync(K.claim, 0, sizeof(unsigned long long)*(size_t)nb, st); cudaMemsetAsync(K.bmask, 0, sizeof(unsigned long long)*(size_t)nb, st); }
+		cudaMemsetAsync(K.ccount, 0, sizeof(int)*(CPB_MAX_COLOURS + 1), st);
+		cudaMemsetAsync(K.jcount, 0, sizeof(int)*(CPB_MAX_COLOURS + 1), st);
+		cudaMemsetAsync(K.remaining, 0, sizeof(int)*(CPB_MAX_COLOUR_ROUNDS + 1), st);
+#ifndef CPB_EMU
+		{
+			DCounters *C = w->C; DRows R = w->R;
+			void *args[] = {&B, &Ac, &J, &R, &K, &C, &iterations, &dt, &dt_coef};
+			CPB_CHECK(cudaLaunchCooperativeKernel((void *)k_colour_solve, dim3(w->coop_blocks), dim3(256), args, 0, st));
+		}
+#else
+		{
+			for(int round = 0; round < CPB_MAX_COLOUR_ROUNDS; round++){
+				LAUNCH(k_colour_a, 4, 64, st, B, Ac, J, K, round);
+				LAUNCH(k_colour_b, 4, 64, st, B, Ac, J, K, w->C, round);
+				if(K.remaining[round] == 0) break;
+			}
+			LAUNCH(k_colour_finish, 1, 32, st, Ac, J, w->R, K, 0);
+			LAUNCH(k_colour_finish, 4, 64, st, Ac, J, w->R, K, 1);
+			int ncol = w->C->n_colours;
+			for(int pass = 0; pass <= iterations; pass++){
+				for(int c = 0; c < ncol; c++) LAUNCH(k_solve_colour, 4, 64, st, B, w->R, J, K, c, (pass == 0 ? 0 : 1), dt, dt_coef);
+			}
+			LAUNCH(k_rows_writeback, 4, 64, st, Ac, w->R, K);
+		}
+#endif
+	}
+	STAGE_END(w, ST_SOLVE);
+	LAUNCH(k_finish_step, 1, 32, st, w->C, (const int *)w->P.count);
+
+	w->steps++;
+	if(w->profiling){
+		CPB_CHECK(cudaStreamSynchronize(st));
+		for(int i = 0; i < ST_COUNT; i++){
+			float ms = 0.f;
+			cudaEventElapsedTime(&ms, w->ev[i], w->ev[i + 1]);
+			w->stage_us[i] = ms*1000.f;
+		}
+	}
+	CPB_CHECK(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int cpb200_world_sync(cpb200_world *w)
+{
+	if(!w) return -1;
+	cudaSetDevice(w->device);
+	if(world_sync(w)) return -1;
+	CPB_CHECK(cudaMemcpyAsync(w->hC, w->C, sizeof(DCounters), cudaMemcpyDeviceToHost, w->stream));
+	CPB_CHECK(cudaStreamSynchronize(w->stream));
+	if(w->hC->overflow){
+		cpb_set_error("device buffer overflow (flags 0x%x: 1 pairs, 2 arbiters, 4 table, 8 bvh stack); call cpb200_world_reserve with larger capacities", w->hC->overflow);
+		return -2;
+	}
+	return 0;
+}
+
+// ------------------------------------------------------------------ read-back
+template <typename T>
+static int download(cpb200_world *w, std::vector<T> &dst, const T *src, size_t n)
+{
+	dst.resize(n);
+	if(n == 0) return 0;
+	CPB_CHECK(cudaMemcpyAsync(dst.data(), src, sizeof(T)*n, cudaMemcpyDeviceToHost, w->stream));
+	return 0;
+}
+
+extern "C" int cpb200_world_get_bodies(cpb200_world *w, int first, int n, cpb200_body_state *out)
+{
+	if(!w || first < 0 || n < 0 || first + n > w->B.n){ cpb_set_error("body range out of bounds"); return -1; }
+	cudaSetDevice(w->device);
+	size_t N = (size_t)n;
+	std::vector<V2> pos, rot; std::vector<double> ang, idle; std::vector<double4> V; std::vector<int> sleeping, sgroup;
+	DBodies &B = w->B;
+	if(download(w, pos, B.pos + first, N) || download(w, rot, B.rot + first, N) || download(w, ang, B.ang + first, N) || download(w, idle, B.idle + first, N) ||
+	   download(w, V, B.V + first, N) || download(w, sleeping, B.sleeping + first, N) || download(w, sgroup, B.sgroup + first, N)) return -1;
+	if(world_sync(w)) return -1;
+	for(size_t i = 0; i < N; i++){
+		cpb200_body_state &o = out[i];
+		o.p[0] = pos[i].x; o.p[1] = pos[i].y; o.v[0] = V[i].x; o.v[1] = V[i].y; o.a = ang[i]; o.w = V[i].z;
+		o.rot[0] = rot[i].x; o.rot[1] = rot[i].y; o.idle_time = idle[i]; o.sleeping = sleeping[i]; o.sleep_group = sgroup[i];
+	}
+	return 0;
+}
+
+static int ensure_cache(cpb200_world *w)
+{
+	if(w->cache_dirty){
+		if(w->S.n) LAUNCH(k_shape_cache, grid_for(w->S.n, 128), 128, w->stream, w->S, w->B, 1);
+		w->cache_dirty = false;
+	}
+	return 0;
+}
+
+extern "C" int cpb200_world_get_shape_bbs(cpb200_world *w, int first, int n, double *out)
+{
+	if(!w || first < 0 || n < 0 || first + n > w->S.n){ cpb_set_error("shape range out of bounds"); return -1; }
+	cudaSetDevice(w->device);
+	ensure_cache(w);
+	if(n == 0) return 0;
+	CPB_CHECK(cudaMemcpyAsync(out, w->S.bb + first, sizeof(double4)*(size_t)n, cudaMemcpyDeviceToHost, w->stream));
+	return world_sync(w);
+}
+
+extern "C" int cpb200_world_get_arbiters(cpb200_world *w, int cap, cpb200_arbiter *out, int active_only)
+{
+	if(!w){ cpb_set_error("null world"); return -1; }
+	cudaSetDevice(w->device);
+	if(w->cap_arbs == 0) return 0;
+	DArbs &A = w->A[w->cur];
+	int n = 0;
+	CPB_CHECK(cudaMemcpyAsync(&n, A.count_ptr, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
+	if(world_sync(w)) return -1;
+	if(n > A.cap) n = A.cap;
+	size_t N = (size_t)n;
+	std::vector<int> sa, sb, ba, bb, cnt, state, active; std::vector<uint32_t> stamp; std::vector<V2> nn, svr, r1, r2;
+	std::vector<double> e, u, nmass, tmass, bounce, bias, jn, jt, jb; std::vector<uint64_t> hash;
+	if(download(w, sa, A.sa, N) || download(w, sb, A.sb, N) || download(w, ba, A.ba, N) || download(w, bb, A.bb, N) || download(w, cnt, A.cnt, N) ||
+	   download(w, state, A.state, N) || download(w, active, A.active, N) || download(w, stamp, A.stamp, N) || download(w, nn, A.n, N) ||
+	   download(w, svr, A.svr, N) || download(w, e, A.e, N) || download(w, u, A.u, N) || download(w, r1, A.r1, 2*N) || download(w, r2, A.r2, 2*N) ||
+	   download(w, nmass, A.nmass, 2*N) || download(w, tmass, A.tmass, 2*N) || download(w, bounce, A.bounce, 2*N) || download(w, bias, A.bias, 2*N) ||
+	   download(w, jn, A.jn, 2*N) || download(w, jt, A.jt, 2*N) || download(w, jb, A.jb, 2*N) || download(w, hash, A.hash, 2*N)) return -1;
+	if(world_sync(w)) return -1;
+	int m = 0;
+	for(size_t i = 0; i < N; i++){
+		if(active_only && active[i] != 1) continue;
+		if(m < cap && out){
+			cpb200_arbiter &o = out[m];
+			memset(&o, 0, sizeof(o));
+			o.shape_a = sa[i]; o.shape_b = sb[i]; o.body_a = ba[i]; o.body_b = bb[i];
+			o.count = (active[i] ? cnt[i] : 0); o.state = state[i]; o.stamp = stamp[i]; o.active = (active[i] == 1);
+			o.n[0] = nn[i].x; o.n[1] = nn[i].y; o.e = e[i]; o.u = u[i]; o.surface_vr[0] = svr[i].x; o.surface_vr[1] = svr[i].y;
+			for(int k = 0; k < 2; k++){
+				size_t c = 2*i + (size_t)k;
+				o.contacts[k].r1[0] = r1[c].x; o.contacts[k].r1[1] = r1[c].y; o.contacts[k].r2[0] = r2[c].x; o.contacts[k].r2[1] = r2[c].y;
+				o.contacts[k].n_mass = nmass[c]; o.contacts[k].t_mass = tmass[c]; o.contacts[k].bounce = bounce[c]; o.contacts[k].bias = bias[c];
+				o.contacts[k].jn_acc = jn[c]; o.contacts[k].jt_acc = jt[c]; o.contacts[k].j_bias = jb[c]; o.contacts[k].hash = hash[c];
+			}
+		}
+		m++;
+	}
+	return m;
+}
+
+__global__ void k_joint_state(DJoints J, cpb200_joint_state *out, int first, int n)
+{
+	int i = CPB_TID;
+	if(i >= n) return;
+	int j = first + i;
+	out[i].acc[0] = J.acc[j].x; out[i].acc[1] = J.acc[j].y;
+	out[i].impulse = joint_impulse(J, j);
+	out[i].aux = J.aux0[j];
+}
+
+extern "C" int cpb200_world_get_joints(cpb200_world *w, int first, int n, cpb200_joint_state *out)
+{
+	if(!w || first < 0 || n < 0 || first + n > w->J.n){ cpb_set_error("joint range out of bounds"); return -1; }
+	if(n == 0) return 0;
+	cudaSetDevice(w->device);
+	void *p = NULL;
+	CPB_CHECK(cudaMalloc(&p, sizeof(cpb200_joint_state)*(size_t)n));
+	LAUNCH(k_joint_state, grid_for(n, 128), 128, w->stream, w->J, (cpb200_joint_state *)p, first, n);
+	cudaError_t e = cudaMemcpyAsync(out, p, sizeof(cpb200_joint_state)*(size_t)n, cudaMemcpyDeviceToHost, w->stream);
+	int r = world_sync(w);
+	cudaFree(p);
+	if(e != cudaSuccess){ cpb_set_error("joint read-back failed"); return -1; }
+	return r;
+}
+
+__global__ void k_stats(DBodies B, DArbs A, double *out, unsigned *awake)
+{
+	double ke = 0.0, pen = 0.0;
+	unsigned aw = 0;
+	for(int i = CPB_TID; i < B.n; i += CPB_NTHREADS){
+		if(B.type[i] != CPB200_BODY_DYNAMIC) continue;
+		if(!B.sleeping[i]) aw++;
+		double4 V = B.V[i]; V2 M = B.M[i];
+		double vsq = V.x*V.x + V.y*V.y, wsq = V.z*V.z;
+		ke += (vsq ? vsq*M.x : 0.0) + (wsq ? wsq*M.y : 0.0); // cpBodyKineticEnergy (cpBody.c:581-588)
+	}
+	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
+	for(int i = CPB_TID; i < nA; i += CPB_NTHREADS){
+		if(A.active[i] != 1) continue;
+		V2 n = A.n[i];
+		V2 delta = vsub(B.pos[A.bb[i]], B.pos[A.ba[i]]);
+		for(int k = 0; k < A.cnt[i]; k++){
+			double dist = vdot(vadd(vsub(A.r2[2*i + k], A.r1[2*i + k]), delta), n);
+			if(-dist > pen) pen = -dist;
+		}
+	}
+	if(ke != 0.0) atomic_add_d(&out[0], ke);
+	if(pen > 0.0) atomic_max_double(&out[1], pen);
+	if(aw) atomicAdd(awake, aw);
+}
+
+extern "C" int cpb200_world_get_stats(cpb200_world *w, cpb200_stats *out)
+{
+	if(!w || !out){ cpb_set_error("bad arguments"); return -1; }
+	cudaSetDevice(w->device);
+	memset(out, 0, sizeof(*out));
+	cudaMemsetAsync(w->d_scratch, 0, sizeof(double)*4, w->stream);
+	if(w->cap_arbs){
+		LAUNCH(k_stats, std::min(grid_for(std::max(w->B.n, 1), 256), w->sm_count*4), 256, w->stream, w->B, w->A[w->cur], w->d_scratch, (unsigned *)(w->d_scratch + 2));
+	}
+	CPB_CHECK(cudaMemcpyAsync(w->h_scratch, w->d_scratch, sizeof(double)*4, cudaMemcpyDeviceToHost, w->stream));
+	CPB_CHECK(cudaMemcpyAsync(w->hC, w->C, sizeof(DCounters), cudaMemcpyDeviceToHost, w->stream));
+	if(world_sync(w)) return -1;
+	out->steps = w->steps;
+	out->n_bodies = (uint32_t)w->B.n; out->n_shapes = (uint32_t)w->S.n; out->n_joints = (uint32_t)w->J.n;
+	out->n_awake = *(unsigned *)(w->h_scratch + 2);
+	out->n_pairs = (uint32_t)(w->hC->n_pairs[0] + w->hC->n_pairs[1] + w->hC->n_pairs[2]);
+	out->n_arbiters = (uint32_t)w->hC->n_active; out->n_contacts = (uint32_t)w->hC->n_contacts;
+	out->n_cached = (uint32_t)w->hC->n_cached; out->n_colours = (uint32_t)w->hC->n_colours; out->overflow = (uint32_t)w->hC->overflow;
+	out->kinetic_energy = w->h_scratch[0]; out->max_penetration = w->h_scratch[1];
+	return 0;
+}
+
+// ------------------------------------------------------------------ validation hooks
+extern "C" long cpb200_world_get_pairs(cpb200_world *w, long cap, uint64_t *out)
+{
+	if(!w){ cpb_set_error("null world"); return -1; }
+	cudaSetDevice(w->device);
+	if(w->cap_pairs == 0) return 0;
+	int cnt[3] = {0, 0, 0};
+	CPB_CHECK(cudaMemcpyAsync(cnt, w->P.count, sizeof(int)*3, cudaMemcpyDeviceToHost, w->stream));
+	if(world_sync(w)) return -1;
+	std::vector<uint64_t> keys;
+	for(int c = 0; c < 3; c++){
+		size_t n = (size_t)std::min(cnt[c], w->P.cap);
+		std::vector<int> a, b;
+		if(download(w, a, w->P.a[c], n) || download(w, b, w->P.b[c], n)) return -1;
+		if(world_sync(w)) return -1;
+		for(size_t i = 0; i < n; i++){
+			uint64_t lo = (uint64_t)(uint32_t)std::min(a[i], b[i]), hi = (uint64_t)(uint32_t)std::max(a[i], b[i]);
+			keys.push_back((lo << 32) | hi);
+		}
+	}
+	std::sort(keys.begin(), keys.end());
+	for(size_t i = 0; i < keys.size() && (long)i < cap; i++) out[i] = keys[i];
+	return (long)keys.size();
+}
+
+extern "C" int cpb200_world_set_solver_mode(cpb200_world *w, int mode)
+{
+	if(!w || (mode != 0 && mode != 1)){ cpb_set_error("solver mode must be 0 or 1"); return -1; }
+	w->solver_mode = mode;
+	return 0;
+}
+
+extern "C" int cpb200_world_set_arbiter_order(cpb200_world *w, int n, const uint64_t *order)
+{
+	if(!w || n < 0){ cpb_set_error("bad arguments"); return -1; }
+	cudaSetDevice(w->device);
+	if(n > w->user_order_cap){
+		if(w->d_user_order) cudaFree(w->d_user_order);
+		void *p = NULL; CPB_CHECK(cudaMalloc(&p, sizeof(uint64_t)*(size_t)n)); w->d_user_order = (uint64_t *)p; w->user_order_cap = n;
+	}
+	if(n) CPB_CHECK(cudaMemcpyAsync(w->d_user_order, order, sizeof(uint64_t)*(size_t)n, cudaMemcpyHostToDevice, w->stream));
+	w->n_user_order = n;
+	return world_sync(w);
+}
+
+extern "C" int cpb200_world_collide_pair(cpb200_world *w, int shape_a, int shape_b, double *out13)
+{
+	if(!w || shape_a < 0 || shape_b < 0 || shape_a >= w->S.n || shape_b >= w->S.n){ cpb_set_error("shape index out of range"); return -1; }
+	cudaSetDevice(w->device);
+	ensure_cache(w);
+	LAUNCH(k_collide_one, 1, 32, w->stream, w->S, w->B, shape_a, shape_b, w->d_scratch + 8);
+	CPB_CHECK(cudaMemcpyAsync(w->h_scratch + 8, w->d_scratch + 8, sizeof(double)*13, cudaMemcpyDeviceToHost, w->stream));
+	if(world_sync(w)) return -1;
+	memcpy(out13, w->h_scratch + 8, sizeof(double)*13);
+	return (int)out13[0];
+}
+
+extern "C" int cpb200_world_get_stage_times(cpb200_world *w, int cap, float *usec)
+{
+	if(!w) return -1;
+	for(int i = 0; i < ST_COUNT && i < cap; i++) usec[i] = w->stage_us[i];
+	return ST_COUNT;
+}
+
+extern "C" int cpb200_world_set_profiling(cpb200_world *w, int on)
+{
+	if(!w) return -1;
+	w->profiling = (on != 0);
+	return 0;
+}

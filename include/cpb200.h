@@ -1,0 +1,233 @@
+/* cpb200.h -- C ABI of the B200 step engine (libcpb200.so).
+ *
+ * This is the drop-in boundary of the hot path: everything cpSpaceStep()
+ * (reference src/cpSpaceStep.c:335-445) does between "the host object graph is
+ * final" and "body / arbiter state is readable again" happens behind these
+ * entry points, as hand-written sm_100a kernels.  The C99 host layer
+ * (chipmunk2d_b200/host/, which implements the public Chipmunk2D API of
+ * include/chipmunk/chipmunk.h) is the only intended caller; INTEGRATION.md shows
+ * the equivalent binding inside the reference's own cpSpace.c / cpSpaceStep.c.
+ *
+ * Plain C: pointers + counts, no C++ or torch types.  All floating point is
+ * IEEE double (cpFloat = double, chipmunk_types.h:55-68).  There is NO CPU
+ * fallback: every call fails loudly (non-zero return + cpb200_last_error())
+ * when no CUDA device is usable.
+ *
+ * Each entry point cites the reference interface it replaces.
+ */
+#ifndef CPB200_H
+#define CPB200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CPB200_API __attribute__((visibility("default")))
+#else
+#define CPB200_API
+#endif
+
+typedef struct cpb200_world cpb200_world;
+
+enum { CPB200_BODY_DYNAMIC = 0, CPB200_BODY_KINEMATIC = 1, CPB200_BODY_STATIC = 2 };
+enum { CPB200_SHAPE_CIRCLE = 0, CPB200_SHAPE_SEGMENT = 1, CPB200_SHAPE_POLY = 2 };
+enum {
+	CPB200_JOINT_PIN = 0, CPB200_JOINT_SLIDE = 1, CPB200_JOINT_PIVOT = 2, CPB200_JOINT_GROOVE = 3,
+	CPB200_JOINT_DAMPED_SPRING = 4, CPB200_JOINT_DAMPED_ROTARY_SPRING = 5, CPB200_JOINT_ROTARY_LIMIT = 6,
+	CPB200_JOINT_RATCHET = 7, CPB200_JOINT_GEAR = 8, CPB200_JOINT_SIMPLE_MOTOR = 9
+};
+/* arbiter states, numerically equal to enum cpArbiterState (chipmunk_structs.h:83-95) */
+enum {
+	CPB200_ARB_FIRST_COLLISION = 0, CPB200_ARB_NORMAL = 1, CPB200_ARB_IGNORE = 2,
+	CPB200_ARB_CACHED = 3, CPB200_ARB_INVALIDATED = 4
+};
+
+/* Per-space parameters: the fields of struct cpSpace read by the step
+ * (chipmunk_structs.h:396-412; setters cpSpace.h:82-124). A world holds
+ * n_spaces independent spaces (1 for a plain cpSpace, many for batched use). */
+typedef struct cpb200_space_params {
+	double gravity[2];
+	double damping;               /* per-second damping; the engine applies pow(damping, dt) computed on the host (cpSpaceStep.c:399) */
+	double idle_speed_threshold;
+	double sleep_time_threshold;  /* INFINITY disables sleeping (cpSpace.c:155) */
+	double collision_slop;
+	double collision_bias;
+	uint32_t collision_persistence;
+	int32_t iterations;
+} cpb200_space_params;
+
+/* struct cpBody (chipmunk_structs.h:35-81) minus pointers. */
+typedef struct cpb200_body_desc {
+	double p[2], v[2], f[2];
+	double a, w, t;
+	double rot[2];                /* transform.a, transform.b = the host's cos(a), sin(a) (cpBody.c:347-357) */
+	double m, i;                  /* INFINITY for kinematic/static (cpBody.c:156-169) */
+	double cog[2];
+	double v_bias[2], w_bias;
+	double idle_time;             /* sleeping.idleTime */
+	int32_t type;                 /* CPB200_BODY_* */
+	int32_t space;                /* index of the owning space within the world */
+	int32_t sleeping;             /* 1 = body is asleep (sleeping.root != NULL) */
+	int32_t sleep_group;          /* bodies asleep together share a group id (component root); -1 when awake */
+} cpb200_body_desc;
+
+/* struct cpShape + cpCircleShape / cpSegmentShape / cpPolyShape (chipmunk_structs.h:177-236). */
+typedef struct cpb200_shape_desc {
+	int32_t type;                 /* CPB200_SHAPE_* */
+	int32_t body;                 /* index into the uploaded body array */
+	uint32_t hashid;              /* shape->hashid (cpSpace.c:432): stable id used in contact hashes and arbiter keys */
+	int32_t sensor;
+	uint32_t categories, mask;
+	uint64_t group;
+	uint64_t collision_type;
+	double e, u;
+	double surface_v[2];
+	double r;
+	double a[2], b[2];            /* circle: a = c (offset); segment: a, b (body-local end points) */
+	double a_tangent[2], b_tangent[2];
+	int32_t n_verts, vert_offset; /* poly: range in the uploaded vertex array (hull order, body-local) */
+} cpb200_shape_desc;
+
+/* struct cpConstraint + the joint structs (chipmunk_structs.h:250-382). */
+typedef struct cpb200_joint_desc {
+	int32_t type;                 /* CPB200_JOINT_* */
+	int32_t a, b;                 /* body indices */
+	int32_t collide_bodies;
+	double max_force, error_bias, max_bias;
+	double anchor_a[2], anchor_b[2];
+	double prm[4];                /* same packing as cpb_scene_joint.prm */
+	double acc[2];                /* accumulated impulse carried between steps (jnAcc / jAcc) */
+} cpb200_joint_desc;
+
+/* State read back per body: what cpBodyUpdatePosition/Velocity + the solver
+ * changed (cpBody.c:493-522).  80 bytes. */
+typedef struct cpb200_body_state {
+	double p[2], v[2];
+	double a, w;
+	double rot[2];                /* cos a, sin a: the device's transform rotation (cpBody.c:347-357) */
+	double idle_time;
+	int32_t sleeping;
+	int32_t sleep_group;
+} cpb200_body_state;
+
+/* One active or cached arbiter (struct cpArbiter + struct cpContact,
+ * chipmunk_structs.h:101-145).  r1/r2 are body-relative like the reference's. */
+typedef struct cpb200_arbiter {
+	int32_t shape_a, shape_b;     /* uploaded shape indices, in cpCollide order (cpCollision.c:701-726) */
+	int32_t body_a, body_b;
+	int32_t count;                /* 0 for cached / sensor / rejected arbiters */
+	int32_t state;                /* CPB200_ARB_* */
+	uint32_t stamp;
+	int32_t active;               /* 1 = solved this step (pushed to space->arbiters, cpSpaceStep.c:274) */
+	double n[2];
+	double e, u;
+	double surface_vr[2];
+	struct {
+		double r1[2], r2[2];
+		double n_mass, t_mass, bounce, bias;
+		double jn_acc, jt_acc, j_bias;
+		uint64_t hash;
+	} contacts[2];
+} cpb200_arbiter;
+
+/* Per-joint solver state after a step (for cpConstraintGetImpulse and warm starting). */
+typedef struct cpb200_joint_state {
+	double acc[2];                /* jnAcc | jAcc(x,y) */
+	double impulse;               /* what klass->getImpulse would return */
+	double aux;                   /* ratchet: current angle */
+} cpb200_joint_state;
+
+/* Step statistics (new).  Reduced over spaces on the device. */
+typedef struct cpb200_stats {
+	uint64_t steps;
+	uint32_t n_bodies, n_awake, n_shapes, n_joints;
+	uint32_t n_pairs;             /* survivors of the QueryReject rules (cpSpaceStep.c:219-232) */
+	uint32_t n_arbiters;          /* active arbiters */
+	uint32_t n_contacts;          /* contacts in active arbiters */
+	uint32_t n_cached;            /* arbiters kept in the cache but inactive */
+	uint32_t n_colours;           /* colours used by the constraint graph this step */
+	uint32_t overflow;            /* non-zero: a device buffer was too small; results of that step are invalid */
+	double kinetic_energy;        /* sum over dynamic bodies of m*v^2 + i*w^2 (cpBody.c:581-588, not halved) */
+	double max_penetration;       /* max over active contacts of -dist (>= 0) */
+} cpb200_stats;
+
+/* ---- lifetime ------------------------------------------------------------------ */
+
+/* Replaces the allocation half of cpSpaceInit (cpSpace.c:119-178).  `device` is the CUDA
+ * ordinal; n_spaces >= 1.  Returns NULL on failure (see cpb200_last_error). */
+CPB200_API cpb200_world *cpb200_world_create(int device, int n_spaces);
+/* Replaces cpSpaceDestroy (cpSpace.c:188-229). */
+CPB200_API void cpb200_world_destroy(cpb200_world *w);
+/* Thread-local description of the last failure; never NULL. */
+CPB200_API const char *cpb200_last_error(void);
+/* 1 when the library was built for sm_100a and a CUDA device is present. */
+CPB200_API int cpb200_device_available(void);
+
+/* ---- upload (host object graph -> SoA device buffers) -------------------------- */
+
+/* Space property setters (cpSpace.h:82-124). */
+CPB200_API int cpb200_world_set_space_params(cpb200_world *w, int space, const cpb200_space_params *p);
+/* Replaces the body/shape/constraint registries filled by cpSpaceAddBody/AddShape/
+ * AddConstraint (cpSpace.c:417-474).  Each call REPLACES the whole set; arbiters are
+ * keyed by shape hashid and survive re-uploads.  Buffers are HOST memory. */
+CPB200_API int cpb200_world_set_bodies(cpb200_world *w, int n, const cpb200_body_desc *bodies);
+CPB200_API int cpb200_world_set_shapes(cpb200_world *w, int n, const cpb200_shape_desc *shapes, int n_verts, const double *verts_xy);
+CPB200_API int cpb200_world_set_joints(cpb200_world *w, int n, const cpb200_joint_desc *joints);
+/* Overwrite kinematic state of bodies [first, first+n) without touching anything else
+ * (cpBodySetPosition/Velocity/Angle... between steps, cpBody.c:374-467). */
+CPB200_API int cpb200_world_update_bodies(cpb200_world *w, int first, int n, const cpb200_body_desc *bodies);
+/* Pre-size device buffers (pairs, arbiters) for at least this many; 0 keeps the default. */
+CPB200_API int cpb200_world_reserve(cpb200_world *w, int max_pairs, int max_arbiters);
+
+/* ---- the step ------------------------------------------------------------------- */
+
+/* cpSpaceStep (cpSpaceStep.c:335-445) for every space of the world.  Asynchronous:
+ * returns once the kernels are enqueued on the world's stream. */
+CPB200_API int cpb200_world_step(cpb200_world *w, double dt);
+/* Block until all enqueued steps have finished; returns non-zero on a device error or
+ * buffer overflow. */
+CPB200_API int cpb200_world_sync(cpb200_world *w);
+
+/* ---- read-back ------------------------------------------------------------------ */
+
+/* Body state after the last step (host buffer of n entries; implies a sync). */
+CPB200_API int cpb200_world_get_bodies(cpb200_world *w, int first, int n, cpb200_body_state *out);
+/* Cached shape AABBs (cpShapeGetBB, cpShape.h:124): out[n][4] = l b r t. */
+CPB200_API int cpb200_world_get_shape_bbs(cpb200_world *w, int first, int n, double *out);
+/* Arbiters of the last step (space->arbiters + cachedArbiters, cpSpaceStep.c:250-288).
+ * Returns the number available; writes at most cap.  active_only != 0 keeps only solved ones. */
+CPB200_API int cpb200_world_get_arbiters(cpb200_world *w, int cap, cpb200_arbiter *out, int active_only);
+CPB200_API int cpb200_world_get_joints(cpb200_world *w, int first, int n, cpb200_joint_state *out);
+CPB200_API int cpb200_world_get_stats(cpb200_world *w, cpb200_stats *out);
+
+/* ---- validation hooks (used by the parity tests; not needed by a normal host) ---- */
+
+/* Overlapping-pair set of the last step as sorted (min<<32|max) of uploaded shape indices
+ * (SURVEY.md 8a a6/a7 contract).  Returns the count; writes at most cap. */
+CPB200_API long cpb200_world_get_pairs(cpb200_world *w, long cap, uint64_t *out);
+/* Solver order: 0 = graph-coloured parallel Gauss-Seidel (default);
+ * 1 = serial, arbiters in the order given to cpb200_world_set_arbiter_order (or by
+ * ascending key when none was given), then joints in upload order -- the reference's
+ * sequential order (cpSpaceStep.c:418-427), used for tight one-step parity. */
+CPB200_API int cpb200_world_set_solver_mode(cpb200_world *w, int mode);
+/* order[n] = (shape index a)<<32 | (shape index b) in the sequence the reference pushed
+ * its arbiters; pairs not listed are solved afterwards in key order. Applies to the next step only. */
+CPB200_API int cpb200_world_set_arbiter_order(cpb200_world *w, int n, const uint64_t *order);
+/* Run only the narrowphase on one uploaded shape pair with current world caches
+ * (cpShapesCollide, cpShape.c:259-283): out = count n.x n.y (pA.xy pB.xy dist) x2. */
+CPB200_API int cpb200_world_collide_pair(cpb200_world *w, int shape_a, int shape_b, double *out13);
+/* Per-stage device time of the last step in microseconds (CUDA events), names via
+ * cpb200_stage_name(i).  Returns the number of stages. */
+CPB200_API int cpb200_world_get_stage_times(cpb200_world *w, int cap, float *usec);
+CPB200_API const char *cpb200_stage_name(int i);
+/* Enable (1) / disable (0) per-stage event timing (adds syncs; off by default). */
+CPB200_API int cpb200_world_set_profiling(cpb200_world *w, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

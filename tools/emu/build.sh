@@ -1,0 +1,10 @@
+#!/bin/sh
+# Developer tool: compile the kernels as plain C++ (CPB_EMU, see csrc/cpb_rt.h) so their
+# per-thread logic can be debugged in the GPU-less build container.  NOT part of the product,
+# not built by __graft_entry__.build(), never loaded by chipmunk2d_b200.
+set -e
+cd "$(dirname "$0")/../.."
+mkdir -p tools/emu/_build
+g++ -x c++ -std=c++17 -DCPB_EMU -O1 -g -fPIC -shared -ffp-contract=off -Wall -Wno-unused-function -Wno-unused-variable \
+    -o tools/emu/_build/libcpb200_emu.so chipmunk2d_b200/csrc/world.cu
+echo built tools/emu/_build/libcpb200_emu.so
