@@ -44,6 +44,7 @@ struct DShapes {
 	int n, nv;
 	int *type, *body;
 	uint32_t *hashid;
+	uint32_t *hlocal;     // hashid minus the lowest hashid of the shape's space (colouring priorities)
 	int *sensor;
 	uint32_t *cat, *mask;
 	uint64_t *group, *ctype;
@@ -83,6 +84,7 @@ struct DArbs {
 	double *jn, *jt, *jb;  // jnAcc, jtAcc, jBias
 	uint64_t *hash;
 	int *colour;           // colour assigned this step (-1 = not in the solver)
+	uint64_t *pri;         // colouring priority: hash of the space-local shape pair (same in a batch as alone)
 };
 
 // open-addressing table: shape-pair key -> arbiter record index (replaces cpHashSet cachedArbiters)
@@ -123,6 +125,7 @@ struct DJoints {
 	V2 *jspring;           // impulse applied by damped springs in preStep (cpDampedSpring.c:49-52)
 	int *colour;
 	int *row;              // colour-sorted order: row -> joint index
+	uint64_t *pri;         // colouring priority: hash of the space-local joint index
 };
 
 // ---- broadphase scratch (LBVH over all shapes, rebuilt every step) ----

@@ -37,13 +37,13 @@ CPB_DEVICE bool cons_fetch(const DArbs &A, const DJoints &J, int nA, int c, int 
 	if(c < nA){
 		if(A.active[c] != 1) return false;
 		a = A.ba[c]; b = A.bb[c]; col = A.colour[c];
-		pri = mix64(A.key[c]) >> 8;
+		pri = A.pri[c];
 	} else {
 		int j = c - nA;
 		col = J.colour[j];
 		if(col == -2) return false;
 		a = J.a[j]; b = J.b[j];
-		pri = mix64(0x9e3779b97f4a7c15ull ^ (uint64_t)j) >> 8;
+		pri = J.pri[j];
 	}
 	return true;
 }
@@ -297,9 +297,12 @@ __global__ void k_rows_writeback(DArbs A, DRows R, DColour K){
 
 // ---- serial validation mode: the reference's exact order (cpSpaceStep.c:406-427) ----
 // order[n_order] lists arbiter record indices; joints follow in upload order.
-__global__ void k_solve_serial(DBodies B, DArbs A, DJoints J, const int *__restrict__ order, int n_order, int iterations, double dt, double dt_coef)
+__global__ void k_solve_serial(DBodies B, DArbs A, DJoints J, const int *__restrict__ order, int n_order, const int *__restrict__ jorder, int n_jorder, int iterations, double dt, double dt_coef)
 {
 	if(CPB_TID != 0) return;
+	// joints named by the caller first (J.row doubles as a "listed" marker here), the rest in upload order
+	for(int j = 0; j < J.n; j++) J.row[j] = 0;
+	for(int q = 0; q < n_jorder; q++){ int j = jorder[q]; if(j >= 0 && j < J.n) J.row[j] = 1; }
 	for(int pass = 0; pass <= iterations; pass++){
 		for(int q = 0; q < n_order; q++){
 			int i = order[q];
@@ -322,8 +325,13 @@ __global__ void k_solve_serial(DBodies B, DArbs A, DJoints J, const int *__restr
 			if(mia.x != 0.0 || mia.y != 0.0){ B.V[ba] = Va; B.VB[ba] = VBa; }
 			if(mib.x != 0.0 || mib.y != 0.0){ B.V[bb] = Vb; B.VB[bb] = VBb; }
 		}
+		for(int q = 0; q < n_jorder; q++){
+			int j = jorder[q];
+			if(j < 0 || j >= J.n || J.colour[j] == -2) continue;
+			solve_joint(B, J, j, (pass == 0 ? 0 : 1), dt, dt_coef);
+		}
 		for(int j = 0; j < J.n; j++){
-			if(J.colour[j] == -2) continue;
+			if(J.colour[j] == -2 || J.row[j]) continue;
 			solve_joint(B, J, j, (pass == 0 ? 0 : 1), dt, dt_coef);
 		}
 	}

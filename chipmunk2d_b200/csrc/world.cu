@@ -101,6 +101,7 @@ struct cpb200_world {
 	int solver_mode;
 	int *d_order; int order_cap;
 	uint64_t *d_user_order; int n_user_order; int user_order_cap;
+	int *d_joint_order; int n_joint_order; int joint_order_cap;
 
 	bool profiling;
 	cudaEvent_t ev[ST_COUNT + 1];
@@ -130,6 +131,15 @@ static int upload(cpb200_world *w, T *dst, const std::vector<T> &src)
 	if(src.empty()) return 0;
 	CPB_CHECK(cudaMemcpyAsync(dst, src.data(), sizeof(T)*src.size(), cudaMemcpyHostToDevice, w->stream));
 	CPB_CHECK(cudaStreamSynchronize(w->stream));
+	return 0;
+}
+
+template <typename T>
+static int download(cpb200_world *w, std::vector<T> &dst, const T *src, size_t n)
+{
+	dst.resize(n);
+	if(n == 0) return 0;
+	CPB_CHECK(cudaMemcpyAsync(dst.data(), src, sizeof(T)*n, cudaMemcpyDeviceToHost, w->stream));
 	return 0;
 }
 
@@ -191,6 +201,7 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	w->cap_pairs = 0; w->cap_arbs = 0; w->user_cap_pairs = 0; w->user_cap_arbs = 0;
 	w->stamp = 0; w->curr_dt = 0.0; w->steps = 0; w->cache_dirty = true; w->any_sleep_enabled = false;
 	w->solver_mode = 0; w->d_order = NULL; w->order_cap = 0; w->d_user_order = NULL; w->n_user_order = 0; w->user_order_cap = 0;
+	w->d_joint_order = NULL; w->n_joint_order = 0; w->joint_order_cap = 0;
 	w->profiling = false;
 	for(int i = 0; i <= ST_COUNT; i++) cudaEventCreate(&w->ev[i]);
 	memset(w->stage_us, 0, sizeof(w->stage_us));
@@ -213,6 +224,7 @@ extern "C" void cpb200_world_destroy(cpb200_world *w)
 	cudaFree(w->d_spaces); cudaFree(w->C); cudaFreeHost(w->hC); cudaFree(w->d_scratch); cudaFreeHost(w->h_scratch);
 	if(w->d_order) cudaFree(w->d_order);
 	if(w->d_user_order) cudaFree(w->d_user_order);
+	if(w->d_joint_order) cudaFree(w->d_joint_order);
 	if(w->d_nocollide) cudaFree(w->d_nocollide);
 	for(int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(w->ev[i]);
 	cudaStreamDestroy(w->stream);
@@ -344,7 +356,7 @@ static int alloc_arbs(cpb200_world *w, int cap)
 		DA(w->gA, A.r1, 2*(size_t)cap); DA(w->gA, A.r2, 2*(size_t)cap);
 		DA(w->gA, A.nmass, 2*(size_t)cap); DA(w->gA, A.tmass, 2*(size_t)cap); DA(w->gA, A.bounce, 2*(size_t)cap); DA(w->gA, A.bias, 2*(size_t)cap);
 		DA(w->gA, A.jn, 2*(size_t)cap); DA(w->gA, A.jt, 2*(size_t)cap); DA(w->gA, A.jb, 2*(size_t)cap); DA(w->gA, A.hash, 2*(size_t)cap);
-		DA(w->gA, A.colour, cap);
+		DA(w->gA, A.colour, cap); DA(w->gA, A.pri, cap);
 		DTable &T = w->T[k];
 		T.mask = tcap - 1;
 		DA(w->gA, T.keys, tcap); DA(w->gA, T.vals, tcap);
@@ -368,7 +380,10 @@ extern "C" int cpb200_world_set_shapes(cpb200_world *w, int n, const cpb200_shap
 	if(world_sync(w)) return -1;
 	size_t N = (size_t)n, NV = (size_t)n_verts;
 	std::vector<int> type(N), body(N), sensor(N), pcount(N), poff(N);
-	std::vector<uint32_t> hashid(N), cat(N), mask(N);
+	std::vector<uint32_t> hashid(N), cat(N), mask(N), hlocal(N);
+	std::vector<int> body_space;
+	if(download(w, body_space, w->B.space, (size_t)w->B.n) || world_sync(w)) return -1;
+	std::vector<uint32_t> space_base((size_t)w->n_spaces, 0xffffffffu);
 	std::vector<uint64_t> group(N), ctype(N);
 	std::vector<double> e(N), u(N), r(N);
 	std::vector<V2> surfv(N), la(N), lb(N), ln(N), atan_(N), btan_(N), lpv(NV), lpn(NV);
@@ -398,15 +413,17 @@ extern "C" int cpb200_world_set_shapes(cpb200_world *w, int n, const cpb200_shap
 			}
 		}
 	}
+	for(size_t i = 0; i < N; i++){ uint32_t &b = space_base[(size_t)body_space[(size_t)body[i]]]; b = std::min(b, hashid[i]); }
+	for(size_t i = 0; i < N; i++) hlocal[i] = hashid[i] - space_base[(size_t)body_space[(size_t)body[i]]];
 	w->gS.release();
 	DShapes &S = w->S;
 	S.n = n; S.nv = n_verts;
-	DA(w->gS, S.type, n); DA(w->gS, S.body, n); DA(w->gS, S.hashid, n); DA(w->gS, S.sensor, n); DA(w->gS, S.cat, n); DA(w->gS, S.mask, n);
+	DA(w->gS, S.type, n); DA(w->gS, S.body, n); DA(w->gS, S.hashid, n); DA(w->gS, S.hlocal, n); DA(w->gS, S.sensor, n); DA(w->gS, S.cat, n); DA(w->gS, S.mask, n);
 	DA(w->gS, S.group, n); DA(w->gS, S.ctype, n); DA(w->gS, S.e, n); DA(w->gS, S.u, n); DA(w->gS, S.r, n); DA(w->gS, S.surfv, n);
 	DA(w->gS, S.la, n); DA(w->gS, S.lb, n); DA(w->gS, S.ln, n); DA(w->gS, S.atan, n); DA(w->gS, S.btan, n);
 	DA(w->gS, S.pcount, n); DA(w->gS, S.poff, n); DA(w->gS, S.lpv, n_verts); DA(w->gS, S.lpn, n_verts);
 	DA(w->gS, S.wa, n); DA(w->gS, S.wb, n); DA(w->gS, S.wn, n); DA(w->gS, S.wpv, n_verts); DA(w->gS, S.wpn, n_verts); DA(w->gS, S.bb, n);
-	if(upload(w, S.type, type) || upload(w, S.body, body) || upload(w, S.hashid, hashid) || upload(w, S.sensor, sensor) || upload(w, S.cat, cat) ||
+	if(upload(w, S.type, type) || upload(w, S.body, body) || upload(w, S.hashid, hashid) || upload(w, S.hlocal, hlocal) || upload(w, S.sensor, sensor) || upload(w, S.cat, cat) ||
 	   upload(w, S.mask, mask) || upload(w, S.group, group) || upload(w, S.ctype, ctype) || upload(w, S.e, e) || upload(w, S.u, u) || upload(w, S.r, r) ||
 	   upload(w, S.surfv, surfv) || upload(w, S.la, la) || upload(w, S.lb, lb) || upload(w, S.ln, ln) || upload(w, S.atan, atan_) || upload(w, S.btan, btan_) ||
 	   upload(w, S.pcount, pcount) || upload(w, S.poff, poff) || upload(w, S.lpv, lpv) || upload(w, S.lpn, lpn)) return -1;
@@ -442,7 +459,10 @@ extern "C" int cpb200_world_set_joints(cpb200_world *w, int n, const cpb200_join
 	std::vector<double> max_force(N), max_bias(N), aux0(N, 0.0);
 	std::vector<V2> anchor_a(N), anchor_b(N), acc(N);
 	std::vector<double4> prm(N);
-	std::vector<uint64_t> nocollide;
+	std::vector<uint64_t> nocollide, jpri(N);
+	std::vector<int> body_space;
+	if(download(w, body_space, w->B.space, (size_t)w->B.n) || world_sync(w)) return -1;
+	std::vector<int> joint_base((size_t)w->n_spaces, -1);
 	w->joint_error_bias.resize(N);
 	for(size_t i = 0; i < N; i++){
 		const cpb200_joint_desc &d = joints[i];
@@ -452,6 +472,11 @@ extern "C" int cpb200_world_set_joints(cpb200_world *w, int n, const cpb200_join
 		anchor_a[i] = v2(d.anchor_a[0], d.anchor_a[1]); anchor_b[i] = v2(d.anchor_b[0], d.anchor_b[1]);
 		prm[i] = make_double4(d.prm[0], d.prm[1], d.prm[2], d.prm[3]);
 		acc[i] = v2(d.acc[0], d.acc[1]);
+		{
+			int &jb = joint_base[(size_t)body_space[(size_t)d.a]];
+			if(jb < 0) jb = (int)i;
+			jpri[i] = mix64(0x9e3779b97f4a7c15ull ^ (uint64_t)((int)i - jb)) >> 8;
+		}
 		if(d.type == CPB200_JOINT_RATCHET) aux0[i] = d.prm[0];
 		if(d.type == CPB200_JOINT_GROOVE){
 			// cpGrooveJointInit: grv_n = cpvperp(cpvnormalize(cpvsub(groove_b, groove_a))) (cpGrooveJoint.c:128)
@@ -471,9 +496,9 @@ extern "C" int cpb200_world_set_joints(cpb200_world *w, int n, const cpb200_join
 	DA(w->gJ, J.type, n); DA(w->gJ, J.a, n); DA(w->gJ, J.b, n); DA(w->gJ, J.max_force, n); DA(w->gJ, J.max_bias, n); DA(w->gJ, J.bias_coef, n);
 	DA(w->gJ, J.anchor_a, n); DA(w->gJ, J.anchor_b, n); DA(w->gJ, J.prm, n);
 	DA(w->gJ, J.r1, n); DA(w->gJ, J.r2, n); DA(w->gJ, J.nrm, n); DA(w->gJ, J.nmass, n); DA(w->gJ, J.k, n); DA(w->gJ, J.bias, n); DA(w->gJ, J.acc, n);
-	DA(w->gJ, J.aux0, n); DA(w->gJ, J.aux1, n); DA(w->gJ, J.jspring, n); DA(w->gJ, J.colour, n); DA(w->gJ, J.row, n);
+	DA(w->gJ, J.aux0, n); DA(w->gJ, J.aux1, n); DA(w->gJ, J.jspring, n); DA(w->gJ, J.colour, n); DA(w->gJ, J.row, n); DA(w->gJ, J.pri, n);
 	if(upload(w, J.type, type) || upload(w, J.a, a) || upload(w, J.b, b) || upload(w, J.max_force, max_force) || upload(w, J.max_bias, max_bias) ||
-	   upload(w, J.anchor_a, anchor_a) || upload(w, J.anchor_b, anchor_b) || upload(w, J.prm, prm) || upload(w, J.acc, acc) || upload(w, J.aux0, aux0)) return -1;
+	   upload(w, J.anchor_a, anchor_a) || upload(w, J.anchor_b, anchor_b) || upload(w, J.prm, prm) || upload(w, J.acc, acc) || upload(w, J.aux0, aux0) || upload(w, J.pri, jpri)) return -1;
 	if(w->d_nocollide){ cudaFree(w->d_nocollide); w->d_nocollide = NULL; }
 	w->n_nocollide = (int)nocollide.size();
 	if(w->n_nocollide){
@@ -652,8 +677,8 @@ extern "C" int cpb200_world_step(cpb200_world *w, double dt)
 		CPB_CHECK(cudaMemcpyAsync(w->h_scratch, w->d_order + need, sizeof(int), cudaMemcpyDeviceToHost, st));
 		CPB_CHECK(cudaStreamSynchronize(st));
 		int n_order = *(int *)w->h_scratch;
-		LAUNCH(k_solve_serial, 1, 32, st, B, Ac, J, (const int *)w->d_order, n_order, iterations, dt, dt_coef);
-		w->n_user_order = 0;
+		LAUNCH(k_solve_serial, 1, 32, st, B, Ac, J, (const int *)w->d_order, n_order, (const int *)w->d_joint_order, w->n_joint_order, iterations, dt, dt_coef);
+		w->n_user_order = 0; w->n_joint_order = 0;
 	} else {
 		DColour &K = w->K;
 		if(nb){ cudaMemsetAsync(K.claim, 0, sizeof(unsigned long long)*(size_t)nb, st); cudaMemsetAsync(K.bmask, 0, sizeof(unsigned long long)*(size_t)nb, st); }
@@ -714,14 +739,6 @@ extern "C" int cpb200_world_sync(cpb200_world *w)
 }
 
 // ------------------------------------------------------------------ read-back
-template <typename T>
-static int download(cpb200_world *w, std::vector<T> &dst, const T *src, size_t n)
-{
-	dst.resize(n);
-	if(n == 0) return 0;
-	CPB_CHECK(cudaMemcpyAsync(dst.data(), src, sizeof(T)*n, cudaMemcpyDeviceToHost, w->stream));
-	return 0;
-}
 
 extern "C" int cpb200_world_get_bodies(cpb200_world *w, int first, int n, cpb200_body_state *out)
 {
@@ -918,6 +935,19 @@ extern "C" int cpb200_world_set_arbiter_order(cpb200_world *w, int n, const uint
 	return world_sync(w);
 }
 
+extern "C" int cpb200_world_set_joint_order(cpb200_world *w, int n, const int32_t *order)
+{
+	if(!w || n < 0){ cpb_set_error("bad arguments"); return -1; }
+	cudaSetDevice(w->device);
+	if(n > w->joint_order_cap){
+		if(w->d_joint_order) cudaFree(w->d_joint_order);
+		void *p = NULL; CPB_CHECK(cudaMalloc(&p, sizeof(int)*(size_t)n)); w->d_joint_order = (int *)p; w->joint_order_cap = n;
+	}
+	if(n) CPB_CHECK(cudaMemcpyAsync(w->d_joint_order, order, sizeof(int)*(size_t)n, cudaMemcpyHostToDevice, w->stream));
+	w->n_joint_order = n;
+	return world_sync(w);
+}
+
 extern "C" int cpb200_world_collide_pair(cpb200_world *w, int shape_a, int shape_b, double *out13)
 {
 	if(!w || shape_a < 0 || shape_b < 0 || shape_a >= w->S.n || shape_b >= w->S.n){ cpb_set_error("shape index out of range"); return -1; }
@@ -941,5 +971,47 @@ extern "C" int cpb200_world_set_profiling(cpb200_world *w, int on)
 {
 	if(!w) return -1;
 	w->profiling = (on != 0);
+	return 0;
+}
+
+// ------------------------------------------------------------------ primitive self-tests
+// (exercised by tests/test_gpu_prims.py; host buffers in, host buffers out)
+extern "C" int cpb200_debug_sort_pairs(int device, int n, int bits, uint64_t *keys, int32_t *vals)
+{
+	if(n < 0) return -1;
+	cudaSetDevice(device);
+	uint64_t *ka = NULL, *kb = NULL; int *va = NULL, *vb = NULL; uint32_t *tmp = NULL;
+	size_t N = (size_t)(n > 0 ? n : 1);
+	void *p = NULL;
+	CPB_CHECK(cudaMalloc(&p, 8*N)); ka = (uint64_t *)p;
+	CPB_CHECK(cudaMalloc(&p, 8*N)); kb = (uint64_t *)p;
+	CPB_CHECK(cudaMalloc(&p, 4*N)); va = (int *)p;
+	CPB_CHECK(cudaMalloc(&p, 4*N)); vb = (int *)p;
+	CPB_CHECK(cudaMalloc(&p, 4*(cpb_sort_tmp_elems(n) + 16))); tmp = (uint32_t *)p;
+	CPB_CHECK(cudaMemcpy(ka, keys, 8*(size_t)n, cudaMemcpyHostToDevice));
+	CPB_CHECK(cudaMemcpy(va, vals, 4*(size_t)n, cudaMemcpyHostToDevice));
+	int where = cpb_radix_sort(ka, va, kb, vb, n, bits, tmp, 0);
+	CPB_CHECK(cudaDeviceSynchronize());
+	CPB_CHECK(cudaMemcpy(keys, where ? kb : ka, 8*(size_t)n, cudaMemcpyDeviceToHost));
+	CPB_CHECK(cudaMemcpy(vals, where ? vb : va, 4*(size_t)n, cudaMemcpyDeviceToHost));
+	cudaFree(ka); cudaFree(kb); cudaFree(va); cudaFree(vb); cudaFree(tmp);
+	CPB_CHECK(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int cpb200_debug_exclusive_scan(int device, int n, uint32_t *data)
+{
+	if(n < 0) return -1;
+	cudaSetDevice(device);
+	uint32_t *d = NULL, *tmp = NULL;
+	void *p = NULL;
+	CPB_CHECK(cudaMalloc(&p, 4*(size_t)(n > 0 ? n : 1))); d = (uint32_t *)p;
+	CPB_CHECK(cudaMalloc(&p, 4*(cpb_scan_tmp_elems(n) + 16))); tmp = (uint32_t *)p;
+	CPB_CHECK(cudaMemcpy(d, data, 4*(size_t)n, cudaMemcpyHostToDevice));
+	cpb_exclusive_scan(d, d, n, tmp, 0);
+	CPB_CHECK(cudaDeviceSynchronize());
+	CPB_CHECK(cudaMemcpy(data, d, 4*(size_t)n, cudaMemcpyDeviceToHost));
+	cudaFree(d); cudaFree(tmp);
+	CPB_CHECK(cudaGetLastError());
 	return 0;
 }

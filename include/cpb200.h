@@ -217,6 +217,10 @@ CPB200_API int cpb200_world_set_solver_mode(cpb200_world *w, int mode);
 /* order[n] = (shape index a)<<32 | (shape index b) in the sequence the reference pushed
  * its arbiters; pairs not listed are solved afterwards in key order. Applies to the next step only. */
 CPB200_API int cpb200_world_set_arbiter_order(cpb200_world *w, int n, const uint64_t *order);
+/* Serial mode only: order[n] = joint indices in the sequence the reference holds them in
+ * space->constraints (sleeping reorders that array); joints not listed follow in upload order.
+ * Applies to the next step only. */
+CPB200_API int cpb200_world_set_joint_order(cpb200_world *w, int n, const int32_t *order);
 /* Run only the narrowphase on one uploaded shape pair with current world caches
  * (cpShapesCollide, cpShape.c:259-283): out = count n.x n.y (pA.xy pB.xy dist) x2. */
 CPB200_API int cpb200_world_collide_pair(cpb200_world *w, int shape_a, int shape_b, double *out13);
@@ -226,6 +230,11 @@ CPB200_API int cpb200_world_get_stage_times(cpb200_world *w, int cap, float *use
 CPB200_API const char *cpb200_stage_name(int i);
 /* Enable (1) / disable (0) per-stage event timing (adds syncs; off by default). */
 CPB200_API int cpb200_world_set_profiling(cpb200_world *w, int on);
+
+/* Self-tests of the device-wide primitives under the broadphase (radix sort of (u64 key, i32
+ * value) pairs by the low `bits` key bits; exclusive scan), host buffers in and out. */
+CPB200_API int cpb200_debug_sort_pairs(int device, int n, int bits, uint64_t *keys, int32_t *vals);
+CPB200_API int cpb200_debug_exclusive_scan(int device, int n, uint32_t *data);
 
 #ifdef __cplusplus
 }

@@ -136,6 +136,8 @@ class Ref:
         cp.refp_pairs_bruteforce.restype = C.c_long
         cp.refp_pairs_bruteforce.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.POINTER(C.c_uint64)]
         cp.refp_step.argtypes = [C.c_void_p, C.c_double, C.c_int]
+        cp.refp_get_constraint_order.restype = C.c_int
+        cp.refp_get_constraint_order.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         cp.refp_space_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         cp.cpSpaceStep.argtypes = [C.c_void_p, C.c_double]
 
@@ -202,6 +204,11 @@ class RefSpace(SceneSpace):
         out = np.zeros((max(self.n_joints, 1), JOINT_ROW))
         self.ref.cp.refp_get_joints(self.space, self.n_joints, _p(out))
         return out[:self.n_joints]
+
+    def constraint_order(self):
+        out = np.zeros(max(self.n_joints, 1), dtype=np.int32)
+        n = self.ref.cp.refp_get_constraint_order(self.space, len(out), out.ctypes.data_as(C.POINTER(C.c_int)))
+        return out[:n]
 
     def pairs(self, asleep=None):
         cap = 64 * max(self.n_shapes, 16)

@@ -429,6 +429,15 @@ REFP_EXPORT void refp_step(cpSpace *space, double dt, int n)
 	for(int i = 0; i < n; i++) cpSpaceStep(space, dt);
 }
 
+/* space->constraints in SOLVER ORDER (cpSpaceStep.c:423-426) as scene joint indices.  Sleeping
+ * and waking reorder this array (cpArrayDeleteObj moves the last element into the hole). */
+REFP_EXPORT int refp_get_constraint_order(cpSpace *space, int cap, int *out)
+{
+	cpArray *cons = space->constraints;
+	for(int i = 0; i < cons->num && i < cap; i++) out[i] = UNTAG(((cpConstraint *)cons->arr[i])->userData);
+	return cons->num;
+}
+
 REFP_EXPORT int refp_space_counts(cpSpace *space, int *out)
 {
 	out[0] = space->dynamicBodies->num;

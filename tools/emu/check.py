@@ -32,6 +32,7 @@ def compare(name, steps, mode):
         if mode == 1:
             order = (arbs[:, 0].astype(np.uint64) << np.uint64(32)) | arbs[:, 1].astype(np.uint64)
             w.set_arbiter_order(order)
+            w.set_joint_order(rs.constraint_order())
         w.step(dt)
         w.sync()
         st = w.stats()
