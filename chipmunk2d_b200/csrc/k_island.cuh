@@ -79,8 +79,15 @@ __global__ void k_sleep_wake_apply(DBodies B, DIslands I)
 }
 
 CPB_DEVICE int uf_find(int *parent, int x){
-	int p = ((volatile int *)parent)[x];
-	while(p != x){ x = p; p = ((volatile int *)parent)[x]; }
+	// find with path halving: every visited node is re-pointed at its grandparent.  Racing
+	// writers only ever store an ancestor, so the forest stays valid without atomics.
+	volatile int *vp = (volatile int *)parent;
+	int p = vp[x];
+	while(p != x){
+		int g = vp[p];
+		if(g != p) vp[x] = g;
+		x = p; p = g;
+	}
 	return x;
 }
 

@@ -159,6 +159,21 @@ CPB_DEVICE void contact_apply(double4 &Va, double4 &Vb, double4 &VBa, double4 &V
 	apply_impulses(Va, Vb, mia, mib, r1, r2, vrotate(n, v2(jnAcc - jnOld, jtAcc - jtOld)));
 }
 
+// Body velocities are gathered/scattered once per colour phase and are written by other SMs in
+// the previous phase: go through L2 (ld.cg / st.cg), never through the non-coherent L1.
+#ifndef CPB_EMU
+__device__ __forceinline__ double4 ld_vel(const double4 *p){
+	double2 lo = __ldcg((const double2 *)p), hi = __ldcg((const double2 *)p + 1);
+	return make_double4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ void st_vel(double4 *p, double4 v){
+	__stcg((double2 *)p, make_double2(v.x, v.y)); __stcg((double2 *)p + 1, make_double2(v.z, v.w));
+}
+#else
+static inline double4 ld_vel(const double4 *p){ return *p; }
+static inline void st_vel(double4 *p, double4 v){ *p = v; }
+#endif
+
 // one colour-sorted row: mode 0 = warm start, 1 = iteration
 CPB_DEVICE void solve_row(const DBodies &B, const DRows &R, int r, int mode, double dt_coef){
 	int ba = R.ba[r], bb = R.bb[r];
@@ -167,7 +182,7 @@ CPB_DEVICE void solve_row(const DBodies &B, const DRows &R, int r, int mode, dou
 	if(first) cnt = -cnt;
 	if(mode == 0 && first) return;
 	V2 mia = B.MI[ba], mib = B.MI[bb];
-	double4 Va = B.V[ba], Vb = B.V[bb];
+	double4 Va = ld_vel(&B.V[ba]), Vb = ld_vel(&B.V[bb]);
 	V2 n = R.n[r];
 	bool dyn_a = (mia.x != 0.0 || mia.y != 0.0), dyn_b = (mib.x != 0.0 || mib.y != 0.0);
 	if(mode == 0){
@@ -175,11 +190,11 @@ CPB_DEVICE void solve_row(const DBodies &B, const DRows &R, int r, int mode, dou
 			int d = k*R.cap + r;
 			contact_apply_cached(Va, Vb, mia, mib, n, R.r1[d], R.r2[d], R.jn[d], R.jt[d], dt_coef);
 		}
-		if(dyn_a) B.V[ba] = Va;
-		if(dyn_b) B.V[bb] = Vb;
+		if(dyn_a) st_vel(&B.V[ba], Va);
+		if(dyn_b) st_vel(&B.V[bb], Vb);
 		return;
 	}
-	double4 VBa = B.VB[ba], VBb = B.VB[bb];
+	double4 VBa = ld_vel(&B.VB[ba]), VBb = ld_vel(&B.VB[bb]);
 	V2 svr = R.svr[r];
 	double u = R.u[r];
 	for(int k = 0; k < cnt; k++){
@@ -188,18 +203,18 @@ CPB_DEVICE void solve_row(const DBodies &B, const DRows &R, int r, int mode, dou
 		contact_apply(Va, Vb, VBa, VBb, mia, mib, n, svr, u, R.r1[d], R.r2[d], R.nmass[d], R.tmass[d], R.bias[d], R.bounce[d], jn, jt, jb);
 		R.jn[d] = jn; R.jt[d] = jt; R.jb[d] = jb;
 	}
-	if(dyn_a){ B.V[ba] = Va; B.VB[ba] = VBa; }
-	if(dyn_b){ B.V[bb] = Vb; B.VB[bb] = VBb; }
+	if(dyn_a){ st_vel(&B.V[ba], Va); st_vel(&B.VB[ba], VBa); }
+	if(dyn_b){ st_vel(&B.V[bb], Vb); st_vel(&B.VB[bb], VBb); }
 }
 
 CPB_DEVICE void solve_joint(const DBodies &B, const DJoints &J, int j, int mode, double dt, double dt_coef){
 	int a = J.a[j], b = J.b[j];
 	V2 mia = B.MI[a], mib = B.MI[b];
-	double4 Va = B.V[a], Vb = B.V[b];
+	double4 Va = ld_vel(&B.V[a]), Vb = ld_vel(&B.V[b]);
 	if(mode == 0) joint_apply_cached(J, j, Va, Vb, mia, mib, dt_coef);
 	else joint_apply(J, j, Va, Vb, mia, mib, dt);
-	if(mia.x != 0.0 || mia.y != 0.0) B.V[a] = Va;
-	if(mib.x != 0.0 || mib.y != 0.0) B.V[b] = Vb;
+	if(mia.x != 0.0 || mia.y != 0.0) st_vel(&B.V[a], Va);
+	if(mib.x != 0.0 || mib.y != 0.0) st_vel(&B.V[b], Vb);
 }
 
 // all rows + joints of one colour
@@ -231,27 +246,49 @@ CPB_DEVICE void rows_writeback(const DArbs &A, const DRows &R, int n_rows, int t
 }
 
 #ifndef CPB_EMU
-namespace cg = cooperative_groups;
+// Grid-wide barrier for the persistent kernel (launched cooperatively, so all CTAs are resident).
+// bar[0] = arrival count, bar[1] = generation.  Thread 0 of every CTA arrives with one atomic and
+// spins on the generation word; the gpu-scope fences on both sides order the phase's global
+// writes before every later read (the same pattern cooperative_groups::grid_group::sync uses),
+// at one L2 round trip instead of a library call per colour.
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned nblocks)
+{
+	__syncthreads();
+	if(threadIdx.x == 0){
+		__threadfence();
+		unsigned gen = *((volatile unsigned *)&bar[1]);
+		unsigned arrived = atomicAdd(&bar[0], 1u) + 1u;
+		if(arrived == nblocks){
+			bar[0] = 0u;
+			__threadfence();
+			atomicAdd(&bar[1], 1u);
+		} else {
+			while(*((volatile unsigned *)&bar[1]) == gen){ }
+		}
+		__threadfence();
+	}
+	__syncthreads();
+}
+#define GRID_SYNC() grid_barrier(bar, gridDim.x)
 
 // K10 + K11 in one persistent launch.
-__global__ void __launch_bounds__(256) k_colour_solve(DBodies B, DArbs A, DJoints J, DRows R, DColour K, DCounters *C, int iterations, double dt, double dt_coef)
+__global__ void __launch_bounds__(256) k_colour_solve(DBodies B, DArbs A, DJoints J, DRows R, DColour K, DCounters *C, unsigned *bar, int iterations, double dt, double dt_coef)
 {
-	cg::grid_group grid = cg::this_grid();
 	const int tid = CPB_TID, nth = CPB_NTHREADS;
 	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
 
 	// K10: colouring rounds
 	for(int round = 0; round < CPB_MAX_COLOUR_ROUNDS; round++){
 		colour_phase_a(B, A, J, K, nA, round, tid, nth);
-		grid.sync();
+		GRID_SYNC();
 		colour_phase_b(B, A, J, K, C, nA, round, tid, nth);
-		grid.sync();
+		GRID_SYNC();
 		if(*((volatile int *)&K.remaining[round]) == 0) break;
 	}
 	if(tid == 0) colour_starts(K);
-	grid.sync();
+	GRID_SYNC();
 	build_rows(A, J, R, K, nA, tid, nth);
-	grid.sync();
+	GRID_SYNC();
 
 	// K11: warm start then iterations, colour by colour
 	int ncol = *((volatile int *)&C->n_colours);
@@ -261,11 +298,11 @@ __global__ void __launch_bounds__(256) k_colour_solve(DBodies B, DArbs A, DJoint
 		int mode = (pass == 0 ? 0 : 1);
 		for(int c = 0; c < nreg; c++){
 			solve_colour(B, R, J, K, c, mode, dt, dt_coef, tid, nth);
-			grid.sync();
+			GRID_SYNC();
 		}
 		if(has_overflow){
 			if(tid == 0) solve_overflow(B, R, J, K, mode, dt, dt_coef);
-			grid.sync();
+			GRID_SYNC();
 		}
 	}
 	int n_rows = K.cstart[CPB_MAX_COLOURS];

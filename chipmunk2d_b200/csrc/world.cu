@@ -107,6 +107,8 @@ struct cpb200_world {
 	cudaEvent_t ev[ST_COUNT + 1];
 	float stage_us[ST_COUNT];
 
+	unsigned *d_barrier;    // grid barrier words of the persistent solver
+	int last_active;        // active arbiters seen at the last host read-back (grid sizing hint)
 	double *d_scratch;      // small scratch (collide_one output, stats)
 	double *h_scratch;      // pinned
 };
@@ -182,7 +184,7 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 		int per_sm = 1;
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colour_solve, 256, 0);
 		if(per_sm < 1) per_sm = 1;
-		if(per_sm > 4) per_sm = 4;
+		if(per_sm > 2) per_sm = 2;
 		w->coop_blocks = w->sm_count*per_sm;
 	}
 #endif
@@ -209,6 +211,8 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	cudaMalloc(&p, sizeof(DSpace)*(size_t)n_spaces); w->d_spaces = (DSpace *)p;
 	cudaMalloc(&p, sizeof(DCounters)); w->C = (DCounters *)p; cudaMemsetAsync(w->C, 0, sizeof(DCounters), w->stream);
 	cudaMallocHost(&p, sizeof(DCounters)); w->hC = (DCounters *)p; memset(w->hC, 0, sizeof(DCounters));
+	cudaMalloc(&p, sizeof(unsigned)*8); w->d_barrier = (unsigned *)p; cudaMemsetAsync(w->d_barrier, 0, sizeof(unsigned)*8, w->stream);
+	w->last_active = 0;
 	cudaMalloc(&p, sizeof(double)*64); w->d_scratch = (double *)p;
 	cudaMallocHost(&p, sizeof(double)*64); w->h_scratch = (double *)p;
 	if(!w->d_spaces || !w->C || !w->hC){ cpb_set_error("device allocation failed"); delete w; return NULL; }
@@ -221,6 +225,7 @@ extern "C" void cpb200_world_destroy(cpb200_world *w)
 	cudaSetDevice(w->device);
 	cudaStreamSynchronize(w->stream);
 	w->gB.release(); w->gS.release(); w->gJ.release(); w->gA.release(); w->gK.release(); w->gV.release(); w->gP.release(); w->gI.release();
+	cudaFree(w->d_barrier);
 	cudaFree(w->d_spaces); cudaFree(w->C); cudaFreeHost(w->hC); cudaFree(w->d_scratch); cudaFreeHost(w->h_scratch);
 	if(w->d_order) cudaFree(w->d_order);
 	if(w->d_user_order) cudaFree(w->d_user_order);
@@ -687,9 +692,13 @@ extern "C" int cpb200_world_step(cpb200_world *w, double dt)
 		cudaMemsetAsync(K.remaining, 0, sizeof(int)*(CPB_MAX_COLOUR_ROUNDS + 1), st);
 #ifndef CPB_EMU
 		{
-			DCounters *C = w->C; DRows R = w->R;
-			void *args[] = {&B, &Ac, &J, &R, &K, &C, &iterations, &dt, &dt_coef};
-			CPB_CHECK(cudaLaunchCooperativeKernel((void *)k_colour_solve, dim3(w->coop_blocks), dim3(256), args, 0, st));
+			DCounters *C = w->C; DRows R = w->R; unsigned *bar = w->d_barrier;
+			// size the persistent grid to the work: ~256 rows of one colour per CTA, never more than
+			// what is co-resident (148 SMs x 2 CTAs of 256 threads)
+			int est_cons = std::max(w->last_active, nb/2) + J.n;
+			int blocks = std::max(1, std::min(w->coop_blocks, cpb_div_up(est_cons/4 + 1, 256)));
+			void *args[] = {&B, &Ac, &J, &R, &K, &C, &bar, &iterations, &dt, &dt_coef};
+			CPB_CHECK(cudaLaunchCooperativeKernel((void *)k_colour_solve, dim3(blocks), dim3(256), args, 0, st));
 		}
 #else
 		{
@@ -731,6 +740,7 @@ extern "C" int cpb200_world_sync(cpb200_world *w)
 	if(world_sync(w)) return -1;
 	CPB_CHECK(cudaMemcpyAsync(w->hC, w->C, sizeof(DCounters), cudaMemcpyDeviceToHost, w->stream));
 	CPB_CHECK(cudaStreamSynchronize(w->stream));
+	w->last_active = w->hC->n_active;
 	if(w->hC->overflow){
 		cpb_set_error("device buffer overflow (flags 0x%x: 1 pairs, 2 arbiters, 4 table, 8 bvh stack); call cpb200_world_reserve with larger capacities", w->hC->overflow);
 		return -2;
@@ -884,6 +894,7 @@ extern "C" int cpb200_world_get_stats(cpb200_world *w, cpb200_stats *out)
 	out->n_bodies = (uint32_t)w->B.n; out->n_shapes = (uint32_t)w->S.n; out->n_joints = (uint32_t)w->J.n;
 	out->n_awake = *(unsigned *)(w->h_scratch + 2);
 	out->n_pairs = (uint32_t)(w->hC->n_pairs[0] + w->hC->n_pairs[1] + w->hC->n_pairs[2]);
+	w->last_active = w->hC->n_active;
 	out->n_arbiters = (uint32_t)w->hC->n_active; out->n_contacts = (uint32_t)w->hC->n_contacts;
 	out->n_cached = (uint32_t)w->hC->n_cached; out->n_colours = (uint32_t)w->hC->n_colours; out->overflow = (uint32_t)w->hC->overflow;
 	out->kinetic_energy = w->h_scratch[0]; out->max_penetration = w->h_scratch[1];

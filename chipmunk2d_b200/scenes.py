@@ -111,22 +111,33 @@ def moment_for_poly(m, verts):
     return (m * sum1) / (6.0 * sum2)
 
 
-def circle_pile(n, seed=88172645463325252, sleep=0.5, columns=None, radius=5.0, iterations=10):
+def circle_pile(n, seed=88172645463325252, sleep=0.5, columns=None, radius=5.0, iterations=10, dense=False):
     """Config 4: n radius-5 circles (demo/Bench.c add_circle: m = r^2/25, e = 0, u = 0.9) on a
     jittered hexagonal grid inside a floor+walls container; sleeping enabled."""
     rng = XorShift64(seed)
     if columns is None:
         columns = max(8, int(math.sqrt(n) * 1.5))
-    pitch = 2.0 * radius * 1.05
     rows = int(math.ceil(n / columns))
-    width = columns * pitch + pitch
-    height = rows * pitch * 0.95 + 4 * pitch
     idx = np.arange(n)
     col = idx % columns
     row = idx // columns
-    jitter = (rng.uniform(2 * n).reshape(n, 2) - 0.5) * 0.4
-    x = pitch * 0.75 + col * pitch + (row % 2) * (pitch * 0.5) * 0.9 + jitter[:, 0]
-    y = radius + 1.0 + row * pitch * 0.95 + jitter[:, 1]
+    if dense:
+        # hexagonal close packing with a 0.2 % gap: the pile is (nearly) settled from step one,
+        # ~3 contacts per body, which is what the 1M-circle benchmark is specified on
+        pitch = 2.0 * radius * 1.002
+        rowh = pitch * math.sqrt(3.0) / 2.0 * 1.001
+        jitter = (rng.uniform(2 * n).reshape(n, 2) - 0.5) * 0.004
+        width = columns * pitch + pitch * 0.5 + 2.0 * radius * 0.004 + 0.02
+        height = rows * rowh + 4 * pitch
+        x = radius + 0.01 + col * pitch + (row % 2) * (pitch * 0.5) + jitter[:, 0]
+        y = radius + 0.01 + row * rowh + jitter[:, 1]
+    else:
+        pitch = 2.0 * radius * 1.05
+        width = columns * pitch + pitch
+        height = rows * pitch * 0.95 + 4 * pitch
+        jitter = (rng.uniform(2 * n).reshape(n, 2) - 0.5) * 0.4
+        x = pitch * 0.75 + col * pitch + (row % 2) * (pitch * 0.5) * 0.9 + jitter[:, 0]
+        y = radius + 1.0 + row * pitch * 0.95 + jitter[:, 1]
     bodies = np.zeros(n + 1, dtype=SCENE_BODY)
     bodies[0] = _static_body()[0]
     m = radius * radius / 25.0

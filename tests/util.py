@@ -33,9 +33,32 @@ def match_arbiters(ref_rows, ref_hash_hi, dev):
         yield r, hi, d, (d is not None and int(r[0]) != int(d["shape_a"]))
 
 
-def lockstep(ref_space, world, dt, steps, check=None):
-    """Step the oracle and the device side by side with the device solving in the oracle's order."""
+def oracle_body_descs(ref_rows, scene, dev_state):
+    """refp_get_bodies rows -> cpb200_body_desc records (sleep bookkeeping taken from the device)."""
+    from chipmunk2d_b200.engine import BODY_DESC
+    n = len(ref_rows)
+    d = np.zeros(n, dtype=BODY_DESC)
+    r = np.nan_to_num(ref_rows, nan=0.0, posinf=np.inf, neginf=-np.inf)
+    d["p"] = r[:, 0:2]; d["v"] = r[:, 2:4]; d["a"] = r[:, 4]; d["w"] = r[:, 5]
+    d["v_bias"] = r[:, 6:8]; d["w_bias"] = r[:, 8]; d["f"] = r[:, 9:11]; d["t"] = r[:, 11]
+    d["rot"] = r[:, 12:14]
+    d["idle_time"] = r[:, 18]
+    d["m"] = scene.bodies["m"]; d["i"] = scene.bodies["i"]; d["cog"] = scene.bodies["cog"]
+    d["type"] = scene.bodies["type"]
+    d["sleeping"] = dev_state["sleeping"]; d["sleep_group"] = dev_state["sleep_group"]
+    # row 0 (the space's static body) is not reported by cpSpaceEachBody: keep the scene's values
+    d["rot"][0] = (1.0, 0.0); d["idle_time"][0] = np.inf
+    return d
+
+
+def lockstep(ref_space, world, dt, steps, check=None, resync_scene=None):
+    """Step the oracle and the device side by side with the device solving in the oracle's order.
+    With resync_scene the device's body state is overwritten with the oracle's before every step, so
+    each step is a one-step parity check from identical inputs (arbiter warm-start state stays the
+    device's own)."""
     for s in range(steps):
+        if resync_scene is not None:
+            world.update_bodies(0, oracle_body_descs(ref_space.priv_bodies(), resync_scene, world.bodies()))
         asleep = np.nan_to_num(ref_space.priv_bodies()[:, 19]).astype(np.uint8)
         ref_space.step(dt)
         arbs, hi = ref_space.priv_arbiters()
