@@ -108,7 +108,11 @@ __global__ void k_sleep_union(DBodies B, DIslands I, DArbs A, DJoints J)
 		for(;;){
 			int ra = uf_find(I.parent, a), rb = uf_find(I.parent, b);
 			if(ra == rb) break;
-			if(ra < rb){ int t = ra; ra = rb; rb = t; }
+			// randomised linking: the root with the smaller hash goes under the other one, which keeps
+			// the expected tree depth logarithmic whatever the body numbering (index-ordered linking
+			// degenerates into chains as long as a row of the pile)
+			uint64_t ha = mix64((uint64_t)ra), hb = mix64((uint64_t)rb);
+			if(ha > hb || (ha == hb && ra < rb)){ int t = ra; ra = rb; rb = t; }
 			if(atomicCAS(&I.parent[ra], ra, rb) == ra) break;
 		}
 	}

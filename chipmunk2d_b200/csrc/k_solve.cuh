@@ -30,6 +30,16 @@ struct DColour {
 	int *remaining;              // [CPB_MAX_COLOUR_ROUNDS + 1]
 };
 
+// Words that other CTAs update while the persistent kernel runs are read through L2 (ld.cg) and
+// updated with atomics, never through a possibly stale L1 line.
+#ifndef CPB_EMU
+__device__ __forceinline__ unsigned long long ld_u64(const unsigned long long *p){ return __ldcg(p); }
+__device__ __forceinline__ double ld_f64(const double *p){ return __ldcg(p); }
+#else
+static inline unsigned long long ld_u64(const unsigned long long *p){ return *p; }
+static inline double ld_f64(const double *p){ return *p; }
+#endif
+
 CPB_DEVICE bool body_is_dynamic(const DBodies &B, int b){ V2 mi = B.MI[b]; return mi.x != 0.0 || mi.y != 0.0; }
 
 // unified constraint index c: [0, nA) arbiter records, [nA, nA + nJ) joints
@@ -67,15 +77,15 @@ CPB_DEVICE void colour_phase_b(const DBodies &B, const DArbs &A, const DJoints &
 		if(!cons_fetch(A, J, nA, c, a, b, pri, col) || col >= 0) continue;
 		unsigned long long bid = ((unsigned long long)(round + 1) << 56) | pri;
 		bool da = body_is_dynamic(B, a), db = body_is_dynamic(B, b);
-		bool win = (!da || K.claim[a] == bid) && (!db || K.claim[b] == bid);
+		bool win = (!da || ld_u64(&K.claim[a]) == bid) && (!db || ld_u64(&K.claim[b]) == bid);
 		if(!win){ lost++; continue; }
-		unsigned long long m = (da ? K.bmask[a] : 0ull) | (db ? K.bmask[b] : 0ull);
+		unsigned long long m = (da ? ld_u64(&K.bmask[a]) : 0ull) | (db ? ld_u64(&K.bmask[b]) : 0ull);
 		unsigned long long freebits = ~m & ((1ull << CPB_OVERFLOW_COLOUR) - 1ull);
 		int colour = (freebits ? __ffsll((long long)freebits) - 1 : CPB_OVERFLOW_COLOUR);
 		if(colour != CPB_OVERFLOW_COLOUR){
 			unsigned long long bit = 1ull << colour;
-			if(da) K.bmask[a] |= bit;
-			if(db) K.bmask[b] |= bit;
+			if(da) atomicOr(&K.bmask[a], bit);
+			if(db) atomicOr(&K.bmask[b], bit);
 		}
 		if(c < nA){ A.colour[c] = colour; atomicAdd(&K.ccount[colour], 1); }
 		else { J.colour[c - nA] = colour; atomicAdd(&K.jcount[colour], 1); }
@@ -240,7 +250,7 @@ CPB_DEVICE void rows_writeback(const DArbs &A, const DRows &R, int n_rows, int t
 		int cnt = R.cnt[r]; if(cnt < 0) cnt = -cnt;
 		for(int k = 0; k < cnt; k++){
 			int s = 2*i + k, d = k*R.cap + r;
-			A.jn[s] = R.jn[d]; A.jt[s] = R.jt[d]; A.jb[s] = R.jb[d];
+			A.jn[s] = ld_f64(&R.jn[d]); A.jt[s] = ld_f64(&R.jt[d]); A.jb[s] = ld_f64(&R.jb[d]);
 		}
 	}
 }

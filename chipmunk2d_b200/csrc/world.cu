@@ -108,6 +108,7 @@ struct cpb200_world {
 	float stage_us[ST_COUNT];
 
 	unsigned *d_barrier;    // grid barrier words of the persistent solver
+	int force_blocks;       // validation hook: fixed persistent grid size (0 = automatic)
 	int last_active;        // active arbiters seen at the last host read-back (grid sizing hint)
 	double *d_scratch;      // small scratch (collide_one output, stats)
 	double *h_scratch;      // pinned
@@ -212,7 +213,7 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	cudaMalloc(&p, sizeof(DCounters)); w->C = (DCounters *)p; cudaMemsetAsync(w->C, 0, sizeof(DCounters), w->stream);
 	cudaMallocHost(&p, sizeof(DCounters)); w->hC = (DCounters *)p; memset(w->hC, 0, sizeof(DCounters));
 	cudaMalloc(&p, sizeof(unsigned)*8); w->d_barrier = (unsigned *)p; cudaMemsetAsync(w->d_barrier, 0, sizeof(unsigned)*8, w->stream);
-	w->last_active = 0;
+	w->last_active = 0; w->force_blocks = 0;
 	cudaMalloc(&p, sizeof(double)*64); w->d_scratch = (double *)p;
 	cudaMallocHost(&p, sizeof(double)*64); w->h_scratch = (double *)p;
 	if(!w->d_spaces || !w->C || !w->hC){ cpb_set_error("device allocation failed"); delete w; return NULL; }
@@ -695,8 +696,9 @@ extern "C" int cpb200_world_step(cpb200_world *w, double dt)
 			DCounters *C = w->C; DRows R = w->R; unsigned *bar = w->d_barrier;
 			// size the persistent grid to the work: ~256 rows of one colour per CTA, never more than
 			// what is co-resident (148 SMs x 2 CTAs of 256 threads)
-			int est_cons = std::max(w->last_active, nb/2) + J.n;
-			int blocks = std::max(1, std::min(w->coop_blocks, cpb_div_up(est_cons/4 + 1, 256)));
+			int est_cons = std::max(w->last_active, nb) + J.n;
+			int blocks = std::max(1, std::min(w->coop_blocks, cpb_div_up(est_cons + 1, 256)));
+			if(w->force_blocks > 0) blocks = std::min(w->coop_blocks, w->force_blocks);
 			void *args[] = {&B, &Ac, &J, &R, &K, &C, &bar, &iterations, &dt, &dt_coef};
 			CPB_CHECK(cudaLaunchCooperativeKernel((void *)k_colour_solve, dim3(blocks), dim3(256), args, 0, st));
 		}
@@ -944,6 +946,13 @@ extern "C" int cpb200_world_set_arbiter_order(cpb200_world *w, int n, const uint
 	if(n) CPB_CHECK(cudaMemcpyAsync(w->d_user_order, order, sizeof(uint64_t)*(size_t)n, cudaMemcpyHostToDevice, w->stream));
 	w->n_user_order = n;
 	return world_sync(w);
+}
+
+extern "C" int cpb200_world_set_solver_grid(cpb200_world *w, int blocks)
+{
+	if(!w || blocks < 0){ cpb_set_error("bad arguments"); return -1; }
+	w->force_blocks = blocks;
+	return 0;
 }
 
 extern "C" int cpb200_world_set_joint_order(cpb200_world *w, int n, const int32_t *order)

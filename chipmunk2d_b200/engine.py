@@ -110,6 +110,7 @@ def load_engine(path=None):
     lib.cpb200_world_set_solver_mode.argtypes = [vp, ci]
     lib.cpb200_world_set_arbiter_order.argtypes = [vp, ci, vp]
     lib.cpb200_world_set_joint_order.argtypes = [vp, ci, vp]
+    lib.cpb200_world_set_solver_grid.argtypes = [vp, ci]
     lib.cpb200_world_collide_pair.argtypes = [vp, ci, ci, vp]
     lib.cpb200_world_get_stage_times.argtypes = [vp, ci, vp]
     lib.cpb200_stage_name.restype = C.c_char_p
@@ -318,6 +319,9 @@ class World:
     def set_arbiter_order(self, order):
         order = np.ascontiguousarray(order, dtype=np.uint64)
         self._ck(self.lib.cpb200_world_set_arbiter_order(self.w, len(order), order.ctypes.data))
+
+    def set_solver_grid(self, blocks):
+        self._ck(self.lib.cpb200_world_set_solver_grid(self.w, int(blocks)))
 
     def set_joint_order(self, order):
         order = np.ascontiguousarray(order, dtype=np.int32)

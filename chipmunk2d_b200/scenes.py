@@ -122,11 +122,12 @@ def circle_pile(n, seed=88172645463325252, sleep=0.5, columns=None, radius=5.0, 
     col = idx % columns
     row = idx // columns
     if dense:
-        # hexagonal close packing with a 0.2 % gap: the pile is (nearly) settled from step one,
-        # ~3 contacts per body, which is what the 1M-circle benchmark is specified on
-        pitch = 2.0 * radius * 1.002
-        rowh = pitch * math.sqrt(3.0) / 2.0 * 1.001
-        jitter = (rng.uniform(2 * n).reshape(n, 2) - 0.5) * 0.004
+        # hexagonal close packing with a 0.1 % overlap (well inside collisionSlop, so no push-out):
+        # every circle touches its six neighbours from step one -- ~3 contacts per body, the settled
+        # pile the 1M-circle benchmark is specified on
+        pitch = 2.0 * radius * 0.999
+        rowh = pitch * math.sqrt(3.0) / 2.0
+        jitter = (rng.uniform(2 * n).reshape(n, 2) - 0.5) * 0.002
         width = columns * pitch + pitch * 0.5 + 2.0 * radius * 0.004 + 0.02
         height = rows * rowh + 4 * pitch
         x = radius + 0.01 + col * pitch + (row % 2) * (pitch * 0.5) + jitter[:, 0]

@@ -217,6 +217,9 @@ CPB200_API int cpb200_world_set_solver_mode(cpb200_world *w, int mode);
 /* order[n] = (shape index a)<<32 | (shape index b) in the sequence the reference pushed
  * its arbiters; pairs not listed are solved afterwards in key order. Applies to the next step only. */
 CPB200_API int cpb200_world_set_arbiter_order(cpb200_world *w, int n, const uint64_t *order);
+/* Force the persistent coloured solver to run on `blocks` CTAs (0 = size automatically).  Results do
+ * not depend on the grid size; the determinism test runs 1 CTA against the full grid. */
+CPB200_API int cpb200_world_set_solver_grid(cpb200_world *w, int blocks);
 /* Serial mode only: order[n] = joint indices in the sequence the reference holds them in
  * space->constraints (sleeping reorders that array); joints not listed follow in upload order.
  * Applies to the next step only. */

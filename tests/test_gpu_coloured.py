@@ -29,6 +29,22 @@ def test_coloured_is_deterministic():
     assert np.array_equal(a["p"], b["p"]) and np.array_equal(a["v"], b["v"]) and np.array_equal(a["a"], b["a"])
 
 
+@pytest.mark.parametrize("name", ["ComplexTerrainHexagons_1000", "Chains", "PyramidStack"])
+def test_result_independent_of_solver_grid(name):
+    """Colours are race-free: one CTA and the full persistent grid give bit-identical states."""
+    sc = golden_scene(name)
+    out = []
+    for blocks in (1, 7, 0, 1000):
+        w = World(1)
+        w.load_scene(sc)
+        w.set_solver_grid(blocks)
+        w.step(sc.dt, 200)
+        w.sync()
+        out.append(w.bodies())
+    for b in out[1:]:
+        assert np.array_equal(out[0]["p"], b["p"]) and np.array_equal(out[0]["v"], b["v"]) and np.array_equal(out[0]["w"], b["w"])
+
+
 @pytest.mark.parametrize("name", ["SimpleTerrainCircles_1000", "ComplexTerrainHexagons_1000", "SimpleTerrainBoxes_1000"])
 def test_bench_scene_statistics(name):
     sc = golden_scene(name)
