@@ -149,7 +149,7 @@ __global__ void k_arb_carry(DBodies B, DArbs prev, DArbs cur, DTable cur_table, 
 		int i = base + threadIdx.x;
 		bool keep = false;
 		int new_state = 0, new_active = 0;
-		if(i < n_prev && !prev.seen[i]){
+		if(i < n_prev && !prev.seen[i] && prev.key[i] != ~0ull){ // ~0 = a shape of this record was removed
 			int ba = prev.ba[i], bb = prev.bb[i];
 			bool a_rest = (B.type[ba] == CPB200_BODY_STATIC) || B.sleeping[ba];
 			bool b_rest = (B.type[bb] == CPB200_BODY_STATIC) || B.sleeping[bb];

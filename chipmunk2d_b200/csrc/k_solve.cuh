@@ -28,6 +28,7 @@ struct DColour {
 	int *ccount, *cstart, *ccursor;   // [CPB_MAX_COLOURS + 1] arbiters per colour
 	int *jcount, *jstart, *jcursor;   // [CPB_MAX_COLOURS + 1] joints per colour
 	int *remaining;              // [CPB_MAX_COLOUR_ROUNDS + 1]
+	unsigned long long *prof;    // [8] globaltimer stamps of the persistent kernel (start, coloured, rows built, warm start done, end) + rounds
 };
 
 // Words that other CTAs update while the persistent kernel runs are read through L2 (ld.cg) and
@@ -280,6 +281,8 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned nblocks)
 	__syncthreads();
 }
 #define GRID_SYNC() grid_barrier(bar, gridDim.x)
+__device__ __forceinline__ unsigned long long global_ns(){ unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PROF(i) do { if(tid == 0) K.prof[i] = global_ns(); } while(0)
 
 // K10 + K11 in one persistent launch.
 __global__ void __launch_bounds__(256) k_colour_solve(DBodies B, DArbs A, DJoints J, DRows R, DColour K, DCounters *C, unsigned *bar, int iterations, double dt, double dt_coef)
@@ -287,18 +290,23 @@ __global__ void __launch_bounds__(256) k_colour_solve(DBodies B, DArbs A, DJoint
 	const int tid = CPB_TID, nth = CPB_NTHREADS;
 	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
 
+	PROF(0);
 	// K10: colouring rounds
+	int rounds_done = 0;
 	for(int round = 0; round < CPB_MAX_COLOUR_ROUNDS; round++){
+		rounds_done = round + 1;
 		colour_phase_a(B, A, J, K, nA, round, tid, nth);
 		GRID_SYNC();
 		colour_phase_b(B, A, J, K, C, nA, round, tid, nth);
 		GRID_SYNC();
 		if(*((volatile int *)&K.remaining[round]) == 0) break;
 	}
-	if(tid == 0) colour_starts(K);
+	PROF(1);
+	if(tid == 0){ colour_starts(K); K.prof[5] = (unsigned long long)rounds_done; }
 	GRID_SYNC();
 	build_rows(A, J, R, K, nA, tid, nth);
 	GRID_SYNC();
+	PROF(2);
 
 	// K11: warm start then iterations, colour by colour
 	int ncol = *((volatile int *)&C->n_colours);
@@ -314,7 +322,9 @@ __global__ void __launch_bounds__(256) k_colour_solve(DBodies B, DArbs A, DJoint
 			if(tid == 0) solve_overflow(B, R, J, K, mode, dt, dt_coef);
 			GRID_SYNC();
 		}
+		if(pass == 0) PROF(3);
 	}
+	PROF(4);
 	int n_rows = K.cstart[CPB_MAX_COLOURS];
 	rows_writeback(A, R, n_rows, tid, nth);
 }

@@ -298,7 +298,7 @@ extern "C" int cpb200_world_set_bodies(cpb200_world *w, int n, const cpb200_body
 	DA(w->gK, w->K.claim, n); DA(w->gK, w->K.bmask, n);
 	DA(w->gK, w->K.ccount, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.cstart, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.ccursor, CPB_MAX_COLOURS + 1);
 	DA(w->gK, w->K.jcount, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.jstart, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.jcursor, CPB_MAX_COLOURS + 1);
-	DA(w->gK, w->K.remaining, CPB_MAX_COLOUR_ROUNDS + 1);
+	DA(w->gK, w->K.remaining, CPB_MAX_COLOUR_ROUNDS + 1); DA(w->gK, w->K.prof, 8);
 	w->gI.release();
 	DA(w->gI, w->I.parent, n); DA(w->gI, w->I.wake, n); DA(w->gI, w->I.comp_active, n); DA(w->gI, w->I.woken, n);
 	int r = cpb200_world_update_bodies(w, 0, n, bodies);
@@ -385,6 +385,12 @@ extern "C" int cpb200_world_set_shapes(cpb200_world *w, int n, const cpb200_shap
 	cudaSetDevice(w->device);
 	if(world_sync(w)) return -1;
 	size_t N = (size_t)n, NV = (size_t)n_verts;
+	// arbiter records refer to shapes/bodies by index: remember which hashid each old index had so the
+	// cached records can be re-pointed after this re-upload (warm-start data survives structural edits)
+	std::vector<uint32_t> old_hashid;
+	if(w->steps > 0 && w->S.n > 0 && w->cap_arbs > 0){
+		if(download(w, old_hashid, w->S.hashid, (size_t)w->S.n) || world_sync(w)) return -1;
+	}
 	std::vector<int> type(N), body(N), sensor(N), pcount(N), poff(N);
 	std::vector<uint32_t> hashid(N), cat(N), mask(N), hlocal(N);
 	std::vector<int> body_space;
@@ -450,6 +456,29 @@ extern "C" int cpb200_world_set_shapes(cpb200_world *w, int n, const cpb200_shap
 	if(want_arbs > w->cap_arbs){
 		// growing drops the cached arbiters (warm-start data); callers that care reserve up front
 		if(alloc_arbs(w, want_arbs)) return -1;
+	} else if(!old_hashid.empty()){
+		DArbs &A = w->A[w->cur];
+		int n_rec = 0;
+		CPB_CHECK(cudaMemcpyAsync(&n_rec, A.count_ptr, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
+		if(world_sync(w)) return -1;
+		n_rec = std::min(n_rec, A.cap);
+		if(n_rec > 0){
+			uint32_t max_hash = 0;
+			for(size_t i = 0; i < N; i++) max_hash = std::max(max_hash, hashid[i]);
+			std::vector<int> by_hash((size_t)max_hash + 1, -1);
+			for(size_t i = 0; i < N; i++) by_hash[hashid[i]] = (int)i;
+			std::vector<int> sa, sb, ba, bb; std::vector<uint64_t> key;
+			if(download(w, sa, A.sa, (size_t)n_rec) || download(w, sb, A.sb, (size_t)n_rec) || download(w, key, A.key, (size_t)n_rec) || world_sync(w)) return -1;
+			ba.resize((size_t)n_rec); bb.resize((size_t)n_rec);
+			for(int i = 0; i < n_rec; i++){
+				int na = -1, nb = -1;
+				if(sa[i] >= 0 && (size_t)sa[i] < old_hashid.size() && old_hashid[sa[i]] <= max_hash) na = by_hash[old_hashid[sa[i]]];
+				if(sb[i] >= 0 && (size_t)sb[i] < old_hashid.size() && old_hashid[sb[i]] <= max_hash) nb = by_hash[old_hashid[sb[i]]];
+				if(na < 0 || nb < 0){ key[i] = ~0ull; sa[i] = sb[i] = 0; ba[i] = bb[i] = 0; } // a shape was removed: record dies in the next carry pass
+				else { sa[i] = na; sb[i] = nb; ba[i] = body[(size_t)na]; bb[i] = body[(size_t)nb]; }
+			}
+			if(upload(w, A.sa, sa) || upload(w, A.sb, sb) || upload(w, A.ba, ba) || upload(w, A.bb, bb) || upload(w, A.key, key)) return -1;
+		}
 	}
 	w->cache_dirty = true;
 	return world_sync(w);
@@ -815,7 +844,7 @@ extern "C" int cpb200_world_get_arbiters(cpb200_world *w, int cap, cpb200_arbite
 			cpb200_arbiter &o = out[m];
 			memset(&o, 0, sizeof(o));
 			o.shape_a = sa[i]; o.shape_b = sb[i]; o.body_a = ba[i]; o.body_b = bb[i];
-			o.count = (active[i] ? cnt[i] : 0); o.state = state[i]; o.stamp = stamp[i]; o.active = (active[i] == 1);
+			o.count = (active[i] ? cnt[i] : 0); o.state = state[i]; o.stamp = stamp[i]; o.active = active[i];
 			o.n[0] = nn[i].x; o.n[1] = nn[i].y; o.e = e[i]; o.u = u[i]; o.surface_vr[0] = svr[i].x; o.surface_vr[1] = svr[i].y;
 			for(int k = 0; k < 2; k++){
 				size_t c = 2*i + (size_t)k;
@@ -985,6 +1014,17 @@ extern "C" int cpb200_world_get_stage_times(cpb200_world *w, int cap, float *use
 	if(!w) return -1;
 	for(int i = 0; i < ST_COUNT && i < cap; i++) usec[i] = w->stage_us[i];
 	return ST_COUNT;
+}
+
+extern "C" int cpb200_world_get_solver_profile(cpb200_world *w, double *usec5)
+{
+	if(!w || !w->K.prof){ cpb_set_error("no solver profile"); return -1; }
+	unsigned long long t[8];
+	CPB_CHECK(cudaMemcpyAsync(t, w->K.prof, sizeof(t), cudaMemcpyDeviceToHost, w->stream));
+	if(world_sync(w)) return -1;
+	for(int i = 0; i < 4; i++) usec5[i] = (double)(t[i + 1] - t[i])*1e-3;
+	usec5[4] = (double)t[5];
+	return 0;
 }
 
 extern "C" int cpb200_world_set_profiling(cpb200_world *w, int on)

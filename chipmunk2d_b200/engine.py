@@ -116,6 +116,7 @@ def load_engine(path=None):
     lib.cpb200_stage_name.restype = C.c_char_p
     lib.cpb200_stage_name.argtypes = [ci]
     lib.cpb200_world_set_profiling.argtypes = [vp, ci]
+    lib.cpb200_world_get_solver_profile.argtypes = [vp, vp]
     _lib_cache[path] = lib
     return lib
 
@@ -334,6 +335,11 @@ class World:
 
     def set_profiling(self, on):
         self._ck(self.lib.cpb200_world_set_profiling(self.w, int(bool(on))))
+
+    def solver_profile(self):
+        buf = np.zeros(5)
+        self._ck(self.lib.cpb200_world_get_solver_profile(self.w, buf.ctypes.data))
+        return dict(zip(['colour_us', 'rows_us', 'warm_us', 'iterate_us', 'rounds'], buf.tolist()))
 
     def stage_times(self):
         buf = np.zeros(32, dtype=np.float32)

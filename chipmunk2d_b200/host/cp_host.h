@@ -1,0 +1,183 @@
+/* cp_host.h -- private object model of the C99 host layer.
+ *
+ * The host keeps plain C mirrors of the user's objects (what the reference keeps in
+ * chipmunk_structs.h); the simulation state itself lives in SoA device buffers behind the
+ * C ABI of include/cpb200.h.  Coherence protocol (SURVEY.md 8b "host-visible state"):
+ *   - structural edits and parameter setters mark the space dirty; cpSpaceStep uploads before
+ *     stepping (full re-upload for structure, body-state upload for kinematic setters);
+ *   - after a step the mirrors are stale; the first getter downloads body state, shape AABBs,
+ *     arbiters or joint impulses on demand.
+ */
+#ifndef CP_HOST_H
+#define CP_HOST_H
+
+#include "chipmunk/chipmunk.h"
+#include "chipmunk/cpHastySpace.h"
+#include "cpb200.h"
+
+enum { CP_CIRCLE_SHAPE = 0, CP_SEGMENT_SHAPE = 1, CP_POLY_SHAPE = 2 };
+
+/* numerically equal to CPB200_ARB_* and to the reference's enum cpArbiterState */
+enum {
+	CP_ARBITER_STATE_FIRST_COLLISION = 0, CP_ARBITER_STATE_NORMAL = 1, CP_ARBITER_STATE_IGNORE = 2,
+	CP_ARBITER_STATE_CACHED = 3, CP_ARBITER_STATE_INVALIDATED = 4
+};
+
+struct cpBody {
+	cpSpace *space;
+	cpFloat m, m_inv, i, i_inv;
+	cpVect cog, p, v, f;
+	cpFloat a, w, t;
+	cpTransform transform;
+	cpVect v_bias;
+	cpFloat w_bias;
+	cpDataPointer userData;
+	cpBodyVelocityFunc velocity_func;
+	cpBodyPositionFunc position_func;
+	cpShape *shapeList;
+	cpConstraint *constraintList;
+	cpFloat idleTime;          /* INFINITY <=> static (cpBody.c:136-146) */
+	cpBody *sleepRoot;         /* non-NULL <=> asleep; all members of a sleeping component share it */
+	int index;                 /* slot in space->bodies == device body index, -1 when not in a space */
+	int firstArb;              /* head of this body's arbiter list in space->arbs, -1 = none */
+};
+
+struct cpShapeMassInfo { cpFloat m, i; cpVect cog; cpFloat area; };
+
+struct cpShape {
+	int klass;                 /* CP_*_SHAPE */
+	cpSpace *space;
+	cpBody *body;
+	struct cpShapeMassInfo massInfo;
+	cpBB bb;
+	cpBool sensor;
+	cpFloat e, u;
+	cpVect surfaceV;
+	cpDataPointer userData;
+	cpCollisionType type;
+	cpShapeFilter filter;
+	cpShape *next, *prev;      /* body's shape list */
+	cpHashValue hashid;
+	int index;                 /* slot in space->shapes == device shape index */
+};
+
+struct cpCircleShape { cpShape shape; cpVect c, tc; cpFloat r; };
+struct cpSegmentShape { cpShape shape; cpVect a, b, n, ta, tb, tn; cpFloat r; cpVect a_tangent, b_tangent; };
+struct cpPolyShape { cpShape shape; cpFloat r; int count; cpVect *verts, *normals, *tverts, *tnormals; };
+
+/* every joint class shares one record; cpPinJoint etc. are this struct under another tag */
+struct cpConstraint {
+	int klass;                 /* CPB200_JOINT_* */
+	cpSpace *space;
+	cpBody *a, *b;
+	cpConstraint *next_a, *next_b;
+	cpFloat maxForce, errorBias, maxBias;
+	cpBool collideBodies;
+	cpConstraintPreSolveFunc preSolve;
+	cpConstraintPostSolveFunc postSolve;
+	cpDataPointer userData;
+	cpVect anchorA, anchorB;   /* groove: anchorA = grv_a */
+	cpFloat prm[4];            /* packing of cpb200_joint_desc.prm */
+	cpVect acc;                /* accumulated impulse mirror */
+	cpFloat impulse;           /* getImpulse mirror */
+	void *forceFunc;           /* spring force / torque function (default = NULL) */
+	int index;
+};
+struct cpPinJoint { cpConstraint constraint; };
+struct cpSlideJoint { cpConstraint constraint; };
+struct cpPivotJoint { cpConstraint constraint; };
+struct cpGrooveJoint { cpConstraint constraint; };
+struct cpDampedSpring { cpConstraint constraint; };
+struct cpDampedRotarySpring { cpConstraint constraint; };
+struct cpRotaryLimitJoint { cpConstraint constraint; };
+struct cpRatchetJoint { cpConstraint constraint; };
+struct cpGearJoint { cpConstraint constraint; };
+struct cpSimpleMotor { cpConstraint constraint; };
+
+struct cpContact { cpVect r1, r2; cpFloat nMass, tMass, bounce, jnAcc, jtAcc, jBias, bias; cpHashValue hash; };
+
+struct cpArbiter {
+	cpSpace *space;
+	cpFloat e, u;
+	cpVect surface_vr;
+	cpDataPointer data;
+	cpShape *a, *b;
+	cpBody *body_a, *body_b;
+	int count;
+	struct cpContact contacts[CP_MAX_CONTACTS_PER_ARBITER];
+	cpVect n;
+	cpCollisionHandler *handler;
+	cpBool swapped;
+	cpTimestamp stamp;
+	int state;
+	int active;
+	int next_a, next_b;        /* per-body lists (indices into space->arbs) */
+};
+
+typedef struct cpPostStepCallback { cpPostStepFunc func; void *key; void *data; } cpPostStepCallback;
+
+struct cpSpace {
+	int iterations;
+	cpVect gravity;
+	cpFloat damping;
+	cpFloat idleSpeedThreshold, sleepTimeThreshold;
+	cpFloat collisionSlop, collisionBias;
+	cpTimestamp collisionPersistence;
+	cpDataPointer userData;
+	cpTimestamp stamp;
+	cpFloat curr_dt;
+	int locked;
+	cpHashValue shapeIDCounter;
+
+	cpBody *staticBody;
+	cpBody _staticBody;
+	cpBody **bodies; int nBodies, capBodies;              /* bodies[0] is always staticBody */
+	cpShape **shapes; int nShapes, capShapes;
+	cpConstraint **constraints; int nConstraints, capConstraints;
+
+	cpCollisionHandler *handlers; int nHandlers, capHandlers;
+	cpCollisionHandler defaultHandler;
+	cpBool usesWildcards, hasDefaultHandler;
+	cpPostStepCallback *postStep; int nPostStep, capPostStep;
+	cpBool skipPostStep;
+
+	/* device side */
+	cpb200_world *world;
+	int device;
+	int solverMode;
+	cpBool topologyDirty;      /* bodies/shapes/joints added, removed or re-parameterised */
+	cpBool bodiesDirty;        /* kinematic state of some body changed on the host */
+	cpBool paramsDirty;
+	cpBool hostStale;          /* device has newer body state than the mirrors */
+	cpBool bbStale, arbStale, jointStale;
+	cpArbiter *arbs; int nArbs, capArbs;
+
+	cpBool hasty;
+	unsigned long hastyThreads;
+};
+
+/* internal helpers */
+void cpSpaceFetchBodiesB200(cpSpace *space);
+void cpSpaceFetchArbitersB200(cpSpace *space);
+void cpSpaceFetchJointsB200(cpSpace *space);
+void cpSpaceFetchBBsB200(cpSpace *space);
+void cpSpaceMarkTopologyDirty(cpSpace *space);
+void cpBodySetTransformInternal(cpBody *body, cpVect p, cpFloat a);
+void cpBodyAccumulateMassFromShapes(cpBody *body);
+void cpBodyAddShape(cpBody *body, cpShape *shape);
+void cpBodyRemoveShape(cpBody *body, cpShape *shape);
+void cpBodyAddConstraint(cpBody *body, cpConstraint *constraint);
+void cpBodyRemoveConstraint(cpBody *body, cpConstraint *constraint);
+void cpEngineError(const char *what);
+
+static inline cpConstraint *cpConstraintNext(cpConstraint *node, cpBody *body){ return (node->a == body ? node->next_a : node->next_b); }
+
+/* make sure the mirrors of `body` are current before the host reads or edits them */
+static inline void cpBodySyncForRead(const cpBody *body){ if(body->space && body->space->hostStale) cpSpaceFetchBodiesB200(body->space); }
+
+#define cpAssertSpaceUnlocked(space) \
+	cpAssertHard(!(space)->locked, \
+		"This operation cannot be done safely during a call to cpSpaceStep() or during a query. " \
+		"Put these calls into a post-step callback.");
+
+#endif

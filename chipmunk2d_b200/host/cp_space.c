@@ -1,0 +1,726 @@
+/* cp_space.c -- cpSpace / cpHastySpace on top of the C ABI (include/cpb200.h).
+ *
+ * Replaces reference src/cpSpace.c (lifecycle, registries, handlers) and the host half of
+ * src/cpSpaceStep.c / src/cpHastySpace.c: cpSpaceStep() uploads whatever changed on the host,
+ * enqueues ONE device step (every stage of cpSpaceStep.c:335-445 is a CUDA kernel) and marks the
+ * mirrors stale.  User callbacks run on the host after the device step from downloaded state:
+ *   - constraint preSolve before the step, postSolve after it (Chains' breakable joints);
+ *   - collision handlers begin / preSolve / postSolve / separate in that order per arbiter,
+ *     observational (their return values cannot retro-actively filter the finished solve);
+ *   - post-step callbacks exactly like cpSpaceUnlock(space, true) (cpSpaceStep.c:84-103).
+ */
+#include <string.h>
+#include <stdio.h>
+
+#include "cp_host.h"
+
+static int g_default_device = -1;
+
+void cpSpaceSetDefaultDeviceB200(int device){ g_default_device = device; }
+
+static int
+default_device(void)
+{
+	if(g_default_device >= 0) return g_default_device;
+	const char *env = getenv("CPB200_DEVICE");
+	return (env ? atoi(env) : 0);
+}
+
+static void *
+grow(void *arr, int *cap, int need, size_t elt)
+{
+	if(need <= *cap) return arr;
+	int ncap = (*cap ? *cap : 16);
+	while(ncap < need) ncap *= 2;
+	arr = cprealloc(arr, elt*(size_t)ncap);
+	*cap = ncap;
+	return arr;
+}
+
+/* ---- lifecycle (cpSpace.c:105-229) ---- */
+static cpBool handler_true(cpArbiter *arb, cpSpace *space, cpDataPointer data){ (void)arb; (void)space; (void)data; return cpTrue; }
+static void handler_nothing(cpArbiter *arb, cpSpace *space, cpDataPointer data){ (void)arb; (void)space; (void)data; }
+static const cpCollisionHandler handler_do_nothing = {CP_WILDCARD_COLLISION_TYPE, CP_WILDCARD_COLLISION_TYPE, handler_true, handler_true, handler_nothing, handler_nothing, NULL};
+
+cpSpace *cpSpaceAlloc(void){ return (cpSpace *)cpcalloc(1, sizeof(cpSpace)); }
+
+cpSpace *
+cpSpaceInit(cpSpace *space)
+{
+	memset(space, 0, sizeof(*space));
+	space->iterations = 10;
+	space->gravity = cpvzero;
+	space->damping = 1.0;
+	space->collisionSlop = 0.1;
+	space->collisionBias = cpfpow(1.0 - 0.1, 60.0);
+	space->collisionPersistence = 3;
+	space->idleSpeedThreshold = 0.0;
+	space->sleepTimeThreshold = INFINITY;
+	space->device = default_device();
+	memcpy(&space->defaultHandler, &handler_do_nothing, sizeof(cpCollisionHandler));
+
+	cpBody *staticBody = cpBodyInit(&space->_staticBody, 0.0, 0.0);
+	cpBodySetType(staticBody, CP_BODY_TYPE_STATIC);
+	space->staticBody = staticBody;
+	space->bodies = (cpBody **)grow(NULL, &space->capBodies, 16, sizeof(cpBody *));
+	space->bodies[0] = staticBody;
+	space->nBodies = 1;
+	staticBody->space = space;
+	staticBody->index = 0;
+	space->topologyDirty = cpTrue;
+	space->paramsDirty = cpTrue;
+	return space;
+}
+
+cpSpace *cpSpaceNew(void){ return cpSpaceInit(cpSpaceAlloc()); }
+
+void
+cpSpaceDestroy(cpSpace *space)
+{
+	/* like the reference, the space never owns bodies/shapes/constraints (cpSpace.c:188-229) */
+	for(int i = 0; i < space->nBodies; i++){ space->bodies[i]->space = NULL; space->bodies[i]->index = -1; }
+	for(int i = 0; i < space->nShapes; i++){ space->shapes[i]->space = NULL; space->shapes[i]->index = -1; }
+	for(int i = 0; i < space->nConstraints; i++){ space->constraints[i]->space = NULL; space->constraints[i]->index = -1; }
+	if(space->world) cpb200_world_destroy(space->world);
+	space->world = NULL;
+	cpfree(space->bodies); cpfree(space->shapes); cpfree(space->constraints);
+	cpfree(space->handlers); cpfree(space->postStep); cpfree(space->arbs);
+	space->bodies = NULL; space->shapes = NULL; space->constraints = NULL;
+	space->handlers = NULL; space->postStep = NULL; space->arbs = NULL;
+}
+
+void cpSpaceFree(cpSpace *space){ if(space){ cpSpaceDestroy(space); cpfree(space); } }
+
+/* ---- properties (cpSpace.c:231-381) ---- */
+#define SPACE_PROP(ctype, Name, field) \
+	ctype cpSpaceGet##Name(const cpSpace *space){ return space->field; } \
+	void cpSpaceSet##Name(cpSpace *space, ctype value){ space->field = value; space->paramsDirty = cpTrue; }
+SPACE_PROP(cpVect, Gravity, gravity)
+SPACE_PROP(cpFloat, IdleSpeedThreshold, idleSpeedThreshold)
+SPACE_PROP(cpFloat, SleepTimeThreshold, sleepTimeThreshold)
+SPACE_PROP(cpTimestamp, CollisionPersistence, collisionPersistence)
+SPACE_PROP(cpDataPointer, UserData, userData)
+int cpSpaceGetIterations(const cpSpace *space){ return space->iterations; }
+void cpSpaceSetIterations(cpSpace *space, int iterations){ cpAssertHard(iterations > 0, "Iterations must be positive and non-zero."); space->iterations = iterations; space->paramsDirty = cpTrue; }
+cpFloat cpSpaceGetDamping(const cpSpace *space){ return space->damping; }
+void cpSpaceSetDamping(cpSpace *space, cpFloat damping){ cpAssertHard(damping >= 0.0, "Damping must be positive."); space->damping = damping; space->paramsDirty = cpTrue; }
+cpFloat cpSpaceGetCollisionSlop(const cpSpace *space){ return space->collisionSlop; }
+void cpSpaceSetCollisionSlop(cpSpace *space, cpFloat collisionSlop){ space->collisionSlop = collisionSlop; space->paramsDirty = cpTrue; }
+cpFloat cpSpaceGetCollisionBias(const cpSpace *space){ return space->collisionBias; }
+void cpSpaceSetCollisionBias(cpSpace *space, cpFloat collisionBias){ space->collisionBias = collisionBias; space->paramsDirty = cpTrue; }
+cpBody *cpSpaceGetStaticBody(const cpSpace *space){ return space->staticBody; }
+cpFloat cpSpaceGetCurrentTimeStep(const cpSpace *space){ return space->curr_dt; }
+cpBool cpSpaceIsLocked(cpSpace *space){ return (space->locked > 0); }
+void cpSpaceMarkTopologyDirty(cpSpace *space){ space->topologyDirty = cpTrue; }
+void cpSpaceSetSolverModeB200(cpSpace *space, int mode){ space->solverMode = mode; space->paramsDirty = cpTrue; }
+
+/* ---- collision handlers (cpSpace.c:383-413) ---- */
+static cpCollisionHandler *
+add_handler(cpSpace *space, cpCollisionType a, cpCollisionType b)
+{
+	for(int i = 0; i < space->nHandlers; i++){
+		cpCollisionHandler *h = &space->handlers[i];
+		if((h->typeA == a && h->typeB == b) || (h->typeA == b && h->typeB == a)) return h;
+	}
+	cpAssertHard(space->nHandlers < 256, "Too many collision handlers (the handler table is fixed so that returned pointers stay valid).");
+	if(!space->handlers){ space->handlers = (cpCollisionHandler *)cpcalloc(256, sizeof(cpCollisionHandler)); space->capHandlers = 256; }
+	cpCollisionHandler init = {a, b, handler_true, handler_true, handler_nothing, handler_nothing, NULL};
+	memcpy(&space->handlers[space->nHandlers], &init, sizeof(init));
+	return &space->handlers[space->nHandlers++];
+}
+
+cpCollisionHandler *
+cpSpaceAddDefaultCollisionHandler(cpSpace *space)
+{
+	space->hasDefaultHandler = cpTrue;
+	return &space->defaultHandler;
+}
+
+cpCollisionHandler *cpSpaceAddCollisionHandler(cpSpace *space, cpCollisionType a, cpCollisionType b){ return add_handler(space, a, b); }
+
+cpCollisionHandler *
+cpSpaceAddWildcardHandler(cpSpace *space, cpCollisionType type)
+{
+	space->usesWildcards = cpTrue;
+	return add_handler(space, type, CP_WILDCARD_COLLISION_TYPE);
+}
+
+cpCollisionHandler *
+cpSpaceLookupWildcardB200(cpSpace *space, cpCollisionType type)
+{
+	for(int i = 0; i < space->nHandlers; i++){
+		cpCollisionHandler *h = &space->handlers[i];
+		if(h->typeA == type && h->typeB == CP_WILDCARD_COLLISION_TYPE) return h;
+	}
+	return NULL;
+}
+
+static cpCollisionHandler *
+lookup_handler(cpSpace *space, cpCollisionType a, cpCollisionType b)
+{
+	for(int i = 0; i < space->nHandlers; i++){
+		cpCollisionHandler *h = &space->handlers[i];
+		if(h->typeB == CP_WILDCARD_COLLISION_TYPE) continue;
+		if((h->typeA == a && h->typeB == b) || (h->typeA == b && h->typeB == a)) return h;
+	}
+	return &space->defaultHandler;
+}
+
+/* ---- registries (cpSpace.c:415-571) ---- */
+cpBody *
+cpSpaceAddBody(cpSpace *space, cpBody *body)
+{
+	cpAssertHard(body->space != space, "You have already added this body to this space. You must not add it a second time.");
+	cpAssertHard(!body->space, "You have already added this body to another space. You cannot add it to a second.");
+	cpAssertSpaceUnlocked(space);
+	space->bodies = (cpBody **)grow(space->bodies, &space->capBodies, space->nBodies + 1, sizeof(cpBody *));
+	body->index = space->nBodies;
+	space->bodies[space->nBodies++] = body;
+	body->space = space;
+	space->topologyDirty = cpTrue;
+	return body;
+}
+
+cpShape *
+cpSpaceAddShape(cpSpace *space, cpShape *shape)
+{
+	cpAssertHard(shape->space != space, "You have already added this shape to this space. You must not add it a second time.");
+	cpAssertHard(!shape->space, "You have already added this shape to another space. You cannot add it to a second.");
+	cpAssertHard(shape->body, "The shape's body is not defined.");
+	cpAssertHard(shape->body->space == space, "The shape's body must be added to the space before the shape.");
+	cpAssertSpaceUnlocked(space);
+	cpBody *body = shape->body;
+	cpBodyActivate(body);
+	cpBodyAddShape(body, shape);
+	shape->hashid = space->shapeIDCounter++;
+	cpBodySyncForRead(body);
+	cpShapeUpdate(shape, body->transform);
+	space->shapes = (cpShape **)grow(space->shapes, &space->capShapes, space->nShapes + 1, sizeof(cpShape *));
+	shape->index = space->nShapes;
+	space->shapes[space->nShapes++] = shape;
+	shape->space = space;
+	space->topologyDirty = cpTrue;
+	return shape;
+}
+
+cpConstraint *
+cpSpaceAddConstraint(cpSpace *space, cpConstraint *constraint)
+{
+	cpAssertHard(constraint->space != space, "You have already added this constraint to this space. You must not add it a second time.");
+	cpAssertHard(!constraint->space, "You have already added this constraint to another space. You cannot add it to a second.");
+	cpAssertSpaceUnlocked(space);
+	cpBody *a = constraint->a, *b = constraint->b;
+	cpAssertHard(a != NULL && b != NULL, "Constraint is attached to a NULL body.");
+	cpAssertHard(a->space == space && b->space == space, "The constraint's bodies must be added to the space before the constraint.");
+	cpBodyActivate(a);
+	cpBodyActivate(b);
+	space->constraints = (cpConstraint **)grow(space->constraints, &space->capConstraints, space->nConstraints + 1, sizeof(cpConstraint *));
+	constraint->index = space->nConstraints;
+	space->constraints[space->nConstraints++] = constraint;
+	cpBodyAddConstraint(a, constraint);
+	cpBodyAddConstraint(b, constraint);
+	constraint->space = space;
+	space->topologyDirty = cpTrue;
+	return constraint;
+}
+
+/* before a structural edit the mirrors must hold the device's latest state, because the edit forces a
+ * full re-upload from them */
+static void
+sync_before_edit(cpSpace *space)
+{
+	if(space->hostStale) cpSpaceFetchBodiesB200(space);
+	if(space->jointStale) cpSpaceFetchJointsB200(space);
+	space->arbStale = cpTrue;
+}
+
+void
+cpSpaceRemoveShape(cpSpace *space, cpShape *shape)
+{
+	cpAssertHard(cpSpaceContainsShape(space, shape), "Cannot remove a shape that was not added to the space. (Removed twice maybe?)");
+	cpAssertSpaceUnlocked(space);
+	if((space->nHandlers > 0 || space->hasDefaultHandler) && space->world && !space->topologyDirty){
+		/* arbiters of the removed shape separate now (cpSpaceFilterArbiters, cpSpace.c:482-511) */
+		if(space->arbStale) cpSpaceFetchArbitersB200(space);
+		space->locked++;
+		for(int k = 0; k < space->nArbs; k++){
+			cpArbiter *arb = &space->arbs[k];
+			if((arb->a == shape || arb->b == shape) && arb->state != CP_ARBITER_STATE_CACHED && arb->stamp == space->stamp){
+				arb->state = CP_ARBITER_STATE_INVALIDATED;
+				arb->handler->separateFunc(arb, space, arb->handler->userData);
+			}
+		}
+		space->locked--;
+	}
+	sync_before_edit(space);
+	cpBody *body = shape->body;
+	cpBodyActivate(body);
+	cpBodyRemoveShape(body, shape);
+	int i = shape->index, last = --space->nShapes;
+	if(i != last){ space->shapes[i] = space->shapes[last]; space->shapes[i]->index = i; }
+	shape->space = NULL;
+	shape->index = -1;
+	space->topologyDirty = cpTrue;
+}
+
+void
+cpSpaceRemoveBody(cpSpace *space, cpBody *body)
+{
+	cpAssertHard(body != cpSpaceGetStaticBody(space), "Cannot remove the designated static body for the space.");
+	cpAssertHard(cpSpaceContainsBody(space, body), "Cannot remove a body that was not added to the space. (Removed twice maybe?)");
+	cpAssertSpaceUnlocked(space);
+	sync_before_edit(space);
+	cpBodyActivate(body);
+	int i = body->index, last = --space->nBodies;
+	if(i != last){ space->bodies[i] = space->bodies[last]; space->bodies[i]->index = i; }
+	body->space = NULL;
+	body->index = -1;
+	body->sleepRoot = NULL;
+	space->topologyDirty = cpTrue;
+}
+
+void
+cpSpaceRemoveConstraint(cpSpace *space, cpConstraint *constraint)
+{
+	cpAssertHard(cpSpaceContainsConstraint(space, constraint), "Cannot remove a constraint that was not added to the space. (Removed twice maybe?)");
+	cpAssertSpaceUnlocked(space);
+	sync_before_edit(space);
+	cpBodyActivate(constraint->a);
+	cpBodyActivate(constraint->b);
+	cpBodyRemoveConstraint(constraint->a, constraint);
+	cpBodyRemoveConstraint(constraint->b, constraint);
+	int i = constraint->index, last = --space->nConstraints;
+	if(i != last){ space->constraints[i] = space->constraints[last]; space->constraints[i]->index = i; }
+	constraint->space = NULL;
+	constraint->index = -1;
+	space->topologyDirty = cpTrue;
+}
+
+cpBool cpSpaceContainsShape(cpSpace *space, cpShape *shape){ return (shape->space == space); }
+cpBool cpSpaceContainsBody(cpSpace *space, cpBody *body){ return (body->space == space); }
+cpBool cpSpaceContainsConstraint(cpSpace *space, cpConstraint *constraint){ return (constraint->space == space); }
+
+/* ---- iteration (cpSpace.c:573-651) ---- */
+void
+cpSpaceEachBody(cpSpace *space, cpSpaceBodyIteratorFunc func, void *data)
+{
+	space->locked++;
+	for(int i = 1; i < space->nBodies; i++) func(space->bodies[i], data);
+	space->locked--;
+}
+
+void
+cpSpaceEachShape(cpSpace *space, cpSpaceShapeIteratorFunc func, void *data)
+{
+	space->locked++;
+	for(int i = 0; i < space->nShapes; i++) func(space->shapes[i], data);
+	space->locked--;
+}
+
+void
+cpSpaceEachConstraint(cpSpace *space, cpSpaceConstraintIteratorFunc func, void *data)
+{
+	space->locked++;
+	for(int i = 0; i < space->nConstraints; i++) func(space->constraints[i], data);
+	space->locked--;
+}
+
+/* the device rebuilds its broadphase from scratch every step; "reindexing" is a re-upload */
+void cpSpaceReindexStatic(cpSpace *space){ space->topologyDirty = cpTrue; }
+void cpSpaceReindexShape(cpSpace *space, cpShape *shape){ (void)shape; space->topologyDirty = cpTrue; }
+void cpSpaceReindexShapesForBody(cpSpace *space, cpBody *body){ (void)body; space->topologyDirty = cpTrue; }
+void cpSpaceUseSpatialHash(cpSpace *space, cpFloat dim, int count){ (void)space; (void)dim; (void)count; }
+
+cpBool
+cpSpaceAddPostStepCallback(cpSpace *space, cpPostStepFunc func, void *key, void *data)
+{
+	for(int i = 0; i < space->nPostStep; i++){ if(space->postStep[i].key == key) return cpFalse; }
+	space->postStep = (cpPostStepCallback *)grow(space->postStep, &space->capPostStep, space->nPostStep + 1, sizeof(cpPostStepCallback));
+	cpPostStepCallback cb = {func, key, data};
+	space->postStep[space->nPostStep++] = cb;
+	return cpTrue;
+}
+
+static void
+run_post_step_callbacks(cpSpace *space)
+{
+	if(space->locked != 0 || space->skipPostStep) return;
+	space->skipPostStep = cpTrue;
+	for(int i = 0; i < space->nPostStep; i++){
+		cpPostStepCallback cb = space->postStep[i];
+		space->postStep[i].func = NULL;
+		if(cb.func) cb.func(space, cb.key, cb.data);
+	}
+	space->nPostStep = 0;
+	space->skipPostStep = cpFalse;
+}
+
+/* ---- host <-> device ---- */
+static void
+ensure_world(cpSpace *space)
+{
+	if(space->world) return;
+	space->world = cpb200_world_create(space->device, 1);
+	if(!space->world) cpEngineError("cpb200_world_create");
+}
+
+static void
+fill_body_desc(cpb200_body_desc *d, const cpBody *b)
+{
+	memset(d, 0, sizeof(*d));
+	d->p[0] = b->p.x; d->p[1] = b->p.y; d->v[0] = b->v.x; d->v[1] = b->v.y; d->f[0] = b->f.x; d->f[1] = b->f.y;
+	d->a = b->a; d->w = b->w; d->t = b->t;
+	d->rot[0] = b->transform.a; d->rot[1] = b->transform.b;
+	d->m = b->m; d->i = b->i;
+	d->cog[0] = b->cog.x; d->cog[1] = b->cog.y;
+	d->v_bias[0] = b->v_bias.x; d->v_bias[1] = b->v_bias.y; d->w_bias = b->w_bias;
+	d->idle_time = b->idleTime;
+	d->type = (b->idleTime == INFINITY ? CPB200_BODY_STATIC : (b->m == INFINITY ? CPB200_BODY_KINEMATIC : CPB200_BODY_DYNAMIC));
+	d->space = 0;
+	d->sleeping = (b->sleepRoot != NULL);
+	d->sleep_group = (b->sleepRoot ? b->sleepRoot->index : -1);
+}
+
+static void
+upload_bodies(cpSpace *space, cpBool full)
+{
+	int n = space->nBodies;
+	cpb200_body_desc *descs = (cpb200_body_desc *)cpcalloc((size_t)n, sizeof(cpb200_body_desc));
+	for(int i = 0; i < n; i++) fill_body_desc(&descs[i], space->bodies[i]);
+	int rc = (full ? cpb200_world_set_bodies(space->world, n, descs) : cpb200_world_update_bodies(space->world, 0, n, descs));
+	cpfree(descs);
+	if(rc) cpEngineError("body upload");
+}
+
+static void
+upload_shapes(cpSpace *space)
+{
+	int n = space->nShapes, nv = 0;
+	for(int i = 0; i < n; i++){ if(space->shapes[i]->klass == CP_POLY_SHAPE) nv += ((cpPolyShape *)space->shapes[i])->count; }
+	cpb200_shape_desc *descs = (cpb200_shape_desc *)cpcalloc((size_t)(n ? n : 1), sizeof(cpb200_shape_desc));
+	double *verts = (double *)cpcalloc((size_t)(nv ? nv : 1), 2*sizeof(double));
+	int voff = 0;
+	for(int i = 0; i < n; i++){
+		cpShape *s = space->shapes[i];
+		cpb200_shape_desc *d = &descs[i];
+		d->type = s->klass;
+		cpAssertHard(s->body->space == space, "A shape's body was removed from the space while the shape is still in it.");
+		d->body = s->body->index;
+		d->hashid = (uint32_t)s->hashid;
+		d->sensor = s->sensor;
+		d->categories = s->filter.categories; d->mask = s->filter.mask; d->group = (uint64_t)s->filter.group;
+		d->collision_type = (uint64_t)s->type;
+		d->e = s->e; d->u = s->u;
+		d->surface_v[0] = s->surfaceV.x; d->surface_v[1] = s->surfaceV.y;
+		switch(s->klass){
+		case CP_CIRCLE_SHAPE: { cpCircleShape *c = (cpCircleShape *)s; d->r = c->r; d->a[0] = c->c.x; d->a[1] = c->c.y; break; }
+		case CP_SEGMENT_SHAPE: {
+			cpSegmentShape *g = (cpSegmentShape *)s;
+			d->r = g->r; d->a[0] = g->a.x; d->a[1] = g->a.y; d->b[0] = g->b.x; d->b[1] = g->b.y;
+			d->a_tangent[0] = g->a_tangent.x; d->a_tangent[1] = g->a_tangent.y; d->b_tangent[0] = g->b_tangent.x; d->b_tangent[1] = g->b_tangent.y;
+			break;
+		}
+		default: {
+			cpPolyShape *p = (cpPolyShape *)s;
+			d->r = p->r; d->n_verts = p->count; d->vert_offset = voff;
+			for(int k = 0; k < p->count; k++){ verts[2*(voff + k)] = p->verts[k].x; verts[2*(voff + k) + 1] = p->verts[k].y; }
+			voff += p->count;
+			break;
+		}
+		}
+	}
+	int rc = cpb200_world_set_shapes(space->world, n, descs, nv, verts);
+	cpfree(descs); cpfree(verts);
+	if(rc) cpEngineError("shape upload");
+}
+
+static void
+upload_joints(cpSpace *space)
+{
+	int n = space->nConstraints;
+	cpb200_joint_desc *descs = (cpb200_joint_desc *)cpcalloc((size_t)(n ? n : 1), sizeof(cpb200_joint_desc));
+	for(int i = 0; i < n; i++){
+		cpConstraint *c = space->constraints[i];
+		cpb200_joint_desc *d = &descs[i];
+		cpAssertHard(c->a->space == space && c->b->space == space, "A constraint's body was removed from the space while the constraint is still in it.");
+		d->type = c->klass; d->a = c->a->index; d->b = c->b->index;
+		d->collide_bodies = c->collideBodies;
+		d->max_force = c->maxForce; d->error_bias = c->errorBias; d->max_bias = c->maxBias;
+		d->anchor_a[0] = c->anchorA.x; d->anchor_a[1] = c->anchorA.y; d->anchor_b[0] = c->anchorB.x; d->anchor_b[1] = c->anchorB.y;
+		for(int k = 0; k < 4; k++) d->prm[k] = c->prm[k];
+		d->acc[0] = c->acc.x; d->acc[1] = c->acc.y;
+	}
+	int rc = cpb200_world_set_joints(space->world, n, descs);
+	cpfree(descs);
+	if(rc) cpEngineError("joint upload");
+}
+
+static void
+upload_params(cpSpace *space)
+{
+	cpb200_space_params p;
+	memset(&p, 0, sizeof(p));
+	p.gravity[0] = space->gravity.x; p.gravity[1] = space->gravity.y;
+	p.damping = space->damping;
+	p.idle_speed_threshold = space->idleSpeedThreshold;
+	p.sleep_time_threshold = space->sleepTimeThreshold;
+	p.collision_slop = space->collisionSlop;
+	p.collision_bias = space->collisionBias;
+	p.collision_persistence = space->collisionPersistence;
+	p.iterations = space->iterations;
+	if(cpb200_world_set_space_params(space->world, 0, &p)) cpEngineError("parameter upload");
+	if(cpb200_world_set_solver_mode(space->world, space->solverMode)) cpEngineError("solver mode");
+}
+
+static void
+sync_to_device(cpSpace *space)
+{
+	ensure_world(space);
+	if(space->topologyDirty){
+		if(space->hostStale) cpSpaceFetchBodiesB200(space);
+		if(space->jointStale) cpSpaceFetchJointsB200(space);
+		upload_bodies(space, cpTrue);
+		upload_shapes(space);
+		upload_joints(space);
+		space->topologyDirty = cpFalse;
+		space->bodiesDirty = cpFalse;
+	} else if(space->bodiesDirty){
+		upload_bodies(space, cpFalse);
+		space->bodiesDirty = cpFalse;
+	}
+	if(space->paramsDirty){ upload_params(space); space->paramsDirty = cpFalse; }
+}
+
+void
+cpSpaceFetchBodiesB200(cpSpace *space)
+{
+	if(!space->hostStale || !space->world){ space->hostStale = cpFalse; return; }
+	space->hostStale = cpFalse;
+	int n = space->nBodies;
+	cpb200_body_state *st = (cpb200_body_state *)cpcalloc((size_t)n, sizeof(cpb200_body_state));
+	if(cpb200_world_get_bodies(space->world, 0, n, st)) cpEngineError("body download");
+	for(int i = 0; i < n; i++){
+		cpBody *b = space->bodies[i];
+		const cpb200_body_state *s = &st[i];
+		if(b->idleTime == INFINITY) continue; /* static bodies never change on the device */
+		b->p = cpv(s->p[0], s->p[1]);
+		b->v = cpv(s->v[0], s->v[1]);
+		b->a = s->a;
+		b->w = s->w;
+		cpVect rot = cpv(s->rot[0], s->rot[1]), c = b->cog;
+		b->transform = cpTransformNewTranspose(
+			rot.x, -rot.y, b->p.x - (c.x*rot.x - c.y*rot.y),
+			rot.y,  rot.x, b->p.y - (c.x*rot.y + c.y*rot.x));
+		b->idleTime = s->idle_time;
+		b->sleepRoot = (s->sleeping && s->sleep_group >= 0 && s->sleep_group < n ? space->bodies[s->sleep_group] : NULL);
+		if(!s->sleeping){
+			/* the step consumed the forces and the bias velocities (cpBody.c:505-507, 518-519) */
+			if(b->m != INFINITY){ b->f = cpvzero; b->t = 0.0; }
+			b->v_bias = cpvzero; b->w_bias = 0.0;
+		}
+	}
+	cpfree(st);
+}
+
+void cpSpaceSyncB200(cpSpace *space){ cpSpaceFetchBodiesB200(space); }
+
+void
+cpSpaceFetchBBsB200(cpSpace *space)
+{
+	space->bbStale = cpFalse;
+	if(!space->world || space->nShapes == 0 || space->topologyDirty) return;
+	int n = space->nShapes;
+	double *bbs = (double *)cpcalloc((size_t)n, 4*sizeof(double));
+	if(cpb200_world_get_shape_bbs(space->world, 0, n, bbs)) cpEngineError("AABB download");
+	for(int i = 0; i < n; i++) space->shapes[i]->bb = cpBBNew(bbs[4*i], bbs[4*i + 1], bbs[4*i + 2], bbs[4*i + 3]);
+	cpfree(bbs);
+}
+
+void
+cpSpaceFetchJointsB200(cpSpace *space)
+{
+	space->jointStale = cpFalse;
+	if(!space->world || space->nConstraints == 0 || space->topologyDirty) return;
+	int n = space->nConstraints;
+	cpb200_joint_state *st = (cpb200_joint_state *)cpcalloc((size_t)n, sizeof(cpb200_joint_state));
+	if(cpb200_world_get_joints(space->world, 0, n, st)) cpEngineError("joint download");
+	for(int i = 0; i < n; i++){
+		cpConstraint *c = space->constraints[i];
+		c->acc = cpv(st[i].acc[0], st[i].acc[1]);
+		c->impulse = st[i].impulse;
+		if(c->klass == CPB200_JOINT_RATCHET) c->prm[0] = st[i].aux;
+	}
+	cpfree(st);
+}
+
+void
+cpSpaceFetchArbitersB200(cpSpace *space)
+{
+	space->arbStale = cpFalse;
+	for(int i = 0; i < space->nBodies; i++) space->bodies[i]->firstArb = -1;
+	space->nArbs = 0;
+	if(!space->world || space->topologyDirty) return;
+	/* everything in the cache: active, dormant (sleeping) and cached-for-persistence records */
+	int n = cpb200_world_get_arbiters(space->world, 0, NULL, 0);
+	if(n < 0) cpEngineError("arbiter download");
+	if(n == 0) return;
+	cpb200_arbiter *recs = (cpb200_arbiter *)cpcalloc((size_t)n, sizeof(cpb200_arbiter));
+	n = cpb200_world_get_arbiters(space->world, n, recs, 0);
+	if(n < 0) cpEngineError("arbiter download");
+	space->arbs = (cpArbiter *)grow(space->arbs, &space->capArbs, n, sizeof(cpArbiter));
+	if(space->hostStale) cpSpaceFetchBodiesB200(space);
+	for(int i = 0; i < n; i++){
+		const cpb200_arbiter *r = &recs[i];
+		if(r->shape_a < 0 || r->shape_a >= space->nShapes || r->shape_b < 0 || r->shape_b >= space->nShapes) continue;
+		cpArbiter *arb = &space->arbs[space->nArbs];
+		memset(arb, 0, sizeof(*arb));
+		arb->space = space;
+		arb->a = space->shapes[r->shape_a]; arb->b = space->shapes[r->shape_b];
+		arb->body_a = arb->a->body; arb->body_b = arb->b->body;
+		arb->e = r->e; arb->u = r->u;
+		arb->surface_vr = cpv(r->surface_vr[0], r->surface_vr[1]);
+		arb->n = cpv(r->n[0], r->n[1]);
+		arb->count = r->count;
+		arb->state = r->state;
+		arb->stamp = r->stamp;
+		arb->active = r->active;
+		for(int k = 0; k < 2; k++){
+			struct cpContact *c = &arb->contacts[k];
+			c->r1 = cpv(r->contacts[k].r1[0], r->contacts[k].r1[1]);
+			c->r2 = cpv(r->contacts[k].r2[0], r->contacts[k].r2[1]);
+			c->nMass = r->contacts[k].n_mass; c->tMass = r->contacts[k].t_mass;
+			c->bounce = r->contacts[k].bounce; c->bias = r->contacts[k].bias;
+			c->jnAcc = r->contacts[k].jn_acc; c->jtAcc = r->contacts[k].jt_acc; c->jBias = r->contacts[k].j_bias;
+			c->hash = (cpHashValue)r->contacts[k].hash;
+		}
+		cpCollisionHandler *h = lookup_handler(space, arb->a->type, arb->b->type);
+		arb->handler = h;
+		/* cpArbiterUpdate (cpArbiter.c:402-404) */
+		arb->swapped = (arb->a->type != h->typeA && h->typeA != CP_WILDCARD_COLLISION_TYPE);
+		arb->next_a = arb->next_b = -1;
+		/* thread onto both bodies: only arbiters that take part in the contact graph (active this step,
+		 * or dormant ones of sleeping bodies: r->count is kept for those) */
+		if(r->active || (r->count > 0 && r->state != CP_ARBITER_STATE_CACHED && (arb->body_a->sleepRoot || arb->body_b->sleepRoot))){
+			int k = space->nArbs;
+			arb->next_a = arb->body_a->firstArb; arb->body_a->firstArb = k;
+			arb->next_b = arb->body_b->firstArb; arb->body_b->firstArb = k;
+		}
+		space->nArbs++;
+	}
+	cpfree(recs);
+}
+
+void
+cpSpaceCollidePairB200(cpSpace *space, const cpShape *a, const cpShape *b, cpContactPointSet *out)
+{
+	sync_to_device(space);
+	double buf[13];
+	if(cpb200_world_collide_pair(space->world, a->index, b->index, buf) < 0) cpEngineError("cpShapesCollide");
+	out->count = (int)buf[0];
+	out->normal = cpv(buf[1], buf[2]);
+	for(int k = 0; k < out->count && k < CP_MAX_CONTACTS_PER_ARBITER; k++){
+		out->points[k].pointA = cpv(buf[3 + 5*k], buf[4 + 5*k]);
+		out->points[k].pointB = cpv(buf[5 + 5*k], buf[6 + 5*k]);
+		out->points[k].distance = buf[7 + 5*k];
+	}
+}
+
+/* ---- callbacks that need downloaded state ---- */
+static cpBool
+space_has_collision_callbacks(const cpSpace *space)
+{
+	return (space->nHandlers > 0 || space->hasDefaultHandler);
+}
+
+static void
+run_collision_callbacks(cpSpace *space)
+{
+	cpSpaceFetchArbitersB200(space);
+	for(int i = 0; i < space->nArbs; i++){
+		cpArbiter *arb = &space->arbs[i];
+		cpCollisionHandler *h = arb->handler;
+		if(arb->state == CP_ARBITER_STATE_CACHED){
+			/* became cached this step <=> last touched on the previous stamp (cpSpaceStep.c:309-314) */
+			if(arb->stamp + 1 == space->stamp) h->separateFunc(arb, space, h->userData);
+			continue;
+		}
+		if(arb->stamp != space->stamp) continue;
+		if(arb->state == CP_ARBITER_STATE_FIRST_COLLISION) h->beginFunc(arb, space, h->userData);
+		h->preSolveFunc(arb, space, h->userData);
+		if(arb->active == 1) h->postSolveFunc(arb, space, h->userData);
+	}
+}
+
+/* ---- the step ---- */
+static void
+step_once(cpSpace *space, cpFloat dt, cpBool callbacks)
+{
+	if(callbacks){
+		space->locked++;
+		for(int i = 0; i < space->nConstraints; i++){
+			cpConstraint *c = space->constraints[i];
+			if(c->preSolve) c->preSolve(c, space);
+		}
+		space->locked--;
+	}
+	sync_to_device(space);
+	if(cpb200_world_step(space->world, dt)) cpEngineError("cpSpaceStep");
+	space->stamp++;
+	space->curr_dt = dt;
+	space->hostStale = cpTrue;
+	space->bbStale = cpTrue;
+	space->arbStale = cpTrue;
+	space->jointStale = cpTrue;
+	if(callbacks){
+		space->locked++;
+		cpBool any = cpFalse;
+		for(int i = 0; i < space->nConstraints; i++){ if(space->constraints[i]->postSolve){ any = cpTrue; break; } }
+		if(any){
+			cpSpaceFetchJointsB200(space);
+			for(int i = 0; i < space->nConstraints; i++){
+				cpConstraint *c = space->constraints[i];
+				if(c->postSolve) c->postSolve(c, space);
+			}
+		}
+		if(space_has_collision_callbacks(space)) run_collision_callbacks(space);
+		space->locked--;
+		run_post_step_callbacks(space);
+	}
+}
+
+void
+cpSpaceStep(cpSpace *space, cpFloat dt)
+{
+	if(dt == 0.0) return; /* cpSpaceStep.c:339 */
+	cpAssertHard(space->locked == 0, "cpSpaceStep() cannot be called from inside a callback of the same space.");
+	step_once(space, dt, cpTrue);
+}
+
+void
+cpSpaceStepManyB200(cpSpace *space, cpFloat dt, int n)
+{
+	if(dt == 0.0) return;
+	for(int i = 0; i < n; i++) step_once(space, dt, (i == n - 1));
+}
+
+/* ---- cpHastySpace (reference cpHastySpace.c:513-700) ---- */
+cpSpace *
+cpHastySpaceNew(void)
+{
+	cpSpace *space = cpSpaceNew();
+	space->hasty = cpTrue;
+	space->hastyThreads = 1;
+	return space;
+}
+
+void cpHastySpaceFree(cpSpace *space){ cpSpaceFree(space); }
+
+void
+cpHastySpaceSetThreads(cpSpace *space, unsigned long threads)
+{
+	/* recorded only: the solver already runs on all SMs of the device */
+	space->hastyThreads = (threads == 0 ? 1 : threads);
+}
+
+unsigned long cpHastySpaceGetThreads(cpSpace *space){ return space->hastyThreads; }
+void cpHastySpaceStep(cpSpace *space, cpFloat dt){ cpSpaceStep(space, dt); }

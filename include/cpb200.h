@@ -122,7 +122,8 @@ typedef struct cpb200_arbiter {
 	int32_t count;                /* 0 for cached / sensor / rejected arbiters */
 	int32_t state;                /* CPB200_ARB_* */
 	uint32_t stamp;
-	int32_t active;               /* 1 = solved this step (pushed to space->arbiters, cpSpaceStep.c:274) */
+	int32_t active;               /* 1 = solved this step (pushed to space->arbiters, cpSpaceStep.c:274); 2 = dormant: kept with
+	                               * its contacts while its bodies sleep (cpSpaceComponent.c:94-105); 0 = inactive */
 	double n[2];
 	double e, u;
 	double surface_vr[2];
@@ -231,6 +232,9 @@ CPB200_API int cpb200_world_collide_pair(cpb200_world *w, int shape_a, int shape
  * cpb200_stage_name(i).  Returns the number of stages. */
 CPB200_API int cpb200_world_get_stage_times(cpb200_world *w, int cap, float *usec);
 CPB200_API const char *cpb200_stage_name(int i);
+/* Inside the persistent colour+solve kernel of the last step (device globaltimer): microseconds spent
+ * colouring, building rows, warm starting, iterating; usec5[4] = colouring rounds. */
+CPB200_API int cpb200_world_get_solver_profile(cpb200_world *w, double *usec5);
 /* Enable (1) / disable (0) per-stage event timing (adds syncs; off by default). */
 CPB200_API int cpb200_world_set_profiling(cpb200_world *w, int on);
 

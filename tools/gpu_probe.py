@@ -34,6 +34,7 @@ def probe(label, scenes, warm, steps):
     print("%-28s bodies %8d load %.1fs  %.3f ms/step  %.3e body-steps/s  arbs %d contacts %d colours %d pairs %d awake %d overflow %d" % (
         label, nb, t_load, dt_ms, nb / (dt_ms * 1e-3), st["n_arbiters"], st["n_contacts"], st["n_colours"], st["n_pairs"], st["n_awake"], st["overflow"]))
     print("    stages(us): " + "  ".join("%s %.0f" % (k, v) for k, v in acc.items()), flush=True)
+    print("    solver: " + "  ".join("%s %.0f" % (k, v) for k, v in w.solver_profile().items()), flush=True)
     w.close()
 
 
