@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the cpSpaceStep hot path on B200 (one JSON line; see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload pile1m|batch|c1|c2|mixed100k] [--impl ours|reference]
+
+Workloads (BASELINE.json configs):
+  pile1m     config 4: 1 000 000 radius-5 circles, settled hexagonal pile, single space, iterations 10,
+             dt 1/60 (the north star's roofline target; DEFAULT).  A single space does not shard
+             (SURVEY.md 8e): with N GPUs every rank steps its own replica ("replicas only").
+  batch      config 5: independent PyramidStack / Chains spaces, 4096 per GPU, sharded by space index with no
+             data-path collective (weak scaling); step statistics are reduced over NCCL.
+  c1 / c2    configs 1 / 2 (demo/Bench.c scenes, 1000 bodies): latency-bound, reported for completeness.
+  mixed100k  config 3.
+
+A "step" is one cpSpaceStep of the whole workload.  `value` = non-static bodies x steps / device seconds with
+everything resident in HBM (CUDA events on the engine's stream, max over ranks).  `e2e` = the same metric
+through the public Chipmunk2D C API with host buffers: every step writes a force into every body (H2D),
+calls cpSpaceStep and reads every position back (D2H).
+`--impl reference` times the unmodified reference (oracle/_ref, cpSpaceStep, CPU) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# cpu sample: the reference needs ~20 s just to BUILD a 100k-circle space (BBTree inserts) and ~0.6 s per
+# step there; a 20k-circle pile of the same packing steps in ~75 ms, so K steps stay within a minute.
+REF_SAMPLE_BODIES = 20000
+
+
+def rank_info():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def build_scenes(workload, rank, for_reference=False):
+    from chipmunk2d_b200.scenes import circle_pile, mixed_drop, batched_demo_scenes, golden_scene
+    if workload == "pile1m":
+        n = REF_SAMPLE_BODIES if for_reference else 1000000
+        return [circle_pile(n, dense=True, sleep=np.inf)], {"workload": "config4_circle_pile_1M_single_space", "bodies_per_gpu": n,
+                                                             "iterations": 10, "dt": 1.0 / 60.0, "sleeping": "off (threshold inf) so every body is solved every step"}
+    if workload == "pile1m_sleep":
+        n = REF_SAMPLE_BODIES if for_reference else 1000000
+        return [circle_pile(n, dense=True, sleep=0.5)], {"workload": "config4_circle_pile_1M_single_space_sleeping_on", "bodies_per_gpu": n, "iterations": 10, "dt": 1.0 / 60.0}
+    if workload == "batch":
+        n = 64 if for_reference else 4096
+        sc = batched_demo_scenes(n)
+        return sc, {"workload": "config5_batched_PyramidStack_Chains_spaces", "spaces_per_gpu": n, "bodies_per_gpu": sum(s.n_dynamic() for s in sc),
+                    "iterations": 30, "dt": 1.0 / 180.0}
+    if workload == "c1":
+        return [golden_scene("SimpleTerrainCircles_1000")], {"workload": "config1_simple_terrain_circles_1000", "bodies_per_gpu": 1000, "iterations": 10, "dt": 1.0 / 60.0}
+    if workload == "c2":
+        return [golden_scene("ComplexTerrainHexagons_1000")], {"workload": "config2_complex_terrain_hexagons_1000", "bodies_per_gpu": 1000, "iterations": 10, "dt": 1.0 / 60.0}
+    if workload == "mixed100k":
+        n = REF_SAMPLE_BODIES if for_reference else 100000
+        return [mixed_drop(n)], {"workload": "config3_mixed_100k_with_springs_and_pivots", "bodies_per_gpu": n, "iterations": 10, "dt": 1.0 / 60.0}
+    raise SystemExit("unknown workload %r" % workload)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 9 for k in range(4) if r[5 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def algorithmic_bytes_solver(n_contacts, n_joints, iterations):
+    """384 B per contact-iteration + 192 B per contact of warm start (+ ~300 B per joint pass)."""
+    return 384.0 * iterations * n_contacts + 192.0 * n_contacts + 300.0 * (iterations + 1) * n_joints
+
+
+def cpu_baseline_sample(workload, steps, warmup):
+    """The unmodified reference (oracle/_ref) on a bounded sample of the workload, one thread."""
+    from oracle import ref as oref
+    if not oref.available():
+        return None
+    scenes, cfg = build_scenes(workload, 0, for_reference=True)
+    r = oref.Ref()
+    spaces = [r.load(sc.blob) for sc in scenes]
+    dt = scenes[0].dt
+    nb = sum(sc.n_dynamic() for sc in scenes)
+    for s in spaces:
+        s.step(dt, warmup)
+    t = sum(s.time_steps(dt, steps) for s in spaces)
+    contacts = sum(s.counts()["contacts"] for s in spaces)
+    for s in spaces:
+        s.space = None  # leak: tearing a 20k-body reference space down is O(n^2)
+    return {"value": nb * steps / t, "unit": "body-steps/s", "cores": 1, "kind": "reference",
+            "sample": "%s at %d bodies (%d spaces), %d warm-up + %d timed cpSpaceStep, gcc -O2 -ffp-contract=off no fast-math, 1 thread (cpHastySpace's 2 threads are slower, BASELINE.md)" % (
+                cfg["workload"], nb, len(scenes), warmup, steps),
+            "ms_per_step": 1000.0 * t / steps, "contacts_per_step": contacts}
+
+
+def run_reference(args):
+    rank, local_rank, world = rank_info()
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 100))
+    warm = max(0, min(args.warmup, 20))
+    base = cpu_baseline_sample(args.workload, steps, warm)
+    _, cfg = build_scenes(args.workload, 0, for_reference=False)
+    if base is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
+        return
+    line = {"impl": "reference", "metric": "body_steps_per_sec", "value": base["value"], "unit": "body-steps/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": cfg, "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    sys.stdout.flush()
+    os._exit(0)
+
+
+def run_ours(args):
+    rank, local_rank, world = rank_info()
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the step engine has no CPU fallback)")
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        dist = None
+    from chipmunk2d_b200.engine import World, BODY_DESC, BODY_STATE
+    from chipmunk2d_b200.api import load_scene_lib
+    from oracle.ref import SceneSpace
+
+    scenes, cfg = build_scenes(args.workload, rank)
+    dt = scenes[0].dt
+    nb = sum(sc.n_dynamic() for sc in scenes)
+    iterations = int(scenes[0].header["iterations"])
+
+    w = World(len(scenes), device=local_rank)
+    w.load_scenes(scenes)
+    settle = {"pile1m": 30, "pile1m_sleep": 30, "batch": 300, "c1": 300, "c2": 300, "mixed100k": 120}.get(args.workload, 0)
+    w.step(dt, settle)          # untimed: let contacts form so the timed steps see the settled workload
+    w.step(dt, max(3, args.warmup))
+    w.sync()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    launches0 = w.launch_count()
+    barrier()
+    sampler.start()
+    ms = w.time_steps(dt, args.steps)
+    barrier()
+    clocks = sampler.stop()
+    launches = w.launch_count() - launches0
+    st = w.stats()
+
+    # per-stage device times + solver internals (separate short pass, profiling adds a sync per step)
+    w.set_profiling(True)
+    acc = {}
+    nprof = 5
+    for _ in range(nprof):
+        w.step(dt)
+        for k, v in w.stage_times().items():
+            acc[k] = acc.get(k, 0.0) + v / nprof
+    sp = w.solver_profile()
+    w.set_profiling(False)
+    st2 = w.stats()
+
+    t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    totals = torch.tensor([float(nb), float(st["n_contacts"]), float(st["n_arbiters"]), float(st["n_pairs"]), st["kinetic_energy"]], dtype=torch.float64, device="cuda")
+    maxes = torch.tensor([st["max_penetration"]], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        # the only inter-GPU traffic of the batched layout: step statistics (north star)
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(totals, op=dist.ReduceOp.SUM)
+        dist.all_reduce(maxes, op=dist.ReduceOp.MAX)
+    t_max = float(t_ms.item()) * 1e-3
+    total_bodies, total_contacts, total_arbs, total_pairs, total_ke = (float(x) for x in totals.tolist())
+
+    # ---- e2e through the public C API (host buffers every step) ----
+    e2e = None
+    try:
+        k2 = max(1, min(args.steps, 10))
+        if len(scenes) == 1:
+            api = SceneSpace(load_scene_lib(), scenes[0].blob)
+            api.step(dt, settle)
+            api.e2e_steps(dt, 2)
+            barrier()
+            sec, _pos = api.e2e_steps(dt, k2)
+            n_api = api.n_bodies
+            api.space = None
+            e2e_bodies = nb
+        else:
+            # batched layout: one cpSpace per space through the C API, sampled (64 spaces) -- the C API has no
+            # batched entry point in the reference, so this is its per-space cost
+            sub = scenes[:64]
+            apis = [SceneSpace(load_scene_lib(), sc.blob) for sc in sub]
+            for a in apis:
+                a.step(dt, 2)
+            barrier()
+            sec = sum(a.e2e_steps(dt, k2)[0] for a in apis)
+            n_api = sum(a.n_bodies for a in apis)
+            e2e_bodies = sum(sc.n_dynamic() for sc in sub)
+        t_e = torch.tensor([sec], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": e2e_bodies * world * k2 / float(t_e.item()), "unit": "body-steps/s", "steps": k2,
+               "h2d_bytes_per_step": int(n_api * BODY_DESC.itemsize), "d2h_bytes_per_step": int(n_api * BODY_STATE.itemsize),
+               "ms_per_step": 1000.0 * float(t_e.item()) / k2,
+               "path": "cpBodySetForce on every body -> cpSpaceStep -> cpBodyGetPosition on every body (scene_io.c cpb_scene_e2e_steps)" +
+                       ("" if len(scenes) == 1 else "; sampled on 64 spaces stepped one cpSpace at a time")}
+    except Exception as exc:  # keep the device-resident number even if the API libs are missing
+        e2e = {"value": None, "unit": "body-steps/s", "error": str(exc)}
+
+    if rank != 0:
+        return
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    solve_us = acc.get("colour_solve", 0.0)
+    alg = algorithmic_bytes_solver(st2["n_contacts"], st2["n_joints"], iterations)
+    achieved = alg / (solve_us * 1e-6) / 1e9 if solve_us > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(args.workload)
+    except Exception:
+        pass
+    whole_step_alg = 264.0 * nb + 108.0 * nb + 32.0 * st2["n_shapes"] + (8.0 + 170.0) * st2["n_pairs"] + 64.0 * st2["n_arbiters"] + 400.0 * st2["n_contacts"] + 384.0 * iterations * st2["n_contacts"]
+    step_ms_dev = ms / args.steps
+
+    cpu = None
+    if world == 1 or rank == 0:
+        try:
+            cpu = cpu_baseline_sample(args.workload, 40, 10)
+        except Exception as exc:
+            cpu = {"value": None, "error": str(exc)}
+
+    line = {
+        "metric": "body_steps_per_sec", "value": total_bodies * args.steps / t_max, "unit": "body-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": 1000.0 * t_max / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": dict(cfg, parallelism=("replicas x%d (a single space does not shard)" % world if len(scenes) == 1 else "spaces sharded x%d, no data-path collective" % world),
+                       l2="inputs larger than L2 (solver rows + arbiter records >> 126 MB)" if nb >= 300000 else "working set fits L2; latency-bound configuration",
+                       settle_steps=settle),
+        "contacts_solved_per_sec": total_contacts * args.steps / t_max,
+        "contact_iterations_per_sec": total_contacts * iterations * args.steps / t_max,
+        "per_step": {"bodies": total_bodies, "pairs": total_pairs, "arbiters": total_arbs, "contacts": total_contacts, "colours": st["n_colours"],
+                     "max_penetration": float(maxes.item()), "kinetic_energy": total_ke},
+        "clocks": clocks,
+        "gpu_launches": int(launches),
+        "e2e": e2e,
+        "roofline": {"bound": "hbm", "kernel": "k_colour_solve (persistent colouring + warm start + %d Gauss-Seidel iterations)" % iterations,
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                     "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg, "launch_us": solve_us,
+                     "whole_step": {"algorithmic_bytes": whole_step_alg, "achieved_gbs": whole_step_alg / (step_ms_dev * 1e-3) / 1e9,
+                                    "frac": whole_step_alg / (step_ms_dev * 1e-3) / 1e9 / peak}},
+        "stage_us": acc, "solver_us": sp,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    sys.stdout.flush()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default=os.environ.get("CPB200_BENCH_WORKLOAD", "pile1m"))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

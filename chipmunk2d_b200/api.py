@@ -37,6 +37,8 @@ def load_scene_lib(path=None):
     lib.cpb_scene_get_arbiters.argtypes = [C.c_void_p, C.c_int, dp]
     lib.cpb_scene_shapes_collide.restype = C.c_int
     lib.cpb_scene_shapes_collide.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
+    lib.cpb_scene_e2e_steps.restype = C.c_double
+    lib.cpb_scene_e2e_steps.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, dp, C.c_double, C.c_double, C.c_int]
     _cache[path] = lib
     return lib
 

@@ -20,7 +20,8 @@
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 
-#define LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+extern unsigned long long g_cpb_launches;   // kernels launched by this library (bench.py reports it)
+#define LAUNCH(kernel, grid, block, stream, ...) do { g_cpb_launches++; kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__); } while(0)
 #define CPB_DEVICE __device__ __forceinline__
 #define CPB_HD __host__ __device__ __forceinline__
 

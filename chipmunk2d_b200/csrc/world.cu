@@ -18,6 +18,8 @@
 
 #ifdef CPB_EMU
 emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+#else
+unsigned long long g_cpb_launches = 0;
 #endif
 
 // ------------------------------------------------------------------ errors
@@ -730,6 +732,7 @@ extern "C" int cpb200_world_step(cpb200_world *w, double dt)
 			if(w->force_blocks > 0) blocks = std::min(w->coop_blocks, w->force_blocks);
 			void *args[] = {&B, &Ac, &J, &R, &K, &C, &bar, &iterations, &dt, &dt_coef};
 			CPB_CHECK(cudaLaunchCooperativeKernel((void *)k_colour_solve, dim3(blocks), dim3(256), args, 0, st));
+			g_cpb_launches++;
 		}
 #else
 		{
@@ -762,6 +765,35 @@ extern "C" int cpb200_world_step(cpb200_world *w, double dt)
 	}
 	CPB_CHECK(cudaGetLastError());
 	return 0;
+}
+
+extern "C" unsigned long long cpb200_launch_count(void)
+{
+#ifdef CPB_EMU
+	return 0;
+#else
+	return g_cpb_launches;
+#endif
+}
+
+// n steps bracketed by CUDA events on the world's own stream (what bench.py times)
+extern "C" int cpb200_world_time_steps(cpb200_world *w, double dt, int n, float *ms)
+{
+	if(!w || n < 0 || !ms){ cpb_set_error("bad arguments"); return -1; }
+	cudaSetDevice(w->device);
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0); cudaEventCreate(&e1);
+	CPB_CHECK(cudaStreamSynchronize(w->stream));
+	cudaEventRecord(e0, w->stream);
+	int rc = 0;
+	for(int i = 0; i < n && rc == 0; i++) rc = cpb200_world_step(w, dt);
+	cudaEventRecord(e1, w->stream);
+	cudaEventSynchronize(e1);
+	*ms = 0.f;
+	cudaEventElapsedTime(ms, e0, e1);
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	if(rc) return rc;
+	return cpb200_world_sync(w);
 }
 
 extern "C" int cpb200_world_sync(cpb200_world *w)

@@ -100,6 +100,8 @@ def load_engine(path=None):
     lib.cpb200_world_reserve.argtypes = [vp, ci, ci]
     lib.cpb200_world_step.argtypes = [vp, cd]
     lib.cpb200_world_sync.argtypes = [vp]
+    lib.cpb200_world_time_steps.argtypes = [vp, cd, ci, vp]
+    lib.cpb200_launch_count.restype = C.c_ulonglong
     lib.cpb200_world_get_bodies.argtypes = [vp, ci, ci, vp]
     lib.cpb200_world_get_shape_bbs.argtypes = [vp, ci, ci, vp]
     lib.cpb200_world_get_arbiters.argtypes = [vp, ci, vp, ci]
@@ -277,6 +279,15 @@ class World:
     def step(self, dt, n=1):
         for _ in range(n):
             self._ck(self.lib.cpb200_world_step(self.w, float(dt)))
+
+    def time_steps(self, dt, n):
+        """n steps; returns device milliseconds (CUDA events on the engine's stream)."""
+        ms = C.c_float(0.0)
+        self._ck(self.lib.cpb200_world_time_steps(self.w, float(dt), int(n), C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self):
+        return int(self.lib.cpb200_launch_count())
 
     def sync(self):
         self._ck(self.lib.cpb200_world_sync(self.w))

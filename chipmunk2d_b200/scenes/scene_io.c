@@ -342,3 +342,34 @@ cpb_scene_shapes_collide(cpSpace *space, int ia, int ib, double *out)
 	}
 	return set.count;
 }
+
+/* ---- end-to-end loop for the benchmark: host buffers in, host buffers out, every step ----
+ * Per step: write an external force into every dynamic body (host -> library), cpSpaceStep, read every
+ * body's position back into out_xy[n][2] (library -> host).  Returns wall seconds for n_steps. */
+typedef struct e2e_ctx { double fx, fy; double *out; int n; } e2e_ctx;
+static void e2e_push(cpBody *body, void *ctx){
+	e2e_ctx *c = (e2e_ctx *)ctx;
+	if(cpBodyGetType(body) == CP_BODY_TYPE_DYNAMIC) cpBodySetForce(body, cpv(c->fx, c->fy));
+}
+static void e2e_pull(cpBody *body, void *ctx){
+	e2e_ctx *c = (e2e_ctx *)ctx;
+	int i = UNTAG(cpBodyGetUserData(body));
+	if(i < 0 || i >= c->n) return;
+	cpVect p = cpBodyGetPosition(body);
+	c->out[2*(size_t)i] = p.x; c->out[2*(size_t)i + 1] = p.y;
+}
+
+CPB_EXPORT double
+cpb_scene_e2e_steps(cpSpace *space, double dt, int n_steps, int n_bodies, double *out_xy, double fx, double fy, int hasty)
+{
+	struct timespec t0, t1;
+	e2e_ctx ctx = {fx, fy, out_xy, n_bodies};
+	clock_gettime(CLOCK_MONOTONIC, &t0);
+	for(int s = 0; s < n_steps; s++){
+		cpSpaceEachBody(space, e2e_push, &ctx);
+		if(hasty) cpHastySpaceStep(space, dt); else cpSpaceStep(space, dt);
+		cpSpaceEachBody(space, e2e_pull, &ctx);
+	}
+	clock_gettime(CLOCK_MONOTONIC, &t1);
+	return (double)(t1.tv_sec - t0.tv_sec) + 1e-9*(double)(t1.tv_nsec - t0.tv_nsec);
+}

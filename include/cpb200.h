@@ -189,6 +189,10 @@ CPB200_API int cpb200_world_reserve(cpb200_world *w, int max_pairs, int max_arbi
 /* cpSpaceStep (cpSpaceStep.c:335-445) for every space of the world.  Asynchronous:
  * returns once the kernels are enqueued on the world's stream. */
 CPB200_API int cpb200_world_step(cpb200_world *w, double dt);
+/* n steps timed with CUDA events recorded on the world's stream; *ms = device time in milliseconds. */
+CPB200_API int cpb200_world_time_steps(cpb200_world *w, double dt, int n, float *ms);
+/* Number of kernels this library has launched in this process (all worlds). */
+CPB200_API unsigned long long cpb200_launch_count(void);
 /* Block until all enqueued steps have finished; returns non-zero on a device error or
  * buffer overflow. */
 CPB200_API int cpb200_world_sync(cpb200_world *w);

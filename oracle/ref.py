@@ -51,6 +51,8 @@ def bind_scene_api(lib):
     lib.cpb_scene_get_arbiters.argtypes = [C.c_void_p, C.c_int, _dp]
     lib.cpb_scene_shapes_collide.restype = C.c_int
     lib.cpb_scene_shapes_collide.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
+    lib.cpb_scene_e2e_steps.restype = C.c_double
+    lib.cpb_scene_e2e_steps.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, _dp, C.c_double, C.c_double, C.c_int]
     return lib
 
 
@@ -73,6 +75,12 @@ class SceneSpace:
 
     def time_steps(self, dt, n):
         return self.lib.cpb_scene_time_steps(self.space, dt, n, self.hasty)
+
+    def e2e_steps(self, dt, n, force=(0.0, 0.0)):
+        """n steps with per-step host writes (forces) and host reads (positions); returns (seconds, positions)."""
+        out = np.zeros((self.n_bodies, 2))
+        t = self.lib.cpb_scene_e2e_steps(self.space, dt, n, self.n_bodies, _p(out), force[0], force[1], self.hasty)
+        return t, out
 
     def bodies(self):
         out = np.full((self.n_bodies, PUB_BODY_ROW), np.nan)
