@@ -107,6 +107,9 @@ def algorithmic_bytes_solver(n_contacts, n_joints, iterations):
     return 384.0 * iterations * n_contacts + 192.0 * n_contacts + 300.0 * (iterations + 1) * n_joints
 
 
+SETTLE = {"pile1m": 30, "pile1m_sleep": 30, "batch": 300, "c1": 300, "c2": 300, "mixed100k": 120}
+
+
 def cpu_baseline_sample(workload, steps, warmup):
     """The unmodified reference (oracle/_ref) on a bounded sample of the workload, one thread."""
     from oracle import ref as oref
@@ -114,18 +117,19 @@ def cpu_baseline_sample(workload, steps, warmup):
         return None
     scenes, cfg = build_scenes(workload, 0, for_reference=True)
     r = oref.Ref()
+    settle = SETTLE.get(workload, 0)
     spaces = [r.load(sc.blob) for sc in scenes]
     dt = scenes[0].dt
     nb = sum(sc.n_dynamic() for sc in scenes)
     for s in spaces:
-        s.step(dt, warmup)
+        s.step(dt, settle + warmup)     # same untimed settling as the GPU arm, so both time the settled workload
     t = sum(s.time_steps(dt, steps) for s in spaces)
     contacts = sum(s.counts()["contacts"] for s in spaces)
     for s in spaces:
         s.space = None  # leak: tearing a 20k-body reference space down is O(n^2)
     return {"value": nb * steps / t, "unit": "body-steps/s", "cores": 1, "kind": "reference",
-            "sample": "%s at %d bodies (%d spaces), %d warm-up + %d timed cpSpaceStep, gcc -O2 -ffp-contract=off no fast-math, 1 thread (cpHastySpace's 2 threads are slower, BASELINE.md)" % (
-                cfg["workload"], nb, len(scenes), warmup, steps),
+            "sample": "%s at %d bodies (%d spaces), %d settle + %d warm-up + %d timed cpSpaceStep, gcc -O2 -ffp-contract=off no fast-math, 1 thread (cpHastySpace's 2 threads are slower, BASELINE.md)" % (
+                cfg["workload"], nb, len(scenes), settle, warmup, steps),
             "ms_per_step": 1000.0 * t / steps, "contacts_per_step": contacts}
 
 
@@ -171,7 +175,7 @@ def run_ours(args):
 
     w = World(len(scenes), device=local_rank)
     w.load_scenes(scenes)
-    settle = {"pile1m": 30, "pile1m_sleep": 30, "batch": 300, "c1": 300, "c2": 300, "mixed100k": 120}.get(args.workload, 0)
+    settle = SETTLE.get(args.workload, 0)
     w.step(dt, settle)          # untimed: let contacts form so the timed steps see the settled workload
     w.step(dt, max(3, args.warmup))
     w.sync()

@@ -109,6 +109,7 @@ struct cpb200_world {
 	cudaEvent_t ev[ST_COUNT + 1];
 	float stage_us[ST_COUNT];
 
+	void *d_stage; size_t stage_bytes;   // device staging for host <-> SoA conversion kernels
 	unsigned *d_barrier;    // grid barrier words of the persistent solver
 	int force_blocks;       // validation hook: fixed persistent grid size (0 = automatic)
 	int last_active;        // active arbiters seen at the last host read-back (grid sizing hint)
@@ -215,7 +216,7 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	cudaMalloc(&p, sizeof(DCounters)); w->C = (DCounters *)p; cudaMemsetAsync(w->C, 0, sizeof(DCounters), w->stream);
 	cudaMallocHost(&p, sizeof(DCounters)); w->hC = (DCounters *)p; memset(w->hC, 0, sizeof(DCounters));
 	cudaMalloc(&p, sizeof(unsigned)*8); w->d_barrier = (unsigned *)p; cudaMemsetAsync(w->d_barrier, 0, sizeof(unsigned)*8, w->stream);
-	w->last_active = 0; w->force_blocks = 0;
+	w->last_active = 0; w->force_blocks = 0; w->d_stage = NULL; w->stage_bytes = 0;
 	cudaMalloc(&p, sizeof(double)*64); w->d_scratch = (double *)p;
 	cudaMallocHost(&p, sizeof(double)*64); w->h_scratch = (double *)p;
 	if(!w->d_spaces || !w->C || !w->hC){ cpb_set_error("device allocation failed"); delete w; return NULL; }
@@ -229,6 +230,7 @@ extern "C" void cpb200_world_destroy(cpb200_world *w)
 	cudaStreamSynchronize(w->stream);
 	w->gB.release(); w->gS.release(); w->gJ.release(); w->gA.release(); w->gK.release(); w->gV.release(); w->gP.release(); w->gI.release();
 	cudaFree(w->d_barrier);
+	if(w->d_stage) cudaFree(w->d_stage);
 	cudaFree(w->d_spaces); cudaFree(w->C); cudaFreeHost(w->hC); cudaFree(w->d_scratch); cudaFreeHost(w->h_scratch);
 	if(w->d_order) cudaFree(w->d_order);
 	if(w->d_user_order) cudaFree(w->d_user_order);
@@ -272,16 +274,57 @@ static int refresh_spaces(cpb200_world *w, double dt)
 }
 
 // ------------------------------------------------------------------ uploads
-static void fill_body(const cpb200_body_desc &d, V2 &pos, double &ang, V2 &rot, V2 &cog, double4 &V, double4 &VB, V2 &MI, V2 &M, V2 &force, double &torque, double &idle, int &type, int &space, int &sleeping, int &sgroup)
+// Host records travel as ONE copy into a device staging buffer and are scattered into / gathered from the
+// SoA arrays by a kernel (no per-field host loops, no per-field cudaMemcpy).
+static int stage_reserve(cpb200_world *w, size_t bytes)
 {
-	pos = v2(d.p[0], d.p[1]); ang = d.a; rot = v2(d.rot[0], d.rot[1]); cog = v2(d.cog[0], d.cog[1]);
-	V = make_double4(d.v[0], d.v[1], d.w, 0.0); VB = make_double4(d.v_bias[0], d.v_bias[1], d.w_bias, 0.0);
+	if(bytes <= w->stage_bytes) return 0;
+	if(w->d_stage) cudaFree(w->d_stage);
+	w->d_stage = NULL; w->stage_bytes = 0;
+	void *p = NULL;
+	CPB_CHECK(cudaMalloc(&p, bytes + bytes/4 + 256));
+	w->d_stage = p; w->stage_bytes = bytes + bytes/4 + 256;
+	return 0;
+}
+
+__global__ void k_unpack_bodies(DBodies B, const cpb200_body_desc *__restrict__ src, int first, int n, int n_spaces, int *bad)
+{
+	int k = CPB_TID;
+	if(k >= n) return;
+	cpb200_body_desc d = src[k];
+	int i = first + k;
+	if(d.space < 0 || d.space >= n_spaces){ *bad = 1; d.space = 0; }
+	B.pos[i] = v2(d.p[0], d.p[1]); B.ang[i] = d.a; B.rot[i] = v2(d.rot[0], d.rot[1]); B.cog[i] = v2(d.cog[0], d.cog[1]);
+	B.V[i] = make_double4(d.v[0], d.v[1], d.w, 0.0); B.VB[i] = make_double4(d.v_bias[0], d.v_bias[1], d.w_bias, 0.0);
 	bool dyn = (d.type == CPB200_BODY_DYNAMIC);
-	// m_inv/i_inv exactly as cpBodySetMass/SetMoment compute them (cpBody.c:246-270): 1/m, 0 for infinite
-	MI = v2(dyn ? 1.0/d.m : 0.0, dyn ? 1.0/d.i : 0.0);
-	M = v2(d.m, d.i);
-	force = v2(d.f[0], d.f[1]); torque = d.t; idle = d.idle_time;
-	type = d.type; space = d.space; sleeping = d.sleeping; sgroup = d.sleep_group;
+	// m_inv / i_inv exactly as cpBodySetMass / SetMoment compute them (cpBody.c:246-270): 1/m, 0 for infinite mass
+	B.MI[i] = v2(dyn ? 1.0/d.m : 0.0, dyn ? 1.0/d.i : 0.0);
+	B.M[i] = v2(d.m, d.i);
+	B.force[i] = v2(d.f[0], d.f[1]); B.torque[i] = d.t; B.idle[i] = d.idle_time;
+	B.type[i] = d.type; B.space[i] = d.space; B.sleeping[i] = d.sleeping; B.sgroup[i] = d.sleep_group;
+	// translation part of SetTransform from the host-supplied rotation (cpBody.c:347-357)
+	V2 p = v2(d.p[0], d.p[1]), rot = v2(d.rot[0], d.rot[1]), cg = v2(d.cog[0], d.cog[1]);
+	B.txy[i] = v2(p.x - (cg.x*rot.x - cg.y*rot.y), p.y - (cg.x*rot.y + cg.y*rot.x));
+}
+
+__global__ void k_pack_body_state(DBodies B, cpb200_body_state *__restrict__ dst, int first, int n)
+{
+	int k = CPB_TID;
+	if(k >= n) return;
+	int i = first + k;
+	cpb200_body_state o;
+	V2 p = B.pos[i], rot = B.rot[i]; double4 V = B.V[i];
+	o.p[0] = p.x; o.p[1] = p.y; o.v[0] = V.x; o.v[1] = V.y; o.a = B.ang[i]; o.w = V.z;
+	o.rot[0] = rot.x; o.rot[1] = rot.y; o.idle_time = B.idle[i]; o.sleeping = B.sleeping[i]; o.sleep_group = B.sgroup[i];
+	dst[k] = o;
+}
+
+__global__ void k_set_forces(DBodies B, const double *__restrict__ fxyt, int first, int n)
+{
+	int k = CPB_TID;
+	if(k >= n) return;
+	B.force[first + k] = v2(fxyt[3*k], fxyt[3*k + 1]);
+	B.torque[first + k] = fxyt[3*k + 2];
 }
 
 extern "C" int cpb200_world_set_bodies(cpb200_world *w, int n, const cpb200_body_desc *bodies)
@@ -313,22 +356,31 @@ extern "C" int cpb200_world_update_bodies(cpb200_world *w, int first, int n, con
 	if(!w || first < 0 || n < 0 || first + n > w->B.n){ cpb_set_error("body range out of bounds"); return -1; }
 	if(n == 0) return 0;
 	cudaSetDevice(w->device);
-	size_t N = (size_t)n;
-	std::vector<V2> pos(N), rot(N), cog(N), MI(N), M(N), force(N);
-	std::vector<double> ang(N), torque(N), idle(N);
-	std::vector<double4> V(N), VB(N);
-	std::vector<int> type(N), space(N), sleeping(N), sgroup(N);
-	for(size_t i = 0; i < N; i++){
-		fill_body(bodies[i], pos[i], ang[i], rot[i], cog[i], V[i], VB[i], MI[i], M[i], force[i], torque[i], idle[i], type[i], space[i], sleeping[i], sgroup[i]);
-		if(space[i] < 0 || space[i] >= w->n_spaces){ cpb_set_error("body %zu: space index %d out of range", i, space[i]); return -1; }
-	}
-	DBodies &B = w->B;
-	if(upload(w, B.pos + first, pos) || upload(w, B.ang + first, ang) || upload(w, B.rot + first, rot) || upload(w, B.cog + first, cog) ||
-	   upload(w, B.V + first, V) || upload(w, B.VB + first, VB) || upload(w, B.MI + first, MI) || upload(w, B.M + first, M) ||
-	   upload(w, B.force + first, force) || upload(w, B.torque + first, torque) || upload(w, B.idle + first, idle) ||
-	   upload(w, B.type + first, type) || upload(w, B.space + first, space) || upload(w, B.sleeping + first, sleeping) || upload(w, B.sgroup + first, sgroup)) return -1;
-	LAUNCH(k_body_transform, grid_for(n, 256), 256, w->stream, B, first, n);
+	size_t bytes = sizeof(cpb200_body_desc)*(size_t)n;
+	if(stage_reserve(w, bytes + 64)) return -1;
+	int *bad = (int *)((char *)w->d_stage + ((bytes + 15) & ~(size_t)15));
+	CPB_CHECK(cudaMemsetAsync(bad, 0, sizeof(int), w->stream));
+	CPB_CHECK(cudaMemcpyAsync(w->d_stage, bodies, bytes, cudaMemcpyHostToDevice, w->stream));
+	LAUNCH(k_unpack_bodies, grid_for(n, 128), 128, w->stream, w->B, (const cpb200_body_desc *)w->d_stage, first, n, w->n_spaces, bad);
+	int h_bad = 0;
+	CPB_CHECK(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
 	w->cache_dirty = true;
+	if(world_sync(w)) return -1;
+	if(h_bad){ cpb_set_error("a body names a space index outside [0, %d)", w->n_spaces); return -1; }
+	return 0;
+}
+
+/* Forces only: the common per-step host input (cpBodySetForce / cpBodyApplyForce*, cpBody.c:420-424, 534-543).
+ * fxyt[n][3] = f.x f.y torque. */
+extern "C" int cpb200_world_set_body_forces(cpb200_world *w, int first, int n, const double *fxyt)
+{
+	if(!w || first < 0 || n < 0 || first + n > w->B.n){ cpb_set_error("body range out of bounds"); return -1; }
+	if(n == 0) return 0;
+	cudaSetDevice(w->device);
+	size_t bytes = sizeof(double)*3*(size_t)n;
+	if(stage_reserve(w, bytes)) return -1;
+	CPB_CHECK(cudaMemcpyAsync(w->d_stage, fxyt, bytes, cudaMemcpyHostToDevice, w->stream));
+	LAUNCH(k_set_forces, grid_for(n, 256), 256, w->stream, w->B, (const double *)w->d_stage, first, n);
 	return world_sync(w);
 }
 
@@ -816,19 +868,13 @@ extern "C" int cpb200_world_sync(cpb200_world *w)
 extern "C" int cpb200_world_get_bodies(cpb200_world *w, int first, int n, cpb200_body_state *out)
 {
 	if(!w || first < 0 || n < 0 || first + n > w->B.n){ cpb_set_error("body range out of bounds"); return -1; }
+	if(n == 0) return 0;
 	cudaSetDevice(w->device);
-	size_t N = (size_t)n;
-	std::vector<V2> pos, rot; std::vector<double> ang, idle; std::vector<double4> V; std::vector<int> sleeping, sgroup;
-	DBodies &B = w->B;
-	if(download(w, pos, B.pos + first, N) || download(w, rot, B.rot + first, N) || download(w, ang, B.ang + first, N) || download(w, idle, B.idle + first, N) ||
-	   download(w, V, B.V + first, N) || download(w, sleeping, B.sleeping + first, N) || download(w, sgroup, B.sgroup + first, N)) return -1;
-	if(world_sync(w)) return -1;
-	for(size_t i = 0; i < N; i++){
-		cpb200_body_state &o = out[i];
-		o.p[0] = pos[i].x; o.p[1] = pos[i].y; o.v[0] = V[i].x; o.v[1] = V[i].y; o.a = ang[i]; o.w = V[i].z;
-		o.rot[0] = rot[i].x; o.rot[1] = rot[i].y; o.idle_time = idle[i]; o.sleeping = sleeping[i]; o.sleep_group = sgroup[i];
-	}
-	return 0;
+	size_t bytes = sizeof(cpb200_body_state)*(size_t)n;
+	if(stage_reserve(w, bytes)) return -1;
+	LAUNCH(k_pack_body_state, grid_for(n, 128), 128, w->stream, w->B, (cpb200_body_state *)w->d_stage, first, n);
+	CPB_CHECK(cudaMemcpyAsync(out, w->d_stage, bytes, cudaMemcpyDeviceToHost, w->stream));
+	return world_sync(w);
 }
 
 static int ensure_cache(cpb200_world *w)

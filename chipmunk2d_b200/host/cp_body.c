@@ -18,6 +18,13 @@ touch(cpBody *body)
 	if(body->space) body->space->bodiesDirty = cpTrue;
 }
 
+static void
+touch_force(cpBody *body)
+{
+	/* forces are consumed by the step and never written back by the device: no fetch needed */
+	if(body->space) body->space->forcesDirty = cpTrue;
+}
+
 void
 cpBodySetTransformInternal(cpBody *body, cpVect p, cpFloat a)
 {
@@ -229,7 +236,7 @@ cpBodySetCenterOfGravity(cpBody *body, cpVect cog)
 cpVect cpBodyGetVelocity(const cpBody *body){ cpBodySyncForRead(body); return body->v; }
 void cpBodySetVelocity(cpBody *body, cpVect velocity){ cpBodyActivate(body); touch(body); body->v = velocity; }
 cpVect cpBodyGetForce(const cpBody *body){ cpBodySyncForRead(body); return body->f; }
-void cpBodySetForce(cpBody *body, cpVect force){ cpBodyActivate(body); touch(body); body->f = force; }
+void cpBodySetForce(cpBody *body, cpVect force){ cpBodyActivate(body); touch_force(body); body->f = force; }
 cpFloat cpBodyGetAngle(const cpBody *body){ cpBodySyncForRead(body); return body->a; }
 
 void
@@ -244,7 +251,7 @@ cpBodySetAngle(cpBody *body, cpFloat angle)
 cpFloat cpBodyGetAngularVelocity(const cpBody *body){ cpBodySyncForRead(body); return body->w; }
 void cpBodySetAngularVelocity(cpBody *body, cpFloat angularVelocity){ cpBodyActivate(body); touch(body); body->w = angularVelocity; }
 cpFloat cpBodyGetTorque(const cpBody *body){ cpBodySyncForRead(body); return body->t; }
-void cpBodySetTorque(cpBody *body, cpFloat torque){ cpBodyActivate(body); touch(body); body->t = torque; }
+void cpBodySetTorque(cpBody *body, cpFloat torque){ cpBodyActivate(body); touch_force(body); body->t = torque; }
 cpDataPointer cpBodyGetUserData(const cpBody *body){ return body->userData; }
 void cpBodySetUserData(cpBody *body, cpDataPointer userData){ body->userData = userData; }
 
@@ -295,7 +302,8 @@ void
 cpBodyApplyForceAtWorldPoint(cpBody *body, cpVect force, cpVect point)
 {
 	cpBodyActivate(body);
-	touch(body);
+	cpBodySyncForRead(body);
+	touch_force(body);
 	body->f = cpvadd(body->f, force);
 	cpVect r = cpvsub(point, cpTransformPoint(body->transform, body->cog));
 	body->t += cpvcross(r, force);

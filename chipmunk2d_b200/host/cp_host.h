@@ -147,6 +147,7 @@ struct cpSpace {
 	int solverMode;
 	cpBool topologyDirty;      /* bodies/shapes/joints added, removed or re-parameterised */
 	cpBool bodiesDirty;        /* kinematic state of some body changed on the host */
+	cpBool forcesDirty;        /* only forces / torques changed: uploaded as 24 bytes per body */
 	cpBool paramsDirty;
 	cpBool hostStale;          /* device has newer body state than the mirrors */
 	cpBool bbStale, arbStale, jointStale;

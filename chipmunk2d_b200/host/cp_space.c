@@ -393,6 +393,17 @@ upload_bodies(cpSpace *space, cpBool full)
 }
 
 static void
+upload_forces(cpSpace *space)
+{
+	int n = space->nBodies;
+	double *f = (double *)cpcalloc((size_t)n, 3*sizeof(double));
+	for(int i = 0; i < n; i++){ const cpBody *b = space->bodies[i]; f[3*i] = b->f.x; f[3*i + 1] = b->f.y; f[3*i + 2] = b->t; }
+	int rc = cpb200_world_set_body_forces(space->world, 0, n, f);
+	cpfree(f);
+	if(rc) cpEngineError("force upload");
+}
+
+static void
 upload_shapes(cpSpace *space)
 {
 	int n = space->nShapes, nv = 0;
@@ -484,9 +495,14 @@ sync_to_device(cpSpace *space)
 		upload_joints(space);
 		space->topologyDirty = cpFalse;
 		space->bodiesDirty = cpFalse;
+		space->forcesDirty = cpFalse;
 	} else if(space->bodiesDirty){
 		upload_bodies(space, cpFalse);
 		space->bodiesDirty = cpFalse;
+		space->forcesDirty = cpFalse;
+	} else if(space->forcesDirty){
+		upload_forces(space);
+		space->forcesDirty = cpFalse;
 	}
 	if(space->paramsDirty){ upload_params(space); space->paramsDirty = cpFalse; }
 }
@@ -515,7 +531,7 @@ cpSpaceFetchBodiesB200(cpSpace *space)
 		b->sleepRoot = (s->sleeping && s->sleep_group >= 0 && s->sleep_group < n ? space->bodies[s->sleep_group] : NULL);
 		if(!s->sleeping){
 			/* the step consumed the forces and the bias velocities (cpBody.c:505-507, 518-519) */
-			if(b->m != INFINITY){ b->f = cpvzero; b->t = 0.0; }
+			if(b->m != INFINITY && !space->forcesDirty){ b->f = cpvzero; b->t = 0.0; }
 			b->v_bias = cpvzero; b->w_bias = 0.0;
 		}
 	}

@@ -181,6 +181,9 @@ CPB200_API int cpb200_world_set_joints(cpb200_world *w, int n, const cpb200_join
 /* Overwrite kinematic state of bodies [first, first+n) without touching anything else
  * (cpBodySetPosition/Velocity/Angle... between steps, cpBody.c:374-467). */
 CPB200_API int cpb200_world_update_bodies(cpb200_world *w, int first, int n, const cpb200_body_desc *bodies);
+/* Forces only -- the usual per-step host input (cpBodySetForce / cpBodyApplyForceAt*, cpBody.c:420-424,
+ * 534-543): fxyt[n][3] = f.x f.y torque for bodies [first, first+n). */
+CPB200_API int cpb200_world_set_body_forces(cpb200_world *w, int first, int n, const double *fxyt);
 /* Pre-size device buffers (pairs, arbiters) for at least this many; 0 keeps the default. */
 CPB200_API int cpb200_world_reserve(cpb200_world *w, int max_pairs, int max_arbiters);
 

@@ -51,7 +51,7 @@ def test_api_hasty_space_is_the_same_device_path():
     h = SceneSpace(load_scene_lib(), sc.blob, hasty=True, threads=2)
     a.step(sc.dt, 100)
     h.step(sc.dt, 100)
-    assert np.array_equal(a.bodies(), h.bodies())
+    assert np.array_equal(a.bodies(), h.bodies(), equal_nan=True)
 
 
 def test_api_shapes_collide_matches_reference(ref):
