@@ -85,6 +85,7 @@ struct DArbs {
 	uint64_t *hash;
 	int *colour;           // colour assigned this step (-1 = not in the solver)
 	uint64_t *pri;         // colouring priority: hash of the space-local shape pair (same in a batch as alone)
+	int *hint;             // last step's colour if the arbiter was solved then, else -1
 };
 
 // open-addressing table: shape-pair key -> arbiter record index (replaces cpHashSet cachedArbiters)
@@ -126,6 +127,7 @@ struct DJoints {
 	int *colour;
 	int *row;              // colour-sorted order: row -> joint index
 	uint64_t *pri;         // colouring priority: hash of the space-local joint index
+	int *hint;             // last step's colour, -1 if none
 };
 
 // ---- broadphase scratch (LBVH over all shapes, rebuilt every step) ----

@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 		cur.seen[slot] = 0;
 		cur.colour[slot] = -1;
 		cur.pri[slot] = mix64(arb_key(S.hlocal[sa], S.hlocal[sb])) >> 8;
+		cur.hint[slot] = (pi >= 0 && prev.active[pi] == 1 ? prev.colour[pi] : -1);
 		// active <=> pushed to space->arbiters (cpSpaceStep.c:261-274); the default handler accepts everything
 		bool both_inf = (B.type[ba] != CPB200_BODY_DYNAMIC) && (B.type[bb] != CPB200_BODY_DYNAMIC);
 		bool active = (state != CPB200_ARB_IGNORE) && !(S.sensor[sa] || S.sensor[sb]) && !both_inf;
@@ -181,6 +182,7 @@ __global__ void k_arb_carry(DBodies B, DArbs prev, DArbs cur, DTable cur_table, 
 		cur.n[slot] = prev.n[i]; cur.e[slot] = prev.e[i]; cur.u[slot] = prev.u[i]; cur.svr[slot] = prev.svr[i];
 		cur.colour[slot] = -1;
 		cur.pri[slot] = prev.pri[i];
+		cur.hint[slot] = -1;
 		for(int k = 0; k < 2; k++){
 			int c = 2*slot + k, p = 2*i + k;
 			cur.r1[c] = prev.r1[p]; cur.r2[c] = prev.r2[p];

@@ -63,6 +63,7 @@ __global__ void k_joint_prestep(DJoints J, DBodies B, double dt)
 	int j = CPB_TID;
 	if(j >= J.n) return;
 	int a = J.a[j], b = J.b[j];
+	J.hint[j] = J.colour[j];   // last step's colour (or a negative marker) seeds this step's colouring
 	if(B.sleeping[a] || B.sleeping[b]){
 		// the reference removes joints of sleeping bodies from space->constraints (cpSpaceComponent.c:107-110)
 		if((B.sleeping[a] || B.type[a] == CPB200_BODY_STATIC) && (B.sleeping[b] || B.type[b] == CPB200_BODY_STATIC)){ J.colour[j] = -2; return; }

@@ -18,6 +18,7 @@
 #pragma once
 #include "cpb_world.h"
 #include "k_joint.cuh"
+#include "prims.cuh"
 
 #define CPB_OVERFLOW_COLOUR (CPB_MAX_COLOURS - 1)
 #define CPB_MAX_COLOUR_ROUNDS 200
@@ -27,7 +28,8 @@ struct DColour {
 	unsigned long long *bmask;   // [n_bodies]
 	int *ccount, *cstart, *ccursor;   // [CPB_MAX_COLOURS + 1] arbiters per colour
 	int *jcount, *jstart, *jcursor;   // [CPB_MAX_COLOURS + 1] joints per colour
-	int *remaining;              // [CPB_MAX_COLOUR_ROUNDS + 1]
+	int *wl[2];                  // worklists of still uncoloured constraints (ping-pong per round)
+	int *wl_n;                   // [CPB_MAX_COLOUR_ROUNDS + 2] worklist length entering each round
 	unsigned long long *prof;    // [8] globaltimer stamps of the persistent kernel (start, coloured, rows built, warm start done, end) + rounds
 };
 
@@ -59,71 +61,150 @@ CPB_DEVICE bool cons_fetch(const DArbs &A, const DJoints &J, int nA, int c, int 
 	return true;
 }
 
-CPB_DEVICE void colour_phase_a(const DBodies &B, const DArbs &A, const DJoints &J, const DColour &K, int nA, int round, int tid, int nth){
+// per-colour histogram: block-local in shared memory inside the persistent kernel (one global atomic per
+// colour per CTA instead of one per constraint on a handful of hot addresses)
+CPB_DEVICE void hist_add(int *shist, int *ghist, int colour){
+	if(shist) atomicAdd(&shist[colour], 1); else atomicAdd(&ghist[colour], 1);
+}
+
+CPB_DEVICE void cons_set_colour(const DArbs &A, const DJoints &J, const DColour &K, int *shist, int nA, int c, int colour){
+	if(c < nA){ A.colour[c] = colour; hist_add(shist, K.ccount, colour); }
+	else { J.colour[c - nA] = colour; hist_add(shist ? shist + CPB_MAX_COLOURS : NULL, K.jcount, colour); }
+}
+
+// Seed: a constraint that was solved last step keeps last step's colour (all of those were mutually
+// conflict-free then and still join the same two bodies, so they cannot collide with each other now);
+// everything else -- new contacts, re-activated ones, or all of them after a re-upload -- goes on the
+// worklist for the Jones-Plassmann rounds.  In a settled pile the worklist is a fraction of a percent.
+CPB_DEVICE void colour_seed(const DBodies &B, const DArbs &A, const DJoints &J, const DColour &K, int *shist, int nA, int use_hints, int tid, int nth){
 	int total = nA + J.n;
-	for(int c = tid; c < total; c += nth){
+	int rounded = ((total + 31)/32)*32;
+	for(int c = tid; c < rounded; c += nth){
+		int a = 0, b = 0, col = 0; uint64_t pri = 0;
+		bool live = (c < total) && cons_fetch(A, J, nA, c, a, b, pri, col);
+		bool queued = false;
+		if(live){
+			int hint = (c < nA ? A.hint[c] : J.hint[c - nA]);
+			if(use_hints && hint >= 0 && hint < CPB_OVERFLOW_COLOUR){
+				unsigned long long bit = 1ull << hint;
+				if(body_is_dynamic(B, a)) atomicOr(&K.bmask[a], bit);
+				if(body_is_dynamic(B, b)) atomicOr(&K.bmask[b], bit);
+				cons_set_colour(A, J, K, shist, nA, c, hint);
+			} else queued = true;
+		}
+		int slot = cpb_warp_append(&K.wl_n[0], queued);
+		if(queued) K.wl[0][slot] = c;
+	}
+}
+
+CPB_DEVICE void colour_phase_a(const DBodies &B, const DArbs &A, const DJoints &J, const DColour &K, int nA, int round, int tid, int nth){
+	const int *wl = K.wl[round & 1];
+	int n = *((volatile int *)&K.wl_n[round]);
+	for(int k = tid; k < n; k += nth){
+		int c = wl[k];
 		int a, b, col; uint64_t pri;
-		if(!cons_fetch(A, J, nA, c, a, b, pri, col) || col >= 0) continue;
+		cons_fetch(A, J, nA, c, a, b, pri, col);
 		unsigned long long bid = ((unsigned long long)(round + 1) << 56) | pri;
 		if(body_is_dynamic(B, a)) atomicMax(&K.claim[a], bid);
 		if(body_is_dynamic(B, b)) atomicMax(&K.claim[b], bid);
 	}
 }
 
-CPB_DEVICE void colour_phase_b(const DBodies &B, const DArbs &A, const DJoints &J, const DColour &K, DCounters *C, int nA, int round, int tid, int nth){
-	int total = nA + J.n;
-	int lost = 0;
-	for(int c = tid; c < total; c += nth){
-		int a, b, col; uint64_t pri;
-		if(!cons_fetch(A, J, nA, c, a, b, pri, col) || col >= 0) continue;
-		unsigned long long bid = ((unsigned long long)(round + 1) << 56) | pri;
-		bool da = body_is_dynamic(B, a), db = body_is_dynamic(B, b);
-		bool win = (!da || ld_u64(&K.claim[a]) == bid) && (!db || ld_u64(&K.claim[b]) == bid);
-		if(!win){ lost++; continue; }
-		unsigned long long m = (da ? ld_u64(&K.bmask[a]) : 0ull) | (db ? ld_u64(&K.bmask[b]) : 0ull);
-		unsigned long long freebits = ~m & ((1ull << CPB_OVERFLOW_COLOUR) - 1ull);
-		int colour = (freebits ? __ffsll((long long)freebits) - 1 : CPB_OVERFLOW_COLOUR);
-		if(colour != CPB_OVERFLOW_COLOUR){
-			unsigned long long bit = 1ull << colour;
-			if(da) atomicOr(&K.bmask[a], bit);
-			if(db) atomicOr(&K.bmask[b], bit);
+CPB_DEVICE void colour_phase_b(const DBodies &B, const DArbs &A, const DJoints &J, const DColour &K, int *shist, int nA, int round, int tid, int nth){
+	const int *wl = K.wl[round & 1];
+	int *next = K.wl[(round + 1) & 1];
+	int n = *((volatile int *)&K.wl_n[round]);
+	int rounded = ((n + 31)/32)*32;
+	for(int k = tid; k < rounded; k += nth){
+		bool lost = false;
+		int c = 0;
+		if(k < n){
+			c = wl[k];
+			int a, b, col; uint64_t pri;
+			cons_fetch(A, J, nA, c, a, b, pri, col);
+			unsigned long long bid = ((unsigned long long)(round + 1) << 56) | pri;
+			bool da = body_is_dynamic(B, a), db = body_is_dynamic(B, b);
+			bool win = (!da || ld_u64(&K.claim[a]) == bid) && (!db || ld_u64(&K.claim[b]) == bid);
+			if(win){
+				unsigned long long m = (da ? ld_u64(&K.bmask[a]) : 0ull) | (db ? ld_u64(&K.bmask[b]) : 0ull);
+				unsigned long long freebits = ~m & ((1ull << CPB_OVERFLOW_COLOUR) - 1ull);
+				int colour = (freebits ? __ffsll((long long)freebits) - 1 : CPB_OVERFLOW_COLOUR);
+				if(colour != CPB_OVERFLOW_COLOUR){
+					unsigned long long bit = 1ull << colour;
+					if(da) atomicOr(&K.bmask[a], bit);
+					if(db) atomicOr(&K.bmask[b], bit);
+				}
+				cons_set_colour(A, J, K, shist, nA, c, colour);
+			} else lost = true;
 		}
-		if(c < nA){ A.colour[c] = colour; atomicAdd(&K.ccount[colour], 1); }
-		else { J.colour[c - nA] = colour; atomicAdd(&K.jcount[colour], 1); }
-		atomicMax(&C->n_colours, colour + 1);
+		int slot = cpb_warp_append(&K.wl_n[round + 1], lost);
+		if(lost) next[slot] = c;
 	}
-	if(lost) atomicAdd(&K.remaining[round], lost);
 }
 
-// exclusive prefix of the per-colour counts (single thread; 64 entries)
-CPB_DEVICE void colour_starts(const DColour &K){
-	int ra = 0, rj = 0;
+// exclusive prefix of the per-colour counts (single thread; 64 entries) + number of colours in use
+CPB_DEVICE void colour_starts(const DColour &K, DCounters *C){
+	int ra = 0, rj = 0, ncol = 0;
 	for(int c = 0; c <= CPB_MAX_COLOURS; c++){
 		int na = (c < CPB_MAX_COLOURS ? K.ccount[c] : 0), nj = (c < CPB_MAX_COLOURS ? K.jcount[c] : 0);
 		K.cstart[c] = ra; K.jstart[c] = rj;
 		K.ccursor[c] = 0; K.jcursor[c] = 0;
 		ra += na; rj += nj;
+		if(na + nj > 0) ncol = c + 1;
+	}
+	C->n_colours = ncol;
+}
+
+CPB_DEVICE void write_row(const DArbs &A, const DRows &R, int i, int r){
+	if(r >= R.cap) return;
+	R.arb[r] = i; R.ba[r] = A.ba[i]; R.bb[r] = A.bb[i];
+	int cnt = A.cnt[i];
+	// first-collision arbiters skip the warm start (cpArbiter.c:444): flag in the sign of cnt
+	R.cnt[r] = (A.state[i] == CPB200_ARB_FIRST_COLLISION ? -cnt : cnt);
+	R.n[r] = A.n[i]; R.svr[r] = A.svr[i]; R.u[r] = A.u[i];
+	for(int k = 0; k < cnt; k++){
+		int s = 2*i + k, d = k*R.cap + r;
+		R.r1[d] = A.r1[s]; R.r2[d] = A.r2[s];
+		R.nmass[d] = A.nmass[s]; R.tmass[d] = A.tmass[s]; R.bounce[d] = A.bounce[s]; R.bias[d] = A.bias[s];
+		R.jn[d] = A.jn[s]; R.jt[d] = A.jt[s]; R.jb[d] = A.jb[s];
 	}
 }
 
-// scatter arbiter records into colour-sorted SoA rows (the solver's coalesced working set)
-CPB_DEVICE void build_rows(const DArbs &A, const DJoints &J, const DRows &R, const DColour &K, int nA, int tid, int nth){
-	for(int i = tid; i < nA; i += nth){
-		if(A.active[i] != 1) continue;
-		int col = A.colour[i];
-		if(col < 0) continue;
-		int r = K.cstart[col] + atomicAdd(&K.ccursor[col], 1);
-		if(r >= R.cap) continue;
-		R.arb[r] = i; R.ba[r] = A.ba[i]; R.bb[r] = A.bb[i];
-		int cnt = A.cnt[i];
-		// first-collision arbiters skip the warm start (cpArbiter.c:444): flag in the sign of cnt
-		R.cnt[r] = (A.state[i] == CPB200_ARB_FIRST_COLLISION ? -cnt : cnt);
-		R.n[r] = A.n[i]; R.svr[r] = A.svr[i]; R.u[r] = A.u[i];
-		for(int k = 0; k < cnt; k++){
-			int s = 2*i + k, d = k*R.cap + r;
-			R.r1[d] = A.r1[s]; R.r2[d] = A.r2[s];
-			R.nmass[d] = A.nmass[s]; R.tmass[d] = A.tmass[s]; R.bounce[d] = A.bounce[s]; R.bias[d] = A.bias[s];
-			R.jn[d] = A.jn[s]; R.jt[d] = A.jt[s]; R.jb[d] = A.jb[s];
+// scatter arbiter records into colour-sorted SoA rows (the solver's coalesced working set).
+// scnt/sbase: per-CTA shared scratch [CPB_MAX_COLOURS] (NULL in the emulation build): a CTA counts its
+// rows per colour, reserves one contiguous range per colour with a single global atomic, then hands the
+// slots out with shared-memory atomics.
+CPB_DEVICE void build_rows(const DArbs &A, const DJoints &J, const DRows &R, const DColour &K, int *scnt, int *sbase, int nA, int tid, int nth){
+#ifndef CPB_EMU
+	if(scnt){
+		for(int i = tid; i < nA; i += nth){
+			if(A.active[i] != 1) continue;
+			int col = A.colour[i];
+			if(col >= 0) atomicAdd(&scnt[col], 1);
+		}
+		__syncthreads();
+		if(threadIdx.x < CPB_MAX_COLOURS){
+			int n = scnt[threadIdx.x];
+			sbase[threadIdx.x] = (n ? atomicAdd(&K.ccursor[threadIdx.x], n) : 0);
+			scnt[threadIdx.x] = 0;
+		}
+		__syncthreads();
+		for(int i = tid; i < nA; i += nth){
+			if(A.active[i] != 1) continue;
+			int col = A.colour[i];
+			if(col < 0) continue;
+			write_row(A, R, i, K.cstart[col] + sbase[col] + atomicAdd(&scnt[col], 1));
+		}
+		__syncthreads();
+		if(threadIdx.x < CPB_MAX_COLOURS) scnt[threadIdx.x] = 0;
+	} else
+#endif
+	{
+		for(int i = tid; i < nA; i += nth){
+			if(A.active[i] != 1) continue;
+			int col = A.colour[i];
+			if(col < 0) continue;
+			write_row(A, R, i, K.cstart[col] + atomicAdd(&K.ccursor[col], 1));
 		}
 	}
 	for(int j = tid; j < J.n; j += nth){
@@ -285,26 +366,37 @@ __device__ __forceinline__ unsigned long long global_ns(){ unsigned long long t;
 #define PROF(i) do { if(tid == 0) K.prof[i] = global_ns(); } while(0)
 
 // K10 + K11 in one persistent launch.
-__global__ void __launch_bounds__(256) k_colour_solve(DBodies B, DArbs A, DJoints J, DRows R, DColour K, DCounters *C, unsigned *bar, int iterations, double dt, double dt_coef)
+__global__ void __launch_bounds__(256) k_colour_solve(DBodies B, DArbs A, DJoints J, DRows R, DColour K, DCounters *C, unsigned *bar, int use_hints, int iterations, double dt, double dt_coef)
 {
+	__shared__ int s_hist[2*CPB_MAX_COLOURS];
+	__shared__ int s_base[CPB_MAX_COLOURS];
 	const int tid = CPB_TID, nth = CPB_NTHREADS;
 	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
+	if(threadIdx.x < 2*CPB_MAX_COLOURS) s_hist[threadIdx.x] = 0;
+	__syncthreads();
+	// flush this CTA's colour histogram (arbiters | joints) into the global one
+	#define HIST_FLUSH() do { __syncthreads(); if(threadIdx.x < 2*CPB_MAX_COLOURS){ int v_ = s_hist[threadIdx.x]; \
+		if(v_){ atomicAdd(threadIdx.x < CPB_MAX_COLOURS ? &K.ccount[threadIdx.x] : &K.jcount[threadIdx.x - CPB_MAX_COLOURS], v_); s_hist[threadIdx.x] = 0; } } } while(0)
 
 	PROF(0);
-	// K10: colouring rounds
+	// K10: colouring -- keep last step's colours, then Jones-Plassmann rounds over the worklist
+	colour_seed(B, A, J, K, s_hist, nA, use_hints, tid, nth);
+	HIST_FLUSH();
+	GRID_SYNC();
 	int rounds_done = 0;
 	for(int round = 0; round < CPB_MAX_COLOUR_ROUNDS; round++){
+		if(*((volatile int *)&K.wl_n[round]) == 0) break;
 		rounds_done = round + 1;
 		colour_phase_a(B, A, J, K, nA, round, tid, nth);
 		GRID_SYNC();
-		colour_phase_b(B, A, J, K, C, nA, round, tid, nth);
+		colour_phase_b(B, A, J, K, s_hist, nA, round, tid, nth);
+		HIST_FLUSH();
 		GRID_SYNC();
-		if(*((volatile int *)&K.remaining[round]) == 0) break;
 	}
 	PROF(1);
-	if(tid == 0){ colour_starts(K); K.prof[5] = (unsigned long long)rounds_done; }
+	if(tid == 0){ colour_starts(K, C); K.prof[5] = (unsigned long long)rounds_done; K.prof[6] = (unsigned long long)K.wl_n[0]; }
 	GRID_SYNC();
-	build_rows(A, J, R, K, nA, tid, nth);
+	build_rows(A, J, R, K, s_hist, s_base, nA, tid, nth);
 	GRID_SYNC();
 	PROF(2);
 
@@ -330,19 +422,23 @@ __global__ void __launch_bounds__(256) k_colour_solve(DBodies B, DArbs A, DJoint
 }
 #endif
 
-// kernels used by the emulation build (and available as a multi-launch variant)
+// kernels used by the emulation build (multi-launch variant of the same phases)
+__global__ void k_colour_seed(DBodies B, DArbs A, DJoints J, DColour K, int use_hints){
+	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
+	colour_seed(B, A, J, K, (int *)NULL, nA, use_hints, CPB_TID, CPB_NTHREADS);
+}
 __global__ void k_colour_a(DBodies B, DArbs A, DJoints J, DColour K, int round){
 	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
 	colour_phase_a(B, A, J, K, nA, round, CPB_TID, CPB_NTHREADS);
 }
-__global__ void k_colour_b(DBodies B, DArbs A, DJoints J, DColour K, DCounters *C, int round){
+__global__ void k_colour_b(DBodies B, DArbs A, DJoints J, DColour K, int round){
 	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
-	colour_phase_b(B, A, J, K, C, nA, round, CPB_TID, CPB_NTHREADS);
+	colour_phase_b(B, A, J, K, (int *)NULL, nA, round, CPB_TID, CPB_NTHREADS);
 }
-__global__ void k_colour_finish(DArbs A, DJoints J, DRows R, DColour K, int stage){
+__global__ void k_colour_finish(DArbs A, DJoints J, DRows R, DColour K, DCounters *C, int stage){
 	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
-	if(stage == 0){ if(CPB_TID == 0) colour_starts(K); }
-	else build_rows(A, J, R, K, nA, CPB_TID, CPB_NTHREADS);
+	if(stage == 0){ if(CPB_TID == 0) colour_starts(K, C); }
+	else build_rows(A, J, R, K, (int *)NULL, (int *)NULL, nA, CPB_TID, CPB_NTHREADS);
 }
 __global__ void k_solve_colour(DBodies B, DRows R, DJoints J, DColour K, int colour, int mode, double dt, double dt_coef){
 	if(colour == CPB_OVERFLOW_COLOUR){ if(CPB_TID == 0) solve_overflow(B, R, J, K, mode, dt, dt_coef); }

@@ -111,6 +111,8 @@ struct cpb200_world {
 
 	void *d_stage; size_t stage_bytes;   // device staging for host <-> SoA conversion kernels
 	unsigned *d_barrier;    // grid barrier words of the persistent solver
+	bool hints_valid;       // last step's colours may seed this step's colouring
+	int wl_cap; AllocGroup gW;
 	int force_blocks;       // validation hook: fixed persistent grid size (0 = automatic)
 	int last_active;        // active arbiters seen at the last host read-back (grid sizing hint)
 	double *d_scratch;      // small scratch (collide_one output, stats)
@@ -216,7 +218,7 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	cudaMalloc(&p, sizeof(DCounters)); w->C = (DCounters *)p; cudaMemsetAsync(w->C, 0, sizeof(DCounters), w->stream);
 	cudaMallocHost(&p, sizeof(DCounters)); w->hC = (DCounters *)p; memset(w->hC, 0, sizeof(DCounters));
 	cudaMalloc(&p, sizeof(unsigned)*8); w->d_barrier = (unsigned *)p; cudaMemsetAsync(w->d_barrier, 0, sizeof(unsigned)*8, w->stream);
-	w->last_active = 0; w->force_blocks = 0; w->d_stage = NULL; w->stage_bytes = 0;
+	w->last_active = 0; w->force_blocks = 0; w->hints_valid = false; w->wl_cap = 0; w->d_stage = NULL; w->stage_bytes = 0;
 	cudaMalloc(&p, sizeof(double)*64); w->d_scratch = (double *)p;
 	cudaMallocHost(&p, sizeof(double)*64); w->h_scratch = (double *)p;
 	if(!w->d_spaces || !w->C || !w->hC){ cpb_set_error("device allocation failed"); delete w; return NULL; }
@@ -228,7 +230,7 @@ extern "C" void cpb200_world_destroy(cpb200_world *w)
 	if(!w) return;
 	cudaSetDevice(w->device);
 	cudaStreamSynchronize(w->stream);
-	w->gB.release(); w->gS.release(); w->gJ.release(); w->gA.release(); w->gK.release(); w->gV.release(); w->gP.release(); w->gI.release();
+	w->gB.release(); w->gS.release(); w->gJ.release(); w->gA.release(); w->gK.release(); w->gV.release(); w->gP.release(); w->gI.release(); w->gW.release();
 	cudaFree(w->d_barrier);
 	if(w->d_stage) cudaFree(w->d_stage);
 	cudaFree(w->d_spaces); cudaFree(w->C); cudaFreeHost(w->hC); cudaFree(w->d_scratch); cudaFreeHost(w->h_scratch);
@@ -343,7 +345,8 @@ extern "C" int cpb200_world_set_bodies(cpb200_world *w, int n, const cpb200_body
 	DA(w->gK, w->K.claim, n); DA(w->gK, w->K.bmask, n);
 	DA(w->gK, w->K.ccount, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.cstart, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.ccursor, CPB_MAX_COLOURS + 1);
 	DA(w->gK, w->K.jcount, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.jstart, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.jcursor, CPB_MAX_COLOURS + 1);
-	DA(w->gK, w->K.remaining, CPB_MAX_COLOUR_ROUNDS + 1); DA(w->gK, w->K.prof, 8);
+	DA(w->gK, w->K.wl_n, CPB_MAX_COLOUR_ROUNDS + 2); DA(w->gK, w->K.prof, 8);
+	w->hints_valid = false; // body types / masses may have changed: colour from scratch once
 	w->gI.release();
 	DA(w->gI, w->I.parent, n); DA(w->gI, w->I.wake, n); DA(w->gI, w->I.comp_active, n); DA(w->gI, w->I.woken, n);
 	int r = cpb200_world_update_bodies(w, 0, n, bodies);
@@ -391,6 +394,15 @@ extern "C" int cpb200_world_reserve(cpb200_world *w, int max_pairs, int max_arbi
 	return 0;
 }
 
+static int ensure_worklists(cpb200_world *w, int need)
+{
+	if(need <= w->wl_cap) return 0;
+	w->gW.release();
+	DA(w->gW, w->K.wl[0], need); DA(w->gW, w->K.wl[1], need);
+	w->wl_cap = need;
+	return 0;
+}
+
 static int alloc_pairs(cpb200_world *w, int cap)
 {
 	w->gP.release();
@@ -416,7 +428,7 @@ static int alloc_arbs(cpb200_world *w, int cap)
 		DA(w->gA, A.r1, 2*(size_t)cap); DA(w->gA, A.r2, 2*(size_t)cap);
 		DA(w->gA, A.nmass, 2*(size_t)cap); DA(w->gA, A.tmass, 2*(size_t)cap); DA(w->gA, A.bounce, 2*(size_t)cap); DA(w->gA, A.bias, 2*(size_t)cap);
 		DA(w->gA, A.jn, 2*(size_t)cap); DA(w->gA, A.jt, 2*(size_t)cap); DA(w->gA, A.jb, 2*(size_t)cap); DA(w->gA, A.hash, 2*(size_t)cap);
-		DA(w->gA, A.colour, cap); DA(w->gA, A.pri, cap);
+		DA(w->gA, A.colour, cap); DA(w->gA, A.pri, cap); DA(w->gA, A.hint, cap);
 		DTable &T = w->T[k];
 		T.mask = tcap - 1;
 		DA(w->gA, T.keys, tcap); DA(w->gA, T.vals, tcap);
@@ -535,6 +547,7 @@ extern "C" int cpb200_world_set_shapes(cpb200_world *w, int n, const cpb200_shap
 		}
 	}
 	w->cache_dirty = true;
+	w->hints_valid = false;
 	return world_sync(w);
 }
 
@@ -585,7 +598,7 @@ extern "C" int cpb200_world_set_joints(cpb200_world *w, int n, const cpb200_join
 	DA(w->gJ, J.type, n); DA(w->gJ, J.a, n); DA(w->gJ, J.b, n); DA(w->gJ, J.max_force, n); DA(w->gJ, J.max_bias, n); DA(w->gJ, J.bias_coef, n);
 	DA(w->gJ, J.anchor_a, n); DA(w->gJ, J.anchor_b, n); DA(w->gJ, J.prm, n);
 	DA(w->gJ, J.r1, n); DA(w->gJ, J.r2, n); DA(w->gJ, J.nrm, n); DA(w->gJ, J.nmass, n); DA(w->gJ, J.k, n); DA(w->gJ, J.bias, n); DA(w->gJ, J.acc, n);
-	DA(w->gJ, J.aux0, n); DA(w->gJ, J.aux1, n); DA(w->gJ, J.jspring, n); DA(w->gJ, J.colour, n); DA(w->gJ, J.row, n); DA(w->gJ, J.pri, n);
+	DA(w->gJ, J.aux0, n); DA(w->gJ, J.aux1, n); DA(w->gJ, J.jspring, n); DA(w->gJ, J.colour, n); DA(w->gJ, J.row, n); DA(w->gJ, J.pri, n); DA(w->gJ, J.hint, n);
 	if(upload(w, J.type, type) || upload(w, J.a, a) || upload(w, J.b, b) || upload(w, J.max_force, max_force) || upload(w, J.max_bias, max_bias) ||
 	   upload(w, J.anchor_a, anchor_a) || upload(w, J.anchor_b, anchor_b) || upload(w, J.prm, prm) || upload(w, J.acc, acc) || upload(w, J.aux0, aux0) || upload(w, J.pri, jpri)) return -1;
 	if(w->d_nocollide){ cudaFree(w->d_nocollide); w->d_nocollide = NULL; }
@@ -597,6 +610,7 @@ extern "C" int cpb200_world_set_joints(cpb200_world *w, int n, const cpb200_join
 		CPB_CHECK(cudaMemcpyAsync(w->d_nocollide, nocollide.data(), sizeof(uint64_t)*nocollide.size(), cudaMemcpyHostToDevice, w->stream));
 	}
 	w->joints_dt = 0.0; // force bias_coef refresh
+	w->hints_valid = false;
 	return world_sync(w);
 }
 
@@ -773,7 +787,10 @@ extern "C" int cpb200_world_step(cpb200_world *w, double dt)
 		if(nb){ cudaMemsetAsync(K.claim, 0, sizeof(unsigned long long)*(size_t)nb, st); cudaMemsetAsync(K.bmask, 0, sizeof(unsigned long long)*(size_t)nb, st); }
 		cudaMemsetAsync(K.ccount, 0, sizeof(int)*(CPB_MAX_COLOURS + 1), st);
 		cudaMemsetAsync(K.jcount, 0, sizeof(int)*(CPB_MAX_COLOURS + 1), st);
-		cudaMemsetAsync(K.remaining, 0, sizeof(int)*(CPB_MAX_COLOUR_ROUNDS + 1), st);
+		cudaMemsetAsync(K.wl_n, 0, sizeof(int)*(CPB_MAX_COLOUR_ROUNDS + 2), st);
+		if(ensure_worklists(w, Ac.cap + J.n + 64)) return -1;
+		int use_hints = (w->hints_valid ? 1 : 0);
+		w->hints_valid = true;
 #ifndef CPB_EMU
 		{
 			DCounters *C = w->C; DRows R = w->R; unsigned *bar = w->d_barrier;
@@ -782,19 +799,20 @@ extern "C" int cpb200_world_step(cpb200_world *w, double dt)
 			int est_cons = std::max(w->last_active, nb) + J.n;
 			int blocks = std::max(1, std::min(w->coop_blocks, cpb_div_up(est_cons + 1, 256)));
 			if(w->force_blocks > 0) blocks = std::min(w->coop_blocks, w->force_blocks);
-			void *args[] = {&B, &Ac, &J, &R, &K, &C, &bar, &iterations, &dt, &dt_coef};
+			void *args[] = {&B, &Ac, &J, &R, &K, &C, &bar, &use_hints, &iterations, &dt, &dt_coef};
 			CPB_CHECK(cudaLaunchCooperativeKernel((void *)k_colour_solve, dim3(blocks), dim3(256), args, 0, st));
 			g_cpb_launches++;
 		}
 #else
 		{
+			LAUNCH(k_colour_seed, 4, 64, st, B, Ac, J, K, use_hints);
 			for(int round = 0; round < CPB_MAX_COLOUR_ROUNDS; round++){
+				if(K.wl_n[round] == 0) break;
 				LAUNCH(k_colour_a, 4, 64, st, B, Ac, J, K, round);
-				LAUNCH(k_colour_b, 4, 64, st, B, Ac, J, K, w->C, round);
-				if(K.remaining[round] == 0) break;
+				LAUNCH(k_colour_b, 4, 64, st, B, Ac, J, K, round);
 			}
-			LAUNCH(k_colour_finish, 1, 32, st, Ac, J, w->R, K, 0);
-			LAUNCH(k_colour_finish, 4, 64, st, Ac, J, w->R, K, 1);
+			LAUNCH(k_colour_finish, 1, 32, st, Ac, J, w->R, K, w->C, 0);
+			LAUNCH(k_colour_finish, 4, 64, st, Ac, J, w->R, K, w->C, 1);
 			int ncol = w->C->n_colours;
 			for(int pass = 0; pass <= iterations; pass++){
 				for(int c = 0; c < ncol; c++) LAUNCH(k_solve_colour, 4, 64, st, B, w->R, J, K, c, (pass == 0 ? 0 : 1), dt, dt_coef);
@@ -1094,7 +1112,7 @@ extern "C" int cpb200_world_get_stage_times(cpb200_world *w, int cap, float *use
 	return ST_COUNT;
 }
 
-extern "C" int cpb200_world_get_solver_profile(cpb200_world *w, double *usec5)
+extern "C" int cpb200_world_get_solver_profile(cpb200_world *w, double *usec5 /* [6] */)
 {
 	if(!w || !w->K.prof){ cpb_set_error("no solver profile"); return -1; }
 	unsigned long long t[8];
@@ -1102,6 +1120,7 @@ extern "C" int cpb200_world_get_solver_profile(cpb200_world *w, double *usec5)
 	if(world_sync(w)) return -1;
 	for(int i = 0; i < 4; i++) usec5[i] = (double)(t[i + 1] - t[i])*1e-3;
 	usec5[4] = (double)t[5];
+	usec5[5] = (double)t[6];
 	return 0;
 }
 

@@ -348,9 +348,9 @@ class World:
         self._ck(self.lib.cpb200_world_set_profiling(self.w, int(bool(on))))
 
     def solver_profile(self):
-        buf = np.zeros(5)
+        buf = np.zeros(6)
         self._ck(self.lib.cpb200_world_get_solver_profile(self.w, buf.ctypes.data))
-        return dict(zip(['colour_us', 'rows_us', 'warm_us', 'iterate_us', 'rounds'], buf.tolist()))
+        return dict(zip(['colour_us', 'rows_us', 'warm_us', 'iterate_us', 'rounds', 'recoloured'], buf.tolist()))
 
     def stage_times(self):
         buf = np.zeros(32, dtype=np.float32)

@@ -240,8 +240,9 @@ CPB200_API int cpb200_world_collide_pair(cpb200_world *w, int shape_a, int shape
 CPB200_API int cpb200_world_get_stage_times(cpb200_world *w, int cap, float *usec);
 CPB200_API const char *cpb200_stage_name(int i);
 /* Inside the persistent colour+solve kernel of the last step (device globaltimer): microseconds spent
- * colouring, building rows, warm starting, iterating; usec5[4] = colouring rounds. */
-CPB200_API int cpb200_world_get_solver_profile(cpb200_world *w, double *usec5);
+ * colouring, building rows, warm starting, iterating; out6[4] = colouring rounds, out6[5] = constraints that
+ * had to be (re)coloured (the rest kept last step's colour). */
+CPB200_API int cpb200_world_get_solver_profile(cpb200_world *w, double *out6);
 /* Enable (1) / disable (0) per-stage event timing (adds syncs; off by default). */
 CPB200_API int cpb200_world_set_profiling(cpb200_world *w, int on);
 
