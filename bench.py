@@ -207,16 +207,13 @@ def run_ours(args):
     w.set_profiling(False)
     st2 = w.stats()
 
-    t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    totals = torch.tensor([float(nb), float(st["n_contacts"]), float(st["n_arbiters"]), float(st["n_pairs"]), st["kinetic_energy"]], dtype=torch.float64, device="cuda")
-    maxes = torch.tensor([st["max_penetration"]], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        # the only inter-GPU traffic of the batched layout: step statistics (north star)
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(totals, op=dist.ReduceOp.SUM)
-        dist.all_reduce(maxes, op=dist.ReduceOp.MAX)
-    t_max = float(t_ms.item()) * 1e-3
-    total_bodies, total_contacts, total_arbs, total_pairs, total_ke = (float(x) for x in totals.tolist())
+    # the only inter-GPU traffic: timings (MAX) and step statistics (SUM / MAX) -- north star
+    from chipmunk2d_b200.sharding import reduce_step_stats
+    sums, mx, t_ms_max = reduce_step_stats(dist, torch, "cuda", [float(nb), float(st["n_contacts"]), float(st["n_arbiters"]), float(st["n_pairs"]), st["kinetic_energy"]],
+                                           [st["max_penetration"]], ms)
+    t_max = t_ms_max * 1e-3
+    total_bodies, total_contacts, total_arbs, total_pairs, total_ke = sums
+    maxes = torch.tensor(mx, dtype=torch.float64)
 
     # ---- e2e through the public C API (host buffers every step) ----
     e2e = None
