@@ -142,14 +142,13 @@ def run_reference(args):
     base = cpu_baseline_sample(args.workload, steps, warm)
     _, cfg = build_scenes(args.workload, 0, for_reference=False)
     if base is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"})
         return
     line = {"impl": "reference", "metric": "body_steps_per_sec", "value": base["value"], "unit": "body-steps/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": cfg, "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
-    sys.stdout.flush()
+    emit(line)
     os._exit(0)
 
 
@@ -168,6 +167,7 @@ def run_ours(args):
     from chipmunk2d_b200.api import load_scene_lib
     from oracle.ref import SceneSpace
 
+    os.environ["CPB200_DEVICE"] = str(local_rank)   # spaces created through the C API follow the rank's GPU
     scenes, cfg = build_scenes(args.workload, rank)
     dt = scenes[0].dt
     nb = sum(sc.n_dynamic() for sc in scenes)
@@ -250,6 +250,11 @@ def run_ours(args):
     except Exception as exc:  # keep the device-resident number even if the API libs are missing
         e2e = {"value": None, "unit": "body-steps/s", "error": str(exc)}
 
+    if dist is not None:
+        # every rank leaves the process group together, BEFORE rank 0 goes on to its CPU-only work
+        dist.barrier()
+        dist.destroy_process_group()
+        dist = None
     if rank != 0:
         return
 
@@ -302,13 +307,28 @@ def run_ours(args):
         "stage_us": acc, "solver_us": sp,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
-    sys.stdout.flush()
-    if dist is not None:
-        dist.destroy_process_group()
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's original stdout; everything else any library prints while
+    the benchmark runs (e.g. NCCL's version banner) was diverted to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

@@ -266,34 +266,45 @@ static inline double4 ld_vel(const double4 *p){ return *p; }
 static inline void st_vel(double4 *p, double4 v){ *p = v; }
 #endif
 
+// Solver rows are streamed once per pass and never reused before the next pass evicts them: load/store them
+// with the evict-first policy (ld.global.cs / st.global.cs) so the ~80 MB of body velocities that every
+// pass gathers again stays resident in the 126 MB L2.
+#if !defined(CPB_EMU) && !defined(CPB_NO_ROW_STREAM)
+#define ROW_LD(p) __ldcs(p)
+#define ROW_ST(p, v) __stcs((p), (v))
+#else
+#define ROW_LD(p) (*(p))
+#define ROW_ST(p, v) (*(p) = (v))
+#endif
+
 // one colour-sorted row: mode 0 = warm start, 1 = iteration
 CPB_DEVICE void solve_row(const DBodies &B, const DRows &R, int r, int mode, double dt_coef){
-	int ba = R.ba[r], bb = R.bb[r];
-	int cnt = R.cnt[r];
+	int ba = ROW_LD(&R.ba[r]), bb = ROW_LD(&R.bb[r]);
+	int cnt = ROW_LD(&R.cnt[r]);
 	bool first = (cnt < 0);
 	if(first) cnt = -cnt;
 	if(mode == 0 && first) return;
 	V2 mia = B.MI[ba], mib = B.MI[bb];
 	double4 Va = ld_vel(&B.V[ba]), Vb = ld_vel(&B.V[bb]);
-	V2 n = R.n[r];
+	V2 n = ROW_LD(&R.n[r]);
 	bool dyn_a = (mia.x != 0.0 || mia.y != 0.0), dyn_b = (mib.x != 0.0 || mib.y != 0.0);
 	if(mode == 0){
 		for(int k = 0; k < cnt; k++){
 			int d = k*R.cap + r;
-			contact_apply_cached(Va, Vb, mia, mib, n, R.r1[d], R.r2[d], R.jn[d], R.jt[d], dt_coef);
+			contact_apply_cached(Va, Vb, mia, mib, n, ROW_LD(&R.r1[d]), ROW_LD(&R.r2[d]), ROW_LD(&R.jn[d]), ROW_LD(&R.jt[d]), dt_coef);
 		}
 		if(dyn_a) st_vel(&B.V[ba], Va);
 		if(dyn_b) st_vel(&B.V[bb], Vb);
 		return;
 	}
 	double4 VBa = ld_vel(&B.VB[ba]), VBb = ld_vel(&B.VB[bb]);
-	V2 svr = R.svr[r];
-	double u = R.u[r];
+	V2 svr = ROW_LD(&R.svr[r]);
+	double u = ROW_LD(&R.u[r]);
 	for(int k = 0; k < cnt; k++){
 		int d = k*R.cap + r;
-		double jn = R.jn[d], jt = R.jt[d], jb = R.jb[d];
-		contact_apply(Va, Vb, VBa, VBb, mia, mib, n, svr, u, R.r1[d], R.r2[d], R.nmass[d], R.tmass[d], R.bias[d], R.bounce[d], jn, jt, jb);
-		R.jn[d] = jn; R.jt[d] = jt; R.jb[d] = jb;
+		double jn = ROW_LD(&R.jn[d]), jt = ROW_LD(&R.jt[d]), jb = ROW_LD(&R.jb[d]);
+		contact_apply(Va, Vb, VBa, VBb, mia, mib, n, svr, u, ROW_LD(&R.r1[d]), ROW_LD(&R.r2[d]), ROW_LD(&R.nmass[d]), ROW_LD(&R.tmass[d]), ROW_LD(&R.bias[d]), ROW_LD(&R.bounce[d]), jn, jt, jb);
+		ROW_ST(&R.jn[d], jn); ROW_ST(&R.jt[d], jt); ROW_ST(&R.jb[d], jb);
 	}
 	if(dyn_a){ st_vel(&B.V[ba], Va); st_vel(&B.VB[ba], VBa); }
 	if(dyn_b){ st_vel(&B.V[bb], Vb); st_vel(&B.VB[bb], VBb); }
@@ -366,7 +377,10 @@ __device__ __forceinline__ unsigned long long global_ns(){ unsigned long long t;
 #define PROF(i) do { if(tid == 0) K.prof[i] = global_ns(); } while(0)
 
 // K10 + K11 in one persistent launch.
-__global__ void __launch_bounds__(256) k_colour_solve(DBodies B, DArbs A, DJoints J, DRows R, DColour K, DCounters *C, unsigned *bar, int use_hints, int iterations, double dt, double dt_coef)
+#ifndef CPB_SOLVE_MIN_BLOCKS
+#define CPB_SOLVE_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(256, CPB_SOLVE_MIN_BLOCKS) k_colour_solve(DBodies B, DArbs A, DJoints J, DRows R, DColour K, DCounters *C, unsigned *bar, int use_hints, int iterations, double dt, double dt_coef)
 {
 	__shared__ int s_hist[2*CPB_MAX_COLOURS];
 	__shared__ int s_base[CPB_MAX_COLOURS];

@@ -190,7 +190,7 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 		int per_sm = 1;
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colour_solve, 256, 0);
 		if(per_sm < 1) per_sm = 1;
-		if(per_sm > 2) per_sm = 2;
+		if(per_sm > 4) per_sm = 4;
 		w->coop_blocks = w->sm_count*per_sm;
 	}
 #endif
