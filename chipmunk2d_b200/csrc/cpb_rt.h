@@ -44,10 +44,12 @@ extern emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 struct double2 { double x, y; };
 struct double4 { double x, y, z, w; };
 struct int2 { int x, y; };
+struct int4 { int x, y, z, w; };
 struct uint2 { unsigned x, y; };
 static inline double2 make_double2(double x, double y){ double2 r = {x, y}; return r; }
 static inline double4 make_double4(double x, double y, double z, double w){ double4 r = {x, y, z, w}; return r; }
 static inline int2 make_int2(int x, int y){ int2 r = {x, y}; return r; }
+static inline int4 make_int4(int x, int y, int z, int w){ int4 r = {x, y, z, w}; return r; }
 
 typedef int cudaError_t;
 typedef void *cudaStream_t;

@@ -26,8 +26,8 @@ struct DBodies {
 	V2 *rot;        // (cos a, sin a)  = transform.a, transform.b
 	V2 *txy;        // transform.tx, transform.ty
 	V2 *cog;
-	double4 *V;     // (v.x, v.y, w, unused)          solver-hot: one 32-byte sector
-	double4 *VB;    // (v_bias.x, v_bias.y, w_bias, unused)
+	double4 *V;     // (v.x, v.y, w, m_inv)           solver-hot: one 32-byte sector
+	double4 *VB;    // (v_bias.x, v_bias.y, w_bias, i_inv)
 	V2 *MI;         // (m_inv, i_inv)
 	V2 *M;          // (m, i)
 	V2 *force;      // f
@@ -141,6 +141,11 @@ struct DBvh {
 	int2 *nsp;             // [2n-1] node space-id range
 	int *flags;            // [n-1] refit arrival counters
 	double *bounds;        // [4] world bounds l b r t
+	int *nskip;            // [2n-1] subtree skip key: last leaf position if every leaf below is active, INT_MAX otherwise
+	// traversal layout, packed after the refit: one dependent load per level
+	double4 *cbox;         // [2(n-1)] boxes of the two children of internal node i at [2i], [2i+1]
+	int4 *cinfo;           // [n-1] (left, right, left skip key, right skip key)
+	int4 *cspace;          // [n-1] (left space min, max, right space min, max)
 };
 
 // pair lists by class: 0 circle-circle, 1 circle-segment, 2 everything that needs GJK

@@ -21,7 +21,7 @@ __global__ void k_integrate_pos(DBodies B, double dt)
 	B.ang[i] = a;
 	B.rot[i] = rot;
 	B.txy[i] = v2(p.x - (cg.x*rot.x - cg.y*rot.y), p.y - (cg.x*rot.y + cg.y*rot.x));
-	B.VB[i] = make_double4(0.0, 0.0, 0.0, 0.0);
+	B.VB[i] = make_double4(0.0, 0.0, 0.0, VB.w);   // lane w carries i_inv for the solver
 }
 
 // Translation part of SetTransform for bodies whose rotation came from the host
@@ -86,7 +86,7 @@ __global__ void k_integrate_vel(DBodies B, const DSpace *__restrict__ spaces, do
 	double damping = sp.damping_dt;
 	V2 v = vadd(vmul(v2(V.x, V.y), damping), vmul(vadd(sp.gravity, vmul(f, mi.x)), dt));
 	double w = V.z*damping + B.torque[i]*mi.y*dt;
-	B.V[i] = make_double4(v.x, v.y, w, 0.0);
+	B.V[i] = make_double4(v.x, v.y, w, V.w);         // lane w carries m_inv for the solver
 	B.force[i] = v2(0.0, 0.0);
 	B.torque[i] = 0.0;
 }

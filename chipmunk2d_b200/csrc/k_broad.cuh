@@ -137,8 +137,12 @@ __global__ void k_bvh_leaves(DBvh T, DShapes S, DBodies B)
 	if(i >= T.n) return;
 	int s = T.leaf_shape[i];
 	T.nbb[(T.n - 1) + i] = S.bb[s];
-	int sp = B.space[S.body[s]];
+	int body = S.body[s];
+	int sp = B.space[body];
 	T.nsp[(T.n - 1) + i] = make_int2(sp, sp);
+	// a query leaf i only needs partners at Morton positions > i unless the partner is inactive
+	// (static / sleeping shapes never query): an all-active subtree ending at or before i is skipped
+	T.nskip[(T.n - 1) + i] = (shape_is_active(B, body) ? i : 0x7fffffff);
 }
 
 #ifndef CPB_EMU
@@ -151,6 +155,23 @@ __device__ __forceinline__ int2 ld_cg_i2(const int2 *p){ return __ldcg(p); }
 static inline double4 ld_cg4(const double4 *p){ return *p; }
 static inline int2 ld_cg_i2(const int2 *p){ return *p; }
 #endif
+#ifndef CPB_EMU
+__device__ __forceinline__ int ld_cg_i(const int *p){ return __ldcg(p); }
+#else
+static inline int ld_cg_i(const int *p){ return *p; }
+#endif
+
+// pack the children's boxes / skip keys / space ranges next to their parent (traversal layout)
+__global__ void k_bvh_pack(DBvh T)
+{
+	int i = CPB_TID;
+	if(i >= T.n - 1) return;
+	int l = T.left[i], r = T.right[i];
+	T.cbox[2*i] = T.nbb[l]; T.cbox[2*i + 1] = T.nbb[r];
+	T.cinfo[i] = make_int4(l, r, T.nskip[l], T.nskip[r]);
+	int2 a = T.nsp[l], b = T.nsp[r];
+	T.cspace[i] = make_int4(a.x, a.y, b.x, b.y);
+}
 
 __global__ void k_bvh_refit(DBvh T)
 {
@@ -170,6 +191,8 @@ __global__ void k_bvh_refit(DBvh T)
 		T.nbb[cur] = make_double4(fmin(a.x, b.x), fmin(a.y, b.y), fmax(a.z, b.z), fmax(a.w, b.w));
 		int2 sa = ld_cg_i2(&T.nsp[l]), sb = ld_cg_i2(&T.nsp[r]);
 		T.nsp[cur] = make_int2(sa.x < sb.x ? sa.x : sb.x, sa.y > sb.y ? sa.y : sb.y);
+		int ka = ld_cg_i(&T.nskip[l]), kb = ld_cg_i(&T.nskip[r]);
+		T.nskip[cur] = (ka > kb ? ka : kb);
 		cur = T.parent[cur];
 	}
 }
@@ -236,21 +259,19 @@ __global__ void k_bvh_pairs(DBvh T, DShapes S, DBodies B, DPairs P, const uint64
 	int sp = 0;
 	int node = 0;
 	for(;;){
-		int child[2] = {T.left[node], T.right[node]};
+		int4 ci = T.cinfo[node];
+		double4 box[2] = {T.cbox[2*node], T.cbox[2*node + 1]};
+		int4 cs = make_int4(0, 0, 0, 0);
+		if(multi_space) cs = T.cspace[node];
 		int next = -1;
 #pragma unroll
 		for(int c = 0; c < 2; c++){
-			int ch = child[c];
-			double4 cb = T.nbb[ch];
-			bool hit = bb_intersects(q, cb);
-			if(hit && multi_space){ int2 r = T.nsp[ch]; hit = (r.x <= qsp && qsp <= r.y); }
-			if(!hit) continue;
+			int ch = (c ? ci.y : ci.x), skip = (c ? ci.w : ci.z);
+			if(skip <= i) continue;   // every leaf below is active and at/before i: those leaves report the pair
+			if(!bb_intersects(q, box[c])) continue;
+			if(multi_space){ int lo = (c ? cs.z : cs.x), hi = (c ? cs.w : cs.y); if(qsp < lo || qsp > hi) continue; }
 			if(ch >= n - 1){
-				int j = ch - (n - 1);
-				if(j == i) continue;
-				int sj = T.leaf_shape[j];
-				// both active: the lower Morton position reports the pair
-				if(j < i && shape_is_active(B, S.body[sj])) continue;
+				int sj = T.leaf_shape[ch - (n - 1)];
 				if(query_reject(S, si, sj, nocollide, n_nocollide)) continue;
 				emit_pair(S, P, overflow, si, sj);
 			} else {

@@ -284,11 +284,11 @@ CPB_DEVICE void solve_row(const DBodies &B, const DRows &R, int r, int mode, dou
 	bool first = (cnt < 0);
 	if(first) cnt = -cnt;
 	if(mode == 0 && first) return;
-	V2 mia = B.MI[ba], mib = B.MI[bb];
 	double4 Va = ld_vel(&B.V[ba]), Vb = ld_vel(&B.V[bb]);
 	V2 n = ROW_LD(&R.n[r]);
-	bool dyn_a = (mia.x != 0.0 || mia.y != 0.0), dyn_b = (mib.x != 0.0 || mib.y != 0.0);
 	if(mode == 0){
+		V2 mia = B.MI[ba], mib = B.MI[bb];
+		bool dyn_a = (mia.x != 0.0 || mia.y != 0.0), dyn_b = (mib.x != 0.0 || mib.y != 0.0);
 		for(int k = 0; k < cnt; k++){
 			int d = k*R.cap + r;
 			contact_apply_cached(Va, Vb, mia, mib, n, ROW_LD(&R.r1[d]), ROW_LD(&R.r2[d]), ROW_LD(&R.jn[d]), ROW_LD(&R.jt[d]), dt_coef);
@@ -298,6 +298,9 @@ CPB_DEVICE void solve_row(const DBodies &B, const DRows &R, int r, int mode, dou
 		return;
 	}
 	double4 VBa = ld_vel(&B.VB[ba]), VBb = ld_vel(&B.VB[bb]);
+	// (m_inv, i_inv) ride in the spare lanes of the two velocity sectors
+	V2 mia = v2(Va.w, VBa.w), mib = v2(Vb.w, VBb.w);
+	bool dyn_a = (mia.x != 0.0 || mia.y != 0.0), dyn_b = (mib.x != 0.0 || mib.y != 0.0);
 	V2 svr = ROW_LD(&R.svr[r]);
 	double u = ROW_LD(&R.u[r]);
 	for(int k = 0; k < cnt; k++){

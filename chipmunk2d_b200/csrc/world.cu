@@ -297,8 +297,10 @@ __global__ void k_unpack_bodies(DBodies B, const cpb200_body_desc *__restrict__ 
 	int i = first + k;
 	if(d.space < 0 || d.space >= n_spaces){ *bad = 1; d.space = 0; }
 	B.pos[i] = v2(d.p[0], d.p[1]); B.ang[i] = d.a; B.rot[i] = v2(d.rot[0], d.rot[1]); B.cog[i] = v2(d.cog[0], d.cog[1]);
-	B.V[i] = make_double4(d.v[0], d.v[1], d.w, 0.0); B.VB[i] = make_double4(d.v_bias[0], d.v_bias[1], d.w_bias, 0.0);
 	bool dyn = (d.type == CPB200_BODY_DYNAMIC);
+	// the spare lanes of the two velocity sectors carry (m_inv, i_inv): the solver then touches two
+	// 32-byte sectors per body instead of three
+	B.V[i] = make_double4(d.v[0], d.v[1], d.w, dyn ? 1.0/d.m : 0.0); B.VB[i] = make_double4(d.v_bias[0], d.v_bias[1], d.w_bias, dyn ? 1.0/d.i : 0.0);
 	// m_inv / i_inv exactly as cpBodySetMass / SetMoment compute them (cpBody.c:246-270): 1/m, 0 for infinite mass
 	B.MI[i] = v2(dyn ? 1.0/d.m : 0.0, dyn ? 1.0/d.i : 0.0);
 	B.M[i] = v2(d.m, d.i);
@@ -513,6 +515,7 @@ extern "C" int cpb200_world_set_shapes(cpb200_world *w, int n, const cpb200_shap
 	int nn = (n > 0 ? n : 1);
 	DA(w->gV, T.keys, nn); DA(w->gV, T.leaf_shape, nn); DA(w->gV, T.left, nn); DA(w->gV, T.right, nn); DA(w->gV, T.parent, 2*nn);
 	DA(w->gV, T.nbb, 2*nn); DA(w->gV, T.nsp, 2*nn); DA(w->gV, T.flags, nn); DA(w->gV, T.bounds, 4);
+	DA(w->gV, T.nskip, 2*nn); DA(w->gV, T.cbox, 2*nn); DA(w->gV, T.cinfo, nn); DA(w->gV, T.cspace, nn);
 	DA(w->gV, w->keys_b, nn); DA(w->gV, w->vals_b, nn);
 	DA(w->gV, w->sort_tmp, cpb_sort_tmp_elems(nn) + 16);
 
@@ -729,6 +732,7 @@ extern "C" int cpb200_world_step(cpb200_world *w, double dt)
 		LAUNCH(k_bvh_build, grid_for(ns - 1, 256), 256, st, T);
 		LAUNCH(k_bvh_leaves, grid_for(ns, 256), 256, st, T, S, B);
 		LAUNCH(k_bvh_refit, grid_for(ns, 256), 256, st, T);
+		LAUNCH(k_bvh_pack, grid_for(ns - 1, 256), 256, st, T);
 		STAGE_END(w, ST_BVH_BUILD);
 		LAUNCH(k_bvh_pairs, grid_for(ns, 128), 128, st, T, S, B, w->P, (const uint64_t *)w->d_nocollide, w->n_nocollide, (int)(w->n_spaces > 1), &w->C->overflow);
 		STAGE_END(w, ST_BVH_PAIRS);
