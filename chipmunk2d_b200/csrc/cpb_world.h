@@ -58,6 +58,10 @@ struct DShapes {
 	V2 *wa, *wb, *wn;     // circle tc | segment ta, tb, tn
 	V2 *wpv, *wpn;        // [nv]
 	double4 *bb;          // (l, b, r, t)
+	// packed copies for the narrowphase's random gathers (one 32-byte sector instead of 3-6 scattered words)
+	double4 *mat;         // (e, u, surface_v.x, surface_v.y), static
+	double4 *circ;        // circles: (tc.x, tc.y, r, bits: body index | sensor << 31), rewritten by k_shape_cache
+	uint2 *ids;           // (hashid, hlocal)
 };
 
 // ---- arbiters + contacts (cpArbiter / cpContact, chipmunk_structs.h:101-145) ----

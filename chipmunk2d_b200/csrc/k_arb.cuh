@@ -75,24 +75,37 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 		int i = base + threadIdx.x;
 		bool have = false;
 		Manifold m; m.count = 0; m.id = 0; m.n = v2(0, 0);
-		int sa = 0, sb = 0, pi = -1;
+		int sa = 0, sb = 0, pi = -1, ba = 0, bb = 0;
+		bool sensor = false;
+		uint2 ida = {0u, 0u}, idb = {0u, 0u};
 		uint64_t key = 0;
 		if(i < np){
 			sa = pa[i]; sb = pb[i];
-			key = arb_key(S.hashid[sa], S.hashid[sb]);
-			pi = table_find(prev_table, key);
-			m.id = (pi >= 0 ? prev.gjkid[pi] : 0u);
-			NShape a = load_nshape(S, B, sa), b = load_nshape(S, B, sb);
-			if(CLS == 0) circle_to_circle(a, b, m);
-			else if(CLS == 1) circle_to_segment(a, b, m);
-			else collide_shapes(a, b, m);
+			ida = S.ids[sa]; idb = S.ids[sb];
+			key = arb_key(ida.x, idb.x);
+			if(CLS == 0){
+				// circle-circle: everything the test needs sits in one packed sector per shape
+				double4 ca = S.circ[sa], cb = S.circ[sb];
+				NShape a, b;
+				a.type = 0; a.a = v2(ca.x, ca.y); a.r = ca.z; b.type = 0; b.a = v2(cb.x, cb.y); b.r = cb.z;
+				unsigned wa_ = (unsigned)__double_as_longlong(ca.w), wb_ = (unsigned)__double_as_longlong(cb.w);
+				ba = (int)(wa_ & 0x7fffffffu); bb = (int)(wb_ & 0x7fffffffu); sensor = ((wa_ | wb_) >> 31) != 0;
+				circle_to_circle(a, b, m);
+				if(m.count > 0) pi = table_find(prev_table, key);
+			} else {
+				pi = table_find(prev_table, key);
+				m.id = (pi >= 0 ? prev.gjkid[pi] : 0u);
+				NShape a = load_nshape(S, B, sa), b = load_nshape(S, B, sb);
+				if(CLS == 1) circle_to_segment(a, b, m);
+				else collide_shapes(a, b, m);
+				ba = S.body[sa]; bb = S.body[sb]; sensor = (S.sensor[sa] || S.sensor[sb]);
+			}
 			have = (m.count > 0);
 		}
 		int slot = cpb_warp_append(cur.count_ptr, have);
 		if(!have) continue;
 		if(slot >= cur.cap){ atomicOr((unsigned *)&C->overflow, 2u); continue; }
 
-		int ba = S.body[sa], bb = S.body[sb];
 		// cpArbiterUpdate (cpArbiter.c:356-414)
 		int state = CPB200_ARB_FIRST_COLLISION;
 		int pcnt = 0;
@@ -121,18 +134,19 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 		cur.cnt[slot] = m.count;
 		cur.n[slot] = m.n;
 		cur.gjkid[slot] = m.id;
-		cur.e[slot] = S.e[sa]*S.e[sb];
-		cur.u[slot] = S.u[sa]*S.u[sb];
-		V2 svr = vsub(S.surfv[sb], S.surfv[sa]);
+		double4 ma = S.mat[sa], mb = S.mat[sb];
+		cur.e[slot] = ma.x*mb.x;
+		cur.u[slot] = ma.y*mb.y;
+		V2 svr = vsub(v2(mb.z, mb.w), v2(ma.z, ma.w));
 		cur.svr[slot] = vsub(svr, vmul(m.n, vdot(svr, m.n)));
 		cur.stamp[slot] = stamp;
 		cur.seen[slot] = 0;
 		cur.colour[slot] = -1;
-		cur.pri[slot] = mix64(arb_key(S.hlocal[sa], S.hlocal[sb])) >> 8;
+		cur.pri[slot] = mix64(arb_key(ida.y, idb.y)) >> 8;
 		cur.hint[slot] = (pi >= 0 && prev.active[pi] == 1 ? prev.colour[pi] : -1);
 		// active <=> pushed to space->arbiters (cpSpaceStep.c:261-274); the default handler accepts everything
 		bool both_inf = (B.type[ba] != CPB200_BODY_DYNAMIC) && (B.type[bb] != CPB200_BODY_DYNAMIC);
-		bool active = (state != CPB200_ARB_IGNORE) && !(S.sensor[sa] || S.sensor[sb]) && !both_inf;
+		bool active = (state != CPB200_ARB_IGNORE) && !sensor && !both_inf;
 		cur.active[slot] = active ? 1 : 0;
 		if(!active && state != CPB200_ARB_IGNORE) state = CPB200_ARB_NORMAL; // cpSpaceStep.c:283
 		cur.state[slot] = state;

@@ -50,6 +50,7 @@ __global__ void k_shape_cache(DShapes S, DBodies B, int all)
 		V2 c = xf_point(T, S.la[s]);
 		S.wa[s] = c;
 		S.bb[s] = make_double4(c.x - rad, c.y - rad, c.x + rad, c.y + rad);
+		S.circ[s] = make_double4(c.x, c.y, rad, __longlong_as_double((long long)((unsigned)b | (S.sensor[s] ? 0x80000000u : 0u))));
 	} else if(type == CPB200_SHAPE_SEGMENT){
 		V2 ta = xf_point(T, S.la[s]);
 		V2 tb = xf_point(T, S.lb[s]);

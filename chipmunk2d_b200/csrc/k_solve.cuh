@@ -360,6 +360,7 @@ CPB_DEVICE void rows_writeback(const DArbs &A, const DRows &R, int n_rows, int t
 __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned nblocks)
 {
 	__syncthreads();
+	if(nblocks == 1) return;   // a single CTA (small scenes): the block barrier already orders its global accesses
 	if(threadIdx.x == 0){
 		__threadfence();
 		unsigned gen = *((volatile unsigned *)&bar[1]);

@@ -495,6 +495,8 @@ extern "C" int cpb200_world_set_shapes(cpb200_world *w, int n, const cpb200_shap
 	}
 	for(size_t i = 0; i < N; i++){ uint32_t &b = space_base[(size_t)body_space[(size_t)body[i]]]; b = std::min(b, hashid[i]); }
 	for(size_t i = 0; i < N; i++) hlocal[i] = hashid[i] - space_base[(size_t)body_space[(size_t)body[i]]];
+	std::vector<double4> mat(N); std::vector<uint2> ids(N);
+	for(size_t i = 0; i < N; i++){ mat[i] = make_double4(e[i], u[i], surfv[i].x, surfv[i].y); ids[i].x = hashid[i]; ids[i].y = hlocal[i]; }
 	w->gS.release();
 	DShapes &S = w->S;
 	S.n = n; S.nv = n_verts;
@@ -502,11 +504,12 @@ extern "C" int cpb200_world_set_shapes(cpb200_world *w, int n, const cpb200_shap
 	DA(w->gS, S.group, n); DA(w->gS, S.ctype, n); DA(w->gS, S.e, n); DA(w->gS, S.u, n); DA(w->gS, S.r, n); DA(w->gS, S.surfv, n);
 	DA(w->gS, S.la, n); DA(w->gS, S.lb, n); DA(w->gS, S.ln, n); DA(w->gS, S.atan, n); DA(w->gS, S.btan, n);
 	DA(w->gS, S.pcount, n); DA(w->gS, S.poff, n); DA(w->gS, S.lpv, n_verts); DA(w->gS, S.lpn, n_verts);
+	DA(w->gS, S.mat, n); DA(w->gS, S.circ, n); DA(w->gS, S.ids, n);
 	DA(w->gS, S.wa, n); DA(w->gS, S.wb, n); DA(w->gS, S.wn, n); DA(w->gS, S.wpv, n_verts); DA(w->gS, S.wpn, n_verts); DA(w->gS, S.bb, n);
 	if(upload(w, S.type, type) || upload(w, S.body, body) || upload(w, S.hashid, hashid) || upload(w, S.hlocal, hlocal) || upload(w, S.sensor, sensor) || upload(w, S.cat, cat) ||
 	   upload(w, S.mask, mask) || upload(w, S.group, group) || upload(w, S.ctype, ctype) || upload(w, S.e, e) || upload(w, S.u, u) || upload(w, S.r, r) ||
 	   upload(w, S.surfv, surfv) || upload(w, S.la, la) || upload(w, S.lb, lb) || upload(w, S.ln, ln) || upload(w, S.atan, atan_) || upload(w, S.btan, btan_) ||
-	   upload(w, S.pcount, pcount) || upload(w, S.poff, poff) || upload(w, S.lpv, lpv) || upload(w, S.lpn, lpn)) return -1;
+	   upload(w, S.mat, mat) || upload(w, S.ids, ids) || upload(w, S.pcount, pcount) || upload(w, S.poff, poff) || upload(w, S.lpv, lpv) || upload(w, S.lpn, lpn)) return -1;
 
 	// broadphase scratch
 	w->gV.release();
@@ -802,6 +805,7 @@ extern "C" int cpb200_world_step(cpb200_world *w, double dt)
 			// what is co-resident (148 SMs x 2 CTAs of 256 threads)
 			int est_cons = std::max(w->last_active, nb) + J.n;
 			int blocks = std::max(1, std::min(w->coop_blocks, cpb_div_up(est_cons + 1, 256)));
+			if(est_cons <= 4096) blocks = 1;   // small scenes: one CTA, colours separated by __syncthreads only
 			if(w->force_blocks > 0) blocks = std::min(w->coop_blocks, w->force_blocks);
 			void *args[] = {&B, &Ac, &J, &R, &K, &C, &bar, &use_hints, &iterations, &dt, &dt_coef};
 			CPB_CHECK(cudaLaunchCooperativeKernel((void *)k_colour_solve, dim3(blocks), dim3(256), args, 0, st));
