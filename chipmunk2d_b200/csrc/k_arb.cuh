@@ -150,7 +150,17 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 		cur.active[slot] = active ? 1 : 0;
 		if(!active && state != CPB200_ARB_IGNORE) state = CPB200_ARB_NORMAL; // cpSpaceStep.c:283
 		cur.state[slot] = state;
+#ifndef CPB_EMU
+		{
+			// step statistics: one pair of atomics per warp instead of two per arbiter on two hot words
+			unsigned lanes = __activemask();
+			unsigned votes = __ballot_sync(lanes, active);
+			int contacts = __reduce_add_sync(lanes, active ? m.count : 0);
+			if((threadIdx.x & 31) == (unsigned)(__ffs(lanes) - 1) && votes){ atomicAdd(&C->n_active, __popc(votes)); atomicAdd(&C->n_contacts, contacts); }
+		}
+#else
 		if(active){ atomicAdd(&C->n_active, 1); atomicAdd(&C->n_contacts, m.count); }
+#endif
 		if(!table_insert(cur_table, key, slot)) atomicOr((unsigned *)&C->overflow, 4u);
 	}
 }
