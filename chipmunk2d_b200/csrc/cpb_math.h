@@ -12,6 +12,29 @@
 
 typedef double2 V2;
 
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256).  A double4 read through the compiler's default
+// path is split into two 128-bit requests, i.e. two L1/L2 transactions for the same 32-byte sector; the hot
+// random gathers (body velocity sectors, BVH child boxes, packed shape sectors) use these instead.
+#ifndef CPB_EMU
+__device__ __forceinline__ double4 ld4_cg(const double4 *p){   // through L2 (data written by other SMs)
+	double4 v;
+	asm volatile("ld.global.cg.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ double4 ld4_nc(const double4 *p){   // read-only for the lifetime of the kernel
+	double4 v;
+	asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ void st4_cg(double4 *p, double4 v){
+	asm volatile("st.global.cg.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+#else
+static inline double4 ld4_cg(const double4 *p){ return *p; }
+static inline double4 ld4_nc(const double4 *p){ return *p; }
+static inline void st4_cg(double4 *p, double4 v){ *p = v; }
+#endif
+
 CPB_HD V2 v2(double x, double y){ return make_double2(x, y); }
 CPB_HD V2 vadd(V2 a, V2 b){ return v2(a.x + b.x, a.y + b.y); }
 CPB_HD V2 vsub(V2 a, V2 b){ return v2(a.x - b.x, a.y - b.y); }

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 			key = arb_key(ida.x, idb.x);
 			if(CLS == 0){
 				// circle-circle: everything the test needs sits in one packed sector per shape
-				double4 ca = S.circ[sa], cb = S.circ[sb];
+				double4 ca = ld4_nc(&S.circ[sa]), cb = ld4_nc(&S.circ[sb]);
 				NShape a, b;
 				a.type = 0; a.a = v2(ca.x, ca.y); a.r = ca.z; b.type = 0; b.a = v2(cb.x, cb.y); b.r = cb.z;
 				unsigned wa_ = (unsigned)__double_as_longlong(ca.w), wb_ = (unsigned)__double_as_longlong(cb.w);
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 		cur.cnt[slot] = m.count;
 		cur.n[slot] = m.n;
 		cur.gjkid[slot] = m.id;
-		double4 ma = S.mat[sa], mb = S.mat[sb];
+		double4 ma = ld4_nc(&S.mat[sa]), mb = ld4_nc(&S.mat[sb]);
 		cur.e[slot] = ma.x*mb.x;
 		cur.u[slot] = ma.y*mb.y;
 		V2 svr = vsub(v2(mb.z, mb.w), v2(ma.z, ma.w));

@@ -252,7 +252,7 @@ __global__ void k_bvh_pairs(DBvh T, DShapes S, DBodies B, DPairs P, const uint64
 	int si = T.leaf_shape[i];
 	int bi = S.body[si];
 	if(!shape_is_active(B, bi)) return;
-	double4 q = S.bb[si];
+	double4 q = ld4_nc(&S.bb[si]);
 	int qsp = B.space[bi];
 	if(n < 2) return;
 	int stack[CPB_BVH_STACK];
@@ -260,7 +260,7 @@ __global__ void k_bvh_pairs(DBvh T, DShapes S, DBodies B, DPairs P, const uint64
 	int node = 0;
 	for(;;){
 		int4 ci = T.cinfo[node];
-		double4 box[2] = {T.cbox[2*node], T.cbox[2*node + 1]};
+		double4 box[2] = {ld4_nc(&T.cbox[2*node]), ld4_nc(&T.cbox[2*node + 1])};
 		int4 cs = make_int4(0, 0, 0, 0);
 		if(multi_space) cs = T.cspace[node];
 		int next = -1;

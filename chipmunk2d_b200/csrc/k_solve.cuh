@@ -253,18 +253,8 @@ CPB_DEVICE void contact_apply(double4 &Va, double4 &Vb, double4 &VBa, double4 &V
 
 // Body velocities are gathered/scattered once per colour phase and are written by other SMs in
 // the previous phase: go through L2 (ld.cg / st.cg), never through the non-coherent L1.
-#ifndef CPB_EMU
-__device__ __forceinline__ double4 ld_vel(const double4 *p){
-	double2 lo = __ldcg((const double2 *)p), hi = __ldcg((const double2 *)p + 1);
-	return make_double4(lo.x, lo.y, hi.x, hi.y);
-}
-__device__ __forceinline__ void st_vel(double4 *p, double4 v){
-	__stcg((double2 *)p, make_double2(v.x, v.y)); __stcg((double2 *)p + 1, make_double2(v.z, v.w));
-}
-#else
-static inline double4 ld_vel(const double4 *p){ return *p; }
-static inline void st_vel(double4 *p, double4 v){ *p = v; }
-#endif
+CPB_DEVICE double4 ld_vel(const double4 *p){ return ld4_cg(p); }
+CPB_DEVICE void st_vel(double4 *p, double4 v){ st4_cg(p, v); }
 
 // Solver rows are streamed once per pass and never reused before the next pass evicts them: load/store them
 // with the evict-first policy (ld.global.cs / st.global.cs) so the ~80 MB of body velocities that every
