@@ -229,24 +229,29 @@ def run_ours(args):
             api.space = None
             e2e_bodies = nb
         else:
-            # batched layout: one cpSpace per space through the C API, sampled (64 spaces) -- the C API has no
-            # batched entry point in the reference, so this is its per-space cost
-            sub = scenes[:64]
-            apis = [SceneSpace(load_scene_lib(), sc.blob) for sc in sub]
-            for a in apis:
-                a.step(dt, 2)
+            # batched layout: the reference's C API has no batched entry point (one cpSpace = one world), so the
+            # call a user of this workload makes is the engine's batched world with HOST buffers: forces for
+            # every body in, cpSpaceStep for all spaces, every body's state out -- each step, inside the timer
+            import numpy as np, time
+            forces = np.zeros((w.n_bodies, 3), dtype=np.float64)
+            states = np.zeros(w.n_bodies, dtype=BODY_STATE)
+            for _ in range(2):
+                w.set_body_forces(0, forces); w.step(dt); w.bodies_into(states)
             barrier()
-            sec = sum(a.e2e_steps(dt, k2)[0] for a in apis)
-            n_api = sum(a.n_bodies for a in apis)
-            e2e_bodies = sum(sc.n_dynamic() for sc in sub)
+            t0 = time.perf_counter()
+            for _ in range(k2):
+                w.set_body_forces(0, forces); w.step(dt); w.bodies_into(states)
+            sec = time.perf_counter() - t0
+            n_api = w.n_bodies
+            e2e_bodies = nb
         t_e = torch.tensor([sec], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         e2e = {"value": e2e_bodies * world * k2 / float(t_e.item()), "unit": "body-steps/s", "steps": k2,
-               "h2d_bytes_per_step": int(n_api * BODY_DESC.itemsize), "d2h_bytes_per_step": int(n_api * BODY_STATE.itemsize),
+               "h2d_bytes_per_step": int(n_api * 24), "d2h_bytes_per_step": int(n_api * BODY_STATE.itemsize),
                "ms_per_step": 1000.0 * float(t_e.item()) / k2,
                "path": "cpBodySetForce on every body -> cpSpaceStep -> cpBodyGetPosition on every body (scene_io.c cpb_scene_e2e_steps)" +
-                       ("" if len(scenes) == 1 else "; sampled on 64 spaces stepped one cpSpace at a time")}
+                       ("" if len(scenes) == 1 else " -- batched: World.set_body_forces(host) -> World.step -> World.bodies_into(host) over all spaces")}
     except Exception as exc:  # keep the device-resident number even if the API libs are missing
         e2e = {"value": None, "unit": "body-steps/s", "error": str(exc)}
 

@@ -124,7 +124,6 @@ __global__ void k_sleep_components(DBodies B, DIslands I, const DSpace *__restri
 	if(i >= B.n) return;
 	if(B.type[i] != CPB200_BODY_DYNAMIC || B.sleeping[i]) return;
 	int r = uf_find(I.parent, i);
-	I.parent[i] = r;
 	DSpace sp = spaces[B.space[i]];
 	// ComponentActive (cpSpaceComponent.c:210-218)
 	if(!space_sleeps(sp) || B.idle[i] < sp.sleep_threshold) I.comp_active[r] = 1;
@@ -135,7 +134,9 @@ __global__ void k_sleep_apply(DBodies B, DIslands I)
 	int i = CPB_TID;
 	if(i >= B.n) return;
 	if(B.type[i] != CPB200_BODY_DYNAMIC || B.sleeping[i]) return;
-	int r = I.parent[i];
+	// look the root up again instead of caching it in parent[i]: another thread's path halving may
+	// still overwrite parent[i] with a (valid, but non-root) ancestor it read earlier
+	int r = uf_find(I.parent, i);
 	if(!I.comp_active[r]){ B.sleeping[i] = 1; B.sgroup[i] = r; }
 }
 

@@ -112,6 +112,7 @@ struct cpb200_world {
 	void *d_stage; size_t stage_bytes;   // device staging for host <-> SoA conversion kernels
 	unsigned *d_barrier;    // grid barrier words of the persistent solver
 	bool hints_valid;       // last step's colours may seed this step's colouring
+	bool no_hints;          // validation hook (env CPB200_NO_HINTS): colour from scratch every step
 	int wl_cap; AllocGroup gW;
 	int force_blocks;       // validation hook: fixed persistent grid size (0 = automatic)
 	int last_active;        // active arbiters seen at the last host read-back (grid sizing hint)
@@ -218,6 +219,7 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	cudaMalloc(&p, sizeof(DCounters)); w->C = (DCounters *)p; cudaMemsetAsync(w->C, 0, sizeof(DCounters), w->stream);
 	cudaMallocHost(&p, sizeof(DCounters)); w->hC = (DCounters *)p; memset(w->hC, 0, sizeof(DCounters));
 	cudaMalloc(&p, sizeof(unsigned)*8); w->d_barrier = (unsigned *)p; cudaMemsetAsync(w->d_barrier, 0, sizeof(unsigned)*8, w->stream);
+	w->no_hints = (getenv("CPB200_NO_HINTS") != NULL);
 	w->last_active = 0; w->force_blocks = 0; w->hints_valid = false; w->wl_cap = 0; w->d_stage = NULL; w->stage_bytes = 0;
 	cudaMalloc(&p, sizeof(double)*64); w->d_scratch = (double *)p;
 	cudaMallocHost(&p, sizeof(double)*64); w->h_scratch = (double *)p;
@@ -796,7 +798,7 @@ extern "C" int cpb200_world_step(cpb200_world *w, double dt)
 		cudaMemsetAsync(K.jcount, 0, sizeof(int)*(CPB_MAX_COLOURS + 1), st);
 		cudaMemsetAsync(K.wl_n, 0, sizeof(int)*(CPB_MAX_COLOUR_ROUNDS + 2), st);
 		if(ensure_worklists(w, Ac.cap + J.n + 64)) return -1;
-		int use_hints = (w->hints_valid ? 1 : 0);
+		int use_hints = (w->hints_valid && !w->no_hints ? 1 : 0);
 		w->hints_valid = true;
 #ifndef CPB_EMU
 		{

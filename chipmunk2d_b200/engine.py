@@ -97,6 +97,7 @@ def load_engine(path=None):
     lib.cpb200_world_set_shapes.argtypes = [vp, ci, vp, ci, vp]
     lib.cpb200_world_set_joints.argtypes = [vp, ci, vp]
     lib.cpb200_world_update_bodies.argtypes = [vp, ci, ci, vp]
+    lib.cpb200_world_set_body_forces.argtypes = [vp, ci, ci, vp]
     lib.cpb200_world_reserve.argtypes = [vp, ci, ci]
     lib.cpb200_world_step.argtypes = [vp, cd]
     lib.cpb200_world_sync.argtypes = [vp]
@@ -242,6 +243,16 @@ class World:
     def update_bodies(self, first, bd):
         bd = np.ascontiguousarray(bd, dtype=BODY_DESC)
         self._ck(self.lib.cpb200_world_update_bodies(self.w, first, len(bd), bd.ctypes.data))
+
+    def set_body_forces(self, first, fxyt):
+        """Per-step host input: (f.x, f.y, torque) rows for bodies [first, first + len(fxyt))."""
+        f = np.ascontiguousarray(fxyt, dtype=np.float64).reshape(-1, 3)
+        self._ck(self.lib.cpb200_world_set_body_forces(self.w, int(first), len(f), f.ctypes.data))
+
+    def bodies_into(self, out):
+        """Read-back into a caller-owned BODY_STATE array (no allocation in the step loop)."""
+        self._ck(self.lib.cpb200_world_get_bodies(self.w, 0, self.n_bodies, out.ctypes.data))
+        return out
 
     def set_shapes(self, sd, verts):
         sd = np.ascontiguousarray(sd, dtype=SHAPE_DESC)

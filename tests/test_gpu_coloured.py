@@ -29,6 +29,22 @@ def test_coloured_is_deterministic():
     assert np.array_equal(a["p"], b["p"]) and np.array_equal(a["v"], b["v"]) and np.array_equal(a["a"], b["a"])
 
 
+def test_islands_are_deterministic_over_a_long_run():
+    """Regression: the union-find roots used to be cached in parent[] where a concurrent path-halving store
+    could replace them by a non-root ancestor, which put single bodies of a live pile to sleep now and then.
+    Two worlds interleaved on their own streams, 1500 steps of stacking, sleeping and waking."""
+    sc = golden_scene("PyramidStack")
+    a, b = World(1), World(1)
+    a.load_scene(sc); b.load_scene(sc)
+    b.set_solver_grid(8)
+    for i in range(1500):
+        a.step(sc.dt); b.step(sc.dt)
+        if i % 100 == 99 or i > 1400:
+            x, y = a.bodies(), b.bodies()
+            assert np.array_equal(x["sleeping"], y["sleeping"]), i
+            assert np.array_equal(x["p"], y["p"]) and np.array_equal(x["v"], y["v"]), i
+
+
 @pytest.mark.parametrize("name", ["ComplexTerrainHexagons_1000", "Chains", "PyramidStack"])
 def test_result_independent_of_solver_grid(name):
     """Colours are race-free: one CTA and the full persistent grid give bit-identical states."""
