@@ -258,7 +258,8 @@ CPB_DEVICE void st_vel(double4 *p, double4 v){ st4_cg(p, v); }
 
 // Solver rows are streamed once per pass and never reused before the next pass evicts them: load/store them
 // with the evict-first policy (ld.global.cs / st.global.cs) so the ~80 MB of body velocities that every
-// pass gathers again stays resident in the 126 MB L2.
+// pass gathers again stays resident in the 126 MB L2.  (A run-time createpolicy/L2::cache_hint variant that
+// keeps small row sets L2-resident measured 9% slower on both the 1M pile and the batched spaces.)
 #if !defined(CPB_EMU) && !defined(CPB_NO_ROW_STREAM)
 #define ROW_LD(p) __ldcs(p)
 #define ROW_ST(p, v) __stcs((p), (v))
@@ -267,10 +268,13 @@ CPB_DEVICE void st_vel(double4 *p, double4 v){ st4_cg(p, v); }
 #define ROW_ST(p, v) (*(p) = (v))
 #endif
 
+CPB_DEVICE bool same_bits(double a, double b){ return __double_as_longlong(a) == __double_as_longlong(b); }
+CPB_DEVICE bool same_bits3(double4 a, double4 b){ return same_bits(a.x, b.x) && same_bits(a.y, b.y) && same_bits(a.z, b.z); }
+
 // one colour-sorted row: mode 0 = warm start, 1 = iteration
-CPB_DEVICE void solve_row(const DBodies &B, const DRows &R, int r, int mode, double dt_coef){
-	int ba = ROW_LD(&R.ba[r]), bb = ROW_LD(&R.bb[r]);
-	int cnt = ROW_LD(&R.cnt[r]);
+// (ba, bb, cnt) are passed in: the persistent kernel fetches them for a thread's next row while the previous
+// phase is still draining, so that after the barrier the velocity gathers do not wait for an index load
+CPB_DEVICE void solve_row_idx(const DBodies &B, const DRows &R, int r, int ba, int bb, int cnt, int mode, double dt_coef){
 	bool first = (cnt < 0);
 	if(first) cnt = -cnt;
 	if(mode == 0 && first) return;
@@ -293,24 +297,52 @@ CPB_DEVICE void solve_row(const DBodies &B, const DRows &R, int r, int mode, dou
 	bool dyn_a = (mia.x != 0.0 || mia.y != 0.0), dyn_b = (mib.x != 0.0 || mib.y != 0.0);
 	V2 svr = ROW_LD(&R.svr[r]);
 	double u = ROW_LD(&R.u[r]);
+#ifndef CPB_NO_SKIP_SAME
+	// A contact that does not push this iteration (clamped impulses) leaves both bodies exactly as they
+	// were: skip the scatter then.  Bitwise comparison, so the stored state is identical either way.
+	const double4 Va0 = Va, Vb0 = Vb, VBa0 = VBa, VBb0 = VBb;
+#endif
 	for(int k = 0; k < cnt; k++){
 		int d = k*R.cap + r;
 		double jn = ROW_LD(&R.jn[d]), jt = ROW_LD(&R.jt[d]), jb = ROW_LD(&R.jb[d]);
+#ifndef CPB_NO_SKIP_SAME
+		const double jn0 = jn, jt0 = jt, jb0 = jb;
+#endif
 		contact_apply(Va, Vb, VBa, VBb, mia, mib, n, svr, u, ROW_LD(&R.r1[d]), ROW_LD(&R.r2[d]), ROW_LD(&R.nmass[d]), ROW_LD(&R.tmass[d]), ROW_LD(&R.bias[d]), ROW_LD(&R.bounce[d]), jn, jt, jb);
+#ifndef CPB_NO_SKIP_SAME
+		if(!same_bits(jn, jn0)) ROW_ST(&R.jn[d], jn);
+		if(!same_bits(jt, jt0)) ROW_ST(&R.jt[d], jt);
+		if(!same_bits(jb, jb0)) ROW_ST(&R.jb[d], jb);
+#else
 		ROW_ST(&R.jn[d], jn); ROW_ST(&R.jt[d], jt); ROW_ST(&R.jb[d], jb);
+#endif
 	}
+#ifndef CPB_NO_SKIP_SAME
+	if(dyn_a){ if(!same_bits3(Va, Va0)) st_vel(&B.V[ba], Va); if(!same_bits3(VBa, VBa0)) st_vel(&B.VB[ba], VBa); }
+	if(dyn_b){ if(!same_bits3(Vb, Vb0)) st_vel(&B.V[bb], Vb); if(!same_bits3(VBb, VBb0)) st_vel(&B.VB[bb], VBb); }
+#else
 	if(dyn_a){ st_vel(&B.V[ba], Va); st_vel(&B.VB[ba], VBa); }
 	if(dyn_b){ st_vel(&B.V[bb], Vb); st_vel(&B.VB[bb], VBb); }
+#endif
 }
 
-CPB_DEVICE void solve_joint(const DBodies &B, const DJoints &J, int j, int mode, double dt, double dt_coef){
-	int a = J.a[j], b = J.b[j];
+CPB_DEVICE void solve_row(const DBodies &B, const DRows &R, int r, int mode, double dt_coef){
+	int ba = ROW_LD(&R.ba[r]), bb = ROW_LD(&R.bb[r]);
+	int cnt = ROW_LD(&R.cnt[r]);
+	solve_row_idx(B, R, r, ba, bb, cnt, mode, dt_coef);
+}
+
+CPB_DEVICE void solve_joint_idx(const DBodies &B, const DJoints &J, int j, int a, int b, int mode, double dt, double dt_coef){
 	V2 mia = B.MI[a], mib = B.MI[b];
 	double4 Va = ld_vel(&B.V[a]), Vb = ld_vel(&B.V[b]);
 	if(mode == 0) joint_apply_cached(J, j, Va, Vb, mia, mib, dt_coef);
 	else joint_apply(J, j, Va, Vb, mia, mib, dt);
 	if(mia.x != 0.0 || mia.y != 0.0) st_vel(&B.V[a], Va);
 	if(mib.x != 0.0 || mib.y != 0.0) st_vel(&B.V[b], Vb);
+}
+
+CPB_DEVICE void solve_joint(const DBodies &B, const DJoints &J, int j, int mode, double dt, double dt_coef){
+	solve_joint_idx(B, J, j, J.a[j], J.b[j], mode, dt, dt_coef);
 }
 
 // all rows + joints of one colour
@@ -374,6 +406,7 @@ __device__ __forceinline__ unsigned long long global_ns(){ unsigned long long t;
 #ifndef CPB_SOLVE_MIN_BLOCKS
 #define CPB_SOLVE_MIN_BLOCKS 2
 #endif
+
 __global__ void __launch_bounds__(256, CPB_SOLVE_MIN_BLOCKS) k_colour_solve(DBodies B, DArbs A, DJoints J, DRows R, DColour K, DCounters *C, unsigned *bar, int use_hints, int iterations, double dt, double dt_coef)
 {
 	__shared__ int s_hist[2*CPB_MAX_COLOURS];
@@ -408,15 +441,46 @@ __global__ void __launch_bounds__(256, CPB_SOLVE_MIN_BLOCKS) k_colour_solve(DBod
 	GRID_SYNC();
 	PROF(2);
 
-	// K11: warm start then iterations, colour by colour
+	// K11: warm start then iterations, colour by colour.  A thread's rows of a colour are r0 + tid + k*nth and
+	// its joints q0 + (nth-1-tid) + k*nth (from the other end of the grid, so that in small colours a thread
+	// has a row or a joint, not both).  The indices of the first row/joint of the NEXT phase are fetched
+	// before the barrier: once it opens, the velocity gathers can issue at once.
+	__shared__ int s_cstart[CPB_MAX_COLOURS + 1], s_jstart[CPB_MAX_COLOURS + 1];
+	if(threadIdx.x <= CPB_MAX_COLOURS){ s_cstart[threadIdx.x] = K.cstart[threadIdx.x]; s_jstart[threadIdx.x] = K.jstart[threadIdx.x]; }
+	__syncthreads();
 	int ncol = *((volatile int *)&C->n_colours);
 	int nreg = (ncol > CPB_OVERFLOW_COLOUR ? CPB_OVERFLOW_COLOUR : ncol);
 	bool has_overflow = (ncol > CPB_OVERFLOW_COLOUR);
+	const int jtid = nth - 1 - tid;
+	int pr = -1, pba = 0, pbb = 0, pcnt = 0;     // prefetched row
+	int pq = -1, pj = 0, pja = 0, pjb = 0;       // prefetched joint
+	#define PREFETCH_PHASE(c_) do { \
+		pr = s_cstart[c_] + tid; if(pr < s_cstart[(c_) + 1]){ pba = ROW_LD(&R.ba[pr]); pbb = ROW_LD(&R.bb[pr]); pcnt = ROW_LD(&R.cnt[pr]); } else pr = -1; \
+		pq = s_jstart[c_] + jtid; if(pq < s_jstart[(c_) + 1]){ pj = J.row[pq]; pja = J.a[pj]; pjb = J.b[pj]; } else pq = -1; } while(0)
+	if(nreg > 0) PREFETCH_PHASE(0);
 	for(int pass = 0; pass <= iterations; pass++){
 		int mode = (pass == 0 ? 0 : 1);
 		for(int c = 0; c < nreg; c++){
-			solve_colour(B, R, J, K, c, mode, dt, dt_coef, tid, nth);
+			const int r1 = s_cstart[c + 1], j1 = s_jstart[c + 1];
+			while(pr >= 0){
+				int r = pr, ba = pba, bb = pbb, cnt = pcnt;
+				pr += nth;
+				if(pr < r1){ pba = ROW_LD(&R.ba[pr]); pbb = ROW_LD(&R.bb[pr]); pcnt = ROW_LD(&R.cnt[pr]); } else pr = -1;
+				solve_row_idx(B, R, r, ba, bb, cnt, mode, dt_coef);
+			}
+			while(pq >= 0){
+				int j = pj, a = pja, b = pjb;
+				pq += nth;
+				if(pq < j1){ pj = J.row[pq]; pja = J.a[pj]; pjb = J.b[pj]; } else pq = -1;
+				solve_joint_idx(B, J, j, a, b, mode, dt, dt_coef);
+			}
+			int cn = (c + 1 < nreg ? c + 1 : 0);
+			if(c + 1 < nreg || pass < iterations) PREFETCH_PHASE(cn);
+#ifdef CPB_EXP_NOBAR   // timing experiment only (results are wrong): what do the barriers + tails cost?
+			__syncthreads();
+#else
 			GRID_SYNC();
+#endif
 		}
 		if(has_overflow){
 			if(tid == 0) solve_overflow(B, R, J, K, mode, dt, dt_coef);
@@ -424,6 +488,7 @@ __global__ void __launch_bounds__(256, CPB_SOLVE_MIN_BLOCKS) k_colour_solve(DBod
 		}
 		if(pass == 0) PROF(3);
 	}
+	#undef PREFETCH_PHASE
 	PROF(4);
 	int n_rows = K.cstart[CPB_MAX_COLOURS];
 	rows_writeback(A, R, n_rows, tid, nth);

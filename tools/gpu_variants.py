@@ -16,6 +16,7 @@ def run(lib, scenes, warm, steps):
     w.set_profiling(True)
     for _ in range(3): w.step(dt)
     sp = w.solver_profile(); st = w.stage_times()
+    sp["n_colours"] = w.stats()["n_colours"]
     w.close()
     return ms, sp, st
 
@@ -26,4 +27,4 @@ if __name__ == "__main__":
     for name, (sc, warm, steps) in sets.items():
         for lib in libs:
             ms, sp, st = run(os.path.join(ROOT, "chipmunk2d_b200/lib", lib), sc, warm, steps)
-            print("%-10s %-22s %.3f ms/step  solve %.0f us (colour %.0f rows %.0f warm %.0f iterate %.0f)" % (name, lib, ms, st["colour_solve"], sp["colour_us"], sp["rows_us"], sp["warm_us"], sp["iterate_us"]), flush=True)
+            print("%-10s %-22s %.3f ms/step  solve %.0f us (colour %.0f rows %.0f warm %.0f iterate %.0f) colours %d" % (name, lib, ms, st["colour_solve"], sp["colour_us"], sp["rows_us"], sp["warm_us"], sp["iterate_us"], sp["n_colours"]), flush=True)
