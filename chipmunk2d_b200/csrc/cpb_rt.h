@@ -22,6 +22,7 @@
 
 extern unsigned long long g_cpb_launches;   // kernels launched by this library (bench.py reports it)
 #define LAUNCH(kernel, grid, block, stream, ...) do { g_cpb_launches++; kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__); } while(0)
+#define LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) do { g_cpb_launches++; kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); } while(0)
 #define CPB_DEVICE __device__ __forceinline__
 #define CPB_HD __host__ __device__ __forceinline__
 

@@ -256,6 +256,36 @@ CPB_DEVICE void contact_apply(double4 &Va, double4 &Vb, double4 &VBa, double4 &V
 CPB_DEVICE double4 ld_vel(const double4 *p){ return ld4_cg(p); }
 CPB_DEVICE void st_vel(double4 *p, double4 v){ st4_cg(p, v); }
 
+// Where the solver keeps the two velocity sectors of a body: in global memory behind L2 (one world-wide
+// constraint graph, any CTA may touch any body) or in the shared memory of the CTA that owns the whole space
+// (space-local solver below; bodies of a space are contiguous, index = body - first body of the space).
+#ifdef CPB_EMU
+#define CPB_MEMBER inline
+#else
+#define CPB_MEMBER __device__ __forceinline__
+#endif
+struct VelGlobal {
+	static const bool STREAM = true;     // rows go past the L2 (see ROW_LD)
+	static const bool EAGER = false;
+	double4 *V, *VB;
+	CPB_MEMBER double4 ldV(int b) const { return ld_vel(&V[b]); }
+	CPB_MEMBER double4 ldVB(int b) const { return ld_vel(&VB[b]); }
+	CPB_MEMBER void stV(int b, double4 v) const { st_vel(&V[b], v); }
+	CPB_MEMBER void stVB(int b, double4 v) const { st_vel(&VB[b], v); }
+};
+struct VelShared {
+	static const bool STREAM = false;    // a space's rows are re-read by the same SM every pass: cache them
+#ifndef CPB_SL_EAGER
+#define CPB_SL_EAGER 1
+#endif
+	static const bool EAGER = (CPB_SL_EAGER != 0);      // few warps per space: shorten the dependent load chain (see solve_row_idx)
+	double4 *V, *VB; int b0;
+	CPB_MEMBER double4 ldV(int b) const { return V[b - b0]; }
+	CPB_MEMBER double4 ldVB(int b) const { return VB[b - b0]; }
+	CPB_MEMBER void stV(int b, double4 v) const { V[b - b0] = v; }
+	CPB_MEMBER void stVB(int b, double4 v) const { VB[b - b0] = v; }
+};
+
 // Solver rows are streamed once per pass and never reused before the next pass evicts them: load/store them
 // with the evict-first policy (ld.global.cs / st.global.cs) so the ~80 MB of body velocities that every
 // pass gathers again stays resident in the 126 MB L2.  (A run-time createpolicy/L2::cache_hint variant that
@@ -268,81 +298,114 @@ CPB_DEVICE void st_vel(double4 *p, double4 v){ st4_cg(p, v); }
 #define ROW_ST(p, v) (*(p) = (v))
 #endif
 
+#ifndef CPB_EMU
+template<bool STREAM, class T> __device__ __forceinline__ T row_ld(const T *p){ if(STREAM) return __ldcs(p); else return *p; }
+template<bool STREAM, class T> __device__ __forceinline__ void row_st(T *p, T v){ if(STREAM) __stcs(p, v); else *p = v; }
+#else
+template<bool STREAM, class T> static inline T row_ld(const T *p){ return *p; }
+template<bool STREAM, class T> static inline void row_st(T *p, T v){ *p = v; }
+#endif
+
 CPB_DEVICE bool same_bits(double a, double b){ return __double_as_longlong(a) == __double_as_longlong(b); }
 CPB_DEVICE bool same_bits3(double4 a, double4 b){ return same_bits(a.x, b.x) && same_bits(a.y, b.y) && same_bits(a.z, b.z); }
+
+// one contact of a row: constants + accumulated impulses
+template<bool STREAM> struct RowContact {
+	V2 r1, r2; double nmass, tmass, bias, bounce, jn, jt, jb;
+	CPB_MEMBER void load(const DRows &R, int d){
+		r1 = row_ld<STREAM>(&R.r1[d]); r2 = row_ld<STREAM>(&R.r2[d]);
+		nmass = row_ld<STREAM>(&R.nmass[d]); tmass = row_ld<STREAM>(&R.tmass[d]); bias = row_ld<STREAM>(&R.bias[d]); bounce = row_ld<STREAM>(&R.bounce[d]);
+		jn = row_ld<STREAM>(&R.jn[d]); jt = row_ld<STREAM>(&R.jt[d]); jb = row_ld<STREAM>(&R.jb[d]);
+	}
+	CPB_MEMBER void solve(const DRows &R, int d, double4 &Va, double4 &Vb, double4 &VBa, double4 &VBb, V2 mia, V2 mib, V2 n, V2 svr, double u){
+#ifndef CPB_NO_SKIP_SAME
+		const double jn0 = jn, jt0 = jt, jb0 = jb;
+#endif
+		contact_apply(Va, Vb, VBa, VBb, mia, mib, n, svr, u, r1, r2, nmass, tmass, bias, bounce, jn, jt, jb);
+#ifndef CPB_NO_SKIP_SAME
+		if(!same_bits(jn, jn0)) row_st<STREAM>(&R.jn[d], jn);
+		if(!same_bits(jt, jt0)) row_st<STREAM>(&R.jt[d], jt);
+		if(!same_bits(jb, jb0)) row_st<STREAM>(&R.jb[d], jb);
+#else
+		row_st<STREAM>(&R.jn[d], jn); row_st<STREAM>(&R.jt[d], jt); row_st<STREAM>(&R.jb[d], jb);
+#endif
+	}
+};
 
 // one colour-sorted row: mode 0 = warm start, 1 = iteration
 // (ba, bb, cnt) are passed in: the persistent kernel fetches them for a thread's next row while the previous
 // phase is still draining, so that after the barrier the velocity gathers do not wait for an index load
-CPB_DEVICE void solve_row_idx(const DBodies &B, const DRows &R, int r, int ba, int bb, int cnt, int mode, double dt_coef){
+template<class VS> CPB_DEVICE void solve_row_idx(const VS &vs, const DBodies &B, const DRows &R, int r, int ba, int bb, int cnt, int mode, double dt_coef){
 	bool first = (cnt < 0);
 	if(first) cnt = -cnt;
 	if(mode == 0 && first) return;
-	double4 Va = ld_vel(&B.V[ba]), Vb = ld_vel(&B.V[bb]);
-	V2 n = ROW_LD(&R.n[r]);
+	double4 Va = vs.ldV(ba), Vb = vs.ldV(bb);
+	V2 n = row_ld<VS::STREAM>(&R.n[r]);
 	if(mode == 0){
 		V2 mia = B.MI[ba], mib = B.MI[bb];
 		bool dyn_a = (mia.x != 0.0 || mia.y != 0.0), dyn_b = (mib.x != 0.0 || mib.y != 0.0);
 		for(int k = 0; k < cnt; k++){
 			int d = k*R.cap + r;
-			contact_apply_cached(Va, Vb, mia, mib, n, ROW_LD(&R.r1[d]), ROW_LD(&R.r2[d]), ROW_LD(&R.jn[d]), ROW_LD(&R.jt[d]), dt_coef);
+			contact_apply_cached(Va, Vb, mia, mib, n, row_ld<VS::STREAM>(&R.r1[d]), row_ld<VS::STREAM>(&R.r2[d]), row_ld<VS::STREAM>(&R.jn[d]), row_ld<VS::STREAM>(&R.jt[d]), dt_coef);
 		}
-		if(dyn_a) st_vel(&B.V[ba], Va);
-		if(dyn_b) st_vel(&B.V[bb], Vb);
+		if(dyn_a) vs.stV(ba, Va);
+		if(dyn_b) vs.stV(bb, Vb);
 		return;
 	}
-	double4 VBa = ld_vel(&B.VB[ba]), VBb = ld_vel(&B.VB[bb]);
+	double4 VBa = vs.ldVB(ba), VBb = vs.ldVB(bb);
 	// (m_inv, i_inv) ride in the spare lanes of the two velocity sectors
 	V2 mia = v2(Va.w, VBa.w), mib = v2(Vb.w, VBb.w);
 	bool dyn_a = (mia.x != 0.0 || mia.y != 0.0), dyn_b = (mib.x != 0.0 || mib.y != 0.0);
-	V2 svr = ROW_LD(&R.svr[r]);
-	double u = ROW_LD(&R.u[r]);
+	V2 svr = row_ld<VS::STREAM>(&R.svr[r]);
+	double u = row_ld<VS::STREAM>(&R.u[r]);
 #ifndef CPB_NO_SKIP_SAME
 	// A contact that does not push this iteration (clamped impulses) leaves both bodies exactly as they
 	// were: skip the scatter then.  Bitwise comparison, so the stored state is identical either way.
 	const double4 Va0 = Va, Vb0 = Vb, VBa0 = VBa, VBb0 = VBb;
 #endif
-	for(int k = 0; k < cnt; k++){
-		int d = k*R.cap + r;
-		double jn = ROW_LD(&R.jn[d]), jt = ROW_LD(&R.jt[d]), jb = ROW_LD(&R.jb[d]);
-#ifndef CPB_NO_SKIP_SAME
-		const double jn0 = jn, jt0 = jt, jb0 = jb;
-#endif
-		contact_apply(Va, Vb, VBa, VBb, mia, mib, n, svr, u, ROW_LD(&R.r1[d]), ROW_LD(&R.r2[d]), ROW_LD(&R.nmass[d]), ROW_LD(&R.tmass[d]), ROW_LD(&R.bias[d]), ROW_LD(&R.bounce[d]), jn, jt, jb);
-#ifndef CPB_NO_SKIP_SAME
-		if(!same_bits(jn, jn0)) ROW_ST(&R.jn[d], jn);
-		if(!same_bits(jt, jt0)) ROW_ST(&R.jt[d], jt);
-		if(!same_bits(jb, jb0)) ROW_ST(&R.jb[d], jb);
-#else
-		ROW_ST(&R.jn[d], jn); ROW_ST(&R.jt[d], jt); ROW_ST(&R.jb[d], jb);
-#endif
+	if(VS::EAGER){
+		// issue the loads of both contacts before the first one is solved: one memory latency per row
+		// instead of one per contact (the compiler cannot hoist them over the impulse stores itself)
+		RowContact<VS::STREAM> c0, c1;
+		c0.load(R, r);
+		if(cnt == 2) c1.load(R, R.cap + r);
+		c0.solve(R, r, Va, Vb, VBa, VBb, mia, mib, n, svr, u);
+		if(cnt == 2) c1.solve(R, R.cap + r, Va, Vb, VBa, VBb, mia, mib, n, svr, u);
+	} else {
+		for(int k = 0; k < cnt; k++){
+			RowContact<VS::STREAM> c;
+			c.load(R, k*R.cap + r);
+			c.solve(R, k*R.cap + r, Va, Vb, VBa, VBb, mia, mib, n, svr, u);
+		}
 	}
 #ifndef CPB_NO_SKIP_SAME
-	if(dyn_a){ if(!same_bits3(Va, Va0)) st_vel(&B.V[ba], Va); if(!same_bits3(VBa, VBa0)) st_vel(&B.VB[ba], VBa); }
-	if(dyn_b){ if(!same_bits3(Vb, Vb0)) st_vel(&B.V[bb], Vb); if(!same_bits3(VBb, VBb0)) st_vel(&B.VB[bb], VBb); }
+	if(dyn_a){ if(!same_bits3(Va, Va0)) vs.stV(ba, Va); if(!same_bits3(VBa, VBa0)) vs.stVB(ba, VBa); }
+	if(dyn_b){ if(!same_bits3(Vb, Vb0)) vs.stV(bb, Vb); if(!same_bits3(VBb, VBb0)) vs.stVB(bb, VBb); }
 #else
-	if(dyn_a){ st_vel(&B.V[ba], Va); st_vel(&B.VB[ba], VBa); }
-	if(dyn_b){ st_vel(&B.V[bb], Vb); st_vel(&B.VB[bb], VBb); }
+	if(dyn_a){ vs.stV(ba, Va); vs.stVB(ba, VBa); }
+	if(dyn_b){ vs.stV(bb, Vb); vs.stVB(bb, VBb); }
 #endif
 }
 
 CPB_DEVICE void solve_row(const DBodies &B, const DRows &R, int r, int mode, double dt_coef){
 	int ba = ROW_LD(&R.ba[r]), bb = ROW_LD(&R.bb[r]);
 	int cnt = ROW_LD(&R.cnt[r]);
-	solve_row_idx(B, R, r, ba, bb, cnt, mode, dt_coef);
+	VelGlobal vs = {B.V, B.VB};
+	solve_row_idx(vs, B, R, r, ba, bb, cnt, mode, dt_coef);
 }
 
-CPB_DEVICE void solve_joint_idx(const DBodies &B, const DJoints &J, int j, int a, int b, int mode, double dt, double dt_coef){
+template<class VS> CPB_DEVICE void solve_joint_idx(const VS &vs, const DBodies &B, const DJoints &J, int j, int a, int b, int mode, double dt, double dt_coef){
 	V2 mia = B.MI[a], mib = B.MI[b];
-	double4 Va = ld_vel(&B.V[a]), Vb = ld_vel(&B.V[b]);
+	double4 Va = vs.ldV(a), Vb = vs.ldV(b);
 	if(mode == 0) joint_apply_cached(J, j, Va, Vb, mia, mib, dt_coef);
 	else joint_apply(J, j, Va, Vb, mia, mib, dt);
-	if(mia.x != 0.0 || mia.y != 0.0) st_vel(&B.V[a], Va);
-	if(mib.x != 0.0 || mib.y != 0.0) st_vel(&B.V[b], Vb);
+	if(mia.x != 0.0 || mia.y != 0.0) vs.stV(a, Va);
+	if(mib.x != 0.0 || mib.y != 0.0) vs.stV(b, Vb);
 }
 
 CPB_DEVICE void solve_joint(const DBodies &B, const DJoints &J, int j, int mode, double dt, double dt_coef){
-	solve_joint_idx(B, J, j, J.a[j], J.b[j], mode, dt, dt_coef);
+	VelGlobal vs = {B.V, B.VB};
+	solve_joint_idx(vs, B, J, j, J.a[j], J.b[j], mode, dt, dt_coef);
 }
 
 // all rows + joints of one colour
@@ -372,6 +435,128 @@ CPB_DEVICE void rows_writeback(const DArbs &A, const DRows &R, int n_rows, int t
 		}
 	}
 }
+
+// ---- space-local solver: batched worlds of many small spaces -------------------------------------------------
+// Spaces never interact, so a space that fits one CTA does not need the grid: its bodies' velocity sectors
+// live in shared memory for the whole solve and the colours are separated by __syncthreads (no L2 round trip,
+// no waiting for the slowest CTA of the device).  The colouring is still the world-wide one above; the rows
+// are sorted by (space, colour) instead of colour:
+//   k_colour_solve (SL mode)  colours, then histograms the buckets  start[space*64 + colour]
+//   exclusive scan            bucket begins
+//   k_sl_rows                 rows / joint list in bucket order; the atomic cursor IS the bucket word, which
+//                             therefore ends up holding the bucket END = the next bucket's begin
+//   k_sl_solve                one CTA per space: warm start + iterations + write-back
+// Bucket layout: [n_spaces*64 arbiter buckets][1 sentinel, always empty][n_spaces*64 joint buckets]; after the
+// scan the sentinel holds the number of rows, the base of the joint list.
+struct DSpaceLocal {
+	int n_spaces;
+	const int *body0, *nbody;    // [n_spaces] contiguous body range of each space
+	uint32_t *start;             // [2*n_spaces*CPB_MAX_COLOURS + 2]; NULL = mode off
+};
+CPB_DEVICE int sl_arb_bucket(int space, int colour){ return space*CPB_MAX_COLOURS + colour; }
+CPB_DEVICE int sl_joint_bucket(const DSpaceLocal &SL, int space, int colour){ return SL.n_spaces*CPB_MAX_COLOURS + 1 + space*CPB_MAX_COLOURS + colour; }
+
+CPB_DEVICE void sl_count(const DBodies &B, const DArbs &A, const DJoints &J, const DSpaceLocal &SL, int nA, int tid, int nth){
+	for(int i = tid; i < nA; i += nth){
+		if(A.active[i] != 1) continue;
+		int col = A.colour[i];
+		if(col >= 0) atomicAdd(&SL.start[sl_arb_bucket(B.space[A.ba[i]], col)], 1u);
+	}
+	for(int j = tid; j < J.n; j += nth){
+		int col = J.colour[j];
+		if(col >= 0) atomicAdd(&SL.start[sl_joint_bucket(SL, B.space[J.a[j]], col)], 1u);
+	}
+}
+
+__global__ void k_sl_rows(DBodies B, DArbs A, DJoints J, DRows R, DSpaceLocal SL)
+{
+	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
+	const int tid = CPB_TID, nth = CPB_NTHREADS;
+	const int jbase = (int)SL.start[SL.n_spaces*CPB_MAX_COLOURS];   // sentinel: never incremented
+	for(int i = tid; i < nA; i += nth){
+		if(A.active[i] != 1) continue;
+		int col = A.colour[i];
+		if(col < 0) continue;
+		write_row(A, R, i, (int)atomicAdd(&SL.start[sl_arb_bucket(B.space[A.ba[i]], col)], 1u));
+	}
+	for(int j = tid; j < J.n; j += nth){
+		int col = J.colour[j];
+		if(col < 0) continue;
+		J.row[(int)atomicAdd(&SL.start[sl_joint_bucket(SL, B.space[J.a[j]], col)], 1u) - jbase] = j;
+	}
+}
+
+#ifndef CPB_EMU
+__global__ void k_sl_solve(DBodies B, DArbs A, DJoints J, DRows R, DSpaceLocal SL, int iterations, double dt, double dt_coef)
+{
+	extern __shared__ double4 s_vel[];
+	__shared__ int s_a[CPB_MAX_COLOURS + 1], s_j[CPB_MAX_COLOURS + 1];   // bucket begins ([c]) / ends ([c + 1])
+	__shared__ int s_cols[CPB_MAX_COLOURS], s_ncols;
+	const int s = blockIdx.x, t = threadIdx.x, nt = blockDim.x;
+	const int b0 = SL.body0[s], nb = SL.nbody[s];
+	const int jbase = (int)SL.start[SL.n_spaces*CPB_MAX_COLOURS];
+	for(int c = t; c <= CPB_MAX_COLOURS; c += nt){
+		int ka = sl_arb_bucket(s, c) - 1, kj = sl_joint_bucket(SL, s, c) - 1;
+		s_a[c] = (ka >= 0 ? (int)SL.start[ka] : 0);
+		s_j[c] = (int)SL.start[kj] - jbase;
+	}
+	VelShared vs = {s_vel, s_vel + nb, b0};
+	for(int b = t; b < nb; b += nt){ s_vel[b] = B.V[b0 + b]; s_vel[nb + b] = B.VB[b0 + b]; }
+	__syncthreads();
+	if(t == 0){
+		int n = 0;
+		for(int c = 0; c < CPB_MAX_COLOURS; c++) if(s_a[c + 1] > s_a[c] || s_j[c + 1] > s_j[c]) s_cols[n++] = c;
+		s_ncols = n;
+	}
+	__syncthreads();
+	const int ncols = s_ncols;
+	// indices of this thread's first row / joint of the next phase are fetched one phase ahead
+	int pr = -1, pba = 0, pbb = 0, pcnt = 0, pq = -1, pj = 0, pja = 0, pjb = 0;
+	#define SL_PREFETCH(c_) do { \
+		pr = s_a[c_] + t; if(pr < s_a[(c_) + 1]){ pba = R.ba[pr]; pbb = R.bb[pr]; pcnt = R.cnt[pr]; } else pr = -1; \
+		pq = s_j[c_] + (nt - 1 - t); if(pq < s_j[(c_) + 1]){ pj = J.row[pq]; pja = J.a[pj]; pjb = J.b[pj]; } else pq = -1; } while(0)
+	if(ncols > 0) SL_PREFETCH(s_cols[0]);
+	for(int pass = 0; pass <= iterations; pass++){
+		const int mode = (pass == 0 ? 0 : 1);
+		for(int ci = 0; ci < ncols; ci++){
+			const int c = s_cols[ci];
+			const int cn = s_cols[ci + 1 < ncols ? ci + 1 : 0];
+			if(c == CPB_OVERFLOW_COLOUR){
+				if(t == 0){
+					for(int r = s_a[c]; r < s_a[c + 1]; r++) solve_row_idx(vs, B, R, r, R.ba[r], R.bb[r], R.cnt[r], mode, dt_coef);
+					for(int q = s_j[c]; q < s_j[c + 1]; q++){ int j = J.row[q]; solve_joint_idx(vs, B, J, j, J.a[j], J.b[j], mode, dt, dt_coef); }
+				}
+				SL_PREFETCH(cn);
+			} else {
+				int r = pr, ba = pba, bb = pbb, cnt = pcnt, q = pq, j = pj, ja = pja, jb = pjb;
+				SL_PREFETCH(cn);   // constant data: issue before this phase's work so the latency overlaps it
+				const int r1 = s_a[c + 1], q1 = s_j[c + 1];
+				if(r >= 0){
+					solve_row_idx(vs, B, R, r, ba, bb, cnt, mode, dt_coef);
+					for(r += nt; r < r1; r += nt) solve_row_idx(vs, B, R, r, R.ba[r], R.bb[r], R.cnt[r], mode, dt_coef);
+				}
+				// joints from the far end of the CTA: in small colours a thread gets a row or a joint, not both
+				if(q >= 0){
+					solve_joint_idx(vs, B, J, j, ja, jb, mode, dt, dt_coef);
+					for(q += nt; q < q1; q += nt){ int j2 = J.row[q]; solve_joint_idx(vs, B, J, j2, J.a[j2], J.b[j2], mode, dt, dt_coef); }
+				}
+			}
+			__syncthreads();
+		}
+	}
+	#undef SL_PREFETCH
+	for(int b = t; b < nb; b += nt){ B.V[b0 + b] = s_vel[b]; B.VB[b0 + b] = s_vel[nb + b]; }
+	// accumulated impulses back into the arbiter records
+	for(int r = s_a[0] + t; r < s_a[CPB_MAX_COLOURS]; r += nt){
+		int i = R.arb[r];
+		int cnt = R.cnt[r]; if(cnt < 0) cnt = -cnt;
+		for(int k = 0; k < cnt; k++){
+			int sidx = 2*i + k, d = k*R.cap + r;
+			A.jn[sidx] = R.jn[d]; A.jt[sidx] = R.jt[d]; A.jb[sidx] = R.jb[d];
+		}
+	}
+}
+#endif
 
 #ifndef CPB_EMU
 // Grid-wide barrier for the persistent kernel (launched cooperatively, so all CTAs are resident).
@@ -407,7 +592,8 @@ __device__ __forceinline__ unsigned long long global_ns(){ unsigned long long t;
 #define CPB_SOLVE_MIN_BLOCKS 2
 #endif
 
-__global__ void __launch_bounds__(256, CPB_SOLVE_MIN_BLOCKS) k_colour_solve(DBodies B, DArbs A, DJoints J, DRows R, DColour K, DCounters *C, unsigned *bar, int use_hints, int iterations, double dt, double dt_coef)
+// SPACE_LOCAL: colour only, then histogram the (space, colour) buckets for the space-local solver below.
+template<bool SPACE_LOCAL> __global__ void __launch_bounds__(256, CPB_SOLVE_MIN_BLOCKS) k_colour_solve(DBodies B, DArbs A, DJoints J, DRows R, DColour K, DCounters *C, unsigned *bar, DSpaceLocal SL, int use_hints, int iterations, double dt, double dt_coef)
 {
 	__shared__ int s_hist[2*CPB_MAX_COLOURS];
 	__shared__ int s_base[CPB_MAX_COLOURS];
@@ -436,6 +622,12 @@ __global__ void __launch_bounds__(256, CPB_SOLVE_MIN_BLOCKS) k_colour_solve(DBod
 	}
 	PROF(1);
 	if(tid == 0){ colour_starts(K, C); K.prof[5] = (unsigned long long)rounds_done; K.prof[6] = (unsigned long long)K.wl_n[0]; }
+	if(SPACE_LOCAL){
+		// space-local mode: this launch only colours; count the (space, colour) buckets for k_sl_rows
+		sl_count(B, A, J, SL, nA, tid, nth);
+		if(tid == 0){ K.prof[2] = K.prof[3] = K.prof[4] = global_ns(); }
+		return;
+	}
 	GRID_SYNC();
 	build_rows(A, J, R, K, s_hist, s_base, nA, tid, nth);
 	GRID_SYNC();
@@ -452,6 +644,7 @@ __global__ void __launch_bounds__(256, CPB_SOLVE_MIN_BLOCKS) k_colour_solve(DBod
 	int nreg = (ncol > CPB_OVERFLOW_COLOUR ? CPB_OVERFLOW_COLOUR : ncol);
 	bool has_overflow = (ncol > CPB_OVERFLOW_COLOUR);
 	const int jtid = nth - 1 - tid;
+	const VelGlobal vg = {B.V, B.VB};
 	int pr = -1, pba = 0, pbb = 0, pcnt = 0;     // prefetched row
 	int pq = -1, pj = 0, pja = 0, pjb = 0;       // prefetched joint
 	#define PREFETCH_PHASE(c_) do { \
@@ -466,13 +659,13 @@ __global__ void __launch_bounds__(256, CPB_SOLVE_MIN_BLOCKS) k_colour_solve(DBod
 				int r = pr, ba = pba, bb = pbb, cnt = pcnt;
 				pr += nth;
 				if(pr < r1){ pba = ROW_LD(&R.ba[pr]); pbb = ROW_LD(&R.bb[pr]); pcnt = ROW_LD(&R.cnt[pr]); } else pr = -1;
-				solve_row_idx(B, R, r, ba, bb, cnt, mode, dt_coef);
+				solve_row_idx(vg, B, R, r, ba, bb, cnt, mode, dt_coef);
 			}
 			while(pq >= 0){
 				int j = pj, a = pja, b = pjb;
 				pq += nth;
 				if(pq < j1){ pj = J.row[pq]; pja = J.a[pj]; pjb = J.b[pj]; } else pq = -1;
-				solve_joint_idx(B, J, j, a, b, mode, dt, dt_coef);
+				solve_joint_idx(vg, B, J, j, a, b, mode, dt, dt_coef);
 			}
 			int cn = (c + 1 < nreg ? c + 1 : 0);
 			if(c + 1 < nreg || pass < iterations) PREFETCH_PHASE(cn);

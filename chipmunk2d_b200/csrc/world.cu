@@ -21,6 +21,7 @@ emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 #else
 unsigned long long g_cpb_launches = 0;
 #endif
+#define CPB_SL_MAX_SMEM (200*1024)   // shared memory a space's velocity sectors may take in k_sl_solve
 
 // ------------------------------------------------------------------ errors
 static thread_local char g_error[512] = "";
@@ -116,6 +117,12 @@ struct cpb200_world {
 	int wl_cap; AllocGroup gW;
 	int force_blocks;       // validation hook: fixed persistent grid size (0 = automatic)
 	int last_active;        // active arbiters seen at the last host read-back (grid sizing hint)
+	// space-local solver (k_sl_solve): usable when every space owns one contiguous, small body range
+	std::vector<int> body_space;   // host copy of the bodies' space index
+	bool sl_dirty, sl_ok, sl_disabled;
+	int sl_max_nbody;
+	DSpaceLocal SL; AllocGroup gSL;
+	uint32_t *sl_tmp;
 	double *d_scratch;      // small scratch (collide_one output, stats)
 	double *h_scratch;      // pinned
 };
@@ -189,10 +196,11 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 		cudaDeviceProp prop;
 		if(cudaGetDeviceProperties(&prop, device) == cudaSuccess) w->sm_count = prop.multiProcessorCount;
 		int per_sm = 1;
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colour_solve, 256, 0);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colour_solve<false>, 256, 0);
 		if(per_sm < 1) per_sm = 1;
 		if(per_sm > 4) per_sm = 4;
 		w->coop_blocks = w->sm_count*per_sm;
+		cudaFuncSetAttribute(k_sl_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, CPB_SL_MAX_SMEM);
 	}
 #endif
 	cpb200_space_params def;
@@ -220,6 +228,8 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	cudaMallocHost(&p, sizeof(DCounters)); w->hC = (DCounters *)p; memset(w->hC, 0, sizeof(DCounters));
 	cudaMalloc(&p, sizeof(unsigned)*8); w->d_barrier = (unsigned *)p; cudaMemsetAsync(w->d_barrier, 0, sizeof(unsigned)*8, w->stream);
 	w->no_hints = (getenv("CPB200_NO_HINTS") != NULL);
+	w->sl_dirty = true; w->sl_ok = false; w->sl_disabled = (getenv("CPB200_NO_SPACE_LOCAL") != NULL); w->sl_max_nbody = 0;
+	memset(&w->SL, 0, sizeof(w->SL)); w->sl_tmp = NULL;
 	w->last_active = 0; w->force_blocks = 0; w->hints_valid = false; w->wl_cap = 0; w->d_stage = NULL; w->stage_bytes = 0;
 	cudaMalloc(&p, sizeof(double)*64); w->d_scratch = (double *)p;
 	cudaMallocHost(&p, sizeof(double)*64); w->h_scratch = (double *)p;
@@ -351,6 +361,7 @@ extern "C" int cpb200_world_set_bodies(cpb200_world *w, int n, const cpb200_body
 	DA(w->gK, w->K.jcount, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.jstart, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.jcursor, CPB_MAX_COLOURS + 1);
 	DA(w->gK, w->K.wl_n, CPB_MAX_COLOUR_ROUNDS + 2); DA(w->gK, w->K.prof, 8);
 	w->hints_valid = false; // body types / masses may have changed: colour from scratch once
+	w->body_space.clear(); w->sl_dirty = true;
 	w->gI.release();
 	DA(w->gI, w->I.parent, n); DA(w->gI, w->I.wake, n); DA(w->gI, w->I.comp_active, n); DA(w->gI, w->I.woken, n);
 	int r = cpb200_world_update_bodies(w, 0, n, bodies);
@@ -364,6 +375,10 @@ extern "C" int cpb200_world_update_bodies(cpb200_world *w, int first, int n, con
 	if(n == 0) return 0;
 	cudaSetDevice(w->device);
 	size_t bytes = sizeof(cpb200_body_desc)*(size_t)n;
+	if((int)w->body_space.size() != w->B.n){ w->body_space.assign((size_t)w->B.n, 0); w->sl_dirty = true; }
+	for(int i = 0; i < n; i++){
+		if(w->body_space[(size_t)(first + i)] != (int)bodies[i].space){ w->body_space[(size_t)(first + i)] = (int)bodies[i].space; w->sl_dirty = true; }
+	}
 	if(stage_reserve(w, bytes + 64)) return -1;
 	int *bad = (int *)((char *)w->d_stage + ((bytes + 15) & ~(size_t)15));
 	CPB_CHECK(cudaMemsetAsync(bad, 0, sizeof(int), w->stream));
@@ -681,6 +696,38 @@ __global__ void k_build_order(DShapes S, DArbs A, DTable T, const uint64_t *__re
 	*n_order_out = n;
 }
 
+// Space-local solver layout: every space must own one contiguous body range small enough for the shared
+// memory of a CTA (two 32-byte velocity sectors per body).
+static int sl_refresh(cpb200_world *w)
+{
+	w->sl_dirty = false; w->sl_ok = false;
+	w->gSL.release(); memset(&w->SL, 0, sizeof(w->SL)); w->sl_tmp = NULL;
+	const int ns = w->n_spaces, nb = w->B.n;
+	if(w->sl_disabled || nb == 0 || (int)w->body_space.size() != nb) return 0;
+	std::vector<int> first((size_t)ns, -1), count((size_t)ns, 0);
+	for(int i = 0; i < nb; i++){
+		int sp = w->body_space[(size_t)i];
+		if(sp < 0 || sp >= ns) return 0;
+		if(first[(size_t)sp] < 0) first[(size_t)sp] = i;
+		else if(first[(size_t)sp] + count[(size_t)sp] != i) return 0;   // not contiguous
+		count[(size_t)sp]++;
+	}
+	int mx = 0;
+	for(int sp = 0; sp < ns; sp++){ if(first[(size_t)sp] < 0) first[(size_t)sp] = 0; mx = std::max(mx, count[(size_t)sp]); }
+	if((size_t)mx*64 > CPB_SL_MAX_SMEM) return 0;
+	int *d_first = NULL, *d_count = NULL; uint32_t *d_start = NULL;
+	size_t nbuckets = 2*(size_t)ns*CPB_MAX_COLOURS + 2;
+	DA(w->gSL, d_first, ns); DA(w->gSL, d_count, ns); DA(w->gSL, d_start, nbuckets);
+	DA(w->gSL, w->sl_tmp, cpb_scan_tmp_elems((int)nbuckets) + 16);
+	CPB_CHECK(cudaMemcpyAsync(d_first, first.data(), sizeof(int)*(size_t)ns, cudaMemcpyHostToDevice, w->stream));
+	CPB_CHECK(cudaMemcpyAsync(d_count, count.data(), sizeof(int)*(size_t)ns, cudaMemcpyHostToDevice, w->stream));
+	CPB_CHECK(cudaStreamSynchronize(w->stream));
+	w->SL.n_spaces = ns; w->SL.body0 = d_first; w->SL.nbody = d_count; w->SL.start = d_start;
+	w->sl_max_nbody = mx;
+	w->sl_ok = true;
+	return 0;
+}
+
 extern "C" int cpb200_world_step(cpb200_world *w, double dt)
 {
 	if(!w){ cpb_set_error("null world"); return -1; }
@@ -809,9 +856,27 @@ extern "C" int cpb200_world_step(cpb200_world *w, double dt)
 			int blocks = std::max(1, std::min(w->coop_blocks, cpb_div_up(est_cons + 1, 256)));
 			if(est_cons <= 4096) blocks = 1;   // small scenes: one CTA, colours separated by __syncthreads only
 			if(w->force_blocks > 0) blocks = std::min(w->coop_blocks, w->force_blocks);
-			void *args[] = {&B, &Ac, &J, &R, &K, &C, &bar, &use_hints, &iterations, &dt, &dt_coef};
-			CPB_CHECK(cudaLaunchCooperativeKernel((void *)k_colour_solve, dim3(blocks), dim3(256), args, 0, st));
+			// Space-local path: worlds whose spaces are each a small contiguous body range (batched demo
+			// spaces, or one small scene).  A forced grid (validation hook) keeps the world-wide solver.
+			if(w->sl_dirty && sl_refresh(w)) return -1;
+			bool space_local = w->sl_ok && w->force_blocks == 0 && est_cons/w->n_spaces <= 4096;
+			DSpaceLocal SL = w->SL;
+			if(!space_local) SL.start = NULL;
+			size_t nbuckets = 2*(size_t)w->n_spaces*CPB_MAX_COLOURS + 2;
+			if(space_local) cudaMemsetAsync(SL.start, 0, sizeof(uint32_t)*nbuckets, st);
+			void *args[] = {&B, &Ac, &J, &R, &K, &C, &bar, &SL, &use_hints, &iterations, &dt, &dt_coef};
+			CPB_CHECK(cudaLaunchCooperativeKernel(space_local ? (void *)k_colour_solve<true> : (void *)k_colour_solve<false>, dim3(blocks), dim3(256), args, 0, st));
 			g_cpb_launches++;
+			if(space_local){
+				cpb_exclusive_scan(SL.start, SL.start, (int)nbuckets, w->sl_tmp, st);
+				int g = std::min(grid_for(Ac.cap + J.n, 256), wide);
+				LAUNCH(k_sl_rows, g, 256, st, B, Ac, J, R, SL);
+				// CTA width: about one row per thread in an average colour, a warp at least
+				int per_space = est_cons/w->n_spaces;
+				int threads = 32; while(threads < 256 && threads*8 < per_space) threads *= 2;
+				size_t smem = (size_t)w->sl_max_nbody*64;
+				LAUNCH_SMEM(k_sl_solve, w->n_spaces, threads, smem, st, B, Ac, J, R, SL, iterations, dt, dt_coef);
+			}
 		}
 #else
 		{

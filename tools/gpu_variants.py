@@ -24,7 +24,9 @@ if __name__ == "__main__":
     libs = sys.argv[1:]
     sets = {"pile1m": ([circle_pile(1000000, dense=True, sleep=np.inf)], 40, 30), "batch4096": (batched_demo_scenes(4096), 300, 100),
             "c1": ([golden_scene("SimpleTerrainCircles_1000")], 200, 300)}
+    only = os.environ.get("SETS")
     for name, (sc, warm, steps) in sets.items():
+        if only and name not in only.split(","): continue
         for lib in libs:
             ms, sp, st = run(os.path.join(ROOT, "chipmunk2d_b200/lib", lib), sc, warm, steps)
             print("%-10s %-22s %.3f ms/step  solve %.0f us (colour %.0f rows %.0f warm %.0f iterate %.0f) colours %d" % (name, lib, ms, st["colour_solve"], sp["colour_us"], sp["rows_us"], sp["warm_us"], sp["iterate_us"], sp["n_colours"]), flush=True)
