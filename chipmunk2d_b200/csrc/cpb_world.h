@@ -82,7 +82,8 @@ struct DArbs {
 	V2 *n;
 	double *e, *u;
 	V2 *svr;               // surface_vr
-	// contacts, index = 2*arb + k
+	// contacts: contact k of record i at CIDX(A, i, k) = k*cap + i (two planes: records with one contact, the
+	// common case, then touch dense memory; prev and cur always share cap)
 	V2 *r1, *r2;
 	double *nmass, *tmass, *bounce, *bias;
 	double *jn, *jt, *jb;  // jnAcc, jtAcc, jBias
@@ -90,13 +91,17 @@ struct DArbs {
 	int *colour;           // colour assigned this step (-1 = not in the solver)
 	uint64_t *pri;         // colouring priority: hash of the space-local shape pair (same in a batch as alone)
 	int *hint;             // last step's colour if the arbiter was solved then, else -1
+	// what the NEXT step's collision phase needs from a record, packed into one 64-byte line by k_pack_warm:
+	// warm[2i] = (jn0, jt0, jn1, jt1), warm[2i+1] = (hash0, hash1, gjkid<<32 | colour<<24 | active<<16 | cnt<<8 | state, -)
+	double4 *warm;
 };
+
+#define CIDX(A, i, k) ((k)*(A).cap + (i))
 
 // open-addressing table: shape-pair key -> arbiter record index (replaces cpHashSet cachedArbiters)
 struct DTable {
 	uint32_t mask;         // capacity - 1 (capacity is a power of two)
-	uint64_t *keys;        // 0 = empty
-	int *vals;
+	ulonglong2 *slots;     // x = key (0 = empty), y = record index: one 16-byte access per probe
 };
 
 // ---- colour-sorted solver rows (one per active arbiter), rebuilt every step ----

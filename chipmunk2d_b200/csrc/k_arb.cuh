@@ -46,9 +46,9 @@ CPB_DEVICE uint64_t arb_key(uint32_t ha, uint32_t hb){
 CPB_DEVICE int table_find(const DTable &T, uint64_t key){
 	uint32_t slot = (uint32_t)mix64(key) & T.mask;
 	for(uint32_t probe = 0; probe <= T.mask; probe++){
-		uint64_t k = T.keys[slot];
-		if(k == key) return T.vals[slot];
-		if(k == 0) return -1;
+		ulonglong2 e = T.slots[slot];
+		if(e.x == key) return (int)e.y;
+		if(e.x == 0) return -1;
 		slot = (slot + 1) & T.mask;
 	}
 	return -1;
@@ -57,8 +57,8 @@ CPB_DEVICE int table_find(const DTable &T, uint64_t key){
 CPB_DEVICE bool table_insert(const DTable &T, uint64_t key, int val){
 	uint32_t slot = (uint32_t)mix64(key) & T.mask;
 	for(uint32_t probe = 0; probe <= T.mask; probe++){
-		unsigned long long old = atomicCAS((unsigned long long *)&T.keys[slot], 0ull, (unsigned long long)key);
-		if(old == 0ull || old == (unsigned long long)key){ T.vals[slot] = val; return true; }
+		unsigned long long old = atomicCAS(&T.slots[slot].x, 0ull, (unsigned long long)key);
+		if(old == 0ull || old == (unsigned long long)key){ T.slots[slot].y = (unsigned long long)val; return true; }
 		slot = (slot + 1) & T.mask;
 	}
 	return false;
@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 		bool sensor = false;
 		uint2 ida = {0u, 0u}, idb = {0u, 0u};
 		uint64_t key = 0;
+		double4 w0 = make_double4(0, 0, 0, 0), w1 = w0;
 		if(i < np){
 			sa = pa[i]; sb = pb[i];
 			ida = S.ids[sa]; idb = S.ids[sb];
@@ -92,9 +93,11 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 				ba = (int)(wa_ & 0x7fffffffu); bb = (int)(wb_ & 0x7fffffffu); sensor = ((wa_ | wb_) >> 31) != 0;
 				circle_to_circle(a, b, m);
 				if(m.count > 0) pi = table_find(prev_table, key);
+				if(pi >= 0){ w0 = ld4_nc(&prev.warm[2*pi]); w1 = ld4_nc(&prev.warm[2*pi + 1]); }
 			} else {
 				pi = table_find(prev_table, key);
-				m.id = (pi >= 0 ? prev.gjkid[pi] : 0u);
+				if(pi >= 0){ w0 = ld4_nc(&prev.warm[2*pi]); w1 = ld4_nc(&prev.warm[2*pi + 1]); }
+				m.id = (pi >= 0 ? (uint32_t)((unsigned long long)__double_as_longlong(w1.z) >> 32) : 0u);
 				NShape a = load_nshape(S, B, sa), b = load_nshape(S, B, sb);
 				if(CLS == 1) circle_to_segment(a, b, m);
 				else collide_shapes(a, b, m);
@@ -106,13 +109,18 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 		if(!have) continue;
 		if(slot >= cur.cap){ atomicOr((unsigned *)&C->overflow, 2u); continue; }
 
-		// cpArbiterUpdate (cpArbiter.c:356-414)
+		// cpArbiterUpdate (cpArbiter.c:356-414); the previous record's fields come from its packed line
 		int state = CPB200_ARB_FIRST_COLLISION;
-		int pcnt = 0;
+		int pcnt = 0, pactive = 0, pcolour = -1;
+		uint64_t phash[2] = {0, 0};
+		double pjn[2] = {0.0, 0.0}, pjt[2] = {0.0, 0.0};
 		if(pi >= 0){
 			prev.seen[pi] = 1;
-			int ps = prev.state[pi];
-			pcnt = prev.cnt[pi];
+			unsigned meta = (unsigned)(unsigned long long)__double_as_longlong(w1.z);
+			int ps = (int)(meta & 0xffu);
+			pcnt = (int)((meta >> 8) & 0xffu); pactive = (int)((meta >> 16) & 0xffu); pcolour = (int)(signed char)(meta >> 24);
+			phash[0] = (uint64_t)__double_as_longlong(w1.x); phash[1] = (uint64_t)__double_as_longlong(w1.y);
+			pjn[0] = w0.x; pjt[0] = w0.y; pjn[1] = w0.z; pjt[1] = w0.w;
 			// CACHED -> FIRST_COLLISION (cpArbiter.c:412-413); IGNORE is sticky until separation
 			state = (ps == CPB200_ARB_CACHED ? CPB200_ARB_FIRST_COLLISION : (ps == CPB200_ARB_IGNORE ? CPB200_ARB_IGNORE : CPB200_ARB_NORMAL));
 		}
@@ -120,9 +128,9 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 		for(int k = 0; k < m.count; k++){
 			double jn = 0.0, jt = 0.0;
 			for(int j = 0; j < pcnt; j++){
-				if(m.hash[k] == prev.hash[2*pi + j]){ jn = prev.jn[2*pi + j]; jt = prev.jt[2*pi + j]; }
+				if(m.hash[k] == phash[j]){ jn = pjn[j]; jt = pjt[j]; }
 			}
-			int c = 2*slot + k;
+			int c = CIDX(cur, slot, k);
 			cur.r1[c] = vsub(m.p1[k], pa_);
 			cur.r2[c] = vsub(m.p2[k], pb_);
 			cur.jn[c] = jn; cur.jt[c] = jt; cur.jb[c] = 0.0;
@@ -143,7 +151,7 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 		cur.seen[slot] = 0;
 		cur.colour[slot] = -1;
 		cur.pri[slot] = mix64(arb_key(ida.y, idb.y)) >> 8;
-		cur.hint[slot] = (pi >= 0 && prev.active[pi] == 1 ? prev.colour[pi] : -1);
+		cur.hint[slot] = (pi >= 0 && pactive == 1 ? pcolour : -1);
 		// active <=> pushed to space->arbiters (cpSpaceStep.c:261-274); the default handler accepts everything
 		bool both_inf = (B.type[ba] != CPB200_BODY_DYNAMIC) && (B.type[bb] != CPB200_BODY_DYNAMIC);
 		bool active = (state != CPB200_ARB_IGNORE) && !sensor && !both_inf;
@@ -162,6 +170,20 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 		if(active){ atomicAdd(&C->n_active, 1); atomicAdd(&C->n_contacts, m.count); }
 #endif
 		if(!table_insert(cur_table, key, slot)) atomicOr((unsigned *)&C->overflow, 4u);
+	}
+}
+
+// Packs what the collision phase reads from last step's records into one 64-byte line per record (the
+// lookups are random: one DRAM burst instead of eight scattered sectors).
+__global__ void k_pack_warm(DArbs A)
+{
+	int n = *A.count_ptr; if(n > A.cap) n = A.cap;
+	for(int i = CPB_TID; i < n; i += CPB_NTHREADS){
+		unsigned long long meta = ((unsigned long long)A.gjkid[i] << 32) | ((unsigned long long)(unsigned char)(signed char)A.colour[i] << 24) |
+			((unsigned long long)(A.active[i] & 0xff) << 16) | ((unsigned long long)(A.cnt[i] & 0xff) << 8) | (unsigned long long)(A.state[i] & 0xff);
+		const int c0 = CIDX(A, i, 0), c1 = CIDX(A, i, 1);
+		A.warm[2*i] = make_double4(A.jn[c0], A.jt[c0], A.jn[c1], A.jt[c1]);
+		A.warm[2*i + 1] = make_double4(__longlong_as_double((long long)A.hash[c0]), __longlong_as_double((long long)A.hash[c1]), __longlong_as_double((long long)meta), 0.0);
 	}
 }
 
@@ -208,7 +230,7 @@ __global__ void k_arb_carry(DBodies B, DArbs prev, DArbs cur, DTable cur_table, 
 		cur.pri[slot] = prev.pri[i];
 		cur.hint[slot] = -1;
 		for(int k = 0; k < 2; k++){
-			int c = 2*slot + k, p = 2*i + k;
+			int c = CIDX(cur, slot, k), p = CIDX(prev, i, k);
 			cur.r1[c] = prev.r1[p]; cur.r2[c] = prev.r2[p];
 			cur.nmass[c] = prev.nmass[p]; cur.tmass[c] = prev.tmass[p]; cur.bounce[c] = prev.bounce[p]; cur.bias[c] = prev.bias[p];
 			cur.jn[c] = prev.jn[p]; cur.jt[c] = prev.jt[p]; cur.jb[c] = prev.jb[p];
@@ -240,7 +262,7 @@ __global__ void k_arb_prestep(DBodies B, DArbs A, const DSpace *__restrict__ spa
 	double e = A.e[i];
 	int cnt = A.cnt[i];
 	for(int k = 0; k < cnt; k++){
-		int c = 2*i + k;
+		int c = CIDX(A, i, k);
 		V2 r1 = A.r1[c], r2 = A.r2[c];
 		A.nmass[c] = 1.0/(k_scalar_body(mia, r1, n_) + k_scalar_body(mib, r2, n_));
 		V2 t = vperp(n_);

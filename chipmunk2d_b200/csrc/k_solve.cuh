@@ -163,7 +163,7 @@ CPB_DEVICE void write_row(const DArbs &A, const DRows &R, int i, int r){
 	R.cnt[r] = (A.state[i] == CPB200_ARB_FIRST_COLLISION ? -cnt : cnt);
 	R.n[r] = A.n[i]; R.svr[r] = A.svr[i]; R.u[r] = A.u[i];
 	for(int k = 0; k < cnt; k++){
-		int s = 2*i + k, d = k*R.cap + r;
+		int s = CIDX(A, i, k), d = k*R.cap + r;
 		R.r1[d] = A.r1[s]; R.r2[d] = A.r2[s];
 		R.nmass[d] = A.nmass[s]; R.tmass[d] = A.tmass[s]; R.bounce[d] = A.bounce[s]; R.bias[d] = A.bias[s];
 		R.jn[d] = A.jn[s]; R.jt[d] = A.jt[s]; R.jb[d] = A.jb[s];
@@ -430,7 +430,7 @@ CPB_DEVICE void rows_writeback(const DArbs &A, const DRows &R, int n_rows, int t
 		int i = R.arb[r];
 		int cnt = R.cnt[r]; if(cnt < 0) cnt = -cnt;
 		for(int k = 0; k < cnt; k++){
-			int s = 2*i + k, d = k*R.cap + r;
+			int s = CIDX(A, i, k), d = k*R.cap + r;
 			A.jn[s] = ld_f64(&R.jn[d]); A.jt[s] = ld_f64(&R.jt[d]); A.jb[s] = ld_f64(&R.jb[d]);
 		}
 	}
@@ -551,7 +551,7 @@ __global__ void k_sl_solve(DBodies B, DArbs A, DJoints J, DRows R, DSpaceLocal S
 		int i = R.arb[r];
 		int cnt = R.cnt[r]; if(cnt < 0) cnt = -cnt;
 		for(int k = 0; k < cnt; k++){
-			int sidx = 2*i + k, d = k*R.cap + r;
+			int sidx = CIDX(A, i, k), d = k*R.cap + r;
 			A.jn[sidx] = R.jn[d]; A.jt[sidx] = R.jt[d]; A.jb[sidx] = R.jb[d];
 		}
 	}
@@ -737,7 +737,7 @@ __global__ void k_solve_serial(DBodies B, DArbs A, DJoints J, const int *__restr
 			int cnt = A.cnt[i];
 			for(int kk = 0; kk < cnt; kk++){
 				int k = (reversed ? cnt - 1 - kk : kk);
-				int s = 2*i + k;
+				int s = CIDX(A, i, k);
 				if(pass == 0) contact_apply_cached(Va, Vb, mia, mib, n, A.r1[s], A.r2[s], A.jn[s], A.jt[s], dt_coef);
 				else contact_apply(Va, Vb, VBa, VBb, mia, mib, n, A.svr[i], A.u[i], A.r1[s], A.r2[s], A.nmass[s], A.tmass[s], A.bias[s], A.bounce[s], A.jn[s], A.jt[s], A.jb[s]);
 			}

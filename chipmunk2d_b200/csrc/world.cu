@@ -159,6 +159,17 @@ static int download(cpb200_world *w, std::vector<T> &dst, const T *src, size_t n
 	return 0;
 }
 
+// per-contact arrays: plane k of n records lives at src + k*cap; dst = [plane 0 | plane 1]
+template <typename T>
+static int download2(cpb200_world *w, std::vector<T> &dst, const T *src, size_t n, int cap)
+{
+	dst.resize(2*n);
+	if(n == 0) return 0;
+	CPB_CHECK(cudaMemcpyAsync(dst.data(), src, sizeof(T)*n, cudaMemcpyDeviceToHost, w->stream));
+	CPB_CHECK(cudaMemcpyAsync(dst.data() + n, src + cap, sizeof(T)*n, cudaMemcpyDeviceToHost, w->stream));
+	return 0;
+}
+
 static inline int grid_for(int n, int block){ int g = cpb_div_up(n > 0 ? n : 1, block); return g; }
 
 static int world_sync(cpb200_world *w)
@@ -447,10 +458,10 @@ static int alloc_arbs(cpb200_world *w, int cap)
 		DA(w->gA, A.r1, 2*(size_t)cap); DA(w->gA, A.r2, 2*(size_t)cap);
 		DA(w->gA, A.nmass, 2*(size_t)cap); DA(w->gA, A.tmass, 2*(size_t)cap); DA(w->gA, A.bounce, 2*(size_t)cap); DA(w->gA, A.bias, 2*(size_t)cap);
 		DA(w->gA, A.jn, 2*(size_t)cap); DA(w->gA, A.jt, 2*(size_t)cap); DA(w->gA, A.jb, 2*(size_t)cap); DA(w->gA, A.hash, 2*(size_t)cap);
-		DA(w->gA, A.colour, cap); DA(w->gA, A.pri, cap); DA(w->gA, A.hint, cap);
+		DA(w->gA, A.colour, cap); DA(w->gA, A.pri, cap); DA(w->gA, A.hint, cap); DA(w->gA, A.warm, 2*(size_t)cap);
 		DTable &T = w->T[k];
 		T.mask = tcap - 1;
-		DA(w->gA, T.keys, tcap); DA(w->gA, T.vals, tcap);
+		DA(w->gA, T.slots, tcap);
 	}
 	DRows &R = w->R;
 	R.cap = cap;
@@ -757,7 +768,7 @@ extern "C" int cpb200_world_step(cpb200_world *w, double dt)
 	DArbs &Ap = w->A[prv]; DArbs &Ac = w->A[w->cur];
 	DTable &Tp = w->T[prv]; DTable &Tc = w->T[w->cur];
 	LAUNCH(k_reset_step, 1, 32, st, w->C, w->P.count, Ac.count_ptr);
-	cudaMemsetAsync(Tc.keys, 0, sizeof(uint64_t)*((size_t)Tc.mask + 1), st);
+	cudaMemsetAsync(Tc.slots, 0, sizeof(ulonglong2)*((size_t)Tc.mask + 1), st);
 
 	const int nb = B.n, ns = S.n;
 	const int wide = w->sm_count*8;
@@ -795,6 +806,7 @@ extern "C" int cpb200_world_step(cpb200_world *w, double dt)
 	// K5 + K6
 	{
 		int g = std::min(grid_for(w->P.cap, 128), wide);
+		LAUNCH(k_pack_warm, std::min(grid_for(Ap.cap, 256), wide), 256, st, Ap);
 		LAUNCH(k_collide<0>, g, 128, st, S, B, (const int *)w->P.a[0], (const int *)w->P.b[0], (const int *)&w->P.count[0], w->P.cap, Ap, Tp, Ac, Tc, w->stamp, w->C);
 		LAUNCH(k_collide<1>, g, 128, st, S, B, (const int *)w->P.a[1], (const int *)w->P.b[1], (const int *)&w->P.count[1], w->P.cap, Ap, Tp, Ac, Tc, w->stamp, w->C);
 		LAUNCH(k_collide<2>, g, 128, st, S, B, (const int *)w->P.a[2], (const int *)w->P.b[2], (const int *)&w->P.count[2], w->P.cap, Ap, Tp, Ac, Tc, w->stamp, w->C);
@@ -1004,9 +1016,9 @@ extern "C" int cpb200_world_get_arbiters(cpb200_world *w, int cap, cpb200_arbite
 	std::vector<double> e, u, nmass, tmass, bounce, bias, jn, jt, jb; std::vector<uint64_t> hash;
 	if(download(w, sa, A.sa, N) || download(w, sb, A.sb, N) || download(w, ba, A.ba, N) || download(w, bb, A.bb, N) || download(w, cnt, A.cnt, N) ||
 	   download(w, state, A.state, N) || download(w, active, A.active, N) || download(w, stamp, A.stamp, N) || download(w, nn, A.n, N) ||
-	   download(w, svr, A.svr, N) || download(w, e, A.e, N) || download(w, u, A.u, N) || download(w, r1, A.r1, 2*N) || download(w, r2, A.r2, 2*N) ||
-	   download(w, nmass, A.nmass, 2*N) || download(w, tmass, A.tmass, 2*N) || download(w, bounce, A.bounce, 2*N) || download(w, bias, A.bias, 2*N) ||
-	   download(w, jn, A.jn, 2*N) || download(w, jt, A.jt, 2*N) || download(w, jb, A.jb, 2*N) || download(w, hash, A.hash, 2*N)) return -1;
+	   download(w, svr, A.svr, N) || download(w, e, A.e, N) || download(w, u, A.u, N) || download2(w, r1, A.r1, N, A.cap) || download2(w, r2, A.r2, N, A.cap) ||
+	   download2(w, nmass, A.nmass, N, A.cap) || download2(w, tmass, A.tmass, N, A.cap) || download2(w, bounce, A.bounce, N, A.cap) || download2(w, bias, A.bias, N, A.cap) ||
+	   download2(w, jn, A.jn, N, A.cap) || download2(w, jt, A.jt, N, A.cap) || download2(w, jb, A.jb, N, A.cap) || download2(w, hash, A.hash, N, A.cap)) return -1;
 	if(world_sync(w)) return -1;
 	int m = 0;
 	for(size_t i = 0; i < N; i++){
@@ -1018,7 +1030,7 @@ extern "C" int cpb200_world_get_arbiters(cpb200_world *w, int cap, cpb200_arbite
 			o.count = (active[i] ? cnt[i] : 0); o.state = state[i]; o.stamp = stamp[i]; o.active = active[i];
 			o.n[0] = nn[i].x; o.n[1] = nn[i].y; o.e = e[i]; o.u = u[i]; o.surface_vr[0] = svr[i].x; o.surface_vr[1] = svr[i].y;
 			for(int k = 0; k < 2; k++){
-				size_t c = 2*i + (size_t)k;
+				size_t c = (size_t)k*N + i;
 				o.contacts[k].r1[0] = r1[c].x; o.contacts[k].r1[1] = r1[c].y; o.contacts[k].r2[0] = r2[c].x; o.contacts[k].r2[1] = r2[c].y;
 				o.contacts[k].n_mass = nmass[c]; o.contacts[k].t_mass = tmass[c]; o.contacts[k].bounce = bounce[c]; o.contacts[k].bias = bias[c];
 				o.contacts[k].jn_acc = jn[c]; o.contacts[k].jt_acc = jt[c]; o.contacts[k].j_bias = jb[c]; o.contacts[k].hash = hash[c];
@@ -1071,7 +1083,7 @@ __global__ void k_stats(DBodies B, DArbs A, double *out, unsigned *awake)
 		V2 n = A.n[i];
 		V2 delta = vsub(B.pos[A.bb[i]], B.pos[A.ba[i]]);
 		for(int k = 0; k < A.cnt[i]; k++){
-			double dist = vdot(vadd(vsub(A.r2[2*i + k], A.r1[2*i + k]), delta), n);
+			double dist = vdot(vadd(vsub(A.r2[CIDX(A, i, k)], A.r1[CIDX(A, i, k)]), delta), n);
 			if(-dist > pen) pen = -dist;
 		}
 	}
