@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "lib")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
-CC_FLAGS = ["-O2", "-std=gnu99", "-ffp-contract=off", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wextra",
+CC_FLAGS = ["-O2", "-std=gnu99", "-ffp-contract=off", "-fopenmp", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wextra",
             "-Wno-unused-parameter", "-DNDEBUG"]
 
 

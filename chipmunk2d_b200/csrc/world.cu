@@ -35,6 +35,26 @@ void cpb_set_error(const char *fmt, ...)
 
 extern "C" const char *cpb200_last_error(void){ return g_error; }
 
+extern "C" void *cpb200_host_alloc(size_t bytes)
+{
+#ifdef CPB_EMU
+	return malloc(bytes);
+#else
+	void *p = NULL;
+	if(cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess){ cudaGetLastError(); return NULL; }
+	return p;
+#endif
+}
+
+extern "C" void cpb200_host_free(void *p)
+{
+#ifdef CPB_EMU
+	free(p);
+#else
+	if(p) cudaFreeHost(p);
+#endif
+}
+
 extern "C" int cpb200_device_available(void)
 {
 #ifdef CPB_EMU

@@ -153,6 +153,10 @@ struct cpSpace {
 	cpBool bbStale, arbStale, jointStale;
 	cpArbiter *arbs; int nArbs, capArbs;
 
+	/* per-step exchange buffers, page-locked, grown on demand and kept for the life of the space */
+	void *xferStates; size_t xferStatesBytes;
+	void *xferForces; size_t xferForcesBytes;
+
 	cpBool hasty;
 	unsigned long hastyThreads;
 };

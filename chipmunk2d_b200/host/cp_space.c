@@ -13,6 +13,7 @@
 #include <stdio.h>
 
 #include "cp_host.h"
+#include <omp.h>
 
 static int g_default_device = -1;
 
@@ -81,6 +82,9 @@ cpSpaceDestroy(cpSpace *space)
 	for(int i = 0; i < space->nBodies; i++){ space->bodies[i]->space = NULL; space->bodies[i]->index = -1; }
 	for(int i = 0; i < space->nShapes; i++){ space->shapes[i]->space = NULL; space->shapes[i]->index = -1; }
 	for(int i = 0; i < space->nConstraints; i++){ space->constraints[i]->space = NULL; space->constraints[i]->index = -1; }
+	if(space->xferStates) cpb200_host_free(space->xferStates);
+	if(space->xferForces) cpb200_host_free(space->xferForces);
+	space->xferStates = space->xferForces = NULL; space->xferStatesBytes = space->xferForcesBytes = 0;
 	if(space->world) cpb200_world_destroy(space->world);
 	space->world = NULL;
 	cpfree(space->bodies); cpfree(space->shapes); cpfree(space->constraints);
@@ -392,15 +396,42 @@ upload_bodies(cpSpace *space, cpBool full)
 	if(rc) cpEngineError("body upload");
 }
 
+/* grow-only page-locked exchange buffer */
+static void *
+xfer_buffer(void **buf, size_t *have, size_t need)
+{
+	if(*have < need){
+		if(*buf) cpb200_host_free(*buf);
+		size_t bytes = need + need/4 + 4096;
+		*buf = cpb200_host_alloc(bytes);
+		cpAssertHard(*buf != NULL, "Could not allocate the page-locked exchange buffer.");
+		*have = bytes;
+	}
+	return *buf;
+}
+
+/* Host loops over all bodies (mirror <-> exchange buffer) are memory bound; large spaces split them over
+ * the host cores.  cpHastySpaceSetThreads() caps the team (the reference's knob for its threaded solver). */
+#define CP_PARALLEL_MIN_BODIES 20000
+static int
+host_threads(const cpSpace *space, int n)
+{
+	if(n < CP_PARALLEL_MIN_BODIES) return 1;
+	int t = omp_get_num_procs();
+	if(t > 16) t = 16;
+	if(space->hasty && space->hastyThreads > 0 && (int)space->hastyThreads < t) t = (int)space->hastyThreads;
+	return (t < 1 ? 1 : t);
+}
+
 static void
 upload_forces(cpSpace *space)
 {
 	int n = space->nBodies;
-	double *f = (double *)cpcalloc((size_t)n, 3*sizeof(double));
-	for(int i = 0; i < n; i++){ const cpBody *b = space->bodies[i]; f[3*i] = b->f.x; f[3*i + 1] = b->f.y; f[3*i + 2] = b->t; }
-	int rc = cpb200_world_set_body_forces(space->world, 0, n, f);
-	cpfree(f);
-	if(rc) cpEngineError("force upload");
+	double *f = (double *)xfer_buffer(&space->xferForces, &space->xferForcesBytes, (size_t)n*3*sizeof(double));
+	cpBody **bodies = space->bodies;
+	#pragma omp parallel for schedule(static) num_threads(host_threads(space, n))
+	for(int i = 0; i < n; i++){ const cpBody *b = bodies[i]; f[3*i] = b->f.x; f[3*i + 1] = b->f.y; f[3*i + 2] = b->t; }
+	if(cpb200_world_set_body_forces(space->world, 0, n, f)) cpEngineError("force upload");
 }
 
 static void
@@ -513,8 +544,10 @@ cpSpaceFetchBodiesB200(cpSpace *space)
 	if(!space->hostStale || !space->world){ space->hostStale = cpFalse; return; }
 	space->hostStale = cpFalse;
 	int n = space->nBodies;
-	cpb200_body_state *st = (cpb200_body_state *)cpcalloc((size_t)n, sizeof(cpb200_body_state));
+	cpb200_body_state *st = (cpb200_body_state *)xfer_buffer(&space->xferStates, &space->xferStatesBytes, (size_t)n*sizeof(cpb200_body_state));
 	if(cpb200_world_get_bodies(space->world, 0, n, st)) cpEngineError("body download");
+	const cpBool forcesDirty = space->forcesDirty;
+	#pragma omp parallel for schedule(static) num_threads(host_threads(space, n))
 	for(int i = 0; i < n; i++){
 		cpBody *b = space->bodies[i];
 		const cpb200_body_state *s = &st[i];
@@ -531,11 +564,10 @@ cpSpaceFetchBodiesB200(cpSpace *space)
 		b->sleepRoot = (s->sleeping && s->sleep_group >= 0 && s->sleep_group < n ? space->bodies[s->sleep_group] : NULL);
 		if(!s->sleeping){
 			/* the step consumed the forces and the bias velocities (cpBody.c:505-507, 518-519) */
-			if(b->m != INFINITY && !space->forcesDirty){ b->f = cpvzero; b->t = 0.0; }
+			if(b->m != INFINITY && !forcesDirty){ b->f = cpvzero; b->t = 0.0; }
 			b->v_bias = cpvzero; b->w_bias = 0.0;
 		}
 	}
-	cpfree(st);
 }
 
 void cpSpaceSyncB200(cpSpace *space){ cpSpaceFetchBodiesB200(space); }

@@ -184,6 +184,10 @@ CPB200_API int cpb200_world_update_bodies(cpb200_world *w, int first, int n, con
 /* Forces only -- the usual per-step host input (cpBodySetForce / cpBodyApplyForceAt*, cpBody.c:420-424,
  * 534-543): fxyt[n][3] = f.x f.y torque for bodies [first, first+n). */
 CPB200_API int cpb200_world_set_body_forces(cpb200_world *w, int first, int n, const double *fxyt);
+/* Page-locked host memory for the per-step exchange buffers (forces in, body states out): a transfer from/to
+ * such a buffer is one DMA at full link speed, without the driver's bounce copy.  NULL on failure. */
+CPB200_API void *cpb200_host_alloc(size_t bytes);
+CPB200_API void cpb200_host_free(void *p);
 /* Pre-size device buffers (pairs, arbiters) for at least this many; 0 keeps the default. */
 CPB200_API int cpb200_world_reserve(cpb200_world *w, int max_pairs, int max_arbiters);
 

@@ -9,7 +9,7 @@ g++ -x c++ -std=c++17 -DCPB_EMU -O1 -g -fPIC -shared -ffp-contract=off -Wall -Wn
     -o tools/emu/_build/libcpb200_emu.so chipmunk2d_b200/csrc/world.cu
 echo built tools/emu/_build/libcpb200_emu.so
 # host layer + scene loader against the emulated engine (same sources as the product build)
-gcc -O1 -g -std=gnu99 -ffp-contract=off -fPIC -w -DNDEBUG -shared -o tools/emu/_build/libchipmunk_b200_emu.so \
+gcc -O1 -g -std=gnu99 -ffp-contract=off -fopenmp -fPIC -w -DNDEBUG -shared -o tools/emu/_build/libchipmunk_b200_emu.so \
     -I include -I chipmunk2d_b200/host chipmunk2d_b200/host/*.c -Ltools/emu/_build -lcpb200_emu -Wl,-rpath,'$ORIGIN' -lm -lpthread
 gcc -O1 -g -std=gnu99 -fPIC -w -shared -o tools/emu/_build/libscene_b200_emu.so -I include -I chipmunk2d_b200/scenes \
     chipmunk2d_b200/scenes/scene_io.c -Ltools/emu/_build -lchipmunk_b200_emu -Wl,-rpath,'$ORIGIN' -lm
