@@ -98,6 +98,7 @@ static inline unsigned long long atomicMax(unsigned long long *p, unsigned long 
 static inline unsigned atomicMax(unsigned *p, unsigned v){ unsigned o = *p; if(v > o) *p = v; return o; }
 static inline int atomicMax(int *p, int v){ int o = *p; if(v > o) *p = v; return o; }
 static inline int atomicMin(int *p, int v){ int o = *p; if(v < o) *p = v; return o; }
+static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v){ unsigned long long o = *p; if(v < o) *p = v; return o; }
 static inline unsigned atomicMin(unsigned *p, unsigned v){ unsigned o = *p; if(v < o) *p = v; return o; }
 static inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long c, unsigned long long v){ unsigned long long o = *p; if(o == c) *p = v; return o; }
 static inline unsigned atomicCAS(unsigned *p, unsigned c, unsigned v){ unsigned o = *p; if(o == c) *p = v; return o; }

@@ -15,6 +15,7 @@
 #include "k_joint.cuh"
 #include "k_solve.cuh"
 #include "k_island.cuh"
+#include "k_query.cuh"
 
 #ifdef CPB_EMU
 emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -143,6 +144,7 @@ struct cpb200_world {
 	int sl_max_nbody;
 	DSpaceLocal SL; AllocGroup gSL;
 	uint32_t *sl_tmp;
+	void *d_query; size_t query_bytes;   // device buffer for query hits (+ counters in its first 64 bytes)
 	double *d_scratch;      // small scratch (collide_one output, stats)
 	double *h_scratch;      // pinned
 };
@@ -259,6 +261,7 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	cudaMallocHost(&p, sizeof(DCounters)); w->hC = (DCounters *)p; memset(w->hC, 0, sizeof(DCounters));
 	cudaMalloc(&p, sizeof(unsigned)*8); w->d_barrier = (unsigned *)p; cudaMemsetAsync(w->d_barrier, 0, sizeof(unsigned)*8, w->stream);
 	w->no_hints = (getenv("CPB200_NO_HINTS") != NULL);
+	w->d_query = NULL; w->query_bytes = 0;
 	w->sl_dirty = true; w->sl_ok = false; w->sl_disabled = (getenv("CPB200_NO_SPACE_LOCAL") != NULL); w->sl_max_nbody = 0;
 	memset(&w->SL, 0, sizeof(w->SL)); w->sl_tmp = NULL;
 	w->last_active = 0; w->force_blocks = 0; w->hints_valid = false; w->wl_cap = 0; w->d_stage = NULL; w->stage_bytes = 0;
@@ -277,6 +280,7 @@ extern "C" void cpb200_world_destroy(cpb200_world *w)
 	cudaFree(w->d_barrier);
 	if(w->d_stage) cudaFree(w->d_stage);
 	cudaFree(w->d_spaces); cudaFree(w->C); cudaFreeHost(w->hC); cudaFree(w->d_scratch); cudaFreeHost(w->h_scratch);
+	if(w->d_query) cudaFree(w->d_query);
 	if(w->d_order) cudaFree(w->d_order);
 	if(w->d_user_order) cudaFree(w->d_user_order);
 	if(w->d_joint_order) cudaFree(w->d_joint_order);
@@ -1210,6 +1214,206 @@ extern "C" int cpb200_world_collide_pair(cpb200_world *w, int shape_a, int shape
 	if(world_sync(w)) return -1;
 	memcpy(out13, w->h_scratch + 8, sizeof(double)*13);
 	return (int)out13[0];
+}
+
+// ------------------------------------------------------------------ space queries
+static int query_reserve(cpb200_world *w, size_t bytes)
+{
+	bytes += 64;
+	if(w->query_bytes >= bytes) return 0;
+	if(w->d_query) cudaFree(w->d_query);
+	w->d_query = NULL; w->query_bytes = 0;
+	size_t want = bytes + bytes/2 + 4096;
+	CPB_CHECK(cudaMalloc(&w->d_query, want));
+	w->query_bytes = want;
+	return 0;
+}
+
+static QFilter make_filter(const cpb200_filter *f)
+{
+	QFilter q; q.group = 0; q.categories = ~0u; q.mask = ~0u;     // CP_SHAPE_FILTER_ALL
+	if(f){ q.group = f->group; q.categories = f->categories; q.mask = f->mask; }
+	return q;
+}
+
+static void copy_hit(cpb200_query_hit *o, const QHit &h)
+{
+	o->shape = h.shape; o->pad = 0; o->point[0] = h.px; o->point[1] = h.py; o->d = h.d; o->g[0] = h.gx; o->g[1] = h.gy;
+}
+
+// all hits of one scan, sorted by shape index; retried once with a larger buffer if the first guess was short
+static int query_all(cpb200_world *w, const QParams &Q, std::vector<QHit> &hits)
+{
+	cudaSetDevice(w->device);
+	ensure_cache(w);
+	hits.clear();
+	if(w->S.n == 0) return 0;
+	int cap = 1024;
+	for(int attempt = 0; attempt < 2; attempt++){
+		if(query_reserve(w, sizeof(QHit)*(size_t)cap)) return -1;
+		int *count = (int *)w->d_query;
+		QHit *out = (QHit *)((char *)w->d_query + 64);
+		CPB_CHECK(cudaMemsetAsync(count, 0, sizeof(int), w->stream));
+		LAUNCH(k_query_all, std::min(grid_for(w->S.n, 256), w->sm_count*8), 256, w->stream, w->S, w->B, Q, out, cap, count);
+		int n = 0;
+		CPB_CHECK(cudaMemcpyAsync(&n, count, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
+		if(world_sync(w)) return -1;
+		if(n <= cap){
+			hits.resize((size_t)n);
+			if(n){ CPB_CHECK(cudaMemcpyAsync(hits.data(), out, sizeof(QHit)*(size_t)n, cudaMemcpyDeviceToHost, w->stream)); if(world_sync(w)) return -1; }
+			std::sort(hits.begin(), hits.end(), [](const QHit &a, const QHit &b){ return a.shape < b.shape; });
+			return n;
+		}
+		cap = n;
+	}
+	cpb_set_error("query buffer could not be sized");
+	return -1;
+}
+
+static int query_best(cpb200_world *w, const QParams &Q, cpb200_query_hit *out)
+{
+	cudaSetDevice(w->device);
+	ensure_cache(w);
+	if(w->S.n == 0) return 0;
+	if(query_reserve(w, sizeof(QHit))) return -1;
+	unsigned long long *key = (unsigned long long *)w->d_query;
+	int *best = (int *)((char *)w->d_query + 8);
+	QHit *rec = (QHit *)((char *)w->d_query + 64);
+	CPB_CHECK(cudaMemsetAsync(key, 0xff, 8, w->stream));
+	int big = 0x7fffffff;
+	CPB_CHECK(cudaMemcpyAsync(best, &big, sizeof(int), cudaMemcpyHostToDevice, w->stream));
+	int g = std::min(grid_for(w->S.n, 256), w->sm_count*8);
+	for(int pass = 0; pass < 3; pass++) LAUNCH(k_query_best, g, 256, w->stream, w->S, w->B, Q, pass, key, best, rec);
+	int h_best = 0; QHit h;
+	CPB_CHECK(cudaMemcpyAsync(&h_best, best, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
+	CPB_CHECK(cudaMemcpyAsync(&h, rec, sizeof(QHit), cudaMemcpyDeviceToHost, w->stream));
+	if(world_sync(w)) return -1;
+	if(h_best == big) return 0;
+	if(out) copy_hit(out, h);
+	return 1;
+}
+
+static QParams make_query(int kind, int space, int only_shape, int skip_sensors, const double a[2], const double b[2], double radius, const cpb200_filter *f)
+{
+	QParams Q;
+	Q.kind = kind; Q.space = space; Q.only_shape = only_shape; Q.skip_sensors = skip_sensors;
+	Q.a = make_double2(a[0], a[1]); Q.b = (b ? make_double2(b[0], b[1]) : make_double2(0.0, 0.0));
+	Q.radius = radius; Q.filter = make_filter(f);
+	return Q;
+}
+
+extern "C" int cpb200_world_point_query(cpb200_world *w, int space, const double point[2], double max_distance, const cpb200_filter *filter, int cap, cpb200_query_hit *out)
+{
+	if(!w || !point){ cpb_set_error("bad arguments"); return -1; }
+	std::vector<QHit> hits;
+	int n = query_all(w, make_query(0, space, -1, 0, point, NULL, max_distance, filter), hits);
+	for(int i = 0; i < n && i < cap && out; i++) copy_hit(&out[i], hits[(size_t)i]);
+	return n;
+}
+
+extern "C" int cpb200_world_point_query_nearest(cpb200_world *w, int space, const double point[2], double max_distance, const cpb200_filter *filter, cpb200_query_hit *out)
+{
+	if(!w || !point){ cpb_set_error("bad arguments"); return -1; }
+	return query_best(w, make_query(0, space, -1, 1, point, NULL, max_distance, filter), out);
+}
+
+extern "C" int cpb200_world_segment_query(cpb200_world *w, int space, const double a[2], const double b[2], double radius, const cpb200_filter *filter, int cap, cpb200_query_hit *out)
+{
+	if(!w || !a || !b){ cpb_set_error("bad arguments"); return -1; }
+	std::vector<QHit> hits;
+	int n = query_all(w, make_query(1, space, -1, 0, a, b, radius, filter), hits);
+	for(int i = 0; i < n && i < cap && out; i++) copy_hit(&out[i], hits[(size_t)i]);
+	return n;
+}
+
+extern "C" int cpb200_world_segment_query_first(cpb200_world *w, int space, const double a[2], const double b[2], double radius, const cpb200_filter *filter, cpb200_query_hit *out)
+{
+	if(!w || !a || !b){ cpb_set_error("bad arguments"); return -1; }
+	cpb200_query_hit h;
+	int n = query_best(w, make_query(1, space, -1, 1, a, b, radius, filter), &h);
+	if(n == 1 && !(h.d < 1.0)) n = 0;     // info.alpha < out->alpha with out->alpha = 1 (cpSpaceQuery.c:158)
+	if(n == 1 && out) *out = h;
+	return n;
+}
+
+extern "C" int cpb200_world_bb_query(cpb200_world *w, int space, const double bb[4], const cpb200_filter *filter, int cap, int32_t *shapes)
+{
+	if(!w || !bb){ cpb_set_error("bad arguments"); return -1; }
+	std::vector<QHit> hits;
+	int n = query_all(w, make_query(2, space, -1, 0, bb, bb + 2, 0.0, filter), hits);
+	for(int i = 0; i < n && i < cap && shapes; i++) shapes[i] = hits[(size_t)i].shape;
+	return n;
+}
+
+extern "C" int cpb200_world_shape_point_query(cpb200_world *w, int shape, const double point[2], cpb200_query_hit *out)
+{
+	if(!w || !point || shape < 0 || shape >= w->S.n){ cpb_set_error("shape index out of range"); return -1; }
+	std::vector<QHit> hits;
+	int n = query_all(w, make_query(0, -1, shape, 0, point, NULL, 0.0, NULL), hits);
+	if(n == 1 && out) copy_hit(out, hits[0]);
+	return n;
+}
+
+extern "C" int cpb200_world_shape_segment_query(cpb200_world *w, int shape, const double a[2], const double b[2], double radius, cpb200_query_hit *out)
+{
+	if(!w || !a || !b || shape < 0 || shape >= w->S.n){ cpb_set_error("shape index out of range"); return -1; }
+	std::vector<QHit> hits;
+	int n = query_all(w, make_query(1, -1, shape, 0, a, b, radius, NULL), hits);
+	if(n == 1 && out) copy_hit(out, hits[0]);
+	return n;
+}
+
+extern "C" int cpb200_world_shape_query(cpb200_world *w, int space, const cpb200_query_shape *q, const double *verts_normals, int cap, cpb200_shape_hit *out)
+{
+	if(!w || !q || (q->type == CPB200_SHAPE_POLY && (!verts_normals || q->count < 1))){ cpb_set_error("bad arguments"); return -1; }
+	cudaSetDevice(w->device);
+	ensure_cache(w);
+	if(w->S.n == 0) return 0;
+	QShape qs;
+	qs.type = q->type; qs.count = (q->type == CPB200_SHAPE_POLY ? q->count : 0); qs.r = q->r; qs.self = q->self;
+	qs.a = make_double2(q->a[0], q->a[1]); qs.b = make_double2(q->b[0], q->b[1]); qs.n = make_double2(q->n[0], q->n[1]);
+	qs.rot = make_double2(q->rot[0], q->rot[1]);
+	qs.atan = make_double2(q->a_tangent[0], q->a_tangent[1]); qs.btan = make_double2(q->b_tangent[0], q->b_tangent[1]);
+	qs.bb = make_double4(q->bb[0], q->bb[1], q->bb[2], q->bb[3]);
+	qs.pv = NULL; qs.pn = NULL;
+	QFilter filter = make_filter(&q->filter);
+	size_t poly_bytes = sizeof(V2)*2*(size_t)qs.count;
+	poly_bytes = (poly_bytes + 63) & ~(size_t)63;
+	int hcap = std::max(cap, 256);
+	std::vector<QShapeHit> hits;
+	for(int attempt = 0; attempt < 2; attempt++){
+		if(query_reserve(w, poly_bytes + sizeof(QShapeHit)*(size_t)hcap)) return -1;
+		int *count = (int *)w->d_query;
+		char *base = (char *)w->d_query + 64;
+		if(qs.count){
+			std::vector<V2> pv((size_t)qs.count), pn((size_t)qs.count);
+			for(int i = 0; i < qs.count; i++){ pv[(size_t)i] = make_double2(verts_normals[4*i], verts_normals[4*i + 1]); pn[(size_t)i] = make_double2(verts_normals[4*i + 2], verts_normals[4*i + 3]); }
+			CPB_CHECK(cudaMemcpyAsync(base, pv.data(), sizeof(V2)*(size_t)qs.count, cudaMemcpyHostToDevice, w->stream));
+			CPB_CHECK(cudaMemcpyAsync(base + sizeof(V2)*(size_t)qs.count, pn.data(), sizeof(V2)*(size_t)qs.count, cudaMemcpyHostToDevice, w->stream));
+			if(world_sync(w)) return -1;     // pv / pn are stack vectors
+			qs.pv = (const V2 *)base; qs.pn = (const V2 *)(base + sizeof(V2)*(size_t)qs.count);
+		}
+		QShapeHit *dout = (QShapeHit *)(base + poly_bytes);
+		CPB_CHECK(cudaMemsetAsync(count, 0, sizeof(int), w->stream));
+		LAUNCH(k_query_shape, std::min(grid_for(w->S.n, 128), w->sm_count*8), 128, w->stream, w->S, w->B, qs, filter, space, dout, hcap, count);
+		int n = 0;
+		CPB_CHECK(cudaMemcpyAsync(&n, count, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
+		if(world_sync(w)) return -1;
+		if(n <= hcap){
+			hits.resize((size_t)n);
+			if(n){ CPB_CHECK(cudaMemcpyAsync(hits.data(), dout, sizeof(QShapeHit)*(size_t)n, cudaMemcpyDeviceToHost, w->stream)); if(world_sync(w)) return -1; }
+			std::sort(hits.begin(), hits.end(), [](const QShapeHit &a, const QShapeHit &b){ return a.shape < b.shape; });
+			for(int i = 0; i < n && i < cap && out; i++){
+				const QShapeHit &h = hits[(size_t)i];
+				out[i].shape = h.shape; out[i].count = h.count; out[i].normal[0] = h.nx; out[i].normal[1] = h.ny;
+				memcpy(out[i].points, h.pts, sizeof(h.pts));
+			}
+			return n;
+		}
+		hcap = n;
+	}
+	cpb_set_error("query buffer could not be sized");
+	return -1;
 }
 
 extern "C" int cpb200_world_get_stage_times(cpb200_world *w, int cap, float *usec)

@@ -162,6 +162,7 @@ struct cpSpace {
 };
 
 /* internal helpers */
+void cpSpacePrepareDeviceB200(cpSpace *space);
 void cpSpaceFetchBodiesB200(cpSpace *space);
 void cpSpaceFetchArbitersB200(cpSpace *space);
 void cpSpaceFetchJointsB200(cpSpace *space);

@@ -439,7 +439,7 @@ upload_shapes(cpSpace *space)
 {
 	int n = space->nShapes, nv = 0;
 	for(int i = 0; i < n; i++){ if(space->shapes[i]->klass == CP_POLY_SHAPE) nv += ((cpPolyShape *)space->shapes[i])->count; }
-	cpb200_shape_desc *descs = (cpb200_shape_desc *)cpcalloc((size_t)(n ? n : 1), sizeof(cpb200_shape_desc));
+	cpb200_shape_desc *descs = (cpb200_shape_desc *)cpcalloc((n > 0 ? (size_t)n : 1), sizeof(cpb200_shape_desc));
 	double *verts = (double *)cpcalloc((size_t)(nv ? nv : 1), 2*sizeof(double));
 	int voff = 0;
 	for(int i = 0; i < n; i++){
@@ -537,6 +537,9 @@ sync_to_device(cpSpace *space)
 	}
 	if(space->paramsDirty){ upload_params(space); space->paramsDirty = cpFalse; }
 }
+
+/* make the device world current with every host-side edit (used by the query entry points) */
+void cpSpacePrepareDeviceB200(cpSpace *space){ sync_to_device(space); }
 
 void
 cpSpaceFetchBodiesB200(cpSpace *space)

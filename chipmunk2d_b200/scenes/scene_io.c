@@ -387,3 +387,124 @@ cpb_scene_e2e_steps(cpSpace *space, double dt, int n_steps, int n_bodies, double
 	clock_gettime(CLOCK_MONOTONIC, &t1);
 	return (double)(t1.tv_sec - t0.tv_sec) + 1e-9*(double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ---- space queries through the public API (cpSpaceQuery.c), same code against either library ----
+ * Hits are reported by shape tag; rows are sorted by tag because the visiting order of the reference
+ * depends on its tree shape.  Row layouts: point [tag px py distance gx gy], segment [tag px py nx ny alpha],
+ * bb [tag], shape query [tag count nx ny (pA.xy pB.xy dist) x2]. */
+typedef struct query_rows { double *out; int stride, cap, n; } query_rows;
+static double *query_row(query_rows *q){ double *r = (q->n < q->cap ? q->out + (size_t)q->stride*q->n : NULL); q->n++; return r; }
+static int cmp_row(const void *a, const void *b){ double x = *(const double *)a, y = *(const double *)b; return (x > y) - (x < y); }
+static void point_cb(cpShape *s, cpVect p, cpFloat d, cpVect g, void *ctx){
+	double *r = query_row((query_rows *)ctx);
+	if(r){ r[0] = UNTAG(cpShapeGetUserData(s)); r[1] = p.x; r[2] = p.y; r[3] = d; r[4] = g.x; r[5] = g.y; }
+}
+static void segment_cb(cpShape *s, cpVect p, cpVect n, cpFloat alpha, void *ctx){
+	double *r = query_row((query_rows *)ctx);
+	if(r){ r[0] = UNTAG(cpShapeGetUserData(s)); r[1] = p.x; r[2] = p.y; r[3] = n.x; r[4] = n.y; r[5] = alpha; }
+}
+static void bb_cb(cpShape *s, void *ctx){
+	double *r = query_row((query_rows *)ctx);
+	if(r) r[0] = UNTAG(cpShapeGetUserData(s));
+}
+static void shape_cb(cpShape *s, cpContactPointSet *set, void *ctx){
+	double *r = query_row((query_rows *)ctx);
+	if(!r) return;
+	memset(r, 0, sizeof(double)*14);
+	r[0] = UNTAG(cpShapeGetUserData(s)); r[1] = set->count; r[2] = set->normal.x; r[3] = set->normal.y;
+	for(int k = 0; k < set->count && k < 2; k++){
+		r[4 + 5*k] = set->points[k].pointA.x; r[5 + 5*k] = set->points[k].pointA.y;
+		r[6 + 5*k] = set->points[k].pointB.x; r[7 + 5*k] = set->points[k].pointB.y; r[8 + 5*k] = set->points[k].distance;
+	}
+}
+static int finish_rows(query_rows *q){ if(q->n <= q->cap) qsort(q->out, (size_t)q->n, sizeof(double)*(size_t)q->stride, cmp_row); return q->n; }
+
+CPB_EXPORT int
+cpb_scene_point_query(cpSpace *space, double x, double y, double max_dist, uint64_t group, uint32_t cat, uint32_t mask, int cap, double *out6)
+{
+	query_rows q = {out6, 6, cap, 0};
+	cpSpacePointQuery(space, cpv(x, y), max_dist, cpShapeFilterNew((cpGroup)group, cat, mask), point_cb, &q);
+	return finish_rows(&q);
+}
+
+/* out6 = [tag px py distance gx gy]; returns 1 if a shape was found */
+CPB_EXPORT int
+cpb_scene_point_query_nearest(cpSpace *space, double x, double y, double max_dist, uint64_t group, uint32_t cat, uint32_t mask, double *out6)
+{
+	cpPointQueryInfo info;
+	cpShape *s = cpSpacePointQueryNearest(space, cpv(x, y), max_dist, cpShapeFilterNew((cpGroup)group, cat, mask), &info);
+	out6[0] = (s ? UNTAG(cpShapeGetUserData(s)) : -1); out6[1] = info.point.x; out6[2] = info.point.y; out6[3] = info.distance;
+	out6[4] = info.gradient.x; out6[5] = info.gradient.y;
+	return s != NULL;
+}
+
+CPB_EXPORT int
+cpb_scene_segment_query(cpSpace *space, double ax, double ay, double bx, double by, double radius, uint64_t group, uint32_t cat, uint32_t mask, int cap, double *out6)
+{
+	query_rows q = {out6, 6, cap, 0};
+	cpSpaceSegmentQuery(space, cpv(ax, ay), cpv(bx, by), radius, cpShapeFilterNew((cpGroup)group, cat, mask), segment_cb, &q);
+	return finish_rows(&q);
+}
+
+CPB_EXPORT int
+cpb_scene_segment_query_first(cpSpace *space, double ax, double ay, double bx, double by, double radius, uint64_t group, uint32_t cat, uint32_t mask, double *out6)
+{
+	cpSegmentQueryInfo info;
+	cpShape *s = cpSpaceSegmentQueryFirst(space, cpv(ax, ay), cpv(bx, by), radius, cpShapeFilterNew((cpGroup)group, cat, mask), &info);
+	out6[0] = (s ? UNTAG(cpShapeGetUserData(s)) : -1); out6[1] = info.point.x; out6[2] = info.point.y; out6[3] = info.normal.x; out6[4] = info.normal.y;
+	out6[5] = info.alpha;
+	return s != NULL;
+}
+
+CPB_EXPORT int
+cpb_scene_bb_query(cpSpace *space, double l, double b, double r, double t, uint64_t group, uint32_t cat, uint32_t mask, int cap, double *out1)
+{
+	query_rows q = {out1, 1, cap, 0};
+	cpSpaceBBQuery(space, cpBBNew(l, b, r, t), cpShapeFilterNew((cpGroup)group, cat, mask), bb_cb, &q);
+	return finish_rows(&q);
+}
+
+/* per-shape queries on the shape with the given tag: out6 as above; returns distance hit flag */
+CPB_EXPORT int
+cpb_scene_shape_point_query(cpSpace *space, int tag, double x, double y, double *out6)
+{
+	find_shape f = {tag, NULL};
+	cpSpaceEachShape(space, find_shape_cb, &f);
+	if(!f.found) return -1;
+	cpPointQueryInfo info;
+	cpShapePointQuery(f.found, cpv(x, y), &info);
+	out6[0] = tag; out6[1] = info.point.x; out6[2] = info.point.y; out6[3] = info.distance; out6[4] = info.gradient.x; out6[5] = info.gradient.y;
+	return 1;
+}
+
+CPB_EXPORT int
+cpb_scene_shape_segment_query(cpSpace *space, int tag, double ax, double ay, double bx, double by, double radius, double *out6)
+{
+	find_shape f = {tag, NULL};
+	cpSpaceEachShape(space, find_shape_cb, &f);
+	if(!f.found) return -1;
+	cpSegmentQueryInfo info;
+	cpBool hit = cpShapeSegmentQuery(f.found, cpv(ax, ay), cpv(bx, by), radius, &info);
+	out6[0] = (hit ? tag : -1); out6[1] = info.point.x; out6[2] = info.point.y; out6[3] = info.normal.x; out6[4] = info.normal.y; out6[5] = info.alpha;
+	return hit;
+}
+
+/* cpSpaceShapeQuery with a probe that is NOT part of the space: kind 0 = circle(radius) at (x, y),
+ * 1 = fat segment from (x, y) to (x + w, y + h) with `radius`, 2 = box w x h with bevel `radius`, rotated by angle.
+ * Returns the hit count (rows sorted by tag); *any = the function's return value. */
+CPB_EXPORT int
+cpb_scene_shape_query(cpSpace *space, int kind, double x, double y, double angle, double w, double h, double radius, int cap, double *out14, int *any)
+{
+	cpBody *body = cpBodyNewKinematic();
+	cpBodySetPosition(body, cpv(x, y));
+	cpBodySetAngle(body, angle);
+	cpShape *probe = (kind == 0 ? cpCircleShapeNew(body, radius, cpvzero)
+	               : kind == 1 ? cpSegmentShapeNew(body, cpvzero, cpv(w, h), radius)
+	                           : cpBoxShapeNew(body, w, h, radius));
+	query_rows q = {out14, 14, cap, 0};
+	cpBool r = cpSpaceShapeQuery(space, probe, shape_cb, &q);
+	if(any) *any = r;
+	cpShapeFree(probe);
+	cpBodyFree(body);
+	return finish_rows(&q);
+}

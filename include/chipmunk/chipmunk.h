@@ -351,6 +351,11 @@ CP_EXPORT void cpShapeFree(cpShape *shape);
 CP_EXPORT cpBB cpShapeCacheBB(cpShape *shape);
 CP_EXPORT cpBB cpShapeUpdate(cpShape *shape, cpTransform transform);
 CP_EXPORT cpContactPointSet cpShapesCollide(const cpShape *a, const cpShape *b);
+/* nearest-point / segment queries on one shape (reference cpShape.h:27-49, 88-97) */
+typedef struct cpPointQueryInfo { const cpShape *shape; cpVect point; cpFloat distance; cpVect gradient; } cpPointQueryInfo;
+typedef struct cpSegmentQueryInfo { const cpShape *shape; cpVect point; cpVect normal; cpFloat alpha; } cpSegmentQueryInfo;
+CP_EXPORT cpFloat cpShapePointQuery(const cpShape *shape, cpVect p, cpPointQueryInfo *out);
+CP_EXPORT cpBool cpShapeSegmentQuery(const cpShape *shape, cpVect a, cpVect b, cpFloat radius, cpSegmentQueryInfo *info);
 CP_EXPORT cpSpace *cpShapeGetSpace(const cpShape *shape);
 CP_EXPORT cpBody *cpShapeGetBody(const cpShape *shape);
 CP_EXPORT void cpShapeSetBody(cpShape *shape, cpBody *body);
@@ -581,6 +586,17 @@ CP_EXPORT cpBool cpSpaceAddPostStepCallback(cpSpace *space, cpPostStepFunc func,
 CP_EXPORT void cpSpaceEachBody(cpSpace *space, cpSpaceBodyIteratorFunc func, void *data);
 CP_EXPORT void cpSpaceEachShape(cpSpace *space, cpSpaceShapeIteratorFunc func, void *data);
 CP_EXPORT void cpSpaceEachConstraint(cpSpace *space, cpSpaceConstraintIteratorFunc func, void *data);
+/* space queries (reference cpSpace.h:191-222, cpSpaceQuery.c): run as data-parallel scans on the device */
+typedef void (*cpSpacePointQueryFunc)(cpShape *shape, cpVect point, cpFloat distance, cpVect gradient, void *data);
+typedef void (*cpSpaceSegmentQueryFunc)(cpShape *shape, cpVect point, cpVect normal, cpFloat alpha, void *data);
+typedef void (*cpSpaceBBQueryFunc)(cpShape *shape, void *data);
+typedef void (*cpSpaceShapeQueryFunc)(cpShape *shape, cpContactPointSet *points, void *data);
+CP_EXPORT void cpSpacePointQuery(cpSpace *space, cpVect point, cpFloat maxDistance, cpShapeFilter filter, cpSpacePointQueryFunc func, void *data);
+CP_EXPORT cpShape *cpSpacePointQueryNearest(cpSpace *space, cpVect point, cpFloat maxDistance, cpShapeFilter filter, cpPointQueryInfo *out);
+CP_EXPORT void cpSpaceSegmentQuery(cpSpace *space, cpVect start, cpVect end, cpFloat radius, cpShapeFilter filter, cpSpaceSegmentQueryFunc func, void *data);
+CP_EXPORT cpShape *cpSpaceSegmentQueryFirst(cpSpace *space, cpVect start, cpVect end, cpFloat radius, cpShapeFilter filter, cpSegmentQueryInfo *out);
+CP_EXPORT void cpSpaceBBQuery(cpSpace *space, cpBB bb, cpShapeFilter filter, cpSpaceBBQueryFunc func, void *data);
+CP_EXPORT cpBool cpSpaceShapeQuery(cpSpace *space, cpShape *shape, cpSpaceShapeQueryFunc func, void *data);
 CP_EXPORT void cpSpaceReindexStatic(cpSpace *space);
 CP_EXPORT void cpSpaceReindexShape(cpSpace *space, cpShape *shape);
 CP_EXPORT void cpSpaceReindexShapesForBody(cpSpace *space, cpBody *body);

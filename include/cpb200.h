@@ -239,6 +239,42 @@ CPB200_API int cpb200_world_set_joint_order(cpb200_world *w, int n, const int32_
 /* Run only the narrowphase on one uploaded shape pair with current world caches
  * (cpShapesCollide, cpShape.c:259-283): out = count n.x n.y (pA.xy pB.xy dist) x2. */
 CPB200_API int cpb200_world_collide_pair(cpb200_world *w, int shape_a, int shape_b, double *out13);
+/* ---- space queries (cpSpaceQuery.c:24-246) against the world cache of the last step ---------------------
+ * One data-parallel scan over all shapes per query (filter reject -> AABB reject -> exact per-shape test of
+ * cpShape.c:298-455 / cpPolyShape.c:66-145).  `space` restricts a batched world to one space (-1 = all).
+ * All functions return the number of hits found (which may exceed `cap`; only the first `cap` records, in
+ * ascending shape index, are written) or -1 on error. */
+typedef struct cpb200_filter { uint64_t group; uint32_t categories, mask; } cpb200_filter;
+/* point query: d = signed distance, g = gradient | segment query: d = alpha in [0,1], g = surface normal */
+typedef struct cpb200_query_hit { int32_t shape; int32_t pad; double point[2]; double d; double g[2]; } cpb200_query_hit;
+/* cpSpacePointQuery (cpSpaceQuery.c:33-59): every shape with distance < max_distance, sensors included. */
+CPB200_API int cpb200_world_point_query(cpb200_world *w, int space, const double point[2], double max_distance, const cpb200_filter *filter, int cap, cpb200_query_hit *out);
+/* cpSpacePointQueryNearest (cpSpaceQuery.c:61-101): the closest non-sensor shape; returns 0 or 1. */
+CPB200_API int cpb200_world_point_query_nearest(cpb200_world *w, int space, const double point[2], double max_distance, const cpb200_filter *filter, cpb200_query_hit *out);
+/* cpSpaceSegmentQuery (cpSpaceQuery.c:113-147): every shape the swept circle of `radius` hits, sensors included. */
+CPB200_API int cpb200_world_segment_query(cpb200_world *w, int space, const double a[2], const double b[2], double radius, const cpb200_filter *filter, int cap, cpb200_query_hit *out);
+/* cpSpaceSegmentQueryFirst (cpSpaceQuery.c:149-188): the first non-sensor hit with alpha < 1; returns 0 or 1. */
+CPB200_API int cpb200_world_segment_query_first(cpb200_world *w, int space, const double a[2], const double b[2], double radius, const cpb200_filter *filter, cpb200_query_hit *out);
+/* cpSpaceBBQuery (cpSpaceQuery.c:190-221): shapes whose cached AABB intersects bb = (l, b, r, t). */
+CPB200_API int cpb200_world_bb_query(cpb200_world *w, int space, const double bb[4], const cpb200_filter *filter, int cap, int32_t *shapes);
+/* cpShapePointQuery / cpShapeSegmentQuery (cpShape.c:223-258) on one uploaded shape: no filter, no range. */
+CPB200_API int cpb200_world_shape_point_query(cpb200_world *w, int shape, const double point[2], cpb200_query_hit *out);
+CPB200_API int cpb200_world_shape_segment_query(cpb200_world *w, int shape, const double a[2], const double b[2], double radius, cpb200_query_hit *out);
+/* cpSpaceShapeQuery (cpSpaceQuery.c:223-246): narrowphase of a caller-supplied shape, given in world space as
+ * cacheData would leave it, against every shape whose AABB it overlaps.  `self` = its index if it is part of
+ * the world (never reported), else -1.  Polygon: verts_normals = count x (v.x v.y n.x n.y), world space. */
+typedef struct cpb200_query_shape {
+	int32_t type, count, self, pad;
+	double r;
+	double a[2], b[2], n[2];         /* circle: a = centre | segment: a, b, n */
+	double rot[2];                   /* owning body's rotation */
+	double a_tangent[2], b_tangent[2];
+	double bb[4];
+	cpb200_filter filter;
+} cpb200_query_shape;
+typedef struct cpb200_shape_hit { int32_t shape, count; double normal[2]; double points[2][5]; /* pointA.xy pointB.xy distance */ } cpb200_shape_hit;
+CPB200_API int cpb200_world_shape_query(cpb200_world *w, int space, const cpb200_query_shape *q, const double *verts_normals, int cap, cpb200_shape_hit *out);
+
 /* Per-stage device time of the last step in microseconds (CUDA events), names via
  * cpb200_stage_name(i).  Returns the number of stages. */
 CPB200_API int cpb200_world_get_stage_times(cpb200_world *w, int cap, float *usec);

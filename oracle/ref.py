@@ -53,6 +53,23 @@ def bind_scene_api(lib):
     lib.cpb_scene_shapes_collide.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
     lib.cpb_scene_e2e_steps.restype = C.c_double
     lib.cpb_scene_e2e_steps.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, _dp, C.c_double, C.c_double, C.c_int]
+    d, vp, ci, u64, u32 = C.c_double, C.c_void_p, C.c_int, C.c_uint64, C.c_uint32
+    lib.cpb_scene_point_query.restype = ci
+    lib.cpb_scene_point_query.argtypes = [vp, d, d, d, u64, u32, u32, ci, _dp]
+    lib.cpb_scene_point_query_nearest.restype = ci
+    lib.cpb_scene_point_query_nearest.argtypes = [vp, d, d, d, u64, u32, u32, _dp]
+    lib.cpb_scene_segment_query.restype = ci
+    lib.cpb_scene_segment_query.argtypes = [vp, d, d, d, d, d, u64, u32, u32, ci, _dp]
+    lib.cpb_scene_segment_query_first.restype = ci
+    lib.cpb_scene_segment_query_first.argtypes = [vp, d, d, d, d, d, u64, u32, u32, _dp]
+    lib.cpb_scene_bb_query.restype = ci
+    lib.cpb_scene_bb_query.argtypes = [vp, d, d, d, d, u64, u32, u32, ci, _dp]
+    lib.cpb_scene_shape_point_query.restype = ci
+    lib.cpb_scene_shape_point_query.argtypes = [vp, ci, d, d, _dp]
+    lib.cpb_scene_shape_segment_query.restype = ci
+    lib.cpb_scene_shape_segment_query.argtypes = [vp, ci, d, d, d, d, d, _dp]
+    lib.cpb_scene_shape_query.restype = ci
+    lib.cpb_scene_shape_query.argtypes = [vp, ci, d, d, d, d, d, d, ci, _dp, C.POINTER(ci)]
     return lib
 
 
@@ -104,6 +121,51 @@ class SceneSpace:
         out = np.zeros(13)
         n = self.lib.cpb_scene_shapes_collide(self.space, ia, ib, _p(out))
         return n, out
+
+    # -- space queries (public cpSpace*Query API); filter = (group, categories, mask)
+    ALL = (0, 0xffffffff, 0xffffffff)
+
+    def _rows(self, call, stride, cap=256):
+        while True:
+            out = np.zeros((cap, stride))
+            n = call(cap, _p(out))
+            if n <= cap:
+                return out[:n]
+            cap = n
+
+    def point_query(self, p, max_dist, filt=ALL):
+        return self._rows(lambda cap, o: self.lib.cpb_scene_point_query(self.space, p[0], p[1], max_dist, filt[0], filt[1], filt[2], cap, o), 6)
+
+    def point_query_nearest(self, p, max_dist, filt=ALL):
+        out = np.zeros(6)
+        hit = self.lib.cpb_scene_point_query_nearest(self.space, p[0], p[1], max_dist, filt[0], filt[1], filt[2], _p(out))
+        return bool(hit), out
+
+    def segment_query(self, a, b, radius=0.0, filt=ALL):
+        return self._rows(lambda cap, o: self.lib.cpb_scene_segment_query(self.space, a[0], a[1], b[0], b[1], radius, filt[0], filt[1], filt[2], cap, o), 6)
+
+    def segment_query_first(self, a, b, radius=0.0, filt=ALL):
+        out = np.zeros(6)
+        hit = self.lib.cpb_scene_segment_query_first(self.space, a[0], a[1], b[0], b[1], radius, filt[0], filt[1], filt[2], _p(out))
+        return bool(hit), out
+
+    def bb_query(self, bb, filt=ALL):
+        return self._rows(lambda cap, o: self.lib.cpb_scene_bb_query(self.space, bb[0], bb[1], bb[2], bb[3], filt[0], filt[1], filt[2], cap, o), 1)[:, 0].astype(int)
+
+    def shape_point_query(self, tag, p):
+        out = np.zeros(6)
+        rc = self.lib.cpb_scene_shape_point_query(self.space, tag, p[0], p[1], _p(out))
+        return rc, out
+
+    def shape_segment_query(self, tag, a, b, radius=0.0):
+        out = np.zeros(6)
+        rc = self.lib.cpb_scene_shape_segment_query(self.space, tag, a[0], a[1], b[0], b[1], radius, _p(out))
+        return rc, out
+
+    def shape_query(self, kind, pos, angle=0.0, w=0.0, h=0.0, radius=0.0):
+        any_ = C.c_int(0)
+        rows = self._rows(lambda cap, o: self.lib.cpb_scene_shape_query(self.space, kind, pos[0], pos[1], angle, w, h, radius, cap, o, C.byref(any_)), 14)
+        return rows, bool(any_.value)
 
     def free(self):
         if self.space:

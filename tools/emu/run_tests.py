@@ -11,4 +11,7 @@ sys.path.insert(0, ROOT)
 import chipmunk2d_b200.engine as engine  # noqa: E402
 
 engine.ENGINE_LIB = os.path.join(ROOT, "tools/emu/_build/libcpb200_emu.so")
+import chipmunk2d_b200.api as api  # noqa: E402
+
+api.SCENE_LIB = os.path.join(ROOT, "tools/emu/_build/libscene_b200_emu.so")
 sys.exit(pytest.main(["-x", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + (sys.argv[1:] or [os.path.join(ROOT, "tests")])))
