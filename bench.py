@@ -168,6 +168,8 @@ def run_ours(args):
     from oracle.ref import SceneSpace
 
     os.environ["CPB200_DEVICE"] = str(local_rank)   # spaces created through the C API follow the rank's GPU
+    # the host layer threads its mirror loops: share the host cores between the ranks of this node
+    os.environ.setdefault("CPB200_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, world))))
     scenes, cfg = build_scenes(args.workload, rank)
     dt = scenes[0].dt
     nb = sum(sc.n_dynamic() for sc in scenes)

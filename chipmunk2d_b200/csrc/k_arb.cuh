@@ -156,7 +156,9 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 		bool both_inf = (B.type[ba] != CPB200_BODY_DYNAMIC) && (B.type[bb] != CPB200_BODY_DYNAMIC);
 		bool active = (state != CPB200_ARB_IGNORE) && !sensor && !both_inf;
 		cur.active[slot] = active ? 1 : 0;
-		if(!active && state != CPB200_ARB_IGNORE) state = CPB200_ARB_NORMAL; // cpSpaceStep.c:283
+		// a rejected first contact still shows FIRST_COLLISION to the begin handler; k_arb_prestep downgrades it
+		// to NORMAL afterwards (cpSpaceStep.c:283)
+		if(!active && state != CPB200_ARB_IGNORE && state != CPB200_ARB_FIRST_COLLISION) state = CPB200_ARB_NORMAL;
 		cur.state[slot] = state;
 #ifndef CPB_EMU
 		{
@@ -252,7 +254,10 @@ __global__ void k_arb_prestep(DBodies B, DArbs A, const DSpace *__restrict__ spa
 {
 	int n = *A.count_ptr; if(n > A.cap) n = A.cap;
 	for(int i = CPB_TID; i < n; i += CPB_NTHREADS){
-	if(A.active[i] != 1) continue;
+	if(A.active[i] != 1){
+		if(A.active[i] == 0 && A.state[i] == CPB200_ARB_FIRST_COLLISION) A.state[i] = CPB200_ARB_NORMAL;   // cpSpaceStep.c:283
+		continue;
+	}
 	int ba = A.ba[i], bb = A.bb[i];
 	DSpace sp = spaces[B.space[ba]];
 	V2 n_ = A.n[i];

@@ -133,6 +133,8 @@ struct cpb200_world {
 
 	void *d_stage; size_t stage_bytes;   // device staging for host <-> SoA conversion kernels
 	unsigned *d_barrier;    // grid barrier words of the persistent solver
+	bool mid_step;          // between cpb200_world_step_collide and cpb200_world_step_finish
+	double step_dt, step_dt_coef; int step_iterations;
 	bool hints_valid;       // last step's colours may seed this step's colouring
 	bool no_hints;          // validation hook (env CPB200_NO_HINTS): colour from scratch every step
 	int wl_cap; AllocGroup gW;
@@ -262,6 +264,7 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	cudaMalloc(&p, sizeof(unsigned)*8); w->d_barrier = (unsigned *)p; cudaMemsetAsync(w->d_barrier, 0, sizeof(unsigned)*8, w->stream);
 	w->no_hints = (getenv("CPB200_NO_HINTS") != NULL);
 	w->d_query = NULL; w->query_bytes = 0;
+	w->mid_step = false; w->step_dt = 0.0; w->step_dt_coef = 0.0; w->step_iterations = 0;
 	w->sl_dirty = true; w->sl_ok = false; w->sl_disabled = (getenv("CPB200_NO_SPACE_LOCAL") != NULL); w->sl_max_nbody = 0;
 	memset(&w->SL, 0, sizeof(w->SL)); w->sl_tmp = NULL;
 	w->last_active = 0; w->force_blocks = 0; w->hints_valid = false; w->wl_cap = 0; w->d_stage = NULL; w->stage_bytes = 0;
@@ -763,10 +766,12 @@ static int sl_refresh(cpb200_world *w)
 	return 0;
 }
 
-extern "C" int cpb200_world_step(cpb200_world *w, double dt)
+// The step in two halves.  Phase A: positions, shape cache, broadphase, narrowphase + arbiter update (everything
+// up to the point where the reference calls the begin/preSolve collision handlers, cpSpaceStep.c:234-290).
+// Phase B: islands, cache ageing, prestep, velocities, solver.  cpb200_world_step runs both back to back;
+// the host layer of a space WITH collision handlers calls them separately and edits arbiters in between.
+static int step_phase_a(cpb200_world *w, double dt)
 {
-	if(!w){ cpb_set_error("null world"); return -1; }
-	if(dt == 0.0) return 0; // cpSpaceStep.c:339
 	cudaSetDevice(w->device);
 	cudaStream_t st = w->stream;
 	DBodies &B = w->B; DShapes &S = w->S; DJoints &J = w->J;
@@ -836,6 +841,25 @@ extern "C" int cpb200_world_step(cpb200_world *w, double dt)
 		LAUNCH(k_collide<2>, g, 128, st, S, B, (const int *)w->P.a[2], (const int *)w->P.b[2], (const int *)&w->P.count[2], w->P.cap, Ap, Tp, Ac, Tc, w->stamp, w->C);
 	}
 	STAGE_END(w, ST_COLLIDE);
+	w->step_dt = dt; w->step_dt_coef = dt_coef; w->step_iterations = iterations;
+	w->mid_step = true;
+	return 0;
+}
+
+static int step_phase_b(cpb200_world *w)
+{
+	cudaSetDevice(w->device);
+	cudaStream_t st = w->stream;
+	DBodies &B = w->B; DShapes &S = w->S; DJoints &J = w->J;
+	(void)S; (void)J;
+	double dt = w->step_dt, dt_coef = w->step_dt_coef;
+	int iterations = w->step_iterations;
+	const int prv = w->cur ^ 1;
+	DArbs &Ap = w->A[prv]; DArbs &Ac = w->A[w->cur];
+	DTable &Tc = w->T[w->cur];
+	const int nb = B.n;
+	const int wide = w->sm_count*8;
+	w->mid_step = false;
 
 	// K7: islands / sleeping (cpSpaceProcessComponents) -- before the cache filter, like the reference
 	if(w->any_sleep_enabled){
@@ -948,6 +972,71 @@ extern "C" int cpb200_world_step(cpb200_world *w, double dt)
 	return 0;
 }
 
+extern "C" int cpb200_world_step(cpb200_world *w, double dt)
+{
+	if(!w){ cpb_set_error("null world"); return -1; }
+	if(dt == 0.0) return 0; // cpSpaceStep.c:339
+	if(w->mid_step){ cpb_set_error("cpb200_world_step while a split step is open (call cpb200_world_step_finish)"); return -1; }
+	if(step_phase_a(w, dt)) return -1;
+	return step_phase_b(w);
+}
+
+extern "C" int cpb200_world_step_collide(cpb200_world *w, double dt)
+{
+	if(!w){ cpb_set_error("null world"); return -1; }
+	if(dt == 0.0){ cpb_set_error("split step with dt == 0"); return -1; }
+	if(w->mid_step){ cpb_set_error("a split step is already open"); return -1; }
+	return step_phase_a(w, dt);
+}
+
+extern "C" int cpb200_world_step_finish(cpb200_world *w)
+{
+	if(!w){ cpb_set_error("null world"); return -1; }
+	if(!w->mid_step){ cpb_set_error("cpb200_world_step_finish without cpb200_world_step_collide"); return -1; }
+	return step_phase_b(w);
+}
+
+// Host decisions of the begin/preSolve handlers applied to this step's records (cpSpaceStep.c:257-285,
+// cpArbiter.c:46-50, 97-143).
+__global__ void k_arb_edit(DArbs A, DCounters *C, const cpb200_arbiter_edit *edits, int n)
+{
+	int e = CPB_TID;
+	if(e >= n) return;
+	cpb200_arbiter_edit ed = edits[e];
+	int i = ed.record;
+	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
+	if(i < 0 || i >= nA) return;
+	if(ed.flags & CPB200_EDIT_MATERIAL){ A.e[i] = ed.e; A.u[i] = ed.u; A.svr[i] = make_double2(ed.surface_vr[0], ed.surface_vr[1]); }
+	if(ed.flags & CPB200_EDIT_CONTACTS){
+		A.n[i] = make_double2(ed.n[0], ed.n[1]);
+		for(int k = 0; k < A.cnt[i] && k < 2; k++){
+			A.r1[CIDX(A, i, k)] = make_double2(ed.r1[k][0], ed.r1[k][1]);
+			A.r2[CIDX(A, i, k)] = make_double2(ed.r2[k][0], ed.r2[k][1]);
+		}
+	}
+	if(ed.flags & (CPB200_EDIT_IGNORE | CPB200_EDIT_REJECT)){
+		if(A.active[i] == 1){ atomicAdd(&C->n_active, -1); atomicAdd(&C->n_contacts, -A.cnt[i]); }
+		A.active[i] = 0;
+		// the reference drops the contacts of a rejected arbiter (arb->count = 0): nothing to warm start from
+		A.cnt[i] = 0;
+		if(ed.flags & CPB200_EDIT_IGNORE) A.state[i] = CPB200_ARB_IGNORE;
+		else if(A.state[i] != CPB200_ARB_IGNORE) A.state[i] = CPB200_ARB_NORMAL;
+	}
+}
+
+extern "C" int cpb200_world_edit_arbiters(cpb200_world *w, int n, const cpb200_arbiter_edit *edits)
+{
+	if(!w || n < 0 || (n > 0 && !edits)){ cpb_set_error("bad arguments"); return -1; }
+	if(!w->mid_step){ cpb_set_error("arbiters can only be edited between cpb200_world_step_collide and cpb200_world_step_finish"); return -1; }
+	if(n == 0) return 0;
+	cudaSetDevice(w->device);
+	size_t bytes = sizeof(cpb200_arbiter_edit)*(size_t)n;
+	if(stage_reserve(w, bytes)) return -1;
+	CPB_CHECK(cudaMemcpyAsync(w->d_stage, edits, bytes, cudaMemcpyHostToDevice, w->stream));
+	LAUNCH(k_arb_edit, grid_for(n, 128), 128, w->stream, w->A[w->cur], w->C, (const cpb200_arbiter_edit *)w->d_stage, n);
+	return world_sync(w);
+}
+
 extern "C" unsigned long long cpb200_launch_count(void)
 {
 #ifdef CPB_EMU
@@ -1051,7 +1140,7 @@ extern "C" int cpb200_world_get_arbiters(cpb200_world *w, int cap, cpb200_arbite
 			cpb200_arbiter &o = out[m];
 			memset(&o, 0, sizeof(o));
 			o.shape_a = sa[i]; o.shape_b = sb[i]; o.body_a = ba[i]; o.body_b = bb[i];
-			o.count = (active[i] ? cnt[i] : 0); o.state = state[i]; o.stamp = stamp[i]; o.active = active[i];
+			o.count = (active[i] || w->mid_step ? cnt[i] : 0); o.state = state[i]; o.stamp = stamp[i]; o.active = active[i]; o.record = (int32_t)i;
 			o.n[0] = nn[i].x; o.n[1] = nn[i].y; o.e = e[i]; o.u = u[i]; o.surface_vr[0] = svr[i].x; o.surface_vr[1] = svr[i].y;
 			for(int k = 0; k < 2; k++){
 				size_t c = (size_t)k*N + i;

@@ -61,7 +61,7 @@ CONTACT = np.dtype([
     ("jn_acc", "<f8"), ("jt_acc", "<f8"), ("j_bias", "<f8"), ("hash", "<u8")], align=True)
 ARBITER = np.dtype([
     ("shape_a", "<i4"), ("shape_b", "<i4"), ("body_a", "<i4"), ("body_b", "<i4"), ("count", "<i4"), ("state", "<i4"),
-    ("stamp", "<u4"), ("active", "<i4"), ("n", "<f8", 2), ("e", "<f8"), ("u", "<f8"), ("surface_vr", "<f8", 2),
+    ("stamp", "<u4"), ("active", "<i4"), ("record", "<i4"), ("pad", "<i4"), ("n", "<f8", 2), ("e", "<f8"), ("u", "<f8"), ("surface_vr", "<f8", 2),
     ("contacts", CONTACT, 2)], align=True)
 JOINT_STATE = np.dtype([("acc", "<f8", 2), ("impulse", "<f8"), ("aux", "<f8")], align=True)
 STATS = np.dtype([

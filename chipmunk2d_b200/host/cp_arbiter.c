@@ -3,8 +3,9 @@
  *
  * A cpArbiter* handed out by cpBodyEachArbiter or a collision handler is valid until the next
  * cpSpaceStep, like the reference's (cpSpaceStep.c:187-202).  Setters that change the outcome of
- * the solve (cpArbiterSet*, cpArbiterIgnore) only make sense inside begin/preSolve callbacks, which
- * on this build run after the step (observational slow path); they update the mirror only.
+ * the solve (cpArbiterSet*, cpArbiterIgnore) only make sense inside begin/preSolve callbacks; those run
+ * between the two halves of a split device step (cp_space.c: run_begin_presolve_callbacks), where the
+ * changes made to the mirror are diffed and sent to the device before the solver runs.
  */
 #include "cp_host.h"
 

@@ -27,7 +27,7 @@ joint_init(cpConstraint *c, int klass, cpBody *a, cpBody *b)
 	c->next_a = NULL;
 	c->next_b = NULL;
 	c->maxForce = (cpFloat)INFINITY;
-	c->errorBias = cpfpow(1.0 - 0.1, 60.0);
+	c->errorBias = cpfpow((cpFloat)(1.0f - 0.1f), 60.0);   /* float literals in the reference (cpConstraint.c:50) */
 	c->maxBias = (cpFloat)INFINITY;
 	c->collideBodies = cpTrue;
 	c->preSolve = NULL;

@@ -112,6 +112,7 @@ struct cpArbiter {
 	int state;
 	int active;
 	int next_a, next_b;        /* per-body lists (indices into space->arbs) */
+	int record;                /* device record (edits between the two halves of a step) */
 };
 
 typedef struct cpPostStepCallback { cpPostStepFunc func; void *key; void *data; } cpPostStepCallback;

@@ -14,6 +14,7 @@
 
 #include "cp_host.h"
 #include <omp.h>
+#include <stdlib.h>
 
 static int g_default_device = -1;
 
@@ -52,8 +53,10 @@ cpSpaceInit(cpSpace *space)
 	space->iterations = 10;
 	space->gravity = cpvzero;
 	space->damping = 1.0;
-	space->collisionSlop = 0.1;
-	space->collisionBias = cpfpow(1.0 - 0.1, 60.0);
+	/* the reference spells these defaults with float literals (cpSpace.c:136-137): the values are the
+	 * float-rounded ones, 0.100000001490116 and 0.899999976158142^60 */
+	space->collisionSlop = (cpFloat)0.1f;
+	space->collisionBias = cpfpow((cpFloat)(1.0f - 0.1f), 60.0);
 	space->collisionPersistence = 3;
 	space->idleSpeedThreshold = 0.0;
 	space->sleepTimeThreshold = INFINITY;
@@ -119,6 +122,26 @@ void cpSpaceMarkTopologyDirty(cpSpace *space){ space->topologyDirty = cpTrue; }
 void cpSpaceSetSolverModeB200(cpSpace *space, int mode){ space->solverMode = mode; space->paramsDirty = cpTrue; }
 
 /* ---- collision handlers (cpSpace.c:383-413) ---- */
+/* DefaultBegin .. DefaultSeparate (cpSpace.c:63-90): dispatch to the wildcard handlers of both shapes */
+static cpBool default_begin(cpArbiter *arb, cpSpace *space, cpDataPointer data){
+	cpBool retA = cpArbiterCallWildcardBeginA(arb, space);
+	cpBool retB = cpArbiterCallWildcardBeginB(arb, space);
+	return retA && retB;
+}
+static cpBool default_presolve(cpArbiter *arb, cpSpace *space, cpDataPointer data){
+	cpBool retA = cpArbiterCallWildcardPreSolveA(arb, space);
+	cpBool retB = cpArbiterCallWildcardPreSolveB(arb, space);
+	return retA && retB;
+}
+static void default_postsolve(cpArbiter *arb, cpSpace *space, cpDataPointer data){
+	cpArbiterCallWildcardPostSolveA(arb, space);
+	cpArbiterCallWildcardPostSolveB(arb, space);
+}
+static void default_separate(cpArbiter *arb, cpSpace *space, cpDataPointer data){
+	cpArbiterCallWildcardSeparateA(arb, space);
+	cpArbiterCallWildcardSeparateB(arb, space);
+}
+
 static cpCollisionHandler *
 add_handler(cpSpace *space, cpCollisionType a, cpCollisionType b)
 {
@@ -128,15 +151,30 @@ add_handler(cpSpace *space, cpCollisionType a, cpCollisionType b)
 	}
 	cpAssertHard(space->nHandlers < 256, "Too many collision handlers (the handler table is fixed so that returned pointers stay valid).");
 	if(!space->handlers){ space->handlers = (cpCollisionHandler *)cpcalloc(256, sizeof(cpCollisionHandler)); space->capHandlers = 256; }
-	cpCollisionHandler init = {a, b, handler_true, handler_true, handler_nothing, handler_nothing, NULL};
-	memcpy(&space->handlers[space->nHandlers], &init, sizeof(init));
+	/* a pair handler's unset callbacks fall through to the wildcard handlers of both types
+	 * (cpSpace.c:398-403); a wildcard handler's own defaults accept everything (cpSpace.c:405-413) */
+	cpCollisionHandler pair = {a, b, default_begin, default_presolve, default_postsolve, default_separate, NULL};
+	cpCollisionHandler wild = {a, b, handler_true, handler_true, handler_nothing, handler_nothing, NULL};
+	memcpy(&space->handlers[space->nHandlers], (b == CP_WILDCARD_COLLISION_TYPE ? &wild : &pair), sizeof(pair));
 	return &space->handlers[space->nHandlers++];
+}
+
+/* cpSpaceUseWildcardDefaultHandler (cpSpace.c:382-390) */
+static void
+use_wildcard_default_handler(cpSpace *space)
+{
+	if(!space->usesWildcards){
+		space->usesWildcards = cpTrue;
+		cpCollisionHandler def = {CP_WILDCARD_COLLISION_TYPE, CP_WILDCARD_COLLISION_TYPE, default_begin, default_presolve, default_postsolve, default_separate, NULL};
+		memcpy(&space->defaultHandler, &def, sizeof(def));
+	}
+	space->hasDefaultHandler = cpTrue;   /* every pair may now reach a user callback */
 }
 
 cpCollisionHandler *
 cpSpaceAddDefaultCollisionHandler(cpSpace *space)
 {
-	space->hasDefaultHandler = cpTrue;
+	use_wildcard_default_handler(space);
 	return &space->defaultHandler;
 }
 
@@ -145,7 +183,7 @@ cpCollisionHandler *cpSpaceAddCollisionHandler(cpSpace *space, cpCollisionType a
 cpCollisionHandler *
 cpSpaceAddWildcardHandler(cpSpace *space, cpCollisionType type)
 {
-	space->usesWildcards = cpTrue;
+	use_wildcard_default_handler(space);
 	return add_handler(space, type, CP_WILDCARD_COLLISION_TYPE);
 }
 
@@ -419,6 +457,9 @@ host_threads(const cpSpace *space, int n)
 	if(n < CP_PARALLEL_MIN_BODIES) return 1;
 	int t = omp_get_num_procs();
 	if(t > 16) t = 16;
+	/* several processes on one host (one per GPU) share the cores: CPB200_HOST_THREADS caps the team */
+	const char *cap = getenv("CPB200_HOST_THREADS");
+	if(cap && atoi(cap) > 0 && atoi(cap) < t) t = atoi(cap);
 	if(space->hasty && space->hastyThreads > 0 && (int)space->hastyThreads < t) t = (int)space->hastyThreads;
 	return (t < 1 ? 1 : t);
 }
@@ -635,6 +676,7 @@ cpSpaceFetchArbitersB200(cpSpace *space)
 		arb->state = r->state;
 		arb->stamp = r->stamp;
 		arb->active = r->active;
+		arb->record = r->record;
 		for(int k = 0; k < 2; k++){
 			struct cpContact *c = &arb->contacts[k];
 			c->r1 = cpv(r->contacts[k].r1[0], r->contacts[k].r1[1]);
@@ -683,22 +725,59 @@ space_has_collision_callbacks(const cpSpace *space)
 	return (space->nHandlers > 0 || space->hasDefaultHandler);
 }
 
+/* Between the two halves of the step (the point where the reference runs them, cpSpaceStep.c:257-285): the
+ * device has produced this step's arbiters; begin/preSolve decide which of them are solved and may change
+ * their material or contacts.  The decisions go back as a list of edits. */
 static void
-run_collision_callbacks(cpSpace *space)
+run_begin_presolve_callbacks(cpSpace *space)
+{
+	cpSpaceFetchArbitersB200(space);
+	int nEdits = 0;
+	cpb200_arbiter_edit *edits = (cpb200_arbiter_edit *)cpcalloc((size_t)(space->nArbs > 0 ? space->nArbs : 1), sizeof(cpb200_arbiter_edit));
+	for(int i = 0; i < space->nArbs; i++){
+		cpArbiter *arb = &space->arbs[i];
+		cpCollisionHandler *h = arb->handler;
+		if(arb->stamp != space->stamp) continue;
+		const cpArbiter before = *arb;
+		uint32_t flags = 0;
+		if(arb->state == CP_ARBITER_STATE_FIRST_COLLISION && !h->beginFunc(arb, space, h->userData)) cpArbiterIgnore(arb);
+		if(arb->state != CP_ARBITER_STATE_IGNORE && !h->preSolveFunc(arb, space, h->userData)) flags |= CPB200_EDIT_REJECT;
+		if(arb->state == CP_ARBITER_STATE_IGNORE && before.state != CP_ARBITER_STATE_IGNORE) flags |= CPB200_EDIT_IGNORE;
+		if(arb->e != before.e || arb->u != before.u || !cpveql(arb->surface_vr, before.surface_vr)) flags |= CPB200_EDIT_MATERIAL;
+		if(!cpveql(arb->n, before.n)) flags |= CPB200_EDIT_CONTACTS;
+		for(int k = 0; k < arb->count && k < CP_MAX_CONTACTS_PER_ARBITER; k++){
+			if(!cpveql(arb->contacts[k].r1, before.contacts[k].r1) || !cpveql(arb->contacts[k].r2, before.contacts[k].r2)) flags |= CPB200_EDIT_CONTACTS;
+		}
+		if(!flags) continue;
+		cpb200_arbiter_edit *ed = &edits[nEdits++];
+		ed->record = arb->record; ed->flags = flags;
+		ed->e = arb->e; ed->u = arb->u; ed->surface_vr[0] = arb->surface_vr.x; ed->surface_vr[1] = arb->surface_vr.y;
+		ed->n[0] = arb->n.x; ed->n[1] = arb->n.y;
+		for(int k = 0; k < CP_MAX_CONTACTS_PER_ARBITER; k++){
+			ed->r1[k][0] = arb->contacts[k].r1.x; ed->r1[k][1] = arb->contacts[k].r1.y;
+			ed->r2[k][0] = arb->contacts[k].r2.x; ed->r2[k][1] = arb->contacts[k].r2.y;
+		}
+	}
+	if(cpb200_world_edit_arbiters(space->world, nEdits, edits)) cpEngineError("arbiter edits");
+	cpfree(edits);
+}
+
+/* After the solver: separate for the pairs that stopped touching this step (cpSpaceStep.c:309-314), then
+ * postSolve for everything that was solved (cpSpaceStep.c:438-443). */
+static void
+run_separate_postsolve_callbacks(cpSpace *space)
 {
 	cpSpaceFetchArbitersB200(space);
 	for(int i = 0; i < space->nArbs; i++){
 		cpArbiter *arb = &space->arbs[i];
 		cpCollisionHandler *h = arb->handler;
-		if(arb->state == CP_ARBITER_STATE_CACHED){
-			/* became cached this step <=> last touched on the previous stamp (cpSpaceStep.c:309-314) */
-			if(arb->stamp + 1 == space->stamp) h->separateFunc(arb, space, h->userData);
-			continue;
-		}
-		if(arb->stamp != space->stamp) continue;
-		if(arb->state == CP_ARBITER_STATE_FIRST_COLLISION) h->beginFunc(arb, space, h->userData);
-		h->preSolveFunc(arb, space, h->userData);
-		if(arb->active == 1) h->postSolveFunc(arb, space, h->userData);
+		/* became cached this step <=> last touched on the previous stamp */
+		if(arb->state == CP_ARBITER_STATE_CACHED && arb->stamp + 1 == space->stamp) h->separateFunc(arb, space, h->userData);
+	}
+	for(int i = 0; i < space->nArbs; i++){
+		cpArbiter *arb = &space->arbs[i];
+		cpCollisionHandler *h = arb->handler;
+		if(arb->state != CP_ARBITER_STATE_CACHED && arb->stamp == space->stamp && arb->active == 1) h->postSolveFunc(arb, space, h->userData);
 	}
 }
 
@@ -715,14 +794,27 @@ step_once(cpSpace *space, cpFloat dt, cpBool callbacks)
 		space->locked--;
 	}
 	sync_to_device(space);
-	if(cpb200_world_step(space->world, dt)) cpEngineError("cpSpaceStep");
-	space->stamp++;
-	space->curr_dt = dt;
+	const cpBool handlers = space_has_collision_callbacks(space);
+	if(handlers){
+		/* split step: the handlers' return values and edits take effect in THIS step, like the reference */
+		if(cpb200_world_step_collide(space->world, dt)) cpEngineError("cpSpaceStep (collision phase)");
+		space->stamp++;
+		space->curr_dt = dt;
+		space->hostStale = cpTrue; space->bbStale = cpTrue; space->arbStale = cpTrue;
+		space->locked++;
+		run_begin_presolve_callbacks(space);
+		space->locked--;
+		if(cpb200_world_step_finish(space->world)) cpEngineError("cpSpaceStep (solver phase)");
+	} else {
+		if(cpb200_world_step(space->world, dt)) cpEngineError("cpSpaceStep");
+		space->stamp++;
+		space->curr_dt = dt;
+	}
 	space->hostStale = cpTrue;
 	space->bbStale = cpTrue;
 	space->arbStale = cpTrue;
 	space->jointStale = cpTrue;
-	if(callbacks){
+	if(callbacks || handlers){
 		space->locked++;
 		cpBool any = cpFalse;
 		for(int i = 0; i < space->nConstraints; i++){ if(space->constraints[i]->postSolve){ any = cpTrue; break; } }
@@ -733,7 +825,7 @@ step_once(cpSpace *space, cpFloat dt, cpBool callbacks)
 				if(c->postSolve) c->postSolve(c, space);
 			}
 		}
-		if(space_has_collision_callbacks(space)) run_collision_callbacks(space);
+		if(handlers) run_separate_postsolve_callbacks(space);
 		space->locked--;
 		run_post_step_callbacks(space);
 	}

@@ -508,3 +508,80 @@ cpb_scene_shape_query(cpSpace *space, int kind, double x, double y, double angle
 	cpBodyFree(body);
 	return finish_rows(&q);
 }
+
+/* ---- collision-handler semantics (cpSpaceStep.c:257-285, cpArbiter.c:46-50, 97-143), same code against
+ * either library: one dynamic ball over static geometry, so the solver order cannot matter and the
+ * trajectories of the two libraries agree to rounding.
+ * out[12] = nBegin nPreSolve nPostSolve nSeparate  p.x p.y v.x v.y w  maxHeightAfterFirstContact  firstContactStep  spare */
+typedef struct hs_ctx { int which; int nBegin, nPre, nPost, nSep; int step, firstStep; } hs_ctx;
+static cpBool hs_begin(cpArbiter *arb, cpSpace *space, void *data){
+	hs_ctx *c = (hs_ctx *)data;
+	c->nBegin++;
+	if(c->firstStep < 0) c->firstStep = c->step;
+	if(c->which == 2) return cpFalse;                 /* ignored until the shapes separate */
+	return cpTrue;
+}
+static cpBool hs_presolve(cpArbiter *arb, cpSpace *space, void *data){
+	hs_ctx *c = (hs_ctx *)data;
+	c->nPre++;
+	switch(c->which){
+	case 1: return cpFalse;                            /* never solved: the ball falls through */
+	case 3: cpArbiterSetRestitution(arb, 1.0); break;  /* bouncy although both shapes have e = 0 */
+	case 4: cpArbiterSetSurfaceVelocity(arb, cpv(50.0, 0.0)); cpArbiterSetFriction(arb, 1.0); break;   /* conveyor */
+	case 6: if(cpArbiterGetNormal(arb).y > 0.0) return cpArbiterIgnore(arb); break;   /* one-way platform (demo/OneWay.c) */
+	case 7: if(c->nPre == 10) return cpArbiterIgnore(arb); break;
+	default: break;
+	}
+	return cpTrue;
+}
+static void hs_postsolve(cpArbiter *arb, cpSpace *space, void *data){ ((hs_ctx *)data)->nPost++; }
+static void hs_separate(cpArbiter *arb, cpSpace *space, void *data){ ((hs_ctx *)data)->nSep++; }
+
+CPB_EXPORT int
+cpb_scene_handler_scenario(int which, int n_steps, double *out12)
+{
+	cpSpace *space = cpSpaceNew();
+	cpSpaceSetIterations(space, 10);
+	cpSpaceSetGravity(space, cpv(0.0, -100.0));
+	cpSpaceSetCollisionSlop(space, 0.5);
+	cpBody *sb = cpSpaceGetStaticBody(space);
+	cpShape *ground = cpSpaceAddShape(space, cpSegmentShapeNew(sb, cpv(-400.0, 0.0), cpv(400.0, 0.0), 0.0));
+	cpShapeSetElasticity(ground, 0.0); cpShapeSetFriction(ground, (which == 4 ? 0.0 : 0.7));
+	cpShapeSetCollisionType(ground, 1);
+	if(which == 5) cpShapeSetSensor(ground, cpTrue);
+	cpShape *floor2 = NULL;
+	if(which == 6){
+		/* the platform is `ground`; a second floor far below catches nothing within the run */
+		floor2 = cpSpaceAddShape(space, cpSegmentShapeNew(sb, cpv(-400.0, -1000.0), cpv(400.0, -1000.0), 0.0));
+		cpShapeSetCollisionType(floor2, 3);
+	}
+	cpBody *ball = cpSpaceAddBody(space, cpBodyNew(1.0, cpMomentForCircle(1.0, 0.0, 10.0, cpvzero)));
+	cpShape *bs = cpSpaceAddShape(space, cpCircleShapeNew(ball, 10.0, cpvzero));
+	cpShapeSetElasticity(bs, 0.0); cpShapeSetFriction(bs, 0.7);
+	cpShapeSetCollisionType(bs, 2);
+	if(which == 6){ cpBodySetPosition(ball, cpv(0.0, -40.0)); cpBodySetVelocity(ball, cpv(0.0, 160.0)); }
+	else cpBodySetPosition(ball, cpv(0.0, 50.0));
+
+	hs_ctx ctx = {which, 0, 0, 0, 0, 0, -1};
+	cpCollisionHandler *h = (which == 8 ? cpSpaceAddWildcardHandler(space, 2)
+	                       : which == 9 ? cpSpaceAddDefaultCollisionHandler(space)
+	                                    : cpSpaceAddCollisionHandler(space, 1, 2));
+	h->beginFunc = hs_begin; h->preSolveFunc = hs_presolve; h->postSolveFunc = hs_postsolve; h->separateFunc = hs_separate;
+	h->userData = &ctx;
+
+	double maxh = -1e300;
+	for(int s = 0; s < n_steps; s++){
+		ctx.step = s;
+		cpSpaceStep(space, 1.0/60.0);
+		if(ctx.firstStep >= 0 && s > ctx.firstStep + 2){ double y = cpBodyGetPosition(ball).y; if(y > maxh) maxh = y; }
+	}
+	cpVect p = cpBodyGetPosition(ball), v = cpBodyGetVelocity(ball);
+	out12[0] = ctx.nBegin; out12[1] = ctx.nPre; out12[2] = ctx.nPost; out12[3] = ctx.nSep;
+	out12[4] = p.x; out12[5] = p.y; out12[6] = v.x; out12[7] = v.y; out12[8] = cpBodyGetAngularVelocity(ball);
+	out12[9] = (maxh > -1e299 ? maxh : 0.0); out12[10] = ctx.firstStep; out12[11] = 0.0;
+	cpSpaceRemoveShape(space, bs); cpSpaceRemoveBody(space, ball); cpSpaceRemoveShape(space, ground);
+	if(floor2){ cpSpaceRemoveShape(space, floor2); cpShapeFree(floor2); }
+	cpShapeFree(bs); cpBodyFree(ball); cpShapeFree(ground);
+	cpSpaceFree(space);
+	return 0;
+}

@@ -124,6 +124,7 @@ typedef struct cpb200_arbiter {
 	uint32_t stamp;
 	int32_t active;               /* 1 = solved this step (pushed to space->arbiters, cpSpaceStep.c:274); 2 = dormant: kept with
 	                               * its contacts while its bodies sleep (cpSpaceComponent.c:94-105); 0 = inactive */
+	int32_t record, pad;          /* index of the device record (cpb200_world_edit_arbiters) */
 	double n[2];
 	double e, u;
 	double surface_vr[2];
@@ -196,6 +197,22 @@ CPB200_API int cpb200_world_reserve(cpb200_world *w, int max_pairs, int max_arbi
 /* cpSpaceStep (cpSpaceStep.c:335-445) for every space of the world.  Asynchronous:
  * returns once the kernels are enqueued on the world's stream. */
 CPB200_API int cpb200_world_step(cpb200_world *w, double dt);
+/* The same step in two halves for spaces with collision handlers (cpSpaceStep.c:234-290): after
+ * cpb200_world_step_collide the records touched this step can be read with cpb200_world_get_arbiters, the
+ * handlers' decisions are written back with cpb200_world_edit_arbiters, cpb200_world_step_finish runs
+ * islands, cache ageing, prestep, velocity integration and the solver. */
+CPB200_API int cpb200_world_step_collide(cpb200_world *w, double dt);
+CPB200_API int cpb200_world_step_finish(cpb200_world *w);
+#define CPB200_EDIT_IGNORE   1u   /* begin() returned false / cpArbiterIgnore: ignored until the shapes separate (cpArbiter.c:46-50) */
+#define CPB200_EDIT_REJECT   2u   /* preSolve() returned false: not solved this step (cpSpaceStep.c:275-285) */
+#define CPB200_EDIT_MATERIAL 4u   /* cpArbiterSetRestitution / SetFriction / SetSurfaceVelocity (cpArbiter.c:97-143) */
+#define CPB200_EDIT_CONTACTS 8u   /* cpArbiterSetContactPointSet (cpArbiter.c:181-209): n, r1, r2 of the existing contacts */
+typedef struct cpb200_arbiter_edit {
+	int32_t record; uint32_t flags;
+	double e, u, surface_vr[2];
+	double n[2], r1[2][2], r2[2][2];
+} cpb200_arbiter_edit;
+CPB200_API int cpb200_world_edit_arbiters(cpb200_world *w, int n, const cpb200_arbiter_edit *edits);
 /* n steps timed with CUDA events recorded on the world's stream; *ms = device time in milliseconds. */
 CPB200_API int cpb200_world_time_steps(cpb200_world *w, double dt, int n, float *ms);
 /* Number of kernels this library has launched in this process (all worlds). */

@@ -106,3 +106,25 @@ def test_structural_edit_keeps_warm_start():
     # velocities of the resting pile stay small: warm-start impulses survived the re-upload
     assert np.nanmax(np.abs(after[1:, 2:4])) < np.nanmax(np.abs(before[1:, 2:4])) + 15.0
     assert np.nanmax(np.abs(after[1:, 0:2] - before[1:, 0:2])) < 1.0
+
+
+@pytest.mark.parametrize("which", range(10))
+def test_collision_handler_semantics_match_reference(ref, which):
+    """begin/preSolve return values, cpArbiterIgnore, cpArbiterSet{Restitution,Friction,SurfaceVelocity}, sensors,
+    wildcard and default handlers take effect inside the step they are called in (split device step), with the
+    reference's callback counts and the reference's trajectory (scenes/scene_io.c cpb_scene_handler_scenario:
+    one ball over static geometry, so the solver order cannot matter).
+    0 plain, 1 preSolve false, 2 begin false, 3 restitution, 4 conveyor, 5 sensor, 6 one-way platform,
+    7 ignore from the 10th preSolve, 8 wildcard handler, 9 default handler."""
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+    out = []
+    for lib in (ref.scene, load_scene_lib()):
+        lib.cpb_scene_handler_scenario.restype = C.c_int
+        lib.cpb_scene_handler_scenario.argtypes = [C.c_int, C.c_int, dp]
+        o = np.zeros(12)
+        assert lib.cpb_scene_handler_scenario(which, 150, o.ctypes.data_as(dp)) == 0
+        out.append(o)
+    assert np.array_equal(out[0][:4], out[1][:4]), "callback counts (begin, preSolve, postSolve, separate)"
+    assert out[0][10] == out[1][10], "step of the first contact"
+    assert np.allclose(out[0], out[1], rtol=1e-9, atol=1e-9)
