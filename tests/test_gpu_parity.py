@@ -144,3 +144,44 @@ def test_narrowphase_against_cpShapesCollide(ref, name):
             assert rel_err(out_dev[:3 + 5 * n_ref], out_ref[:3 + 5 * n_ref]) < TOL, (a, b, out_dev, out_ref)
             checked += 1
     assert checked > 0
+
+
+BENCH_SCENES = ["SimpleTerrainCircles_1000", "SimpleTerrainCircles_500", "SimpleTerrainCircles_100",
+                "SimpleTerrainBoxes_1000", "SimpleTerrainBoxes_500", "SimpleTerrainBoxes_100",
+                "SimpleTerrainHexagons_1000", "SimpleTerrainHexagons_500", "SimpleTerrainHexagons_100",
+                "SimpleTerrainVCircles_200", "SimpleTerrainVBoxes_200", "SimpleTerrainVHexagons_200",
+                "ComplexTerrainCircles_1000", "ComplexTerrainHexagons_1000",
+                "BouncyTerrainCircles_500", "BouncyTerrainHexagons_500", "NoCollide"]
+
+
+@pytest.mark.parametrize("name", BENCH_SCENES)
+def test_every_bench_scene_pairs_exact_and_one_step_state(ref, name):
+    """North star: 'matches the reference broadphase pairs bit-exactly and its step state within tolerance on
+    every Bench.c scene'.  The scene is built by the reference's own demo code at run time (oracle/_ref), flattened
+    and loaded into both libraries; 40 steps, each from the reference's body state, device in the reference's
+    solver order: pair sets bit-exact, p/a/v/w within 1e-9."""
+    from chipmunk2d_b200.engine import Scene
+    if name not in ref.demo_names():
+        pytest.skip("demo not in the reference build")
+    blob, dt = ref.demo_scene(name)
+    sc = Scene(blob)
+    rs = ref.load(blob)
+    w = World(1)
+    w.load_scene(sc)
+    w.set_solver_mode(1)
+    worst = {"p": 0.0, "v": 0.0, "pairs_bad": 0, "pairs": 0}
+
+    def check(step, asleep, arbs, hi):
+        pr, pw = rs.pairs(asleep), w.pairs()
+        worst["pairs"] += len(pr)
+        if not np.array_equal(pr, pw):
+            worst["pairs_bad"] += 1
+        rb = rs.priv_bodies(); wb = w.bodies()
+        worst["p"] = max(worst["p"], rel_err(wb["p"][1:], rb[1:, 0:2]), rel_err(wb["a"][1:], rb[1:, 4]))
+        worst["v"] = max(worst["v"], rel_err(wb["v"][1:], rb[1:, 2:4]), rel_err(wb["w"][1:], rb[1:, 5]))
+
+    lockstep(rs, w, dt, 40, check, resync_scene=sc)
+    assert worst["pairs_bad"] == 0
+    assert name == "NoCollide" or worst["pairs"] > 0
+    assert worst["p"] < TOL and worst["v"] < TOL, worst
+    rs.space = None
