@@ -157,16 +157,34 @@ CPB_DEVICE void colour_starts(const DColour &K, DCounters *C){
 
 CPB_DEVICE void write_row(const DArbs &A, const DRows &R, int i, int r){
 	if(r >= R.cap) return;
-	R.arb[r] = i; R.ba[r] = A.ba[i]; R.bb[r] = A.bb[i];
-	int cnt = A.cnt[i];
+	// gather everything first, then scatter: the record and row arrays may alias as far as the compiler knows, so
+	// interleaved copies would serialise into load -> store -> load chains (one memory latency per field)
+	const int ba = A.ba[i], bb = A.bb[i], cnt = A.cnt[i], state = A.state[i];
+	const V2 n = A.n[i], svr = A.svr[i];
+	const double u = A.u[i];
+	const int s0 = CIDX(A, i, 0), s1 = CIDX(A, i, 1);
+	const V2 r1a = A.r1[s0], r2a = A.r2[s0];
+	const double nma = A.nmass[s0], tma = A.tmass[s0], boa = A.bounce[s0], bia = A.bias[s0], jna = A.jn[s0], jta = A.jt[s0], jba = A.jb[s0];
+	V2 r1b = r1a, r2b = r2a;
+	double nmb = 0.0, tmb = 0.0, bob = 0.0, bib = 0.0, jnb = 0.0, jtb = 0.0, jbb = 0.0;
+	if(cnt == 2){
+		r1b = A.r1[s1]; r2b = A.r2[s1];
+		nmb = A.nmass[s1]; tmb = A.tmass[s1]; bob = A.bounce[s1]; bib = A.bias[s1]; jnb = A.jn[s1]; jtb = A.jt[s1]; jbb = A.jb[s1];
+	}
+	R.arb[r] = i; R.ba[r] = ba; R.bb[r] = bb;
 	// first-collision arbiters skip the warm start (cpArbiter.c:444): flag in the sign of cnt
-	R.cnt[r] = (A.state[i] == CPB200_ARB_FIRST_COLLISION ? -cnt : cnt);
-	R.n[r] = A.n[i]; R.svr[r] = A.svr[i]; R.u[r] = A.u[i];
-	for(int k = 0; k < cnt; k++){
-		int s = CIDX(A, i, k), d = k*R.cap + r;
-		R.r1[d] = A.r1[s]; R.r2[d] = A.r2[s];
-		R.nmass[d] = A.nmass[s]; R.tmass[d] = A.tmass[s]; R.bounce[d] = A.bounce[s]; R.bias[d] = A.bias[s];
-		R.jn[d] = A.jn[s]; R.jt[d] = A.jt[s]; R.jb[d] = A.jb[s];
+	R.cnt[r] = (state == CPB200_ARB_FIRST_COLLISION ? -cnt : cnt);
+	R.n[r] = n; R.svr[r] = svr; R.u[r] = u;
+	if(cnt >= 1){
+		R.r1[r] = r1a; R.r2[r] = r2a;
+		R.nmass[r] = nma; R.tmass[r] = tma; R.bounce[r] = boa; R.bias[r] = bia;
+		R.jn[r] = jna; R.jt[r] = jta; R.jb[r] = jba;
+	}
+	if(cnt == 2){
+		const int d = R.cap + r;
+		R.r1[d] = r1b; R.r2[d] = r2b;
+		R.nmass[d] = nmb; R.tmass[d] = tmb; R.bounce[d] = bob; R.bias[d] = bib;
+		R.jn[d] = jnb; R.jt[d] = jtb; R.jb[d] = jbb;
 	}
 }
 
