@@ -80,6 +80,11 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 		uint2 ida = {0u, 0u}, idb = {0u, 0u};
 		uint64_t key = 0;
 		double4 w0 = make_double4(0, 0, 0, 0), w1 = w0;
+		// gathers the record needs (body positions, materials, body types) are issued as soon as the body indices
+		// are known, together with the table probe: one memory latency for all of them instead of a chain
+		V2 pa_ = v2(0, 0), pb_ = v2(0, 0);
+		double4 ma = w0, mb = w0;
+		int type_a = 0, type_b = 0;
 		if(i < np){
 			sa = pa[i]; sb = pb[i];
 			ida = S.ids[sa]; idb = S.ids[sb];
@@ -92,16 +97,25 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 				unsigned wa_ = (unsigned)__double_as_longlong(ca.w), wb_ = (unsigned)__double_as_longlong(cb.w);
 				ba = (int)(wa_ & 0x7fffffffu); bb = (int)(wb_ & 0x7fffffffu); sensor = ((wa_ | wb_) >> 31) != 0;
 				circle_to_circle(a, b, m);
-				if(m.count > 0) pi = table_find(prev_table, key);
+				if(m.count > 0){
+					pa_ = B.pos[ba]; pb_ = B.pos[bb]; type_a = B.type[ba]; type_b = B.type[bb];
+					ma = ld4_nc(&S.mat[sa]); mb = ld4_nc(&S.mat[sb]);
+					pi = table_find(prev_table, key);
+				}
 				if(pi >= 0){ w0 = ld4_nc(&prev.warm[2*pi]); w1 = ld4_nc(&prev.warm[2*pi + 1]); }
 			} else {
+				ba = S.body[sa]; bb = S.body[sb]; sensor = (S.sensor[sa] || S.sensor[sb]);
 				pi = table_find(prev_table, key);
 				if(pi >= 0){ w0 = ld4_nc(&prev.warm[2*pi]); w1 = ld4_nc(&prev.warm[2*pi + 1]); }
 				m.id = (pi >= 0 ? (uint32_t)((unsigned long long)__double_as_longlong(w1.z) >> 32) : 0u);
 				NShape a = load_nshape(S, B, sa), b = load_nshape(S, B, sb);
 				if(CLS == 1) circle_to_segment(a, b, m);
 				else collide_shapes(a, b, m);
-				ba = S.body[sa]; bb = S.body[sb]; sensor = (S.sensor[sa] || S.sensor[sb]);
+				// (not before the narrowphase: GJK/EPA needs the registers, and many box pairs do not touch)
+				if(m.count > 0){
+					pa_ = B.pos[ba]; pb_ = B.pos[bb]; type_a = B.type[ba]; type_b = B.type[bb];
+					ma = ld4_nc(&S.mat[sa]); mb = ld4_nc(&S.mat[sb]);
+				}
 			}
 			have = (m.count > 0);
 		}
@@ -115,7 +129,6 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 		uint64_t phash[2] = {0, 0};
 		double pjn[2] = {0.0, 0.0}, pjt[2] = {0.0, 0.0};
 		if(pi >= 0){
-			prev.seen[pi] = 1;
 			unsigned meta = (unsigned)(unsigned long long)__double_as_longlong(w1.z);
 			int ps = (int)(meta & 0xffu);
 			pcnt = (int)((meta >> 8) & 0xffu); pactive = (int)((meta >> 16) & 0xffu); pcolour = (int)(signed char)(meta >> 24);
@@ -124,7 +137,14 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 			// CACHED -> FIRST_COLLISION (cpArbiter.c:412-413); IGNORE is sticky until separation
 			state = (ps == CPB200_ARB_CACHED ? CPB200_ARB_FIRST_COLLISION : (ps == CPB200_ARB_IGNORE ? CPB200_ARB_IGNORE : CPB200_ARB_NORMAL));
 		}
-		V2 pa_ = B.pos[ba], pb_ = B.pos[bb];
+		// active <=> pushed to space->arbiters (cpSpaceStep.c:261-274); the default handler accepts everything
+		const bool both_inf = (type_a != CPB200_BODY_DYNAMIC) && (type_b != CPB200_BODY_DYNAMIC);
+		const bool active = (state != CPB200_ARB_IGNORE) && !sensor && !both_inf;
+		// a rejected first contact still shows FIRST_COLLISION to the begin handler; k_arb_prestep downgrades it
+		// to NORMAL afterwards (cpSpaceStep.c:283)
+		if(!active && state != CPB200_ARB_IGNORE && state != CPB200_ARB_FIRST_COLLISION) state = CPB200_ARB_NORMAL;
+		const V2 svr0 = vsub(v2(mb.z, mb.w), v2(ma.z, ma.w));
+		if(pi >= 0) prev.seen[pi] = 1;
 		for(int k = 0; k < m.count; k++){
 			double jn = 0.0, jt = 0.0;
 			for(int j = 0; j < pcnt; j++){
@@ -142,23 +162,15 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 		cur.cnt[slot] = m.count;
 		cur.n[slot] = m.n;
 		cur.gjkid[slot] = m.id;
-		double4 ma = ld4_nc(&S.mat[sa]), mb = ld4_nc(&S.mat[sb]);
 		cur.e[slot] = ma.x*mb.x;
 		cur.u[slot] = ma.y*mb.y;
-		V2 svr = vsub(v2(mb.z, mb.w), v2(ma.z, ma.w));
-		cur.svr[slot] = vsub(svr, vmul(m.n, vdot(svr, m.n)));
+		cur.svr[slot] = vsub(svr0, vmul(m.n, vdot(svr0, m.n)));
 		cur.stamp[slot] = stamp;
 		cur.seen[slot] = 0;
 		cur.colour[slot] = -1;
 		cur.pri[slot] = mix64(arb_key(ida.y, idb.y)) >> 8;
 		cur.hint[slot] = (pi >= 0 && pactive == 1 ? pcolour : -1);
-		// active <=> pushed to space->arbiters (cpSpaceStep.c:261-274); the default handler accepts everything
-		bool both_inf = (B.type[ba] != CPB200_BODY_DYNAMIC) && (B.type[bb] != CPB200_BODY_DYNAMIC);
-		bool active = (state != CPB200_ARB_IGNORE) && !sensor && !both_inf;
 		cur.active[slot] = active ? 1 : 0;
-		// a rejected first contact still shows FIRST_COLLISION to the begin handler; k_arb_prestep downgrades it
-		// to NORMAL afterwards (cpSpaceStep.c:283)
-		if(!active && state != CPB200_ARB_IGNORE && state != CPB200_ARB_FIRST_COLLISION) state = CPB200_ARB_NORMAL;
 		cur.state[slot] = state;
 #ifndef CPB_EMU
 		{

@@ -461,10 +461,12 @@ CPB_DEVICE void rows_writeback(const DArbs &A, const DRows &R, int n_rows, int t
 	for(int r = tid; r < n_rows; r += nth){
 		int i = R.arb[r];
 		int cnt = R.cnt[r]; if(cnt < 0) cnt = -cnt;
-		for(int k = 0; k < cnt; k++){
-			int s = CIDX(A, i, k), d = k*R.cap + r;
-			A.jn[s] = ld_f64(&R.jn[d]); A.jt[s] = ld_f64(&R.jt[d]); A.jb[s] = ld_f64(&R.jb[d]);
-		}
+		// loads first, stores after (the compiler must assume the arrays alias and would chain them otherwise)
+		const double jn0 = ld_f64(&R.jn[r]), jt0 = ld_f64(&R.jt[r]), jb0 = ld_f64(&R.jb[r]);
+		double jn1 = 0.0, jt1 = 0.0, jb1 = 0.0;
+		if(cnt == 2){ const int d = R.cap + r; jn1 = ld_f64(&R.jn[d]); jt1 = ld_f64(&R.jt[d]); jb1 = ld_f64(&R.jb[d]); }
+		if(cnt >= 1){ const int s = CIDX(A, i, 0); A.jn[s] = jn0; A.jt[s] = jt0; A.jb[s] = jb0; }
+		if(cnt == 2){ const int s = CIDX(A, i, 1); A.jn[s] = jn1; A.jt[s] = jt1; A.jb[s] = jb1; }
 	}
 }
 
