@@ -26,6 +26,22 @@ __device__ __forceinline__ double4 ld4_nc(const double4 *p){   // read-only for 
 	asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
 	return v;
 }
+__device__ __forceinline__ double4 ld4_cs(const double4 *p){   // streamed once: evict-first
+	double4 v;
+	asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ void st4_cs(double4 *p, double4 v){
+	asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+__device__ __forceinline__ double4 ld4_ca(const double4 *p){   // default caching (L1 + L2)
+	double4 v;
+	asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ void st4_wb(double4 *p, double4 v){
+	asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
 __device__ __forceinline__ void st4_cg(double4 *p, double4 v){
 	asm volatile("st.global.cg.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
 }
@@ -33,6 +49,10 @@ __device__ __forceinline__ void st4_cg(double4 *p, double4 v){
 static inline double4 ld4_cg(const double4 *p){ return *p; }
 static inline double4 ld4_nc(const double4 *p){ return *p; }
 static inline void st4_cg(double4 *p, double4 v){ *p = v; }
+static inline double4 ld4_cs(const double4 *p){ return *p; }
+static inline void st4_cs(double4 *p, double4 v){ *p = v; }
+static inline double4 ld4_ca(const double4 *p){ return *p; }
+static inline void st4_wb(double4 *p, double4 v){ *p = v; }
 #endif
 
 CPB_HD V2 v2(double x, double y){ return make_double2(x, y); }

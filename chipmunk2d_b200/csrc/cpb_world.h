@@ -116,6 +116,16 @@ struct DRows {
 	V2 *r1, *r2;
 	double *nmass, *tmass, *bounce, *bias;
 	double *jn, *jt, *jb;
+	// Packed view for the space-local solver (k_sl_rows / k_sl_solve), carved from separate storage: five vectors
+	// per row instead of sixteen scalar planes.  That solver is latency- and instruction-bound (rows come from
+	// L1/L2, one warp per space), where fewer, wider requests win 20%; the world-wide solver streams its rows from
+	// HBM with a full warp per 256 contiguous bytes, where the scalar planes measured 12% FASTER than 32-byte
+	// per-thread vectors and a packed impulse vector doubles the write traffic.
+	int4 *hdr;             // (body a, body b, count [negative: first collision], arbiter record)
+	double4 *nsv;          // (n.x, n.y, surface_vr.x, surface_vr.y)
+	double4 *r12;          // [k*cap + r] (r1.x, r1.y, r2.x, r2.y)
+	double4 *mass;         // [k*cap + r] (nMass, tMass, bias, bounce)
+	double4 *imp;          // [k*cap + r] (jnAcc, jtAcc, jBias, friction u)
 };
 
 // ---- joints (cpConstraint + joint structs, chipmunk_structs.h:250-382) ----

@@ -188,6 +188,36 @@ CPB_DEVICE void write_row(const DArbs &A, const DRows &R, int i, int r){
 	}
 }
 
+// the same row in the packed layout of the space-local solver
+CPB_DEVICE void write_row_packed(const DArbs &A, const DRows &R, int i, int r){
+	if(r >= R.cap) return;
+	const int ba = A.ba[i], bb = A.bb[i], cnt = A.cnt[i], state = A.state[i];
+	const V2 n = A.n[i], svr = A.svr[i];
+	const double u = A.u[i];
+	const int s0 = CIDX(A, i, 0), s1 = CIDX(A, i, 1);
+	const V2 r1a = A.r1[s0], r2a = A.r2[s0];
+	const double nma = A.nmass[s0], tma = A.tmass[s0], boa = A.bounce[s0], bia = A.bias[s0], jna = A.jn[s0], jta = A.jt[s0], jba = A.jb[s0];
+	V2 r1b = r1a, r2b = r2a;
+	double nmb = 0.0, tmb = 0.0, bob = 0.0, bib = 0.0, jnb = 0.0, jtb = 0.0, jbb = 0.0;
+	if(cnt == 2){
+		r1b = A.r1[s1]; r2b = A.r2[s1];
+		nmb = A.nmass[s1]; tmb = A.tmass[s1]; bob = A.bounce[s1]; bib = A.bias[s1]; jnb = A.jn[s1]; jtb = A.jt[s1]; jbb = A.jb[s1];
+	}
+	R.hdr[r] = make_int4(ba, bb, (state == CPB200_ARB_FIRST_COLLISION ? -cnt : cnt), i);
+	R.nsv[r] = make_double4(n.x, n.y, svr.x, svr.y);
+	if(cnt >= 1){
+		R.r12[r] = make_double4(r1a.x, r1a.y, r2a.x, r2a.y);
+		R.mass[r] = make_double4(nma, tma, bia, boa);
+		R.imp[r] = make_double4(jna, jta, jba, u);
+	}
+	if(cnt == 2){
+		const int d = R.cap + r;
+		R.r12[d] = make_double4(r1b.x, r1b.y, r2b.x, r2b.y);
+		R.mass[d] = make_double4(nmb, tmb, bib, bob);
+		R.imp[d] = make_double4(jnb, jtb, jbb, u);
+	}
+}
+
 // scatter arbiter records into colour-sorted SoA rows (the solver's coalesced working set).
 // scnt/sbase: per-CTA shared scratch [CPB_MAX_COLOURS] (NULL in the emulation build): a CTA counts its
 // rows per colour, reserves one contiguous range per colour with a single global atomic, then hands the
@@ -470,6 +500,47 @@ CPB_DEVICE void rows_writeback(const DArbs &A, const DRows &R, int n_rows, int t
 	}
 }
 
+// One row of the packed layout against shared-memory velocities (space-local solver): every load of the row --
+// both contacts -- is issued up front (one memory latency per row; the compiler cannot hoist the second contact's
+// loads over the first one's stores itself), the impulse vector is written back only if it changed.
+CPB_DEVICE void solve_row_packed(const VelShared &vs, const DRows &R, int r, int ba, int bb, int cnt, int mode, double dt_coef){
+	const bool first = (cnt < 0);
+	if(first) cnt = -cnt;
+	if(mode == 0 && first) return;
+	const double4 nsv = ld4_ca(&R.nsv[r]);
+	const double4 r12a = ld4_ca(&R.r12[r]), impa = ld4_ca(&R.imp[r]);
+	double4 r12b = r12a, impb = impa, massa = impa, massb = impa;
+	if(cnt == 2){ r12b = ld4_ca(&R.r12[R.cap + r]); impb = ld4_ca(&R.imp[R.cap + r]); }
+	if(mode != 0){ massa = ld4_ca(&R.mass[r]); if(cnt == 2) massb = ld4_ca(&R.mass[R.cap + r]); }
+	double4 Va = vs.ldV(ba), Vb = vs.ldV(bb);
+	double4 VBa = vs.ldVB(ba), VBb = vs.ldVB(bb);
+	// (m_inv, i_inv) ride in the spare lanes of the two velocity sectors
+	const V2 mia = v2(Va.w, VBa.w), mib = v2(Vb.w, VBb.w);
+	const bool dyn_a = (mia.x != 0.0 || mia.y != 0.0), dyn_b = (mib.x != 0.0 || mib.y != 0.0);
+	const V2 n = v2(nsv.x, nsv.y);
+	if(mode == 0){
+		contact_apply_cached(Va, Vb, mia, mib, n, v2(r12a.x, r12a.y), v2(r12a.z, r12a.w), impa.x, impa.y, dt_coef);
+		if(cnt == 2) contact_apply_cached(Va, Vb, mia, mib, n, v2(r12b.x, r12b.y), v2(r12b.z, r12b.w), impb.x, impb.y, dt_coef);
+		if(dyn_a) vs.stV(ba, Va);
+		if(dyn_b) vs.stV(bb, Vb);
+		return;
+	}
+	const V2 svr = v2(nsv.z, nsv.w);
+	const double u = impa.w;
+	{
+		double jn = impa.x, jt = impa.y, jb = impa.z;
+		contact_apply(Va, Vb, VBa, VBb, mia, mib, n, svr, u, v2(r12a.x, r12a.y), v2(r12a.z, r12a.w), massa.x, massa.y, massa.z, massa.w, jn, jt, jb);
+		if(!(same_bits(jn, impa.x) && same_bits(jt, impa.y) && same_bits(jb, impa.z))) st4_wb(&R.imp[r], make_double4(jn, jt, jb, impa.w));
+	}
+	if(cnt == 2){
+		double jn = impb.x, jt = impb.y, jb = impb.z;
+		contact_apply(Va, Vb, VBa, VBb, mia, mib, n, svr, u, v2(r12b.x, r12b.y), v2(r12b.z, r12b.w), massb.x, massb.y, massb.z, massb.w, jn, jt, jb);
+		if(!(same_bits(jn, impb.x) && same_bits(jt, impb.y) && same_bits(jb, impb.z))) st4_wb(&R.imp[R.cap + r], make_double4(jn, jt, jb, impb.w));
+	}
+	if(dyn_a){ vs.stV(ba, Va); vs.stVB(ba, VBa); }
+	if(dyn_b){ vs.stV(bb, Vb); vs.stVB(bb, VBb); }
+}
+
 // ---- space-local solver: batched worlds of many small spaces -------------------------------------------------
 // Spaces never interact, so a space that fits one CTA does not need the grid: its bodies' velocity sectors
 // live in shared memory for the whole solve and the colours are separated by __syncthreads (no L2 round trip,
@@ -511,7 +582,7 @@ __global__ void k_sl_rows(DBodies B, DArbs A, DJoints J, DRows R, DSpaceLocal SL
 		if(A.active[i] != 1) continue;
 		int col = A.colour[i];
 		if(col < 0) continue;
-		write_row(A, R, i, (int)atomicAdd(&SL.start[sl_arb_bucket(B.space[A.ba[i]], col)], 1u));
+		write_row_packed(A, R, i, (int)atomicAdd(&SL.start[sl_arb_bucket(B.space[A.ba[i]], col)], 1u));
 	}
 	for(int j = tid; j < J.n; j += nth){
 		int col = J.colour[j];
@@ -547,7 +618,7 @@ __global__ void k_sl_solve(DBodies B, DArbs A, DJoints J, DRows R, DSpaceLocal S
 	// indices of this thread's first row / joint of the next phase are fetched one phase ahead
 	int pr = -1, pba = 0, pbb = 0, pcnt = 0, pq = -1, pj = 0, pja = 0, pjb = 0;
 	#define SL_PREFETCH(c_) do { \
-		pr = s_a[c_] + t; if(pr < s_a[(c_) + 1]){ pba = R.ba[pr]; pbb = R.bb[pr]; pcnt = R.cnt[pr]; } else pr = -1; \
+		pr = s_a[c_] + t; if(pr < s_a[(c_) + 1]){ const int4 h_ = R.hdr[pr]; pba = h_.x; pbb = h_.y; pcnt = h_.z; } else pr = -1; \
 		pq = s_j[c_] + (nt - 1 - t); if(pq < s_j[(c_) + 1]){ pj = J.row[pq]; pja = J.a[pj]; pjb = J.b[pj]; } else pq = -1; } while(0)
 	if(ncols > 0) SL_PREFETCH(s_cols[0]);
 	for(int pass = 0; pass <= iterations; pass++){
@@ -557,7 +628,7 @@ __global__ void k_sl_solve(DBodies B, DArbs A, DJoints J, DRows R, DSpaceLocal S
 			const int cn = s_cols[ci + 1 < ncols ? ci + 1 : 0];
 			if(c == CPB_OVERFLOW_COLOUR){
 				if(t == 0){
-					for(int r = s_a[c]; r < s_a[c + 1]; r++) solve_row_idx(vs, B, R, r, R.ba[r], R.bb[r], R.cnt[r], mode, dt_coef);
+					for(int r = s_a[c]; r < s_a[c + 1]; r++){ const int4 h_ = R.hdr[r]; solve_row_packed(vs, R, r, h_.x, h_.y, h_.z, mode, dt_coef); }
 					for(int q = s_j[c]; q < s_j[c + 1]; q++){ int j = J.row[q]; solve_joint_idx(vs, B, J, j, J.a[j], J.b[j], mode, dt, dt_coef); }
 				}
 				SL_PREFETCH(cn);
@@ -566,8 +637,8 @@ __global__ void k_sl_solve(DBodies B, DArbs A, DJoints J, DRows R, DSpaceLocal S
 				SL_PREFETCH(cn);   // constant data: issue before this phase's work so the latency overlaps it
 				const int r1 = s_a[c + 1], q1 = s_j[c + 1];
 				if(r >= 0){
-					solve_row_idx(vs, B, R, r, ba, bb, cnt, mode, dt_coef);
-					for(r += nt; r < r1; r += nt) solve_row_idx(vs, B, R, r, R.ba[r], R.bb[r], R.cnt[r], mode, dt_coef);
+					solve_row_packed(vs, R, r, ba, bb, cnt, mode, dt_coef);
+					for(r += nt; r < r1; r += nt){ const int4 h_ = R.hdr[r]; solve_row_packed(vs, R, r, h_.x, h_.y, h_.z, mode, dt_coef); }
 				}
 				// joints from the far end of the CTA: in small colours a thread gets a row or a joint, not both
 				if(q >= 0){
@@ -582,12 +653,13 @@ __global__ void k_sl_solve(DBodies B, DArbs A, DJoints J, DRows R, DSpaceLocal S
 	for(int b = t; b < nb; b += nt){ B.V[b0 + b] = s_vel[b]; B.VB[b0 + b] = s_vel[nb + b]; }
 	// accumulated impulses back into the arbiter records
 	for(int r = s_a[0] + t; r < s_a[CPB_MAX_COLOURS]; r += nt){
-		int i = R.arb[r];
-		int cnt = R.cnt[r]; if(cnt < 0) cnt = -cnt;
-		for(int k = 0; k < cnt; k++){
-			int sidx = CIDX(A, i, k), d = k*R.cap + r;
-			A.jn[sidx] = R.jn[d]; A.jt[sidx] = R.jt[d]; A.jb[sidx] = R.jb[d];
-		}
+		const int4 h = R.hdr[r];
+		const int i = h.w, cnt = (h.z < 0 ? -h.z : h.z);
+		const double4 i0 = R.imp[r];
+		double4 i1 = i0;
+		if(cnt == 2) i1 = R.imp[R.cap + r];
+		if(cnt >= 1){ const int sidx = CIDX(A, i, 0); A.jn[sidx] = i0.x; A.jt[sidx] = i0.y; A.jb[sidx] = i0.z; }
+		if(cnt == 2){ const int sidx = CIDX(A, i, 1); A.jn[sidx] = i1.x; A.jt[sidx] = i1.y; A.jb[sidx] = i1.z; }
 	}
 }
 #endif

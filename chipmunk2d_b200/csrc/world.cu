@@ -497,6 +497,8 @@ static int alloc_arbs(cpb200_world *w, int cap)
 	DA(w->gA, R.r1, 2*(size_t)cap); DA(w->gA, R.r2, 2*(size_t)cap);
 	DA(w->gA, R.nmass, 2*(size_t)cap); DA(w->gA, R.tmass, 2*(size_t)cap); DA(w->gA, R.bounce, 2*(size_t)cap); DA(w->gA, R.bias, 2*(size_t)cap);
 	DA(w->gA, R.jn, 2*(size_t)cap); DA(w->gA, R.jt, 2*(size_t)cap); DA(w->gA, R.jb, 2*(size_t)cap);
+	DA(w->gA, R.hdr, cap); DA(w->gA, R.nsv, cap);
+	DA(w->gA, R.r12, 2*(size_t)cap); DA(w->gA, R.mass, 2*(size_t)cap); DA(w->gA, R.imp, 2*(size_t)cap);
 	w->cap_arbs = cap;
 	w->cur = 0;
 	return 0;
