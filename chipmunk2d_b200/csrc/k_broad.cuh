@@ -203,17 +203,20 @@ CPB_DEVICE bool bb_intersects(double4 a, double4 b){
 	return (a.x <= b.z && b.x <= a.z && a.y <= b.w && b.y <= a.w);
 }
 
-CPB_DEVICE bool nocollide_lookup(const uint64_t *__restrict__ keys, int n, int ba, int bb){
+// Body pairs joined by a constraint with collideBodies == false (QueryRejectConstraint, cpSpaceStep.c:204-217):
+// an open-addressing set of (lo << 32 | hi) + 1 keys built by the host, `mask` = capacity - 1.  One probe
+// (one L2 access) in the common case -- the binary search over the sorted list it replaces was 17 dependent
+// loads per candidate pair and the whole cost of the pair kernels on the Chains spaces.
+CPB_DEVICE bool nocollide_lookup(const uint64_t *__restrict__ set, int mask, int ba, int bb){
 	uint64_t lo = (uint64_t)(uint32_t)(ba < bb ? ba : bb), hi = (uint64_t)(uint32_t)(ba < bb ? bb : ba);
-	uint64_t key = (lo << 32) | hi;
-	int a = 0, b = n - 1;
-	while(a <= b){
-		int m = (a + b) >> 1;
-		uint64_t k = keys[m];
+	uint64_t key = ((lo << 32) | hi) + 1ull;
+	uint32_t slot = (uint32_t)mix64(key) & (uint32_t)mask;
+	for(;;){
+		uint64_t k = set[slot];
 		if(k == key) return true;
-		if(k < key) a = m + 1; else b = m - 1;
+		if(k == 0) return false;
+		slot = (slot + 1) & (uint32_t)mask;
 	}
-	return false;
 }
 
 CPB_DEVICE bool query_reject(const DShapes &S, int sa, int sb, const uint64_t *nocollide, int n_nocollide){
@@ -285,3 +288,56 @@ __global__ void k_bvh_pairs(DBvh T, DShapes S, DBodies B, DPairs P, const uint64
 		node = stack[--sp];
 	}
 }
+
+// ---- space-local broadphase: batched worlds of many small spaces -------------------------------------------
+// A space of a few hundred shapes does not need a tree: one CTA per space stages the space's AABBs (and which
+// of them are active) in shared memory and every active shape tests all others -- 10^4 box tests per space,
+// no bounds / Morton / sort / build / refit / traversal launches.  Same membership rule as k_bvh_pairs (a pair
+// needs one active shape; two active shapes are reported by the higher index), same QueryReject filter, same
+// warp-ballot append: the pair SET is identical (tests compare it with the reference bit for bit).
+struct DSpaceShapes { const int *shape0, *nshape; };   // contiguous shape range of each space
+
+#ifndef CPB_EMU
+// Two phases per space.  (1) all-pairs AABB tests from shared memory: a hit only appends (i, j) to a candidate list
+// in shared memory (cheap, so the divergence of "my shape overlaps shape j" costs little).  (2) the candidates
+// are dealt out to the threads one each: the expensive part -- filter gathers, constraint lookup, list append --
+// runs with full, converged warps, 32 pairs per ballot and global atomic.  (Doing (2) inside (1) ran the
+// expensive path once per hit with 14 of 32 lanes active on average and waited for a global atomic each time.)
+#define CPB_SLP_CAND 2048
+__global__ void k_sl_pairs(DSpaceShapes SS, DShapes S, DBodies B, DPairs P, const uint64_t *__restrict__ nocollide, int n_nocollide, int *overflow)
+{
+	extern __shared__ double4 s_bb[];                 // [n] AABBs, then [n] ints: active flags
+	__shared__ unsigned s_cand[CPB_SLP_CAND];
+	__shared__ int s_ncand;
+	const int sp = blockIdx.x, s0 = SS.shape0[sp], n = SS.nshape[sp];
+	int *s_act = (int *)(s_bb + n);
+	if(threadIdx.x == 0) s_ncand = 0;
+	for(int k = threadIdx.x; k < n; k += blockDim.x){
+		s_bb[k] = S.bb[s0 + k];
+		s_act[k] = shape_is_active(B, S.body[s0 + k]) ? 1 : 0;
+	}
+	__syncthreads();
+	for(int i = threadIdx.x; i < n; i += blockDim.x){
+		if(!s_act[i]) continue;
+		const double4 q = s_bb[i];
+		for(int j = 0; j < n; j++){
+			if(j == i || (s_act[j] && j < i) || !bb_intersects(q, s_bb[j])) continue;
+			int slot = atomicAdd(&s_ncand, 1);
+			if(slot < CPB_SLP_CAND) s_cand[slot] = ((unsigned)i << 16) | (unsigned)j;
+			else if(!query_reject(S, s0 + i, s0 + j, nocollide, n_nocollide)) emit_pair(S, P, overflow, s0 + i, s0 + j);   // list full
+		}
+	}
+	__syncthreads();
+	const int nc = (s_ncand < CPB_SLP_CAND ? s_ncand : CPB_SLP_CAND);
+	for(int k = threadIdx.x; k < ((nc + 31) & ~31); k += blockDim.x){
+		bool hit = (k < nc);
+		int sa = 0, sb = 0;
+		if(hit){
+			unsigned c = s_cand[k];
+			sa = s0 + (int)(c >> 16); sb = s0 + (int)(c & 0xffffu);
+			hit = !query_reject(S, sa, sb, nocollide, n_nocollide);
+		}
+		if(__any_sync(__activemask(), hit)){ if(hit) emit_pair(S, P, overflow, sa, sb); }
+	}
+}
+#endif

@@ -22,6 +22,7 @@ emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 #else
 unsigned long long g_cpb_launches = 0;
 #endif
+#define CPB_SL_MAX_SHAPES 512          // a space up to this many shapes is broadphased all-pairs in one CTA (k_sl_pairs)
 #define CPB_SL_MAX_SMEM (200*1024)   // shared memory a space's velocity sectors may take in k_sl_solve
 
 // ------------------------------------------------------------------ errors
@@ -145,6 +146,8 @@ struct cpb200_world {
 	bool sl_dirty, sl_ok, sl_disabled;
 	int sl_max_nbody;
 	DSpaceLocal SL; AllocGroup gSL;
+	std::vector<int> shape_body;   // host copy of the shapes' body index
+	DSpaceShapes SS; bool sl_shapes_ok; int sl_max_nshape;
 	uint32_t *sl_tmp;
 	void *d_query; size_t query_bytes;   // device buffer for query hits (+ counters in its first 64 bytes)
 	double *d_scratch;      // small scratch (collide_one output, stats)
@@ -236,6 +239,7 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 		if(per_sm > 4) per_sm = 4;
 		w->coop_blocks = w->sm_count*per_sm;
 		cudaFuncSetAttribute(k_sl_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, CPB_SL_MAX_SMEM);
+		cudaFuncSetAttribute(k_sl_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, CPB_SL_MAX_SHAPES*(int)(sizeof(double4) + sizeof(int)));
 	}
 #endif
 	cpb200_space_params def;
@@ -267,6 +271,7 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	w->mid_step = false; w->step_dt = 0.0; w->step_dt_coef = 0.0; w->step_iterations = 0;
 	w->sl_dirty = true; w->sl_ok = false; w->sl_disabled = (getenv("CPB200_NO_SPACE_LOCAL") != NULL); w->sl_max_nbody = 0;
 	memset(&w->SL, 0, sizeof(w->SL)); w->sl_tmp = NULL;
+	memset(&w->SS, 0, sizeof(w->SS)); w->sl_shapes_ok = false; w->sl_max_nshape = 0;
 	w->last_active = 0; w->force_blocks = 0; w->hints_valid = false; w->wl_cap = 0; w->d_stage = NULL; w->stage_bytes = 0;
 	cudaMalloc(&p, sizeof(double)*64); w->d_scratch = (double *)p;
 	cudaMallocHost(&p, sizeof(double)*64); w->h_scratch = (double *)p;
@@ -568,6 +573,8 @@ extern "C" int cpb200_world_set_shapes(cpb200_world *w, int n, const cpb200_shap
 	   upload(w, S.surfv, surfv) || upload(w, S.la, la) || upload(w, S.lb, lb) || upload(w, S.ln, ln) || upload(w, S.atan, atan_) || upload(w, S.btan, btan_) ||
 	   upload(w, S.mat, mat) || upload(w, S.ids, ids) || upload(w, S.pcount, pcount) || upload(w, S.poff, poff) || upload(w, S.lpv, lpv) || upload(w, S.lpn, lpn)) return -1;
 
+	w->shape_body = body; w->sl_dirty = true;
+
 	// broadphase scratch
 	w->gV.release();
 	DBvh &T = w->bvh;
@@ -665,12 +672,23 @@ extern "C" int cpb200_world_set_joints(cpb200_world *w, int n, const cpb200_join
 	if(upload(w, J.type, type) || upload(w, J.a, a) || upload(w, J.b, b) || upload(w, J.max_force, max_force) || upload(w, J.max_bias, max_bias) ||
 	   upload(w, J.anchor_a, anchor_a) || upload(w, J.anchor_b, anchor_b) || upload(w, J.prm, prm) || upload(w, J.acc, acc) || upload(w, J.aux0, aux0) || upload(w, J.pri, jpri)) return -1;
 	if(w->d_nocollide){ cudaFree(w->d_nocollide); w->d_nocollide = NULL; }
-	w->n_nocollide = (int)nocollide.size();
-	if(w->n_nocollide){
+	w->n_nocollide = 0;   // = capacity - 1 of the device set (0: no pairs)
+	if(!nocollide.empty()){
+		size_t capn = 16;
+		while(capn < 2*nocollide.size()) capn <<= 1;
+		std::vector<uint64_t> set(capn, 0ull);
+		for(uint64_t k : nocollide){
+			uint64_t key = k + 1ull;
+			size_t slot = (size_t)((uint32_t)mix64(key) & (uint32_t)(capn - 1));
+			while(set[slot] != 0ull) slot = (slot + 1) & (capn - 1);
+			set[slot] = key;
+		}
 		void *p = NULL;
-		CPB_CHECK(cudaMalloc(&p, sizeof(uint64_t)*nocollide.size()));
+		CPB_CHECK(cudaMalloc(&p, sizeof(uint64_t)*capn));
 		w->d_nocollide = (uint64_t *)p;
-		CPB_CHECK(cudaMemcpyAsync(w->d_nocollide, nocollide.data(), sizeof(uint64_t)*nocollide.size(), cudaMemcpyHostToDevice, w->stream));
+		w->n_nocollide = (int)(capn - 1);
+		CPB_CHECK(cudaMemcpyAsync(w->d_nocollide, set.data(), sizeof(uint64_t)*capn, cudaMemcpyHostToDevice, w->stream));
+		CPB_CHECK(cudaStreamSynchronize(w->stream));   // `set` is a local
 	}
 	w->joints_dt = 0.0; // force bias_coef refresh
 	w->hints_valid = false;
@@ -740,7 +758,7 @@ __global__ void k_build_order(DShapes S, DArbs A, DTable T, const uint64_t *__re
 // memory of a CTA (two 32-byte velocity sectors per body).
 static int sl_refresh(cpb200_world *w)
 {
-	w->sl_dirty = false; w->sl_ok = false;
+	w->sl_dirty = false; w->sl_ok = false; w->sl_shapes_ok = false;
 	w->gSL.release(); memset(&w->SL, 0, sizeof(w->SL)); w->sl_tmp = NULL;
 	const int ns = w->n_spaces, nb = w->B.n;
 	if(w->sl_disabled || nb == 0 || (int)w->body_space.size() != nb) return 0;
@@ -765,6 +783,32 @@ static int sl_refresh(cpb200_world *w)
 	w->SL.n_spaces = ns; w->SL.body0 = d_first; w->SL.nbody = d_count; w->SL.start = d_start;
 	w->sl_max_nbody = mx;
 	w->sl_ok = true;
+	// contiguous shape range per space (space-local broadphase)
+	const int nsh = w->S.n;
+	if((int)w->shape_body.size() == nsh && nsh > 0){
+		std::vector<int> sfirst((size_t)ns, -1), scount((size_t)ns, 0);
+		bool ok = true;
+		for(int i = 0; i < nsh && ok; i++){
+			int b = w->shape_body[(size_t)i];
+			if(b < 0 || b >= nb){ ok = false; break; }
+			int sp = w->body_space[(size_t)b];
+			if(sfirst[(size_t)sp] < 0) sfirst[(size_t)sp] = i;
+			else if(sfirst[(size_t)sp] + scount[(size_t)sp] != i) ok = false;
+			scount[(size_t)sp]++;
+		}
+		if(ok){
+			int smx = 0;
+			for(int sp = 0; sp < ns; sp++){ if(sfirst[(size_t)sp] < 0) sfirst[(size_t)sp] = 0; smx = std::max(smx, scount[(size_t)sp]); }
+			int *d_s0 = NULL, *d_sn = NULL;
+			DA(w->gSL, d_s0, ns); DA(w->gSL, d_sn, ns);
+			CPB_CHECK(cudaMemcpyAsync(d_s0, sfirst.data(), sizeof(int)*(size_t)ns, cudaMemcpyHostToDevice, w->stream));
+			CPB_CHECK(cudaMemcpyAsync(d_sn, scount.data(), sizeof(int)*(size_t)ns, cudaMemcpyHostToDevice, w->stream));
+			CPB_CHECK(cudaStreamSynchronize(w->stream));
+			w->SS.shape0 = d_s0; w->SS.nshape = d_sn;
+			w->sl_max_nshape = smx;
+			w->sl_shapes_ok = true;
+		}
+	}
 	return 0;
 }
 
@@ -810,8 +854,22 @@ static int step_phase_a(cpb200_world *w, double dt)
 	if(ns) LAUNCH(k_shape_cache, grid_for(ns, 128), 128, st, S, B, 0);
 	STAGE_END(w, ST_SHAPE_CACHE);
 
-	// K3: LBVH
-	if(ns >= 2){
+	// K3: space-local all-pairs broadphase for worlds of small spaces, else the LBVH
+	if(w->sl_dirty && sl_refresh(w)) return -1;
+#ifndef CPB_EMU
+	const bool sl_broad = w->sl_shapes_ok && w->sl_max_nshape <= CPB_SL_MAX_SHAPES && ns >= 2;
+#else
+	const bool sl_broad = false;
+#endif
+	if(sl_broad){
+#ifndef CPB_EMU
+		STAGE_END(w, ST_BVH_KEYS); STAGE_END(w, ST_BVH_SORT); STAGE_END(w, ST_BVH_BUILD);
+		int threads = 32; while(threads < 256 && threads < w->sl_max_nshape) threads *= 2;
+		size_t smem = (size_t)w->sl_max_nshape*(sizeof(double4) + sizeof(int));
+		LAUNCH_SMEM(k_sl_pairs, w->n_spaces, threads, smem, st, w->SS, S, B, w->P, (const uint64_t *)w->d_nocollide, w->n_nocollide, &w->C->overflow);
+		STAGE_END(w, ST_BVH_PAIRS);
+#endif
+	} else if(ns >= 2){
 		DBvh &T = w->bvh;
 		LAUNCH(k_bounds_init, 1, 32, st, T.bounds);
 		LAUNCH(k_bounds, std::min(grid_for(ns, 256), wide), 256, st, S, T.bounds);
