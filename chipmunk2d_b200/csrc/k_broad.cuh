@@ -247,46 +247,102 @@ CPB_DEVICE void emit_pair(const DShapes &S, const DPairs &P, int *overflow, int 
 }
 
 // One thread per leaf in Morton order (neighbouring threads walk neighbouring paths).
-__global__ void k_bvh_pairs(DBvh T, DShapes S, DBodies B, DPairs P, const uint64_t *__restrict__ nocollide, int n_nocollide, int multi_space, int *overflow)
+// The warp stays converged around the traversal: every iteration each unfinished lane visits ONE node and only
+// appends the leaf hits it finds to a per-warp candidate list in shared memory; when the list runs full (and at
+// the end) the warp deals the candidates out one per lane and runs the expensive part -- filter gathers, constraint
+// lookup, class lists -- converged, 32 pairs per ballot and global atomic.  (Inline, that part ran once per hit
+// with a handful of active lanes and waited for a global atomic each time.)
+#define CPB_PAIR_CAND 192     // per warp; a visit appends at most 2 per lane -> flush above CPB_PAIR_CAND - 64
+#ifndef CPB_EMU
+__device__ __forceinline__ void pairs_flush(int2 *cand, int *count, int lane, const DShapes &S, const DPairs &P,
+	const uint64_t *__restrict__ nocollide, int n_nocollide, int *overflow)
+{
+	__syncwarp();
+	const int n = *count;
+	for(int k = lane; k < ((n + 31) & ~31); k += 32){
+		bool hit = (k < n);
+		int2 c = make_int2(0, 0);
+		if(hit){ c = cand[k]; hit = !query_reject(S, c.x, c.y, nocollide, n_nocollide); }
+		if(__any_sync(0xffffffffu, hit)){ if(hit) emit_pair(S, P, overflow, c.x, c.y); }
+	}
+	__syncwarp();
+	if(lane == 0) *count = 0;
+	__syncwarp();
+}
+#endif
+
+__global__ void __launch_bounds__(128) k_bvh_pairs(DBvh T, DShapes S, DBodies B, DPairs P, const uint64_t *__restrict__ nocollide, int n_nocollide, int multi_space, int *overflow)
 {
 	int i = CPB_TID;
 	int n = T.n;
-	if(i >= n) return;
-	int si = T.leaf_shape[i];
-	int bi = S.body[si];
-	if(!shape_is_active(B, bi)) return;
-	double4 q = ld4_nc(&S.bb[si]);
-	int qsp = B.space[bi];
-	if(n < 2) return;
+#ifndef CPB_EMU
+	__shared__ int2 s_cand[4][CPB_PAIR_CAND];
+	__shared__ int s_n[4];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	if(lane == 0) s_n[wid] = 0;
+	__syncwarp();
+	bool done = (i >= n || n < 2);
+#else
+	if(i >= n || n < 2) return;
+	bool done = false;
+#endif
+	int si = 0, qsp = 0;
+	double4 q = make_double4(0, 0, 0, 0);
+	if(!done){
+		si = T.leaf_shape[i];
+		int bi = S.body[si];
+		if(!shape_is_active(B, bi)) done = true;
+		else { q = ld4_nc(&S.bb[si]); qsp = B.space[bi]; }
+	}
+#ifdef CPB_EMU
+	if(done) return;
+#endif
 	int stack[CPB_BVH_STACK];
 	int sp = 0;
 	int node = 0;
 	for(;;){
-		int4 ci = T.cinfo[node];
-		double4 box[2] = {ld4_nc(&T.cbox[2*node]), ld4_nc(&T.cbox[2*node + 1])};
-		int4 cs = make_int4(0, 0, 0, 0);
-		if(multi_space) cs = T.cspace[node];
-		int next = -1;
+#ifndef CPB_EMU
+		if(!__any_sync(0xffffffffu, !done)) break;
+#endif
+		if(!done){
+			int4 ci = T.cinfo[node];
+			double4 box[2] = {ld4_nc(&T.cbox[2*node]), ld4_nc(&T.cbox[2*node + 1])};
+			int4 cs = make_int4(0, 0, 0, 0);
+			if(multi_space) cs = T.cspace[node];
+			int next = -1;
 #pragma unroll
-		for(int c = 0; c < 2; c++){
-			int ch = (c ? ci.y : ci.x), skip = (c ? ci.w : ci.z);
-			if(skip <= i) continue;   // every leaf below is active and at/before i: those leaves report the pair
-			if(!bb_intersects(q, box[c])) continue;
-			if(multi_space){ int lo = (c ? cs.z : cs.x), hi = (c ? cs.w : cs.y); if(qsp < lo || qsp > hi) continue; }
-			if(ch >= n - 1){
-				int sj = T.leaf_shape[ch - (n - 1)];
-				if(query_reject(S, si, sj, nocollide, n_nocollide)) continue;
-				emit_pair(S, P, overflow, si, sj);
-			} else {
-				if(next < 0) next = ch;
-				else if(sp < CPB_BVH_STACK) stack[sp++] = ch;
-				else atomicOr((unsigned *)overflow, 8u);
+			for(int c = 0; c < 2; c++){
+				int ch = (c ? ci.y : ci.x), skip = (c ? ci.w : ci.z);
+				if(skip <= i) continue;   // every leaf below is active and at/before i: those leaves report the pair
+				if(!bb_intersects(q, box[c])) continue;
+				if(multi_space){ int lo = (c ? cs.z : cs.x), hi = (c ? cs.w : cs.y); if(qsp < lo || qsp > hi) continue; }
+				if(ch >= n - 1){
+					int sj = T.leaf_shape[ch - (n - 1)];
+#ifndef CPB_EMU
+					s_cand[wid][atomicAdd(&s_n[wid], 1)] = make_int2(si, sj);
+#else
+					if(!query_reject(S, si, sj, nocollide, n_nocollide)) emit_pair(S, P, overflow, si, sj);
+#endif
+				} else {
+					if(next < 0) next = ch;
+					else if(sp < CPB_BVH_STACK) stack[sp++] = ch;
+					else atomicOr((unsigned *)overflow, 8u);
+				}
 			}
+			if(next >= 0) node = next;
+			else if(sp == 0) done = true;
+			else node = stack[--sp];
 		}
-		if(next >= 0){ node = next; continue; }
-		if(sp == 0) break;
-		node = stack[--sp];
+#ifndef CPB_EMU
+		__syncwarp();
+		if(s_n[wid] > CPB_PAIR_CAND - 64) pairs_flush(s_cand[wid], &s_n[wid], lane, S, P, nocollide, n_nocollide, overflow);
+#else
+		if(done) break;
+#endif
 	}
+#ifndef CPB_EMU
+	pairs_flush(s_cand[wid], &s_n[wid], lane, S, P, nocollide, n_nocollide, overflow);
+#endif
 }
 
 // ---- space-local broadphase: batched worlds of many small spaces -------------------------------------------
