@@ -231,28 +231,46 @@ __global__ void k_arb_carry(DBodies B, DArbs prev, DArbs cur, DTable cur_table, 
 		int slot = cpb_warp_append(cur.count_ptr, keep);
 		if(!keep) continue;
 		if(slot >= cur.cap){ atomicOr((unsigned *)&C->overflow, 2u); continue; }
-		cur.key[slot] = prev.key[i];
-		cur.sa[slot] = prev.sa[i]; cur.sb[slot] = prev.sb[i]; cur.ba[slot] = prev.ba[i]; cur.bb[slot] = prev.bb[i];
-		cur.cnt[slot] = prev.cnt[i];
+		// gather the whole record first, then scatter it: copied field by field the loads would queue up behind the
+		// stores (the compiler must assume prev and cur alias), one memory latency per field
+		const uint64_t key = prev.key[i];
+		const int sa = prev.sa[i], sb = prev.sb[i], ba_ = prev.ba[i], bb_ = prev.bb[i], cnt = prev.cnt[i];
+		const uint32_t pstamp = prev.stamp[i], gjkid = prev.gjkid[i];
+		const V2 n = prev.n[i], svr = prev.svr[i];
+		const double e = prev.e[i], u = prev.u[i];
+		const uint64_t pri = prev.pri[i];
+		V2 r1[2], r2[2]; double nm[2], tm[2], bo[2], bi[2], jn[2], jt[2], jb[2]; uint64_t hs[2];
+#pragma unroll
+		for(int k = 0; k < 2; k++){
+			int p = CIDX(prev, i, k);
+			r1[k] = prev.r1[p]; r2[k] = prev.r2[p];
+			nm[k] = prev.nmass[p]; tm[k] = prev.tmass[p]; bo[k] = prev.bounce[p]; bi[k] = prev.bias[p];
+			jn[k] = prev.jn[p]; jt[k] = prev.jt[p]; jb[k] = prev.jb[p];
+			hs[k] = prev.hash[p];
+		}
+		cur.key[slot] = key;
+		cur.sa[slot] = sa; cur.sb[slot] = sb; cur.ba[slot] = ba_; cur.bb[slot] = bb_;
+		cur.cnt[slot] = cnt;
 		cur.state[slot] = new_state;
-		cur.stamp[slot] = (new_active == 1 ? stamp : prev.stamp[i]);
+		cur.stamp[slot] = (new_active == 1 ? stamp : pstamp);
 		cur.active[slot] = new_active;
 		cur.seen[slot] = 0;
-		cur.gjkid[slot] = prev.gjkid[i];
-		cur.n[slot] = prev.n[i]; cur.e[slot] = prev.e[i]; cur.u[slot] = prev.u[i]; cur.svr[slot] = prev.svr[i];
+		cur.gjkid[slot] = gjkid;
+		cur.n[slot] = n; cur.e[slot] = e; cur.u[slot] = u; cur.svr[slot] = svr;
 		cur.colour[slot] = -1;
-		cur.pri[slot] = prev.pri[i];
+		cur.pri[slot] = pri;
 		cur.hint[slot] = -1;
+#pragma unroll
 		for(int k = 0; k < 2; k++){
-			int c = CIDX(cur, slot, k), p = CIDX(prev, i, k);
-			cur.r1[c] = prev.r1[p]; cur.r2[c] = prev.r2[p];
-			cur.nmass[c] = prev.nmass[p]; cur.tmass[c] = prev.tmass[p]; cur.bounce[c] = prev.bounce[p]; cur.bias[c] = prev.bias[p];
-			cur.jn[c] = prev.jn[p]; cur.jt[c] = prev.jt[p]; cur.jb[c] = prev.jb[p];
-			cur.hash[c] = prev.hash[p];
+			int c = CIDX(cur, slot, k);
+			cur.r1[c] = r1[k]; cur.r2[c] = r2[k];
+			cur.nmass[c] = nm[k]; cur.tmass[c] = tm[k]; cur.bounce[c] = bo[k]; cur.bias[c] = bi[k];
+			cur.jn[c] = jn[k]; cur.jt[c] = jt[k]; cur.jb[c] = jb[k];
+			cur.hash[c] = hs[k];
 		}
-		if(new_active == 1){ atomicAdd(&C->n_active, 1); atomicAdd(&C->n_contacts, prev.cnt[i]); }
+		if(new_active == 1){ atomicAdd(&C->n_active, 1); atomicAdd(&C->n_contacts, cnt); }
 		else atomicAdd(&C->n_cached, 1);
-		if(!table_insert(cur_table, prev.key[i], slot)) atomicOr((unsigned *)&C->overflow, 4u);
+		if(!table_insert(cur_table, key, slot)) atomicOr((unsigned *)&C->overflow, 4u);
 	}
 }
 

@@ -161,7 +161,8 @@ __device__ __forceinline__ int ld_cg_i(const int *p){ return __ldcg(p); }
 static inline int ld_cg_i(const int *p){ return *p; }
 #endif
 
-// pack the children's boxes / skip keys / space ranges next to their parent (traversal layout)
+// pack the children's boxes / skip keys / space ranges next to their parent (traversal layout).  A separate pass:
+// written from inside the refit's upward walk it lengthened that latency chain by more than this kernel costs.
 __global__ void k_bvh_pack(DBvh T)
 {
 	int i = CPB_TID;

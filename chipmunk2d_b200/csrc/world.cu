@@ -22,6 +22,12 @@ emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 #else
 unsigned long long g_cpb_launches = 0;
 #endif
+#ifndef CPB_CARRY_BLOCK
+#define CPB_CARRY_BLOCK 128
+#endif
+#ifndef CPB_CARRY_CTAS
+#define CPB_CARRY_CTAS 16
+#endif
 #define CPB_SL_MAX_SHAPES 512          // a space up to this many shapes is broadphased all-pairs in one CTA (k_sl_pairs)
 #define CPB_SL_MAX_SMEM (200*1024)   // shared memory a space's velocity sectors may take in k_sl_solve
 
@@ -928,8 +934,8 @@ static int step_phase_b(cpb200_world *w)
 	STAGE_END(w, ST_ISLANDS);
 
 	{
-		int g = std::min(grid_for(Ap.cap, 128), wide);
-		LAUNCH(k_arb_carry, g, 128, st, B, Ap, Ac, Tc, (const DSpace *)w->d_spaces, w->stamp, w->C);
+		int g = std::min(grid_for(Ap.cap, CPB_CARRY_BLOCK), w->sm_count*CPB_CARRY_CTAS);
+		LAUNCH(k_arb_carry, g, CPB_CARRY_BLOCK, st, B, Ap, Ac, Tc, (const DSpace *)w->d_spaces, w->stamp, w->C);
 	}
 	STAGE_END(w, ST_CARRY);
 
