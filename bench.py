@@ -111,25 +111,44 @@ SETTLE = {"pile1m": 30, "pile1m_sleep": 30, "batch": 300, "c1": 300, "c2": 300, 
 
 
 def cpu_baseline_sample(workload, steps, warmup):
-    """The unmodified reference (oracle/_ref) on a bounded sample of the workload, one thread."""
+    """The unmodified reference (oracle/_ref) on a bounded sample of the workload.  A single space runs on one
+    thread (the reference's own 2-thread cpHastySpace is slower); independent spaces (the batched
+    workload) run one cpSpace per host core over all cores -- ctypes releases the GIL inside the library."""
     from oracle import ref as oref
     if not oref.available():
         return None
+    cores = max(1, os.cpu_count() or 1)
     scenes, cfg = build_scenes(workload, 0, for_reference=True)
+    if workload == "batch" and cores > 1:
+        from chipmunk2d_b200.scenes import batched_demo_scenes
+        scenes = batched_demo_scenes(max(64, 8 * cores))
     r = oref.Ref()
     settle = SETTLE.get(workload, 0)
     spaces = [r.load(sc.blob) for sc in scenes]
     dt = scenes[0].dt
     nb = sum(sc.n_dynamic() for sc in scenes)
-    for s in spaces:
-        s.step(dt, settle + warmup)     # same untimed settling as the GPU arm, so both time the settled workload
-    t = sum(s.time_steps(dt, steps) for s in spaces)
+    threads = cores if len(spaces) > 1 else 1
+
+    def run(fn):
+        if threads == 1:
+            return [fn(s) for s in spaces]
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            return list(ex.map(fn, spaces))
+
+    run(lambda s: s.step(dt, settle + warmup))     # same untimed settling as the GPU arm: both time the settled workload
+    t0 = time.perf_counter()
+    per_space = run(lambda s: s.time_steps(dt, steps))
+    wall = time.perf_counter() - t0
+    t = wall if threads > 1 else sum(per_space)
     contacts = sum(s.counts()["contacts"] for s in spaces)
     for s in spaces:
         s.space = None  # leak: tearing a 20k-body reference space down is O(n^2)
-    return {"value": nb * steps / t, "unit": "body-steps/s", "cores": 1, "kind": "reference",
-            "sample": "%s at %d bodies (%d spaces), %d settle + %d warm-up + %d timed cpSpaceStep, gcc -O2 -ffp-contract=off no fast-math, 1 thread (cpHastySpace's 2 threads are slower, BASELINE.md)" % (
-                cfg["workload"], nb, len(scenes), settle, warmup, steps),
+    how = ("1 thread (cpHastySpace's 2 threads are slower, BASELINE.md)" if threads == 1 else
+           "%d host threads, one independent cpSpace each at a time (wall clock over the pool)" % threads)
+    return {"value": nb * steps / t, "unit": "body-steps/s", "cores": threads, "kind": "reference",
+            "sample": "%s at %d bodies (%d spaces), %d settle + %d warm-up + %d timed cpSpaceStep, gcc -O2 -ffp-contract=off no fast-math, %s" % (
+                cfg["workload"], nb, len(scenes), settle, warmup, steps, how),
             "ms_per_step": 1000.0 * t / steps, "contacts_per_step": contacts}
 
 
