@@ -455,6 +455,26 @@ extern "C" int cpb200_world_set_body_forces(cpb200_world *w, int first, int n, c
 	return world_sync(w);
 }
 
+__global__ void k_touch_bodies(DBodies B, const int *__restrict__ idx, int n)
+{
+	int k = CPB_TID;
+	if(k >= n) return;
+	int i = idx[k];
+	if(i >= 0 && i < B.n && !B.sleeping[i]) B.idle[i] = 0.0;
+}
+
+extern "C" int cpb200_world_touch_bodies(cpb200_world *w, int n, const int32_t *indices)
+{
+	if(!w || n < 0 || (n > 0 && !indices)){ cpb_set_error("bad arguments"); return -1; }
+	if(n == 0) return 0;
+	cudaSetDevice(w->device);
+	size_t bytes = sizeof(int32_t)*(size_t)n;
+	if(stage_reserve(w, bytes)) return -1;
+	CPB_CHECK(cudaMemcpyAsync(w->d_stage, indices, bytes, cudaMemcpyHostToDevice, w->stream));
+	LAUNCH(k_touch_bodies, grid_for(n, 256), 256, w->stream, w->B, (const int *)w->d_stage, n);
+	return world_sync(w);
+}
+
 extern "C" int cpb200_world_reserve(cpb200_world *w, int max_pairs, int max_arbiters)
 {
 	if(!w) return -1;

@@ -408,7 +408,11 @@ cpBodyActivate(cpBody *body)
 	cpSpace *space = body->space;
 	if(space == NULL){ body->idleTime = 0.0; return; }
 	cpBodySyncForRead(body);
-	if(body->idleTime != 0.0){ body->idleTime = 0.0; space->bodiesDirty = cpTrue; }
+	if(body->idleTime != 0.0){
+		/* an awake body only needs its idle timer restarted on the device: a 4-byte index, not a re-upload */
+		body->idleTime = 0.0;
+		if(body->sleepRoot) space->bodiesDirty = cpTrue; else { body->idleReset = cpTrue; space->touchDirty = cpTrue; }
+	}
 	cpBody *root = body->sleepRoot;
 	if(root){
 		/* wake the whole sleeping component */

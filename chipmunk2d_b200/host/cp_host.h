@@ -37,6 +37,7 @@ struct cpBody {
 	cpShape *shapeList;
 	cpConstraint *constraintList;
 	cpFloat idleTime;          /* INFINITY <=> static (cpBody.c:136-146) */
+	cpBool idleReset;          /* activated while awake since the last upload: the device restarts its idle timer */
 	cpBody *sleepRoot;         /* non-NULL <=> asleep; all members of a sleeping component share it */
 	int index;                 /* slot in space->bodies == device body index, -1 when not in a space */
 	int firstArb;              /* head of this body's arbiter list in space->arbs, -1 = none */
@@ -149,10 +150,14 @@ struct cpSpace {
 	cpBool topologyDirty;      /* bodies/shapes/joints added, removed or re-parameterised */
 	cpBool bodiesDirty;        /* kinematic state of some body changed on the host */
 	cpBool forcesDirty;        /* only forces / torques changed: uploaded as 24 bytes per body */
+	cpBool touchDirty;         /* some awake body was activated: its idle timer restarts on the device */
 	cpBool paramsDirty;
 	cpBool hostStale;          /* device has newer body state than the mirrors */
 	cpBool bbStale, arbStale, jointStale;
 	cpArbiter *arbs; int nArbs, capArbs;
+	/* user data attached to arbiters (cpArbiterSetUserData) survives the re-download of the mirrors: kept by
+	 * unordered shape pair until the pair separates, like the reference keeps it in the cached arbiter */
+	struct cpArbData { cpHashValue lo, hi; cpDataPointer data; } *arbData; int nArbData, capArbData;
 
 	/* per-step exchange buffers, page-locked, grown on demand and kept for the life of the space */
 	void *xferStates; size_t xferStatesBytes;

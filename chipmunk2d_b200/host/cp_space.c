@@ -91,7 +91,7 @@ cpSpaceDestroy(cpSpace *space)
 	if(space->world) cpb200_world_destroy(space->world);
 	space->world = NULL;
 	cpfree(space->bodies); cpfree(space->shapes); cpfree(space->constraints);
-	cpfree(space->handlers); cpfree(space->postStep); cpfree(space->arbs);
+	cpfree(space->handlers); cpfree(space->postStep); cpfree(space->arbs); cpfree(space->arbData); space->arbData = NULL;
 	space->bodies = NULL; space->shapes = NULL; space->constraints = NULL;
 	space->handlers = NULL; space->postStep = NULL; space->arbs = NULL;
 }
@@ -576,6 +576,15 @@ sync_to_device(cpSpace *space)
 		upload_forces(space);
 		space->forcesDirty = cpFalse;
 	}
+	if(space->touchDirty){
+		/* bodies activated while awake (cpBodySetForce etc. call cpBodyActivate): restart their idle timers */
+		int n = space->nBodies, m = 0;
+		int32_t *idx = (int32_t *)cpcalloc((size_t)(n > 0 ? n : 1), sizeof(int32_t));
+		for(int i = 0; i < n; i++){ cpBody *b = space->bodies[i]; if(b->idleReset){ b->idleReset = cpFalse; idx[m++] = i; } }
+		if(cpb200_world_touch_bodies(space->world, m, idx)) cpEngineError("idle timer reset");
+		cpfree(idx);
+		space->touchDirty = cpFalse;
+	}
 	if(space->paramsDirty){ upload_params(space); space->paramsDirty = cpFalse; }
 }
 
@@ -649,6 +658,16 @@ void
 cpSpaceFetchArbitersB200(cpSpace *space)
 {
 	space->arbStale = cpFalse;
+	/* remember the user data of the outgoing mirrors */
+	space->nArbData = 0;
+	for(int i = 0; i < space->nArbs; i++){
+		cpArbiter *arb = &space->arbs[i];
+		if(arb->data == NULL || arb->state == CP_ARBITER_STATE_CACHED) continue;   /* separated pairs drop theirs */
+		space->arbData = (struct cpArbData *)grow(space->arbData, &space->capArbData, space->nArbData + 1, sizeof(struct cpArbData));
+		cpHashValue ha = arb->a->hashid, hb = arb->b->hashid;
+		struct cpArbData *d = &space->arbData[space->nArbData++];
+		d->lo = (ha < hb ? ha : hb); d->hi = (ha < hb ? hb : ha); d->data = arb->data;
+	}
 	for(int i = 0; i < space->nBodies; i++) space->bodies[i]->firstArb = -1;
 	space->nArbs = 0;
 	if(!space->world || space->topologyDirty) return;
@@ -677,6 +696,10 @@ cpSpaceFetchArbitersB200(cpSpace *space)
 		arb->stamp = r->stamp;
 		arb->active = r->active;
 		arb->record = r->record;
+		if(space->nArbData > 0){
+			cpHashValue ha = arb->a->hashid, hb = arb->b->hashid, lo = (ha < hb ? ha : hb), hi = (ha < hb ? hb : ha);
+			for(int k = 0; k < space->nArbData; k++){ if(space->arbData[k].lo == lo && space->arbData[k].hi == hi){ arb->data = space->arbData[k].data; break; } }
+		}
 		for(int k = 0; k < 2; k++){
 			struct cpContact *c = &arb->contacts[k];
 			c->r1 = cpv(r->contacts[k].r1[0], r->contacts[k].r1[1]);

@@ -512,18 +512,21 @@ cpb_scene_shape_query(cpSpace *space, int kind, double x, double y, double angle
 /* ---- collision-handler semantics (cpSpaceStep.c:257-285, cpArbiter.c:46-50, 97-143), same code against
  * either library: one dynamic ball over static geometry, so the solver order cannot matter and the
  * trajectories of the two libraries agree to rounding.
- * out[12] = nBegin nPreSolve nPostSolve nSeparate  p.x p.y v.x v.y w  maxHeightAfterFirstContact  firstContactStep  spare */
-typedef struct hs_ctx { int which; int nBegin, nPre, nPost, nSep; int step, firstStep; } hs_ctx;
+ * out[12] = nBegin nPreSolve nPostSolve nSeparate  p.x p.y v.x v.y w  maxHeightAfterFirstContact  firstContactStep
+ *           callbacks that found the arbiter user data set in begin (scenario 10) */
+typedef struct hs_ctx { int which; int nBegin, nPre, nPost, nSep; int step, firstStep; int nData; } hs_ctx;
 static cpBool hs_begin(cpArbiter *arb, cpSpace *space, void *data){
 	hs_ctx *c = (hs_ctx *)data;
 	c->nBegin++;
 	if(c->firstStep < 0) c->firstStep = c->step;
 	if(c->which == 2) return cpFalse;                 /* ignored until the shapes separate */
+	if(c->which == 10) cpArbiterSetUserData(arb, data);   /* must still be there in every later callback of this pair */
 	return cpTrue;
 }
 static cpBool hs_presolve(cpArbiter *arb, cpSpace *space, void *data){
 	hs_ctx *c = (hs_ctx *)data;
 	c->nPre++;
+	if(c->which == 10 && cpArbiterGetUserData(arb) == data) c->nData++;
 	switch(c->which){
 	case 1: return cpFalse;                            /* never solved: the ball falls through */
 	case 3: cpArbiterSetRestitution(arb, 1.0); break;  /* bouncy although both shapes have e = 0 */
@@ -534,7 +537,7 @@ static cpBool hs_presolve(cpArbiter *arb, cpSpace *space, void *data){
 	}
 	return cpTrue;
 }
-static void hs_postsolve(cpArbiter *arb, cpSpace *space, void *data){ ((hs_ctx *)data)->nPost++; }
+static void hs_postsolve(cpArbiter *arb, cpSpace *space, void *data){ hs_ctx *c = (hs_ctx *)data; c->nPost++; if(c->which == 10 && cpArbiterGetUserData(arb) == data) c->nData++; }
 static void hs_separate(cpArbiter *arb, cpSpace *space, void *data){ ((hs_ctx *)data)->nSep++; }
 
 CPB_EXPORT int
@@ -562,7 +565,7 @@ cpb_scene_handler_scenario(int which, int n_steps, double *out12)
 	if(which == 6){ cpBodySetPosition(ball, cpv(0.0, -40.0)); cpBodySetVelocity(ball, cpv(0.0, 160.0)); }
 	else cpBodySetPosition(ball, cpv(0.0, 50.0));
 
-	hs_ctx ctx = {which, 0, 0, 0, 0, 0, -1};
+	hs_ctx ctx = {which, 0, 0, 0, 0, 0, -1, 0};
 	cpCollisionHandler *h = (which == 8 ? cpSpaceAddWildcardHandler(space, 2)
 	                       : which == 9 ? cpSpaceAddDefaultCollisionHandler(space)
 	                                    : cpSpaceAddCollisionHandler(space, 1, 2));
@@ -578,7 +581,7 @@ cpb_scene_handler_scenario(int which, int n_steps, double *out12)
 	cpVect p = cpBodyGetPosition(ball), v = cpBodyGetVelocity(ball);
 	out12[0] = ctx.nBegin; out12[1] = ctx.nPre; out12[2] = ctx.nPost; out12[3] = ctx.nSep;
 	out12[4] = p.x; out12[5] = p.y; out12[6] = v.x; out12[7] = v.y; out12[8] = cpBodyGetAngularVelocity(ball);
-	out12[9] = (maxh > -1e299 ? maxh : 0.0); out12[10] = ctx.firstStep; out12[11] = 0.0;
+	out12[9] = (maxh > -1e299 ? maxh : 0.0); out12[10] = ctx.firstStep; out12[11] = ctx.nData;
 	cpSpaceRemoveShape(space, bs); cpSpaceRemoveBody(space, ball); cpSpaceRemoveShape(space, ground);
 	if(floor2){ cpSpaceRemoveShape(space, floor2); cpShapeFree(floor2); }
 	cpShapeFree(bs); cpBodyFree(ball); cpShapeFree(ground);

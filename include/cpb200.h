@@ -189,6 +189,9 @@ CPB200_API int cpb200_world_set_body_forces(cpb200_world *w, int first, int n, c
  * such a buffer is one DMA at full link speed, without the driver's bounce copy.  NULL on failure. */
 CPB200_API void *cpb200_host_alloc(size_t bytes);
 CPB200_API void cpb200_host_free(void *p);
+/* cpBodyActivate on bodies that are awake (cpSpaceComponent.c:113-119): their idle timers restart.  Waking a
+ * SLEEPING body changes the contact graph and goes through cpb200_world_update_bodies instead. */
+CPB200_API int cpb200_world_touch_bodies(cpb200_world *w, int n, const int32_t *indices);
 /* Pre-size device buffers (pairs, arbiters) for at least this many; 0 keeps the default. */
 CPB200_API int cpb200_world_reserve(cpb200_world *w, int max_pairs, int max_arbiters);
 

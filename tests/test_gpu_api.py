@@ -108,14 +108,15 @@ def test_structural_edit_keeps_warm_start():
     assert np.nanmax(np.abs(after[1:, 0:2] - before[1:, 0:2])) < 1.0
 
 
-@pytest.mark.parametrize("which", range(10))
+@pytest.mark.parametrize("which", range(11))
 def test_collision_handler_semantics_match_reference(ref, which):
     """begin/preSolve return values, cpArbiterIgnore, cpArbiterSet{Restitution,Friction,SurfaceVelocity}, sensors,
     wildcard and default handlers take effect inside the step they are called in (split device step), with the
     reference's callback counts and the reference's trajectory (scenes/scene_io.c cpb_scene_handler_scenario:
     one ball over static geometry, so the solver order cannot matter).
     0 plain, 1 preSolve false, 2 begin false, 3 restitution, 4 conveyor, 5 sensor, 6 one-way platform,
-    7 ignore from the 10th preSolve, 8 wildcard handler, 9 default handler."""
+    7 ignore from the 10th preSolve, 8 wildcard handler, 9 default handler, 10 arbiter user data set in begin is
+    seen by every later preSolve/postSolve of the pair."""
     import ctypes as C
     dp = C.POINTER(C.c_double)
     out = []
