@@ -24,11 +24,25 @@ enum {
 };
 
 struct cpBody {
+	/* Field order is the access pattern of the per-body API loops a host runs every step (cpBodySetForce /
+	 * cpBodyApplyForce* on every body, then cpBodyGetPosition / GetVelocity on every body): what those calls
+	 * touch sits in the first two cache lines, so a million-body loop streams 128 B per body, not the whole struct. */
 	cpSpace *space;
-	cpFloat m, m_inv, i, i_inv;
-	cpVect cog, p, v, f;
-	cpFloat a, w, t;
+	cpFloat idleTime;          /* INFINITY <=> static (cpBody.c:136-146) */
+	cpBody *sleepRoot;         /* non-NULL <=> asleep; all members of a sleeping component share it */
+	cpFloat m;
+	cpVect f;
+	cpFloat t;
+	cpBool idleReset;          /* activated while awake since the last upload: the device restarts its idle timer */
+	unsigned fetchStamp;       /* == space->fetchStamp <=> this mirror holds the state of the last download */
+	/* second line: what the getters read */
 	cpTransform transform;
+	cpVect p;
+	/* the rest */
+	cpVect v;
+	cpFloat a, w;
+	cpFloat m_inv, i, i_inv;
+	cpVect cog;
 	cpVect v_bias;
 	cpFloat w_bias;
 	cpDataPointer userData;
@@ -36,9 +50,6 @@ struct cpBody {
 	cpBodyPositionFunc position_func;
 	cpShape *shapeList;
 	cpConstraint *constraintList;
-	cpFloat idleTime;          /* INFINITY <=> static (cpBody.c:136-146) */
-	cpBool idleReset;          /* activated while awake since the last upload: the device restarts its idle timer */
-	cpBody *sleepRoot;         /* non-NULL <=> asleep; all members of a sleeping component share it */
 	int index;                 /* slot in space->bodies == device body index, -1 when not in a space */
 	int firstArb;              /* head of this body's arbiter list in space->arbs, -1 = none */
 };
@@ -152,7 +163,9 @@ struct cpSpace {
 	cpBool forcesDirty;        /* only forces / torques changed: uploaded as 24 bytes per body */
 	cpBool touchDirty;         /* some awake body was activated: its idle timer restarts on the device */
 	cpBool paramsDirty;
-	cpBool hostStale;          /* device has newer body state than the mirrors */
+	cpBool hostStale;          /* device has newer body state than the last download */
+	unsigned fetchStamp;       /* bumped by every download; bodies unpack their record on first access */
+	cpBool someMirrorsStale;   /* a download happened and not every body has unpacked its record yet */
 	cpBool bbStale, arbStale, jointStale;
 	cpArbiter *arbs; int nArbs, capArbs;
 	/* user data attached to arbiters (cpArbiterSetUserData) survives the re-download of the mirrors: kept by
@@ -185,7 +198,16 @@ void cpEngineError(const char *what);
 static inline cpConstraint *cpConstraintNext(cpConstraint *node, cpBody *body){ return (node->a == body ? node->next_a : node->next_b); }
 
 /* make sure the mirrors of `body` are current before the host reads or edits them */
-static inline void cpBodySyncForRead(const cpBody *body){ if(body->space && body->space->hostStale) cpSpaceFetchBodiesB200(body->space); }
+void cpSpaceDownloadBodiesB200(cpSpace *space);
+void cpBodyUnpackB200(cpBody *body);
+void cpSpaceUnpackAllB200(cpSpace *space);
+/* The body state comes back from the device in one transfer and every mirror takes its record right away, split
+ * over the host cores (cpSpaceUnpackAllB200).  Unpacking lazily, per body on first access, measured 20% SLOWER
+ * end to end at 1M bodies: it serialises a million 25 ns unpacks onto the caller's thread. */
+static inline void cpBodySyncForRead(const cpBody *body){
+	cpSpace *space = body->space;
+	if(space && space->hostStale) cpSpaceFetchBodiesB200(space);
+}
 
 #define cpAssertSpaceUnlocked(space) \
 	cpAssertHard(!(space)->locked, \

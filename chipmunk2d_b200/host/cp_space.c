@@ -82,6 +82,7 @@ void
 cpSpaceDestroy(cpSpace *space)
 {
 	/* like the reference, the space never owns bodies/shapes/constraints (cpSpace.c:188-229) */
+	if(space->world) cpSpaceFetchBodiesB200(space);   /* the bodies outlive the space: leave them their last state */
 	for(int i = 0; i < space->nBodies; i++){ space->bodies[i]->space = NULL; space->bodies[i]->index = -1; }
 	for(int i = 0; i < space->nShapes; i++){ space->shapes[i]->space = NULL; space->shapes[i]->index = -1; }
 	for(int i = 0; i < space->nConstraints; i++){ space->constraints[i]->space = NULL; space->constraints[i]->index = -1; }
@@ -215,6 +216,8 @@ cpSpaceAddBody(cpSpace *space, cpBody *body)
 	cpAssertHard(body->space != space, "You have already added this body to this space. You must not add it a second time.");
 	cpAssertHard(!body->space, "You have already added this body to another space. You cannot add it to a second.");
 	cpAssertSpaceUnlocked(space);
+	cpSpaceFetchBodiesB200(space);          /* mirrors current before the index space changes */
+	body->fetchStamp = space->fetchStamp;   /* a newcomer has no record in the last download */
 	space->bodies = (cpBody **)grow(space->bodies, &space->capBodies, space->nBodies + 1, sizeof(cpBody *));
 	body->index = space->nBodies;
 	space->bodies[space->nBodies++] = body;
@@ -271,7 +274,7 @@ cpSpaceAddConstraint(cpSpace *space, cpConstraint *constraint)
 static void
 sync_before_edit(cpSpace *space)
 {
-	if(space->hostStale) cpSpaceFetchBodiesB200(space);
+	cpSpaceFetchBodiesB200(space);
 	if(space->jointStale) cpSpaceFetchJointsB200(space);
 	space->arbStale = cpTrue;
 }
@@ -347,7 +350,14 @@ void
 cpSpaceEachBody(cpSpace *space, cpSpaceBodyIteratorFunc func, void *data)
 {
 	space->locked++;
-	for(int i = 1; i < space->nBodies; i++) func(space->bodies[i], data);
+	/* the callback usually touches the first lines of each body, which the parallel mirror update left in other
+	 * cores' caches: ask for them a few bodies ahead */
+	cpBody **bodies = space->bodies;
+	const int n = space->nBodies;
+	for(int i = 1; i < n; i++){
+		if(i + 8 < n){ const char *nx = (const char *)bodies[i + 8]; __builtin_prefetch(nx, 1); __builtin_prefetch(nx + 64, 0); }
+		func(bodies[i], data);
+	}
 	space->locked--;
 }
 
@@ -560,7 +570,7 @@ sync_to_device(cpSpace *space)
 {
 	ensure_world(space);
 	if(space->topologyDirty){
-		if(space->hostStale) cpSpaceFetchBodiesB200(space);
+		cpSpaceFetchBodiesB200(space);
 		if(space->jointStale) cpSpaceFetchJointsB200(space);
 		upload_bodies(space, cpTrue);
 		upload_shapes(space);
@@ -569,10 +579,12 @@ sync_to_device(cpSpace *space)
 		space->bodiesDirty = cpFalse;
 		space->forcesDirty = cpFalse;
 	} else if(space->bodiesDirty){
+		cpSpaceFetchBodiesB200(space);
 		upload_bodies(space, cpFalse);
 		space->bodiesDirty = cpFalse;
 		space->forcesDirty = cpFalse;
 	} else if(space->forcesDirty){
+		cpSpaceUnpackAllB200(space);   /* forces the last step consumed are zeroed in the mirrors first */
 		upload_forces(space);
 		space->forcesDirty = cpFalse;
 	}
@@ -591,36 +603,63 @@ sync_to_device(cpSpace *space)
 /* make the device world current with every host-side edit (used by the query entry points) */
 void cpSpacePrepareDeviceB200(cpSpace *space){ sync_to_device(space); }
 
+/* one transfer: the state of every body into the space's page-locked buffer */
 void
-cpSpaceFetchBodiesB200(cpSpace *space)
+cpSpaceDownloadBodiesB200(cpSpace *space)
 {
 	if(!space->hostStale || !space->world){ space->hostStale = cpFalse; return; }
 	space->hostStale = cpFalse;
 	int n = space->nBodies;
 	cpb200_body_state *st = (cpb200_body_state *)xfer_buffer(&space->xferStates, &space->xferStatesBytes, (size_t)n*sizeof(cpb200_body_state));
 	if(cpb200_world_get_bodies(space->world, 0, n, st)) cpEngineError("body download");
-	const cpBool forcesDirty = space->forcesDirty;
-	#pragma omp parallel for schedule(static) num_threads(host_threads(space, n))
-	for(int i = 0; i < n; i++){
-		cpBody *b = space->bodies[i];
-		const cpb200_body_state *s = &st[i];
-		if(b->idleTime == INFINITY) continue; /* static bodies never change on the device */
-		b->p = cpv(s->p[0], s->p[1]);
-		b->v = cpv(s->v[0], s->v[1]);
-		b->a = s->a;
-		b->w = s->w;
-		cpVect rot = cpv(s->rot[0], s->rot[1]), c = b->cog;
-		b->transform = cpTransformNewTranspose(
-			rot.x, -rot.y, b->p.x - (c.x*rot.x - c.y*rot.y),
-			rot.y,  rot.x, b->p.y - (c.x*rot.y + c.y*rot.x));
-		b->idleTime = s->idle_time;
-		b->sleepRoot = (s->sleeping && s->sleep_group >= 0 && s->sleep_group < n ? space->bodies[s->sleep_group] : NULL);
-		if(!s->sleeping){
-			/* the step consumed the forces and the bias velocities (cpBody.c:505-507, 518-519) */
-			if(b->m != INFINITY && !forcesDirty){ b->f = cpvzero; b->t = 0.0; }
-			b->v_bias = cpvzero; b->w_bias = 0.0;
-		}
+	space->fetchStamp++;
+	space->someMirrorsStale = cpTrue;
+}
+
+/* this body's record of the last download into its mirror */
+void
+cpBodyUnpackB200(cpBody *b)
+{
+	cpSpace *space = b->space;
+	b->fetchStamp = space->fetchStamp;
+	if(b->idleTime == INFINITY || space->xferStates == NULL || b->index < 0) return; /* static bodies never change on the device */
+	const cpb200_body_state *s = (const cpb200_body_state *)space->xferStates + b->index;
+	b->p = cpv(s->p[0], s->p[1]);
+	b->v = cpv(s->v[0], s->v[1]);
+	b->a = s->a;
+	b->w = s->w;
+	cpVect rot = cpv(s->rot[0], s->rot[1]), c = b->cog;
+	b->transform = cpTransformNewTranspose(
+		rot.x, -rot.y, b->p.x - (c.x*rot.x - c.y*rot.y),
+		rot.y,  rot.x, b->p.y - (c.x*rot.y + c.y*rot.x));
+	b->idleTime = s->idle_time;
+	b->sleepRoot = (s->sleeping && s->sleep_group >= 0 && s->sleep_group < space->nBodies ? space->bodies[s->sleep_group] : NULL);
+	if(!s->sleeping){
+		/* the step consumed the forces and the bias velocities (cpBody.c:505-507, 518-519); a force set after
+		 * the step went through cpBodyActivate, i.e. through this function, BEFORE it was written */
+		if(b->m != INFINITY){ b->f = cpvzero; b->t = 0.0; }
+		b->v_bias = cpvzero; b->w_bias = 0.0;
 	}
+}
+
+/* every mirror current (before anything walks all bodies: uploads, structural edits, arbiter threading) */
+void
+cpSpaceUnpackAllB200(cpSpace *space)
+{
+	if(!space->someMirrorsStale) return;
+	int n = space->nBodies;
+	const unsigned stamp = space->fetchStamp;
+	cpBody **bodies = space->bodies;
+	#pragma omp parallel for schedule(static) num_threads(host_threads(space, n))
+	for(int i = 0; i < n; i++){ if(bodies[i]->fetchStamp != stamp) cpBodyUnpackB200(bodies[i]); }
+	space->someMirrorsStale = cpFalse;
+}
+
+void
+cpSpaceFetchBodiesB200(cpSpace *space)
+{
+	if(space->hostStale) cpSpaceDownloadBodiesB200(space);
+	cpSpaceUnpackAllB200(space);
 }
 
 void cpSpaceSyncB200(cpSpace *space){ cpSpaceFetchBodiesB200(space); }
@@ -679,7 +718,7 @@ cpSpaceFetchArbitersB200(cpSpace *space)
 	n = cpb200_world_get_arbiters(space->world, n, recs, 0);
 	if(n < 0) cpEngineError("arbiter download");
 	space->arbs = (cpArbiter *)grow(space->arbs, &space->capArbs, n, sizeof(cpArbiter));
-	if(space->hostStale) cpSpaceFetchBodiesB200(space);
+	cpSpaceFetchBodiesB200(space);
 	for(int i = 0; i < n; i++){
 		const cpb200_arbiter *r = &recs[i];
 		if(r->shape_a < 0 || r->shape_a >= space->nShapes || r->shape_b < 0 || r->shape_b >= space->nShapes) continue;
