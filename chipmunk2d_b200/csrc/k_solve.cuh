@@ -767,9 +767,6 @@ template<bool SPACE_LOCAL> __global__ void __launch_bounds__(256, CPB_SOLVE_MIN_
 				if(pr < r1){ pba = ROW_LD(&R.ba[pr]); pbb = ROW_LD(&R.bb[pr]); pcnt = ROW_LD(&R.cnt[pr]); row_prefetch(R, pr); } else pr = -1;
 				solve_row_idx(vg, B, R, r, ba, bb, cnt, mode, dt_coef);
 			}
-#ifdef CPB_EXP_NOJOINT
-			pq = -1;
-#endif
 			while(pq >= 0){
 				int j = pj, a = pja, b = pjb;
 				pq += nth;
@@ -778,11 +775,7 @@ template<bool SPACE_LOCAL> __global__ void __launch_bounds__(256, CPB_SOLVE_MIN_
 			}
 			int cn = (c + 1 < nreg ? c + 1 : 0);
 			if(c + 1 < nreg || pass < iterations) PREFETCH_PHASE(cn);
-#ifdef CPB_EXP_NOBAR   // timing experiment only (results are wrong): what do the barriers + tails cost?
-			__syncthreads();
-#else
 			GRID_SYNC();
-#endif
 		}
 		if(has_overflow){
 			if(tid == 0) solve_overflow(B, R, J, K, mode, dt, dt_coef);
