@@ -312,8 +312,10 @@ CPB_DEVICE void st_vel(double4 *p, double4 v){ st4_cg(p, v); }
 #else
 #define CPB_MEMBER __device__ __forceinline__
 #endif
-struct VelGlobal {
-	static const bool STREAM = true;     // rows go past the L2 (see ROW_LD)
+// STREAM_ROWS: rows larger than the L2 can keep next to the velocities go past it (evict-first, see ROW_LD);
+// smaller row sets (mid-size scenes) use the default policy and are served from L2 from the second pass on.
+template<bool STREAM_ROWS> struct VelGlobalT {
+	static const bool STREAM = STREAM_ROWS;
 	static const bool EAGER = false;
 	double4 *V, *VB;
 	CPB_MEMBER double4 ldV(int b) const { return ld_vel(&V[b]); }
@@ -321,6 +323,7 @@ struct VelGlobal {
 	CPB_MEMBER void stV(int b, double4 v) const { st_vel(&V[b], v); }
 	CPB_MEMBER void stVB(int b, double4 v) const { st_vel(&VB[b], v); }
 };
+typedef VelGlobalT<true> VelGlobal;
 struct VelShared {
 	static const bool STREAM = false;    // a space's rows are re-read by the same SM every pass: cache them
 #ifndef CPB_SL_EAGER
@@ -699,7 +702,7 @@ __device__ __forceinline__ unsigned long long global_ns(){ unsigned long long t;
 #endif
 
 // SPACE_LOCAL: colour only, then histogram the (space, colour) buckets for the space-local solver below.
-template<bool SPACE_LOCAL> __global__ void __launch_bounds__(256, CPB_SOLVE_MIN_BLOCKS) k_colour_solve(DBodies B, DArbs A, DJoints J, DRows R, DColour K, DCounters *C, unsigned *bar, DSpaceLocal SL, int use_hints, int iterations, double dt, double dt_coef)
+template<bool SPACE_LOCAL, bool STREAM_ROWS> __global__ void __launch_bounds__(256, CPB_SOLVE_MIN_BLOCKS) k_colour_solve(DBodies B, DArbs A, DJoints J, DRows R, DColour K, DCounters *C, unsigned *bar, DSpaceLocal SL, int use_hints, int iterations, double dt, double dt_coef)
 {
 	__shared__ int s_hist[2*CPB_MAX_COLOURS];
 	__shared__ int s_base[CPB_MAX_COLOURS];
@@ -750,11 +753,11 @@ template<bool SPACE_LOCAL> __global__ void __launch_bounds__(256, CPB_SOLVE_MIN_
 	int nreg = (ncol > CPB_OVERFLOW_COLOUR ? CPB_OVERFLOW_COLOUR : ncol);
 	bool has_overflow = (ncol > CPB_OVERFLOW_COLOUR);
 	const int jtid = nth - 1 - tid;
-	const VelGlobal vg = {B.V, B.VB};
+	const VelGlobalT<STREAM_ROWS> vg = {B.V, B.VB};
 	int pr = -1, pba = 0, pbb = 0, pcnt = 0;     // prefetched row
 	int pq = -1, pj = 0, pja = 0, pjb = 0;       // prefetched joint
 	#define PREFETCH_PHASE(c_) do { \
-		pr = s_cstart[c_] + tid; if(pr < s_cstart[(c_) + 1]){ pba = ROW_LD(&R.ba[pr]); pbb = ROW_LD(&R.bb[pr]); pcnt = ROW_LD(&R.cnt[pr]); row_prefetch(R, pr); } else pr = -1; \
+		pr = s_cstart[c_] + tid; if(pr < s_cstart[(c_) + 1]){ pba = row_ld<STREAM_ROWS>(&R.ba[pr]); pbb = row_ld<STREAM_ROWS>(&R.bb[pr]); pcnt = row_ld<STREAM_ROWS>(&R.cnt[pr]); row_prefetch(R, pr); } else pr = -1; \
 		pq = s_jstart[c_] + jtid; if(pq < s_jstart[(c_) + 1]){ pj = J.row[pq]; pja = J.a[pj]; pjb = J.b[pj]; } else pq = -1; } while(0)
 	if(nreg > 0) PREFETCH_PHASE(0);
 	for(int pass = 0; pass <= iterations; pass++){
@@ -764,7 +767,7 @@ template<bool SPACE_LOCAL> __global__ void __launch_bounds__(256, CPB_SOLVE_MIN_
 			while(pr >= 0){
 				int r = pr, ba = pba, bb = pbb, cnt = pcnt;
 				pr += nth;
-				if(pr < r1){ pba = ROW_LD(&R.ba[pr]); pbb = ROW_LD(&R.bb[pr]); pcnt = ROW_LD(&R.cnt[pr]); row_prefetch(R, pr); } else pr = -1;
+				if(pr < r1){ pba = row_ld<STREAM_ROWS>(&R.ba[pr]); pbb = row_ld<STREAM_ROWS>(&R.bb[pr]); pcnt = row_ld<STREAM_ROWS>(&R.cnt[pr]); row_prefetch(R, pr); } else pr = -1;
 				solve_row_idx(vg, B, R, r, ba, bb, cnt, mode, dt_coef);
 			}
 			while(pq >= 0){

@@ -22,6 +22,10 @@ emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 #else
 unsigned long long g_cpb_launches = 0;
 #endif
+#define CPB_ROW_BYTES_EST 200                 // bytes of one solver row (one contact; two-contact rows are rarer)
+#ifndef CPB_L2_RESIDENT_BYTES
+#define CPB_L2_RESIDENT_BYTES (80u << 20)     // of the 126 MB L2: what a pass may occupy and still be served from it
+#endif
 #ifndef CPB_CARRY_BLOCK
 #define CPB_CARRY_BLOCK 128
 #endif
@@ -240,7 +244,7 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 		cudaDeviceProp prop;
 		if(cudaGetDeviceProperties(&prop, device) == cudaSuccess) w->sm_count = prop.multiProcessorCount;
 		int per_sm = 1;
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colour_solve<false>, 256, 0);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colour_solve<false, true>, 256, 0);
 		if(per_sm < 1) per_sm = 1;
 		if(per_sm > 4) per_sm = 4;
 		w->coop_blocks = w->sm_count*per_sm;
@@ -1011,7 +1015,11 @@ static int step_phase_b(cpb200_world *w)
 			size_t nbuckets = 2*(size_t)w->n_spaces*CPB_MAX_COLOURS + 2;
 			if(space_local) cudaMemsetAsync(SL.start, 0, sizeof(uint32_t)*nbuckets, st);
 			void *args[] = {&B, &Ac, &J, &R, &K, &C, &bar, &SL, &use_hints, &iterations, &dt, &dt_coef};
-			CPB_CHECK(cudaLaunchCooperativeKernel(space_local ? (void *)k_colour_solve<true> : (void *)k_colour_solve<false>, dim3(blocks), dim3(256), args, 0, st));
+			// rows + velocity sectors of one pass: stream the rows past the L2 only if they would not fit next to the velocities
+			const bool stream_rows = ((size_t)est_cons*(size_t)CPB_ROW_BYTES_EST + (size_t)nb*64 > (size_t)CPB_L2_RESIDENT_BYTES);
+			void *kernel = space_local ? (void *)k_colour_solve<true, true>
+			             : stream_rows ? (void *)k_colour_solve<false, true> : (void *)k_colour_solve<false, false>;
+			CPB_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(blocks), dim3(256), args, 0, st));
 			g_cpb_launches++;
 			if(space_local){
 				cpb_exclusive_scan(SL.start, SL.start, (int)nbuckets, w->sl_tmp, st);
