@@ -75,7 +75,7 @@ CPB_DEVICE uint32_t spread16(uint32_t x){
 	return x;
 }
 
-__global__ void k_morton(DShapes S, DBodies B, const double *__restrict__ bounds, uint64_t *keys, int *vals)
+__global__ void k_morton(DShapes S, DBodies B, const double *__restrict__ bounds, uint64_t *keys, int *vals, int drop_bits)
 {
 	int s = CPB_TID;
 	if(s >= S.n) return;
@@ -88,6 +88,9 @@ __global__ void k_morton(DShapes S, DBodies B, const double *__restrict__ bounds
 	if(!(fy == fy)) fy = 0.0;
 	uint32_t qx = (uint32_t)(fx*65535.0), qy = (uint32_t)(fy*65535.0);
 	uint32_t m = spread16(qx) | (spread16(qy) << 1);
+	// only as many Morton bits as the shape count needs (ties keep the upload order, Karras' index fallback handles them):
+	// the radix sort then skips the dropped low digits
+	m &= ~((1u << drop_bits) - 1u);
 	keys[s] = ((uint64_t)(uint32_t)B.space[S.body[s]] << 32) | (uint64_t)m;
 	vals[s] = s;
 }

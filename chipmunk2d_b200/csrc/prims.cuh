@@ -159,16 +159,16 @@ static inline size_t cpb_sort_tmp_elems(int n)
 	return (size_t)256*nblocks + cpb_scan_tmp_elems(256*nblocks);
 }
 
-// Sorts (keys, vals) by bits [0, bits) of the key; ping-pongs between the two buffer
+// Sorts (keys, vals) by bits [first_bit, bits) of the key (first_bit a multiple of 8; lower bits must be equal); ping-pongs between the two buffer
 // pairs and returns 0 if the result is in (keys_a, vals_a), 1 if in (keys_b, vals_b).
-static int cpb_radix_sort(uint64_t *keys_a, int *vals_a, uint64_t *keys_b, int *vals_b, int n, int bits, uint32_t *tmp, cudaStream_t st)
+static int cpb_radix_sort(uint64_t *keys_a, int *vals_a, uint64_t *keys_b, int *vals_b, int n, int bits, uint32_t *tmp, cudaStream_t st, int first_bit = 0)
 {
 	if(n <= 1) return 0;
 	int nblocks = cpb_div_up(n, CPB_SORT_TILE);
 	uint32_t *hist = tmp;
 	uint32_t *scan_tmp = tmp + (size_t)256*nblocks;
 	int cur = 0;
-	for(int shift = 0; shift < bits; shift += 8){
+	for(int shift = first_bit; shift < bits; shift += 8){
 		const uint64_t *ki = cur ? keys_b : keys_a; const int *vi = cur ? vals_b : vals_a;
 		uint64_t *ko = cur ? keys_a : keys_b; int *vo = cur ? vals_a : vals_b;
 		LAUNCH(k_sort_hist, nblocks, CPB_SORT_BLOCK, st, ki, hist, n, shift, nblocks);
@@ -203,7 +203,7 @@ static void cpb_exclusive_scan(const uint32_t *in, uint32_t *out, int n, uint32_
 	uint32_t run = 0;
 	for(int i = 0; i < n; i++){ uint32_t v = in[i]; out[i] = run; run += v; }
 }
-static int cpb_radix_sort(uint64_t *keys_a, int *vals_a, uint64_t *, int *, int n, int bits, uint32_t *, cudaStream_t)
+static int cpb_radix_sort(uint64_t *keys_a, int *vals_a, uint64_t *, int *, int n, int bits, uint32_t *, cudaStream_t, int = 0)
 {
 	uint64_t mask = (bits >= 64 ? ~0ull : ((1ull << bits) - 1ull));
 	int *idx = (int *)malloc(sizeof(int)*(size_t)(n > 0 ? n : 1));

@@ -903,11 +903,15 @@ static int step_phase_a(cpb200_world *w, double dt)
 		DBvh &T = w->bvh;
 		LAUNCH(k_bounds_init, 1, 32, st, T.bounds);
 		LAUNCH(k_bounds, std::min(grid_for(ns, 256), wide), 256, st, S, T.bounds);
-		LAUNCH(k_morton, grid_for(ns, 256), 256, st, S, B, (const double *)T.bounds, T.keys, T.leaf_shape);
+		// Morton bits: log2(shapes) + 4 (sixteen cells per shape), in whole radix digits
+		int want_bits = 4; while((1 << (want_bits - 4)) < ns && want_bits < 32) want_bits++;
+		want_bits = std::min(32, std::max(16, (want_bits + 7) & ~7));
+		const int drop_bits = 32 - want_bits;
+		LAUNCH(k_morton, grid_for(ns, 256), 256, st, S, B, (const double *)T.bounds, T.keys, T.leaf_shape, drop_bits);
 		STAGE_END(w, ST_BVH_KEYS);
 		int space_bits = 0; while((1 << space_bits) < w->n_spaces) space_bits++;
 		int bits = 32 + space_bits;
-		int where = cpb_radix_sort(T.keys, T.leaf_shape, w->keys_b, w->vals_b, ns, bits, w->sort_tmp, st);
+		int where = cpb_radix_sort(T.keys, T.leaf_shape, w->keys_b, w->vals_b, ns, bits, w->sort_tmp, st, drop_bits);
 		if(where){ std::swap(T.keys, w->keys_b); std::swap(T.leaf_shape, w->vals_b); }
 		STAGE_END(w, ST_BVH_SORT);
 		cudaMemsetAsync(T.flags, 0, sizeof(int)*(size_t)ns, st);
