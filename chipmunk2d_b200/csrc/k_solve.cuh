@@ -595,18 +595,21 @@ __global__ void k_sl_rows(DBodies B, DArbs A, DJoints J, DRows R, DSpaceLocal SL
 }
 
 #ifndef CPB_EMU
-__global__ void k_sl_solve(DBodies B, DArbs A, DJoints J, DRows R, DSpaceLocal SL, int iterations, double dt, double dt_coef)
+// JOINTS = false: instantiation for spaces without constraints (the ten joint classes cost ~40 registers; without
+// them more one-warp CTAs fit an SM).  `spaces`: the spaces this launch handles, one CTA each.
+template<bool JOINTS>
+__global__ void k_sl_solve(DBodies B, DArbs A, DJoints J, DRows R, DSpaceLocal SL, const int *__restrict__ spaces, int iterations, double dt, double dt_coef)
 {
 	extern __shared__ double4 s_vel[];
 	__shared__ int s_a[CPB_MAX_COLOURS + 1], s_j[CPB_MAX_COLOURS + 1];   // bucket begins ([c]) / ends ([c + 1])
 	__shared__ int s_cols[CPB_MAX_COLOURS], s_ncols;
-	const int s = blockIdx.x, t = threadIdx.x, nt = blockDim.x;
+	const int s = spaces[blockIdx.x], t = threadIdx.x, nt = blockDim.x;
 	const int b0 = SL.body0[s], nb = SL.nbody[s];
 	const int jbase = (int)SL.start[SL.n_spaces*CPB_MAX_COLOURS];
 	for(int c = t; c <= CPB_MAX_COLOURS; c += nt){
 		int ka = sl_arb_bucket(s, c) - 1, kj = sl_joint_bucket(SL, s, c) - 1;
 		s_a[c] = (ka >= 0 ? (int)SL.start[ka] : 0);
-		s_j[c] = (int)SL.start[kj] - jbase;
+		s_j[c] = (JOINTS ? (int)SL.start[kj] - jbase : 0);
 	}
 	VelShared vs = {s_vel, s_vel + nb, b0};
 	for(int b = t; b < nb; b += nt){ s_vel[b] = B.V[b0 + b]; s_vel[nb + b] = B.VB[b0 + b]; }
@@ -622,7 +625,7 @@ __global__ void k_sl_solve(DBodies B, DArbs A, DJoints J, DRows R, DSpaceLocal S
 	int pr = -1, pba = 0, pbb = 0, pcnt = 0, pq = -1, pj = 0, pja = 0, pjb = 0;
 	#define SL_PREFETCH(c_) do { \
 		pr = s_a[c_] + t; if(pr < s_a[(c_) + 1]){ const int4 h_ = R.hdr[pr]; pba = h_.x; pbb = h_.y; pcnt = h_.z; } else pr = -1; \
-		pq = s_j[c_] + (nt - 1 - t); if(pq < s_j[(c_) + 1]){ pj = J.row[pq]; pja = J.a[pj]; pjb = J.b[pj]; } else pq = -1; } while(0)
+		pq = s_j[c_] + (nt - 1 - t); if(JOINTS && pq < s_j[(c_) + 1]){ pj = J.row[pq]; pja = J.a[pj]; pjb = J.b[pj]; } else pq = -1; } while(0)
 	if(ncols > 0) SL_PREFETCH(s_cols[0]);
 	for(int pass = 0; pass <= iterations; pass++){
 		const int mode = (pass == 0 ? 0 : 1);
@@ -632,7 +635,7 @@ __global__ void k_sl_solve(DBodies B, DArbs A, DJoints J, DRows R, DSpaceLocal S
 			if(c == CPB_OVERFLOW_COLOUR){
 				if(t == 0){
 					for(int r = s_a[c]; r < s_a[c + 1]; r++){ const int4 h_ = R.hdr[r]; solve_row_packed(vs, R, r, h_.x, h_.y, h_.z, mode, dt_coef); }
-					for(int q = s_j[c]; q < s_j[c + 1]; q++){ int j = J.row[q]; solve_joint_idx(vs, B, J, j, J.a[j], J.b[j], mode, dt, dt_coef); }
+					if(JOINTS) for(int q = s_j[c]; q < s_j[c + 1]; q++){ int j = J.row[q]; solve_joint_idx(vs, B, J, j, J.a[j], J.b[j], mode, dt, dt_coef); }
 				}
 				SL_PREFETCH(cn);
 			} else {
@@ -644,7 +647,7 @@ __global__ void k_sl_solve(DBodies B, DArbs A, DJoints J, DRows R, DSpaceLocal S
 					for(r += nt; r < r1; r += nt){ const int4 h_ = R.hdr[r]; solve_row_packed(vs, R, r, h_.x, h_.y, h_.z, mode, dt_coef); }
 				}
 				// joints from the far end of the CTA: in small colours a thread gets a row or a joint, not both
-				if(q >= 0){
+				if(JOINTS && q >= 0){
 					solve_joint_idx(vs, B, J, j, ja, jb, mode, dt, dt_coef);
 					for(q += nt; q < q1; q += nt){ int j2 = J.row[q]; solve_joint_idx(vs, B, J, j2, J.a[j2], J.b[j2], mode, dt, dt_coef); }
 				}

@@ -158,6 +158,8 @@ struct cpb200_world {
 	DSpaceLocal SL; AllocGroup gSL;
 	std::vector<int> shape_body;   // host copy of the shapes' body index
 	DSpaceShapes SS; bool sl_shapes_ok; int sl_max_nshape;
+	std::vector<int> joint_body;   // host copy: body a of every joint (its space has constraints)
+	int *d_sl_plain, *d_sl_jointed; int n_sl_plain, n_sl_jointed;   // spaces without / with joints (k_sl_solve launches)
 	uint32_t *sl_tmp;
 	void *d_query; size_t query_bytes;   // device buffer for query hits (+ counters in its first 64 bytes)
 	double *d_scratch;      // small scratch (collide_one output, stats)
@@ -248,7 +250,8 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 		if(per_sm < 1) per_sm = 1;
 		if(per_sm > 4) per_sm = 4;
 		w->coop_blocks = w->sm_count*per_sm;
-		cudaFuncSetAttribute(k_sl_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, CPB_SL_MAX_SMEM);
+		cudaFuncSetAttribute(k_sl_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CPB_SL_MAX_SMEM);
+		cudaFuncSetAttribute(k_sl_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CPB_SL_MAX_SMEM);
 		cudaFuncSetAttribute(k_sl_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, CPB_SL_MAX_SHAPES*(int)(sizeof(double4) + sizeof(int)));
 	}
 #endif
@@ -282,6 +285,7 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	w->sl_dirty = true; w->sl_ok = false; w->sl_disabled = (getenv("CPB200_NO_SPACE_LOCAL") != NULL); w->sl_max_nbody = 0;
 	memset(&w->SL, 0, sizeof(w->SL)); w->sl_tmp = NULL;
 	memset(&w->SS, 0, sizeof(w->SS)); w->sl_shapes_ok = false; w->sl_max_nshape = 0;
+	w->d_sl_plain = w->d_sl_jointed = NULL; w->n_sl_plain = w->n_sl_jointed = 0;
 	w->last_active = 0; w->force_blocks = 0; w->hints_valid = false; w->wl_cap = 0; w->d_stage = NULL; w->stage_bytes = 0;
 	cudaMalloc(&p, sizeof(double)*64); w->d_scratch = (double *)p;
 	cudaMallocHost(&p, sizeof(double)*64); w->h_scratch = (double *)p;
@@ -720,6 +724,7 @@ extern "C" int cpb200_world_set_joints(cpb200_world *w, int n, const cpb200_join
 		CPB_CHECK(cudaMemcpyAsync(w->d_nocollide, set.data(), sizeof(uint64_t)*capn, cudaMemcpyHostToDevice, w->stream));
 		CPB_CHECK(cudaStreamSynchronize(w->stream));   // `set` is a local
 	}
+	w->joint_body = a; w->sl_dirty = true;
 	w->joints_dt = 0.0; // force bias_coef refresh
 	w->hints_valid = false;
 	return world_sync(w);
@@ -812,6 +817,18 @@ static int sl_refresh(cpb200_world *w)
 	CPB_CHECK(cudaStreamSynchronize(w->stream));
 	w->SL.n_spaces = ns; w->SL.body0 = d_first; w->SL.nbody = d_count; w->SL.start = d_start;
 	w->sl_max_nbody = mx;
+	{
+		std::vector<char> jointed((size_t)ns, 0);
+		for(int b : w->joint_body){ if(b >= 0 && b < nb) jointed[(size_t)w->body_space[(size_t)b]] = 1; }
+		std::vector<int> plain, withj;
+		for(int sp = 0; sp < ns; sp++) (jointed[(size_t)sp] ? withj : plain).push_back(sp);
+		int *d_a = NULL, *d_b = NULL;
+		DA(w->gSL, d_a, ns); DA(w->gSL, d_b, ns);
+		if(!plain.empty()) CPB_CHECK(cudaMemcpyAsync(d_a, plain.data(), sizeof(int)*plain.size(), cudaMemcpyHostToDevice, w->stream));
+		if(!withj.empty()) CPB_CHECK(cudaMemcpyAsync(d_b, withj.data(), sizeof(int)*withj.size(), cudaMemcpyHostToDevice, w->stream));
+		CPB_CHECK(cudaStreamSynchronize(w->stream));
+		w->d_sl_plain = d_a; w->n_sl_plain = (int)plain.size(); w->d_sl_jointed = d_b; w->n_sl_jointed = (int)withj.size();
+	}
 	w->sl_ok = true;
 	// contiguous shape range per space (space-local broadphase)
 	const int nsh = w->S.n;
@@ -1033,7 +1050,8 @@ static int step_phase_b(cpb200_world *w)
 				int per_space = est_cons/w->n_spaces;
 				int threads = 32; while(threads < 256 && threads*8 < per_space) threads *= 2;
 				size_t smem = (size_t)w->sl_max_nbody*64;
-				LAUNCH_SMEM(k_sl_solve, w->n_spaces, threads, smem, st, B, Ac, J, R, SL, iterations, dt, dt_coef);
+				if(w->n_sl_plain) LAUNCH_SMEM(k_sl_solve<false>, w->n_sl_plain, threads, smem, st, B, Ac, J, R, SL, (const int *)w->d_sl_plain, iterations, dt, dt_coef);
+				if(w->n_sl_jointed) LAUNCH_SMEM(k_sl_solve<true>, w->n_sl_jointed, threads, smem, st, B, Ac, J, R, SL, (const int *)w->d_sl_jointed, iterations, dt, dt_coef);
 			}
 		}
 #else
