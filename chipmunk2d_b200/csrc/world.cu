@@ -159,7 +159,8 @@ struct cpb200_world {
 	std::vector<int> shape_body;   // host copy of the shapes' body index
 	DSpaceShapes SS; bool sl_shapes_ok; int sl_max_nshape;
 	std::vector<int> joint_body;   // host copy: body a of every joint (its space has constraints)
-	int *d_sl_plain, *d_sl_jointed; int n_sl_plain, n_sl_jointed;   // spaces without / with joints (k_sl_solve launches)
+	int *d_sl_plain, *d_sl_jointed; int n_sl_plain, n_sl_jointed;
+	cudaStream_t stream2; cudaEvent_t ev_fork, ev_join;   // the two k_sl_solve launches touch disjoint spaces: run them side by side   // spaces without / with joints (k_sl_solve launches)
 	uint32_t *sl_tmp;
 	void *d_query; size_t query_bytes;   // device buffer for query hits (+ counters in its first 64 bytes)
 	double *d_scratch;      // small scratch (collide_one output, stats)
@@ -239,6 +240,8 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	w->n_spaces = n_spaces;
 	w->stream = 0;
 	cudaStreamCreate(&w->stream);
+	cudaStreamCreate(&w->stream2);
+	cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming);
 	w->sm_count = 148;
 	w->coop_blocks = 148;
 #ifndef CPB_EMU
@@ -308,6 +311,7 @@ extern "C" void cpb200_world_destroy(cpb200_world *w)
 	if(w->d_joint_order) cudaFree(w->d_joint_order);
 	if(w->d_nocollide) cudaFree(w->d_nocollide);
 	for(int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(w->ev[i]);
+	cudaStreamDestroy(w->stream2); cudaEventDestroy(w->ev_fork); cudaEventDestroy(w->ev_join);
 	cudaStreamDestroy(w->stream);
 	delete w;
 }
@@ -1050,8 +1054,12 @@ static int step_phase_b(cpb200_world *w)
 				int per_space = est_cons/w->n_spaces;
 				int threads = 32; while(threads < 256 && threads*8 < per_space) threads *= 2;
 				size_t smem = (size_t)w->sl_max_nbody*64;
+				const bool fork = (w->n_sl_plain > 0 && w->n_sl_jointed > 0);
+				cudaStream_t sj = (fork ? w->stream2 : st);
+				if(fork){ CPB_CHECK(cudaEventRecord(w->ev_fork, st)); CPB_CHECK(cudaStreamWaitEvent(sj, w->ev_fork, 0)); }
 				if(w->n_sl_plain) LAUNCH_SMEM(k_sl_solve<false>, w->n_sl_plain, threads, smem, st, B, Ac, J, R, SL, (const int *)w->d_sl_plain, iterations, dt, dt_coef);
-				if(w->n_sl_jointed) LAUNCH_SMEM(k_sl_solve<true>, w->n_sl_jointed, threads, smem, st, B, Ac, J, R, SL, (const int *)w->d_sl_jointed, iterations, dt, dt_coef);
+				if(w->n_sl_jointed) LAUNCH_SMEM(k_sl_solve<true>, w->n_sl_jointed, threads, smem, sj, B, Ac, J, R, SL, (const int *)w->d_sl_jointed, iterations, dt, dt_coef);
+				if(fork){ CPB_CHECK(cudaEventRecord(w->ev_join, sj)); CPB_CHECK(cudaStreamWaitEvent(st, w->ev_join, 0)); }
 			}
 		}
 #else
