@@ -170,6 +170,7 @@ def scene_descs(scene, space=0, body_base=0, vert_base=0, hashid_base=0):
     bd = np.zeros(len(sb), dtype=BODY_DESC)
     for k in ("p", "v", "f", "a", "w", "t", "m", "i", "cog", "type"):
         bd[k] = sb[k]
+    bd["cog"][sb["type"] != 0] = 0.0      # the scene format gives only dynamic bodies a centre of gravity (scene_io.c:70-74)
     # libm cos/sin (what cpBodySetAngle -> SetTransform uses, cpBody.c:347-357), not numpy's SIMD variants
     bd["rot"][:, 0] = 1.0
     for i in np.nonzero(sb["a"])[0]:
