@@ -171,6 +171,9 @@ def scene_descs(scene, space=0, body_base=0, vert_base=0, hashid_base=0):
     for k in ("p", "v", "f", "a", "w", "t", "m", "i", "cog", "type"):
         bd[k] = sb[k]
     bd["cog"][sb["type"] != 0] = 0.0      # the scene format gives only dynamic bodies a centre of gravity (scene_io.c:70-74)
+    # the scene's p is what cpBodySetPosition receives, i.e. the body's ORIGIN; the loader sets the centre of gravity
+    # first and the angle last, so body->p (what the engine integrates) = p + cog, unrotated (cpBody.c:241-249)
+    bd["p"] = sb["p"] + bd["cog"]
     # libm cos/sin (what cpBodySetAngle -> SetTransform uses, cpBody.c:347-357), not numpy's SIMD variants
     bd["rot"][:, 0] = 1.0
     for i in np.nonzero(sb["a"])[0]:

@@ -45,6 +45,32 @@ def test_api_path_equals_engine_path(name, steps):
     api.free()
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_api_path_equals_engine_path_on_random_scenes(seed):
+    """The same check on scenes with kinematic bodies, sensors, filters, multi-shape bodies and all ten joint
+    classes (tests/test_gpu_fuzz.py), sleeping enabled."""
+    from tests.test_gpu_fuzz import random_scene
+    sc = random_scene(4000 + seed, n_bodies=60, sleep=0.5)
+    api = SceneSpace(load_scene_lib(), sc.blob)
+    eng = World(1)
+    eng.load_scene(sc)
+    for _ in range(250):
+        api.step(sc.dt)
+        eng.step(sc.dt)
+    eng.sync()
+    a = api.bodies()
+    e = eng.bodies()
+    # cpBodyGetPosition is the body's origin: p - rot(cog) (cpBody.c:368-372), the engine reports p
+    cog = np.where((sc.bodies["type"] == 0)[:, None], sc.bodies["cog"], 0.0)
+    origin = np.stack([e["p"][:, 0] - (cog[:, 0]*e["rot"][:, 0] - cog[:, 1]*e["rot"][:, 1]),
+                       e["p"][:, 1] - (cog[:, 0]*e["rot"][:, 1] + cog[:, 1]*e["rot"][:, 0])], axis=1)
+    assert np.array_equal(a[1:, 0:2], origin[1:]) and np.array_equal(a[1:, 2:4], e["v"][1:])
+    assert np.array_equal(a[1:, 4], e["a"][1:]) and np.array_equal(a[1:, 5], e["w"][1:])
+    assert np.array_equal(a[1:, 8].astype(int), e["sleeping"][1:])
+    assert np.array_equal(api.shape_bbs(), eng.shape_bbs())
+    api.free()
+
+
 def test_api_hasty_space_is_the_same_device_path():
     sc = golden_scene("SimpleTerrainCircles_100")
     a = SceneSpace(load_scene_lib(), sc.blob)

@@ -169,3 +169,21 @@ def test_shape_query_with_a_probe_outside_the_space(ref, name):
     assert total > 5
     dev.free()
     rs.space = None
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_queries_on_random_scenes(ref, seed):
+    """Random polygons (3-8 vertices, bevels), fat segments, offset circles, groups, category masks and sensors
+    (tests/test_gpu_fuzz.py): every query kind bit-identical to the reference on the loaded scene."""
+    from tests.test_gpu_fuzz import random_scene
+    sc = random_scene(3000 + seed, n_bodies=60)
+    dev, rs = ours(sc.blob), ref.load(sc.blob)
+    run_queries(dev, rs, sc, exact=True, seed=20 + seed)
+    pts, lo, hi, rng = probes(sc, 40 + seed)
+    for k, p in enumerate(pts[:10]):
+        for kind, args in ((0, dict(radius=9.0)), (1, dict(w=25.0, h=11.0, radius=1.5)), (2, dict(angle=0.4*k, w=20.0, h=12.0, radius=0.5))):
+            (a, any_a), (b, any_b) = dev.shape_query(kind, p, **args), rs.shape_query(kind, p, **args)
+            assert a.shape == b.shape and np.array_equal(a[:, 0:2], b[:, 0:2])
+            assert np.allclose(a, b, rtol=1e-9, atol=1e-9)
+    dev.free()
+    rs.space = None
