@@ -73,6 +73,9 @@ static inline cudaError_t cudaSetDevice(int){ return 0; }
 static inline cudaError_t cudaStreamCreate(cudaStream_t *s){ *s = 0; return 0; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t){ return 0; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e){ *e = 0; return 0; }
+#define cudaEventDisableTiming 2
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned){ *e = 0; return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned){ return 0; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t){ return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t){ return 0; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t){ return 0; }

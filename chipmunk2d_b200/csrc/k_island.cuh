@@ -20,6 +20,8 @@ struct DIslands {
 	int *wake;          // per body: component rooted here must wake
 	int *comp_active;   // per body (root): some member is not idle long enough
 	int *woken;         // per body: woke up this step
+	int *touch;         // per body: idle long enough itself, but joined to an awake body that is not
+	int *any_woken;     // [1] some body woke up this step
 };
 
 CPB_DEVICE bool space_sleeps(const DSpace &sp){ return sp.sleep_threshold != INFINITY; }
@@ -29,7 +31,8 @@ __global__ void k_sleep_idle(DBodies B, DIslands I, const DSpace *__restrict__ s
 {
 	int i = CPB_TID;
 	if(i >= B.n) return;
-	I.parent[i] = i; I.wake[i] = 0; I.comp_active[i] = 0; I.woken[i] = 0;
+	I.parent[i] = i; I.wake[i] = 0; I.comp_active[i] = 0; I.woken[i] = 0; I.touch[i] = 0;
+	if(i == 0) *I.any_woken = 0;
 	if(B.type[i] != CPB200_BODY_DYNAMIC || B.sleeping[i]) return;
 	DSpace sp = spaces[B.space[i]];
 	if(!space_sleeps(sp)) return;
@@ -75,6 +78,7 @@ __global__ void k_sleep_wake_apply(DBodies B, DIslands I)
 	if(g >= 0 && I.wake[g]){
 		B.sleeping[i] = 0; B.sgroup[i] = -1; B.idle[i] = 0.0;
 		I.woken[i] = 1;
+		*I.any_woken = 1;
 	}
 }
 
@@ -91,10 +95,11 @@ CPB_DEVICE int uf_find(int *parent, int x){
 	return x;
 }
 
-// union over edges between awake dynamic bodies; bodies touching a just-woken body get their
-// idle timer reset (cpSpaceComponent.c:145-151)
-__global__ void k_sleep_union(DBodies B, DIslands I, DArbs A, DJoints J)
+// bodies touching a just-woken body get their idle timer reset (cpSpaceComponent.c:145-151); a pass of its own so
+// that the union pass below reads settled idle timers.  Returns at once in the usual step where nothing woke up.
+__global__ void k_sleep_woken_reset(DBodies B, DIslands I, DArbs A, DJoints J)
 {
+	if(!*I.any_woken) return;
 	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
 	int total = nA + J.n;
 	for(int c = CPB_TID; c < total; c += CPB_NTHREADS){
@@ -103,8 +108,31 @@ __global__ void k_sleep_union(DBodies B, DIslands I, DArbs A, DJoints J)
 		else { a = J.a[c - nA]; b = J.b[c - nA]; }
 		if(I.woken[a] && B.type[b] == CPB200_BODY_DYNAMIC) B.idle[b] = 0.0;
 		if(I.woken[b] && B.type[a] == CPB200_BODY_DYNAMIC) B.idle[a] = 0.0;
+	}
+}
+
+// Union over the edges between awake dynamic bodies that have BOTH idled long enough.  A component can only fall
+// asleep if every member has (ComponentActive, cpSpaceComponent.c:210-218), i.e. iff it is a component of this
+// "idle subgraph" with no edge to a body that has not: such edges only mark their idle endpoint.  While a pile
+// is still settling no body qualifies and the pass is a streaming read; the full union-find over millions of
+// edges of one giant component runs only in the step in which that component actually falls asleep.
+__global__ void k_sleep_union(DBodies B, DIslands I, DArbs A, DJoints J, const DSpace *__restrict__ spaces)
+{
+	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
+	int total = nA + J.n;
+	for(int c = CPB_TID; c < total; c += CPB_NTHREADS){
+		int a, b;
+		if(c < nA){ if(A.active[c] != 1) continue; a = A.ba[c]; b = A.bb[c]; }
+		else { a = J.a[c - nA]; b = J.b[c - nA]; }
 		if(B.type[a] != CPB200_BODY_DYNAMIC || B.type[b] != CPB200_BODY_DYNAMIC) continue;
 		if(B.sleeping[a] || B.sleeping[b]) continue;
+		const double thr = spaces[B.space[a]].sleep_threshold;
+		const bool ia = (B.idle[a] >= thr), ib = (B.idle[b] >= thr);
+		if(!(ia && ib)){
+			if(ia) I.touch[a] = 1;
+			if(ib) I.touch[b] = 1;
+			continue;
+		}
 		for(;;){
 			int ra = uf_find(I.parent, a), rb = uf_find(I.parent, b);
 			if(ra == rb) break;
@@ -126,7 +154,7 @@ __global__ void k_sleep_components(DBodies B, DIslands I, const DSpace *__restri
 	int r = uf_find(I.parent, i);
 	DSpace sp = spaces[B.space[i]];
 	// ComponentActive (cpSpaceComponent.c:210-218)
-	if(!space_sleeps(sp) || B.idle[i] < sp.sleep_threshold) I.comp_active[r] = 1;
+	if(!space_sleeps(sp) || B.idle[i] < sp.sleep_threshold || I.touch[i]) I.comp_active[r] = 1;
 }
 
 __global__ void k_sleep_apply(DBodies B, DIslands I)
@@ -165,7 +193,8 @@ static int islands_step(DIslands &I, DBodies &B, DShapes &S, DJoints &J, DArbs &
 	LAUNCH(k_sleep_idle, gb, 256, st, B, I, spaces, dt);
 	LAUNCH(k_sleep_wake_mark, ge, 256, st, B, I, Ac, J, spaces);
 	LAUNCH(k_sleep_wake_apply, gb, 256, st, B, I);
-	LAUNCH(k_sleep_union, ge, 256, st, B, I, Ac, J);
+	LAUNCH(k_sleep_woken_reset, ge, 256, st, B, I, Ac, J);
+	LAUNCH(k_sleep_union, ge, 256, st, B, I, Ac, J, spaces);
 	LAUNCH(k_sleep_components, gb, 256, st, B, I, spaces);
 	LAUNCH(k_sleep_apply, gb, 256, st, B, I);
 	LAUNCH(k_sleep_arbs, ge, 256, st, B, Ac, C);

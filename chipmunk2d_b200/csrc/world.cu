@@ -424,7 +424,7 @@ extern "C" int cpb200_world_set_bodies(cpb200_world *w, int n, const cpb200_body
 	w->hints_valid = false; // body types / masses may have changed: colour from scratch once
 	w->body_space.clear(); w->sl_dirty = true;
 	w->gI.release();
-	DA(w->gI, w->I.parent, n); DA(w->gI, w->I.wake, n); DA(w->gI, w->I.comp_active, n); DA(w->gI, w->I.woken, n);
+	DA(w->gI, w->I.parent, n); DA(w->gI, w->I.wake, n); DA(w->gI, w->I.comp_active, n); DA(w->gI, w->I.woken, n); DA(w->gI, w->I.touch, n); DA(w->gI, w->I.any_woken, 4);
 	int r = cpb200_world_update_bodies(w, 0, n, bodies);
 	w->cache_dirty = true;
 	return r;
