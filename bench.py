@@ -254,8 +254,9 @@ def run_ours(args):
             # call a user of this workload makes is the engine's batched world with HOST buffers: forces for
             # every body in, cpSpaceStep for all spaces, every body's state out -- each step, inside the timer
             import numpy as np, time
-            forces = np.zeros((w.n_bodies, 3), dtype=np.float64)
-            states = np.zeros(w.n_bodies, dtype=BODY_STATE)
+            forces = w.pinned_array(w.n_bodies * 3, np.float64).reshape(-1, 3)   # page-locked host buffers
+            forces[:] = 0.0
+            states = w.pinned_array(w.n_bodies, BODY_STATE)
             for _ in range(2):
                 w.set_body_forces(0, forces); w.step(dt); w.bodies_into(states)
             barrier()
@@ -271,8 +272,8 @@ def run_ours(args):
         e2e = {"value": e2e_bodies * world * k2 / float(t_e.item()), "unit": "body-steps/s", "steps": k2,
                "h2d_bytes_per_step": int(n_api * 24), "d2h_bytes_per_step": int(n_api * BODY_STATE.itemsize),
                "ms_per_step": 1000.0 * float(t_e.item()) / k2,
-               "path": "cpBodySetForce on every body -> cpSpaceStep -> cpBodyGetPosition on every body (scene_io.c cpb_scene_e2e_steps)" +
-                       ("" if len(scenes) == 1 else " -- batched: World.set_body_forces(host) -> World.step -> World.bodies_into(host) over all spaces")}
+               "path": ("cpBodySetForce on every body -> cpSpaceStep -> cpBodyGetPosition on every body (scene_io.c cpb_scene_e2e_steps)" if len(scenes) == 1 else
+                        "World.set_body_forces(page-locked host array) -> World.step -> World.bodies_into(page-locked host array) over all spaces (the reference's C API has no batched entry point)")}
     except Exception as exc:  # keep the device-resident number even if the API libs are missing
         e2e = {"value": None, "unit": "body-steps/s", "error": str(exc)}
 

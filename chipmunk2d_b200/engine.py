@@ -98,6 +98,10 @@ def load_engine(path=None):
     lib.cpb200_world_set_joints.argtypes = [vp, ci, vp]
     lib.cpb200_world_update_bodies.argtypes = [vp, ci, ci, vp]
     lib.cpb200_world_set_body_forces.argtypes = [vp, ci, ci, vp]
+    lib.cpb200_host_alloc.restype = vp
+    lib.cpb200_host_alloc.argtypes = [C.c_size_t]
+    lib.cpb200_host_free.restype = None
+    lib.cpb200_host_free.argtypes = [vp]
     lib.cpb200_world_reserve.argtypes = [vp, ci, ci]
     lib.cpb200_world_step.argtypes = [vp, cd]
     lib.cpb200_world_sync.argtypes = [vp]
@@ -224,6 +228,9 @@ class World:
         return rc
 
     def close(self):
+        for ptr in getattr(self, "_pinned", []):
+            self.lib.cpb200_host_free(ptr)
+        self._pinned = []
         if self.w:
             self.lib.cpb200_world_destroy(self.w)
             self.w = None
@@ -252,6 +259,19 @@ class World:
         """Per-step host input: (f.x, f.y, torque) rows for bodies [first, first + len(fxyt))."""
         f = np.ascontiguousarray(fxyt, dtype=np.float64).reshape(-1, 3)
         self._ck(self.lib.cpb200_world_set_body_forces(self.w, int(first), len(f), f.ctypes.data))
+
+    def pinned_array(self, n, dtype):
+        """A numpy array over page-locked host memory (cpb200_host_alloc): transfers from/to it are one DMA at link
+        speed.  The memory lives as long as the world."""
+        dtype = np.dtype(dtype)
+        nbytes = max(1, int(n) * dtype.itemsize)
+        ptr = self.lib.cpb200_host_alloc(nbytes)
+        if not ptr:
+            raise EngineError("cpb200_host_alloc(%d) failed" % nbytes)
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(ptr)
+        buf = (C.c_char * nbytes).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=int(n))
 
     def bodies_into(self, out):
         """Read-back into a caller-owned BODY_STATE array (no allocation in the step loop)."""
