@@ -316,7 +316,6 @@ CPB_DEVICE void st_vel(double4 *p, double4 v){ st4_cg(p, v); }
 // smaller row sets (mid-size scenes) use the default policy and are served from L2 from the second pass on.
 template<bool STREAM_ROWS> struct VelGlobalT {
 	static const bool STREAM = STREAM_ROWS;
-	static const bool EAGER = false;
 	double4 *V, *VB;
 	CPB_MEMBER double4 ldV(int b) const { return ld_vel(&V[b]); }
 	CPB_MEMBER double4 ldVB(int b) const { return ld_vel(&VB[b]); }
@@ -326,10 +325,6 @@ template<bool STREAM_ROWS> struct VelGlobalT {
 typedef VelGlobalT<true> VelGlobal;
 struct VelShared {
 	static const bool STREAM = false;    // a space's rows are re-read by the same SM every pass: cache them
-#ifndef CPB_SL_EAGER
-#define CPB_SL_EAGER 1
-#endif
-	static const bool EAGER = (CPB_SL_EAGER != 0);      // few warps per space: shorten the dependent load chain (see solve_row_idx)
 	double4 *V, *VB; int b0;
 	CPB_MEMBER double4 ldV(int b) const { return V[b - b0]; }
 	CPB_MEMBER double4 ldVB(int b) const { return VB[b - b0]; }
@@ -428,20 +423,10 @@ template<class VS> CPB_DEVICE void solve_row_idx(const VS &vs, const DBodies &B,
 	// were: skip the scatter then.  Bitwise comparison, so the stored state is identical either way.
 	const double4 Va0 = Va, Vb0 = Vb, VBa0 = VBa, VBb0 = VBb;
 #endif
-	if(VS::EAGER){
-		// issue the loads of both contacts before the first one is solved: one memory latency per row
-		// instead of one per contact (the compiler cannot hoist them over the impulse stores itself)
-		RowContact<VS::STREAM> c0, c1;
-		c0.load(R, r);
-		if(cnt == 2) c1.load(R, R.cap + r);
-		c0.solve(R, r, Va, Vb, VBa, VBb, mia, mib, n, svr, u);
-		if(cnt == 2) c1.solve(R, R.cap + r, Va, Vb, VBa, VBb, mia, mib, n, svr, u);
-	} else {
-		for(int k = 0; k < cnt; k++){
-			RowContact<VS::STREAM> c;
-			c.load(R, k*R.cap + r);
-			c.solve(R, k*R.cap + r, Va, Vb, VBa, VBb, mia, mib, n, svr, u);
-		}
+	for(int k = 0; k < cnt; k++){
+		RowContact<VS::STREAM> c;
+		c.load(R, k*R.cap + r);
+		c.solve(R, k*R.cap + r, Va, Vb, VBa, VBb, mia, mib, n, svr, u);
 	}
 #ifndef CPB_NO_SKIP_SAME
 	if(dyn_a){ if(!same_bits3(Va, Va0)) vs.stV(ba, Va); if(!same_bits3(VBa, VBa0)) vs.stVB(ba, VBa); }
