@@ -2,7 +2,8 @@
  *
  * In the reference a hasty space farms the solver loop out to at most two pthreads
  * (src/cpHastySpace.c:446-495).  Here every space already solves on the GPU, so a hasty space is a
- * regular B200 space: the thread count is stored and reported but has no effect. */
+ * regular B200 space; the thread count caps the host threads that copy body state between the device buffers
+ * and the cpBody mirrors of large spaces (host/cp_space.c host_threads). */
 #ifndef CHIPMUNK_B200_HASTY_SPACE_H
 #define CHIPMUNK_B200_HASTY_SPACE_H
 #include "chipmunk.h"
