@@ -75,10 +75,12 @@ __global__ void k_shape_cache(DShapes S, DBodies B, int all)
 }
 
 // K9: cpBodyUpdateVelocity (cpBody.c:493-509); kinematic bodies are skipped, forces reset.
-__global__ void k_integrate_vel(DBodies B, const DSpace *__restrict__ spaces, double dt)
+// Also clears the two per-body words of the colouring that follows (one launch instead of two memsets).
+__global__ void k_integrate_vel(DBodies B, const DSpace *__restrict__ spaces, double dt, unsigned long long *claim, unsigned long long *bmask)
 {
 	int i = CPB_TID;
 	if(i >= B.n) return;
+	claim[i] = 0ull; bmask[i] = 0ull;
 	if(B.type[i] != CPB200_BODY_DYNAMIC || B.sleeping[i]) return;
 	DSpace sp = spaces[B.space[i]];
 	double4 V = B.V[i];

@@ -75,10 +75,11 @@ CPB_DEVICE uint32_t spread16(uint32_t x){
 	return x;
 }
 
-__global__ void k_morton(DShapes S, DBodies B, const double *__restrict__ bounds, uint64_t *keys, int *vals, int drop_bits)
+__global__ void k_morton(DShapes S, DBodies B, const double *__restrict__ bounds, uint64_t *keys, int *vals, int drop_bits, int *refit_flags)
 {
 	int s = CPB_TID;
 	if(s >= S.n) return;
+	refit_flags[s] = 0;   // arrival counters of k_bvh_refit (saves a memset launch)
 	double4 bb = S.bb[s];
 	double cx = (bb.x + bb.z)*0.5, cy = (bb.y + bb.w)*0.5;
 	double w = bounds[2] - bounds[0], h = bounds[3] - bounds[1];

@@ -753,8 +753,13 @@ static int refresh_joint_bias(cpb200_world *w, double dt)
 #define STAGE_BEGIN(w) do { if((w)->profiling) cudaEventRecord((w)->ev[0], (w)->stream); } while(0)
 #define STAGE_END(w, id) do { if((w)->profiling){ cudaEventRecord((w)->ev[(id) + 1], (w)->stream); } } while(0)
 
-__global__ void k_reset_step(DCounters *C, int *pair_count, int *cur_count)
+// start-of-step bookkeeping in one launch (the small per-step clears used to be five memsets)
+__global__ void k_reset_step(DCounters *C, int *pair_count, int *cur_count, int *ccount, int *jcount, int *wl_n)
 {
+	if(ccount){
+		for(int k = CPB_TID; k <= CPB_MAX_COLOURS; k += CPB_NTHREADS){ ccount[k] = 0; jcount[k] = 0; }
+		for(int k = CPB_TID; k < CPB_MAX_COLOUR_ROUNDS + 2; k += CPB_NTHREADS) wl_n[k] = 0;
+	}
 	if(CPB_TID != 0) return;
 	C->n_pairs[0] = C->n_pairs[1] = C->n_pairs[2] = 0;
 	C->n_contacts = 0; C->n_active = 0; C->n_colours = 0; C->n_cached = 0;
@@ -893,7 +898,7 @@ static int step_phase_a(cpb200_world *w, double dt)
 	int prv = w->cur; w->cur ^= 1;
 	DArbs &Ap = w->A[prv]; DArbs &Ac = w->A[w->cur];
 	DTable &Tp = w->T[prv]; DTable &Tc = w->T[w->cur];
-	LAUNCH(k_reset_step, 1, 32, st, w->C, w->P.count, Ac.count_ptr);
+	LAUNCH(k_reset_step, 1, 32, st, w->C, w->P.count, Ac.count_ptr, w->K.ccount, w->K.jcount, w->K.wl_n);
 	cudaMemsetAsync(Tc.slots, 0, sizeof(ulonglong2)*((size_t)Tc.mask + 1), st);
 
 	const int nb = B.n, ns = S.n;
@@ -928,14 +933,13 @@ static int step_phase_a(cpb200_world *w, double dt)
 		int want_bits = 4; while((1 << (want_bits - 4)) < ns && want_bits < 32) want_bits++;
 		want_bits = std::min(32, std::max(16, (want_bits + 7) & ~7));
 		const int drop_bits = 32 - want_bits;
-		LAUNCH(k_morton, grid_for(ns, 256), 256, st, S, B, (const double *)T.bounds, T.keys, T.leaf_shape, drop_bits);
+		LAUNCH(k_morton, grid_for(ns, 256), 256, st, S, B, (const double *)T.bounds, T.keys, T.leaf_shape, drop_bits, T.flags);
 		STAGE_END(w, ST_BVH_KEYS);
 		int space_bits = 0; while((1 << space_bits) < w->n_spaces) space_bits++;
 		int bits = 32 + space_bits;
 		int where = cpb_radix_sort(T.keys, T.leaf_shape, w->keys_b, w->vals_b, ns, bits, w->sort_tmp, st, drop_bits);
 		if(where){ std::swap(T.keys, w->keys_b); std::swap(T.leaf_shape, w->vals_b); }
 		STAGE_END(w, ST_BVH_SORT);
-		cudaMemsetAsync(T.flags, 0, sizeof(int)*(size_t)ns, st);
 		LAUNCH(k_bvh_build, grid_for(ns - 1, 256), 256, st, T);
 		LAUNCH(k_bvh_leaves, grid_for(ns, 256), 256, st, T, S, B);
 		LAUNCH(k_bvh_refit, grid_for(ns, 256), 256, st, T);
@@ -997,7 +1001,7 @@ static int step_phase_b(cpb200_world *w)
 	STAGE_END(w, ST_PRESTEP);
 
 	// K9
-	if(nb) LAUNCH(k_integrate_vel, grid_for(nb, 256), 256, st, B, (const DSpace *)w->d_spaces, dt);
+	if(nb) LAUNCH(k_integrate_vel, grid_for(nb, 256), 256, st, B, (const DSpace *)w->d_spaces, dt, w->K.claim, w->K.bmask);
 	STAGE_END(w, ST_INTEGRATE_VEL);
 
 	// K10 + K11
@@ -1015,10 +1019,7 @@ static int step_phase_b(cpb200_world *w)
 		w->n_user_order = 0; w->n_joint_order = 0;
 	} else {
 		DColour &K = w->K;
-		if(nb){ cudaMemsetAsync(K.claim, 0, sizeof(unsigned long long)*(size_t)nb, st); cudaMemsetAsync(K.bmask, 0, sizeof(unsigned long long)*(size_t)nb, st); }
-		cudaMemsetAsync(K.ccount, 0, sizeof(int)*(CPB_MAX_COLOURS + 1), st);
-		cudaMemsetAsync(K.jcount, 0, sizeof(int)*(CPB_MAX_COLOURS + 1), st);
-		cudaMemsetAsync(K.wl_n, 0, sizeof(int)*(CPB_MAX_COLOUR_ROUNDS + 2), st);
+		// (claim / bmask were cleared by k_integrate_vel, the colour histograms and worklist lengths by k_reset_step)
 		if(ensure_worklists(w, Ac.cap + J.n + 64)) return -1;
 		int use_hints = (w->hints_valid && !w->no_hints ? 1 : 0);
 		w->hints_valid = true;
