@@ -14,8 +14,10 @@ Workloads (BASELINE.json configs):
 
 A "step" is one cpSpaceStep of the whole workload.  `value` = non-static bodies x steps / device seconds with
 everything resident in HBM (CUDA events on the engine's stream, max over ranks).  `e2e` = the same metric
-through the public Chipmunk2D C API with host buffers: every step writes a force into every body (H2D),
-calls cpSpaceStep and reads every position back (D2H).
+through the C-ABI (include/cpb200.h) with HOST buffers: every step uploads a force for every body from a
+page-locked host array (H2D), steps, and downloads every body's state into a host array (D2H).
+`e2e_per_body_api` = the same through the per-object Chipmunk2D C API (cpBodySetForce / cpSpaceStep /
+cpBodyGetPosition on every body).
 `--impl reference` times the unmodified reference (oracle/_ref, cpSpaceStep, CPU) on a bounded sample.
 """
 import argparse
@@ -236,46 +238,57 @@ def run_ours(args):
     total_bodies, total_contacts, total_arbs, total_pairs, total_ke = sums
     maxes = torch.tensor(mx, dtype=torch.float64)
 
-    # ---- e2e through the public C API (host buffers every step) ----
+    # ---- e2e: the same metric with HOST buffers every step, copies inside the timed region ----
+    # (1) `e2e`: through the C-ABI (include/cpb200.h) -- forces of every body in from a page-locked host array
+    #     (cpb200_world_set_body_forces), cpb200_world_step, the state of every body out into a page-locked host
+    #     array (cpb200_world_get_bodies, which waits for the step).  This is the call the reference-side binding
+    #     of INTEGRATION.md makes, and for the batched workload the only one there is (one cpSpace = one world).
+    # (2) `e2e_per_body_api` (single-space workloads): the same through the object API of include/chipmunk --
+    #     cpBodySetForce on every body, cpSpaceStep, cpBodyGetPosition on every body: 2 M serial host calls on
+    #     1 M heap objects per step, which the reference arm (cpSpaceStep alone) does not pay.  Reported beside it.
     e2e = None
+    e2e_api = None
     try:
+        import numpy as np, time
         k2 = max(1, min(args.steps, 10))
-        if len(scenes) == 1:
+        forces = w.pinned_array(w.n_bodies * 3, np.float64).reshape(-1, 3)   # page-locked host buffers
+        forces[:] = 0.0
+        states = w.pinned_array(w.n_bodies, BODY_STATE)
+        for _ in range(3):
+            w.set_body_forces(0, forces); w.step(dt); w.bodies_into(states)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k2):
+            w.set_body_forces(0, forces); w.step(dt); w.bodies_into(states)
+        sec = time.perf_counter() - t0
+        n_api = w.n_bodies
+        t_e = torch.tensor([sec], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": nb * world * k2 / float(t_e.item()), "unit": "body-steps/s", "steps": k2,
+               "h2d_bytes_per_step": int(n_api * 24), "d2h_bytes_per_step": int(n_api * BODY_STATE.itemsize),
+               "ms_per_step": 1000.0 * float(t_e.item()) / k2,
+               "path": "C-ABI with page-locked host arrays: cpb200_world_set_body_forces -> cpb200_world_step -> cpb200_world_get_bodies (all bodies, every step)"}
+    except Exception as exc:  # keep the device-resident number even if something on the host path is missing
+        e2e = {"value": None, "unit": "body-steps/s", "error": str(exc)}
+    if len(scenes) == 1:
+        try:
+            k3 = max(1, min(args.steps, 5))
             api = SceneSpace(load_scene_lib(), scenes[0].blob)
             api.step(dt, settle)
             api.e2e_steps(dt, 2)
             barrier()
-            sec, _pos = api.e2e_steps(dt, k2)
-            n_api = api.n_bodies
+            sec, _pos = api.e2e_steps(dt, k3)
+            t_a = torch.tensor([sec], dtype=torch.float64, device="cuda")
+            if dist is not None:
+                dist.all_reduce(t_a, op=dist.ReduceOp.MAX)
+            e2e_api = {"value": nb * world * k3 / float(t_a.item()), "unit": "body-steps/s", "steps": k3,
+                       "h2d_bytes_per_step": int(api.n_bodies * 24), "d2h_bytes_per_step": int(api.n_bodies * BODY_STATE.itemsize),
+                       "ms_per_step": 1000.0 * float(t_a.item()) / k3,
+                       "path": "cpBodySetForce on every body -> cpSpaceStep -> cpBodyGetPosition on every body (scene_io.c cpb_scene_e2e_steps)"}
             api.space = None
-            e2e_bodies = nb
-        else:
-            # batched layout: the reference's C API has no batched entry point (one cpSpace = one world), so the
-            # call a user of this workload makes is the engine's batched world with HOST buffers: forces for
-            # every body in, cpSpaceStep for all spaces, every body's state out -- each step, inside the timer
-            import numpy as np, time
-            forces = w.pinned_array(w.n_bodies * 3, np.float64).reshape(-1, 3)   # page-locked host buffers
-            forces[:] = 0.0
-            states = w.pinned_array(w.n_bodies, BODY_STATE)
-            for _ in range(2):
-                w.set_body_forces(0, forces); w.step(dt); w.bodies_into(states)
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(k2):
-                w.set_body_forces(0, forces); w.step(dt); w.bodies_into(states)
-            sec = time.perf_counter() - t0
-            n_api = w.n_bodies
-            e2e_bodies = nb
-        t_e = torch.tensor([sec], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        e2e = {"value": e2e_bodies * world * k2 / float(t_e.item()), "unit": "body-steps/s", "steps": k2,
-               "h2d_bytes_per_step": int(n_api * 24), "d2h_bytes_per_step": int(n_api * BODY_STATE.itemsize),
-               "ms_per_step": 1000.0 * float(t_e.item()) / k2,
-               "path": ("cpBodySetForce on every body -> cpSpaceStep -> cpBodyGetPosition on every body (scene_io.c cpb_scene_e2e_steps)" if len(scenes) == 1 else
-                        "World.set_body_forces(page-locked host array) -> World.step -> World.bodies_into(page-locked host array) over all spaces (the reference's C API has no batched entry point)")}
-    except Exception as exc:  # keep the device-resident number even if the API libs are missing
-        e2e = {"value": None, "unit": "body-steps/s", "error": str(exc)}
+        except Exception as exc:
+            e2e_api = {"value": None, "unit": "body-steps/s", "error": str(exc)}
 
     if dist is not None:
         # every rank leaves the process group together, BEFORE rank 0 goes on to its CPU-only work
@@ -326,6 +339,7 @@ def run_ours(args):
         "clocks": clocks,
         "gpu_launches": int(launches),
         "e2e": e2e,
+        "e2e_per_body_api": e2e_api,
         "roofline": {"bound": "hbm", "kernel": "k_colour_solve (persistent colouring + warm start + %d Gauss-Seidel iterations)" % iterations,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                      **({"note": "batched small spaces are solved from shared memory / L2 (space-local solver): the algorithmic bytes never reach HBM, so this fraction can exceed 1 and is not a bound for this workload"} if args.workload == "batch" else {}),

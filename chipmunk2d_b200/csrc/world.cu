@@ -396,6 +396,14 @@ __global__ void k_pack_body_state(DBodies B, cpb200_body_state *__restrict__ dst
 	dst[k] = o;
 }
 
+__global__ void k_pack_body_bias(DBodies B, double *__restrict__ dst, int first, int n)
+{
+	int k = CPB_TID;
+	if(k >= n) return;
+	double4 VB = B.VB[first + k];
+	dst[3*k] = VB.x; dst[3*k + 1] = VB.y; dst[3*k + 2] = VB.z;
+}
+
 __global__ void k_set_forces(DBodies B, const double *__restrict__ fxyt, int first, int n)
 {
 	int k = CPB_TID;
@@ -1216,6 +1224,18 @@ extern "C" int cpb200_world_get_bodies(cpb200_world *w, int first, int n, cpb200
 	size_t bytes = sizeof(cpb200_body_state)*(size_t)n;
 	if(stage_reserve(w, bytes)) return -1;
 	LAUNCH(k_pack_body_state, grid_for(n, 128), 128, w->stream, w->B, (cpb200_body_state *)w->d_stage, first, n);
+	CPB_CHECK(cudaMemcpyAsync(out, w->d_stage, bytes, cudaMemcpyDeviceToHost, w->stream));
+	return world_sync(w);
+}
+
+extern "C" int cpb200_world_get_body_bias(cpb200_world *w, int first, int n, double *out)
+{
+	if(!w || first < 0 || n < 0 || first + n > w->B.n){ cpb_set_error("body range out of bounds"); return -1; }
+	if(n == 0) return 0;
+	cudaSetDevice(w->device);
+	size_t bytes = 3*sizeof(double)*(size_t)n;
+	if(stage_reserve(w, bytes)) return -1;
+	LAUNCH(k_pack_body_bias, grid_for(n, 128), 128, w->stream, w->B, (double *)w->d_stage, first, n);
 	CPB_CHECK(cudaMemcpyAsync(out, w->d_stage, bytes, cudaMemcpyDeviceToHost, w->stream));
 	return world_sync(w);
 }

@@ -164,6 +164,8 @@ struct cpSpace {
 	cpBool touchDirty;         /* some awake body was activated: its idle timer restarts on the device */
 	cpBool paramsDirty;
 	cpBool hostStale;          /* device has newer body state than the last download */
+	cpBool biasStale;          /* the device holds bias velocities of the last step that the mirrors do not */
+	int nBodiesOnDevice;       /* body count of the last upload (host slot == device index below it) */
 	unsigned fetchStamp;       /* bumped by every download; bodies unpack their record on first access */
 	cpBool someMirrorsStale;   /* a download happened and not every body has unpacked its record yet */
 	cpBool bbStale, arbStale, jointStale;
@@ -183,6 +185,7 @@ struct cpSpace {
 /* internal helpers */
 void cpSpacePrepareDeviceB200(cpSpace *space);
 void cpSpaceFetchBodiesB200(cpSpace *space);
+void cpSpaceFetchBiasB200(cpSpace *space);
 void cpSpaceFetchArbitersB200(cpSpace *space);
 void cpSpaceFetchJointsB200(cpSpace *space);
 void cpSpaceFetchBBsB200(cpSpace *space);

@@ -275,6 +275,7 @@ static void
 sync_before_edit(cpSpace *space)
 {
 	cpSpaceFetchBodiesB200(space);
+	cpSpaceFetchBiasB200(space);
 	if(space->jointStale) cpSpaceFetchJointsB200(space);
 	space->arbStale = cpTrue;
 }
@@ -442,6 +443,8 @@ upload_bodies(cpSpace *space, cpBool full)
 	int rc = (full ? cpb200_world_set_bodies(space->world, n, descs) : cpb200_world_update_bodies(space->world, 0, n, descs));
 	cpfree(descs);
 	if(rc) cpEngineError("body upload");
+	space->nBodiesOnDevice = n;
+	space->biasStale = cpFalse;
 }
 
 /* grow-only page-locked exchange buffer */
@@ -571,6 +574,7 @@ sync_to_device(cpSpace *space)
 	ensure_world(space);
 	if(space->topologyDirty){
 		cpSpaceFetchBodiesB200(space);
+		cpSpaceFetchBiasB200(space);
 		if(space->jointStale) cpSpaceFetchJointsB200(space);
 		upload_bodies(space, cpTrue);
 		upload_shapes(space);
@@ -580,6 +584,7 @@ sync_to_device(cpSpace *space)
 		space->forcesDirty = cpFalse;
 	} else if(space->bodiesDirty){
 		cpSpaceFetchBodiesB200(space);
+		cpSpaceFetchBiasB200(space);
 		upload_bodies(space, cpFalse);
 		space->bodiesDirty = cpFalse;
 		space->forcesDirty = cpFalse;
@@ -663,6 +668,26 @@ cpSpaceFetchBodiesB200(cpSpace *space)
 }
 
 void cpSpaceSyncB200(cpSpace *space){ cpSpaceFetchBodiesB200(space); }
+
+/* The bias velocities the last step's solver left for the next position update (cpBody.c:511-522) live only on
+ * the device; the mirrors hold zero after a download.  Before the host re-uploads bodies between two steps
+ * (an edited body, a structural change) it takes them back, so that the upload does not cancel the pending
+ * penetration correction -- in the reference they simply stay in the cpBody across such edits.  Must run while
+ * host slots still equal device indices, i.e. before a removal compacts space->bodies. */
+void
+cpSpaceFetchBiasB200(cpSpace *space)
+{
+	if(!space->biasStale || !space->world) return;
+	cpSpaceFetchBodiesB200(space);
+	space->biasStale = cpFalse;
+	int n = space->nBodiesOnDevice;
+	if(n > space->nBodies) n = space->nBodies;
+	if(n <= 0) return;
+	double *vb = (double *)cpcalloc((size_t)n, 3*sizeof(double));
+	if(cpb200_world_get_body_bias(space->world, 0, n, vb)) cpEngineError("bias velocity download");
+	for(int i = 0; i < n; i++){ cpBody *b = space->bodies[i]; b->v_bias = cpv(vb[3*i], vb[3*i + 1]); b->w_bias = vb[3*i + 2]; }
+	cpfree(vb);
+}
 
 void
 cpSpaceFetchBBsB200(cpSpace *space)
@@ -873,6 +898,7 @@ step_once(cpSpace *space, cpFloat dt, cpBool callbacks)
 		space->curr_dt = dt;
 	}
 	space->hostStale = cpTrue;
+	space->biasStale = cpTrue;
 	space->bbStale = cpTrue;
 	space->arbStale = cpTrue;
 	space->jointStale = cpTrue;

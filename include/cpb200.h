@@ -228,6 +228,11 @@ CPB200_API int cpb200_world_sync(cpb200_world *w);
 
 /* Body state after the last step (host buffer of n entries; implies a sync). */
 CPB200_API int cpb200_world_get_bodies(cpb200_world *w, int first, int n, cpb200_body_state *out);
+/* Pending bias velocities: out[n][3] = v_bias.x, v_bias.y, w_bias.  The solver of the last step wrote them and
+ * the NEXT step's position update consumes them (cpBodyUpdatePosition, cpBody.c:511-522), so a host that
+ * re-uploads bodies between two steps (cpb200_world_update_bodies / set_bodies) reads them first and hands them
+ * back in cpb200_body_desc.v_bias / w_bias -- in the reference they simply stay in the cpBody (implies a sync). */
+CPB200_API int cpb200_world_get_body_bias(cpb200_world *w, int first, int n, double *out);
 /* Cached shape AABBs (cpShapeGetBB, cpShape.h:124): out[n][4] = l b r t. */
 CPB200_API int cpb200_world_get_shape_bbs(cpb200_world *w, int first, int n, double *out);
 /* Arbiters of the last step (space->arbiters + cachedArbiters, cpSpaceStep.c:250-288).

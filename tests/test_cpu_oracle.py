@@ -68,6 +68,19 @@ def test_reference_passes_its_restated_known_answers(ref, tmp_path):
     assert out.returncode == 0 and out.stdout.count("PASS") == 8, out.stdout
 
 
+def test_edge_cases_golden_is_the_reference_output(ref, tmp_path):
+    """tests/golden/edge_cases.ref.txt (what tests/test_gpu_edges.py holds the drop-in to) is the output of
+    tests/c/edge_cases.c linked against the unmodified reference -- regenerate it with exactly this recipe."""
+    from oracle.ref import REF_DIR
+    exe = str(tmp_path / "edge_cases_ref")
+    subprocess.check_call(["gcc", "-O1", "-w", "-o", exe, os.path.join(ROOT, "tests/c/edge_cases.c"), "-I", os.path.join(ROOT, "include"),
+                           "-L", REF_DIR, "-lchipmunk_ref", "-Wl,-rpath," + REF_DIR, "-lm"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0
+    with open(os.path.join(ROOT, "tests/golden/edge_cases.ref.txt")) as f:
+        assert out.stdout == f.read()
+
+
 def test_pair_set_is_index_independent(ref):
     """the surviving pair set equals brute force over cached AABBs; spot-check that the
     probe's brute force agrees with the arbiters the reference actually created (every arbiter's pair is in it)."""
