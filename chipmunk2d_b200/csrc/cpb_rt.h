@@ -48,6 +48,7 @@ struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
 struct uint2 { unsigned x, y; };
 struct ulonglong2 { unsigned long long x, y; };
+static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y){ ulonglong2 v; v.x = x; v.y = y; return v; }
 static inline double2 make_double2(double x, double y){ double2 r = {x, y}; return r; }
 static inline double4 make_double4(double x, double y, double z, double w){ double4 r = {x, y, z, w}; return r; }
 static inline int2 make_int2(int x, int y){ int2 r = {x, y}; return r; }

@@ -60,7 +60,10 @@ struct DShapes {
 	double4 *bb;          // (l, b, r, t)
 	// packed copies for the narrowphase's random gathers (one 32-byte sector instead of 3-6 scattered words)
 	double4 *mat;         // (e, u, surface_v.x, surface_v.y), static
-	double4 *circ;        // circles: (tc.x, tc.y, r, bits: body index | sensor << 31), rewritten by k_shape_cache
+	double4 *circ;        // circles, one 64-byte line per shape, rewritten by k_shape_cache: [2s] = (tc.x, tc.y, r, bits) with
+	                      // bits = body index (29) | has surface velocity << 29 | body not dynamic << 30 | sensor << 31 | hashid << 32;
+	                      // [2s+1] = (body p.x, p.y, e, u).  The circle-circle narrowphase gathers sector 0 of both shapes for the
+	                      // test and, on a hit, sector 1 of the same lines: two DRAM bursts per pair instead of ten scattered sectors
 	uint2 *ids;           // (hashid, hlocal)
 };
 
@@ -100,8 +103,11 @@ struct DArbs {
 
 // open-addressing table: shape-pair key -> arbiter record index (replaces cpHashSet cachedArbiters)
 struct DTable {
-	uint32_t mask;         // capacity - 1 (capacity is a power of two)
+	uint32_t mask;         // allocated capacity - 1 (capacity is a power of two)
 	ulonglong2 *slots;     // x = key (0 = empty), y = record index: one 16-byte access per probe
+	uint32_t *dmask;       // device word: the mask in use = smallest power of two >= 2 x this step's records, minus 1
+	                       // (k_table_clear): the table is rebuilt every step, so it is only as large -- to clear and to
+	                       // scatter over -- as the step needs, not as the capacity allows
 };
 
 // ---- colour-sorted solver rows (one per active arbiter), rebuilt every step ----

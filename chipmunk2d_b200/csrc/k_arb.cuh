@@ -43,32 +43,74 @@ CPB_DEVICE uint64_t arb_key(uint32_t ha, uint32_t hb){
 	return (lo << 32) | hi;
 }
 
+#ifndef CPB_EMU
+__device__ __forceinline__ ulonglong2 ld_slot(const ulonglong2 *p){   // one 128-bit load per probe (the tables are read-only while probed)
+	ulonglong2 v;
+	asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+	return v;
+}
+#else
+static inline ulonglong2 ld_slot(const ulonglong2 *p){ return *p; }
+#endif
+
 CPB_DEVICE int table_find(const DTable &T, uint64_t key){
-	uint32_t slot = (uint32_t)mix64(key) & T.mask;
-	for(uint32_t probe = 0; probe <= T.mask; probe++){
-		ulonglong2 e = T.slots[slot];
+	const uint32_t mask = *T.dmask;
+	uint32_t slot = (uint32_t)mix64(key) & mask;
+	for(uint32_t probe = 0; probe <= mask; probe++){
+		ulonglong2 e = ld_slot(&T.slots[slot]);
 		if(e.x == key) return (int)e.y;
 		if(e.x == 0) return -1;
-		slot = (slot + 1) & T.mask;
+		slot = (slot + 1) & mask;
 	}
 	return -1;
 }
 
-CPB_DEVICE bool table_insert(const DTable &T, uint64_t key, int val){
-	uint32_t slot = (uint32_t)mix64(key) & T.mask;
-	for(uint32_t probe = 0; probe <= T.mask; probe++){
+CPB_DEVICE bool table_insert(const DTable &T, uint32_t mask, uint64_t key, int val){
+	uint32_t slot = (uint32_t)mix64(key) & mask;
+	for(uint32_t probe = 0; probe <= mask; probe++){
 		unsigned long long old = atomicCAS(&T.slots[slot].x, 0ull, (unsigned long long)key);
 		if(old == 0ull || old == (unsigned long long)key){ T.slots[slot].y = (unsigned long long)val; return true; }
-		slot = (slot + 1) & T.mask;
+		slot = (slot + 1) & mask;
 	}
 	return false;
 }
 
+// The table of this step's records is built in one pass AFTER the collision phase and the cache filter have
+// appended them (k_collide, k_arb_carry): inside those kernels the insert's compare-and-swap sat at the end of a
+// chain of dependent memory accesses per pair (a quarter of k_collide's stall samples); here every record is an
+// independent thread.  The table is sized to the records of the step: clear (which picks the size) -> build.
+__global__ void k_table_clear(DArbs cur, DTable T)
+{
+	int n = *cur.count_ptr; if(n > cur.cap) n = cur.cap;
+	uint32_t want = 64;
+	while(want < 2u*(uint32_t)n && want - 1u < T.mask) want <<= 1;
+	const uint32_t mask = want - 1u;
+	if(CPB_TID == 0) *T.dmask = mask;       // read by k_table_build and by the next step's lookups
+	for(size_t i = CPB_TID; i <= (size_t)mask; i += CPB_NTHREADS) T.slots[i] = make_ulonglong2(0ull, 0ull);
+}
+
+__global__ void k_table_build(DArbs cur, DTable T, DCounters *C)
+{
+	int n = *cur.count_ptr; if(n > cur.cap) n = cur.cap;
+	const uint32_t mask = *T.dmask;
+	for(int i = CPB_TID; i < n; i += CPB_NTHREADS){
+		uint64_t key = cur.key[i];
+		if(key == ~0ull || key == 0ull) continue;
+		if(!table_insert(T, mask, key, i)) atomicOr((unsigned *)&C->overflow, 4u);
+	}
+}
+
 // K5 + K6 for one pair class (CLS 0 circle-circle, 1 circle-segment, 2 GJK family).
 // P lists shape pairs with a.type <= b.type.  Block-stride loop over a device-side count.
+#ifndef CPB_COLLIDE_CTAS
+#define CPB_COLLIDE_CTAS 8
+#endif
+#ifndef CPB_COLLIDE_MINB
+#define CPB_COLLIDE_MINB 1
+#endif
 template <int CLS>
-__global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int *__restrict__ pa, const int *__restrict__ pb, const int *__restrict__ pcount, int pcap,
-	DArbs prev, DTable prev_table, DArbs cur, DTable cur_table, uint32_t stamp, DCounters *C)
+__global__ void __launch_bounds__(128, (CLS == 0 ? CPB_COLLIDE_MINB : 1)) k_collide(DShapes S, DBodies B, const int *__restrict__ pa, const int *__restrict__ pb, const int *__restrict__ pcount, int pcap,
+	DArbs prev, DTable prev_table, DArbs cur, uint32_t stamp, DCounters *C)
 {
 	int np = *pcount; if(np > pcap) np = pcap;
 	for(int base = blockIdx.x*blockDim.x; base < np; base += gridDim.x*blockDim.x){
@@ -87,23 +129,30 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 		int type_a = 0, type_b = 0;
 		if(i < np){
 			sa = pa[i]; sb = pb[i];
-			ida = S.ids[sa]; idb = S.ids[sb];
-			key = arb_key(ida.x, idb.x);
 			if(CLS == 0){
-				// circle-circle: everything the test needs sits in one packed sector per shape
-				double4 ca = ld4_nc(&S.circ[sa]), cb = ld4_nc(&S.circ[sb]);
+				// circle-circle: everything the test needs sits in sector 0 of one packed line per shape, everything a
+				// hit needs beyond that in sector 1 of the same lines (cpb_world.h)
+				double4 ca = ld4_nc(&S.circ[2*(size_t)sa]), cb = ld4_nc(&S.circ[2*(size_t)sb]);
 				NShape a, b;
 				a.type = 0; a.a = v2(ca.x, ca.y); a.r = ca.z; b.type = 0; b.a = v2(cb.x, cb.y); b.r = cb.z;
-				unsigned wa_ = (unsigned)__double_as_longlong(ca.w), wb_ = (unsigned)__double_as_longlong(cb.w);
-				ba = (int)(wa_ & 0x7fffffffu); bb = (int)(wb_ & 0x7fffffffu); sensor = ((wa_ | wb_) >> 31) != 0;
+				const unsigned long long wa_ = (unsigned long long)__double_as_longlong(ca.w), wb_ = (unsigned long long)__double_as_longlong(cb.w);
+				ba = (int)(wa_ & 0x1fffffffull); bb = (int)(wb_ & 0x1fffffffull); sensor = (((wa_ | wb_) >> 31) & 1ull) != 0;
+				ida.x = (uint32_t)(wa_ >> 32); idb.x = (uint32_t)(wb_ >> 32);
+				key = arb_key(ida.x, idb.x);
 				circle_to_circle(a, b, m);
 				if(m.count > 0){
-					pa_ = B.pos[ba]; pb_ = B.pos[bb]; type_a = B.type[ba]; type_b = B.type[bb];
-					ma = ld4_nc(&S.mat[sa]); mb = ld4_nc(&S.mat[sb]);
+					double4 da = ld4_nc(&S.circ[2*(size_t)sa + 1]), db = ld4_nc(&S.circ[2*(size_t)sb + 1]);
 					pi = table_find(prev_table, key);
+					pa_ = v2(da.x, da.y); pb_ = v2(db.x, db.y);
+					ma = make_double4(da.z, da.w, 0.0, 0.0); mb = make_double4(db.z, db.w, 0.0, 0.0);
+					type_a = ((wa_ >> 30) & 1ull) ? CPB200_BODY_STATIC : CPB200_BODY_DYNAMIC;   // only "dynamic or not" matters below
+					type_b = ((wb_ >> 30) & 1ull) ? CPB200_BODY_STATIC : CPB200_BODY_DYNAMIC;
+					if(((wa_ | wb_) >> 29) & 1ull){ ma = ld4_nc(&S.mat[sa]); mb = ld4_nc(&S.mat[sb]); }    // surface velocities are rare
 				}
 				if(pi >= 0){ w0 = ld4_nc(&prev.warm[2*pi]); w1 = ld4_nc(&prev.warm[2*pi + 1]); }
 			} else {
+				ida = S.ids[sa]; idb = S.ids[sb];
+				key = arb_key(ida.x, idb.x);
 				ba = S.body[sa]; bb = S.body[sb]; sensor = (S.sensor[sa] || S.sensor[sb]);
 				pi = table_find(prev_table, key);
 				if(pi >= 0){ w0 = ld4_nc(&prev.warm[2*pi]); w1 = ld4_nc(&prev.warm[2*pi + 1]); }
@@ -168,7 +217,9 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 		cur.stamp[slot] = stamp;
 		cur.seen[slot] = 0;
 		cur.colour[slot] = -1;
-		cur.pri[slot] = mix64(arb_key(ida.y, idb.y)) >> 8;
+		// colouring priority: hash of the space-local shape pair; circle pairs never loaded the local ids, the
+		// colouring resolves the sentinel for the few records it has to colour afresh (arb_pri, k_solve.cuh)
+		cur.pri[slot] = (CLS == 0 ? ~0ull : mix64(arb_key(ida.y, idb.y)) >> 8);
 		cur.hint[slot] = (pi >= 0 && pactive == 1 ? pcolour : -1);
 		cur.active[slot] = active ? 1 : 0;
 		cur.state[slot] = state;
@@ -183,7 +234,6 @@ __global__ void __launch_bounds__(128) k_collide(DShapes S, DBodies B, const int
 #else
 		if(active){ atomicAdd(&C->n_active, 1); atomicAdd(&C->n_contacts, m.count); }
 #endif
-		if(!table_insert(cur_table, key, slot)) atomicOr((unsigned *)&C->overflow, 4u);
 	}
 }
 
@@ -203,7 +253,7 @@ __global__ void k_pack_warm(DArbs A)
 
 // cpSpaceArbiterSetFilter (cpSpaceStep.c:292-325) over the previous step's records that the
 // collision phase did not touch.
-__global__ void k_arb_carry(DBodies B, DArbs prev, DArbs cur, DTable cur_table, const DSpace *__restrict__ spaces, uint32_t stamp, DCounters *C)
+__global__ void k_arb_carry(DBodies B, DArbs prev, DArbs cur, const DSpace *__restrict__ spaces, uint32_t stamp, DCounters *C)
 {
 	int n_prev = *prev.count_ptr; if(n_prev > prev.cap) n_prev = prev.cap;
 	for(int base = blockIdx.x*blockDim.x; base < n_prev; base += gridDim.x*blockDim.x){
@@ -270,7 +320,6 @@ __global__ void k_arb_carry(DBodies B, DArbs prev, DArbs cur, DTable cur_table, 
 		}
 		if(new_active == 1){ atomicAdd(&C->n_active, 1); atomicAdd(&C->n_contacts, cnt); }
 		else atomicAdd(&C->n_cached, 1);
-		if(!table_insert(cur_table, key, slot)) atomicOr((unsigned *)&C->overflow, 4u);
 	}
 }
 

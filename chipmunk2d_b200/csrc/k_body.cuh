@@ -50,7 +50,14 @@ __global__ void k_shape_cache(DShapes S, DBodies B, int all)
 		V2 c = xf_point(T, S.la[s]);
 		S.wa[s] = c;
 		S.bb[s] = make_double4(c.x - rad, c.y - rad, c.x + rad, c.y + rad);
-		S.circ[s] = make_double4(c.x, c.y, rad, __longlong_as_double((long long)((unsigned)b | (S.sensor[s] ? 0x80000000u : 0u))));
+		// the packed line of the circle-circle narrowphase (cpb_world.h)
+		const double4 mt = S.mat[s];
+		const V2 bp = B.pos[b];
+		const unsigned lo = ((unsigned)b & 0x1fffffffu) | ((mt.z != 0.0 || mt.w != 0.0) ? 0x20000000u : 0u) |
+			(B.type[b] != CPB200_BODY_DYNAMIC ? 0x40000000u : 0u) | (S.sensor[s] ? 0x80000000u : 0u);
+		const unsigned long long bits = (unsigned long long)lo | ((unsigned long long)S.ids[s].x << 32);
+		S.circ[2*(size_t)s] = make_double4(c.x, c.y, rad, __longlong_as_double((long long)bits));
+		S.circ[2*(size_t)s + 1] = make_double4(bp.x, bp.y, mt.x, mt.y);
 	} else if(type == CPB200_SHAPE_SEGMENT){
 		V2 ta = xf_point(T, S.la[s]);
 		V2 tb = xf_point(T, S.lb[s]);

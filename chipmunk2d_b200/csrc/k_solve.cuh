@@ -30,6 +30,7 @@ struct DColour {
 	int *jcount, *jstart, *jcursor;   // [CPB_MAX_COLOURS + 1] joints per colour
 	int *wl[2];                  // worklists of still uncoloured constraints (ping-pong per round)
 	int *wl_n;                   // [CPB_MAX_COLOUR_ROUNDS + 2] worklist length entering each round
+	const uint2 *ids;            // DShapes::ids (hashid, hlocal): priorities of records that carry the ~0 sentinel
 	unsigned long long *prof;    // [8] globaltimer stamps of the persistent kernel (start, coloured, rows built, warm start done, end) + rounds
 };
 
@@ -59,6 +60,17 @@ CPB_DEVICE bool cons_fetch(const DArbs &A, const DJoints &J, int nA, int c, int 
 		pri = J.pri[j];
 	}
 	return true;
+}
+
+// priority of a worklist constraint; k_collide<0> leaves ~0 instead of gathering the space-local shape ids for
+// every circle pair (only records that must be coloured afresh ever need them)
+CPB_DEVICE uint64_t cons_pri(const DArbs &A, const DColour &K, int nA, int c, uint64_t pri){
+	if(c < nA && pri == ~0ull){
+		uint32_t la = K.ids[A.sa[c]].y, lb = K.ids[A.sb[c]].y;
+		uint64_t lo = (la < lb ? la : lb), hi = (la < lb ? lb : la);
+		pri = mix64((lo << 32) | hi) >> 8;
+	}
+	return pri;
 }
 
 // per-colour histogram: block-local in shared memory inside the persistent kernel (one global atomic per
@@ -104,6 +116,7 @@ CPB_DEVICE void colour_phase_a(const DBodies &B, const DArbs &A, const DJoints &
 		int c = wl[k];
 		int a, b, col; uint64_t pri;
 		cons_fetch(A, J, nA, c, a, b, pri, col);
+		pri = cons_pri(A, K, nA, c, pri);
 		unsigned long long bid = ((unsigned long long)(round + 1) << 56) | pri;
 		if(body_is_dynamic(B, a)) atomicMax(&K.claim[a], bid);
 		if(body_is_dynamic(B, b)) atomicMax(&K.claim[b], bid);
@@ -122,6 +135,7 @@ CPB_DEVICE void colour_phase_b(const DBodies &B, const DArbs &A, const DJoints &
 			c = wl[k];
 			int a, b, col; uint64_t pri;
 			cons_fetch(A, J, nA, c, a, b, pri, col);
+			pri = cons_pri(A, K, nA, c, pri);
 			unsigned long long bid = ((unsigned long long)(round + 1) << 56) | pri;
 			bool da = body_is_dynamic(B, a), db = body_is_dynamic(B, b);
 			bool win = (!da || ld_u64(&K.claim[a]) == bid) && (!db || ld_u64(&K.claim[b]) == bid);

@@ -540,6 +540,9 @@ static int alloc_arbs(cpb200_world *w, int cap)
 		DTable &T = w->T[k];
 		T.mask = tcap - 1;
 		DA(w->gA, T.slots, tcap);
+		DA(w->gA, T.dmask, 4);
+		CPB_CHECK(cudaMemcpyAsync(T.dmask, &T.mask, sizeof(uint32_t), cudaMemcpyHostToDevice, 0));
+		CPB_CHECK(cudaStreamSynchronize(0));
 	}
 	DRows &R = w->R;
 	R.cap = cap;
@@ -612,7 +615,7 @@ extern "C" int cpb200_world_set_shapes(cpb200_world *w, int n, const cpb200_shap
 	DA(w->gS, S.group, n); DA(w->gS, S.ctype, n); DA(w->gS, S.e, n); DA(w->gS, S.u, n); DA(w->gS, S.r, n); DA(w->gS, S.surfv, n);
 	DA(w->gS, S.la, n); DA(w->gS, S.lb, n); DA(w->gS, S.ln, n); DA(w->gS, S.atan, n); DA(w->gS, S.btan, n);
 	DA(w->gS, S.pcount, n); DA(w->gS, S.poff, n); DA(w->gS, S.lpv, n_verts); DA(w->gS, S.lpn, n_verts);
-	DA(w->gS, S.mat, n); DA(w->gS, S.circ, n); DA(w->gS, S.ids, n);
+	DA(w->gS, S.mat, n); DA(w->gS, S.circ, 2*(size_t)n); DA(w->gS, S.ids, n);
 	DA(w->gS, S.wa, n); DA(w->gS, S.wb, n); DA(w->gS, S.wn, n); DA(w->gS, S.wpv, n_verts); DA(w->gS, S.wpn, n_verts); DA(w->gS, S.bb, n);
 	if(upload(w, S.type, type) || upload(w, S.body, body) || upload(w, S.hashid, hashid) || upload(w, S.hlocal, hlocal) || upload(w, S.sensor, sensor) || upload(w, S.cat, cat) ||
 	   upload(w, S.mask, mask) || upload(w, S.group, group) || upload(w, S.ctype, ctype) || upload(w, S.e, e) || upload(w, S.u, u) || upload(w, S.r, r) ||
@@ -907,7 +910,6 @@ static int step_phase_a(cpb200_world *w, double dt)
 	DArbs &Ap = w->A[prv]; DArbs &Ac = w->A[w->cur];
 	DTable &Tp = w->T[prv]; DTable &Tc = w->T[w->cur];
 	LAUNCH(k_reset_step, 1, 32, st, w->C, w->P.count, Ac.count_ptr, w->K.ccount, w->K.jcount, w->K.wl_n);
-	cudaMemsetAsync(Tc.slots, 0, sizeof(ulonglong2)*((size_t)Tc.mask + 1), st);
 
 	const int nb = B.n, ns = S.n;
 	const int wide = w->sm_count*8;
@@ -961,11 +963,11 @@ static int step_phase_a(cpb200_world *w, double dt)
 
 	// K5 + K6
 	{
-		int g = std::min(grid_for(w->P.cap, 128), wide);
+		int g = std::min(grid_for(w->P.cap, 128), w->sm_count*CPB_COLLIDE_CTAS);
 		LAUNCH(k_pack_warm, std::min(grid_for(Ap.cap, 256), wide), 256, st, Ap);
-		LAUNCH(k_collide<0>, g, 128, st, S, B, (const int *)w->P.a[0], (const int *)w->P.b[0], (const int *)&w->P.count[0], w->P.cap, Ap, Tp, Ac, Tc, w->stamp, w->C);
-		LAUNCH(k_collide<1>, g, 128, st, S, B, (const int *)w->P.a[1], (const int *)w->P.b[1], (const int *)&w->P.count[1], w->P.cap, Ap, Tp, Ac, Tc, w->stamp, w->C);
-		LAUNCH(k_collide<2>, g, 128, st, S, B, (const int *)w->P.a[2], (const int *)w->P.b[2], (const int *)&w->P.count[2], w->P.cap, Ap, Tp, Ac, Tc, w->stamp, w->C);
+		LAUNCH(k_collide<0>, g, 128, st, S, B, (const int *)w->P.a[0], (const int *)w->P.b[0], (const int *)&w->P.count[0], w->P.cap, Ap, Tp, Ac, w->stamp, w->C);
+		LAUNCH(k_collide<1>, g, 128, st, S, B, (const int *)w->P.a[1], (const int *)w->P.b[1], (const int *)&w->P.count[1], w->P.cap, Ap, Tp, Ac, w->stamp, w->C);
+		LAUNCH(k_collide<2>, g, 128, st, S, B, (const int *)w->P.a[2], (const int *)w->P.b[2], (const int *)&w->P.count[2], w->P.cap, Ap, Tp, Ac, w->stamp, w->C);
 	}
 	STAGE_END(w, ST_COLLIDE);
 	w->step_dt = dt; w->step_dt_coef = dt_coef; w->step_iterations = iterations;
@@ -996,7 +998,10 @@ static int step_phase_b(cpb200_world *w)
 
 	{
 		int g = std::min(grid_for(Ap.cap, CPB_CARRY_BLOCK), w->sm_count*CPB_CARRY_CTAS);
-		LAUNCH(k_arb_carry, g, CPB_CARRY_BLOCK, st, B, Ap, Ac, Tc, (const DSpace *)w->d_spaces, w->stamp, w->C);
+		LAUNCH(k_arb_carry, g, CPB_CARRY_BLOCK, st, B, Ap, Ac, (const DSpace *)w->d_spaces, w->stamp, w->C);
+		// the table of this step's records (next step's warm-start lookups), sized to what the step produced
+		LAUNCH(k_table_clear, std::min(grid_for(Ac.cap, 128), wide), 256, st, Ac, Tc);
+		LAUNCH(k_table_build, std::min(grid_for(Ac.cap, 256), wide*2), 256, st, Ac, Tc, w->C);
 	}
 	STAGE_END(w, ST_CARRY);
 
@@ -1027,6 +1032,7 @@ static int step_phase_b(cpb200_world *w)
 		w->n_user_order = 0; w->n_joint_order = 0;
 	} else {
 		DColour &K = w->K;
+		K.ids = S.ids;
 		// (claim / bmask were cleared by k_integrate_vel, the colour histograms and worklist lengths by k_reset_step)
 		if(ensure_worklists(w, Ac.cap + J.n + 64)) return -1;
 		int use_hints = (w->hints_valid && !w->no_hints ? 1 : 0);
