@@ -86,9 +86,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples that fell inside the timed region [t0, t1].  The sampler is started before the warm-up steps
+        (nvidia-smi needs ~0.2 s to deliver its first line); a timed region shorter than the 100 ms sampling
+        period may hold no sample, then the nearest ones around it (the GPU is under the same load in the warm-up
+        before and in the profiling steps after) are used and `window` says so."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -97,11 +101,19 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        good = [(t, r) for t, r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        window = "timed region"
+        rows = [r for t, r in good if t0 is None or (t0 <= t <= t1 + 0.05)]
+        if not rows and good:
+            mid = 0.5 * (t0 + t1)
+            rows = [r for t, r in sorted(good, key=lambda tr: abs(tr[0] - mid))[:2]]
+            window = "nearest samples (timed region shorter than the sampling period)"
+        sm = [float(r[1]) for r in rows]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for r in self.rows if len(r) >= 9 for k in range(4) if r[5 + k].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({names[k] for r in rows for k in range(4) if r[5 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm), "window": window}
 
 
 def algorithmic_bytes_solver(n_contacts, n_joints, iterations):
@@ -200,21 +212,26 @@ def run_ours(args):
     w.load_scenes(scenes)
     settle = SETTLE.get(args.workload, 0)
     w.step(dt, settle)          # untimed: let contacts form so the timed steps see the settled workload
+    sampler = ClockSampler(local_rank)
+    sampler.start()             # before the warm-up: nvidia-smi takes a moment to deliver its first sample
     w.step(dt, max(3, args.warmup))
     w.sync()
+    t_wait = time.time()
+    while sampler.proc and not sampler.rows and time.time() - t_wait < 2.0:
+        w.step(dt, 5)           # more untimed steps until the clock sampler delivers (keeps the GPU under load)
+        w.sync()
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
     launches0 = w.launch_count()
     barrier()
-    sampler.start()
+    t_wall0 = time.time()
     ms = w.time_steps(dt, args.steps)
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_wall0, time.time())
     launches = w.launch_count() - launches0
     st = w.stats()
 
