@@ -266,7 +266,7 @@ def run_ours(args):
     e2e = None
     e2e_api = None
     try:
-        import numpy as np, time
+
         k2 = max(1, min(args.steps, 10))
         forces = w.pinned_array(w.n_bodies * 3, np.float64).reshape(-1, 3)   # page-locked host buffers
         forces[:] = 0.0

@@ -65,6 +65,8 @@ struct DShapes {
 	                      // [2s+1] = (body p.x, p.y, e, u).  The circle-circle narrowphase gathers sector 0 of both shapes for the
 	                      // test and, on a hit, sector 1 of the same lines: two DRAM bursts per pair instead of ten scattered sectors
 	uint2 *ids;           // (hashid, hlocal)
+	double4 *filt;        // bit patterns (body | type << 32, categories | mask << 32, group, 0), static: everything QueryReject and
+	                      // the pair classes read about a shape in one sector (k_bvh_pairs' flush)
 };
 
 // ---- arbiters + contacts (cpArbiter / cpContact, chipmunk_structs.h:101-145) ----
@@ -176,8 +178,9 @@ struct DBvh {
 // pair lists by class: 0 circle-circle, 1 circle-segment, 2 everything that needs GJK
 struct DPairs {
 	int cap;
-	int *count;            // [3]
+	int *count;            // [4]: pairs per class, [3] = raw candidates
 	int *a[3], *b[3];      // shape indices, a.type <= b.type
+	int2 *cand;            // [cap] leaf hits of the tree traversal, before QueryReject (k_bvh_pairs -> k_pair_filter)
 };
 
 // device-side step counters / flags

@@ -259,20 +259,87 @@ CPB_DEVICE void emit_pair(const DShapes &S, const DPairs &P, int *overflow, int 
 // with a handful of active lanes and waited for a global atomic each time.)
 #define CPB_PAIR_CAND 192     // per warp; a visit appends at most 2 per lane -> flush above CPB_PAIR_CAND - 64
 #ifndef CPB_EMU
-__device__ __forceinline__ void pairs_flush(int2 *cand, int *count, int lane, const DShapes &S, const DPairs &P,
-	const uint64_t *__restrict__ nocollide, int n_nocollide, int *overflow)
+// The traversal only collects leaf hits: when a warp's list runs full (and at the end) it is copied to the global
+// candidate list with one reservation.  QueryReject and the class lists are a pass of their own (k_pair_filter):
+// done inside the traversal, that part needed registers the traversal cannot afford (occupancy is what hides the
+// tree's latency) and put a returning atomic on a hot word behind every 32 hits.
+__device__ __forceinline__ void pairs_flush(int2 *cand, int *count, int lane, const DPairs &P, int *overflow)
 {
 	__syncwarp();
 	const int n = *count;
-	for(int k = lane; k < ((n + 31) & ~31); k += 32){
-		bool hit = (k < n);
-		int2 c = make_int2(0, 0);
-		if(hit){ c = cand[k]; hit = !query_reject(S, c.x, c.y, nocollide, n_nocollide); }
-		if(__any_sync(0xffffffffu, hit)){ if(hit) emit_pair(S, P, overflow, c.x, c.y); }
+	int base = 0;
+	if(lane == 0 && n) base = atomicAdd(&P.count[3], n);
+	base = __shfl_sync(0xffffffffu, base, 0);
+	for(int k = lane; k < n; k += 32){
+		if(base + k < P.cap) P.cand[base + k] = cand[k];
+		else atomicOr((unsigned *)overflow, 1u);
 	}
 	__syncwarp();
 	if(lane == 0) *count = 0;
 	__syncwarp();
+}
+
+// K4 over the candidate list: a warp takes 32 x CPB_FILTER_ROUNDS candidates at a time; every lane filters and
+// classifies its candidates first -- one packed sector per shape (DShapes::filt), no atomic between the rounds, so
+// the gathers of all rounds are in flight together -- then ONE reservation per pair class for the whole chunk
+// (the list counters are single hot words), then the writes in list order.
+#define CPB_FILTER_ROUNDS 4
+__global__ void __launch_bounds__(128) k_pair_filter(DShapes S, DPairs P, const uint64_t *__restrict__ nocollide, int n_nocollide, int *overflow)
+{
+	int n = P.count[3]; if(n > P.cap) n = P.cap;
+	const int lane = threadIdx.x & 31;
+	const int warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x*blockDim.x) >> 5;
+	const int chunk = 32*CPB_FILTER_ROUNDS;
+	for(int first = warp*chunk; first < n; first += n_warps*chunk){
+		int sa[CPB_FILTER_ROUNDS], sb[CPB_FILTER_ROUNDS], cl[CPB_FILTER_ROUNDS];
+		double4 fa[CPB_FILTER_ROUNDS], fb[CPB_FILTER_ROUNDS];
+#pragma unroll
+		for(int t = 0; t < CPB_FILTER_ROUNDS; t++){
+			const int k = first + lane + 32*t;
+			cl[t] = -1; sa[t] = 0; sb[t] = 0;
+			fa[t] = make_double4(0, 0, 0, 0); fb[t] = fa[t];
+			if(k < n){ int2 c = P.cand[k]; sa[t] = c.x; sb[t] = c.y; cl[t] = 3; fa[t] = ld4_nc(&S.filt[c.x]); fb[t] = ld4_nc(&S.filt[c.y]); }
+		}
+		unsigned v0[CPB_FILTER_ROUNDS], v1[CPB_FILTER_ROUNDS], v2[CPB_FILTER_ROUNDS];
+		int tot0 = 0, tot1 = 0, tot2 = 0;
+#pragma unroll
+		for(int t = 0; t < CPB_FILTER_ROUNDS; t++){
+			if(cl[t] == 3){
+				const unsigned long long xa = (unsigned long long)__double_as_longlong(fa[t].x), ya = (unsigned long long)__double_as_longlong(fa[t].y);
+				const unsigned long long xb = (unsigned long long)__double_as_longlong(fb[t].x), yb = (unsigned long long)__double_as_longlong(fb[t].y);
+				const unsigned long long ga = (unsigned long long)__double_as_longlong(fa[t].z), gb = (unsigned long long)__double_as_longlong(fb[t].z);
+				const int ba = (int)(uint32_t)xa, bb = (int)(uint32_t)xb;
+				int ta = (int)(xa >> 32), tb = (int)(xb >> 32);
+				// QueryReject (cpSpaceStep.c:204-232): same body, same non-zero group, category / mask, a joint between the bodies
+				bool rej = (ba == bb) || (ga != 0 && ga == gb) || (((uint32_t)ya & (uint32_t)(yb >> 32)) == 0) || (((uint32_t)yb & (uint32_t)(ya >> 32)) == 0);
+				if(!rej && n_nocollide > 0) rej = nocollide_lookup(nocollide, n_nocollide, ba, bb);
+				if(rej) cl[t] = -1;
+				else {
+					// cpCollide orders by shape type (cpCollision.c:706-710); equal types: lower index first
+					if(ta > tb || (ta == tb && sa[t] > sb[t])){ int x = sa[t]; sa[t] = sb[t]; sb[t] = x; x = ta; ta = tb; tb = x; }
+					cl[t] = (tb == 0 ? 0 : (ta == 0 && tb == 1 ? 1 : 2));
+				}
+			}
+			v0[t] = __ballot_sync(0xffffffffu, cl[t] == 0); v1[t] = __ballot_sync(0xffffffffu, cl[t] == 1); v2[t] = __ballot_sync(0xffffffffu, cl[t] == 2);
+			tot0 += __popc(v0[t]); tot1 += __popc(v1[t]); tot2 += __popc(v2[t]);
+		}
+		int base = 0;
+		if(lane == 0 && tot0) base = atomicAdd(&P.count[0], tot0);
+		if(lane == 1 && tot1) base = atomicAdd(&P.count[1], tot1);
+		if(lane == 2 && tot2) base = atomicAdd(&P.count[2], tot2);
+		int run0 = __shfl_sync(0xffffffffu, base, 0), run1 = __shfl_sync(0xffffffffu, base, 1), run2 = __shfl_sync(0xffffffffu, base, 2);
+		const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+		for(int t = 0; t < CPB_FILTER_ROUNDS; t++){
+			if(cl[t] >= 0){
+				const int c = cl[t];
+				const int slot = (c == 0 ? run0 + __popc(v0[t] & lt) : (c == 1 ? run1 + __popc(v1[t] & lt) : run2 + __popc(v2[t] & lt)));
+				if(slot < P.cap){ P.a[c][slot] = sa[t]; P.b[c][slot] = sb[t]; }
+				else atomicOr((unsigned *)overflow, 1u);
+			}
+			run0 += __popc(v0[t]); run1 += __popc(v1[t]); run2 += __popc(v2[t]);
+		}
+	}
 }
 #endif
 
@@ -340,13 +407,13 @@ __global__ void __launch_bounds__(128) k_bvh_pairs(DBvh T, DShapes S, DBodies B,
 		}
 #ifndef CPB_EMU
 		__syncwarp();
-		if(s_n[wid] > CPB_PAIR_CAND - 64) pairs_flush(s_cand[wid], &s_n[wid], lane, S, P, nocollide, n_nocollide, overflow);
+		if(s_n[wid] > CPB_PAIR_CAND - 64) pairs_flush(s_cand[wid], &s_n[wid], lane, P, overflow);
 #else
 		if(done) break;
 #endif
 	}
 #ifndef CPB_EMU
-	pairs_flush(s_cand[wid], &s_n[wid], lane, S, P, nocollide, n_nocollide, overflow);
+	pairs_flush(s_cand[wid], &s_n[wid], lane, P, overflow);
 #endif
 }
 

@@ -517,6 +517,7 @@ static int alloc_pairs(cpb200_world *w, int cap)
 	w->P.cap = cap;
 	DA(w->gP, w->P.count, 4);
 	for(int c = 0; c < 3; c++){ DA(w->gP, w->P.a[c], cap); DA(w->gP, w->P.b[c], cap); }
+	DA(w->gP, w->P.cand, cap);
 	w->cap_pairs = cap;
 	return 0;
 }
@@ -607,6 +608,12 @@ extern "C" int cpb200_world_set_shapes(cpb200_world *w, int n, const cpb200_shap
 	for(size_t i = 0; i < N; i++){ uint32_t &b = space_base[(size_t)body_space[(size_t)body[i]]]; b = std::min(b, hashid[i]); }
 	for(size_t i = 0; i < N; i++) hlocal[i] = hashid[i] - space_base[(size_t)body_space[(size_t)body[i]]];
 	std::vector<double4> mat(N); std::vector<uint2> ids(N);
+	std::vector<double4> filt(N);
+	for(size_t i = 0; i < N; i++){
+		const unsigned long long x = (unsigned long long)(uint32_t)body[i] | ((unsigned long long)(uint32_t)type[i] << 32);
+		const unsigned long long y = (unsigned long long)cat[i] | ((unsigned long long)mask[i] << 32), z = group[i];
+		memcpy(&filt[i].x, &x, 8); memcpy(&filt[i].y, &y, 8); memcpy(&filt[i].z, &z, 8); filt[i].w = 0.0;
+	}
 	for(size_t i = 0; i < N; i++){ mat[i] = make_double4(e[i], u[i], surfv[i].x, surfv[i].y); ids[i].x = hashid[i]; ids[i].y = hlocal[i]; }
 	w->gS.release();
 	DShapes &S = w->S;
@@ -615,12 +622,12 @@ extern "C" int cpb200_world_set_shapes(cpb200_world *w, int n, const cpb200_shap
 	DA(w->gS, S.group, n); DA(w->gS, S.ctype, n); DA(w->gS, S.e, n); DA(w->gS, S.u, n); DA(w->gS, S.r, n); DA(w->gS, S.surfv, n);
 	DA(w->gS, S.la, n); DA(w->gS, S.lb, n); DA(w->gS, S.ln, n); DA(w->gS, S.atan, n); DA(w->gS, S.btan, n);
 	DA(w->gS, S.pcount, n); DA(w->gS, S.poff, n); DA(w->gS, S.lpv, n_verts); DA(w->gS, S.lpn, n_verts);
-	DA(w->gS, S.mat, n); DA(w->gS, S.circ, 2*(size_t)n); DA(w->gS, S.ids, n);
+	DA(w->gS, S.mat, n); DA(w->gS, S.circ, 2*(size_t)n); DA(w->gS, S.ids, n); DA(w->gS, S.filt, n);
 	DA(w->gS, S.wa, n); DA(w->gS, S.wb, n); DA(w->gS, S.wn, n); DA(w->gS, S.wpv, n_verts); DA(w->gS, S.wpn, n_verts); DA(w->gS, S.bb, n);
 	if(upload(w, S.type, type) || upload(w, S.body, body) || upload(w, S.hashid, hashid) || upload(w, S.hlocal, hlocal) || upload(w, S.sensor, sensor) || upload(w, S.cat, cat) ||
 	   upload(w, S.mask, mask) || upload(w, S.group, group) || upload(w, S.ctype, ctype) || upload(w, S.e, e) || upload(w, S.u, u) || upload(w, S.r, r) ||
 	   upload(w, S.surfv, surfv) || upload(w, S.la, la) || upload(w, S.lb, lb) || upload(w, S.ln, ln) || upload(w, S.atan, atan_) || upload(w, S.btan, btan_) ||
-	   upload(w, S.mat, mat) || upload(w, S.ids, ids) || upload(w, S.pcount, pcount) || upload(w, S.poff, poff) || upload(w, S.lpv, lpv) || upload(w, S.lpn, lpn)) return -1;
+	   upload(w, S.mat, mat) || upload(w, S.ids, ids) || upload(w, S.filt, filt) || upload(w, S.pcount, pcount) || upload(w, S.poff, poff) || upload(w, S.lpv, lpv) || upload(w, S.lpn, lpn)) return -1;
 
 	w->shape_body = body; w->sl_dirty = true;
 
@@ -775,7 +782,7 @@ __global__ void k_reset_step(DCounters *C, int *pair_count, int *cur_count, int 
 	C->n_pairs[0] = C->n_pairs[1] = C->n_pairs[2] = 0;
 	C->n_contacts = 0; C->n_active = 0; C->n_colours = 0; C->n_cached = 0;
 	C->colour_remaining[0] = C->colour_remaining[1] = 0; C->colour_rounds = 0; C->n_overflow_colour = 0;
-	pair_count[0] = pair_count[1] = pair_count[2] = 0;
+	pair_count[0] = pair_count[1] = pair_count[2] = pair_count[3] = 0;
 	*cur_count = 0;
 }
 
@@ -956,6 +963,9 @@ static int step_phase_a(cpb200_world *w, double dt)
 		LAUNCH(k_bvh_pack, grid_for(ns - 1, 256), 256, st, T);
 		STAGE_END(w, ST_BVH_BUILD);
 		LAUNCH(k_bvh_pairs, grid_for(ns, 128), 128, st, T, S, B, w->P, (const uint64_t *)w->d_nocollide, w->n_nocollide, (int)(w->n_spaces > 1), &w->C->overflow);
+#ifndef CPB_EMU
+		LAUNCH(k_pair_filter, std::min(grid_for(w->P.cap, 128*CPB_FILTER_ROUNDS), wide), 128, st, S, w->P, (const uint64_t *)w->d_nocollide, w->n_nocollide, &w->C->overflow);
+#endif
 		STAGE_END(w, ST_BVH_PAIRS);
 	} else {
 		STAGE_END(w, ST_BVH_KEYS); STAGE_END(w, ST_BVH_SORT); STAGE_END(w, ST_BVH_BUILD); STAGE_END(w, ST_BVH_PAIRS);
