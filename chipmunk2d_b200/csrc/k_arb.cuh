@@ -53,8 +53,7 @@ __device__ __forceinline__ ulonglong2 ld_slot(const ulonglong2 *p){   // one 128
 static inline ulonglong2 ld_slot(const ulonglong2 *p){ return *p; }
 #endif
 
-CPB_DEVICE int table_find(const DTable &T, uint64_t key){
-	const uint32_t mask = *T.dmask;
+CPB_DEVICE int table_find(const DTable &T, uint32_t mask, uint64_t key){   // mask = *T.dmask, read once per kernel
 	uint32_t slot = (uint32_t)mix64(key) & mask;
 	for(uint32_t probe = 0; probe <= mask; probe++){
 		ulonglong2 e = ld_slot(&T.slots[slot]);
@@ -100,19 +99,42 @@ __global__ void k_table_build(DArbs cur, DTable T, DCounters *C)
 	}
 }
 
+// small worlds (launch-bound): both passes in one CTA
+#ifndef CPB_EMU
+__global__ void __launch_bounds__(1024) k_table_small(DArbs cur, DTable T, DCounters *C)
+{
+	int n = *cur.count_ptr; if(n > cur.cap) n = cur.cap;
+	uint32_t want = 64;
+	while(want < 2u*(uint32_t)n && want - 1u < T.mask) want <<= 1;
+	const uint32_t mask = want - 1u;
+	if(CPB_TID == 0) *T.dmask = mask;
+	for(size_t i = CPB_TID; i <= (size_t)mask; i += CPB_NTHREADS) T.slots[i] = make_ulonglong2(0ull, 0ull);
+	__syncthreads();
+	for(int i = CPB_TID; i < n; i += CPB_NTHREADS){
+		uint64_t key = cur.key[i];
+		if(key == ~0ull || key == 0ull) continue;
+		if(!table_insert(T, mask, key, i)) atomicOr((unsigned *)&C->overflow, 4u);
+	}
+}
+#endif
+
 // K5 + K6 for one pair class (CLS 0 circle-circle, 1 circle-segment, 2 GJK family).
 // P lists shape pairs with a.type <= b.type.  Block-stride loop over a device-side count.
 #ifndef CPB_COLLIDE_CTAS
 #define CPB_COLLIDE_CTAS 8
 #endif
-#ifndef CPB_COLLIDE_MINB
-#define CPB_COLLIDE_MINB 1
+// The GJK/EPA family must leave room for CPB_COLLIDE_GJK_CTAS resident CTAs per SM (4 -> at most 128 registers; left
+// alone the compiler takes 233 and a third of the warps: +12 % on the polygon scenes).  The circle kernels are
+// faster with the registers they ask for (capped to 80 they spill: +8 % on the 1 M pile).
+#ifndef CPB_COLLIDE_GJK_CTAS
+#define CPB_COLLIDE_GJK_CTAS 4
 #endif
 template <int CLS>
-__global__ void __launch_bounds__(128, (CLS == 0 ? CPB_COLLIDE_MINB : 1)) k_collide(DShapes S, DBodies B, const int *__restrict__ pa, const int *__restrict__ pb, const int *__restrict__ pcount, int pcap,
+__global__ void __launch_bounds__(128, (CLS == 2 ? CPB_COLLIDE_GJK_CTAS : 1)) k_collide(DShapes S, DBodies B, const int *__restrict__ pa, const int *__restrict__ pb, const int *__restrict__ pcount, int pcap,
 	DArbs prev, DTable prev_table, DArbs cur, uint32_t stamp, DCounters *C)
 {
 	int np = *pcount; if(np > pcap) np = pcap;
+	const uint32_t pmask = *prev_table.dmask;
 	int my_active = 0, my_contacts = 0;     // step statistics: summed per thread, flushed once per warp after the loop
 	for(int base = blockIdx.x*blockDim.x; base < np; base += gridDim.x*blockDim.x){
 		int i = base + threadIdx.x;
@@ -143,7 +165,7 @@ __global__ void __launch_bounds__(128, (CLS == 0 ? CPB_COLLIDE_MINB : 1)) k_coll
 				circle_to_circle(a, b, m);
 				if(m.count > 0){
 					double4 da = ld4_nc(&S.circ[2*(size_t)sa + 1]), db = ld4_nc(&S.circ[2*(size_t)sb + 1]);
-					pi = table_find(prev_table, key);
+					pi = table_find(prev_table, pmask, key);
 					pa_ = v2(da.x, da.y); pb_ = v2(db.x, db.y);
 					ma = make_double4(da.z, da.w, 0.0, 0.0); mb = make_double4(db.z, db.w, 0.0, 0.0);
 					type_a = ((wa_ >> 30) & 1ull) ? CPB200_BODY_STATIC : CPB200_BODY_DYNAMIC;   // only "dynamic or not" matters below
@@ -155,7 +177,7 @@ __global__ void __launch_bounds__(128, (CLS == 0 ? CPB_COLLIDE_MINB : 1)) k_coll
 				ida = S.ids[sa]; idb = S.ids[sb];
 				key = arb_key(ida.x, idb.x);
 				ba = S.body[sa]; bb = S.body[sb]; sensor = (S.sensor[sa] || S.sensor[sb]);
-				pi = table_find(prev_table, key);
+				pi = table_find(prev_table, pmask, key);
 				if(pi >= 0){ w0 = ld4_nc(&prev.warm[2*pi]); w1 = ld4_nc(&prev.warm[2*pi + 1]); }
 				m.id = (pi >= 0 ? (uint32_t)((unsigned long long)__double_as_longlong(w1.z) >> 32) : 0u);
 				NShape a = load_nshape(S, B, sa), b = load_nshape(S, B, sb);

@@ -802,7 +802,7 @@ __global__ void k_build_order(DShapes S, DArbs A, DTable T, const uint64_t *__re
 	for(int q = 0; q < n_user; q++){
 		int sa = (int)(user[q] >> 32), sb = (int)(user[q] & 0xffffffffu);
 		if(sa < 0 || sa >= S.n || sb < 0 || sb >= S.n) continue;
-		int idx = table_find(T, arb_key(S.hashid[sa], S.hashid[sb]));
+		int idx = table_find(T, *T.dmask, arb_key(S.hashid[sa], S.hashid[sb]));
 		if(idx >= 0 && A.active[idx] == 1 && !A.seen[idx]){
 			// bit 30 = the caller's a/b orientation is the reverse of ours: contacts are then visited in
 			// reverse, which is the order the reference's ContactPoints produced them in (cpCollision.c:477-518)
@@ -1010,8 +1010,14 @@ static int step_phase_b(cpb200_world *w)
 		int g = std::min(grid_for(Ap.cap, CPB_CARRY_BLOCK), w->sm_count*CPB_CARRY_CTAS);
 		LAUNCH(k_arb_carry, g, CPB_CARRY_BLOCK, st, B, Ap, Ac, (const DSpace *)w->d_spaces, w->stamp, w->C);
 		// the table of this step's records (next step's warm-start lookups), sized to what the step produced
-		LAUNCH(k_table_clear, std::min(grid_for(Ac.cap, 128), wide), 256, st, Ac, Tc);
-		LAUNCH(k_table_build, std::min(grid_for(Ac.cap, 256), wide*2), 256, st, Ac, Tc, w->C);
+#ifndef CPB_EMU
+		if(Ac.cap <= 65536) LAUNCH(k_table_small, 1, 1024, st, Ac, Tc, w->C);
+		else
+#endif
+		{
+			LAUNCH(k_table_clear, std::min(grid_for(Ac.cap, 128), wide), 256, st, Ac, Tc);
+			LAUNCH(k_table_build, std::min(grid_for(Ac.cap, 256), wide*2), 256, st, Ac, Tc, w->C);
+		}
 	}
 	STAGE_END(w, ST_CARRY);
 

@@ -5,7 +5,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from chipmunk2d_b200.engine import World
-from chipmunk2d_b200.scenes import circle_pile, batched_demo_scenes, golden_scene
+from chipmunk2d_b200.scenes import circle_pile, batched_demo_scenes, golden_scene, mixed_drop
 
 def run(lib, scenes, warm, steps):
     w = World(len(scenes), lib_path=lib)
@@ -23,7 +23,8 @@ def run(lib, scenes, warm, steps):
 if __name__ == "__main__":
     libs = sys.argv[1:]
     sets = {"pile1m": ([circle_pile(1000000, dense=True, sleep=np.inf)], 40, 30), "batch4096": (batched_demo_scenes(4096), 300, 100),
-            "c1": ([golden_scene("SimpleTerrainCircles_1000")], 200, 300)}
+            "c1": ([golden_scene("SimpleTerrainCircles_1000")], 200, 300), "c2": ([golden_scene("ComplexTerrainHexagons_1000")], 200, 300),
+            "mixed100k": ([mixed_drop(100000)], 120, 60)}
     only = os.environ.get("SETS")
     for name, (sc, warm, steps) in sets.items():
         if only and name not in only.split(","): continue
