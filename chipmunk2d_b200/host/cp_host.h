@@ -166,6 +166,8 @@ struct cpSpace {
 	cpBool hostStale;          /* device has newer body state than the last download */
 	cpBool biasStale;          /* the device holds bias velocities of the last step that the mirrors do not */
 	int nBodiesOnDevice;       /* body count of the last upload (host slot == device index below it) */
+	int nConstraintsOnDevice;  /* the same for constraints ... */
+	cpBool jointIndexDirty;    /* ... until a removal compacts the host array (cleared by the next upload) */
 	unsigned fetchStamp;       /* bumped by every download; bodies unpack their record on first access */
 	cpBool someMirrorsStale;   /* a download happened and not every body has unpacked its record yet */
 	cpBool bbStale, arbStale, jointStale;

@@ -337,6 +337,7 @@ cpSpaceRemoveConstraint(cpSpace *space, cpConstraint *constraint)
 	cpBodyRemoveConstraint(constraint->b, constraint);
 	int i = constraint->index, last = --space->nConstraints;
 	if(i != last){ space->constraints[i] = space->constraints[last]; space->constraints[i]->index = i; }
+	space->jointIndexDirty = cpTrue;   /* host slots no longer match device indices until the next upload */
 	constraint->space = NULL;
 	constraint->index = -1;
 	space->topologyDirty = cpTrue;
@@ -549,6 +550,8 @@ upload_joints(cpSpace *space)
 	int rc = cpb200_world_set_joints(space->world, n, descs);
 	cpfree(descs);
 	if(rc) cpEngineError("joint upload");
+	space->nConstraintsOnDevice = n;
+	space->jointIndexDirty = cpFalse;
 }
 
 static void
@@ -705,8 +708,13 @@ void
 cpSpaceFetchJointsB200(cpSpace *space)
 {
 	space->jointStale = cpFalse;
-	if(!space->world || space->nConstraints == 0 || space->topologyDirty) return;
-	int n = space->nConstraints;
+	/* Host slots equal device indices until a removal compacts space->constraints (removals fetch first, see
+	 * sync_before_edit); constraints added since the last upload sit behind the device's count.  A pending
+	 * parameter edit or addition (topologyDirty) must NOT skip this fetch: the re-upload that follows would hand
+	 * the device stale accumulated impulses and the joints would lose their warm start. */
+	if(!space->world || space->jointIndexDirty) return;
+	int n = (space->nConstraintsOnDevice < space->nConstraints ? space->nConstraintsOnDevice : space->nConstraints);
+	if(n <= 0) return;
 	cpb200_joint_state *st = (cpb200_joint_state *)cpcalloc((size_t)n, sizeof(cpb200_joint_state));
 	if(cpb200_world_get_joints(space->world, 0, n, st)) cpEngineError("joint download");
 	for(int i = 0; i < n; i++){

@@ -389,6 +389,68 @@ static void remove_and_return(void)
 	cpShapeFree(s0); cpShapeFree(s1); cpBodyFree(a); cpBodyFree(b); cpShapeFree(g); cpSpaceFree(space);
 }
 
+/* ---- part 3: polygons and fat segments (one arbiter with two contacts per body: still order-free) ---- */
+
+/* 18. a capsule (fat segment) dropped on the ground segment: segment-segment narrowphase, then a kick */
+static void capsule_on_ground(void)
+{
+	cpShape *g; cpSpace *space = ground_space(&g);
+	cpBody *cap = cpSpaceAddBody(space, cpBodyNew(2.0, cpMomentForSegment(2.0, cpv(-8, 0), cpv(8, 0), 2.0)));
+	cpBodySetPosition(cap, cpv(0, 4.0));
+	cpShape *cs = cpSpaceAddShape(space, cpSegmentShapeNew(cap, cpv(-8, 0), cpv(8, 0), 2.0));
+	cpShapeSetFriction(cs, 0.5);
+	for(int k = 0; k < 40; k++) cpSpaceStep(space, 1.0/60.0);
+	body_line("capsule_on_ground_rest", "A", cap);
+	cpBodyApplyImpulseAtLocalPoint(cap, cpv(6.0, 0.0), cpv(0.0, 0.0));
+	for(int k = 0; k < 20; k++) cpSpaceStep(space, 1.0/60.0);
+	body_line("capsule_on_ground_kick", "A", cap);
+	cpSpaceRemoveShape(space, cs); cpSpaceRemoveBody(space, cap); cpSpaceRemoveShape(space, g);
+	cpShapeFree(cs); cpBodyFree(cap); cpShapeFree(g); cpSpaceFree(space);
+}
+
+/* 19. a box whose rounding radius, angle and position are edited while it rests */
+static void box_edits_midrun(void)
+{
+	cpShape *g; cpSpace *space = ground_space(&g);
+	cpBody *box = cpSpaceAddBody(space, cpBodyNew(2.0, cpMomentForBox(2.0, 10, 6)));
+	cpBodySetPosition(box, cpv(0, 3.2));
+	cpShape *bs = cpSpaceAddShape(space, cpBoxShapeNew(box, 10, 6, 0.0));
+	cpShapeSetFriction(bs, 0.6);
+	for(int k = 0; k < 30; k++) cpSpaceStep(space, 1.0/60.0);
+	body_line("box_edits_midrun_rest", "A", box);
+	cpPolyShapeSetRadius(bs, 0.5);
+	for(int k = 0; k < 20; k++) cpSpaceStep(space, 1.0/60.0);
+	body_line("box_edits_midrun_radius", "A", box);
+	cpBodySetAngle(box, 0.3); cpBodySetPosition(box, cpv(30.0, 9.0)); cpSpaceReindexShapesForBody(space, box);
+	for(int k = 0; k < 12; k++) cpSpaceStep(space, 1.0/60.0);
+	body_line("box_edits_midrun_tilted", "A", box);
+	cpContactPointSet set = cpShapesCollide(bs, g);
+	printf("box_edits_midrun_set A %d %a %a\n", set.count, set.normal.x, set.normal.y);
+	cpSpaceRemoveShape(space, bs); cpSpaceRemoveBody(space, box); cpSpaceRemoveShape(space, g);
+	cpShapeFree(bs); cpBodyFree(box); cpShapeFree(g); cpSpaceFree(space);
+}
+
+/* 20. a static platform (its own static body) is moved under a resting ball and reindexed */
+static void moved_static_platform(void)
+{
+	cpSpace *space = cpSpaceNew();
+	cpSpaceSetGravity(space, cpv(0, -100));
+	cpBody *plat = cpSpaceAddBody(space, cpBodyNewStatic());
+	cpBodySetPosition(plat, cpv(0, 0));
+	cpShape *ps = cpSpaceAddShape(space, cpSegmentShapeNew(plat, cpv(-30, 0), cpv(30, 0), 1.0));
+	cpShapeSetFriction(ps, 1.0);
+	cpShape *bs; cpBody *ball = add_ball(space, cpv(0, 6.3), 5.0, 1.0, &bs);
+	for(int k = 0; k < 20; k++) cpSpaceStep(space, 1.0/60.0);
+	body_line("moved_static_platform_rest", "E", ball);
+	cpBodySetPosition(plat, cpv(0, -3.0)); cpSpaceReindexShapesForBody(space, plat);
+	for(int k = 0; k < 20; k++) cpSpaceStep(space, 1.0/60.0);
+	body_line("moved_static_platform_lowered", "E", ball);
+	cpBB bb = cpShapeGetBB(ps);
+	printf("moved_static_platform_bb E %a %a %a %a\n", bb.l, bb.b, bb.r, bb.t);
+	cpSpaceRemoveShape(space, bs); cpSpaceRemoveBody(space, ball); cpSpaceRemoveShape(space, ps); cpSpaceRemoveBody(space, plat);
+	cpShapeFree(bs); cpBodyFree(ball); cpShapeFree(ps); cpBodyFree(plat); cpSpaceFree(space);
+}
+
 int main(void)
 {
 	empty_space();
@@ -408,5 +470,8 @@ int main(void)
 	elastic_bounce();
 	joints_midrun();
 	remove_and_return();
+	capsule_on_ground();
+	box_edits_midrun();
+	moved_static_platform();
 	return 0;
 }
