@@ -451,6 +451,64 @@ static void moved_static_platform(void)
 	cpShapeFree(bs); cpBodyFree(ball); cpShapeFree(ps); cpBodyFree(plat); cpSpaceFree(space);
 }
 
+/* ---- part 4: sleeping with joints, idle timers, queries right after an edit ---- */
+
+/* 21. two free balls joined by a slide joint fall asleep together and wake together */
+static void sleeping_pair_with_joint(void)
+{
+	cpSpace *space = cpSpaceNew();
+	cpSpaceSetSleepTimeThreshold(space, 0.2);
+	cpShape *s0, *s1; cpBody *a = add_ball(space, cpv(0, 0), 2.0, 1.0, &s0), *b = add_ball(space, cpv(10, 0), 2.0, 3.0, &s1);
+	cpConstraint *slide = cpSpaceAddConstraint(space, cpSlideJointNew(a, b, cpvzero, cpvzero, 5.0, 15.0));
+	for(int k = 0; k < 30; k++) cpSpaceStep(space, 1.0/60.0);
+	printf("sleeping_pair_with_joint_flags E %d %d\n", cpBodyIsSleeping(a), cpBodyIsSleeping(b));
+	cpBodyApplyImpulseAtLocalPoint(a, cpv(-8.0, 1.0), cpvzero);
+	printf("sleeping_pair_with_joint_woken E %d %d\n", cpBodyIsSleeping(a), cpBodyIsSleeping(b));
+	for(int k = 0; k < 60; k++) cpSpaceStep(space, 1.0/60.0);
+	body_line("sleeping_pair_with_joint", "E", a); body_line("sleeping_pair_with_joint", "E", b);
+	printf("sleeping_pair_with_joint_impulse E %a\n", cpConstraintGetImpulse(slide));
+	cpSpaceRemoveConstraint(space, slide); cpConstraintFree(slide);
+	cpSpaceRemoveShape(space, s0); cpSpaceRemoveShape(space, s1); cpSpaceRemoveBody(space, a); cpSpaceRemoveBody(space, b);
+	cpShapeFree(s0); cpShapeFree(s1); cpBodyFree(a); cpBodyFree(b); cpSpaceFree(space);
+}
+
+/* 22. cpBodyActivate restarts the idle timer: a resting ball that is poked every 20 steps stays awake, then sleeps */
+static void idle_timer_reset(void)
+{
+	cpShape *g, *bs; cpSpace *space = ground_space(&g);
+	cpSpaceSetSleepTimeThreshold(space, 0.5);
+	cpSpaceSetIdleSpeedThreshold(space, 1.0);
+	cpBody *ball = add_ball(space, cpv(0, 5.0), 5.0, 1.0, &bs);
+	int flags[6];
+	for(int k = 0; k < 120; k++){
+		cpSpaceStep(space, 1.0/60.0);
+		if(k % 20 == 19){ flags[k/20] = cpBodyIsSleeping(ball); if(k < 70) cpBodyActivate(ball); }
+	}
+	printf("idle_timer_reset E %d %d %d %d %d %d\n", flags[0], flags[1], flags[2], flags[3], flags[4], flags[5]);
+	body_line("idle_timer_reset", "E", ball);
+	cpSpaceRemoveShape(space, bs); cpSpaceRemoveBody(space, ball); cpSpaceRemoveShape(space, g);
+	cpShapeFree(bs); cpBodyFree(ball); cpShapeFree(g); cpSpaceFree(space);
+}
+
+/* 23. queries see a teleport at once (no step in between), after cpSpaceReindexShapesForBody */
+static void query_after_edit(void)
+{
+	cpShape *g, *bs; cpSpace *space = ground_space(&g);
+	cpBody *ball = add_ball(space, cpv(0, 5.5), 5.0, 1.0, &bs);
+	for(int k = 0; k < 5; k++) cpSpaceStep(space, 1.0/60.0);
+	cpBodySetPosition(ball, cpv(40.0, 20.0)); cpSpaceReindexShapesForBody(space, ball);
+	cpPointQueryInfo info;
+	cpShape *hit = cpSpacePointQueryNearest(space, cpv(40.0, 30.0), 100.0, CP_SHAPE_FILTER_ALL, &info);
+	printf("query_after_edit_point E %d %a %a %a\n", hit == bs, info.distance, info.point.x, info.point.y);
+	cpSegmentQueryInfo seg;
+	hit = cpSpaceSegmentQueryFirst(space, cpv(40.0, 50.0), cpv(40.0, -50.0), 0.0, CP_SHAPE_FILTER_ALL, &seg);
+	printf("query_after_edit_segment E %d %a %a %a\n", hit == bs, seg.alpha, seg.point.y, seg.normal.y);
+	cpBB bb = cpShapeGetBB(bs);
+	printf("query_after_edit_bb E %a %a %a %a\n", bb.l, bb.b, bb.r, bb.t);
+	cpSpaceRemoveShape(space, bs); cpSpaceRemoveBody(space, ball); cpSpaceRemoveShape(space, g);
+	cpShapeFree(bs); cpBodyFree(ball); cpShapeFree(g); cpSpaceFree(space);
+}
+
 int main(void)
 {
 	empty_space();
@@ -473,5 +531,8 @@ int main(void)
 	capsule_on_ground();
 	box_edits_midrun();
 	moved_static_platform();
+	sleeping_pair_with_joint();
+	idle_timer_reset();
+	query_after_edit();
 	return 0;
 }
