@@ -58,7 +58,13 @@ __global__ void k_bounds(DShapes S, double *bounds)
 		l = fmin(l, __shfl_xor_sync(0xffffffffu, l, d)); b = fmin(b, __shfl_xor_sync(0xffffffffu, b, d));
 		r = fmax(r, __shfl_xor_sync(0xffffffffu, r, d)); t = fmax(t, __shfl_xor_sync(0xffffffffu, t, d));
 	}
-	if((threadIdx.x & 31) != 0) return;
+	// one set of atomics per CTA, not per warp: the four words share a sector and every warp of the grid hit it
+	__shared__ double s_red[32][4];
+	const int wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+	if((threadIdx.x & 31) == 0){ s_red[wid][0] = l; s_red[wid][1] = b; s_red[wid][2] = r; s_red[wid][3] = t; }
+	__syncthreads();
+	if(threadIdx.x != 0) return;
+	for(int k = 1; k < nw; k++){ l = fmin(l, s_red[k][0]); b = fmin(b, s_red[k][1]); r = fmax(r, s_red[k][2]); t = fmax(t, s_red[k][3]); }
 #endif
 	if(l <= r){
 		atomic_min_double(&bounds[0], l); atomic_min_double(&bounds[1], b);
