@@ -509,6 +509,36 @@ static void query_after_edit(void)
 	cpShapeFree(bs); cpBodyFree(ball); cpShapeFree(g); cpSpaceFree(space);
 }
 
+/* ---- part 5: the cpArbiter accessors and derived body getters after a step ---- */
+static void print_arbiter(cpBody *body, cpArbiter *arb, void *tag)
+{
+	cpVect n = cpArbiterGetNormal(arb), pa = cpArbiterGetPointA(arb, 0), pb = cpArbiterGetPointB(arb, 0), j = cpArbiterTotalImpulse(arb);
+	cpShape *a, *b; cpArbiterGetShapes(arb, &a, &b);
+	cpBody *ba, *bb; cpArbiterGetBodies(arb, &ba, &bb);
+	printf("%s E %d %d %d %d %a %a %a %a %a %a %a\n", (const char *)tag, cpArbiterGetCount(arb), cpArbiterIsFirstContact(arb), ba == body, cpShapeGetBody(a) == ba,
+		n.x, n.y, cpArbiterGetDepth(arb, 0), pa.x, pa.y, pb.x, pb.y);
+	printf("%s_impulse E %a %a %a %a %a %a\n", (const char *)tag, j.x, j.y, cpArbiterTotalKE(arb), cpArbiterGetRestitution(arb), cpArbiterGetFriction(arb), cpArbiterGetSurfaceVelocity(arb).x);
+	cpContactPointSet set = cpArbiterGetContactPointSet(arb);
+	printf("%s_set E %d %a %a %a %a %a\n", (const char *)tag, set.count, set.normal.x, set.normal.y, set.points[0].pointA.y, set.points[0].pointB.y, set.points[0].distance);
+}
+
+/* 24. a ball sliding on a conveyor ground: every accessor of its one arbiter, on the first contact and later */
+static void arbiter_accessors(void)
+{
+	cpShape *g, *bs; cpSpace *space = ground_space(&g);
+	cpShapeSetSurfaceVelocity(g, cpv(5.0, 0.0)); cpShapeSetElasticity(g, 0.5);
+	cpBody *ball = add_ball(space, cpv(0, 5.2), 5.0, 2.0, &bs);
+	cpBodySetVelocity(ball, cpv(3.0, -1.0));
+	cpSpaceStep(space, 1.0/60.0);
+	cpBodyEachArbiter(ball, print_arbiter, (void *)"arbiter_accessors_first");
+	for(int k = 0; k < 9; k++) cpSpaceStep(space, 1.0/60.0);
+	cpBodyEachArbiter(ball, print_arbiter, (void *)"arbiter_accessors_later");
+	cpVect vw = cpBodyGetVelocityAtWorldPoint(ball, cpvadd(cpBodyGetPosition(ball), cpv(0, -5))), lw = cpBodyLocalToWorld(ball, cpv(1, 2)), wl = cpBodyWorldToLocal(ball, cpv(1, 2));
+	printf("arbiter_accessors_body A %a %a %a %a %a %a %a\n", cpBodyKineticEnergy(ball), vw.x, vw.y, lw.x, lw.y, wl.x, wl.y);
+	cpSpaceRemoveShape(space, bs); cpSpaceRemoveBody(space, ball); cpSpaceRemoveShape(space, g);
+	cpShapeFree(bs); cpBodyFree(ball); cpShapeFree(g); cpSpaceFree(space);
+}
+
 int main(void)
 {
 	empty_space();
@@ -534,5 +564,6 @@ int main(void)
 	sleeping_pair_with_joint();
 	idle_timer_reset();
 	query_after_edit();
+	arbiter_accessors();
 	return 0;
 }
