@@ -527,7 +527,7 @@ static void arbiter_accessors(void)
 {
 	cpShape *g, *bs; cpSpace *space = ground_space(&g);
 	cpShapeSetSurfaceVelocity(g, cpv(5.0, 0.0)); cpShapeSetElasticity(g, 0.5);
-	cpBody *ball = add_ball(space, cpv(0, 5.2), 5.0, 2.0, &bs);
+	cpBody *ball = add_ball(space, cpv(0, 4.95), 5.0, 2.0, &bs);
 	cpBodySetVelocity(ball, cpv(3.0, -1.0));
 	cpSpaceStep(space, 1.0/60.0);
 	cpBodyEachArbiter(ball, print_arbiter, (void *)"arbiter_accessors_first");
