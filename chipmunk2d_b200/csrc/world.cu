@@ -145,6 +145,9 @@ struct cpb200_world {
 	void *d_stage; size_t stage_bytes;   // device staging for host <-> SoA conversion kernels
 	unsigned *d_barrier;    // grid barrier words of the persistent solver
 	bool mid_step;          // between cpb200_world_step_collide and cpb200_world_step_finish
+	bool mid_solve;         // validation hook: between cpb200_world_step_presolve and cpb200_world_step_finish
+	int solver_variant;     // validation hook: 0 automatic, 1 world-wide + cached rows, 2 world-wide + streamed rows, 3 space-local
+	int last_solver_path;   // what the last step ran: 0 serial, 1 world-wide coloured, 2 space-local
 	double step_dt, step_dt_coef; int step_iterations;
 	bool hints_valid;       // last step's colours may seed this step's colouring
 	bool no_hints;          // validation hook (env CPB200_NO_HINTS): colour from scratch every step
@@ -284,6 +287,7 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	cudaMalloc(&p, sizeof(unsigned)*8); w->d_barrier = (unsigned *)p; cudaMemsetAsync(w->d_barrier, 0, sizeof(unsigned)*8, w->stream);
 	w->no_hints = (getenv("CPB200_NO_HINTS") != NULL);
 	w->d_query = NULL; w->query_bytes = 0;
+	w->mid_solve = false; w->solver_variant = 0; w->last_solver_path = 0;
 	w->mid_step = false; w->step_dt = 0.0; w->step_dt_coef = 0.0; w->step_iterations = 0;
 	w->sl_dirty = true; w->sl_ok = false; w->sl_disabled = (getenv("CPB200_NO_SPACE_LOCAL") != NULL); w->sl_max_nbody = 0;
 	memset(&w->SL, 0, sizeof(w->SL)); w->sl_tmp = NULL;
@@ -985,14 +989,16 @@ static int step_phase_a(cpb200_world *w, double dt)
 	return 0;
 }
 
-static int step_phase_b(cpb200_world *w)
+static int step_phase_b2(cpb200_world *w);
+
+// Phase B up to the solver: islands, cache ageing + table, prestep, velocity integration.
+static int step_phase_b1(cpb200_world *w)
 {
 	cudaSetDevice(w->device);
 	cudaStream_t st = w->stream;
 	DBodies &B = w->B; DShapes &S = w->S; DJoints &J = w->J;
 	(void)S; (void)J;
-	double dt = w->step_dt, dt_coef = w->step_dt_coef;
-	int iterations = w->step_iterations;
+	double dt = w->step_dt;
 	const int prv = w->cur ^ 1;
 	DArbs &Ap = w->A[prv]; DArbs &Ac = w->A[w->cur];
 	DTable &Tc = w->T[w->cur];
@@ -1032,8 +1038,30 @@ static int step_phase_b(cpb200_world *w)
 	// K9
 	if(nb) LAUNCH(k_integrate_vel, grid_for(nb, 256), 256, st, B, (const DSpace *)w->d_spaces, dt, w->K.claim, w->K.bmask);
 	STAGE_END(w, ST_INTEGRATE_VEL);
+	w->mid_solve = true;
+	return 0;
+}
 
-	// K10 + K11
+static int step_phase_b(cpb200_world *w)
+{
+	if(step_phase_b1(w)) return -1;
+	return step_phase_b2(w);
+}
+
+// K10 + K11 and the end of the step
+static int step_phase_b2(cpb200_world *w)
+{
+	cudaSetDevice(w->device);
+	cudaStream_t st = w->stream;
+	DBodies &B = w->B; DShapes &S = w->S; DJoints &J = w->J;
+	double dt = w->step_dt, dt_coef = w->step_dt_coef;
+	int iterations = w->step_iterations;
+	DArbs &Ac = w->A[w->cur];
+	DTable &Tc = w->T[w->cur];
+	const int nb = B.n;
+	const int wide = w->sm_count*8;
+	w->mid_solve = false;
+
 	if(w->solver_mode == 1){
 		int need = Ac.cap;
 		if(w->order_cap < need){
@@ -1046,6 +1074,7 @@ static int step_phase_b(cpb200_world *w)
 		int n_order = *(int *)w->h_scratch;
 		LAUNCH(k_solve_serial, 1, 32, st, B, Ac, J, (const int *)w->d_order, n_order, (const int *)w->d_joint_order, w->n_joint_order, iterations, dt, dt_coef);
 		w->n_user_order = 0; w->n_joint_order = 0;
+		w->last_solver_path = 0;
 	} else {
 		DColour &K = w->K;
 		K.ids = S.ids;
@@ -1066,13 +1095,21 @@ static int step_phase_b(cpb200_world *w)
 			// spaces, or one small scene).  A forced grid (validation hook) keeps the world-wide solver.
 			if(w->sl_dirty && sl_refresh(w)) return -1;
 			bool space_local = w->sl_ok && w->force_blocks == 0 && est_cons/w->n_spaces <= 4096;
+			if(w->solver_variant == 1 || w->solver_variant == 2) space_local = false;
+			if(w->solver_variant == 3){
+				if(!w->sl_ok){ cpb_set_error("solver variant 3 (space-local) needs every space to own one contiguous body range that fits a CTA's shared memory"); return -1; }
+				space_local = true;
+			}
+			w->last_solver_path = (space_local ? 2 : 1);
 			DSpaceLocal SL = w->SL;
 			if(!space_local) SL.start = NULL;
 			size_t nbuckets = 2*(size_t)w->n_spaces*CPB_MAX_COLOURS + 2;
 			if(space_local) cudaMemsetAsync(SL.start, 0, sizeof(uint32_t)*nbuckets, st);
 			void *args[] = {&B, &Ac, &J, &R, &K, &C, &bar, &SL, &use_hints, &iterations, &dt, &dt_coef};
 			// rows + velocity sectors of one pass: stream the rows past the L2 only if they would not fit next to the velocities
-			const bool stream_rows = ((size_t)est_cons*(size_t)CPB_ROW_BYTES_EST + (size_t)nb*64 > (size_t)CPB_L2_RESIDENT_BYTES);
+			bool stream_rows = ((size_t)est_cons*(size_t)CPB_ROW_BYTES_EST + (size_t)nb*64 > (size_t)CPB_L2_RESIDENT_BYTES);
+			if(w->solver_variant == 1) stream_rows = false;
+			if(w->solver_variant == 2) stream_rows = true;
 			void *kernel = space_local ? (void *)k_colour_solve<true, true>
 			             : stream_rows ? (void *)k_colour_solve<false, true> : (void *)k_colour_solve<false, false>;
 			CPB_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(blocks), dim3(256), args, 0, st));
@@ -1108,6 +1145,7 @@ static int step_phase_b(cpb200_world *w)
 				for(int c = 0; c < ncol; c++) LAUNCH(k_solve_colour, 4, 64, st, B, w->R, J, K, c, (pass == 0 ? 0 : 1), dt, dt_coef);
 			}
 			LAUNCH(k_rows_writeback, 4, 64, st, Ac, w->R, K);
+			w->last_solver_path = 1;
 		}
 #endif
 	}
@@ -1131,7 +1169,7 @@ extern "C" int cpb200_world_step(cpb200_world *w, double dt)
 {
 	if(!w){ cpb_set_error("null world"); return -1; }
 	if(dt == 0.0) return 0; // cpSpaceStep.c:339
-	if(w->mid_step){ cpb_set_error("cpb200_world_step while a split step is open (call cpb200_world_step_finish)"); return -1; }
+	if(w->mid_step || w->mid_solve){ cpb_set_error("cpb200_world_step while a split step is open (call cpb200_world_step_finish)"); return -1; }
 	if(step_phase_a(w, dt)) return -1;
 	return step_phase_b(w);
 }
@@ -1140,15 +1178,23 @@ extern "C" int cpb200_world_step_collide(cpb200_world *w, double dt)
 {
 	if(!w){ cpb_set_error("null world"); return -1; }
 	if(dt == 0.0){ cpb_set_error("split step with dt == 0"); return -1; }
-	if(w->mid_step){ cpb_set_error("a split step is already open"); return -1; }
+	if(w->mid_step || w->mid_solve){ cpb_set_error("a split step is already open"); return -1; }
 	return step_phase_a(w, dt);
 }
 
 extern "C" int cpb200_world_step_finish(cpb200_world *w)
 {
 	if(!w){ cpb_set_error("null world"); return -1; }
+	if(w->mid_solve) return step_phase_b2(w);
 	if(!w->mid_step){ cpb_set_error("cpb200_world_step_finish without cpb200_world_step_collide"); return -1; }
 	return step_phase_b(w);
+}
+
+extern "C" int cpb200_world_step_presolve(cpb200_world *w)
+{
+	if(!w){ cpb_set_error("null world"); return -1; }
+	if(!w->mid_step){ cpb_set_error("cpb200_world_step_presolve without cpb200_world_step_collide"); return -1; }
+	return step_phase_b1(w);
 }
 
 // Host decisions of the begin/preSolve handlers applied to this step's records (cpSpaceStep.c:257-285,
@@ -1459,6 +1505,108 @@ extern "C" int cpb200_world_set_joint_order(cpb200_world *w, int n, const int32_
 	w->n_joint_order = n;
 	return world_sync(w);
 }
+
+// ---- validation hooks for the PRODUCTION solver order (tests/test_gpu_production_order.py) ----
+extern "C" int cpb200_world_set_solver_variant(cpb200_world *w, int variant)
+{
+	if(!w || variant < 0 || variant > 3){ cpb_set_error("solver variant must be 0..3"); return -1; }
+	w->solver_variant = variant;
+	return 0;
+}
+
+__global__ void k_pack_body_solver_state(DBodies B, double *__restrict__ dst, int first, int n)
+{
+	int k = CPB_TID;
+	if(k >= n) return;
+	double4 V = B.V[first + k], VB = B.VB[first + k];
+	double *o = dst + 8*(size_t)k;
+	o[0] = V.x; o[1] = V.y; o[2] = V.z; o[3] = V.w; o[4] = VB.x; o[5] = VB.y; o[6] = VB.z; o[7] = VB.w;
+}
+
+extern "C" int cpb200_world_get_body_solver_state(cpb200_world *w, int first, int n, double *out)
+{
+	if(!w || first < 0 || n < 0 || first + n > w->B.n){ cpb_set_error("body range out of bounds"); return -1; }
+	if(n == 0) return 0;
+	cudaSetDevice(w->device);
+	size_t bytes = 8*sizeof(double)*(size_t)n;
+	if(stage_reserve(w, bytes)) return -1;
+	LAUNCH(k_pack_body_solver_state, grid_for(n, 128), 128, w->stream, w->B, (double *)w->d_stage, first, n);
+	CPB_CHECK(cudaMemcpyAsync(out, w->d_stage, bytes, cudaMemcpyDeviceToHost, w->stream));
+	return world_sync(w);
+}
+
+__global__ void k_pack_joint_solver_state(DJoints J, double *__restrict__ dst, int first, int n)
+{
+	int k = CPB_TID;
+	if(k >= n) return;
+	int j = first + k;
+	double *o = dst + CPB200_JOINT_SOLVER_ROW*(size_t)k;
+	double4 kk = J.k[j], prm = J.prm[j];
+	o[0] = J.type[j]; o[1] = J.a[j]; o[2] = J.b[j]; o[3] = (J.colour[j] == -2 ? 0.0 : 1.0);
+	o[4] = J.max_force[j]; o[5] = J.max_bias[j];
+	o[6] = J.r1[j].x; o[7] = J.r1[j].y; o[8] = J.r2[j].x; o[9] = J.r2[j].y; o[10] = J.nrm[j].x; o[11] = J.nrm[j].y;
+	o[12] = J.nmass[j]; o[13] = kk.x; o[14] = kk.y; o[15] = kk.z; o[16] = kk.w;
+	o[17] = J.bias[j].x; o[18] = J.bias[j].y; o[19] = J.acc[j].x; o[20] = J.acc[j].y; o[21] = J.aux0[j]; o[22] = J.aux1[j];
+	o[23] = prm.x; o[24] = prm.y; o[25] = prm.z; o[26] = prm.w; o[27] = 0.0;
+}
+
+extern "C" int cpb200_world_get_joint_solver_state(cpb200_world *w, int first, int n, double *out)
+{
+	if(!w || first < 0 || n < 0 || first + n > w->J.n){ cpb_set_error("joint range out of bounds"); return -1; }
+	if(n == 0) return 0;
+	cudaSetDevice(w->device);
+	size_t bytes = CPB200_JOINT_SOLVER_ROW*sizeof(double)*(size_t)n;
+	if(stage_reserve(w, bytes)) return -1;
+	LAUNCH(k_pack_joint_solver_state, grid_for(n, 128), 128, w->stream, w->J, (double *)w->d_stage, first, n);
+	CPB_CHECK(cudaMemcpyAsync(out, w->d_stage, bytes, cudaMemcpyDeviceToHost, w->stream));
+	return world_sync(w);
+}
+
+// The sequence in which the last step's production solver visited its constraints, colour phase by colour phase
+// (within a phase the constraints share no dynamic body and ran in parallel): item >= 0 = arbiter record index,
+// item < 0 = joint -(item + 1).  Space-local path: space after space (spaces never interact).
+extern "C" long cpb200_world_get_solver_order(cpb200_world *w, long cap, int64_t *out)
+{
+	if(!w){ cpb_set_error("null world"); return -1; }
+	if(w->last_solver_path == 0){ cpb_set_error("the last step did not run the coloured solver"); return -1; }
+	cudaSetDevice(w->device);
+	if(world_sync(w)) return -1;
+	std::vector<int64_t> seq;
+	std::vector<int> jrow;
+	if(download(w, jrow, w->J.row, (size_t)w->J.n) || world_sync(w)) return -1;
+	if(w->last_solver_path == 1){
+		std::vector<int> cstart, jstart, arb;
+		if(download(w, cstart, w->K.cstart, CPB_MAX_COLOURS + 1) || download(w, jstart, w->K.jstart, CPB_MAX_COLOURS + 1) || world_sync(w)) return -1;
+		int n_rows = std::min(cstart[CPB_MAX_COLOURS], w->R.cap);
+		if(download(w, arb, w->R.arb, (size_t)n_rows) || world_sync(w)) return -1;
+		for(int c = 0; c < CPB_MAX_COLOURS; c++){
+			for(int r = cstart[c]; r < cstart[c + 1] && r < n_rows; r++) seq.push_back(arb[(size_t)r]);
+			for(int q = jstart[c]; q < jstart[c + 1] && q < w->J.n; q++) seq.push_back(-(int64_t)jrow[(size_t)q] - 1);
+		}
+	} else {
+		const int ns = w->n_spaces;
+		size_t nbuckets = 2*(size_t)ns*CPB_MAX_COLOURS + 2;
+		std::vector<uint32_t> start; std::vector<int4> hdr;
+		if(download(w, start, (const uint32_t *)w->SL.start, nbuckets) || world_sync(w)) return -1;
+		// after k_sl_rows every bucket word holds the END of its bucket = the begin of the next one
+		const int jbase = (int)start[(size_t)ns*CPB_MAX_COLOURS];
+		int n_rows = std::min(jbase, w->R.cap);
+		if(download(w, hdr, (const int4 *)w->R.hdr, (size_t)n_rows) || world_sync(w)) return -1;
+		for(int sp = 0; sp < ns; sp++){
+			for(int c = 0; c < CPB_MAX_COLOURS; c++){
+				int ka = sp*CPB_MAX_COLOURS + c, kj = ns*CPB_MAX_COLOURS + 1 + sp*CPB_MAX_COLOURS + c;
+				int r0 = (ka > 0 ? (int)start[(size_t)ka - 1] : 0), r1 = (int)start[(size_t)ka];
+				int q0 = (int)start[(size_t)kj - 1] - jbase, q1 = (int)start[(size_t)kj] - jbase;
+				for(int r = r0; r < r1 && r < n_rows; r++) seq.push_back(hdr[(size_t)r].w);
+				for(int q = q0; q < q1 && q < w->J.n; q++) seq.push_back(-(int64_t)jrow[(size_t)q] - 1);
+			}
+		}
+	}
+	for(size_t i = 0; i < seq.size() && (long)i < cap && out; i++) out[i] = seq[i];
+	return (long)seq.size();
+}
+
+extern "C" int cpb200_world_get_solver_path(cpb200_world *w){ return w ? w->last_solver_path : -1; }
 
 extern "C" int cpb200_world_collide_pair(cpb200_world *w, int shape_a, int shape_b, double *out13)
 {

@@ -124,6 +124,15 @@ def load_engine(path=None):
     lib.cpb200_stage_name.argtypes = [ci]
     lib.cpb200_world_set_profiling.argtypes = [vp, ci]
     lib.cpb200_world_get_solver_profile.argtypes = [vp, vp]
+    lib.cpb200_world_step_collide.argtypes = [vp, cd]
+    lib.cpb200_world_step_presolve.argtypes = [vp]
+    lib.cpb200_world_step_finish.argtypes = [vp]
+    lib.cpb200_world_get_body_solver_state.argtypes = [vp, ci, ci, vp]
+    lib.cpb200_world_get_joint_solver_state.argtypes = [vp, ci, ci, vp]
+    lib.cpb200_world_set_solver_variant.argtypes = [vp, ci]
+    lib.cpb200_world_get_solver_order.restype = C.c_long
+    lib.cpb200_world_get_solver_order.argtypes = [vp, C.c_long, vp]
+    lib.cpb200_world_get_solver_path.argtypes = [vp]
     _lib_cache[path] = lib
     return lib
 
@@ -378,6 +387,41 @@ class World:
         out = np.zeros(13)
         n = self._ck(self.lib.cpb200_world_collide_pair(self.w, int(a), int(b), out.ctypes.data))
         return n, out
+
+    # -- validation hooks for the production solver order (include/cpb200.h)
+    JOINT_SOLVER_ROW = 28
+
+    def step_collide(self, dt):
+        self._ck(self.lib.cpb200_world_step_collide(self.w, float(dt)))
+
+    def step_presolve(self):
+        self._ck(self.lib.cpb200_world_step_presolve(self.w))
+
+    def step_finish(self):
+        self._ck(self.lib.cpb200_world_step_finish(self.w))
+
+    def body_solver_state(self):
+        """[n][8] = v.x v.y w m_inv v_bias.x v_bias.y w_bias i_inv, exactly as the solver kernels hold them."""
+        out = np.zeros((self.n_bodies, 8))
+        self._ck(self.lib.cpb200_world_get_body_solver_state(self.w, 0, self.n_bodies, out.ctypes.data))
+        return out
+
+    def joint_solver_state(self):
+        out = np.zeros((max(self.n_joints, 1), self.JOINT_SOLVER_ROW))
+        self._ck(self.lib.cpb200_world_get_joint_solver_state(self.w, 0, self.n_joints, out.ctypes.data))
+        return out[:self.n_joints]
+
+    def set_solver_variant(self, variant):
+        self._ck(self.lib.cpb200_world_set_solver_variant(self.w, int(variant)))
+
+    def solver_order(self):
+        n = self._ck(self.lib.cpb200_world_get_solver_order(self.w, 0, None))
+        out = np.zeros(max(n, 1), dtype=np.int64)
+        n = self._ck(self.lib.cpb200_world_get_solver_order(self.w, len(out), out.ctypes.data))
+        return out[:n]
+
+    def solver_path(self):
+        return int(self.lib.cpb200_world_get_solver_path(self.w))
 
     def set_profiling(self, on):
         self._ck(self.lib.cpb200_world_set_profiling(self.w, int(bool(on))))

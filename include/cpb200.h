@@ -261,6 +261,29 @@ CPB200_API int cpb200_world_set_solver_grid(cpb200_world *w, int blocks);
  * space->constraints (sleeping reorders that array); joints not listed follow in upload order.
  * Applies to the next step only. */
 CPB200_API int cpb200_world_set_joint_order(cpb200_world *w, int n, const int32_t *order);
+/* ---- the PRODUCTION solver order, pinned against the oracle (tests/test_gpu_production_order.py) ----
+ * A split step can also stop right before the solver: step_collide -> step_presolve (islands, cache ageing,
+ * prestep, velocity integration: everything of cpSpaceStep.c:335-404) -> [read the solver's inputs] ->
+ * step_finish (K10 colouring + K11 warm start / iterations, cpSpaceStep.c:406-427). */
+CPB200_API int cpb200_world_step_presolve(cpb200_world *w);
+/* Solver inputs / outputs as the kernels hold them: out[n][8] = v.x v.y w m_inv v_bias.x v_bias.y w_bias i_inv. */
+CPB200_API int cpb200_world_get_body_solver_state(cpb200_world *w, int first, int n, double *out);
+/* out[n][CPB200_JOINT_SOLVER_ROW] = type a b live max_force max_bias r1.xy r2.xy n.xy nMass|iSum|clamp k[4] bias.xy
+ * jAcc.xy aux0 (spring target_vrn | ratchet angle) aux1 (spring v_coef) prm[4] 0 */
+#define CPB200_JOINT_SOLVER_ROW 28
+CPB200_API int cpb200_world_get_joint_solver_state(cpb200_world *w, int first, int n, double *out);
+/* Which coloured kernel family runs: 0 automatic (default), 1 world-wide persistent kernel with L2-cached rows,
+ * 2 the same with streamed rows, 3 space-local (one CTA per space; fails at step time if the world's layout
+ * does not allow it).  The arithmetic is the same; the tests pin every family. */
+CPB200_API int cpb200_world_set_solver_variant(cpb200_world *w, int variant);
+/* The sequence in which the last step's coloured solver visited its constraints, colour phase after colour
+ * phase (space after space for the space-local family): item >= 0 = arbiter record index (cpb200_arbiter.record),
+ * item < 0 = joint -(item + 1).  Constraints of one phase share no dynamic body, so replaying the sequence
+ * with a sequential solver (cpSpaceStep.c:406-427) must give the parallel result bit for bit.
+ * Returns the count; writes at most cap. */
+CPB200_API long cpb200_world_get_solver_order(cpb200_world *w, long cap, int64_t *out);
+/* 0 serial, 1 world-wide coloured, 2 space-local: what the last step ran. */
+CPB200_API int cpb200_world_get_solver_path(cpb200_world *w);
 /* Run only the narrowphase on one uploaded shape pair with current world caches
  * (cpShapesCollide, cpShape.c:259-283): out = count n.x n.y (pA.xy pB.xy dist) x2. */
 CPB200_API int cpb200_world_collide_pair(cpb200_world *w, int shape_a, int shape_b, double *out13);

@@ -7,7 +7,7 @@
 #include <stdlib.h>
 #include "cp_oracle.h"
 
-int cp_oracle_version(void){ return 2; }
+int cp_oracle_version(void){ return 3; }
 
 /* ---- vector helpers with the reference's association (cpVect.h:58-206) ---- */
 static cpo_vec V(double x, double y){ cpo_vec v = {x, y}; return v; }
@@ -417,7 +417,21 @@ void cpo_arbiter_apply_impulse(cpo_arbiter *arb, cpo_body *bodies)
 }
 
 /* ---- joints: pin cpPinJoint.c:24-75, slide cpSlideJoint.c:24-89, pivot cpPivotJoint.c:24-70,
- * damped spring cpDampedSpring.c:29-77, gear cpGearJoint.c:24-69 ---- */
+ * groove cpGrooveJoint.c:24-98, damped spring cpDampedSpring.c:29-77, damped rotary spring
+ * cpDampedRotarySpring.c:29-72, rotary limit cpRotaryLimitJoint.c:24-86, ratchet cpRatchetJoint.c:24-89,
+ * gear cpGearJoint.c:24-69, simple motor cpSimpleMotor.c:24-65 ---- */
+/* k_tensor (chipmunk_private.h:228-262), inverted, as cpMat2x2 (a b c d) */
+static void k_tensor(const cpo_body *a, const cpo_body *b, cpo_vec r1, cpo_vec r2, double k[4])
+{
+	double m_sum = a->m_inv + b->m_inv;
+	double k11 = m_sum, k12 = 0.0, k21 = 0.0, k22 = m_sum;
+	double a_i = a->i_inv, r1xsq = r1.x*r1.x*a_i, r1ysq = r1.y*r1.y*a_i, r1nxy = -r1.x*r1.y*a_i;
+	k11 += r1ysq; k12 += r1nxy; k21 += r1nxy; k22 += r1xsq;
+	double b_i = b->i_inv, r2xsq = r2.x*r2.x*b_i, r2ysq = r2.y*r2.y*b_i, r2nxy = -r2.x*r2.y*b_i;
+	k11 += r2ysq; k12 += r2nxy; k21 += r2nxy; k22 += r2xsq;
+	double det_inv = 1.0/(k11*k22 - k12*k21);
+	k[0] = k22*det_inv; k[1] = -k12*det_inv; k[2] = -k21*det_inv; k[3] = k11*det_inv;
+}
 static double bias_coef(double errorBias, double dt){ return 1.0 - pow(errorBias, dt); }
 
 void cpo_joint_prestep(cpo_joint *j, cpo_body *bodies, const double *T6, double dt)
@@ -425,7 +439,7 @@ void cpo_joint_prestep(cpo_joint *j, cpo_body *bodies, const double *T6, double 
 	cpo_body *a = &bodies[j->a], *b = &bodies[j->b];
 	const double *Ta = T6 + 6*j->a, *Tb = T6 + 6*j->b;
 	double maxBias = j->maxBias;
-	if(j->type != 8){
+	if(j->type == 0 || j->type == 1 || j->type == 2 || j->type == 4){
 		j->r1 = tvect(Ta, sub(j->anchorA, a->cog));
 		j->r2 = tvect(Tb, sub(j->anchorB, b->cog));
 	}
@@ -446,16 +460,25 @@ void cpo_joint_prestep(cpo_joint *j, cpo_body *bodies, const double *T6, double 
 		j->bias = clamp(-bias_coef(j->errorBias, dt)*pdist/dt, -maxBias, maxBias);
 		break;
 	}
-	case 2: { /* pivot: k_tensor (chipmunk_private.h:228-262) */
-		double m_sum = a->m_inv + b->m_inv;
-		double k11 = m_sum, k12 = 0.0, k21 = 0.0, k22 = m_sum;
-		double a_i = a->i_inv, r1xsq = j->r1.x*j->r1.x*a_i, r1ysq = j->r1.y*j->r1.y*a_i, r1nxy = -j->r1.x*j->r1.y*a_i;
-		k11 += r1ysq; k12 += r1nxy; k21 += r1nxy; k22 += r1xsq;
-		double b_i = b->i_inv, r2xsq = j->r2.x*j->r2.x*b_i, r2ysq = j->r2.y*j->r2.y*b_i, r2nxy = -j->r2.x*j->r2.y*b_i;
-		k11 += r2ysq; k12 += r2nxy; k21 += r2nxy; k22 += r2xsq;
-		double det_inv = 1.0/(k11*k22 - k12*k21);
-		j->k[0] = k22*det_inv; j->k[1] = -k12*det_inv; j->k[2] = -k21*det_inv; j->k[3] = k11*det_inv;
+	case 2: /* pivot */
+		k_tensor(a, b, j->r1, j->r2, j->k);
 		j->bias2 = vclamp(mul(delta, -bias_coef(j->errorBias, dt)/dt), maxBias);
+		break;
+	case 3: { /* groove: anchorA = grv_a, prm[0..1] = grv_b; grv_n = perp(normalize(grv_b - grv_a)) (cpGrooveJoint.c:128) */
+		cpo_vec grv_b = V(j->prm[0], j->prm[1]);
+		cpo_vec grv_n = perp(normalize(sub(grv_b, j->anchorA)));
+		cpo_vec ta = tpoint(Ta, j->anchorA), tb = tpoint(Ta, grv_b);
+		cpo_vec n = tvect(Ta, grv_n);
+		double d = dot(ta, n);
+		j->n = n;
+		j->r2 = tvect(Tb, sub(j->anchorB, b->cog));
+		double td = cross(add(b->p, j->r2), n);
+		if(td <= cross(ta, n)){ j->clamp = 1.0; j->r1 = sub(ta, a->p); }
+		else if(td >= cross(tb, n)){ j->clamp = -1.0; j->r1 = sub(tb, a->p); }
+		else { j->clamp = 0.0; j->r1 = sub(add(mul(perp(n), -td), mul(n, d)), a->p); }
+		k_tensor(a, b, j->r1, j->r2, j->k);
+		cpo_vec gdelta = sub(add(b->p, j->r2), add(a->p, j->r1));
+		j->bias2 = vclamp(mul(gdelta, -bias_coef(j->errorBias, dt)/dt), maxBias);
 		break;
 	}
 	case 4: { /* damped spring: applies its spring impulse here (cpDampedSpring.c:49-52) */
@@ -469,12 +492,44 @@ void cpo_joint_prestep(cpo_joint *j, cpo_body *bodies, const double *T6, double 
 		apply_impulses(a, b, j->r1, j->r2, mul(j->n, j_spring));
 		break;
 	}
+	case 5: { /* damped rotary spring: prm = restAngle, stiffness, damping; applies its torque here */
+		double moment = a->i_inv + b->i_inv;
+		j->iSum = 1.0/moment;
+		j->v_coef = 1.0 - exp(-j->prm[2]*dt*moment);
+		j->target_vrn = 0.0;
+		double j_spring = ((a->a - b->a) - j->prm[0])*j->prm[1]*dt;
+		j->jnAcc = j_spring;
+		a->w -= j_spring*a->i_inv;
+		b->w += j_spring*b->i_inv;
+		break;
+	}
+	case 6: { /* rotary limit: prm = min, max */
+		double rdist = b->a - a->a, pdist = 0.0;
+		if(rdist > j->prm[1]) pdist = j->prm[1] - rdist; else if(rdist < j->prm[0]) pdist = j->prm[0] - rdist;
+		j->iSum = 1.0/(a->i_inv + b->i_inv);
+		j->bias = clamp(-bias_coef(j->errorBias, dt)*pdist/dt, -maxBias, maxBias);
+		if(!j->bias) j->jnAcc = 0.0;
+		break;
+	}
+	case 7: { /* ratchet: prm = angle (state), phase, ratchet */
+		double angle = j->prm[0], phase = j->prm[1], ratchet = j->prm[2];
+		double rdelta = b->a - a->a, diff = angle - rdelta, pdist = 0.0;
+		if(diff*ratchet > 0.0) pdist = diff;
+		else j->prm[0] = floor((rdelta - phase)/ratchet)*ratchet + phase;
+		j->iSum = 1.0/(a->i_inv + b->i_inv);
+		j->bias = clamp(-bias_coef(j->errorBias, dt)*pdist/dt, -maxBias, maxBias);
+		if(!j->bias) j->jnAcc = 0.0;
+		break;
+	}
 	case 8: { /* gear: prm = phase, ratio */
 		double ratio = j->prm[1], ratio_inv = 1.0/ratio;
 		j->iSum = 1.0/(a->i_inv*ratio_inv + ratio*b->i_inv);
 		j->bias = clamp(-bias_coef(j->errorBias, dt)*(b->a*ratio - a->a - j->prm[0])/dt, -maxBias, maxBias);
 		break;
 	}
+	case 9: /* simple motor: prm = rate */
+		j->iSum = 1.0/(a->i_inv + b->i_inv);
+		break;
 	default: break;
 	}
 }
@@ -484,7 +539,8 @@ void cpo_joint_apply_cached(cpo_joint *j, cpo_body *bodies, double dt_coef)
 	cpo_body *a = &bodies[j->a], *b = &bodies[j->b];
 	switch(j->type){
 	case 0: case 1: apply_impulses(a, b, j->r1, j->r2, mul(j->n, j->jnAcc*dt_coef)); break;
-	case 2: apply_impulses(a, b, j->r1, j->r2, mul(j->jAcc2, dt_coef)); break;
+	case 2: case 3: apply_impulses(a, b, j->r1, j->r2, mul(j->jAcc2, dt_coef)); break;
+	case 6: case 7: case 9: { double jj = j->jnAcc*dt_coef; a->w -= jj*a->i_inv; b->w += jj*b->i_inv; break; }
 	case 8: { double jj = j->jnAcc*dt_coef; a->w -= jj*a->i_inv*(1.0/j->prm[1]); b->w += jj*b->i_inv; break; }
 	default: break;
 	}
@@ -528,6 +584,52 @@ void cpo_joint_apply_impulse(cpo_joint *j, cpo_body *bodies, double dt)
 		apply_impulses(a, b, j->r1, j->r2, mul(j->n, j_damp));
 		break;
 	}
+	case 3: {
+		cpo_vec vr = relative_velocity(a, b, j->r1, j->r2);
+		cpo_vec d = sub(j->bias2, vr);
+		cpo_vec jj = V(d.x*j->k[0] + d.y*j->k[1], d.x*j->k[2] + d.y*j->k[3]);
+		cpo_vec jOld = j->jAcc2, jn = add(jOld, jj), n = j->n;
+		/* grooveConstrain (cpGrooveJoint.c:73-78); cpvproject (cpVect.h:98-101) */
+		cpo_vec jClamp = (j->clamp*cross(jn, n) > 0.0) ? jn : mul(n, dot(jn, n)/dot(n, n));
+		j->jAcc2 = vclamp(jClamp, j->maxForce*dt);
+		apply_impulses(a, b, j->r1, j->r2, sub(j->jAcc2, jOld));
+		break;
+	}
+	case 5: {
+		double wrn = a->w - b->w;
+		double w_damp = (j->target_vrn - wrn)*j->v_coef;
+		j->target_vrn = wrn + w_damp;
+		double j_damp = w_damp*j->iSum;
+		j->jnAcc += j_damp;
+		a->w += j_damp*a->i_inv; b->w -= j_damp*b->i_inv;
+		break;
+	}
+	case 6: {
+		if(!j->bias) return;
+		double wr = b->w - a->w, jMax = j->maxForce*dt;
+		double jj = -(j->bias + wr)*j->iSum, jOld = j->jnAcc;
+		if(j->bias < 0.0) j->jnAcc = clamp(jOld + jj, 0.0, jMax); else j->jnAcc = clamp(jOld + jj, -jMax, 0.0);
+		jj = j->jnAcc - jOld;
+		a->w -= jj*a->i_inv; b->w += jj*b->i_inv;
+		break;
+	}
+	case 7: {
+		if(!j->bias) return;
+		double wr = b->w - a->w, ratchet = j->prm[2], jMax = j->maxForce*dt;
+		double jj = -(j->bias + wr)*j->iSum, jOld = j->jnAcc;
+		j->jnAcc = clamp((jOld + jj)*ratchet, 0.0, jMax*fabs_(ratchet))/ratchet;
+		jj = j->jnAcc - jOld;
+		a->w -= jj*a->i_inv; b->w += jj*b->i_inv;
+		break;
+	}
+	case 9: {
+		double wr = b->w - a->w + j->prm[0], jMax = j->maxForce*dt;
+		double jj = -wr*j->iSum, jOld = j->jnAcc;
+		j->jnAcc = clamp(jOld + jj, -jMax, jMax);
+		jj = j->jnAcc - jOld;
+		a->w -= jj*a->i_inv; b->w += jj*b->i_inv;
+		break;
+	}
 	case 8: {
 		double ratio = j->prm[1], ratio_inv = 1.0/ratio;
 		double wr = b->w*ratio - a->w, jMax = j->maxForce*dt;
@@ -539,7 +641,6 @@ void cpo_joint_apply_impulse(cpo_joint *j, cpo_body *bodies, double dt)
 	}
 	default: break;
 	}
-	(void)fabs_;
 }
 
 /* ---- the solver section of cpSpaceStep (cpSpaceStep.c:406-427): cached impulses, then `iterations`
@@ -552,4 +653,29 @@ void cpo_solve(int n_arb, cpo_arbiter *arbs, int n_joints, cpo_joint *joints, cp
 		for(int i = 0; i < n_arb; i++) cpo_arbiter_apply_impulse(&arbs[i], bodies);
 		for(int i = 0; i < n_joints; i++) cpo_joint_apply_impulse(&joints[i], bodies, dt);
 	}
+}
+
+/* ---- the same solver section for an arbitrary interleaving of arbiters and joints: items[q] >= 0 names
+ * arbiter items[q], items[q] < 0 names joint -(items[q] + 1).  This is what a graph-coloured solver does when its
+ * colours are replayed one after the other (constraints of one colour share no dynamic body, so their relative
+ * order inside the colour cannot matter): cached impulses in sequence order, then `iterations` sweeps in
+ * sequence order (cpSpaceStep.c:406-427 with the two arrays merged into one sequence). ---- */
+void cpo_solve_sequence(long n_items, const int64_t *items, cpo_arbiter *arbs, cpo_joint *joints, cpo_body *bodies, int iterations, double dt, double dt_coef)
+{
+	for(long q = 0; q < n_items; q++){
+		if(items[q] >= 0) cpo_arbiter_apply_cached(&arbs[items[q]], bodies, dt_coef);
+		else cpo_joint_apply_cached(&joints[-(items[q] + 1)], bodies, dt_coef);
+	}
+	for(int it = 0; it < iterations; it++){
+		for(long q = 0; q < n_items; q++){
+			if(items[q] >= 0) cpo_arbiter_apply_impulse(&arbs[items[q]], bodies);
+			else cpo_joint_apply_impulse(&joints[-(items[q] + 1)], bodies, dt);
+		}
+	}
+}
+
+/* struct sizes for the numpy mirrors in tests/replay.py: 0 cpo_body, 1 cpo_arbiter, 2 cpo_joint */
+int cpo_sizeof(int what)
+{
+	switch(what){ case 0: return (int)sizeof(cpo_body); case 1: return (int)sizeof(cpo_arbiter); case 2: return (int)sizeof(cpo_joint); default: return -1; }
 }

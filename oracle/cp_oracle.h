@@ -63,6 +63,7 @@ typedef struct cpo_joint {
 } cpo_joint;
 
 int cp_oracle_version(void);
+int cpo_sizeof(int what);
 
 /* K1 / K9 */
 void cpo_body_update_position(cpo_body *b, double dt, double transform6[6]);
@@ -80,11 +81,13 @@ void cpo_collide(const cpo_shape *a, const cpo_shape *b, cpo_manifold *out);
 void cpo_arbiter_prestep(cpo_arbiter *arb, const cpo_body *bodies, double dt, double slop, double bias_coef);
 void cpo_arbiter_apply_cached(cpo_arbiter *arb, cpo_body *bodies, double dt_coef);
 void cpo_arbiter_apply_impulse(cpo_arbiter *arb, cpo_body *bodies);
-/* K8 / K11 for the five joints named by the north star */
+/* K8 / K11 for all ten joint classes */
 void cpo_joint_prestep(cpo_joint *j, cpo_body *bodies, const double *transforms6, double dt);
 void cpo_joint_apply_cached(cpo_joint *j, cpo_body *bodies, double dt_coef);
 void cpo_joint_apply_impulse(cpo_joint *j, cpo_body *bodies, double dt);
 /* the solver loop of cpSpaceStep in the given order */
 void cpo_solve(int n_arb, cpo_arbiter *arbs, int n_joints, cpo_joint *joints, cpo_body *bodies, int iterations, double dt, double dt_coef);
+/* the same loop over one merged sequence: item >= 0 = arbiter index, item < 0 = joint -(item + 1) (a coloured order replayed) */
+void cpo_solve_sequence(long n_items, const int64_t *items, cpo_arbiter *arbs, cpo_joint *joints, cpo_body *bodies, int iterations, double dt, double dt_coef);
 
 #endif

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from chipmunk2d_b200.engine import Scene, SCENE_HEADER, SCENE_BODY, SCENE_SHAPE, SCENE_JOINT
-from chipmunk2d_b200.scenes import golden_scene, ERROR_BIAS_DEFAULT, COLLISION_BIAS_DEFAULT
+from chipmunk2d_b200.scenes import golden_scene, all_joints_scene, ERROR_BIAS_DEFAULT, COLLISION_BIAS_DEFAULT
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -60,6 +60,7 @@ def cpo():
     lib.cpo_arbiter_prestep.argtypes = [C.POINTER(Arbiter), C.POINTER(Body), C.c_double, C.c_double, C.c_double]
     lib.cpo_joint_prestep.argtypes = [C.POINTER(Joint), C.POINTER(Body), C.POINTER(C.c_double), C.c_double]
     lib.cpo_solve.argtypes = [C.c_int, C.POINTER(Arbiter), C.c_int, C.POINTER(Joint), C.POINTER(Body), C.c_int, C.c_double, C.c_double]
+    lib.cpo_solve_sequence.argtypes = [C.c_long, C.POINTER(C.c_int64), C.POINTER(Arbiter), C.POINTER(Joint), C.POINTER(Body), C.c_int, C.c_double, C.c_double]
     lib.cpo_pairs.restype = C.c_long
     lib.cpo_pairs.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_void_p]
     return lib
@@ -274,6 +275,84 @@ def test_joint_step_replay_is_bit_identical(ref, cpo):
         got = (J[q].jAcc2.x, J[q].jAcc2.y) if t == 2 else (J[q].jnAcc,)
         want = (jafter[int(idx)][9], jafter[int(idx)][10]) if t == 2 else (jafter[int(idx)][9],)
         assert got == want, (q, idx, t)
+
+
+VEC2_JOINTS = (2, 3)      # pivot, groove: jAcc is a vector
+
+
+def replay_joint_step(rs, cpo, sc, dt):
+    """One reference step of a contact-free scene replayed through the restated preStep / cached impulse /
+    iterations, in the reference's constraint order.  Returns (bodies, joints, order, after, jafter)."""
+    before = rs.priv_bodies()
+    jprev = rs.priv_joints()
+    rs.step(dt)
+    after = rs.priv_bodies()
+    jafter = rs.priv_joints()
+    order = rs.constraint_order()
+    n = len(before)
+    bodies = bodies_from_priv(before, sc)
+    T = (C.c_double * (6 * n))()
+    T[0:6] = [1, 0, 0, 1, 0, 0]
+    Ti = (C.c_double * 6)()
+    for i in range(1, n):
+        cpo.cpo_body_update_position(C.byref(bodies[i]), dt, Ti)
+        T[6 * i: 6 * i + 6] = list(Ti)
+    J = (Joint * len(order))()
+    for q, idx in enumerate(order):
+        s = sc.joints[int(idx)]
+        jj = J[q]
+        jj.type = int(s["type"]); jj.a = int(s["a"]); jj.b = int(s["b"])
+        jj.maxForce = float(s["max_force"]); jj.errorBias = float(s["error_bias"]); jj.maxBias = float(s["max_bias"])
+        jj.anchorA = Vec(*s["anchor_a"]); jj.anchorB = Vec(*s["anchor_b"]); jj.prm = (C.c_double * 4)(*s["prm"])
+        jj.jnAcc = jprev[int(idx)][9]; jj.jAcc2 = Vec(jprev[int(idx)][9], jprev[int(idx)][10])
+        if jj.type == 7:
+            jj.prm[0] = jprev[int(idx)][8]          # the ratchet's angle is solver state (cpRatchetJoint.c:40)
+        cpo.cpo_joint_prestep(C.byref(jj), bodies, T, dt)
+    h = sc.header
+    g = Vec(float(h["gravity"][0]), float(h["gravity"][1]))
+    damping = float(h["damping"]) ** dt
+    for i in range(1, n):
+        cpo.cpo_body_update_velocity(C.byref(bodies[i]), g, damping, dt)
+    return bodies, J, order, after, jafter
+
+
+def test_all_ten_joint_classes_replay_is_bit_identical(ref, cpo):
+    """groove, damped rotary spring, rotary limit, ratchet and simple motor join the five above: every joint class
+    of the reference, one step replayed from several points of a run (limits and ratchets engaged and free), through
+    cpo_solve AND through cpo_solve_sequence (the merged-sequence loop the coloured-order replay uses)."""
+    sc = all_joints_scene(shapes=False)
+    rs = ref.load(sc.blob)
+    dt = sc.dt
+    engaged = {6: 0, 7: 0}
+    for gap in (1, 6, 33, 36, 50, 94, 12):      # limit engaged from step ~74, ratchet from ~216
+        rs.step(dt, gap)
+        for seq in (False, True):
+            if not seq:
+                # replay the SAME step twice (plain loop, then the sequence loop): snapshot by stepping a twin
+                twin = ref.load(sc.blob)
+                twin.step(dt, int(rs.counts()["stamp"]))
+                assert np.array_equal(np.nan_to_num(twin.priv_bodies()), np.nan_to_num(rs.priv_bodies()))
+                target = twin
+            else:
+                target = rs
+            bodies, J, order, after, jafter = replay_joint_step(target, cpo, sc, dt)
+            n = len(after)
+            if seq:
+                items = (C.c_int64 * len(order))(*[-(q + 1) for q in range(len(order))])
+                cpo.cpo_solve_sequence(len(order), items, None, J, bodies, int(sc.header["iterations"]), dt, 1.0)
+            else:
+                cpo.cpo_solve(0, None, len(order), J, bodies, int(sc.header["iterations"]), dt, 1.0)
+            for i in range(1, n):
+                b = bodies[i]
+                assert [b.v.x, b.v.y, b.w] == [after[i][2], after[i][3], after[i][5]], (gap, seq, i)
+            for q, idx in enumerate(order):
+                t = int(sc.joints[int(idx)]["type"])
+                got = (J[q].jAcc2.x, J[q].jAcc2.y) if t in VEC2_JOINTS else (J[q].jnAcc,)
+                want = (jafter[int(idx)][9], jafter[int(idx)][10]) if t in VEC2_JOINTS else (jafter[int(idx)][9],)
+                assert got == want, (gap, seq, q, idx, t)
+                if t in engaged and J[q].bias != 0.0:
+                    engaged[t] += 1
+    assert engaged[6] > 0 and engaged[7] > 0, engaged     # both limit-type joints were exercised at their limit
 
 
 def test_pair_set_restatement(ref, cpo):
