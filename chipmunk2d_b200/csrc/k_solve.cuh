@@ -156,6 +156,14 @@ CPB_DEVICE void colour_phase_b(const DBodies &B, const DArbs &A, const DJoints &
 	}
 }
 
+// Whatever is still on the worklist when the rounds run out goes to the overflow bucket (solved by one thread after the
+// regular colours of every pass): slower, never dropped.
+CPB_DEVICE void colour_leftover(const DArbs &A, const DJoints &J, const DColour &K, int *shist, int nA, int round, int tid, int nth){
+	const int *wl = K.wl[round & 1];
+	int n = *((volatile int *)&K.wl_n[round]);
+	for(int k = tid; k < n; k += nth) cons_set_colour(A, J, K, shist, nA, wl[k], CPB_OVERFLOW_COLOUR);
+}
+
 // exclusive prefix of the per-colour counts (single thread; 64 entries) + number of colours in use
 CPB_DEVICE void colour_starts(const DColour &K, DCounters *C){
 	int ra = 0, rj = 0, ncol = 0;
@@ -731,6 +739,11 @@ template<bool SPACE_LOCAL, bool STREAM_ROWS> __global__ void __launch_bounds__(2
 		HIST_FLUSH();
 		GRID_SYNC();
 	}
+	if(rounds_done == CPB_MAX_COLOUR_ROUNDS && *((volatile int *)&K.wl_n[CPB_MAX_COLOUR_ROUNDS]) != 0){
+		colour_leftover(A, J, K, s_hist, nA, CPB_MAX_COLOUR_ROUNDS, tid, nth);
+		HIST_FLUSH();
+		GRID_SYNC();
+	}
 	PROF(1);
 	if(tid == 0){ colour_starts(K, C); K.prof[5] = (unsigned long long)rounds_done; K.prof[6] = (unsigned long long)K.wl_n[0]; }
 	if(SPACE_LOCAL){
@@ -810,6 +823,7 @@ __global__ void k_colour_b(DBodies B, DArbs A, DJoints J, DColour K, int round){
 }
 __global__ void k_colour_finish(DArbs A, DJoints J, DRows R, DColour K, DCounters *C, int stage){
 	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
+	if(stage == 2){ colour_leftover(A, J, K, (int *)NULL, nA, CPB_MAX_COLOUR_ROUNDS, CPB_TID, CPB_NTHREADS); return; }
 	if(stage == 0){ if(CPB_TID == 0) colour_starts(K, C); }
 	else build_rows(A, J, R, K, (int *)NULL, (int *)NULL, nA, CPB_TID, CPB_NTHREADS);
 }

@@ -223,6 +223,7 @@ static int world_sync(cpb200_world *w)
 }
 
 static int alloc_arbs(cpb200_world *w, int cap);
+static int counters_check(cpb200_world *w);
 static int alloc_pairs(cpb200_world *w, int cap);
 
 extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
@@ -460,6 +461,9 @@ extern "C" int cpb200_world_update_bodies(cpb200_world *w, int first, int n, con
 	int h_bad = 0;
 	CPB_CHECK(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
 	w->cache_dirty = true;
+	// a body may have changed between dynamic and static / kinematic: two constraints that kept last step's colour
+	// could then share a body that is now written -- colour from scratch once
+	w->hints_valid = false;
 	if(world_sync(w)) return -1;
 	if(h_bad){ cpb_set_error("a body names a space index outside [0, %d)", w->n_spaces); return -1; }
 	return 0;
@@ -1138,6 +1142,7 @@ static int step_phase_b2(cpb200_world *w)
 				LAUNCH(k_colour_a, 4, 64, st, B, Ac, J, K, round);
 				LAUNCH(k_colour_b, 4, 64, st, B, Ac, J, K, round);
 			}
+			if(K.wl_n[CPB_MAX_COLOUR_ROUNDS] != 0) LAUNCH(k_colour_finish, 4, 64, st, Ac, J, w->R, K, w->C, 2);
 			LAUNCH(k_colour_finish, 1, 32, st, Ac, J, w->R, K, w->C, 0);
 			LAUNCH(k_colour_finish, 4, 64, st, Ac, J, w->R, K, w->C, 1);
 			int ncol = w->C->n_colours;
@@ -1267,6 +1272,18 @@ extern "C" int cpb200_world_time_steps(cpb200_world *w, double dt, int n, float 
 	return cpb200_world_sync(w);
 }
 
+// hC holds a fresh copy of the device counters: refresh the grid-sizing hint, turn an overflow flag into an error
+static int counters_check(cpb200_world *w)
+{
+	w->last_active = w->hC->n_active;
+	if(w->hC->overflow){
+		cpb_set_error("device buffer overflow (flags 0x%x: 1 pairs, 2 arbiters, 4 table, 8 bvh stack): collisions of the last step were dropped; "
+			"call cpb200_world_reserve with larger capacities (in use: %d pair candidates, %d arbiter records)", w->hC->overflow, w->cap_pairs, w->cap_arbs);
+		return -2;
+	}
+	return 0;
+}
+
 extern "C" int cpb200_world_sync(cpb200_world *w)
 {
 	if(!w) return -1;
@@ -1274,12 +1291,7 @@ extern "C" int cpb200_world_sync(cpb200_world *w)
 	if(world_sync(w)) return -1;
 	CPB_CHECK(cudaMemcpyAsync(w->hC, w->C, sizeof(DCounters), cudaMemcpyDeviceToHost, w->stream));
 	CPB_CHECK(cudaStreamSynchronize(w->stream));
-	w->last_active = w->hC->n_active;
-	if(w->hC->overflow){
-		cpb_set_error("device buffer overflow (flags 0x%x: 1 pairs, 2 arbiters, 4 table, 8 bvh stack); call cpb200_world_reserve with larger capacities", w->hC->overflow);
-		return -2;
-	}
-	return 0;
+	return counters_check(w);
 }
 
 // ------------------------------------------------------------------ read-back
@@ -1293,7 +1305,11 @@ extern "C" int cpb200_world_get_bodies(cpb200_world *w, int first, int n, cpb200
 	if(stage_reserve(w, bytes)) return -1;
 	LAUNCH(k_pack_body_state, grid_for(n, 128), 128, w->stream, w->B, (cpb200_body_state *)w->d_stage, first, n);
 	CPB_CHECK(cudaMemcpyAsync(out, w->d_stage, bytes, cudaMemcpyDeviceToHost, w->stream));
-	return world_sync(w);
+	// the step counters ride along (64 bytes): a host that only ever reads bodies back -- the Chipmunk API layer -- still
+	// learns about exhausted pair / arbiter buffers, and the solver's grid sizing gets a fresh constraint count
+	CPB_CHECK(cudaMemcpyAsync(w->hC, w->C, sizeof(DCounters), cudaMemcpyDeviceToHost, w->stream));
+	if(world_sync(w)) return -1;
+	return counters_check(w);
 }
 
 extern "C" int cpb200_world_get_body_bias(cpb200_world *w, int first, int n, double *out)
@@ -1335,7 +1351,9 @@ extern "C" int cpb200_world_get_arbiters(cpb200_world *w, int cap, cpb200_arbite
 	DArbs &A = w->A[w->cur];
 	int n = 0;
 	CPB_CHECK(cudaMemcpyAsync(&n, A.count_ptr, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
+	CPB_CHECK(cudaMemcpyAsync(w->hC, w->C, sizeof(DCounters), cudaMemcpyDeviceToHost, w->stream));
 	if(world_sync(w)) return -1;
+	if(counters_check(w)) return -2;   // a host that reads arbiters (collision handlers) must not see a truncated list silently
 	if(n > A.cap) n = A.cap;
 	size_t N = (size_t)n;
 	std::vector<int> sa, sb, ba, bb, cnt, state, active; std::vector<uint32_t> stamp; std::vector<V2> nn, svr, r1, r2;

@@ -416,6 +416,10 @@ ensure_world(cpSpace *space)
 	if(space->world) return;
 	space->world = cpb200_world_create(space->device, 1);
 	if(!space->world) cpEngineError("cpb200_world_create");
+	/* The device buffers default to 16 pair candidates and 8 arbiter records per shape; a scene that needs more fails
+	 * loudly at its next read-back (cpb200_world_get_bodies / get_arbiters report the overflow) and can raise them here. */
+	const char *rp = getenv("CPB200_RESERVE_PAIRS"), *ra = getenv("CPB200_RESERVE_ARBITERS");
+	if(rp || ra) cpb200_world_reserve(space->world, rp ? atoi(rp) : 0, ra ? atoi(ra) : 0);
 }
 
 static void

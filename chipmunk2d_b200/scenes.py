@@ -312,3 +312,25 @@ def all_joints_scene(damping=0.9, shapes=True):
     if not shapes:
         s = s[:0]
     return Scene.build(h, b, s, np.zeros((0, 2)), j)
+
+
+def hub_scene(n=300, hub_radius=200.0, r=2.0):
+    """One big dynamic circle touched by n small dynamic circles on a ring around it: a constraint graph with one body
+    of degree n (more contacts than the 63 regular colours of the device's edge colouring can separate)."""
+    h = _header(gravity=(0.0, 0.0), slop=0.1)
+    b = np.zeros(n + 2, dtype=SCENE_BODY)
+    b[0] = _static_body()[0]
+    b["m"][1] = 50.0; b["i"][1] = 50.0 * 0.5 * hub_radius * hub_radius
+    b["p"][1] = (0.0, 0.0); b["v"][1] = (3.0, -2.0); b["w"][1] = 0.05
+    ang = 2.0 * math.pi * np.arange(n) / n
+    d = hub_radius + r - 0.3
+    b["m"][2:] = 1.0; b["i"][2:] = 0.5 * r * r
+    b["p"][2:, 0] = d * np.cos(ang); b["p"][2:, 1] = d * np.sin(ang)
+    b["v"][2:, 0] = -5.0 * np.cos(ang); b["v"][2:, 1] = -5.0 * np.sin(ang)
+    s = np.zeros(n + 1, dtype=SCENE_SHAPE)
+    s["type"] = 0
+    s["body"] = np.arange(1, n + 2)
+    s["categories"] = ALL_CATEGORIES; s["mask"] = ALL_CATEGORIES
+    s["e"] = 0.1; s["u"] = 0.6
+    s["r"][0] = hub_radius; s["r"][1:] = r
+    return Scene.build(h, b, s, np.zeros((0, 2)), np.zeros(0, dtype=SCENE_JOINT))

@@ -210,6 +210,9 @@ class Ref:
         cp.refp_get_constraint_order.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         cp.refp_space_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         cp.cpSpaceStep.argtypes = [C.c_void_p, C.c_double]
+        cp.refp_install_order_hook.argtypes = [C.c_void_p]
+        cp.refp_set_solver_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        cp.refp_order_hook_stats.argtypes = [C.POINTER(C.c_int)]
 
     def demo_names(self):
         return [self.cp.refp_demo_name(i).decode() for i in range(self.cp.refp_demo_count())]
@@ -290,6 +293,25 @@ class RefSpace(SceneSpace):
         n = self.ref.cp.refp_pairs_bruteforce(self.space, ap, cap, out.ctypes.data_as(C.POINTER(C.c_uint64)))
         assert n <= cap
         return out[:n]
+
+    def install_order_hook(self):
+        """Route every body's velocity_func through the probe's wrapper so that set_solver_order can permute
+        space->arbiters / space->constraints right before the solver loop (ref_probe.c, 'solver-order hook')."""
+        self.ref.cp.refp_install_order_hook(self.space)
+
+    def set_solver_order(self, pairs, hash0=None, joints=()):
+        """Order for the NEXT step: pairs = (shape a << 32 | shape b) per arbiter, hash0 = hash of the contact to
+        visit first per arbiter, joints = scene joint indices."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint64)
+        h = None if hash0 is None else np.ascontiguousarray(hash0, dtype=np.uint64)
+        j = np.ascontiguousarray(joints, dtype=np.int32)
+        self.ref.cp.refp_set_solver_order(self.space, len(pairs), pairs.ctypes.data, None if h is None else h.ctypes.data,
+                                          len(j), j.ctypes.data if len(j) else None, self.n_joints)
+
+    def order_hook_stats(self):
+        out = (C.c_int * 2)()
+        self.ref.cp.refp_order_hook_stats(out)
+        return {"applied": out[0], "unmatched": out[1]}
 
     def counts(self):
         out = (C.c_int * 8)()

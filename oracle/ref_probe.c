@@ -451,3 +451,102 @@ REFP_EXPORT int refp_space_counts(cpSpace *space, int *out)
 	out[6] = contacts;
 	return 7;
 }
+
+/* ---- solver-order hook: let the UNMODIFIED reference solve one step in a caller-given order ----
+ * cpSpaceStep walks space->arbiters and space->constraints in array order (cpSpaceStep.c:406-427).  Both arrays
+ * are complete once the collision phase and cpSpaceProcessComponents are over, and the first thing the reference
+ * calls after that through a public function pointer is every dynamic body's velocity_func (cpSpaceStep.c:398-404).
+ * refp_install_order_hook points that pointer of every body at a wrapper which, once per step, permutes the two
+ * arrays into the order set by refp_set_solver_order and then calls the stock cpBodyUpdateVelocity.  No reference
+ * arithmetic changes: a Gauss-Seidel sweep is run over the same constraints in another order -- the order the
+ * device's coloured solver used -- so that one production step can be compared with the reference itself. */
+typedef struct order_key { uint64_t key; int rank; uint64_t hash0; } order_key;
+static struct {
+	cpSpace *space;
+	int pending;
+	int n_arb; order_key *arb;      /* sorted by key */
+	int n_con; int *con_rank;       /* con_rank[scene joint index] */
+	int n_con_cap;
+	int applied, unmatched;
+} g_order;
+
+static int cmp_order_key(const void *a, const void *b)
+{
+	uint64_t x = ((const order_key *)a)->key, y = ((const order_key *)b)->key;
+	return (x < y ? -1 : (x > y ? 1 : 0));
+}
+
+typedef struct ranked_ptr { void *p; long rank; int idx; } ranked_ptr;
+static int cmp_ranked(const void *a, const void *b)
+{
+	const ranked_ptr *x = (const ranked_ptr *)a, *y = (const ranked_ptr *)b;
+	if(x->rank != y->rank) return (x->rank < y->rank ? -1 : 1);
+	return (x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0));
+}
+
+static void order_apply(cpSpace *space)
+{
+	cpArray *arbs = space->arbiters;
+	ranked_ptr *tmp = (ranked_ptr *)malloc(sizeof(ranked_ptr)*(size_t)(arbs->num + space->constraints->num + 1));
+	g_order.unmatched = 0;
+	for(int i = 0; i < arbs->num; i++){
+		cpArbiter *arb = (cpArbiter *)arbs->arr[i];
+		uint64_t ta = (uint64_t)(uint32_t)UNTAG(arb->a->userData), tb = (uint64_t)(uint32_t)UNTAG(arb->b->userData);
+		order_key probe; probe.key = (ta < tb ? (ta << 32) | tb : (tb << 32) | ta);
+		order_key *hit = (order_key *)bsearch(&probe, g_order.arb, (size_t)g_order.n_arb, sizeof(order_key), cmp_order_key);
+		tmp[i].p = arb; tmp[i].idx = i; tmp[i].rank = (hit ? hit->rank : 0x7fffffffL);
+		if(!hit) g_order.unmatched++;
+		/* visit the two contacts in the caller's order as well */
+		if(hit && arb->count == 2 && arb->contacts[0].hash != hit->hash0 && arb->contacts[1].hash == hit->hash0){
+			struct cpContact c = arb->contacts[0]; arb->contacts[0] = arb->contacts[1]; arb->contacts[1] = c;
+		}
+	}
+	qsort(tmp, (size_t)arbs->num, sizeof(ranked_ptr), cmp_ranked);
+	for(int i = 0; i < arbs->num; i++) arbs->arr[i] = tmp[i].p;
+	cpArray *cons = space->constraints;
+	for(int i = 0; i < cons->num; i++){
+		int tag = UNTAG(((cpConstraint *)cons->arr[i])->userData);
+		tmp[i].p = cons->arr[i]; tmp[i].idx = i;
+		tmp[i].rank = (tag >= 0 && tag < g_order.n_con && g_order.con_rank[tag] >= 0 ? g_order.con_rank[tag] : 0x7fffffffL);
+	}
+	qsort(tmp, (size_t)cons->num, sizeof(ranked_ptr), cmp_ranked);
+	for(int i = 0; i < cons->num; i++) cons->arr[i] = tmp[i].p;
+	free(tmp);
+	g_order.applied++;
+}
+
+static void hook_velocity(cpBody *body, cpVect gravity, cpFloat damping, cpFloat dt)
+{
+	if(g_order.pending && body->space == g_order.space){ g_order.pending = 0; order_apply(body->space); }
+	cpBodyUpdateVelocity(body, gravity, damping, dt);
+}
+
+static void hook_body(cpBody *b, void *unused){ (void)unused; if(b->velocity_func == cpBodyUpdateVelocity) b->velocity_func = hook_velocity; }
+
+REFP_EXPORT void refp_install_order_hook(cpSpace *space){ cpSpaceEachBody(space, hook_body, NULL); }
+
+/* pairs[n_arb] = (shape tag a)<<32 | (shape tag b) in the wanted solver order, hash0[n_arb] = hash of the contact to
+ * visit first (0 = leave the contact order alone); cons[n_con] = scene joint indices in the wanted order.
+ * Applies to the NEXT cpSpaceStep of `space` only.  Arbiters / constraints not listed keep their relative order
+ * after the listed ones. */
+REFP_EXPORT void refp_set_solver_order(cpSpace *space, int n_arb, const uint64_t *pairs, const uint64_t *hash0, int n_con, const int *cons, int n_joints_total)
+{
+	g_order.space = space;
+	g_order.arb = (order_key *)realloc(g_order.arb, sizeof(order_key)*(size_t)(n_arb + 1));
+	for(int i = 0; i < n_arb; i++){
+		uint64_t a = pairs[i] >> 32, b = pairs[i] & 0xffffffffu;
+		g_order.arb[i].key = (a < b ? (a << 32) | b : (b << 32) | a);
+		g_order.arb[i].rank = i;
+		g_order.arb[i].hash0 = (hash0 ? hash0[i] : 0);
+	}
+	g_order.n_arb = n_arb;
+	qsort(g_order.arb, (size_t)n_arb, sizeof(order_key), cmp_order_key);
+	g_order.con_rank = (int *)realloc(g_order.con_rank, sizeof(int)*(size_t)(n_joints_total + 1));
+	for(int i = 0; i < n_joints_total; i++) g_order.con_rank[i] = -1;
+	for(int i = 0; i < n_con; i++) if(cons[i] >= 0 && cons[i] < n_joints_total) g_order.con_rank[cons[i]] = i;
+	g_order.n_con = n_joints_total;
+	g_order.pending = 1;
+}
+
+/* out[0] = times the order was applied, out[1] = arbiters of the last application that the caller had not listed */
+REFP_EXPORT void refp_order_hook_stats(int *out){ out[0] = g_order.applied; out[1] = g_order.unmatched; }
