@@ -1,24 +1,33 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the cpSpaceStep hot path on B200 (one JSON line; see DESIGN.md "Measurement").
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload pile1m|batch|c1|c2|mixed100k] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference] [--no-sub]
 
 Workloads (BASELINE.json configs):
-  pile1m     config 4: 1 000 000 radius-5 circles, settled hexagonal pile, single space, iterations 10,
-             dt 1/60 (the north star's roofline target; DEFAULT).  A single space does not shard
-             (SURVEY.md 8e): with N GPUs every rank steps its own replica ("replicas only").
-  batch      config 5: independent PyramidStack / Chains spaces, 4096 per GPU, sharded by space index with no
-             data-path collective (weak scaling); step statistics are reduced over NCCL.
-  c1 / c2    configs 1 / 2 (demo/Bench.c scenes, 1000 bodies): latency-bound, reported for completeness.
-  mixed100k  config 3.
+  pile1m          config 4 AS BASELINE WORDS IT (DEFAULT): 1 000 000 radius-5 circles in one space, hexagonal close packing
+                  (every circle touches its neighbours from the first step), sleepTimeThreshold 0.5 ("sleeping islands":
+                  the islands pass runs every step), iterations 10, dt 1/60.  The column is 667 rows tall and is still
+                  collapsing during the 20 + K measured steps (v_rms ~ 90), as it is in the reference; nothing can fall
+                  asleep in that window.  A single space does not shard: with N GPUs every rank steps its
+                  own replica ("replicas only").
+  pile1m_nosleep  the same with sleepTimeThreshold = infinity (round-1 headline; no islands pass).
+  pile1m_shallow  1 000 000 circles 20 rows deep, 600 settle steps: kinetic energy decays, islands fall asleep.
+  batch           config 5, weak: 4096 PyramidStack / Chains spaces PER GPU.
+  batch_sharded   config 5 as SURVEY 8(e) words it: 4096 spaces in total, sharded 4096/N per GPU (sharding.shard_range),
+                  no data-path collective; step statistics reduced over NCCL.
+  c1 / c2         configs 1 / 2 (demo/Bench.c scenes, 1000 bodies): latency-bound.
+  mixed100k       config 3.
 
 A "step" is one cpSpaceStep of the whole workload.  `value` = non-static bodies x steps / device seconds with
 everything resident in HBM (CUDA events on the engine's stream, max over ranks).  `e2e` = the same metric
 through the C-ABI (include/cpb200.h) with HOST buffers: every step uploads a force for every body from a
 page-locked host array (H2D), steps, and downloads every body's state into a host array (D2H).
 `e2e_per_body_api` = the same through the per-object Chipmunk2D C API (cpBodySetForce / cpSpaceStep /
-cpBodyGetPosition on every body).
-`--impl reference` times the unmodified reference (oracle/_ref, cpSpaceStep, CPU) on a bounded sample.
+cpBodyGetPosition on every body).  The default line also carries `sub_records`: the other configs measured in the
+same process (device-timed value + C-ABI e2e each), so that one driver run holds every BASELINE config.
+
+`--impl reference` times the UNMODIFIED reference (oracle/_ref) on the host: cpSpace on one thread and cpHastySpace on
+its two solver threads, on the SAME configuration (1 M bodies for the default workload) with fewer steps.
 """
 import argparse
 import json
@@ -33,36 +42,71 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# cpu sample: the reference needs ~20 s just to BUILD a 100k-circle space (BBTree inserts) and ~0.6 s per
-# step there; a 20k-circle pile of the same packing steps in ~75 ms, so K steps stay within a minute.
-REF_SAMPLE_BODIES = 20000
+N_PILE = 1000000
+N_BATCH = 4096
+CPU_SAMPLE_PILE = 100000      # cpu_baseline leg of the GPU arm: a bounded sample (about 10-20 s of host work)
+CPU_SAMPLE_MIXED = 20000
+SETTLE = {"pile1m": 20, "pile1m_nosleep": 20, "pile1m_shallow": 600, "batch": 300, "batch_sharded": 300, "c1": 300, "c2": 300, "mixed100k": 120}
+SUB_RECORDS = ["batch_sharded", "batch", "mixed100k", "c1", "c2", "pile1m_shallow"]
 
 
 def rank_info():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
-def build_scenes(workload, rank, for_reference=False):
+def workload_config(workload, world):
+    """The configuration a workload names -- identical for the GPU arm and the reference arm."""
+    single = "replicas x%d (a single space does not shard)" % world
+    if workload in ("pile1m", "pile1m_nosleep", "pile1m_shallow"):
+        cfg = {"workload": {"pile1m": "config4_circle_pile_1M_single_space_sleeping_islands", "pile1m_nosleep": "config4_circle_pile_1M_single_space_sleeping_off",
+                            "pile1m_shallow": "config4_circle_pile_1M_single_space_20_rows_settled_and_asleep"}[workload],
+               "bodies_per_gpu": N_PILE, "iterations": 10, "dt": 1.0 / 60.0,
+               "sleep_time_threshold": (None if workload == "pile1m_nosleep" else 0.5), "parallelism": single,
+               "l2": "inputs larger than L2 (solver rows + arbiter records >> 126 MB)"}
+    elif workload == "batch":
+        cfg = {"workload": "config5_batched_PyramidStack_Chains_spaces_weak_4096_per_gpu", "spaces_per_gpu": N_BATCH, "spaces_total": N_BATCH * world,
+               "iterations": 30, "dt": 1.0 / 180.0, "parallelism": "spaces sharded x%d, no data-path collective" % world,
+               "l2": "working set fits L2 / shared memory; latency-bound configuration"}
+    elif workload == "batch_sharded":
+        cfg = {"workload": "config5_batched_PyramidStack_Chains_4096_spaces_sharded", "spaces_total": N_BATCH, "spaces_per_gpu": N_BATCH // world,
+               "iterations": 30, "dt": 1.0 / 180.0, "parallelism": "4096 spaces sharded 4096/%d per GPU (strong), no data-path collective" % world,
+               "l2": "working set fits L2 / shared memory; latency-bound configuration"}
+    elif workload == "c1":
+        cfg = {"workload": "config1_simple_terrain_circles_1000", "bodies_per_gpu": 1000, "iterations": 10, "dt": 1.0 / 60.0, "parallelism": single,
+               "l2": "working set fits L2; latency-bound configuration"}
+    elif workload == "c2":
+        cfg = {"workload": "config2_complex_terrain_hexagons_1000", "bodies_per_gpu": 1000, "iterations": 10, "dt": 1.0 / 60.0, "parallelism": single,
+               "l2": "working set fits L2; latency-bound configuration"}
+    elif workload == "mixed100k":
+        cfg = {"workload": "config3_mixed_100k_with_springs_and_pivots", "bodies_per_gpu": 100000, "iterations": 10, "dt": 1.0 / 60.0, "parallelism": single,
+               "l2": "solver rows fit L2 (default caching)"}
+    else:
+        raise SystemExit("unknown workload %r" % workload)
+    cfg["settle_steps"] = SETTLE[workload]
+    return cfg
+
+
+def build_scenes(workload, rank=0, world=1, sample=None):
+    """Scenes of one rank.  `sample` (bodies or spaces) builds the bounded CPU sample of the same generator."""
     from chipmunk2d_b200.scenes import circle_pile, mixed_drop, batched_demo_scenes, golden_scene
-    if workload == "pile1m":
-        n = REF_SAMPLE_BODIES if for_reference else 1000000
-        return [circle_pile(n, dense=True, sleep=np.inf)], {"workload": "config4_circle_pile_1M_single_space", "bodies_per_gpu": n,
-                                                             "iterations": 10, "dt": 1.0 / 60.0, "sleeping": "off (threshold inf) so every body is solved every step"}
-    if workload == "pile1m_sleep":
-        n = REF_SAMPLE_BODIES if for_reference else 1000000
-        return [circle_pile(n, dense=True, sleep=0.5)], {"workload": "config4_circle_pile_1M_single_space_sleeping_on", "bodies_per_gpu": n, "iterations": 10, "dt": 1.0 / 60.0}
+    from chipmunk2d_b200.sharding import shard_range, space_kind
+    if workload in ("pile1m", "pile1m_nosleep"):
+        return [circle_pile(sample or N_PILE, dense=True, sleep=(np.inf if workload == "pile1m_nosleep" else 0.5))]
+    if workload == "pile1m_shallow":
+        n = sample or N_PILE
+        return [circle_pile(n, dense=True, sleep=0.5, columns=max(8, n // 20))]
     if workload == "batch":
-        n = 64 if for_reference else 4096
-        sc = batched_demo_scenes(n)
-        return sc, {"workload": "config5_batched_PyramidStack_Chains_spaces", "spaces_per_gpu": n, "bodies_per_gpu": sum(s.n_dynamic() for s in sc),
-                    "iterations": 30, "dt": 1.0 / 180.0}
+        return batched_demo_scenes(sample or N_BATCH)
+    if workload == "batch_sharded":
+        lo, hi = shard_range(sample or N_BATCH, world, rank)
+        pyr, chn = golden_scene("PyramidStack"), golden_scene("Chains")
+        return [pyr if space_kind(g) == "PyramidStack" else chn for g in range(lo, hi)]
     if workload == "c1":
-        return [golden_scene("SimpleTerrainCircles_1000")], {"workload": "config1_simple_terrain_circles_1000", "bodies_per_gpu": 1000, "iterations": 10, "dt": 1.0 / 60.0}
+        return [golden_scene("SimpleTerrainCircles_1000")]
     if workload == "c2":
-        return [golden_scene("ComplexTerrainHexagons_1000")], {"workload": "config2_complex_terrain_hexagons_1000", "bodies_per_gpu": 1000, "iterations": 10, "dt": 1.0 / 60.0}
+        return [golden_scene("ComplexTerrainHexagons_1000")]
     if workload == "mixed100k":
-        n = REF_SAMPLE_BODIES if for_reference else 100000
-        return [mixed_drop(n)], {"workload": "config3_mixed_100k_with_springs_and_pivots", "bodies_per_gpu": n, "iterations": 10, "dt": 1.0 / 60.0}
+        return [mixed_drop(sample or 100000)]
     raise SystemExit("unknown workload %r" % workload)
 
 
@@ -121,117 +165,161 @@ def algorithmic_bytes_solver(n_contacts, n_joints, iterations):
     return 384.0 * iterations * n_contacts + 192.0 * n_contacts + 300.0 * (iterations + 1) * n_joints
 
 
-SETTLE = {"pile1m": 30, "pile1m_sleep": 30, "batch": 300, "c1": 300, "c2": 300, "mixed100k": 120}
+# ------------------------------------------------------------------------------------------------ CPU (reference) legs
+
+def _ref_penetration(rs):
+    """Deepest contact of a reference space: -min over contacts of dot(r2 - r1 + (p_b - p_a), n) (cpArbiter.c:425)."""
+    arbs, _ = rs.priv_arbiters()
+    if len(arbs) == 0:
+        return 0.0
+    rb = rs.priv_bodies()
+    sh = np.frombuffer(rs.blob.tobytes(), dtype=np.uint8)
+    from chipmunk2d_b200.engine import Scene
+    body = Scene(sh.tobytes()).shapes["body"]
+    pa = np.nan_to_num(rb[body[arbs[:, 0].astype(int)], 0:2]); pb = np.nan_to_num(rb[body[arbs[:, 1].astype(int)], 0:2])
+    n = arbs[:, 4:6]
+    pen = 0.0
+    for k in range(2):
+        m = arbs[:, 2] > k
+        q = arbs[:, 12 + 12 * k: 24 + 12 * k]
+        d = np.sum((q[:, 2:4] - q[:, 0:2] + (pb - pa)) * n, axis=1)
+        if np.any(m):
+            pen = max(pen, float(np.max(-d[m])))
+    return pen
 
 
-def cpu_baseline_sample(workload, steps, warmup):
-    """The unmodified reference (oracle/_ref) on a bounded sample of the workload.  A single space runs on one
-    thread (the reference's own 2-thread cpHastySpace is slower); independent spaces (the batched
-    workload) run one cpSpace per host core over all cores -- ctypes releases the GIL inside the library."""
+def reference_run(workload, steps, warmup, settle, sample=None, hasty=False, threads=0):
+    """The unmodified reference (oracle/_ref) stepping `workload` (or a bounded sample of its generator) on the host.
+    A single space runs cpSpaceStep on one thread (or cpHastySpaceStep on its solver threads); independent spaces (the
+    batched workload) run one cpSpace per host core over all cores -- ctypes releases the GIL inside the library."""
     from oracle import ref as oref
     if not oref.available():
         return None
     cores = max(1, os.cpu_count() or 1)
-    scenes, cfg = build_scenes(workload, 0, for_reference=True)
-    if workload == "batch" and cores > 1:
-        from chipmunk2d_b200.scenes import batched_demo_scenes
-        scenes = batched_demo_scenes(max(64, 8 * cores))
+    scenes = build_scenes(workload, 0, 1, sample=sample)
     r = oref.Ref()
-    settle = SETTLE.get(workload, 0)
-    spaces = [r.load(sc.blob) for sc in scenes]
+    t0 = time.perf_counter()
+    spaces = [r.load(sc.blob, hasty=hasty, threads=threads) for sc in scenes]
+    t_build = time.perf_counter() - t0
     dt = scenes[0].dt
     nb = sum(sc.n_dynamic() for sc in scenes)
-    threads = cores if len(spaces) > 1 else 1
+    pool = cores if len(spaces) > 1 else 1
 
     def run(fn):
-        if threads == 1:
+        if pool == 1:
             return [fn(s) for s in spaces]
         from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(max_workers=threads) as ex:
+        with ThreadPoolExecutor(max_workers=pool) as ex:
             return list(ex.map(fn, spaces))
 
-    run(lambda s: s.step(dt, settle + warmup))     # same untimed settling as the GPU arm: both time the settled workload
+    run(lambda s: s.step(dt, settle + warmup))
     t0 = time.perf_counter()
     per_space = run(lambda s: s.time_steps(dt, steps))
     wall = time.perf_counter() - t0
-    t = wall if threads > 1 else sum(per_space)
-    contacts = sum(s.counts()["contacts"] for s in spaces)
+    t = wall if pool > 1 else sum(per_space)
+    counts = [s.counts() for s in spaces]
+    pen = _ref_penetration(spaces[0]) if (len(spaces) == 1 and nb <= 200000) else None
     for s in spaces:
-        s.space = None  # leak: tearing a 20k-body reference space down is O(n^2)
-    how = ("1 thread (cpHastySpace's 2 threads are slower, BASELINE.md)" if threads == 1 else
-           "%d host threads, one independent cpSpace each at a time (wall clock over the pool)" % threads)
-    return {"value": nb * steps / t, "unit": "body-steps/s", "cores": threads, "kind": "reference",
-            "sample": "%s at %d bodies (%d spaces), %d settle + %d warm-up + %d timed cpSpaceStep, gcc -O2 -ffp-contract=off no fast-math, %s" % (
-                cfg["workload"], nb, len(scenes), settle, warmup, steps, how),
-            "ms_per_step": 1000.0 * t / steps, "contacts_per_step": contacts}
+        s.space = None  # leak on purpose: tearing a large reference space down is quadratic
+    solver_threads = (2 if hasty else 1)     # cpHastySpace caps its solver threads at MAX_THREADS = 2 (cpHastySpace.c:387)
+    how = ("cpHastySpaceStep, %d solver threads (cpHastySpaceSetThreads(%d), capped at 2 by the reference)" % (solver_threads, threads) if hasty else
+           ("cpSpaceStep, 1 thread" if pool == 1 else "%d host threads, one independent cpSpace each at a time (wall clock over the pool)" % pool))
+    return {"value": nb * steps / t, "unit": "body-steps/s", "cores": (pool if pool > 1 else solver_threads), "kind": "reference",
+            "sample": "%s at %d bodies (%d space%s), %d settle + %d warm-up + %d timed steps, %s; gcc -O2 -ffp-contract=off no fast-math; space built in %.1f s" % (
+                workload, nb, len(scenes), "" if len(scenes) == 1 else "s", settle, warmup, steps, how, t_build),
+            "bodies": nb, "ms_per_step": 1000.0 * t / steps, "contacts_per_step": sum(c["contacts"] for c in counts), "arbiters_per_step": sum(c["arbiters"] for c in counts),
+            "max_penetration": pen, "host_cores": cores}
+
+
+def cpu_sample_size(workload):
+    return {"pile1m": CPU_SAMPLE_PILE, "pile1m_nosleep": CPU_SAMPLE_PILE, "pile1m_shallow": CPU_SAMPLE_PILE, "mixed100k": CPU_SAMPLE_MIXED,
+            "batch": max(64, 8 * (os.cpu_count() or 1)), "batch_sharded": max(64, 8 * (os.cpu_count() or 1))}.get(workload)
+
+
+def cpu_baseline_sample(workload, with_hasty=True):
+    """cpu_baseline of the GPU arm: a BOUNDED sample of the workload's generator on the box's host cores."""
+    sample = cpu_sample_size(workload)
+    big = workload.startswith("pile1m") or workload == "mixed100k"
+    settle = (5 if big else SETTLE[workload])
+    if workload == "mixed100k":
+        settle = SETTLE[workload]
+    steps, warm = ((10, 2) if big else (40, 10))
+    base = reference_run(workload, steps, warm, settle, sample=sample)
+    if base is None:
+        return None
+    if with_hasty and not workload.startswith("batch"):
+        h = reference_run(workload, steps, warm, settle, sample=sample, hasty=True, threads=0)
+        if h:
+            base["hasty"] = {k: h[k] for k in ("value", "unit", "cores", "ms_per_step", "sample")}
+    return base
 
 
 def run_reference(args):
     rank, local_rank, world = rank_info()
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 100))
-    warm = max(0, min(args.warmup, 20))
-    base = cpu_baseline_sample(args.workload, steps, warm)
-    _, cfg = build_scenes(args.workload, 0, for_reference=False)
+    cfg = workload_config(args.workload, max(1, args.gpus))
+    steps = max(1, min(args.steps, 3 if args.workload.startswith("pile1m") else 40))
+    warm = max(0, min(args.warmup, 2 if args.workload.startswith("pile1m") else 10))
+    settle = (5 if args.workload.startswith("pile1m") and args.workload != "pile1m_shallow" else SETTLE[args.workload])
+    sample = (cpu_sample_size(args.workload) if args.workload.startswith("batch") else None)
+    base = reference_run(args.workload, steps, warm, settle, sample=sample)
     if base is None:
         emit({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"})
         return
+    if not args.workload.startswith("batch"):
+        h = reference_run(args.workload, steps, warm, settle, sample=sample, hasty=True, threads=0)
+        if h:
+            base["hasty"] = {k: h[k] for k in ("value", "unit", "cores", "ms_per_step", "sample")}
     line = {"impl": "reference", "metric": "body_steps_per_sec", "value": base["value"], "unit": "body-steps/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": cfg, "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
-    os._exit(0)
 
 
-def run_ours(args):
-    rank, local_rank, world = rank_info()
+# ------------------------------------------------------------------------------------------------ the GPU arm
+
+def measure(workload, args, ctx, full):
+    """One workload on this rank's GPU: device-timed value, C-ABI e2e and (full) stage profile / roofline inputs."""
     import torch
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the step engine has no CPU fallback)")
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    else:
-        dist = None
-    from chipmunk2d_b200.engine import World, BODY_DESC, BODY_STATE
-    from chipmunk2d_b200.api import load_scene_lib
-    from oracle.ref import SceneSpace
-
-    os.environ["CPB200_DEVICE"] = str(local_rank)   # spaces created through the C API follow the rank's GPU
-    # the host layer threads its mirror loops: share the host cores between the ranks of this node
-    os.environ.setdefault("CPB200_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, world))))
-    scenes, cfg = build_scenes(args.workload, rank)
+    from chipmunk2d_b200.engine import World, BODY_STATE
+    rank, local_rank, world, dist = ctx["rank"], ctx["local_rank"], ctx["world"], ctx["dist"]
+    scenes = build_scenes(workload, rank, world)
+    cfg = workload_config(workload, world)
     dt = scenes[0].dt
     nb = sum(sc.n_dynamic() for sc in scenes)
     iterations = int(scenes[0].header["iterations"])
-
-    w = World(len(scenes), device=local_rank)
-    w.load_scenes(scenes)
-    settle = SETTLE.get(args.workload, 0)
-    w.step(dt, settle)          # untimed: let contacts form so the timed steps see the settled workload
-    sampler = ClockSampler(local_rank)
-    sampler.start()             # before the warm-up: nvidia-smi takes a moment to deliver its first sample
-    w.step(dt, max(3, args.warmup))
-    w.sync()
-    t_wait = time.time()
-    while sampler.proc and not sampler.rows and time.time() - t_wait < 2.0:
-        w.step(dt, 5)           # more untimed steps until the clock sampler delivers (keeps the GPU under load)
-        w.sync()
+    steps = args.steps
+    warm = max(3, args.warmup)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    w = World(len(scenes), device=local_rank)
+    w.load_scenes(scenes)
+    settle = SETTLE[workload]
+    w.step(dt, settle)          # untimed: let contacts form so the timed steps see the configured workload
+    sampler = None
+    if full:
+        sampler = ClockSampler(local_rank)
+        sampler.start()         # before the warm-up: nvidia-smi takes a moment to deliver its first sample
+    w.step(dt, warm)
+    w.sync()
+    if sampler is not None:
+        t_wait = time.time()
+        while sampler.proc and not sampler.rows and time.time() - t_wait < 2.0:
+            w.step(dt, 5)       # more untimed steps until the clock sampler delivers (keeps the GPU under load)
+            w.sync()
+
     launches0 = w.launch_count()
     barrier()
     t_wall0 = time.time()
-    ms = w.time_steps(dt, args.steps)
+    ms = w.time_steps(dt, steps)
     barrier()
-    clocks = sampler.stop(t_wall0, time.time())
+    clocks = sampler.stop(t_wall0, time.time()) if sampler is not None else None
     launches = w.launch_count() - launches0
     st = w.stats()
 
@@ -249,25 +337,14 @@ def run_ours(args):
 
     # the only inter-GPU traffic: timings (MAX) and step statistics (SUM / MAX) -- north star
     from chipmunk2d_b200.sharding import reduce_step_stats
-    sums, mx, t_ms_max = reduce_step_stats(dist, torch, "cuda", [float(nb), float(st["n_contacts"]), float(st["n_arbiters"]), float(st["n_pairs"]), st["kinetic_energy"]],
-                                           [st["max_penetration"]], ms)
+    sums, mx, t_ms_max = reduce_step_stats(dist, torch, "cuda", [float(nb), float(st["n_contacts"]), float(st["n_arbiters"]), float(st["n_pairs"]), st["kinetic_energy"],
+                                                                    float(st["n_awake"]), float(len(scenes))], [st["max_penetration"]], ms)
     t_max = t_ms_max * 1e-3
-    total_bodies, total_contacts, total_arbs, total_pairs, total_ke = sums
-    maxes = torch.tensor(mx, dtype=torch.float64)
+    total_bodies, total_contacts, total_arbs, total_pairs, total_ke, total_awake, total_spaces = sums
 
-    # ---- e2e: the same metric with HOST buffers every step, copies inside the timed region ----
-    # (1) `e2e`: through the C-ABI (include/cpb200.h) -- forces of every body in from a page-locked host array
-    #     (cpb200_world_set_body_forces), cpb200_world_step, the state of every body out into a page-locked host
-    #     array (cpb200_world_get_bodies, which waits for the step).  This is the call the reference-side binding
-    #     of INTEGRATION.md makes, and for the batched workload the only one there is (one cpSpace = one world).
-    # (2) `e2e_per_body_api` (single-space workloads): the same through the object API of include/chipmunk --
-    #     cpBodySetForce on every body, cpSpaceStep, cpBodyGetPosition on every body: 2 M serial host calls on
-    #     1 M heap objects per step, which the reference arm (cpSpaceStep alone) does not pay.  Reported beside it.
-    e2e = None
-    e2e_api = None
+    # ---- e2e through the C-ABI with HOST buffers every step, copies inside the timed region ----
     try:
-
-        k2 = max(1, min(args.steps, 10))
+        k2 = max(1, min(steps, 10))
         forces = w.pinned_array(w.n_bodies * 3, np.float64).reshape(-1, 3)   # page-locked host buffers
         forces[:] = 0.0
         states = w.pinned_array(w.n_bodies, BODY_STATE)
@@ -278,19 +355,21 @@ def run_ours(args):
         for _ in range(k2):
             w.set_body_forces(0, forces); w.step(dt); w.bodies_into(states)
         sec = time.perf_counter() - t0
-        n_api = w.n_bodies
         t_e = torch.tensor([sec], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        e2e = {"value": nb * world * k2 / float(t_e.item()), "unit": "body-steps/s", "steps": k2,
-               "h2d_bytes_per_step": int(n_api * 24), "d2h_bytes_per_step": int(n_api * BODY_STATE.itemsize),
+        e2e = {"value": total_bodies * k2 / float(t_e.item()), "unit": "body-steps/s", "steps": k2,
+               "h2d_bytes_per_step": int(w.n_bodies * 24), "d2h_bytes_per_step": int(w.n_bodies * BODY_STATE.itemsize),
                "ms_per_step": 1000.0 * float(t_e.item()) / k2,
                "path": "C-ABI with page-locked host arrays: cpb200_world_set_body_forces -> cpb200_world_step -> cpb200_world_get_bodies (all bodies, every step)"}
     except Exception as exc:  # keep the device-resident number even if something on the host path is missing
         e2e = {"value": None, "unit": "body-steps/s", "error": str(exc)}
-    if len(scenes) == 1:
+
+    e2e_api = None
+    if full and len(scenes) == 1:
         try:
-            k3 = max(1, min(args.steps, 5))
+            from chipmunk2d_b200.api import load_scene_lib, SceneSpace
+            k3 = max(1, min(steps, 5))
             api = SceneSpace(load_scene_lib(), scenes[0].blob)
             api.step(dt, settle)
             api.e2e_steps(dt, 2)
@@ -299,22 +378,29 @@ def run_ours(args):
             t_a = torch.tensor([sec], dtype=torch.float64, device="cuda")
             if dist is not None:
                 dist.all_reduce(t_a, op=dist.ReduceOp.MAX)
-            e2e_api = {"value": nb * world * k3 / float(t_a.item()), "unit": "body-steps/s", "steps": k3,
+            e2e_api = {"value": total_bodies * k3 / float(t_a.item()), "unit": "body-steps/s", "steps": k3,
                        "h2d_bytes_per_step": int(api.n_bodies * 24), "d2h_bytes_per_step": int(api.n_bodies * BODY_STATE.itemsize),
                        "ms_per_step": 1000.0 * float(t_a.item()) / k3,
                        "path": "cpBodySetForce on every body -> cpSpaceStep -> cpBodyGetPosition on every body (scene_io.c cpb_scene_e2e_steps)"}
             api.space = None
         except Exception as exc:
             e2e_api = {"value": None, "unit": "body-steps/s", "error": str(exc)}
+    w.close()
 
-    if dist is not None:
-        # every rank leaves the process group together, BEFORE rank 0 goes on to its CPU-only work
-        dist.barrier()
-        dist.destroy_process_group()
-        dist = None
-    if rank != 0:
-        return
+    rec = {"config": cfg, "value": total_bodies * steps / t_max, "unit": "body-steps/s", "steps": steps, "warmup": warm,
+           "ms_per_step": 1000.0 * t_max / steps,
+           "contacts_solved_per_sec": total_contacts * steps / t_max,
+           "contact_iterations_per_sec": total_contacts * iterations * steps / t_max,
+           "per_step": {"bodies": total_bodies, "spaces": total_spaces, "pairs": total_pairs, "arbiters": total_arbs, "contacts": total_contacts, "colours": st["n_colours"],
+                        "awake_bodies": total_awake, "max_penetration": float(mx[0]), "kinetic_energy": total_ke},
+           "gpu_launches": int(launches), "e2e": e2e, "stage_us": acc, "solver_us": sp}
+    if e2e_api is not None:
+        rec["e2e_per_body_api"] = e2e_api
+    rec["_local"] = {"iterations": iterations, "nb": nb, "st2": st2, "clocks": clocks, "ms_local": ms, "n_scenes": len(scenes)}
+    return rec
 
+
+def roofline_of(rec, workload):
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -323,48 +409,100 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    solve_us = acc.get("colour_solve", 0.0)
+    loc = rec["_local"]
+    st2, iterations, nb = loc["st2"], loc["iterations"], loc["nb"]
+    solve_us = rec["stage_us"].get("colour_solve", 0.0)
     alg = algorithmic_bytes_solver(st2["n_contacts"], st2["n_joints"], iterations)
     achieved = alg / (solve_us * 1e-6) / 1e9 if solve_us > 0 else 0.0
     traffic = None
+    dram_frac = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(args.workload)
+            traffic = json.load(f).get(workload)
     except Exception:
         pass
-    whole_step_alg = 264.0 * nb + 108.0 * nb + 32.0 * st2["n_shapes"] + (8.0 + 170.0) * st2["n_pairs"] + 64.0 * st2["n_arbiters"] + 400.0 * st2["n_contacts"] + 384.0 * iterations * st2["n_contacts"]
-    step_ms_dev = ms / args.steps
+    if traffic and solve_us > 0:
+        dram_frac = float(traffic) / (solve_us * 1e-6) / 1e9 / peak
+    whole = 264.0 * nb + 108.0 * nb + 32.0 * st2["n_shapes"] + (8.0 + 170.0) * st2["n_pairs"] + 64.0 * st2["n_arbiters"] + 400.0 * st2["n_contacts"] + 384.0 * iterations * st2["n_contacts"]
+    step_s = loc["ms_local"] / rec["steps"] * 1e-3
+    out = {"bound": "hbm", "kernel": "k_colour_solve (persistent colouring + warm start + %d Gauss-Seidel iterations)" % iterations,
+           "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+           "frac_on_dram_bytes": dram_frac,
+           "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg, "launch_us": solve_us,
+           "whole_step": {"algorithmic_bytes": whole, "achieved_gbs": whole / step_s / 1e9, "frac": whole / step_s / 1e9 / peak}}
+    if workload.startswith("batch"):
+        out["note"] = "batched small spaces are solved from shared memory / L2 (space-local solver): the algorithmic bytes never reach HBM, so this fraction can exceed 1 and is not a bound for this workload"
+    return out
 
+
+def run_ours(args):
+    rank, local_rank, world = rank_info()
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the step engine has no CPU fallback)")
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        dist = None
+    os.environ["CPB200_DEVICE"] = str(local_rank)   # spaces created through the C API follow the rank's GPU
+    # the host layer threads its mirror loops: share the host cores between the ranks of this node
+    os.environ.setdefault("CPB200_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, world))))
+    ctx = {"rank": rank, "local_rank": local_rank, "world": world, "dist": dist}
+
+    main = measure(args.workload, args, ctx, full=True)
+    subs = {}
+    if not args.no_sub:
+        for name in SUB_RECORDS:
+            if name == args.workload:
+                continue
+            try:
+                r = measure(name, args, ctx, full=False)
+                r.pop("_local", None)
+                r.pop("solver_us", None)
+                subs[name] = r
+            except Exception as exc:
+                subs[name] = {"error": str(exc)}
+
+    if dist is not None:
+        # every rank leaves the process group together, BEFORE rank 0 goes on to its CPU-only work
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    roof = roofline_of(main, args.workload)
     cpu = None
-    if world == 1 or rank == 0:
+    try:
+        cpu = cpu_baseline_sample(args.workload)
+    except Exception as exc:
+        cpu = {"value": None, "error": str(exc)}
+    if "mixed100k" in subs and "error" not in subs["mixed100k"] and not args.no_sub:
+        # the deepest contact of config 3 next to the reference's, same generator, same number of steps, 20 k bodies
         try:
-            cpu = cpu_baseline_sample(args.workload, 40, 10)
+            from chipmunk2d_b200.engine import World
+            sc = build_scenes("mixed100k", sample=CPU_SAMPLE_MIXED)[0]
+            wd = World(1, device=local_rank); wd.load_scene(sc); wd.step(sc.dt, SETTLE["mixed100k"] + 12); wd.sync()
+            rr = reference_run("mixed100k", 10, 2, SETTLE["mixed100k"], sample=CPU_SAMPLE_MIXED)
+            subs["mixed100k"]["penetration_check"] = {"bodies": CPU_SAMPLE_MIXED, "steps": SETTLE["mixed100k"] + 12, "device_max_penetration": wd.stats()["max_penetration"],
+                                                      "reference_max_penetration": (rr or {}).get("max_penetration"),
+                                                      "reference_body_steps_per_sec": (rr or {}).get("value")}
+            wd.close()
         except Exception as exc:
-            cpu = {"value": None, "error": str(exc)}
+            subs["mixed100k"]["penetration_check"] = {"error": str(exc)}
 
+    loc = main.pop("_local")
     line = {
-        "metric": "body_steps_per_sec", "value": total_bodies * args.steps / t_max, "unit": "body-steps/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": 1000.0 * t_max / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dict(cfg, parallelism=("replicas x%d (a single space does not shard)" % world if len(scenes) == 1 else "spaces sharded x%d, no data-path collective" % world),
-                       l2="inputs larger than L2 (solver rows + arbiter records >> 126 MB)" if nb >= 300000 else "working set fits L2; latency-bound configuration",
-                       settle_steps=settle),
-        "contacts_solved_per_sec": total_contacts * args.steps / t_max,
-        "contact_iterations_per_sec": total_contacts * iterations * args.steps / t_max,
-        "per_step": {"bodies": total_bodies, "pairs": total_pairs, "arbiters": total_arbs, "contacts": total_contacts, "colours": st["n_colours"],
-                     "max_penetration": float(maxes.item()), "kinetic_energy": total_ke},
-        "clocks": clocks,
-        "gpu_launches": int(launches),
-        "e2e": e2e,
-        "e2e_per_body_api": e2e_api,
-        "roofline": {"bound": "hbm", "kernel": "k_colour_solve (persistent colouring + warm start + %d Gauss-Seidel iterations)" % iterations,
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
-                     **({"note": "batched small spaces are solved from shared memory / L2 (space-local solver): the algorithmic bytes never reach HBM, so this fraction can exceed 1 and is not a bound for this workload"} if args.workload == "batch" else {}),
-                     "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg, "launch_us": solve_us,
-                     "whole_step": {"algorithmic_bytes": whole_step_alg, "achieved_gbs": whole_step_alg / (step_ms_dev * 1e-3) / 1e9,
-                                    "frac": whole_step_alg / (step_ms_dev * 1e-3) / 1e9 / peak}},
-        "stage_us": acc, "solver_us": sp,
-        "cpu_baseline": cpu,
+        "metric": "body_steps_per_sec", "value": main["value"], "unit": "body-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": main["warmup"], "ms_per_step": main["ms_per_step"],
+        "higher_is_better": True, "scaling": ("strong" if args.workload == "batch_sharded" else "weak"), "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": main["config"],
+        "contacts_solved_per_sec": main["contacts_solved_per_sec"], "contact_iterations_per_sec": main["contact_iterations_per_sec"],
+        "per_step": main["per_step"], "clocks": loc["clocks"], "gpu_launches": main["gpu_launches"],
+        "e2e": main["e2e"], "e2e_per_body_api": main.get("e2e_per_body_api"),
+        "roofline": roof, "stage_us": main["stage_us"], "solver_us": main["solver_us"],
+        "cpu_baseline": cpu, "sub_records": subs,
     }
     emit(line)
 
@@ -394,6 +532,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default=os.environ.get("CPB200_BENCH_WORKLOAD", "pile1m"))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-sub", action="store_true", default=(os.environ.get("CPB200_BENCH_SUB", "1") == "0"),
+                    help="skip the sub-records (the other BASELINE configs measured in the same run)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
