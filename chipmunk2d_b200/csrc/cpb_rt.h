@@ -57,6 +57,7 @@ static inline int4 make_int4(int x, int y, int z, int w){ int4 r = {x, y, z, w};
 typedef int cudaError_t;
 typedef void *cudaStream_t;
 typedef void *cudaEvent_t;
+typedef void *cudaGraphExec_t;
 #define cudaSuccess 0
 enum { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 static inline cudaError_t cudaMalloc(void **p, size_t n){ *p = calloc(1, n ? n : 1); return 0; }

@@ -194,7 +194,8 @@ struct DCounters {
 	int colour_rounds;
 	int n_overflow_colour;
 	int n_cached;
-	int pad[4];
+	uint32_t stamp;        // space->stamp (cpSpaceStep.c:349): advanced on the device by k_reset_step, so a captured step graph replays it
+	int pad[3];
 };
 
 #define CPB_MAX_COLOURS 64

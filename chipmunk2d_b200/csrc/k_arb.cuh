@@ -131,9 +131,10 @@ __global__ void __launch_bounds__(1024) k_table_small(DArbs cur, DTable T, DCoun
 #endif
 template <int CLS>
 __global__ void __launch_bounds__(128, (CLS == 2 ? CPB_COLLIDE_GJK_CTAS : 1)) k_collide(DShapes S, DBodies B, const int *__restrict__ pa, const int *__restrict__ pb, const int *__restrict__ pcount, int pcap,
-	DArbs prev, DTable prev_table, DArbs cur, uint32_t stamp, DCounters *C)
+	DArbs prev, DTable prev_table, DArbs cur, DCounters *C)
 {
 	int np = *pcount; if(np > pcap) np = pcap;
+	const uint32_t stamp = C->stamp;
 	const uint32_t pmask = *prev_table.dmask;
 	int my_active = 0, my_contacts = 0;     // step statistics: summed per thread, flushed once per warp after the loop
 	for(int base = blockIdx.x*blockDim.x; base < np; base += gridDim.x*blockDim.x){
@@ -277,9 +278,10 @@ __global__ void k_pack_warm(DArbs A)
 
 // cpSpaceArbiterSetFilter (cpSpaceStep.c:292-325) over the previous step's records that the
 // collision phase did not touch.
-__global__ void k_arb_carry(DBodies B, DArbs prev, DArbs cur, const DSpace *__restrict__ spaces, uint32_t stamp, DCounters *C)
+__global__ void k_arb_carry(DBodies B, DArbs prev, DArbs cur, const DSpace *__restrict__ spaces, DCounters *C)
 {
 	int n_prev = *prev.count_ptr; if(n_prev > prev.cap) n_prev = prev.cap;
+	const uint32_t stamp = C->stamp;
 	for(int base = blockIdx.x*blockDim.x; base < n_prev; base += gridDim.x*blockDim.x){
 		int i = base + threadIdx.x;
 		bool keep = false;

@@ -291,10 +291,27 @@ CPB_DEVICE void contact_apply_cached(double4 &Va, double4 &Vb, V2 mia, V2 mib, V
 	apply_impulses(Va, Vb, mia, mib, r1, r2, vmul(j, dt_coef));
 }
 
+// apply_impulse (chipmunk_private.h:185-189) that also reports whether any bit of the body's sector changed: the
+// solver skips the scatter of an untouched sector, and comparing each component as it is replaced costs no registers
+// (a before/after snapshot of the four sectors cost 24)
+CPB_DEVICE void apply_impulse_track(double4 &V, V2 mi, V2 j, V2 r, bool &changed){
+	const double x = V.x + j.x*mi.x, y = V.y + j.y*mi.x;
+	double z = V.z; z += mi.y*vcross(r, j);
+	changed = changed || __double_as_longlong(x) != __double_as_longlong(V.x) || __double_as_longlong(y) != __double_as_longlong(V.y) || __double_as_longlong(z) != __double_as_longlong(V.z);
+	V.x = x; V.y = y; V.z = z;
+}
+CPB_DEVICE void apply_impulses_track(double4 &Va, double4 &Vb, V2 mia, V2 mib, V2 r1, V2 r2, V2 j, bool &cha, bool &chb){
+	apply_impulse_track(Va, mia, vneg(j), r1, cha);
+	apply_impulse_track(Vb, mib, j, r2, chb);
+}
+
+// which of a row's four body sectors the solve changed
+struct RowDirty { bool va, vb, vba, vbb; };
+
 // cpArbiterApplyImpulse for one contact (cpArbiter.c:459-498)
 CPB_DEVICE void contact_apply(double4 &Va, double4 &Vb, double4 &VBa, double4 &VBb, V2 mia, V2 mib,
 	V2 n, V2 surface_vr, double friction, V2 r1, V2 r2, double nMass, double tMass, double bias, double bounce,
-	double &jnAcc, double &jtAcc, double &jBias)
+	double &jnAcc, double &jtAcc, double &jBias, RowDirty &dirty)
 {
 	V2 vb1 = vadd(v2(VBa.x, VBa.y), vmul(vperp(r1), VBa.z));
 	V2 vb2 = vadd(v2(VBb.x, VBb.y), vmul(vperp(r2), VBb.z));
@@ -317,8 +334,8 @@ CPB_DEVICE void contact_apply(double4 &Va, double4 &Vb, double4 &VBa, double4 &V
 	double jtOld = jtAcc;
 	jtAcc = fclamp_cp(jtOld + jt, -jtMax, jtMax);
 
-	apply_impulses(VBa, VBb, mia, mib, r1, r2, vmul(n, jBias - jbnOld));
-	apply_impulses(Va, Vb, mia, mib, r1, r2, vrotate(n, v2(jnAcc - jnOld, jtAcc - jtOld)));
+	apply_impulses_track(VBa, VBb, mia, mib, r1, r2, vmul(n, jBias - jbnOld), dirty.vba, dirty.vbb);
+	apply_impulses_track(Va, Vb, mia, mib, r1, r2, vrotate(n, v2(jnAcc - jnOld, jtAcc - jtOld)), dirty.va, dirty.vb);
 }
 
 // Body velocities are gathered/scattered once per colour phase and are written by other SMs in
@@ -399,11 +416,11 @@ template<bool STREAM> struct RowContact {
 		nmass = row_ld<STREAM>(&R.nmass[d]); tmass = row_ld<STREAM>(&R.tmass[d]); bias = row_ld<STREAM>(&R.bias[d]); bounce = row_ld<STREAM>(&R.bounce[d]);
 		jn = row_ld<STREAM>(&R.jn[d]); jt = row_ld<STREAM>(&R.jt[d]); jb = row_ld<STREAM>(&R.jb[d]);
 	}
-	CPB_MEMBER void solve(const DRows &R, int d, double4 &Va, double4 &Vb, double4 &VBa, double4 &VBb, V2 mia, V2 mib, V2 n, V2 svr, double u){
+	CPB_MEMBER void solve(const DRows &R, int d, double4 &Va, double4 &Vb, double4 &VBa, double4 &VBb, V2 mia, V2 mib, V2 n, V2 svr, double u, RowDirty &dirty){
 #ifndef CPB_NO_SKIP_SAME
 		const double jn0 = jn, jt0 = jt, jb0 = jb;
 #endif
-		contact_apply(Va, Vb, VBa, VBb, mia, mib, n, svr, u, r1, r2, nmass, tmass, bias, bounce, jn, jt, jb);
+		contact_apply(Va, Vb, VBa, VBb, mia, mib, n, svr, u, r1, r2, nmass, tmass, bias, bounce, jn, jt, jb, dirty);
 #ifndef CPB_NO_SKIP_SAME
 		if(!same_bits(jn, jn0)) row_st<STREAM>(&R.jn[d], jn);
 		if(!same_bits(jt, jt0)) row_st<STREAM>(&R.jt[d], jt);
@@ -440,19 +457,17 @@ template<class VS> CPB_DEVICE void solve_row_idx(const VS &vs, const DBodies &B,
 	bool dyn_a = (mia.x != 0.0 || mia.y != 0.0), dyn_b = (mib.x != 0.0 || mib.y != 0.0);
 	V2 svr = row_ld<VS::STREAM>(&R.svr[r]);
 	double u = row_ld<VS::STREAM>(&R.u[r]);
-#ifndef CPB_NO_SKIP_SAME
 	// A contact that does not push this iteration (clamped impulses) leaves both bodies exactly as they
 	// were: skip the scatter then.  Bitwise comparison, so the stored state is identical either way.
-	const double4 Va0 = Va, Vb0 = Vb, VBa0 = VBa, VBb0 = VBb;
-#endif
+	RowDirty dirty = {false, false, false, false};
 	for(int k = 0; k < cnt; k++){
 		RowContact<VS::STREAM> c;
 		c.load(R, k*R.cap + r);
-		c.solve(R, k*R.cap + r, Va, Vb, VBa, VBb, mia, mib, n, svr, u);
+		c.solve(R, k*R.cap + r, Va, Vb, VBa, VBb, mia, mib, n, svr, u, dirty);
 	}
 #ifndef CPB_NO_SKIP_SAME
-	if(dyn_a){ if(!same_bits3(Va, Va0)) vs.stV(ba, Va); if(!same_bits3(VBa, VBa0)) vs.stVB(ba, VBa); }
-	if(dyn_b){ if(!same_bits3(Vb, Vb0)) vs.stV(bb, Vb); if(!same_bits3(VBb, VBb0)) vs.stVB(bb, VBb); }
+	if(dyn_a){ if(dirty.va) vs.stV(ba, Va); if(dirty.vba) vs.stVB(ba, VBa); }
+	if(dyn_b){ if(dirty.vb) vs.stV(bb, Vb); if(dirty.vbb) vs.stVB(bb, VBb); }
 #else
 	if(dyn_a){ vs.stV(ba, Va); vs.stVB(ba, VBa); }
 	if(dyn_b){ vs.stV(bb, Vb); vs.stVB(bb, VBb); }
@@ -489,9 +504,10 @@ CPB_DEVICE void solve_colour(const DBodies &B, const DRows &R, const DJoints &J,
 }
 
 // overflow bucket: sequential, one thread
-CPB_DEVICE void solve_overflow(const DBodies &B, const DRows &R, const DJoints &J, const DColour &K, int mode, double dt, double dt_coef){
+template<bool JOINTS> CPB_DEVICE void solve_overflow(const DBodies &B, const DRows &R, const DJoints &J, const DColour &K, int mode, double dt, double dt_coef){
 	int r0 = K.cstart[CPB_OVERFLOW_COLOUR], r1 = K.cstart[CPB_OVERFLOW_COLOUR + 1];
 	for(int r = r0; r < r1; r++) solve_row(B, R, r, mode, dt_coef);
+	if(!JOINTS) return;
 	int j0 = K.jstart[CPB_OVERFLOW_COLOUR], j1 = K.jstart[CPB_OVERFLOW_COLOUR + 1];
 	for(int q = j0; q < j1; q++) solve_joint(B, J, J.row[q], mode, dt, dt_coef);
 }
@@ -537,14 +553,15 @@ CPB_DEVICE void solve_row_packed(const VelShared &vs, const DRows &R, int r, int
 	}
 	const V2 svr = v2(nsv.z, nsv.w);
 	const double u = impa.w;
+	RowDirty dirty = {false, false, false, false};
 	{
 		double jn = impa.x, jt = impa.y, jb = impa.z;
-		contact_apply(Va, Vb, VBa, VBb, mia, mib, n, svr, u, v2(r12a.x, r12a.y), v2(r12a.z, r12a.w), massa.x, massa.y, massa.z, massa.w, jn, jt, jb);
+		contact_apply(Va, Vb, VBa, VBb, mia, mib, n, svr, u, v2(r12a.x, r12a.y), v2(r12a.z, r12a.w), massa.x, massa.y, massa.z, massa.w, jn, jt, jb, dirty);
 		if(!(same_bits(jn, impa.x) && same_bits(jt, impa.y) && same_bits(jb, impa.z))) st4_wb(&R.imp[r], make_double4(jn, jt, jb, impa.w));
 	}
 	if(cnt == 2){
 		double jn = impb.x, jt = impb.y, jb = impb.z;
-		contact_apply(Va, Vb, VBa, VBb, mia, mib, n, svr, u, v2(r12b.x, r12b.y), v2(r12b.z, r12b.w), massb.x, massb.y, massb.z, massb.w, jn, jt, jb);
+		contact_apply(Va, Vb, VBa, VBb, mia, mib, n, svr, u, v2(r12b.x, r12b.y), v2(r12b.z, r12b.w), massb.x, massb.y, massb.z, massb.w, jn, jt, jb, dirty);
 		if(!(same_bits(jn, impb.x) && same_bits(jt, impb.y) && same_bits(jb, impb.z))) st4_wb(&R.imp[R.cap + r], make_double4(jn, jt, jb, impb.w));
 	}
 	if(dyn_a){ vs.stV(ba, Va); vs.stVB(ba, VBa); }
@@ -712,12 +729,19 @@ __device__ __forceinline__ unsigned long long global_ns(){ unsigned long long t;
 #endif
 
 // SPACE_LOCAL: colour only, then histogram the (space, colour) buckets for the space-local solver below.
-template<bool SPACE_LOCAL, bool STREAM_ROWS> __global__ void __launch_bounds__(256, CPB_SOLVE_MIN_BLOCKS) k_colour_solve(DBodies B, DArbs A, DJoints J, DRows R, DColour K, DCounters *C, unsigned *bar, DSpaceLocal SL, int use_hints, int iterations, double dt, double dt_coef)
+// JOINTS = false: instantiation for worlds without constraints (the ten joint classes cost ~20 registers of the
+// iteration loop's budget; a pile of circles never needs them).
+// PHASE 1 = colouring + row build, PHASE 2 = warm start + iterations + write-back: two launches, because the register
+// allocation of a kernel is the maximum over its phases -- the row build holds a whole arbiter record in registers
+// (gather, then scatter) and would cap the occupancy of the iteration loop, which is the part that needs warps to
+// hide its gathers.  (PHASE 0 = both in one launch, kept for comparison.)
+template<bool SPACE_LOCAL, bool STREAM_ROWS, bool JOINTS, int PHASE, int MINB> __global__ void __launch_bounds__(256, MINB) k_colour_solve(DBodies B, DArbs A, DJoints J, DRows R, DColour K, DCounters *C, unsigned *bar, DSpaceLocal SL, int use_hints, int iterations, double dt, double dt_coef)
 {
 	__shared__ int s_hist[2*CPB_MAX_COLOURS];
 	__shared__ int s_base[CPB_MAX_COLOURS];
 	const int tid = CPB_TID, nth = CPB_NTHREADS;
 	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
+	if(PHASE != 2){
 	if(threadIdx.x < 2*CPB_MAX_COLOURS) s_hist[threadIdx.x] = 0;
 	__syncthreads();
 	// flush this CTA's colour histogram (arbiters | joints) into the global one
@@ -754,8 +778,10 @@ template<bool SPACE_LOCAL, bool STREAM_ROWS> __global__ void __launch_bounds__(2
 	}
 	GRID_SYNC();
 	build_rows(A, J, R, K, s_hist, s_base, nA, tid, nth);
+	if(PHASE == 1){ __syncthreads(); PROF(2); return; }
 	GRID_SYNC();
 	PROF(2);
+	}
 
 	// K11: warm start then iterations, colour by colour.  A thread's rows of a colour are r0 + tid + k*nth and
 	// its joints q0 + (nth-1-tid) + k*nth (from the other end of the grid, so that in small colours a thread
@@ -773,7 +799,7 @@ template<bool SPACE_LOCAL, bool STREAM_ROWS> __global__ void __launch_bounds__(2
 	int pq = -1, pj = 0, pja = 0, pjb = 0;       // prefetched joint
 	#define PREFETCH_PHASE(c_) do { \
 		pr = s_cstart[c_] + tid; if(pr < s_cstart[(c_) + 1]){ pba = row_ld<STREAM_ROWS>(&R.ba[pr]); pbb = row_ld<STREAM_ROWS>(&R.bb[pr]); pcnt = row_ld<STREAM_ROWS>(&R.cnt[pr]); row_prefetch(R, pr); } else pr = -1; \
-		pq = s_jstart[c_] + jtid; if(pq < s_jstart[(c_) + 1]){ pj = J.row[pq]; pja = J.a[pj]; pjb = J.b[pj]; } else pq = -1; } while(0)
+		pq = s_jstart[c_] + jtid; if(JOINTS && pq < s_jstart[(c_) + 1]){ pj = J.row[pq]; pja = J.a[pj]; pjb = J.b[pj]; } else pq = -1; } while(0)
 	if(nreg > 0) PREFETCH_PHASE(0);
 	for(int pass = 0; pass <= iterations; pass++){
 		int mode = (pass == 0 ? 0 : 1);
@@ -785,7 +811,7 @@ template<bool SPACE_LOCAL, bool STREAM_ROWS> __global__ void __launch_bounds__(2
 				if(pr < r1){ pba = row_ld<STREAM_ROWS>(&R.ba[pr]); pbb = row_ld<STREAM_ROWS>(&R.bb[pr]); pcnt = row_ld<STREAM_ROWS>(&R.cnt[pr]); row_prefetch(R, pr); } else pr = -1;
 				solve_row_idx(vg, B, R, r, ba, bb, cnt, mode, dt_coef);
 			}
-			while(pq >= 0){
+			while(JOINTS && pq >= 0){
 				int j = pj, a = pja, b = pjb;
 				pq += nth;
 				if(pq < j1){ pj = J.row[pq]; pja = J.a[pj]; pjb = J.b[pj]; } else pq = -1;
@@ -796,7 +822,7 @@ template<bool SPACE_LOCAL, bool STREAM_ROWS> __global__ void __launch_bounds__(2
 			GRID_SYNC();
 		}
 		if(has_overflow){
-			if(tid == 0) solve_overflow(B, R, J, K, mode, dt, dt_coef);
+			if(tid == 0) solve_overflow<JOINTS>(B, R, J, K, mode, dt, dt_coef);
 			GRID_SYNC();
 		}
 		if(pass == 0) PROF(3);
@@ -828,7 +854,7 @@ __global__ void k_colour_finish(DArbs A, DJoints J, DRows R, DColour K, DCounter
 	else build_rows(A, J, R, K, (int *)NULL, (int *)NULL, nA, CPB_TID, CPB_NTHREADS);
 }
 __global__ void k_solve_colour(DBodies B, DRows R, DJoints J, DColour K, int colour, int mode, double dt, double dt_coef){
-	if(colour == CPB_OVERFLOW_COLOUR){ if(CPB_TID == 0) solve_overflow(B, R, J, K, mode, dt, dt_coef); }
+	if(colour == CPB_OVERFLOW_COLOUR){ if(CPB_TID == 0) solve_overflow<true>(B, R, J, K, mode, dt, dt_coef); }
 	else solve_colour(B, R, J, K, colour, mode, dt, dt_coef, CPB_TID, CPB_NTHREADS);
 }
 __global__ void k_rows_writeback(DArbs A, DRows R, DColour K){
@@ -856,11 +882,12 @@ __global__ void k_solve_serial(DBodies B, DArbs A, DJoints J, const int *__restr
 			double4 Va = B.V[ba], Vb = B.V[bb], VBa = B.VB[ba], VBb = B.VB[bb];
 			V2 n = A.n[i];
 			int cnt = A.cnt[i];
+			RowDirty dirty = {false, false, false, false};
 			for(int kk = 0; kk < cnt; kk++){
 				int k = (reversed ? cnt - 1 - kk : kk);
 				int s = CIDX(A, i, k);
 				if(pass == 0) contact_apply_cached(Va, Vb, mia, mib, n, A.r1[s], A.r2[s], A.jn[s], A.jt[s], dt_coef);
-				else contact_apply(Va, Vb, VBa, VBb, mia, mib, n, A.svr[i], A.u[i], A.r1[s], A.r2[s], A.nmass[s], A.tmass[s], A.bias[s], A.bounce[s], A.jn[s], A.jt[s], A.jb[s]);
+				else contact_apply(Va, Vb, VBa, VBb, mia, mib, n, A.svr[i], A.u[i], A.r1[s], A.r2[s], A.nmass[s], A.tmass[s], A.bias[s], A.bounce[s], A.jn[s], A.jt[s], A.jb[s], dirty);
 			}
 			if(mia.x != 0.0 || mia.y != 0.0){ B.V[ba] = Va; B.VB[ba] = VBa; }
 			if(mib.x != 0.0 || mib.y != 0.0){ B.V[bb] = Vb; B.VB[bb] = VBb; }

@@ -100,7 +100,8 @@ struct cpb200_world {
 	cudaStream_t stream;
 	int n_spaces;
 	int sm_count;
-	int coop_blocks;
+	int coop_blocks;        // co-resident CTAs of the colouring kernel
+	int solve_minb;         // resident CTAs per SM the iteration kernel is compiled for (2: 128 registers, 3: 80 registers)
 
 	std::vector<cpb200_space_params> sp;
 	DSpace *d_spaces;
@@ -148,6 +149,14 @@ struct cpb200_world {
 	bool mid_solve;         // validation hook: between cpb200_world_step_presolve and cpb200_world_step_finish
 	int solver_variant;     // validation hook: 0 automatic, 1 world-wide + cached rows, 2 world-wide + streamed rows, 3 space-local
 	int last_solver_path;   // what the last step ran: 0 serial, 1 world-wide coloured, 2 space-local
+	// A step whose launch sequence is fixed (no collision handlers, no profiling, same dt, same buffers) is captured once
+	// into a CUDA graph per arbiter-buffer parity and replayed with one launch: a 1000-body scene is ~35 kernels of a few
+	// microseconds each, and their launch gaps were most of its step time.  Every counter a kernel needs lives on the device.
+	struct StepGraph { cudaGraphExec_t exec; unsigned long long sig; int launches; int solver_path; } graph[2];
+	unsigned long long graph_gen;       // bumped by every upload / setting that can change the launch sequence
+	unsigned long long graph_last_sig;  // signature of the previous step (a graph is captured when it repeats)
+	bool graph_enabled;
+	unsigned long long graph_replays, graph_captures;
 	double step_dt, step_dt_coef; int step_iterations;
 	bool hints_valid;       // last step's colours may seed this step's colouring
 	bool no_hints;          // validation hook (env CPB200_NO_HINTS): colour from scratch every step
@@ -247,16 +256,17 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	cudaStreamCreate(&w->stream2);
 	cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming);
 	w->sm_count = 148;
-	w->coop_blocks = 148;
+	w->coop_blocks = 148; w->solve_minb = 2;
 #ifndef CPB_EMU
 	{
 		cudaDeviceProp prop;
 		if(cudaGetDeviceProperties(&prop, device) == cudaSuccess) w->sm_count = prop.multiProcessorCount;
 		int per_sm = 1;
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colour_solve<false, true>, 256, 0);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colour_solve<false, true, true, 1, 2>, 256, 0);
 		if(per_sm < 1) per_sm = 1;
 		if(per_sm > 4) per_sm = 4;
 		w->coop_blocks = w->sm_count*per_sm;
+		{ const char *e = getenv("CPB200_SOLVE_MINB"); w->solve_minb = (e && atoi(e) == 3 ? 3 : 2); }
 		cudaFuncSetAttribute(k_sl_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CPB_SL_MAX_SMEM);
 		cudaFuncSetAttribute(k_sl_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CPB_SL_MAX_SMEM);
 		cudaFuncSetAttribute(k_sl_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, CPB_SL_MAX_SHAPES*(int)(sizeof(double4) + sizeof(int)));
@@ -289,6 +299,8 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	w->no_hints = (getenv("CPB200_NO_HINTS") != NULL);
 	w->d_query = NULL; w->query_bytes = 0;
 	w->mid_solve = false; w->solver_variant = 0; w->last_solver_path = 0;
+	memset(w->graph, 0, sizeof(w->graph)); w->graph_gen = 1; w->graph_last_sig = 0; w->graph_replays = w->graph_captures = 0;
+	w->graph_enabled = (getenv("CPB200_NO_GRAPH") == NULL);
 	w->mid_step = false; w->step_dt = 0.0; w->step_dt_coef = 0.0; w->step_iterations = 0;
 	w->sl_dirty = true; w->sl_ok = false; w->sl_disabled = (getenv("CPB200_NO_SPACE_LOCAL") != NULL); w->sl_max_nbody = 0;
 	memset(&w->SL, 0, sizeof(w->SL)); w->sl_tmp = NULL;
@@ -306,6 +318,9 @@ extern "C" void cpb200_world_destroy(cpb200_world *w)
 	if(!w) return;
 	cudaSetDevice(w->device);
 	cudaStreamSynchronize(w->stream);
+#ifndef CPB_EMU
+	for(int k = 0; k < 2; k++) if(w->graph[k].exec) cudaGraphExecDestroy(w->graph[k].exec);
+#endif
 	w->gB.release(); w->gS.release(); w->gJ.release(); w->gA.release(); w->gK.release(); w->gV.release(); w->gP.release(); w->gI.release(); w->gW.release();
 	cudaFree(w->d_barrier);
 	if(w->d_stage) cudaFree(w->d_stage);
@@ -787,6 +802,7 @@ __global__ void k_reset_step(DCounters *C, int *pair_count, int *cur_count, int 
 		for(int k = CPB_TID; k < CPB_MAX_COLOUR_ROUNDS + 2; k += CPB_NTHREADS) wl_n[k] = 0;
 	}
 	if(CPB_TID != 0) return;
+	C->stamp++;            // cpSpaceStep.c:349
 	C->n_pairs[0] = C->n_pairs[1] = C->n_pairs[2] = 0;
 	C->n_contacts = 0; C->n_active = 0; C->n_colours = 0; C->n_cached = 0;
 	C->colour_remaining[0] = C->colour_remaining[1] = 0; C->colour_rounds = 0; C->n_overflow_colour = 0;
@@ -983,9 +999,9 @@ static int step_phase_a(cpb200_world *w, double dt)
 	{
 		int g = std::min(grid_for(w->P.cap, 128), w->sm_count*CPB_COLLIDE_CTAS);
 		LAUNCH(k_pack_warm, std::min(grid_for(Ap.cap, 256), wide), 256, st, Ap);
-		LAUNCH(k_collide<0>, g, 128, st, S, B, (const int *)w->P.a[0], (const int *)w->P.b[0], (const int *)&w->P.count[0], w->P.cap, Ap, Tp, Ac, w->stamp, w->C);
-		LAUNCH(k_collide<1>, g, 128, st, S, B, (const int *)w->P.a[1], (const int *)w->P.b[1], (const int *)&w->P.count[1], w->P.cap, Ap, Tp, Ac, w->stamp, w->C);
-		LAUNCH(k_collide<2>, g, 128, st, S, B, (const int *)w->P.a[2], (const int *)w->P.b[2], (const int *)&w->P.count[2], w->P.cap, Ap, Tp, Ac, w->stamp, w->C);
+		LAUNCH(k_collide<0>, g, 128, st, S, B, (const int *)w->P.a[0], (const int *)w->P.b[0], (const int *)&w->P.count[0], w->P.cap, Ap, Tp, Ac, w->C);
+		LAUNCH(k_collide<1>, g, 128, st, S, B, (const int *)w->P.a[1], (const int *)w->P.b[1], (const int *)&w->P.count[1], w->P.cap, Ap, Tp, Ac, w->C);
+		LAUNCH(k_collide<2>, g, 128, st, S, B, (const int *)w->P.a[2], (const int *)w->P.b[2], (const int *)&w->P.count[2], w->P.cap, Ap, Tp, Ac, w->C);
 	}
 	STAGE_END(w, ST_COLLIDE);
 	w->step_dt = dt; w->step_dt_coef = dt_coef; w->step_iterations = iterations;
@@ -1018,7 +1034,7 @@ static int step_phase_b1(cpb200_world *w)
 
 	{
 		int g = std::min(grid_for(Ap.cap, CPB_CARRY_BLOCK), w->sm_count*CPB_CARRY_CTAS);
-		LAUNCH(k_arb_carry, g, CPB_CARRY_BLOCK, st, B, Ap, Ac, (const DSpace *)w->d_spaces, w->stamp, w->C);
+		LAUNCH(k_arb_carry, g, CPB_CARRY_BLOCK, st, B, Ap, Ac, (const DSpace *)w->d_spaces, w->C);
 		// the table of this step's records (next step's warm-start lookups), sized to what the step produced
 #ifndef CPB_EMU
 		if(Ac.cap <= 65536) LAUNCH(k_table_small, 1, 1024, st, Ac, Tc, w->C);
@@ -1050,6 +1066,36 @@ static int step_phase_b(cpb200_world *w)
 {
 	if(step_phase_b1(w)) return -1;
 	return step_phase_b2(w);
+}
+
+// How the coloured solver is launched this step: grid of the persistent kernel, kernel family, CTA width of the
+// space-local solver.  Depends on host-side estimates only, so the step-graph signature can include it.
+struct SolvePlan { int blocks, iter_blocks; bool space_local, stream_rows; int threads; };
+static SolvePlan plan_solver(cpb200_world *w)
+{
+	SolvePlan p;
+	const int nb = w->B.n;
+	// size the persistent grid to the work: ~256 rows of one colour per CTA, never more than
+	// what is co-resident (148 SMs x 2 CTAs of 256 threads)
+	int est_cons = std::max(w->last_active, nb) + w->J.n;
+	p.blocks = std::max(1, std::min(w->coop_blocks, cpb_div_up(est_cons + 1, 256)));
+	if(est_cons <= 4096) p.blocks = 1;   // small scenes: one CTA, colours separated by __syncthreads only
+	p.iter_blocks = std::max(1, std::min(w->sm_count*(w->solve_minb == 3 ? 3 : 2), cpb_div_up(est_cons + 1, 256)));
+	if(est_cons <= 4096) p.iter_blocks = 1;
+	if(w->force_blocks > 0){ p.blocks = std::min(w->coop_blocks, w->force_blocks); p.iter_blocks = std::min(w->sm_count*2, w->force_blocks); }
+	// Space-local path: worlds whose spaces are each a small contiguous body range (batched demo
+	// spaces, or one small scene).  A forced grid (validation hook) keeps the world-wide solver.
+	p.space_local = w->sl_ok && w->force_blocks == 0 && est_cons/w->n_spaces <= 4096;
+	if(w->solver_variant == 1 || w->solver_variant == 2) p.space_local = false;
+	if(w->solver_variant == 3) p.space_local = true;
+	// rows + velocity sectors of one pass: stream the rows past the L2 only if they would not fit next to the velocities
+	p.stream_rows = ((size_t)est_cons*(size_t)CPB_ROW_BYTES_EST + (size_t)nb*64 > (size_t)CPB_L2_RESIDENT_BYTES);
+	if(w->solver_variant == 1) p.stream_rows = false;
+	if(w->solver_variant == 2) p.stream_rows = true;
+	// CTA width of k_sl_solve: about one row per thread in an average colour, a warp at least
+	int per_space = est_cons/w->n_spaces;
+	p.threads = 32; while(p.threads < 256 && p.threads*8 < per_space) p.threads *= 2;
+	return p;
 }
 
 // K10 + K11 and the end of the step
@@ -1089,42 +1135,38 @@ static int step_phase_b2(cpb200_world *w)
 #ifndef CPB_EMU
 		{
 			DCounters *C = w->C; DRows R = w->R; unsigned *bar = w->d_barrier;
-			// size the persistent grid to the work: ~256 rows of one colour per CTA, never more than
-			// what is co-resident (148 SMs x 2 CTAs of 256 threads)
-			int est_cons = std::max(w->last_active, nb) + J.n;
-			int blocks = std::max(1, std::min(w->coop_blocks, cpb_div_up(est_cons + 1, 256)));
-			if(est_cons <= 4096) blocks = 1;   // small scenes: one CTA, colours separated by __syncthreads only
-			if(w->force_blocks > 0) blocks = std::min(w->coop_blocks, w->force_blocks);
-			// Space-local path: worlds whose spaces are each a small contiguous body range (batched demo
-			// spaces, or one small scene).  A forced grid (validation hook) keeps the world-wide solver.
 			if(w->sl_dirty && sl_refresh(w)) return -1;
-			bool space_local = w->sl_ok && w->force_blocks == 0 && est_cons/w->n_spaces <= 4096;
-			if(w->solver_variant == 1 || w->solver_variant == 2) space_local = false;
-			if(w->solver_variant == 3){
-				if(!w->sl_ok){ cpb_set_error("solver variant 3 (space-local) needs every space to own one contiguous body range that fits a CTA's shared memory"); return -1; }
-				space_local = true;
-			}
+			if(w->solver_variant == 3 && !w->sl_ok){ cpb_set_error("solver variant 3 (space-local) needs every space to own one contiguous body range that fits a CTA's shared memory"); return -1; }
+			const SolvePlan plan = plan_solver(w);
+			const int blocks = plan.blocks;
+			const bool space_local = plan.space_local, stream_rows = plan.stream_rows;
 			w->last_solver_path = (space_local ? 2 : 1);
 			DSpaceLocal SL = w->SL;
 			if(!space_local) SL.start = NULL;
 			size_t nbuckets = 2*(size_t)w->n_spaces*CPB_MAX_COLOURS + 2;
 			if(space_local) cudaMemsetAsync(SL.start, 0, sizeof(uint32_t)*nbuckets, st);
 			void *args[] = {&B, &Ac, &J, &R, &K, &C, &bar, &SL, &use_hints, &iterations, &dt, &dt_coef};
-			// rows + velocity sectors of one pass: stream the rows past the L2 only if they would not fit next to the velocities
-			bool stream_rows = ((size_t)est_cons*(size_t)CPB_ROW_BYTES_EST + (size_t)nb*64 > (size_t)CPB_L2_RESIDENT_BYTES);
-			if(w->solver_variant == 1) stream_rows = false;
-			if(w->solver_variant == 2) stream_rows = true;
-			void *kernel = space_local ? (void *)k_colour_solve<true, true>
-			             : stream_rows ? (void *)k_colour_solve<false, true> : (void *)k_colour_solve<false, false>;
-			CPB_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(blocks), dim3(256), args, 0, st));
+			const bool joints = (J.n > 0);
+			// colouring (+ row build) and the iteration loop are separate cooperative launches: each gets its own register budget
+			void *k_colour = space_local ? (void *)k_colour_solve<true, true, true, 1, 2> : (void *)k_colour_solve<false, true, true, 1, 2>;
+			CPB_CHECK(cudaLaunchCooperativeKernel(k_colour, dim3(blocks), dim3(256), args, 0, st));
 			g_cpb_launches++;
+			if(!space_local){
+				const int m3 = (w->solve_minb == 3 ? 1 : 0);
+				static void *const k_iterate[2][2][2] = {   // [stream_rows][joints][min blocks 2 | 3]
+					{{(void *)k_colour_solve<false, false, false, 2, 2>, (void *)k_colour_solve<false, false, false, 2, 3>},
+					 {(void *)k_colour_solve<false, false, true, 2, 2>, (void *)k_colour_solve<false, false, true, 2, 3>}},
+					{{(void *)k_colour_solve<false, true, false, 2, 2>, (void *)k_colour_solve<false, true, false, 2, 3>},
+					 {(void *)k_colour_solve<false, true, true, 2, 2>, (void *)k_colour_solve<false, true, true, 2, 3>}}};
+				const int iter_blocks = std::min(plan.iter_blocks, w->sm_count*(m3 ? 3 : 2));
+				CPB_CHECK(cudaLaunchCooperativeKernel(k_iterate[stream_rows ? 1 : 0][joints ? 1 : 0][m3], dim3(iter_blocks), dim3(256), args, 0, st));
+				g_cpb_launches++;
+			}
 			if(space_local){
 				cpb_exclusive_scan(SL.start, SL.start, (int)nbuckets, w->sl_tmp, st);
 				int g = std::min(grid_for(Ac.cap + J.n, 256), wide);
 				LAUNCH(k_sl_rows, g, 256, st, B, Ac, J, R, SL);
-				// CTA width: about one row per thread in an average colour, a warp at least
-				int per_space = est_cons/w->n_spaces;
-				int threads = 32; while(threads < 256 && threads*8 < per_space) threads *= 2;
+				const int threads = plan.threads;
 				size_t smem = (size_t)w->sl_max_nbody*64;
 				const bool fork = (w->n_sl_plain > 0 && w->n_sl_jointed > 0);
 				cudaStream_t sj = (fork ? w->stream2 : st);
@@ -1170,13 +1212,132 @@ static int step_phase_b2(cpb200_world *w)
 	return 0;
 }
 
+#ifndef CPB_EMU
+// ---- the step as a CUDA graph ----
+static unsigned long long sig_mix(unsigned long long h, unsigned long long v){ h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); return h*0x100000001b3ull; }
+static unsigned long long sig_ptr(unsigned long long h, const void *p){ return sig_mix(h, (unsigned long long)(uintptr_t)p); }
+
+// Everything the launch sequence of a production step depends on: buffer addresses and sizes (kernel arguments are
+// captured by value), dt and the iteration count, and the launch plan of the solver.
+static unsigned long long step_signature(cpb200_world *w, double dt, int iterations, const SolvePlan &plan)
+{
+	unsigned long long h = 0xcbf29ce484222325ull, d;
+	memcpy(&d, &dt, 8);
+	h = sig_mix(h, d); h = sig_mix(h, (unsigned long long)iterations);
+	h = sig_mix(h, (unsigned long long)w->B.n); h = sig_mix(h, (unsigned long long)w->S.n); h = sig_mix(h, (unsigned long long)w->S.nv); h = sig_mix(h, (unsigned long long)w->J.n);
+	h = sig_mix(h, (unsigned long long)w->cap_arbs); h = sig_mix(h, (unsigned long long)w->cap_pairs); h = sig_mix(h, (unsigned long long)w->n_spaces);
+	h = sig_ptr(h, w->B.pos); h = sig_ptr(h, w->S.type); h = sig_ptr(h, w->J.type); h = sig_ptr(h, w->A[0].key); h = sig_ptr(h, w->P.cand);
+	h = sig_ptr(h, w->bvh.keys); h = sig_ptr(h, w->keys_b); h = sig_ptr(h, w->K.wl[0]); h = sig_ptr(h, w->d_nocollide); h = sig_ptr(h, w->SL.start); h = sig_ptr(h, w->I.parent);
+	h = sig_mix(h, (unsigned long long)w->n_nocollide);
+	h = sig_mix(h, (unsigned long long)((w->hints_valid && !w->no_hints) ? 1 : 0));
+	h = sig_mix(h, (unsigned long long)(w->any_sleep_enabled ? 1 : 0));
+	h = sig_mix(h, (unsigned long long)plan.iter_blocks);
+	h = sig_mix(h, (unsigned long long)plan.blocks); h = sig_mix(h, (unsigned long long)((plan.space_local ? 1 : 0) | (plan.stream_rows ? 2 : 0))); h = sig_mix(h, (unsigned long long)plan.threads);
+	h = sig_mix(h, (unsigned long long)w->sl_max_nbody); h = sig_mix(h, (unsigned long long)w->sl_max_nshape); h = sig_mix(h, (unsigned long long)((w->sl_shapes_ok ? 1 : 0) | (w->sl_ok ? 2 : 0)));
+	h = sig_mix(h, (unsigned long long)w->n_sl_plain); h = sig_mix(h, (unsigned long long)w->n_sl_jointed);
+	return h ? h : 1ull;
+}
+
+// host-side effects of step_phase_a + step_phase_b, for a replayed graph
+static void step_bookkeeping(cpb200_world *w, double dt, int iterations, int solver_path, int launches)
+{
+	w->stamp++;
+	w->curr_dt = dt;
+	w->cur ^= 1;
+	w->step_dt = dt; w->step_dt_coef = 1.0; w->step_iterations = iterations;
+	w->mid_step = false; w->mid_solve = false;
+	w->hints_valid = true;
+	w->last_solver_path = solver_path;
+	w->steps++;
+	g_cpb_launches += (unsigned long long)launches;
+}
+
+static int step_graphed(cpb200_world *w, double dt)
+{
+	cudaSetDevice(w->device);
+	cudaStream_t st = w->stream;
+	int iterations = 0;
+	for(int i = 0; i < w->n_spaces; i++) iterations = std::max(iterations, w->sp[(size_t)i].iterations);
+	// A step qualifies when nothing on the host side has to happen inside it: same dt as the last step (dt_coef = 1, the
+	// per-space and per-joint pow() terms are current), caches and layouts current, scratch buffers large enough.
+	bool steady = (w->cap_arbs > 0 && !w->cache_dirty && w->curr_dt == dt && !w->spaces_dirty && w->spaces_dt == dt &&
+	               (w->J.n == 0 || w->joints_dt == dt) && !w->sl_dirty && w->wl_cap >= w->A[0].cap + w->J.n + 64 &&
+	               !(w->solver_variant == 3 && !w->sl_ok) && w->B.n > 0);
+	if(!steady){
+		w->graph_last_sig = 0;
+		if(step_phase_a(w, dt)) return -1;
+		return step_phase_b(w);
+	}
+	const SolvePlan plan = plan_solver(w);
+	const unsigned long long sig = step_signature(w, dt, iterations, plan);
+	cpb200_world::StepGraph &G = w->graph[w->cur & 1];
+	if(G.exec && G.sig == sig){
+		step_bookkeeping(w, dt, iterations, G.solver_path, G.launches);
+		CPB_CHECK(cudaGraphLaunch(G.exec, st));
+		w->graph_replays++;
+		return 0;
+	}
+	if(w->graph_last_sig != sig){
+		// first step with this signature: run it as it is; if the next one looks the same it is captured
+		w->graph_last_sig = sig;
+		if(step_phase_a(w, dt)) return -1;
+		return step_phase_b(w);
+	}
+	// capture: the step functions enqueue into the capturing stream; nothing executes until the graph is launched
+	const uint32_t s_stamp = w->stamp; const double s_curr_dt = w->curr_dt; const int s_cur = w->cur; const uint64_t s_steps = w->steps;
+	const bool s_hints = w->hints_valid; const unsigned long long s_launches = g_cpb_launches; const int s_path = w->last_solver_path;
+	if(G.exec){ cudaGraphExecDestroy(G.exec); G.exec = NULL; }
+	cudaGraph_t graph = NULL;
+	int rc = -1;
+	if(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess){
+		rc = step_phase_a(w, dt);
+		if(!rc) rc = step_phase_b(w);
+		if(cudaStreamEndCapture(st, &graph) != cudaSuccess || !graph) rc = -1;
+	}
+	cudaGraphExec_t exec = NULL;
+	if(!rc && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) rc = -1;
+	if(graph) cudaGraphDestroy(graph);
+	if(rc){
+		// this world's step cannot be captured (driver limitation): undo the host bookkeeping and run it the ordinary way from now on
+		cudaGetLastError();
+		w->stamp = s_stamp; w->curr_dt = s_curr_dt; w->cur = s_cur; w->steps = s_steps; w->hints_valid = s_hints; g_cpb_launches = s_launches;
+		w->last_solver_path = s_path; w->mid_step = false; w->mid_solve = false;
+		w->graph_enabled = false;
+		if(step_phase_a(w, dt)) return -1;
+		return step_phase_b(w);
+	}
+	G.exec = exec; G.sig = sig; G.launches = (int)(g_cpb_launches - s_launches); G.solver_path = w->last_solver_path;
+	w->graph_captures++;
+	CPB_CHECK(cudaGraphLaunch(G.exec, st));
+	return 0;
+}
+#endif
+
 extern "C" int cpb200_world_step(cpb200_world *w, double dt)
 {
 	if(!w){ cpb_set_error("null world"); return -1; }
 	if(dt == 0.0) return 0; // cpSpaceStep.c:339
 	if(w->mid_step || w->mid_solve){ cpb_set_error("cpb200_world_step while a split step is open (call cpb200_world_step_finish)"); return -1; }
+#ifndef CPB_EMU
+	if(w->graph_enabled && w->solver_mode == 0 && !w->profiling) return step_graphed(w, dt);
+#endif
 	if(step_phase_a(w, dt)) return -1;
 	return step_phase_b(w);
+}
+
+/* Validation hook: replay the captured step graph (1, default unless CPB200_NO_GRAPH is set) or launch every kernel (0). */
+extern "C" int cpb200_world_set_graph(cpb200_world *w, int on)
+{
+	if(!w) return -1;
+	w->graph_enabled = (on != 0);
+	return 0;
+}
+
+extern "C" int cpb200_world_get_graph_stats(cpb200_world *w, unsigned long long *out2)
+{
+	if(!w || !out2) return -1;
+	out2[0] = w->graph_captures; out2[1] = w->graph_replays;
+	return 0;
 }
 
 extern "C" int cpb200_world_step_collide(cpb200_world *w, double dt)

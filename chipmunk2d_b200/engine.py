@@ -125,6 +125,8 @@ def load_engine(path=None):
     lib.cpb200_world_set_profiling.argtypes = [vp, ci]
     lib.cpb200_world_get_solver_profile.argtypes = [vp, vp]
     lib.cpb200_world_step_collide.argtypes = [vp, cd]
+    lib.cpb200_world_set_graph.argtypes = [vp, ci]
+    lib.cpb200_world_get_graph_stats.argtypes = [vp, vp]
     lib.cpb200_world_step_presolve.argtypes = [vp]
     lib.cpb200_world_step_finish.argtypes = [vp]
     lib.cpb200_world_get_body_solver_state.argtypes = [vp, ci, ci, vp]
@@ -422,6 +424,14 @@ class World:
 
     def solver_path(self):
         return int(self.lib.cpb200_world_get_solver_path(self.w))
+
+    def set_graph(self, on):
+        self._ck(self.lib.cpb200_world_set_graph(self.w, int(bool(on))))
+
+    def graph_stats(self):
+        out = np.zeros(2, dtype=np.uint64)
+        self._ck(self.lib.cpb200_world_get_graph_stats(self.w, out.ctypes.data))
+        return {"captures": int(out[0]), "replays": int(out[1])}
 
     def set_profiling(self, on):
         self._ck(self.lib.cpb200_world_set_profiling(self.w, int(bool(on))))

@@ -200,6 +200,12 @@ CPB200_API int cpb200_world_reserve(cpb200_world *w, int max_pairs, int max_arbi
 /* cpSpaceStep (cpSpaceStep.c:335-445) for every space of the world.  Asynchronous:
  * returns once the kernels are enqueued on the world's stream. */
 CPB200_API int cpb200_world_step(cpb200_world *w, double dt);
+/* A step whose launch sequence repeats (same dt, no upload in between, no profiling) is captured into a CUDA graph on
+ * its second occurrence and replayed with a single launch afterwards.  Results are identical either way
+ * (tests/test_gpu_graph.py); the hook turns the replay off (0) or on (1; default unless CPB200_NO_GRAPH is set).
+ * out2 = (graphs captured, steps replayed). */
+CPB200_API int cpb200_world_set_graph(cpb200_world *w, int on);
+CPB200_API int cpb200_world_get_graph_stats(cpb200_world *w, unsigned long long *out2);
 /* The same step in two halves for spaces with collision handlers (cpSpaceStep.c:234-290): after
  * cpb200_world_step_collide the records touched this step can be read with cpb200_world_get_arbiters, the
  * handlers' decisions are written back with cpb200_world_edit_arbiters, cpb200_world_step_finish runs

@@ -392,20 +392,34 @@ static int cmp_u64(const void *a, const void *b)
 	return (x < y ? -1 : (x > y ? 1 : 0));
 }
 
+static int cmp_shape_left(const void *a, const void *b)
+{
+	cpFloat x = (*(cpShape *const *)a)->bb.l, y = (*(cpShape *const *)b)->bb.l;
+	return (x < y ? -1 : (x > y ? 1 : 0));
+}
+
+/* Every pair of shapes is examined whose closed x-intervals overlap (shapes sorted by bb.l, inner loop until
+ * b.l > a.r): the same set an all-pairs double loop finds, in O(n log n + candidates) -- a 50 000-circle pile is
+ * 2.5e9 box tests per step otherwise. */
 REFP_EXPORT long refp_pairs_bruteforce(cpSpace *space, const unsigned char *asleep, long cap, uint64_t *out)
 {
 	collector shapes = {0};
 	cpSpaceEachShape(space, coll_shape, &shapes);
+	qsort(shapes.arr, (size_t)shapes.n, sizeof(void *), cmp_shape_left);
+	unsigned char *active = (unsigned char *)malloc((size_t)shapes.n + 1);
+	for(int i = 0; i < shapes.n; i++){
+		cpShape *a = (cpShape *)shapes.arr[i];
+		active[i] = (cpBodyGetType(a->body) != CP_BODY_TYPE_STATIC) && !(asleep ? asleep[UNTAG(a->body->userData)] : cpBodyIsSleeping(a->body));
+	}
 	long n = 0;
 	for(int i = 0; i < shapes.n; i++){
 		cpShape *a = (cpShape *)shapes.arr[i];
 		int ia = UNTAG(a->userData);
-		int a_active = (cpBodyGetType(a->body) != CP_BODY_TYPE_STATIC) && !(asleep ? asleep[UNTAG(a->body->userData)] : cpBodyIsSleeping(a->body));
 		for(int j = i + 1; j < shapes.n; j++){
 			cpShape *b = (cpShape *)shapes.arr[j];
+			if(b->bb.l > a->bb.r) break;
 			int ib = UNTAG(b->userData);
-			int b_active = (cpBodyGetType(b->body) != CP_BODY_TYPE_STATIC) && !(asleep ? asleep[UNTAG(b->body->userData)] : cpBodyIsSleeping(b->body));
-			if(!a_active && !b_active) continue;
+			if(!active[i] && !active[j]) continue;
 			if(!cpBBIntersects(a->bb, b->bb)) continue;
 			if(a->body == b->body) continue;
 			if(cpShapeFilterReject(a->filter, b->filter)) continue;
@@ -417,6 +431,7 @@ REFP_EXPORT long refp_pairs_bruteforce(cpSpace *space, const unsigned char *asle
 			n++;
 		}
 	}
+	free(active);
 	free(shapes.arr);
 	if(n <= cap) qsort(out, (size_t)n, sizeof(uint64_t), cmp_u64);
 	return n;

@@ -132,8 +132,12 @@ def production_step_replay(w, dt, dt_coef, iterations):
     out.path = w.solver_path()
     out.n_items = len(order); out.n_arbiters = len(arbs0); out.n_joints = int(np.count_nonzero(js0[:, 3])) if len(js0) else 0
     # record index -> position in the downloaded list
-    pos = {int(r): i for i, r in enumerate(arbs0["record"])}
-    items = np.array([pos[int(x)] if x >= 0 else int(x) for x in order], dtype=np.int64)
+    by_record = np.argsort(arbs0["record"], kind="stable")
+    items = order.astype(np.int64).copy()
+    isarb = order >= 0
+    if np.any(isarb):
+        items[isarb] = by_record[np.searchsorted(arbs0["record"][by_record], order[isarb])]
+        assert np.array_equal(arbs0["record"][items[isarb]], order[isarb])
     # every active arbiter and every live joint is visited exactly once
     seen_a = np.sort(items[items >= 0]); seen_j = np.sort(-(items[items < 0] + 1))
     assert np.array_equal(seen_a, np.arange(len(arbs0))), "solver order does not cover the active arbiters exactly once"

@@ -46,12 +46,14 @@ def device_order_for_reference(w):
     """(pairs, first-contact hashes, joints) of the last device step in the device's solver order."""
     order = w.solver_order()
     arbs = w.arbiters()
-    pos = {int(r): i for i, r in enumerate(arbs["record"])}
-    idx = np.array([pos[int(x)] for x in order if x >= 0], dtype=np.int64)
+    by_record = np.argsort(arbs["record"], kind="stable")
+    rec = order[order >= 0]
+    idx = by_record[np.searchsorted(arbs["record"][by_record], rec)] if len(rec) else np.zeros(0, dtype=np.int64)
+    assert np.array_equal(arbs["record"][idx], rec)
     seq = arbs[idx] if len(idx) else arbs[:0]
     pairs = (seq["shape_a"].astype(np.uint64) << np.uint64(32)) | seq["shape_b"].astype(np.uint64)
     hash0 = seq["contacts"][:, 0]["hash"].astype(np.uint64) if len(seq) else np.zeros(0, dtype=np.uint64)
-    joints = np.array([-(int(x) + 1) for x in order if x < 0], dtype=np.int32)
+    joints = (-(order[order < 0] + 1)).astype(np.int32)
     return pairs, hash0, joints
 
 

@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-9
 
 
-@pytest.mark.parametrize("name,steps", [("circle_pile_50000", 40), ("mixed_drop_20000_no_joints", 40)])
+@pytest.mark.parametrize("name,steps", [("circle_pile_50000", 40), ("mixed_drop_20000_no_joints", 40)])  # 40 + steps
 def test_reduced_scale_production_step_equals_reference_in_the_same_order(ref, name, steps):
     sc = circle_pile(50000, dense=True, sleep=0.5) if name == "circle_pile_50000" else mixed_drop(20000, joints=False)
     rs = ref.load(sc.blob)
@@ -50,7 +50,7 @@ def test_reduced_scale_production_step_equals_reference_in_the_same_order(ref, n
         worst["v"] = max(worst["v"], rel_err(wb["v"][1:], rb[1:, 2:4]), rel_err(wb["w"][1:], rb[1:, 5]))
     st = w.stats()
     assert st["overflow"] == 0
-    assert worst["pairs"] > steps * len(sc.bodies) // 2, worst     # a dense pile: pairs at every step
+    assert worst["pairs"] > (steps * len(sc.bodies) if name == "circle_pile_50000" else 20000), worst     # the dense pile: ~3 pairs per body at every step
     assert worst["pairs_bad"] == 0 and worst["unmatched"] == 0, worst
     assert worst["p"] < TOL and worst["v"] < TOL, worst
     rs.space = None
