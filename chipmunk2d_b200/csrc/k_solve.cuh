@@ -407,6 +407,18 @@ __device__ __forceinline__ void row_prefetch(const DRows &R, int r){
 #else
 CPB_DEVICE void row_prefetch(const DRows &, int){ }
 #endif
+// The first row a thread solves in the NEXT colour phase: its constants and impulses belong to this thread alone, so they
+// can be pulled into L2 while the grid barrier is still closed (one prefetch burst per thread and phase, unlike the
+// per-row variant above); after the barrier only the velocity gathers are left to wait for.
+#ifndef CPB_EMU
+__device__ __forceinline__ void row_prefetch_phase(const DRows &R, int r){
+	asm volatile("prefetch.global.L2 [%0];" :: "l"(&R.n[r])); asm volatile("prefetch.global.L2 [%0];" :: "l"(&R.r1[r])); asm volatile("prefetch.global.L2 [%0];" :: "l"(&R.r2[r]));
+	asm volatile("prefetch.global.L2 [%0];" :: "l"(&R.nmass[r])); asm volatile("prefetch.global.L2 [%0];" :: "l"(&R.tmass[r])); asm volatile("prefetch.global.L2 [%0];" :: "l"(&R.bias[r]));
+	asm volatile("prefetch.global.L2 [%0];" :: "l"(&R.jn[r])); asm volatile("prefetch.global.L2 [%0];" :: "l"(&R.jt[r])); asm volatile("prefetch.global.L2 [%0];" :: "l"(&R.jb[r]));
+}
+#else
+static inline void row_prefetch_phase(const DRows &, int){ }
+#endif
 
 // one contact of a row: constants + accumulated impulses
 template<bool STREAM> struct RowContact {
@@ -700,26 +712,25 @@ __global__ void k_sl_solve(DBodies B, DArbs A, DJoints J, DRows R, DSpaceLocal S
 // spins on the generation word; the gpu-scope fences on both sides order the phase's global
 // writes before every later read (the same pattern cooperative_groups::grid_group::sync uses),
 // at one L2 round trip instead of a library call per colour.
-__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned nblocks)
+__device__ __forceinline__ unsigned bar_ld_acquire(const unsigned *p){ unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ unsigned bar_arrive(unsigned *p){ unsigned o; asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(o) : "l"(p) : "memory"); return o; }
+// One monotonically increasing arrival counter per kernel (zeroed by k_reset_step): barrier number g is open once the
+// count reaches g x nblocks.  The arrival is a release (everything this CTA wrote in the phase, ordered before it by the
+// block barrier), the spin an acquire load: no stand-alone fences, no generation word, no reset by the last arriver.
+// Measured on B200, 296 CTAs: 1.16 us per barrier against 2.35 us for fence + atomicAdd + generation word + fence
+// (tools/micro/barrier_bench.cu); a two-level variant (groups of 16 CTAs) was slower than either.
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned nblocks, unsigned &target)
 {
 	__syncthreads();
 	if(nblocks == 1) return;   // a single CTA (small scenes): the block barrier already orders its global accesses
 	if(threadIdx.x == 0){
-		__threadfence();
-		unsigned gen = *((volatile unsigned *)&bar[1]);
-		unsigned arrived = atomicAdd(&bar[0], 1u) + 1u;
-		if(arrived == nblocks){
-			bar[0] = 0u;
-			__threadfence();
-			atomicAdd(&bar[1], 1u);
-		} else {
-			while(*((volatile unsigned *)&bar[1]) == gen){ }
-		}
-		__threadfence();
+		target += nblocks;
+		bar_arrive(bar);
+		while((int)(bar_ld_acquire(bar) - target) < 0){ }
 	}
 	__syncthreads();
 }
-#define GRID_SYNC() grid_barrier(bar, gridDim.x)
+#define GRID_SYNC() grid_barrier(bar + (PHASE == 2 ? 32 : 0), gridDim.x, bar_target)
 __device__ __forceinline__ unsigned long long global_ns(){ unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define PROF(i) do { if(tid == 0) K.prof[i] = global_ns(); } while(0)
 
@@ -741,6 +752,7 @@ template<bool SPACE_LOCAL, bool STREAM_ROWS, bool JOINTS, int PHASE, int MINB> _
 	__shared__ int s_base[CPB_MAX_COLOURS];
 	const int tid = CPB_TID, nth = CPB_NTHREADS;
 	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
+	unsigned bar_target = 0;
 	if(PHASE != 2){
 	if(threadIdx.x < 2*CPB_MAX_COLOURS) s_hist[threadIdx.x] = 0;
 	__syncthreads();
@@ -750,7 +762,7 @@ template<bool SPACE_LOCAL, bool STREAM_ROWS, bool JOINTS, int PHASE, int MINB> _
 
 	PROF(0);
 	// K10: colouring -- keep last step's colours, then Jones-Plassmann rounds over the worklist
-	colour_seed(B, A, J, K, s_hist, nA, use_hints, tid, nth);
+	colour_seed(B, A, J, K, s_hist, nA, use_hints & 1, tid, nth);
 	HIST_FLUSH();
 	GRID_SYNC();
 	int rounds_done = 0;
@@ -795,10 +807,11 @@ template<bool SPACE_LOCAL, bool STREAM_ROWS, bool JOINTS, int PHASE, int MINB> _
 	bool has_overflow = (ncol > CPB_OVERFLOW_COLOUR);
 	const int jtid = nth - 1 - tid;
 	const VelGlobalT<STREAM_ROWS> vg = {B.V, B.VB};
+	const bool PHASE_PREFETCH = (STREAM_ROWS && (use_hints & 2) == 0);   // bit 1 of use_hints: experiment switch, prefetch off
 	int pr = -1, pba = 0, pbb = 0, pcnt = 0;     // prefetched row
 	int pq = -1, pj = 0, pja = 0, pjb = 0;       // prefetched joint
 	#define PREFETCH_PHASE(c_) do { \
-		pr = s_cstart[c_] + tid; if(pr < s_cstart[(c_) + 1]){ pba = row_ld<STREAM_ROWS>(&R.ba[pr]); pbb = row_ld<STREAM_ROWS>(&R.bb[pr]); pcnt = row_ld<STREAM_ROWS>(&R.cnt[pr]); row_prefetch(R, pr); } else pr = -1; \
+		pr = s_cstart[c_] + tid; if(pr < s_cstart[(c_) + 1]){ pba = row_ld<STREAM_ROWS>(&R.ba[pr]); pbb = row_ld<STREAM_ROWS>(&R.bb[pr]); pcnt = row_ld<STREAM_ROWS>(&R.cnt[pr]); if(PHASE_PREFETCH) row_prefetch_phase(R, pr); } else pr = -1; \
 		pq = s_jstart[c_] + jtid; if(JOINTS && pq < s_jstart[(c_) + 1]){ pj = J.row[pq]; pja = J.a[pj]; pjb = J.b[pj]; } else pq = -1; } while(0)
 	if(nreg > 0) PREFETCH_PHASE(0);
 	for(int pass = 0; pass <= iterations; pass++){
@@ -837,7 +850,7 @@ template<bool SPACE_LOCAL, bool STREAM_ROWS, bool JOINTS, int PHASE, int MINB> _
 // kernels used by the emulation build (multi-launch variant of the same phases)
 __global__ void k_colour_seed(DBodies B, DArbs A, DJoints J, DColour K, int use_hints){
 	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
-	colour_seed(B, A, J, K, (int *)NULL, nA, use_hints, CPB_TID, CPB_NTHREADS);
+	colour_seed(B, A, J, K, (int *)NULL, nA, use_hints & 1, CPB_TID, CPB_NTHREADS);
 }
 __global__ void k_colour_a(DBodies B, DArbs A, DJoints J, DColour K, int round){
 	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;

@@ -154,12 +154,15 @@ struct cpb200_world {
 	// microseconds each, and their launch gaps were most of its step time.  Every counter a kernel needs lives on the device.
 	struct StepGraph { cudaGraphExec_t exec; unsigned long long sig; int launches; int solver_path; } graph[2];
 	unsigned long long graph_gen;       // bumped by every upload / setting that can change the launch sequence
-	unsigned long long graph_last_sig;  // signature of the previous step (a graph is captured when it repeats)
+	unsigned long long graph_last_sig[2];  // signature of the previous step of the same parity (a graph is captured when it repeats;
+	                                       // the radix sort's ping-pong buffers make odd and even steps differ)
 	bool graph_enabled;
+	char graph_error[384];              // why capturing failed (the world then keeps launching kernel by kernel)
 	unsigned long long graph_replays, graph_captures;
 	double step_dt, step_dt_coef; int step_iterations;
 	bool hints_valid;       // last step's colours may seed this step's colouring
 	bool no_hints;          // validation hook (env CPB200_NO_HINTS): colour from scratch every step
+	bool no_phase_prefetch; // experiment switch (env CPB200_NO_PHASE_PREFETCH)
 	int wl_cap; AllocGroup gW;
 	int force_blocks;       // validation hook: fixed persistent grid size (0 = automatic)
 	int last_active;        // active arbiters seen at the last host read-back (grid sizing hint)
@@ -295,12 +298,12 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	cudaMalloc(&p, sizeof(DSpace)*(size_t)n_spaces); w->d_spaces = (DSpace *)p;
 	cudaMalloc(&p, sizeof(DCounters)); w->C = (DCounters *)p; cudaMemsetAsync(w->C, 0, sizeof(DCounters), w->stream);
 	cudaMallocHost(&p, sizeof(DCounters)); w->hC = (DCounters *)p; memset(w->hC, 0, sizeof(DCounters));
-	cudaMalloc(&p, sizeof(unsigned)*8); w->d_barrier = (unsigned *)p; cudaMemsetAsync(w->d_barrier, 0, sizeof(unsigned)*8, w->stream);
-	w->no_hints = (getenv("CPB200_NO_HINTS") != NULL);
+	cudaMalloc(&p, sizeof(unsigned)*64); w->d_barrier = (unsigned *)p; cudaMemsetAsync(w->d_barrier, 0, sizeof(unsigned)*64, w->stream);
+	w->no_hints = (getenv("CPB200_NO_HINTS") != NULL); w->no_phase_prefetch = (getenv("CPB200_NO_PHASE_PREFETCH") != NULL);
 	w->d_query = NULL; w->query_bytes = 0;
 	w->mid_solve = false; w->solver_variant = 0; w->last_solver_path = 0;
-	memset(w->graph, 0, sizeof(w->graph)); w->graph_gen = 1; w->graph_last_sig = 0; w->graph_replays = w->graph_captures = 0;
-	w->graph_enabled = (getenv("CPB200_NO_GRAPH") == NULL);
+	memset(w->graph, 0, sizeof(w->graph)); w->graph_gen = 1; w->graph_last_sig[0] = w->graph_last_sig[1] = 0; w->graph_replays = w->graph_captures = 0;
+	w->graph_enabled = (getenv("CPB200_NO_GRAPH") == NULL); w->graph_error[0] = 0;
 	w->mid_step = false; w->step_dt = 0.0; w->step_dt_coef = 0.0; w->step_iterations = 0;
 	w->sl_dirty = true; w->sl_ok = false; w->sl_disabled = (getenv("CPB200_NO_SPACE_LOCAL") != NULL); w->sl_max_nbody = 0;
 	memset(&w->SL, 0, sizeof(w->SL)); w->sl_tmp = NULL;
@@ -795,8 +798,9 @@ static int refresh_joint_bias(cpb200_world *w, double dt)
 #define STAGE_END(w, id) do { if((w)->profiling){ cudaEventRecord((w)->ev[(id) + 1], (w)->stream); } } while(0)
 
 // start-of-step bookkeeping in one launch (the small per-step clears used to be five memsets)
-__global__ void k_reset_step(DCounters *C, int *pair_count, int *cur_count, int *ccount, int *jcount, int *wl_n)
+__global__ void k_reset_step(DCounters *C, int *pair_count, int *cur_count, int *ccount, int *jcount, int *wl_n, unsigned *bar)
 {
+	if(CPB_TID == 0){ bar[0] = 0u; bar[32] = 0u; }   // arrival counters of the two cooperative solver kernels
 	if(ccount){
 		for(int k = CPB_TID; k <= CPB_MAX_COLOURS; k += CPB_NTHREADS){ ccount[k] = 0; jcount[k] = 0; }
 		for(int k = CPB_TID; k < CPB_MAX_COLOUR_ROUNDS + 2; k += CPB_NTHREADS) wl_n[k] = 0;
@@ -940,7 +944,7 @@ static int step_phase_a(cpb200_world *w, double dt)
 	int prv = w->cur; w->cur ^= 1;
 	DArbs &Ap = w->A[prv]; DArbs &Ac = w->A[w->cur];
 	DTable &Tp = w->T[prv]; DTable &Tc = w->T[w->cur];
-	LAUNCH(k_reset_step, 1, 32, st, w->C, w->P.count, Ac.count_ptr, w->K.ccount, w->K.jcount, w->K.wl_n);
+	LAUNCH(k_reset_step, 1, 32, st, w->C, w->P.count, Ac.count_ptr, w->K.ccount, w->K.jcount, w->K.wl_n, w->d_barrier);
 
 	const int nb = B.n, ns = S.n;
 	const int wide = w->sm_count*8;
@@ -1131,6 +1135,7 @@ static int step_phase_b2(cpb200_world *w)
 		// (claim / bmask were cleared by k_integrate_vel, the colour histograms and worklist lengths by k_reset_step)
 		if(ensure_worklists(w, Ac.cap + J.n + 64)) return -1;
 		int use_hints = (w->hints_valid && !w->no_hints ? 1 : 0);
+		if(w->no_phase_prefetch) use_hints |= 2;
 		w->hints_valid = true;
 #ifndef CPB_EMU
 		{
@@ -1264,7 +1269,7 @@ static int step_graphed(cpb200_world *w, double dt)
 	               (w->J.n == 0 || w->joints_dt == dt) && !w->sl_dirty && w->wl_cap >= w->A[0].cap + w->J.n + 64 &&
 	               !(w->solver_variant == 3 && !w->sl_ok) && w->B.n > 0);
 	if(!steady){
-		w->graph_last_sig = 0;
+		w->graph_last_sig[0] = w->graph_last_sig[1] = 0;
 		if(step_phase_a(w, dt)) return -1;
 		return step_phase_b(w);
 	}
@@ -1277,9 +1282,9 @@ static int step_graphed(cpb200_world *w, double dt)
 		w->graph_replays++;
 		return 0;
 	}
-	if(w->graph_last_sig != sig){
-		// first step with this signature: run it as it is; if the next one looks the same it is captured
-		w->graph_last_sig = sig;
+	if(w->graph_last_sig[w->cur & 1] != sig){
+		// first step with this signature: run it as it is; if the next one of this parity looks the same it is captured
+		w->graph_last_sig[w->cur & 1] = sig;
 		if(step_phase_a(w, dt)) return -1;
 		return step_phase_b(w);
 	}
@@ -1289,15 +1294,21 @@ static int step_graphed(cpb200_world *w, double dt)
 	if(G.exec){ cudaGraphExecDestroy(G.exec); G.exec = NULL; }
 	cudaGraph_t graph = NULL;
 	int rc = -1;
-	if(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess){
+	cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+	const char *where = "cudaStreamBeginCapture";
+	if(ce == cudaSuccess){
 		rc = step_phase_a(w, dt);
 		if(!rc) rc = step_phase_b(w);
-		if(cudaStreamEndCapture(st, &graph) != cudaSuccess || !graph) rc = -1;
+		if(rc){ where = "enqueue under capture"; snprintf(w->graph_error, sizeof(w->graph_error), "%s", cpb200_last_error()); }
+		ce = cudaStreamEndCapture(st, &graph);
+		if(ce != cudaSuccess || !graph){ if(!rc) where = "cudaStreamEndCapture"; rc = -1; }
 	}
 	cudaGraphExec_t exec = NULL;
-	if(!rc && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) rc = -1;
+	if(!rc){ ce = cudaGraphInstantiate(&exec, graph, 0); if(ce != cudaSuccess){ rc = -1; where = "cudaGraphInstantiate"; } }
 	if(graph) cudaGraphDestroy(graph);
 	if(rc){
+		size_t len = strlen(w->graph_error);
+		snprintf(w->graph_error + len, sizeof(w->graph_error) - len, " [%s: %s]", where, cudaGetErrorString(ce));
 		// this world's step cannot be captured (driver limitation): undo the host bookkeeping and run it the ordinary way from now on
 		cudaGetLastError();
 		w->stamp = s_stamp; w->curr_dt = s_curr_dt; w->cur = s_cur; w->steps = s_steps; w->hints_valid = s_hints; g_cpb_launches = s_launches;
@@ -1332,6 +1343,8 @@ extern "C" int cpb200_world_set_graph(cpb200_world *w, int on)
 	w->graph_enabled = (on != 0);
 	return 0;
 }
+
+extern "C" const char *cpb200_world_graph_error(cpb200_world *w){ return w ? w->graph_error : ""; }
 
 extern "C" int cpb200_world_get_graph_stats(cpb200_world *w, unsigned long long *out2)
 {
@@ -1786,6 +1799,16 @@ extern "C" long cpb200_world_get_solver_order(cpb200_world *w, long cap, int64_t
 }
 
 extern "C" int cpb200_world_get_solver_path(cpb200_world *w){ return w ? w->last_solver_path : -1; }
+
+/* out[2][CPB_MAX_COLOURS + 1]: begin of every colour in the row list / in the joint list of the last world-wide coloured step */
+extern "C" int cpb200_world_get_colour_starts(cpb200_world *w, int32_t *out)
+{
+	if(!w || !out || !w->K.cstart){ cpb_set_error("no colouring yet"); return -1; }
+	cudaSetDevice(w->device);
+	CPB_CHECK(cudaMemcpyAsync(out, w->K.cstart, sizeof(int)*(CPB_MAX_COLOURS + 1), cudaMemcpyDeviceToHost, w->stream));
+	CPB_CHECK(cudaMemcpyAsync(out + CPB_MAX_COLOURS + 1, w->K.jstart, sizeof(int)*(CPB_MAX_COLOURS + 1), cudaMemcpyDeviceToHost, w->stream));
+	return world_sync(w);
+}
 
 extern "C" int cpb200_world_collide_pair(cpb200_world *w, int shape_a, int shape_b, double *out13)
 {

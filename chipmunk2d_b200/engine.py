@@ -127,6 +127,8 @@ def load_engine(path=None):
     lib.cpb200_world_step_collide.argtypes = [vp, cd]
     lib.cpb200_world_set_graph.argtypes = [vp, ci]
     lib.cpb200_world_get_graph_stats.argtypes = [vp, vp]
+    lib.cpb200_world_graph_error.restype = C.c_char_p
+    lib.cpb200_world_graph_error.argtypes = [vp]
     lib.cpb200_world_step_presolve.argtypes = [vp]
     lib.cpb200_world_step_finish.argtypes = [vp]
     lib.cpb200_world_get_body_solver_state.argtypes = [vp, ci, ci, vp]
@@ -135,6 +137,7 @@ def load_engine(path=None):
     lib.cpb200_world_get_solver_order.restype = C.c_long
     lib.cpb200_world_get_solver_order.argtypes = [vp, C.c_long, vp]
     lib.cpb200_world_get_solver_path.argtypes = [vp]
+    lib.cpb200_world_get_colour_starts.argtypes = [vp, vp]
     _lib_cache[path] = lib
     return lib
 
@@ -422,6 +425,12 @@ class World:
         n = self._ck(self.lib.cpb200_world_get_solver_order(self.w, len(out), out.ctypes.data))
         return out[:n]
 
+    def colour_sizes(self):
+        """(rows per colour, joints per colour) of the last world-wide coloured step."""
+        out = np.zeros((2, 65), dtype=np.int32)
+        self._ck(self.lib.cpb200_world_get_colour_starts(self.w, out.ctypes.data))
+        return np.diff(out[0]), np.diff(out[1])
+
     def solver_path(self):
         return int(self.lib.cpb200_world_get_solver_path(self.w))
 
@@ -431,7 +440,7 @@ class World:
     def graph_stats(self):
         out = np.zeros(2, dtype=np.uint64)
         self._ck(self.lib.cpb200_world_get_graph_stats(self.w, out.ctypes.data))
-        return {"captures": int(out[0]), "replays": int(out[1])}
+        return {"captures": int(out[0]), "replays": int(out[1]), "error": self.lib.cpb200_world_graph_error(self.w).decode()}
 
     def set_profiling(self, on):
         self._ck(self.lib.cpb200_world_set_profiling(self.w, int(bool(on))))

@@ -206,6 +206,8 @@ CPB200_API int cpb200_world_step(cpb200_world *w, double dt);
  * out2 = (graphs captured, steps replayed). */
 CPB200_API int cpb200_world_set_graph(cpb200_world *w, int on);
 CPB200_API int cpb200_world_get_graph_stats(cpb200_world *w, unsigned long long *out2);
+/* Empty, or why capturing this world's step failed (the world then launches kernel by kernel for good). */
+CPB200_API const char *cpb200_world_graph_error(cpb200_world *w);
 /* The same step in two halves for spaces with collision handlers (cpSpaceStep.c:234-290): after
  * cpb200_world_step_collide the records touched this step can be read with cpb200_world_get_arbiters, the
  * handlers' decisions are written back with cpb200_world_edit_arbiters, cpb200_world_step_finish runs
@@ -288,6 +290,8 @@ CPB200_API int cpb200_world_set_solver_variant(cpb200_world *w, int variant);
  * with a sequential solver (cpSpaceStep.c:406-427) must give the parallel result bit for bit.
  * Returns the count; writes at most cap. */
 CPB200_API long cpb200_world_get_solver_order(cpb200_world *w, long cap, int64_t *out);
+/* out[2][65]: begin of every colour in the solver's row list, then in its joint list (world-wide coloured step). */
+CPB200_API int cpb200_world_get_colour_starts(cpb200_world *w, int32_t *out);
 /* 0 serial, 1 world-wide coloured, 2 space-local: what the last step ran. */
 CPB200_API int cpb200_world_get_solver_path(cpb200_world *w);
 /* Run only the narrowphase on one uploaded shape pair with current world caches
