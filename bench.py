@@ -301,18 +301,18 @@ def measure(workload, args, ctx, full):
     w = World(len(scenes), device=local_rank)
     w.load_scenes(scenes)
     settle = SETTLE[workload]
-    w.step(dt, settle)          # untimed: let contacts form so the timed steps see the configured workload
     sampler = None
     if full:
         sampler = ClockSampler(local_rank)
-        sampler.start()         # before the warm-up: nvidia-smi takes a moment to deliver its first sample
-    w.step(dt, warm)
+        sampler.start()         # before the settle steps: nvidia-smi takes a moment to deliver its first sample
+    w.step(dt, settle)          # untimed: let contacts form so the timed steps see the configured workload
     w.sync()
     if sampler is not None:
         t_wait = time.time()
         while sampler.proc and not sampler.rows and time.time() - t_wait < 2.0:
-            w.step(dt, 5)       # more untimed steps until the clock sampler delivers (keeps the GPU under load)
-            w.sync()
+            time.sleep(0.05)    # (no extra steps here: the timed window must start at the same step in every run)
+    w.step(dt, warm)
+    w.sync()
 
     launches0 = w.launch_count()
     barrier()

@@ -195,7 +195,8 @@ struct DCounters {
 	int n_overflow_colour;
 	int n_cached;
 	uint32_t stamp;        // space->stamp (cpSpaceStep.c:349): advanced on the device by k_reset_step, so a captured step graph replays it
-	int pad[3];
+	int no_gjk_stage;      // experiment switch (env CPB200_NO_GJK_STAGE): k_collide<2> reads polygon vertices from global memory
+	int pad[2];
 };
 
 #define CPB_MAX_COLOURS 64

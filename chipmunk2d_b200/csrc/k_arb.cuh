@@ -21,7 +21,7 @@ CPB_DEVICE NShape load_nshape(const DShapes &S, const DBodies &B, int s){
 	o.r = S.r[s];
 	double4 bb = S.bb[s];
 	o.bbc = vlerp(v2(bb.x, bb.y), v2(bb.z, bb.w), 0.5);
-	o.count = 0; o.pv = 0; o.pn = 0;
+	o.count = 0; o.pv = 0; o.pn = 0; o.sv = 0;
 	o.a = v2(0, 0); o.b = v2(0, 0); o.n = v2(0, 0);
 	o.rot = v2(1, 0); o.atan = v2(0, 0); o.btan = v2(0, 0);
 	if(o.type == CPB200_SHAPE_CIRCLE){
@@ -135,6 +135,11 @@ __global__ void __launch_bounds__(128, (CLS == 2 ? CPB_COLLIDE_GJK_CTAS : 1)) k_
 {
 	int np = *pcount; if(np > pcap) np = pcap;
 	const uint32_t stamp = C->stamp;
+#ifndef CPB_EMU
+	// per-thread staging of both polygons' vertices (GJK class only): 2 shapes x 8 vertices x (x, y) x 128 threads = 32 KB
+	__shared__ double s_verts[CLS == 2 ? 2*2*CPB_GJK_STAGE_VERTS*CPB_GJK_STAGE_STRIDE : 1];
+	const bool stage_verts = (CLS == 2 && C->no_gjk_stage == 0);     // experiment switch CPB200_NO_GJK_STAGE
+#endif
 	const uint32_t pmask = *prev_table.dmask;
 	int my_active = 0, my_contacts = 0;     // step statistics: summed per thread, flushed once per warp after the loop
 	for(int base = blockIdx.x*blockDim.x; base < np; base += gridDim.x*blockDim.x){
@@ -182,6 +187,21 @@ __global__ void __launch_bounds__(128, (CLS == 2 ? CPB_COLLIDE_GJK_CTAS : 1)) k_
 				if(pi >= 0){ w0 = ld4_nc(&prev.warm[2*pi]); w1 = ld4_nc(&prev.warm[2*pi + 1]); }
 				m.id = (pi >= 0 ? (uint32_t)((unsigned long long)__double_as_longlong(w1.z) >> 32) : 0u);
 				NShape a = load_nshape(S, B, sa), b = load_nshape(S, B, sb);
+#ifndef CPB_EMU
+				if(CLS == 2 && stage_verts){
+					// north star stage 3: the polygons' world vertices go to shared memory once per pair (nshape_vert)
+					if(a.type == CPB200_SHAPE_POLY && a.count <= CPB_GJK_STAGE_VERTS){
+						double *sv = s_verts + threadIdx.x;
+						for(int k = 0; k < a.count; k++){ V2 v = a.pv[k]; sv[(2*k)*CPB_GJK_STAGE_STRIDE] = v.x; sv[(2*k + 1)*CPB_GJK_STAGE_STRIDE] = v.y; }
+						a.sv = sv;
+					}
+					if(b.type == CPB200_SHAPE_POLY && b.count <= CPB_GJK_STAGE_VERTS){
+						double *sv = s_verts + 2*CPB_GJK_STAGE_VERTS*CPB_GJK_STAGE_STRIDE + threadIdx.x;
+						for(int k = 0; k < b.count; k++){ V2 v = b.pv[k]; sv[(2*k)*CPB_GJK_STAGE_STRIDE] = v.x; sv[(2*k + 1)*CPB_GJK_STAGE_STRIDE] = v.y; }
+						b.sv = sv;
+					}
+				}
+#endif
 				if(CLS == 1) circle_to_segment(a, b, m);
 				else collide_shapes(a, b, m);
 				// (not before the narrowphase: GJK/EPA needs the registers, and many box pairs do not touch)

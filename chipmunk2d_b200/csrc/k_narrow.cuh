@@ -27,6 +27,7 @@ struct NShape {
 	V2 bbc;              // cpBBCenter(shape->bb) (cpBB.h:97-100)
 	const V2 *pv;        // poly: world vertices  (planes[i].v0)
 	const V2 *pn;        // poly: world normals   (planes[i].n)
+	const double *sv;    // poly: the same vertices staged in shared memory by k_collide<2> (NULL: read pv), see nshape_vert
 	V2 rot;              // owning body's rotation (cpBodyGetRotation)
 	V2 atan, btan;       // segment neighbour tangents (body-local)
 };
@@ -51,6 +52,20 @@ CPB_DEVICE bool check_axis(V2 v0, V2 v1, V2 p, V2 n){
 	return vdot(p, n) <= fmax_cp(vdot(v0, n), vdot(v1, n));
 }
 
+// GJK and EPA evaluate support points over and over (cpCollision.c:62-78: a scan of every vertex per call, several
+// calls per iteration, for both shapes): k_collide<2> copies the world vertices of the pair's polygons into shared
+// memory once -- vertex i of thread t at sv[(2i + c)*CPB_GJK_STAGE_STRIDE], c = 0 (x), 1 (y), so that a warp reading
+// "its" vertex i touches consecutive words -- and every later read comes from there.  Polygons with more than
+// CPB_GJK_STAGE_VERTS vertices, the one-pair hook and the shape queries keep the global pointer.
+#define CPB_GJK_STAGE_VERTS 8
+#define CPB_GJK_STAGE_STRIDE 128     // = threads per CTA of k_collide
+CPB_DEVICE V2 nshape_vert(const NShape &s, int i){
+#ifndef CPB_EMU
+	if(s.sv) return v2(s.sv[(2*i)*CPB_GJK_STAGE_STRIDE], s.sv[(2*i + 1)*CPB_GJK_STAGE_STRIDE]);
+#endif
+	return s.pv[i];
+}
+
 // ---- support points (cpCollision.c:62-117) ----
 struct SupportPoint { V2 p; uint32_t index; };
 
@@ -58,7 +73,7 @@ CPB_DEVICE int poly_support_index(const NShape &s, V2 n){
 	double max = -INFINITY;
 	int index = 0;
 	for(int i = 0; i < s.count; i++){
-		V2 v = s.pv[i];
+		V2 v = nshape_vert(s, i);
 		double d = vdot(v, n);
 		if(d > max){ max = d; index = i; }
 	}
@@ -72,7 +87,7 @@ CPB_DEVICE SupportPoint support_point(const NShape &s, V2 n){
 		if(vdot(s.a, n) > vdot(s.b, n)){ sp.p = s.a; sp.index = 0; } else { sp.p = s.b; sp.index = 1; }
 	} else {
 		int i = poly_support_index(s, n);
-		sp.p = s.pv[i]; sp.index = (uint32_t)i;
+		sp.p = nshape_vert(s, i); sp.index = (uint32_t)i;
 	}
 	return sp;
 }
@@ -82,7 +97,7 @@ CPB_DEVICE SupportPoint shape_point(const NShape &s, int i){
 	SupportPoint sp;
 	if(s.type == 0){ sp.p = s.a; sp.index = 0; }
 	else if(s.type == 1){ sp.p = (i == 0 ? s.a : s.b); sp.index = (uint32_t)i; }
-	else { int index = (i < s.count ? i : 0); sp.p = s.pv[index]; sp.index = (uint32_t)index; }
+	else { int index = (i < s.count ? i : 0); sp.p = nshape_vert(s, index); sp.index = (uint32_t)index; }
 	return sp;
 }
 
@@ -226,12 +241,12 @@ CPB_DEVICE Edge support_edge_poly(const NShape &s, V2 n){
 	uint64_t hashid = s.hashid;
 	Edge e;
 	if(vdot(n, s.pn[i1]) > vdot(n, s.pn[i2])){
-		e.a.p = s.pv[i0]; e.a.hash = hash_pair(hashid, (uint64_t)i0);
-		e.b.p = s.pv[i1]; e.b.hash = hash_pair(hashid, (uint64_t)i1);
+		e.a.p = nshape_vert(s, i0); e.a.hash = hash_pair(hashid, (uint64_t)i0);
+		e.b.p = nshape_vert(s, i1); e.b.hash = hash_pair(hashid, (uint64_t)i1);
 		e.r = s.r; e.n = s.pn[i1];
 	} else {
-		e.a.p = s.pv[i1]; e.a.hash = hash_pair(hashid, (uint64_t)i1);
-		e.b.p = s.pv[i2]; e.b.hash = hash_pair(hashid, (uint64_t)i2);
+		e.a.p = nshape_vert(s, i1); e.a.hash = hash_pair(hashid, (uint64_t)i1);
+		e.b.p = nshape_vert(s, i2); e.b.hash = hash_pair(hashid, (uint64_t)i2);
 		e.r = s.r; e.n = s.pn[i2];
 	}
 	return e;

@@ -297,6 +297,7 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	void *p = NULL;
 	cudaMalloc(&p, sizeof(DSpace)*(size_t)n_spaces); w->d_spaces = (DSpace *)p;
 	cudaMalloc(&p, sizeof(DCounters)); w->C = (DCounters *)p; cudaMemsetAsync(w->C, 0, sizeof(DCounters), w->stream);
+	if(w->C && getenv("CPB200_NO_GJK_STAGE")){ int one = 1; cudaMemcpyAsync(&w->C->no_gjk_stage, &one, sizeof(int), cudaMemcpyHostToDevice, w->stream); cudaStreamSynchronize(w->stream); }
 	cudaMallocHost(&p, sizeof(DCounters)); w->hC = (DCounters *)p; memset(w->hC, 0, sizeof(DCounters));
 	cudaMalloc(&p, sizeof(unsigned)*64); w->d_barrier = (unsigned *)p; cudaMemsetAsync(w->d_barrier, 0, sizeof(unsigned)*64, w->stream);
 	w->no_hints = (getenv("CPB200_NO_HINTS") != NULL); w->no_phase_prefetch = (getenv("CPB200_NO_PHASE_PREFETCH") != NULL);
@@ -1232,7 +1233,9 @@ static unsigned long long step_signature(cpb200_world *w, double dt, int iterati
 	h = sig_mix(h, (unsigned long long)w->B.n); h = sig_mix(h, (unsigned long long)w->S.n); h = sig_mix(h, (unsigned long long)w->S.nv); h = sig_mix(h, (unsigned long long)w->J.n);
 	h = sig_mix(h, (unsigned long long)w->cap_arbs); h = sig_mix(h, (unsigned long long)w->cap_pairs); h = sig_mix(h, (unsigned long long)w->n_spaces);
 	h = sig_ptr(h, w->B.pos); h = sig_ptr(h, w->S.type); h = sig_ptr(h, w->J.type); h = sig_ptr(h, w->A[0].key); h = sig_ptr(h, w->P.cand);
-	h = sig_ptr(h, w->bvh.keys); h = sig_ptr(h, w->keys_b); h = sig_ptr(h, w->K.wl[0]); h = sig_ptr(h, w->d_nocollide); h = sig_ptr(h, w->SL.start); h = sig_ptr(h, w->I.parent);
+	// (the radix sort ping-pongs between two key buffers and the host swaps its pointers when the sorted keys end up in the
+	// second one; no step reads the previous step's keys, so a replayed graph may use them in either role: hash the pair)
+	h = sig_ptr(h, std::min((const void *)w->bvh.keys, (const void *)w->keys_b)); h = sig_ptr(h, std::max((const void *)w->bvh.keys, (const void *)w->keys_b)); h = sig_ptr(h, w->K.wl[0]); h = sig_ptr(h, w->d_nocollide); h = sig_ptr(h, w->SL.start); h = sig_ptr(h, w->I.parent);
 	h = sig_mix(h, (unsigned long long)w->n_nocollide);
 	h = sig_mix(h, (unsigned long long)((w->hints_valid && !w->no_hints) ? 1 : 0));
 	h = sig_mix(h, (unsigned long long)(w->any_sleep_enabled ? 1 : 0));
