@@ -274,7 +274,7 @@ __global__ void k_query_shape(DShapes S, DBodies B, QShape q, QFilter filter, in
 				NShape a;
 				a.type = q.type; a.count = q.count; a.hashid = 0; a.a = q.a; a.b = q.b; a.n = q.n; a.r = q.r;
 				a.bbc = v2((q.bb.x + q.bb.z)*0.5, (q.bb.y + q.bb.w)*0.5);
-				a.pv = q.pv; a.pn = q.pn; a.rot = q.rot; a.atan = q.atan; a.btan = q.btan;
+				a.pv = q.pv; a.pn = q.pn; a.sv = 0; a.rot = q.rot; a.atan = q.atan; a.btan = q.btan;
 				NShape b = load_nshape(S, B, s);
 				// cpShapesCollide (cpShape.c:259-283): cpCollide wants a.type <= b.type; swap back afterwards
 				bool swapped = (a.type > b.type);

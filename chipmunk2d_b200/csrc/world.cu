@@ -157,6 +157,10 @@ struct cpb200_world {
 	unsigned long long graph_last_sig[2];  // signature of the previous step of the same parity (a graph is captured when it repeats;
 	                                       // the radix sort's ping-pong buffers make odd and even steps differ)
 	bool graph_enabled;
+	// per-step host I/O bound to the world (cpb200_world_bind_io): page-locked host buffers, device staging, a side stream
+	const double *io_src; double *io_sink;
+	double *d_io_force, *d_io_pos, *d_io_vel; int io_cap;
+	cudaStream_t stream_io; cudaEvent_t ev_io_begin, ev_io_forces, ev_io_pos, ev_io_join;
 	char graph_error[384];              // why capturing failed (the world then keeps launching kernel by kernel)
 	unsigned long long graph_replays, graph_captures;
 	double step_dt, step_dt_coef; int step_iterations;
@@ -305,6 +309,10 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	w->mid_solve = false; w->solver_variant = 0; w->last_solver_path = 0;
 	memset(w->graph, 0, sizeof(w->graph)); w->graph_gen = 1; w->graph_last_sig[0] = w->graph_last_sig[1] = 0; w->graph_replays = w->graph_captures = 0;
 	w->graph_enabled = (getenv("CPB200_NO_GRAPH") == NULL); w->graph_error[0] = 0;
+	w->io_src = NULL; w->io_sink = NULL; w->d_io_force = w->d_io_pos = w->d_io_vel = NULL; w->io_cap = 0;
+	cudaStreamCreate(&w->stream_io);
+	cudaEventCreateWithFlags(&w->ev_io_begin, cudaEventDisableTiming); cudaEventCreateWithFlags(&w->ev_io_forces, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&w->ev_io_pos, cudaEventDisableTiming); cudaEventCreateWithFlags(&w->ev_io_join, cudaEventDisableTiming);
 	w->mid_step = false; w->step_dt = 0.0; w->step_dt_coef = 0.0; w->step_iterations = 0;
 	w->sl_dirty = true; w->sl_ok = false; w->sl_disabled = (getenv("CPB200_NO_SPACE_LOCAL") != NULL); w->sl_max_nbody = 0;
 	memset(&w->SL, 0, sizeof(w->SL)); w->sl_tmp = NULL;
@@ -336,6 +344,10 @@ extern "C" void cpb200_world_destroy(cpb200_world *w)
 	if(w->d_nocollide) cudaFree(w->d_nocollide);
 	for(int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(w->ev[i]);
 	cudaStreamDestroy(w->stream2); cudaEventDestroy(w->ev_fork); cudaEventDestroy(w->ev_join);
+	cudaStreamDestroy(w->stream_io); cudaEventDestroy(w->ev_io_begin); cudaEventDestroy(w->ev_io_forces); cudaEventDestroy(w->ev_io_pos); cudaEventDestroy(w->ev_io_join);
+	if(w->d_io_force) cudaFree(w->d_io_force);
+	if(w->d_io_pos) cudaFree(w->d_io_pos);
+	if(w->d_io_vel) cudaFree(w->d_io_vel);
 	cudaStreamDestroy(w->stream);
 	delete w;
 }
@@ -454,6 +466,7 @@ extern "C" int cpb200_world_set_bodies(cpb200_world *w, int n, const cpb200_body
 	DA(w->gK, w->K.jcount, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.jstart, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.jcursor, CPB_MAX_COLOURS + 1);
 	DA(w->gK, w->K.wl_n, CPB_MAX_COLOUR_ROUNDS + 2); DA(w->gK, w->K.prof, 8);
 	w->hints_valid = false; // body types / masses may have changed: colour from scratch once
+	w->io_src = NULL; w->io_sink = NULL;   // bound host buffers were sized for the old body count: bind again
 	w->body_space.clear(); w->sl_dirty = true;
 	w->gI.release();
 	DA(w->gI, w->I.parent, n); DA(w->gI, w->I.wake, n); DA(w->gI, w->I.comp_active, n); DA(w->gI, w->I.woken, n); DA(w->gI, w->I.touch, n); DA(w->gI, w->I.any_woken, 4);
@@ -520,6 +533,59 @@ extern "C" int cpb200_world_touch_bodies(cpb200_world *w, int n, const int32_t *
 	CPB_CHECK(cudaMemcpyAsync(w->d_stage, indices, bytes, cudaMemcpyHostToDevice, w->stream));
 	LAUNCH(k_touch_bodies, grid_for(n, 256), 256, w->stream, w->B, (const int *)w->d_stage, n);
 	return world_sync(w);
+}
+
+// ---- per-step host I/O overlapped with the step (cpb200_world_bind_io) ----
+__global__ void k_pack_pos(DBodies B, double *__restrict__ dst)
+{
+	int i = CPB_TID;
+	if(i >= B.n) return;
+	V2 p = B.pos[i];
+	dst[3*(size_t)i] = p.x; dst[3*(size_t)i + 1] = p.y; dst[3*(size_t)i + 2] = B.ang[i];
+}
+
+__global__ void k_pack_vel(DBodies B, double *__restrict__ dst)
+{
+	int i = CPB_TID;
+	if(i >= B.n) return;
+	double4 V = B.V[i];
+	dst[3*(size_t)i] = V.x; dst[3*(size_t)i + 1] = V.y; dst[3*(size_t)i + 2] = V.z;
+}
+
+static bool host_ptr_is_pinned(const void *p)
+{
+#ifdef CPB_EMU
+	return true;
+#else
+	cudaPointerAttributes a;
+	if(cudaPointerGetAttributes(&a, p) != cudaSuccess){ cudaGetLastError(); return false; }
+	return a.type == cudaMemoryTypeHost;
+#endif
+}
+
+extern "C" int cpb200_world_bind_io(cpb200_world *w, const double *forces_fxyt, double *state_out)
+{
+	if(!w){ cpb_set_error("null world"); return -1; }
+	if(w->mid_step || w->mid_solve){ cpb_set_error("cpb200_world_bind_io inside a split step"); return -1; }
+	cudaSetDevice(w->device);
+	if(world_sync(w)) return -1;
+	if((forces_fxyt && !host_ptr_is_pinned(forces_fxyt)) || (state_out && !host_ptr_is_pinned(state_out))){
+		cpb_set_error("cpb200_world_bind_io needs page-locked host buffers (cpb200_host_alloc): the copies run beside the step's kernels");
+		return -1;
+	}
+	if((forces_fxyt || state_out) && w->io_cap < w->B.n){
+		if(w->d_io_force) cudaFree(w->d_io_force);
+		if(w->d_io_pos) cudaFree(w->d_io_pos);
+		if(w->d_io_vel) cudaFree(w->d_io_vel);
+		w->d_io_force = w->d_io_pos = w->d_io_vel = NULL; w->io_cap = 0;
+		void *p = NULL; size_t bytes = sizeof(double)*3*(size_t)std::max(w->B.n, 1);
+		CPB_CHECK(cudaMalloc(&p, bytes)); w->d_io_force = (double *)p;
+		CPB_CHECK(cudaMalloc(&p, bytes)); w->d_io_pos = (double *)p;
+		CPB_CHECK(cudaMalloc(&p, bytes)); w->d_io_vel = (double *)p;
+		w->io_cap = w->B.n;
+	}
+	w->io_src = forces_fxyt; w->io_sink = state_out;
+	return 0;
 }
 
 extern "C" int cpb200_world_reserve(cpb200_world *w, int max_pairs, int max_arbiters)
@@ -951,7 +1017,22 @@ static int step_phase_a(cpb200_world *w, double dt)
 	const int wide = w->sm_count*8;
 
 	STAGE_BEGIN(w);
+	const bool io = ((w->io_src || w->io_sink) && nb > 0 && w->io_cap >= nb);
+	if(io){
+		// host I/O of this step on a side stream: the forces travel while the collision phase runs (K9 consumes them),
+		// the new positions -- final after K1 -- travel while the rest of the step runs
+		CPB_CHECK(cudaEventRecord(w->ev_io_begin, st)); CPB_CHECK(cudaStreamWaitEvent(w->stream_io, w->ev_io_begin, 0));
+		if(w->io_src){
+			CPB_CHECK(cudaMemcpyAsync(w->d_io_force, w->io_src, sizeof(double)*3*(size_t)nb, cudaMemcpyHostToDevice, w->stream_io));
+			CPB_CHECK(cudaEventRecord(w->ev_io_forces, w->stream_io));
+		}
+	}
 	if(nb) LAUNCH(k_integrate_pos, grid_for(nb, 256), 256, st, B, dt);
+	if(io && w->io_sink){
+		LAUNCH(k_pack_pos, grid_for(nb, 256), 256, st, B, w->d_io_pos);
+		CPB_CHECK(cudaEventRecord(w->ev_io_pos, st)); CPB_CHECK(cudaStreamWaitEvent(w->stream_io, w->ev_io_pos, 0));
+		CPB_CHECK(cudaMemcpyAsync(w->io_sink, w->d_io_pos, sizeof(double)*3*(size_t)nb, cudaMemcpyDeviceToHost, w->stream_io));
+	}
 	STAGE_END(w, ST_INTEGRATE_POS);
 	if(ns) LAUNCH(k_shape_cache, grid_for(ns, 128), 128, st, S, B, 0);
 	STAGE_END(w, ST_SHAPE_CACHE);
@@ -1061,6 +1142,10 @@ static int step_phase_b1(cpb200_world *w)
 	STAGE_END(w, ST_PRESTEP);
 
 	// K9
+	if(w->io_src && nb > 0 && w->io_cap >= nb){
+		CPB_CHECK(cudaStreamWaitEvent(st, w->ev_io_forces, 0));
+		LAUNCH(k_set_forces, grid_for(nb, 256), 256, st, B, (const double *)w->d_io_force, 0, nb);
+	}
 	if(nb) LAUNCH(k_integrate_vel, grid_for(nb, 256), 256, st, B, (const DSpace *)w->d_spaces, dt, w->K.claim, w->K.bmask);
 	STAGE_END(w, ST_INTEGRATE_VEL);
 	w->mid_solve = true;
@@ -1204,6 +1289,13 @@ static int step_phase_b2(cpb200_world *w)
 	}
 	STAGE_END(w, ST_SOLVE);
 	LAUNCH(k_finish_step, 1, 32, st, w->C, (const int *)w->P.count);
+	if((w->io_src || w->io_sink) && nb > 0 && w->io_cap >= nb){
+		if(w->io_sink){
+			LAUNCH(k_pack_vel, grid_for(nb, 256), 256, st, B, w->d_io_vel);
+			CPB_CHECK(cudaMemcpyAsync(w->io_sink + 3*(size_t)nb, w->d_io_vel, sizeof(double)*3*(size_t)nb, cudaMemcpyDeviceToHost, st));
+		}
+		CPB_CHECK(cudaEventRecord(w->ev_io_join, w->stream_io)); CPB_CHECK(cudaStreamWaitEvent(st, w->ev_io_join, 0));
+	}
 
 	w->steps++;
 	if(w->profiling){
@@ -1237,6 +1329,7 @@ static unsigned long long step_signature(cpb200_world *w, double dt, int iterati
 	// second one; no step reads the previous step's keys, so a replayed graph may use them in either role: hash the pair)
 	h = sig_ptr(h, std::min((const void *)w->bvh.keys, (const void *)w->keys_b)); h = sig_ptr(h, std::max((const void *)w->bvh.keys, (const void *)w->keys_b)); h = sig_ptr(h, w->K.wl[0]); h = sig_ptr(h, w->d_nocollide); h = sig_ptr(h, w->SL.start); h = sig_ptr(h, w->I.parent);
 	h = sig_mix(h, (unsigned long long)w->n_nocollide);
+	h = sig_ptr(h, w->io_src); h = sig_ptr(h, w->io_sink); h = sig_ptr(h, w->d_io_pos);
 	h = sig_mix(h, (unsigned long long)((w->hints_valid && !w->no_hints) ? 1 : 0));
 	h = sig_mix(h, (unsigned long long)(w->any_sleep_enabled ? 1 : 0));
 	h = sig_mix(h, (unsigned long long)plan.iter_blocks);

@@ -126,6 +126,7 @@ def load_engine(path=None):
     lib.cpb200_world_get_solver_profile.argtypes = [vp, vp]
     lib.cpb200_world_step_collide.argtypes = [vp, cd]
     lib.cpb200_world_set_graph.argtypes = [vp, ci]
+    lib.cpb200_world_bind_io.argtypes = [vp, vp, vp]
     lib.cpb200_world_get_graph_stats.argtypes = [vp, vp]
     lib.cpb200_world_graph_error.restype = C.c_char_p
     lib.cpb200_world_graph_error.argtypes = [vp]
@@ -286,6 +287,13 @@ class World:
         self._pinned.append(ptr)
         buf = (C.c_char * nbytes).from_address(ptr)
         return np.frombuffer(buf, dtype=dtype, count=int(n))
+
+    def bind_io(self, forces=None, state_out=None):
+        """Bind page-locked per-step I/O buffers (pinned_array): forces[n][3] in, state_out[2][n][3] out, every step."""
+        fp = forces.ctypes.data if forces is not None else None
+        sp = state_out.ctypes.data if state_out is not None else None
+        self._ck(self.lib.cpb200_world_bind_io(self.w, fp, sp))
+        self._io = (forces, state_out)
 
     def bodies_into(self, out):
         """Read-back into a caller-owned BODY_STATE array (no allocation in the step loop)."""

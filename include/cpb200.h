@@ -200,6 +200,16 @@ CPB200_API int cpb200_world_reserve(cpb200_world *w, int max_pairs, int max_arbi
 /* cpSpaceStep (cpSpaceStep.c:335-445) for every space of the world.  Asynchronous:
  * returns once the kernels are enqueued on the world's stream. */
 CPB200_API int cpb200_world_step(cpb200_world *w, double dt);
+/* Per-step host I/O bound to the world and overlapped with the step.  While bound, EVERY step (cpb200_world_step or the
+ * split step) reads the bodies' forces from forces_fxyt[n_bodies][3] (f.x f.y torque; what cpBodySetForce / SetTorque
+ * leave in the cpBody, cpBody.c:420-424) and writes state_out[2][n_bodies][3] = (p.x p.y a) of every body, then
+ * (v.x v.y w) of every body.  The copies run on a side stream: the forces are only consumed by the velocity update
+ * (cpBodyUpdateVelocity, cpSpaceStep.c:398-404), so they travel during the collision phase; positions are final after
+ * cpBodyUpdatePosition (cpSpaceStep.c:362-367), so they travel during the rest of the step; only the velocities are
+ * copied after the solver.  Both buffers must be page-locked (cpb200_host_alloc); either may be NULL; (NULL, NULL)
+ * unbinds, and so does cpb200_world_set_bodies.  The caller may write forces_fxyt and read state_out between
+ * cpb200_world_sync and the next step. */
+CPB200_API int cpb200_world_bind_io(cpb200_world *w, const double *forces_fxyt, double *state_out);
 /* A step whose launch sequence repeats (same dt, no upload in between, no profiling) is captured into a CUDA graph on
  * its second occurrence and replayed with a single launch afterwards.  Results are identical either way
  * (tests/test_gpu_graph.py); the hook turns the replay off (0) or on (1; default unless CPB200_NO_GRAPH is set).

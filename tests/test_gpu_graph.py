@@ -58,3 +58,33 @@ def test_graph_survives_dt_changes_uploads_and_split_steps():
         w.sync()
     assert same(a, b)
     assert a.graph_stats()["replays"] > 100
+
+
+@pytest.mark.parametrize("name", ["ComplexTerrainHexagons_1000", "pile20k", "batch8"])
+def test_bound_io_equals_blocking_uploads_and_downloads(name):
+    """cpb200_world_bind_io (forces in / state out on a side stream, overlapped with the step, graph-captured) against
+    cpb200_world_set_body_forces + cpb200_world_get_bodies around every step: identical state, every step."""
+    scenes = {"batch8": lambda: batched_demo_scenes(8), "pile20k": lambda: [circle_pile(20000, dense=True, sleep=0.5)]}.get(name, lambda: [golden_scene(name)])()
+    a, b = World(len(scenes)), World(len(scenes))
+    a.load_scenes(scenes); b.load_scenes(scenes)
+    n = a.n_bodies
+    forces = a.pinned_array(3 * n, np.float64).reshape(n, 3)
+    sink = a.pinned_array(6 * n, np.float64).reshape(2, n, 3)
+    a.bind_io(forces, sink)
+    rng = np.random.default_rng(5)
+    dt = scenes[0].dt
+    for s in range(120):
+        f = rng.normal(size=(n, 3)) * 30.0
+        forces[:] = f
+        a.step(dt); a.sync()
+        b.set_body_forces(0, f); b.step(dt); b.sync()
+        if s % 7 == 0 or s > 110:
+            wb = b.bodies()
+            assert np.array_equal(sink[0][:, 0:2], wb["p"]) and np.array_equal(sink[0][:, 2], wb["a"]), (name, s)
+            assert np.array_equal(sink[1][:, 0:2], wb["v"]) and np.array_equal(sink[1][:, 2], wb["w"]), (name, s)
+    assert a.graph_stats()["replays"] > 60, a.graph_stats()
+    a.bind_io(None, None)
+    a.step(dt, 3); b.step(dt, 3); a.sync(); b.sync()
+    assert np.array_equal(a.bodies()["p"], b.bodies()["p"])
+    with pytest.raises(Exception):
+        a.bind_io(np.zeros((n, 3)), None)          # pageable memory is refused
