@@ -126,6 +126,11 @@ struct cpb200_world {
 	DCounters *C;
 	DCounters *hC;          // pinned
 	int cap_pairs, cap_arbs;
+	// object arrays are allocated with slack so that cpb200_world_append_* can add objects in place (f4)
+	int cap_bodies, cap_shapes, cap_verts, cap_joints;
+	std::vector<uint32_t> space_base;     // lowest shape hashid of every space (hlocal = hashid - base)
+	std::vector<int> joint_base;          // first joint index of every space (colouring priorities)
+	std::vector<uint64_t> nocollide_keys; // sorted body pairs joined by a constraint with collideBodies == 0
 	int user_cap_pairs, user_cap_arbs;
 
 	uint32_t stamp;
@@ -292,6 +297,7 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	w->joints_dt = 0.0; w->d_nocollide = NULL; w->n_nocollide = 0;
 	w->cur = 0; w->keys_b = NULL; w->vals_b = NULL; w->sort_tmp = NULL;
 	w->cap_pairs = 0; w->cap_arbs = 0; w->user_cap_pairs = 0; w->user_cap_arbs = 0;
+	w->cap_bodies = w->cap_shapes = w->cap_verts = w->cap_joints = 0;
 	w->stamp = 0; w->curr_dt = 0.0; w->steps = 0; w->cache_dirty = true; w->any_sleep_enabled = false;
 	w->solver_mode = 0; w->d_order = NULL; w->order_cap = 0; w->d_user_order = NULL; w->n_user_order = 0; w->user_order_cap = 0;
 	w->d_joint_order = NULL; w->n_joint_order = 0; w->joint_order_cap = 0;
@@ -456,12 +462,14 @@ extern "C" int cpb200_world_set_bodies(cpb200_world *w, int n, const cpb200_body
 	w->gB.release();
 	DBodies &B = w->B;
 	B.n = n;
-	DA(w->gB, B.pos, n); DA(w->gB, B.ang, n); DA(w->gB, B.rot, n); DA(w->gB, B.txy, n); DA(w->gB, B.cog, n);
-	DA(w->gB, B.V, n); DA(w->gB, B.VB, n); DA(w->gB, B.MI, n); DA(w->gB, B.M, n); DA(w->gB, B.force, n);
-	DA(w->gB, B.torque, n); DA(w->gB, B.idle, n); DA(w->gB, B.type, n); DA(w->gB, B.space, n);
-	DA(w->gB, B.sleeping, n); DA(w->gB, B.sgroup, n);
+	const int cap = n + n/4 + 256;
+	w->cap_bodies = cap;
+	DA(w->gB, B.pos, cap); DA(w->gB, B.ang, cap); DA(w->gB, B.rot, cap); DA(w->gB, B.txy, cap); DA(w->gB, B.cog, cap);
+	DA(w->gB, B.V, cap); DA(w->gB, B.VB, cap); DA(w->gB, B.MI, cap); DA(w->gB, B.M, cap); DA(w->gB, B.force, cap);
+	DA(w->gB, B.torque, cap); DA(w->gB, B.idle, cap); DA(w->gB, B.type, cap); DA(w->gB, B.space, cap);
+	DA(w->gB, B.sleeping, cap); DA(w->gB, B.sgroup, cap);
 	w->gK.release();
-	DA(w->gK, w->K.claim, n); DA(w->gK, w->K.bmask, n);
+	DA(w->gK, w->K.claim, cap); DA(w->gK, w->K.bmask, cap);
 	DA(w->gK, w->K.ccount, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.cstart, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.ccursor, CPB_MAX_COLOURS + 1);
 	DA(w->gK, w->K.jcount, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.jstart, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.jcursor, CPB_MAX_COLOURS + 1);
 	DA(w->gK, w->K.wl_n, CPB_MAX_COLOUR_ROUNDS + 2); DA(w->gK, w->K.prof, 8);
@@ -469,15 +477,40 @@ extern "C" int cpb200_world_set_bodies(cpb200_world *w, int n, const cpb200_body
 	w->io_src = NULL; w->io_sink = NULL;   // bound host buffers were sized for the old body count: bind again
 	w->body_space.clear(); w->sl_dirty = true;
 	w->gI.release();
-	DA(w->gI, w->I.parent, n); DA(w->gI, w->I.wake, n); DA(w->gI, w->I.comp_active, n); DA(w->gI, w->I.woken, n); DA(w->gI, w->I.touch, n); DA(w->gI, w->I.any_woken, 4);
+	DA(w->gI, w->I.parent, cap); DA(w->gI, w->I.wake, cap); DA(w->gI, w->I.comp_active, cap); DA(w->gI, w->I.woken, cap); DA(w->gI, w->I.touch, cap); DA(w->gI, w->I.any_woken, 4);
 	int r = cpb200_world_update_bodies(w, 0, n, bodies);
 	w->cache_dirty = true;
 	return r;
 }
 
+static int upload_body_range(cpb200_world *w, int first, int n, const cpb200_body_desc *bodies, bool invalidate_hints);
+
 extern "C" int cpb200_world_update_bodies(cpb200_world *w, int first, int n, const cpb200_body_desc *bodies)
 {
 	if(!w || first < 0 || n < 0 || first + n > w->B.n){ cpb_set_error("body range out of bounds"); return -1; }
+	return upload_body_range(w, first, n, bodies, true);
+}
+
+/* f4: bodies appended behind the existing ones; nothing that is already on the device moves or is re-uploaded.
+ * Returns 1 (and changes nothing) when the arrays' slack is used up: the caller then re-uploads with cpb200_world_set_bodies,
+ * which allocates new slack. */
+extern "C" int cpb200_world_append_bodies(cpb200_world *w, int n, const cpb200_body_desc *bodies)
+{
+	if(!w || n < 0 || (n > 0 && !bodies)){ cpb_set_error("bad arguments"); return -1; }
+	if(n == 0) return 0;
+	if(w->mid_step || w->mid_solve){ cpb_set_error("structural edit inside a split step"); return -1; }
+	if(w->B.n + n > w->cap_bodies || (int)w->body_space.size() != w->B.n) return 1;
+	const int first = w->B.n;
+	w->B.n += n;
+	w->body_space.resize((size_t)w->B.n, -1);
+	w->io_src = NULL; w->io_sink = NULL;
+	int rc = upload_body_range(w, first, n, bodies, false);
+	if(rc){ w->B.n = first; w->body_space.resize((size_t)first); }
+	return rc;
+}
+
+static int upload_body_range(cpb200_world *w, int first, int n, const cpb200_body_desc *bodies, bool invalidate_hints)
+{
 	if(n == 0) return 0;
 	cudaSetDevice(w->device);
 	size_t bytes = sizeof(cpb200_body_desc)*(size_t)n;
@@ -494,8 +527,8 @@ extern "C" int cpb200_world_update_bodies(cpb200_world *w, int first, int n, con
 	CPB_CHECK(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
 	w->cache_dirty = true;
 	// a body may have changed between dynamic and static / kinematic: two constraints that kept last step's colour
-	// could then share a body that is now written -- colour from scratch once
-	w->hints_valid = false;
+	// could then share a body that is now written -- colour from scratch once (appended bodies have no constraints yet)
+	if(invalidate_hints) w->hints_valid = false;
 	if(world_sync(w)) return -1;
 	if(h_bad){ cpb_set_error("a body names a space index outside [0, %d)", w->n_spaces); return -1; }
 	return 0;
@@ -711,12 +744,15 @@ extern "C" int cpb200_world_set_shapes(cpb200_world *w, int n, const cpb200_shap
 	w->gS.release();
 	DShapes &S = w->S;
 	S.n = n; S.nv = n_verts;
-	DA(w->gS, S.type, n); DA(w->gS, S.body, n); DA(w->gS, S.hashid, n); DA(w->gS, S.hlocal, n); DA(w->gS, S.sensor, n); DA(w->gS, S.cat, n); DA(w->gS, S.mask, n);
-	DA(w->gS, S.group, n); DA(w->gS, S.ctype, n); DA(w->gS, S.e, n); DA(w->gS, S.u, n); DA(w->gS, S.r, n); DA(w->gS, S.surfv, n);
-	DA(w->gS, S.la, n); DA(w->gS, S.lb, n); DA(w->gS, S.ln, n); DA(w->gS, S.atan, n); DA(w->gS, S.btan, n);
-	DA(w->gS, S.pcount, n); DA(w->gS, S.poff, n); DA(w->gS, S.lpv, n_verts); DA(w->gS, S.lpn, n_verts);
-	DA(w->gS, S.mat, n); DA(w->gS, S.circ, 2*(size_t)n); DA(w->gS, S.ids, n); DA(w->gS, S.filt, n);
-	DA(w->gS, S.wa, n); DA(w->gS, S.wb, n); DA(w->gS, S.wn, n); DA(w->gS, S.wpv, n_verts); DA(w->gS, S.wpn, n_verts); DA(w->gS, S.bb, n);
+	const int cap = n + n/4 + 256, capv = n_verts + n_verts/4 + 1024;
+	w->cap_shapes = cap; w->cap_verts = capv;
+	w->space_base = space_base;
+	DA(w->gS, S.type, cap); DA(w->gS, S.body, cap); DA(w->gS, S.hashid, cap); DA(w->gS, S.hlocal, cap); DA(w->gS, S.sensor, cap); DA(w->gS, S.cat, cap); DA(w->gS, S.mask, cap);
+	DA(w->gS, S.group, cap); DA(w->gS, S.ctype, cap); DA(w->gS, S.e, cap); DA(w->gS, S.u, cap); DA(w->gS, S.r, cap); DA(w->gS, S.surfv, cap);
+	DA(w->gS, S.la, cap); DA(w->gS, S.lb, cap); DA(w->gS, S.ln, cap); DA(w->gS, S.atan, cap); DA(w->gS, S.btan, cap);
+	DA(w->gS, S.pcount, cap); DA(w->gS, S.poff, cap); DA(w->gS, S.lpv, capv); DA(w->gS, S.lpn, capv);
+	DA(w->gS, S.mat, cap); DA(w->gS, S.circ, 2*(size_t)cap); DA(w->gS, S.ids, cap); DA(w->gS, S.filt, cap);
+	DA(w->gS, S.wa, cap); DA(w->gS, S.wb, cap); DA(w->gS, S.wn, cap); DA(w->gS, S.wpv, capv); DA(w->gS, S.wpn, capv); DA(w->gS, S.bb, cap);
 	if(upload(w, S.type, type) || upload(w, S.body, body) || upload(w, S.hashid, hashid) || upload(w, S.hlocal, hlocal) || upload(w, S.sensor, sensor) || upload(w, S.cat, cat) ||
 	   upload(w, S.mask, mask) || upload(w, S.group, group) || upload(w, S.ctype, ctype) || upload(w, S.e, e) || upload(w, S.u, u) || upload(w, S.r, r) ||
 	   upload(w, S.surfv, surfv) || upload(w, S.la, la) || upload(w, S.lb, lb) || upload(w, S.ln, ln) || upload(w, S.atan, atan_) || upload(w, S.btan, btan_) ||
@@ -724,19 +760,19 @@ extern "C" int cpb200_world_set_shapes(cpb200_world *w, int n, const cpb200_shap
 
 	w->shape_body = body; w->sl_dirty = true;
 
-	// broadphase scratch
+	// broadphase scratch (sized for the capacity: appended shapes need no reallocation)
 	w->gV.release();
 	DBvh &T = w->bvh;
 	T.n = n;
-	int nn = (n > 0 ? n : 1);
+	int nn = cap;
 	DA(w->gV, T.keys, nn); DA(w->gV, T.leaf_shape, nn); DA(w->gV, T.left, nn); DA(w->gV, T.right, nn); DA(w->gV, T.parent, 2*nn);
 	DA(w->gV, T.nbb, 2*nn); DA(w->gV, T.nsp, 2*nn); DA(w->gV, T.flags, nn); DA(w->gV, T.bounds, 4);
 	DA(w->gV, T.nskip, 2*nn); DA(w->gV, T.cbox, 2*nn); DA(w->gV, T.cinfo, nn); DA(w->gV, T.cspace, nn);
 	DA(w->gV, w->keys_b, nn); DA(w->gV, w->vals_b, nn);
 	DA(w->gV, w->sort_tmp, cpb_sort_tmp_elems(nn) + 16);
 
-	int want_pairs = std::max(w->user_cap_pairs, 16*n + 1024);
-	int want_arbs = std::max(w->user_cap_arbs, 8*n + 1024);
+	int want_pairs = std::max(w->user_cap_pairs, 16*cap + 1024);
+	int want_arbs = std::max(w->user_cap_arbs, 8*cap + 1024);
 	if(want_pairs > w->cap_pairs){ if(alloc_pairs(w, want_pairs)) return -1; }
 	if(want_arbs > w->cap_arbs){
 		// growing drops the cached arbiters (warm-start data); callers that care reserve up front
@@ -768,6 +804,100 @@ extern "C" int cpb200_world_set_shapes(cpb200_world *w, int n, const cpb200_shap
 	w->cache_dirty = true;
 	w->hints_valid = false;
 	return world_sync(w);
+}
+
+/* f4: shapes appended behind the existing ones.  vert_offset of the new polygons counts from the first appended vertex.
+ * Returns 1 (nothing changed) when the slack of the shape / vertex arrays is used up or a new hashid lies below its
+ * space's lowest one: the caller then re-uploads everything with cpb200_world_set_shapes. */
+extern "C" int cpb200_world_append_shapes(cpb200_world *w, int n, const cpb200_shape_desc *shapes, int n_verts, const double *verts_xy)
+{
+	if(!w || n < 0 || n_verts < 0 || (n > 0 && !shapes)){ cpb_set_error("bad arguments"); return -1; }
+	if(n == 0) return 0;
+	if(w->mid_step || w->mid_solve){ cpb_set_error("structural edit inside a split step"); return -1; }
+	DShapes &S = w->S;
+	if(S.n + n > w->cap_shapes || S.nv + n_verts > w->cap_verts || (int)w->shape_body.size() != S.n || (int)w->body_space.size() != w->B.n ||
+	   (int)w->space_base.size() != w->n_spaces) return 1;
+	cudaSetDevice(w->device);
+	const size_t N = (size_t)n, NV = (size_t)n_verts;
+	const int s0 = S.n, v0 = S.nv;
+	std::vector<int> type(N), body(N), sensor(N), pcount(N), poff(N);
+	std::vector<uint32_t> hashid(N), cat(N), mask(N), hlocal(N);
+	std::vector<uint64_t> group(N), ctype(N);
+	std::vector<double> e(N), u(N), r(N);
+	std::vector<V2> surfv(N), la(N), lb(N), ln(N), atan_(N), btan_(N), lpv(NV), lpn(NV);
+	std::vector<double4> mat(N), filt(N); std::vector<uint2> ids(N);
+	std::vector<uint32_t> base = w->space_base;
+	for(size_t i = 0; i < N; i++){
+		const cpb200_shape_desc &d = shapes[i];
+		if(d.body < 0 || d.body >= w->B.n){ cpb_set_error("appended shape %zu: body index %d out of range (append bodies first)", i, d.body); return -1; }
+		type[i] = d.type; body[i] = d.body; sensor[i] = d.sensor; hashid[i] = d.hashid; cat[i] = d.categories; mask[i] = d.mask;
+		group[i] = d.group; ctype[i] = d.collision_type; e[i] = d.e; u[i] = d.u; r[i] = d.r;
+		surfv[i] = v2(d.surface_v[0], d.surface_v[1]);
+		la[i] = v2(d.a[0], d.a[1]); lb[i] = v2(d.b[0], d.b[1]);
+		atan_[i] = v2(d.a_tangent[0], d.a_tangent[1]); btan_[i] = v2(d.b_tangent[0], d.b_tangent[1]);
+		ln[i] = v2(0, 0); pcount[i] = 0; poff[i] = 0;
+		if(d.type == CPB200_SHAPE_SEGMENT) ln[i] = vrperp(vnormalize(vsub(lb[i], la[i])));          // cpShape.c:498
+		else if(d.type == CPB200_SHAPE_POLY){
+			if(d.n_verts < 1 || d.vert_offset < 0 || d.vert_offset + d.n_verts > n_verts){ cpb_set_error("appended shape %zu: vertex range out of bounds", i); return -1; }
+			if(d.n_verts > 255){ cpb_set_error("appended shape %zu: polygons are limited to 255 vertices", i); return -1; }
+			pcount[i] = d.n_verts; poff[i] = v0 + d.vert_offset;
+			for(int k = 0; k < d.n_verts; k++){                                                        // cpPolyShape.c:147-165
+				const double *va = verts_xy + 2*(size_t)(d.vert_offset + (k - 1 + d.n_verts)%d.n_verts);
+				const double *vb = verts_xy + 2*(size_t)(d.vert_offset + k);
+				V2 a = v2(va[0], va[1]), b = v2(vb[0], vb[1]);
+				lpv[(size_t)d.vert_offset + k] = b;
+				lpn[(size_t)d.vert_offset + k] = vnormalize(vrperp(vsub(b, a)));
+			}
+		}
+		const int sp = w->body_space[(size_t)d.body];
+		if(sp < 0 || sp >= w->n_spaces) return 1;
+		uint32_t &sb = base[(size_t)sp];
+		if(sb == 0xffffffffu) sb = hashid[i];
+		if(hashid[i] < sb) return 1;          // would shift every hlocal of the space
+		hlocal[i] = hashid[i] - sb;
+		const unsigned long long x = (unsigned long long)(uint32_t)body[i] | ((unsigned long long)(uint32_t)type[i] << 32);
+		const unsigned long long y = (unsigned long long)cat[i] | ((unsigned long long)mask[i] << 32), z = group[i];
+		memcpy(&filt[i].x, &x, 8); memcpy(&filt[i].y, &y, 8); memcpy(&filt[i].z, &z, 8); filt[i].w = 0.0;
+		mat[i] = make_double4(e[i], u[i], surfv[i].x, surfv[i].y); ids[i].x = hashid[i]; ids[i].y = hlocal[i];
+	}
+	if(world_sync(w)) return -1;
+	if(upload(w, S.type + s0, type) || upload(w, S.body + s0, body) || upload(w, S.hashid + s0, hashid) || upload(w, S.hlocal + s0, hlocal) || upload(w, S.sensor + s0, sensor) ||
+	   upload(w, S.cat + s0, cat) || upload(w, S.mask + s0, mask) || upload(w, S.group + s0, group) || upload(w, S.ctype + s0, ctype) || upload(w, S.e + s0, e) || upload(w, S.u + s0, u) ||
+	   upload(w, S.r + s0, r) || upload(w, S.surfv + s0, surfv) || upload(w, S.la + s0, la) || upload(w, S.lb + s0, lb) || upload(w, S.ln + s0, ln) || upload(w, S.atan + s0, atan_) ||
+	   upload(w, S.btan + s0, btan_) || upload(w, S.mat + s0, mat) || upload(w, S.ids + s0, ids) || upload(w, S.filt + s0, filt) || upload(w, S.pcount + s0, pcount) ||
+	   upload(w, S.poff + s0, poff) || upload(w, S.lpv + v0, lpv) || upload(w, S.lpn + v0, lpn)) return -1;
+	w->space_base = base;
+	S.n += n; S.nv += n_verts;
+	w->bvh.n = S.n;
+	w->shape_body.insert(w->shape_body.end(), body.begin(), body.end());
+	w->sl_dirty = true;
+	w->cache_dirty = true;      // the world cache of the new shapes (and nothing else changes: same bodies, same transforms)
+	return 0;
+}
+
+// the device set of body pairs joined by a constraint with collideBodies == 0 (QueryRejectConstraint, cpSpaceStep.c:204-217)
+static int upload_nocollide(cpb200_world *w, const std::vector<uint64_t> &nocollide)
+{
+	if(w->d_nocollide){ cudaFree(w->d_nocollide); w->d_nocollide = NULL; }
+	w->n_nocollide = 0;   // = capacity - 1 of the device set (0: no pairs)
+	w->nocollide_keys = nocollide;
+	if(nocollide.empty()) return 0;
+	size_t capn = 16;
+	while(capn < 2*nocollide.size()) capn <<= 1;
+	std::vector<uint64_t> set(capn, 0ull);
+	for(uint64_t k : nocollide){
+		uint64_t key = k + 1ull;
+		size_t slot = (size_t)((uint32_t)mix64(key) & (uint32_t)(capn - 1));
+		while(set[slot] != 0ull) slot = (slot + 1) & (capn - 1);
+		set[slot] = key;
+	}
+	void *p = NULL;
+	CPB_CHECK(cudaMalloc(&p, sizeof(uint64_t)*capn));
+	w->d_nocollide = (uint64_t *)p;
+	w->n_nocollide = (int)(capn - 1);
+	CPB_CHECK(cudaMemcpyAsync(w->d_nocollide, set.data(), sizeof(uint64_t)*capn, cudaMemcpyHostToDevice, w->stream));
+	CPB_CHECK(cudaStreamSynchronize(w->stream));   // `set` is a local
+	return 0;
 }
 
 extern "C" int cpb200_world_set_joints(cpb200_world *w, int n, const cpb200_joint_desc *joints)
@@ -814,34 +944,78 @@ extern "C" int cpb200_world_set_joints(cpb200_world *w, int n, const cpb200_join
 	w->gJ.release();
 	DJoints &J = w->J;
 	J.n = n;
-	DA(w->gJ, J.type, n); DA(w->gJ, J.a, n); DA(w->gJ, J.b, n); DA(w->gJ, J.max_force, n); DA(w->gJ, J.max_bias, n); DA(w->gJ, J.bias_coef, n);
-	DA(w->gJ, J.anchor_a, n); DA(w->gJ, J.anchor_b, n); DA(w->gJ, J.prm, n);
-	DA(w->gJ, J.r1, n); DA(w->gJ, J.r2, n); DA(w->gJ, J.nrm, n); DA(w->gJ, J.nmass, n); DA(w->gJ, J.k, n); DA(w->gJ, J.bias, n); DA(w->gJ, J.acc, n);
-	DA(w->gJ, J.aux0, n); DA(w->gJ, J.aux1, n); DA(w->gJ, J.jspring, n); DA(w->gJ, J.colour, n); DA(w->gJ, J.row, n); DA(w->gJ, J.pri, n); DA(w->gJ, J.hint, n);
+	const int cap = n + n/4 + 256;
+	w->cap_joints = cap;
+	w->joint_base = joint_base;
+	DA(w->gJ, J.type, cap); DA(w->gJ, J.a, cap); DA(w->gJ, J.b, cap); DA(w->gJ, J.max_force, cap); DA(w->gJ, J.max_bias, cap); DA(w->gJ, J.bias_coef, cap);
+	DA(w->gJ, J.anchor_a, cap); DA(w->gJ, J.anchor_b, cap); DA(w->gJ, J.prm, cap);
+	DA(w->gJ, J.r1, cap); DA(w->gJ, J.r2, cap); DA(w->gJ, J.nrm, cap); DA(w->gJ, J.nmass, cap); DA(w->gJ, J.k, cap); DA(w->gJ, J.bias, cap); DA(w->gJ, J.acc, cap);
+	DA(w->gJ, J.aux0, cap); DA(w->gJ, J.aux1, cap); DA(w->gJ, J.jspring, cap); DA(w->gJ, J.colour, cap); DA(w->gJ, J.row, cap); DA(w->gJ, J.pri, cap); DA(w->gJ, J.hint, cap);
 	if(upload(w, J.type, type) || upload(w, J.a, a) || upload(w, J.b, b) || upload(w, J.max_force, max_force) || upload(w, J.max_bias, max_bias) ||
 	   upload(w, J.anchor_a, anchor_a) || upload(w, J.anchor_b, anchor_b) || upload(w, J.prm, prm) || upload(w, J.acc, acc) || upload(w, J.aux0, aux0) || upload(w, J.pri, jpri)) return -1;
-	if(w->d_nocollide){ cudaFree(w->d_nocollide); w->d_nocollide = NULL; }
-	w->n_nocollide = 0;   // = capacity - 1 of the device set (0: no pairs)
-	if(!nocollide.empty()){
-		size_t capn = 16;
-		while(capn < 2*nocollide.size()) capn <<= 1;
-		std::vector<uint64_t> set(capn, 0ull);
-		for(uint64_t k : nocollide){
-			uint64_t key = k + 1ull;
-			size_t slot = (size_t)((uint32_t)mix64(key) & (uint32_t)(capn - 1));
-			while(set[slot] != 0ull) slot = (slot + 1) & (capn - 1);
-			set[slot] = key;
-		}
-		void *p = NULL;
-		CPB_CHECK(cudaMalloc(&p, sizeof(uint64_t)*capn));
-		w->d_nocollide = (uint64_t *)p;
-		w->n_nocollide = (int)(capn - 1);
-		CPB_CHECK(cudaMemcpyAsync(w->d_nocollide, set.data(), sizeof(uint64_t)*capn, cudaMemcpyHostToDevice, w->stream));
-		CPB_CHECK(cudaStreamSynchronize(w->stream));   // `set` is a local
-	}
+	if(upload_nocollide(w, nocollide)) return -1;
 	w->joint_body = a; w->sl_dirty = true;
 	w->joints_dt = 0.0; // force bias_coef refresh
 	w->hints_valid = false;
+	return world_sync(w);
+}
+
+/* f4: joints appended behind the existing ones (their accumulated impulses start from joints[i].acc).  Returns 1 when
+ * the slack is used up: the caller then re-uploads with cpb200_world_set_joints. */
+extern "C" int cpb200_world_append_joints(cpb200_world *w, int n, const cpb200_joint_desc *joints)
+{
+	if(!w || n < 0 || (n > 0 && !joints)){ cpb_set_error("bad arguments"); return -1; }
+	if(n == 0) return 0;
+	if(w->mid_step || w->mid_solve){ cpb_set_error("structural edit inside a split step"); return -1; }
+	DJoints &J = w->J;
+	if(J.n + n > w->cap_joints || (int)w->joint_base.size() != w->n_spaces || (int)w->body_space.size() != w->B.n || w->joint_error_bias.size() != (size_t)J.n) return 1;
+	cudaSetDevice(w->device);
+	const size_t N = (size_t)n;
+	const int j0 = J.n;
+	std::vector<int> type(N), a(N), b(N), colour(N, -1), hint(N, -1);
+	std::vector<double> max_force(N), max_bias(N), aux0(N, 0.0);
+	std::vector<V2> anchor_a(N), anchor_b(N), acc(N);
+	std::vector<double4> prm(N);
+	std::vector<uint64_t> jpri(N), nocollide = w->nocollide_keys;
+	std::vector<int> base = w->joint_base;
+	bool new_nocollide = false;
+	for(size_t i = 0; i < N; i++){
+		const cpb200_joint_desc &d = joints[i];
+		if(d.a < 0 || d.a >= w->B.n || d.b < 0 || d.b >= w->B.n){ cpb_set_error("appended joint %zu: body index out of range", i); return -1; }
+		type[i] = d.type; a[i] = d.a; b[i] = d.b;
+		max_force[i] = d.max_force; max_bias[i] = d.max_bias;
+		anchor_a[i] = v2(d.anchor_a[0], d.anchor_a[1]); anchor_b[i] = v2(d.anchor_b[0], d.anchor_b[1]);
+		prm[i] = make_double4(d.prm[0], d.prm[1], d.prm[2], d.prm[3]);
+		acc[i] = v2(d.acc[0], d.acc[1]);
+		int &jb = base[(size_t)w->body_space[(size_t)d.a]];
+		if(jb < 0) jb = j0 + (int)i;
+		jpri[i] = mix64(0x9e3779b97f4a7c15ull ^ (uint64_t)(j0 + (int)i - jb)) >> 8;
+		if(d.type == CPB200_JOINT_RATCHET) aux0[i] = d.prm[0];
+		if(d.type == CPB200_JOINT_GROOVE){
+			V2 gn = vperp(vnormalize(vsub(v2(d.prm[0], d.prm[1]), anchor_a[i])));          // cpGrooveJoint.c:128
+			prm[i].z = gn.x; prm[i].w = gn.y;
+		}
+		if(!d.collide_bodies){
+			uint64_t lo = (uint64_t)(uint32_t)std::min(d.a, d.b), hi = (uint64_t)(uint32_t)std::max(d.a, d.b);
+			nocollide.push_back((lo << 32) | hi); new_nocollide = true;
+		}
+	}
+	if(world_sync(w)) return -1;
+	// (colour / hint = -1: a new joint has no colour to keep; the colouring puts it on its worklist)
+	if(upload(w, J.type + j0, type) || upload(w, J.a + j0, a) || upload(w, J.b + j0, b) || upload(w, J.max_force + j0, max_force) || upload(w, J.max_bias + j0, max_bias) ||
+	   upload(w, J.anchor_a + j0, anchor_a) || upload(w, J.anchor_b + j0, anchor_b) || upload(w, J.prm + j0, prm) || upload(w, J.acc + j0, acc) || upload(w, J.aux0 + j0, aux0) ||
+	   upload(w, J.pri + j0, jpri) || upload(w, J.colour + j0, colour) || upload(w, J.hint + j0, hint)) return -1;
+	if(new_nocollide){
+		std::sort(nocollide.begin(), nocollide.end());
+		nocollide.erase(std::unique(nocollide.begin(), nocollide.end()), nocollide.end());
+		if(upload_nocollide(w, nocollide)) return -1;
+	}
+	for(size_t i = 0; i < N; i++) w->joint_error_bias.push_back(joints[i].error_bias);
+	w->joint_base = base;
+	J.n += n;
+	w->joint_body.insert(w->joint_body.end(), a.begin(), a.end());
+	w->sl_dirty = true;
+	w->joints_dt = 0.0;   // bias coefficients of all joints are refreshed at the next step (one small upload)
 	return world_sync(w);
 }
 
@@ -1168,6 +1342,9 @@ static SolvePlan plan_solver(cpb200_world *w)
 	// size the persistent grid to the work: ~256 rows of one colour per CTA, never more than
 	// what is co-resident (148 SMs x 2 CTAs of 256 threads)
 	int est_cons = std::max(w->last_active, nb) + w->J.n;
+	// (rounded up to three significant bits: the constraint count moves a little every step, and a plan that followed it
+	// exactly would change the step graph's signature every time the host reads the counters back)
+	{ int sh = 0; while((est_cons >> sh) > 15) sh++; est_cons = (((est_cons >> sh) + (sh ? 1 : 0)) << sh); }
 	p.blocks = std::max(1, std::min(w->coop_blocks, cpb_div_up(est_cons + 1, 256)));
 	if(est_cons <= 4096) p.blocks = 1;   // small scenes: one CTA, colours separated by __syncthreads only
 	p.iter_blocks = std::max(1, std::min(w->sm_count*(w->solve_minb == 3 ? 3 : 2), cpb_div_up(est_cons + 1, 256)));

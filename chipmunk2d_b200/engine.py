@@ -127,6 +127,9 @@ def load_engine(path=None):
     lib.cpb200_world_step_collide.argtypes = [vp, cd]
     lib.cpb200_world_set_graph.argtypes = [vp, ci]
     lib.cpb200_world_bind_io.argtypes = [vp, vp, vp]
+    lib.cpb200_world_append_bodies.argtypes = [vp, ci, vp]
+    lib.cpb200_world_append_shapes.argtypes = [vp, ci, vp, ci, vp]
+    lib.cpb200_world_append_joints.argtypes = [vp, ci, vp]
     lib.cpb200_world_get_graph_stats.argtypes = [vp, vp]
     lib.cpb200_world_graph_error.restype = C.c_char_p
     lib.cpb200_world_graph_error.argtypes = [vp]
@@ -310,6 +313,29 @@ class World:
         jd = np.ascontiguousarray(jd, dtype=JOINT_DESC)
         self._ck(self.lib.cpb200_world_set_joints(self.w, len(jd), jd.ctypes.data))
         self.n_joints = len(jd)
+
+    def append_bodies(self, bd):
+        """Returns False when the arrays' slack is used up (nothing changed; re-upload with set_bodies)."""
+        bd = np.ascontiguousarray(bd, dtype=BODY_DESC)
+        rc = self._ck(self.lib.cpb200_world_append_bodies(self.w, len(bd), bd.ctypes.data))
+        if rc == 0:
+            self.n_bodies += len(bd)
+        return rc == 0
+
+    def append_shapes(self, sd, verts=None):
+        sd = np.ascontiguousarray(sd, dtype=SHAPE_DESC)
+        verts = np.ascontiguousarray(verts if verts is not None else np.zeros((0, 2)), dtype=np.float64).reshape(-1, 2)
+        rc = self._ck(self.lib.cpb200_world_append_shapes(self.w, len(sd), sd.ctypes.data, len(verts), verts.ctypes.data))
+        if rc == 0:
+            self.n_shapes += len(sd)
+        return rc == 0
+
+    def append_joints(self, jd):
+        jd = np.ascontiguousarray(jd, dtype=JOINT_DESC)
+        rc = self._ck(self.lib.cpb200_world_append_joints(self.w, len(jd), jd.ctypes.data))
+        if rc == 0:
+            self.n_joints += len(jd)
+        return rc == 0
 
     def reserve(self, max_pairs=0, max_arbiters=0):
         self._ck(self.lib.cpb200_world_reserve(self.w, int(max_pairs), int(max_arbiters)))

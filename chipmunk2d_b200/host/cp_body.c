@@ -117,7 +117,7 @@ cpBodySetType(cpBody *body, cpBodyType type)
 	if(body->space){
 		cpAssertSpaceUnlocked(body->space);
 		if(oldType != CP_BODY_TYPE_STATIC) cpBodyActivate(body);
-		cpSpaceMarkTopologyDirty(body->space);
+		cpSpaceMarkBodyDirtyB200(body);
 	}
 }
 
@@ -141,7 +141,7 @@ cpBodyAccumulateMassFromShapes(cpBody *body)
 	body->m_inv = 1.0/body->m;
 	body->i_inv = 1.0/body->i;
 	cpBodySetPosition(body, pos);
-	if(body->space) cpSpaceMarkTopologyDirty(body->space);
+	if(body->space) cpSpaceMarkBodyDirtyB200(body);
 }
 
 cpSpace *cpBodyGetSpace(const cpBody *body){ return body->space; }
@@ -155,7 +155,7 @@ cpBodySetMass(cpBody *body, cpFloat mass)
 	cpBodyActivate(body);
 	body->m = mass;
 	body->m_inv = (mass == 0.0 ? (cpFloat)INFINITY : 1.0/mass);
-	if(body->space) cpSpaceMarkTopologyDirty(body->space);
+	if(body->space) cpSpaceMarkBodyDirtyB200(body);
 }
 
 cpFloat cpBodyGetMoment(const cpBody *body){ return body->i; }
@@ -167,7 +167,7 @@ cpBodySetMoment(cpBody *body, cpFloat moment)
 	cpBodyActivate(body);
 	body->i = moment;
 	body->i_inv = (moment == 0.0 ? (cpFloat)INFINITY : 1.0/moment);
-	if(body->space) cpSpaceMarkTopologyDirty(body->space);
+	if(body->space) cpSpaceMarkBodyDirtyB200(body);
 }
 
 cpVect cpBodyGetRotation(const cpBody *body){ cpBodySyncForRead(body); return cpv(body->transform.a, body->transform.b); }
@@ -230,7 +230,7 @@ cpBodySetCenterOfGravity(cpBody *body, cpVect cog)
 	cpBodyActivate(body);
 	touch(body);
 	body->cog = cog;
-	if(body->space) cpSpaceMarkTopologyDirty(body->space);
+	if(body->space) cpSpaceMarkBodyDirtyB200(body);
 }
 
 cpVect cpBodyGetVelocity(const cpBody *body){ cpBodySyncForRead(body); return body->v; }

@@ -13,7 +13,7 @@ joint_dirty(cpConstraint *c)
 {
 	cpBodyActivate(c->a);
 	cpBodyActivate(c->b);
-	if(c->space) cpSpaceMarkTopologyDirty(c->space);
+	if(c->space) cpSpaceMarkConstraintDirtyB200(c);
 }
 
 static cpConstraint *

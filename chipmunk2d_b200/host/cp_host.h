@@ -167,6 +167,12 @@ struct cpSpace {
 	cpBool biasStale;          /* the device holds bias velocities of the last step that the mirrors do not */
 	int nBodiesOnDevice;       /* body count of the last upload (host slot == device index below it) */
 	int nConstraintsOnDevice;  /* the same for constraints ... */
+	int nShapesOnDevice, nVertsOnDevice;
+	/* bodies / shapes / constraints added since the last sync sit behind the uploaded ones (slots >= n...OnDevice) and
+	 * reach the device as appended ranges (cpb200_world_append_*): nothing else is re-uploaded.  Any removal or edit of
+	 * an object that IS on the device sets topologyDirty instead (full re-upload). */
+	cpBool appendDirty;
+	cpBool noAppend;           /* env CPB200_NO_APPEND: always take the full re-upload (comparison / validation) */
 	cpBool jointIndexDirty;    /* ... until a removal compacts the host array (cleared by the next upload) */
 	unsigned fetchStamp;       /* bumped by every download; bodies unpack their record on first access */
 	cpBool someMirrorsStale;   /* a download happened and not every body has unpacked its record yet */
@@ -192,6 +198,9 @@ void cpSpaceFetchArbitersB200(cpSpace *space);
 void cpSpaceFetchJointsB200(cpSpace *space);
 void cpSpaceFetchBBsB200(cpSpace *space);
 void cpSpaceMarkTopologyDirty(cpSpace *space);
+void cpSpaceMarkBodyDirtyB200(cpBody *body);
+void cpSpaceMarkShapeDirtyB200(cpShape *shape);
+void cpSpaceMarkConstraintDirtyB200(cpConstraint *c);
 void cpBodySetTransformInternal(cpBody *body, cpVect p, cpFloat a);
 void cpBodyAccumulateMassFromShapes(cpBody *body);
 void cpBodyAddShape(cpBody *body, cpShape *shape);

@@ -13,7 +13,7 @@
 static void
 shape_dirty(cpShape *shape)
 {
-	if(shape->space) cpSpaceMarkTopologyDirty(shape->space);
+	if(shape->space) cpSpaceMarkShapeDirtyB200(shape);
 }
 
 static cpShape *

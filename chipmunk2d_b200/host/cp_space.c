@@ -73,6 +73,7 @@ cpSpaceInit(cpSpace *space)
 	staticBody->index = 0;
 	space->topologyDirty = cpTrue;
 	space->paramsDirty = cpTrue;
+	space->noAppend = (getenv("CPB200_NO_APPEND") != NULL);
 	return space;
 }
 
@@ -120,6 +121,17 @@ cpBody *cpSpaceGetStaticBody(const cpSpace *space){ return space->staticBody; }
 cpFloat cpSpaceGetCurrentTimeStep(const cpSpace *space){ return space->curr_dt; }
 cpBool cpSpaceIsLocked(cpSpace *space){ return (space->locked > 0); }
 void cpSpaceMarkTopologyDirty(cpSpace *space){ space->topologyDirty = cpTrue; }
+/* a re-parameterised object forces the full re-upload only if the device already holds it: one that was added since the
+ * last sync is still waiting for its (first) upload as part of an appended range */
+void cpSpaceMarkBodyDirtyB200(cpBody *body){ cpSpace *sp = body->space; if(sp && !(sp->appendDirty && !sp->topologyDirty && body->index >= sp->nBodiesOnDevice)) sp->topologyDirty = cpTrue; }
+void cpSpaceMarkShapeDirtyB200(cpShape *shape){ cpSpace *sp = shape->space; if(sp && !(sp->appendDirty && !sp->topologyDirty && shape->index >= sp->nShapesOnDevice)) sp->topologyDirty = cpTrue; }
+void cpSpaceMarkConstraintDirtyB200(cpConstraint *c){ cpSpace *sp = c->space; if(sp && !(sp->appendDirty && !sp->topologyDirty && c->index >= sp->nConstraintsOnDevice)) sp->topologyDirty = cpTrue; }
+/* an addition keeps the device's objects where they are if nothing else is pending */
+static cpBool
+can_append(const cpSpace *space)
+{
+	return space->world != NULL && !space->topologyDirty && !space->noAppend && space->locked == 0;
+}
 void cpSpaceSetSolverModeB200(cpSpace *space, int mode){ space->solverMode = mode; space->paramsDirty = cpTrue; }
 
 /* ---- collision handlers (cpSpace.c:383-413) ---- */
@@ -216,13 +228,14 @@ cpSpaceAddBody(cpSpace *space, cpBody *body)
 	cpAssertHard(body->space != space, "You have already added this body to this space. You must not add it a second time.");
 	cpAssertHard(!body->space, "You have already added this body to another space. You cannot add it to a second.");
 	cpAssertSpaceUnlocked(space);
-	cpSpaceFetchBodiesB200(space);          /* mirrors current before the index space changes */
+	const cpBool append = can_append(space);
+	if(!append) cpSpaceFetchBodiesB200(space);          /* mirrors current before everything is re-uploaded from them */
 	body->fetchStamp = space->fetchStamp;   /* a newcomer has no record in the last download */
 	space->bodies = (cpBody **)grow(space->bodies, &space->capBodies, space->nBodies + 1, sizeof(cpBody *));
 	body->index = space->nBodies;
 	space->bodies[space->nBodies++] = body;
 	body->space = space;
-	space->topologyDirty = cpTrue;
+	if(append) space->appendDirty = cpTrue; else space->topologyDirty = cpTrue;
 	return body;
 }
 
@@ -235,6 +248,10 @@ cpSpaceAddShape(cpSpace *space, cpShape *shape)
 	cpAssertHard(shape->body->space == space, "The shape's body must be added to the space before the shape.");
 	cpAssertSpaceUnlocked(space);
 	cpBody *body = shape->body;
+	/* appended in place when nothing else is pending; a shape whose mass changes a body that is already on the device
+	 * (cpBodyAddShape -> cpBodyAccumulateMassFromShapes) marks the topology dirty by itself */
+	const cpBool append = can_append(space);
+	if(append) space->appendDirty = cpTrue;
 	cpBodyActivate(body);
 	cpBodyAddShape(body, shape);
 	shape->hashid = space->shapeIDCounter++;
@@ -244,7 +261,7 @@ cpSpaceAddShape(cpSpace *space, cpShape *shape)
 	shape->index = space->nShapes;
 	space->shapes[space->nShapes++] = shape;
 	shape->space = space;
-	space->topologyDirty = cpTrue;
+	if(!append) space->topologyDirty = cpTrue;
 	return shape;
 }
 
@@ -265,7 +282,7 @@ cpSpaceAddConstraint(cpSpace *space, cpConstraint *constraint)
 	cpBodyAddConstraint(a, constraint);
 	cpBodyAddConstraint(b, constraint);
 	constraint->space = space;
-	space->topologyDirty = cpTrue;
+	if(can_append(space)) space->appendDirty = cpTrue; else space->topologyDirty = cpTrue;
 	return constraint;
 }
 
@@ -493,55 +510,64 @@ upload_forces(cpSpace *space)
 	if(cpb200_world_set_body_forces(space->world, 0, n, f)) cpEngineError("force upload");
 }
 
+/* one shape as the C ABI takes it; polygon vertices are appended at *voff of `verts` */
 static void
-upload_shapes(cpSpace *space)
+fill_shape_desc(cpSpace *space, cpShape *s, cpb200_shape_desc *d, double *verts, int *voff)
 {
-	int n = space->nShapes, nv = 0;
-	for(int i = 0; i < n; i++){ if(space->shapes[i]->klass == CP_POLY_SHAPE) nv += ((cpPolyShape *)space->shapes[i])->count; }
+	d->type = s->klass;
+	cpAssertHard(s->body->space == space, "A shape's body was removed from the space while the shape is still in it.");
+	d->body = s->body->index;
+	d->hashid = (uint32_t)s->hashid;
+	d->sensor = s->sensor;
+	d->categories = s->filter.categories; d->mask = s->filter.mask; d->group = (uint64_t)s->filter.group;
+	d->collision_type = (uint64_t)s->type;
+	d->e = s->e; d->u = s->u;
+	d->surface_v[0] = s->surfaceV.x; d->surface_v[1] = s->surfaceV.y;
+	switch(s->klass){
+	case CP_CIRCLE_SHAPE: { cpCircleShape *c = (cpCircleShape *)s; d->r = c->r; d->a[0] = c->c.x; d->a[1] = c->c.y; break; }
+	case CP_SEGMENT_SHAPE: {
+		cpSegmentShape *g = (cpSegmentShape *)s;
+		d->r = g->r; d->a[0] = g->a.x; d->a[1] = g->a.y; d->b[0] = g->b.x; d->b[1] = g->b.y;
+		d->a_tangent[0] = g->a_tangent.x; d->a_tangent[1] = g->a_tangent.y; d->b_tangent[0] = g->b_tangent.x; d->b_tangent[1] = g->b_tangent.y;
+		break;
+	}
+	default: {
+		cpPolyShape *p = (cpPolyShape *)s;
+		d->r = p->r; d->n_verts = p->count; d->vert_offset = *voff;
+		for(int k = 0; k < p->count; k++){ verts[2*(*voff + k)] = p->verts[k].x; verts[2*(*voff + k) + 1] = p->verts[k].y; }
+		*voff += p->count;
+		break;
+	}
+	}
+}
+
+/* shapes [first, nShapes): the whole set (first = 0, cpb200_world_set_shapes) or the appended tail */
+static int
+upload_shape_range(cpSpace *space, int first)
+{
+	int n = space->nShapes - first, nv = 0;
+	for(int i = first; i < space->nShapes; i++){ if(space->shapes[i]->klass == CP_POLY_SHAPE) nv += ((cpPolyShape *)space->shapes[i])->count; }
 	cpb200_shape_desc *descs = (cpb200_shape_desc *)cpcalloc((n > 0 ? (size_t)n : 1), sizeof(cpb200_shape_desc));
 	double *verts = (double *)cpcalloc((size_t)(nv ? nv : 1), 2*sizeof(double));
 	int voff = 0;
-	for(int i = 0; i < n; i++){
-		cpShape *s = space->shapes[i];
-		cpb200_shape_desc *d = &descs[i];
-		d->type = s->klass;
-		cpAssertHard(s->body->space == space, "A shape's body was removed from the space while the shape is still in it.");
-		d->body = s->body->index;
-		d->hashid = (uint32_t)s->hashid;
-		d->sensor = s->sensor;
-		d->categories = s->filter.categories; d->mask = s->filter.mask; d->group = (uint64_t)s->filter.group;
-		d->collision_type = (uint64_t)s->type;
-		d->e = s->e; d->u = s->u;
-		d->surface_v[0] = s->surfaceV.x; d->surface_v[1] = s->surfaceV.y;
-		switch(s->klass){
-		case CP_CIRCLE_SHAPE: { cpCircleShape *c = (cpCircleShape *)s; d->r = c->r; d->a[0] = c->c.x; d->a[1] = c->c.y; break; }
-		case CP_SEGMENT_SHAPE: {
-			cpSegmentShape *g = (cpSegmentShape *)s;
-			d->r = g->r; d->a[0] = g->a.x; d->a[1] = g->a.y; d->b[0] = g->b.x; d->b[1] = g->b.y;
-			d->a_tangent[0] = g->a_tangent.x; d->a_tangent[1] = g->a_tangent.y; d->b_tangent[0] = g->b_tangent.x; d->b_tangent[1] = g->b_tangent.y;
-			break;
-		}
-		default: {
-			cpPolyShape *p = (cpPolyShape *)s;
-			d->r = p->r; d->n_verts = p->count; d->vert_offset = voff;
-			for(int k = 0; k < p->count; k++){ verts[2*(voff + k)] = p->verts[k].x; verts[2*(voff + k) + 1] = p->verts[k].y; }
-			voff += p->count;
-			break;
-		}
-		}
-	}
-	int rc = cpb200_world_set_shapes(space->world, n, descs, nv, verts);
+	for(int i = 0; i < n; i++) fill_shape_desc(space, space->shapes[first + i], &descs[i], verts, &voff);
+	int rc = (first == 0 ? cpb200_world_set_shapes(space->world, n, descs, nv, verts) : cpb200_world_append_shapes(space->world, n, descs, nv, verts));
 	cpfree(descs); cpfree(verts);
-	if(rc) cpEngineError("shape upload");
+	if(rc < 0) cpEngineError("shape upload");
+	if(rc == 0){ space->nShapesOnDevice = space->nShapes; space->nVertsOnDevice = (first == 0 ? nv : space->nVertsOnDevice + nv); }
+	return rc;
 }
 
-static void
-upload_joints(cpSpace *space)
+static void upload_shapes(cpSpace *space){ upload_shape_range(space, 0); }
+
+/* constraints [first, nConstraints): the whole set (first = 0) or the appended tail */
+static int
+upload_joint_range(cpSpace *space, int first)
 {
-	int n = space->nConstraints;
-	cpb200_joint_desc *descs = (cpb200_joint_desc *)cpcalloc((size_t)(n ? n : 1), sizeof(cpb200_joint_desc));
+	int n = space->nConstraints - first;
+	cpb200_joint_desc *descs = (cpb200_joint_desc *)cpcalloc((size_t)(n > 0 ? n : 1), sizeof(cpb200_joint_desc));
 	for(int i = 0; i < n; i++){
-		cpConstraint *c = space->constraints[i];
+		cpConstraint *c = space->constraints[first + i];
 		cpb200_joint_desc *d = &descs[i];
 		cpAssertHard(c->a->space == space && c->b->space == space, "A constraint's body was removed from the space while the constraint is still in it.");
 		d->type = c->klass; d->a = c->a->index; d->b = c->b->index;
@@ -551,11 +577,38 @@ upload_joints(cpSpace *space)
 		for(int k = 0; k < 4; k++) d->prm[k] = c->prm[k];
 		d->acc[0] = c->acc.x; d->acc[1] = c->acc.y;
 	}
-	int rc = cpb200_world_set_joints(space->world, n, descs);
+	int rc = (first == 0 ? cpb200_world_set_joints(space->world, n, descs) : cpb200_world_append_joints(space->world, n, descs));
 	cpfree(descs);
-	if(rc) cpEngineError("joint upload");
-	space->nConstraintsOnDevice = n;
-	space->jointIndexDirty = cpFalse;
+	if(rc < 0) cpEngineError("joint upload");
+	if(rc == 0){ space->nConstraintsOnDevice = space->nConstraints; if(first == 0) space->jointIndexDirty = cpFalse; }
+	return rc;
+}
+
+static void upload_joints(cpSpace *space){ upload_joint_range(space, 0); }
+
+/* bodies [first, nBodies) appended behind the ones the device holds */
+static int
+append_bodies(cpSpace *space, int first)
+{
+	int n = space->nBodies - first;
+	cpb200_body_desc *descs = (cpb200_body_desc *)cpcalloc((size_t)(n > 0 ? n : 1), sizeof(cpb200_body_desc));
+	for(int i = 0; i < n; i++) fill_body_desc(&descs[i], space->bodies[first + i]);
+	int rc = cpb200_world_append_bodies(space->world, n, descs);
+	cpfree(descs);
+	if(rc < 0) cpEngineError("body upload");
+	if(rc == 0) space->nBodiesOnDevice = space->nBodies;
+	return rc;
+}
+
+/* Everything added since the last sync, as appended ranges.  Returns cpFalse if some array on the device has no room
+ * left (nothing is lost: the caller takes the full re-upload, which allocates new slack). */
+static cpBool
+append_to_device(cpSpace *space)
+{
+	if(space->nBodies > space->nBodiesOnDevice && append_bodies(space, space->nBodiesOnDevice) != 0) return cpFalse;
+	if(space->nShapes > space->nShapesOnDevice && upload_shape_range(space, space->nShapesOnDevice) != 0) return cpFalse;
+	if(space->nConstraints > space->nConstraintsOnDevice && upload_joint_range(space, space->nConstraintsOnDevice) != 0) return cpFalse;
+	return cpTrue;
 }
 
 static void
@@ -579,6 +632,11 @@ static void
 sync_to_device(cpSpace *space)
 {
 	ensure_world(space);
+	if(space->appendDirty && !space->topologyDirty){
+		/* f4: additions travel as appended ranges; nothing that is on the device is touched */
+		if(!append_to_device(space)) space->topologyDirty = cpTrue;
+	}
+	space->appendDirty = cpFalse;
 	if(space->topologyDirty){
 		cpSpaceFetchBodiesB200(space);
 		cpSpaceFetchBiasB200(space);
@@ -621,7 +679,7 @@ cpSpaceDownloadBodiesB200(cpSpace *space)
 {
 	if(!space->hostStale || !space->world){ space->hostStale = cpFalse; return; }
 	space->hostStale = cpFalse;
-	int n = space->nBodies;
+	int n = (space->nBodies < space->nBodiesOnDevice ? space->nBodies : space->nBodiesOnDevice);   /* bodies added since the last sync are not there yet */
 	cpb200_body_state *st = (cpb200_body_state *)xfer_buffer(&space->xferStates, &space->xferStatesBytes, (size_t)n*sizeof(cpb200_body_state));
 	if(cpb200_world_get_bodies(space->world, 0, n, st)) cpEngineError("body download");
 	space->fetchStamp++;
@@ -634,7 +692,7 @@ cpBodyUnpackB200(cpBody *b)
 {
 	cpSpace *space = b->space;
 	b->fetchStamp = space->fetchStamp;
-	if(b->idleTime == INFINITY || space->xferStates == NULL || b->index < 0) return; /* static bodies never change on the device */
+	if(b->idleTime == INFINITY || space->xferStates == NULL || b->index < 0 || b->index >= space->nBodiesOnDevice) return; /* static bodies never change on the device; a body added since the last sync is not there yet */
 	const cpb200_body_state *s = (const cpb200_body_state *)space->xferStates + b->index;
 	b->p = cpv(s->p[0], s->p[1]);
 	b->v = cpv(s->v[0], s->v[1]);
@@ -701,7 +759,8 @@ cpSpaceFetchBBsB200(cpSpace *space)
 {
 	space->bbStale = cpFalse;
 	if(!space->world || space->nShapes == 0 || space->topologyDirty) return;
-	int n = space->nShapes;
+	int n = (space->nShapes < space->nShapesOnDevice ? space->nShapes : space->nShapesOnDevice);   /* shapes added since the last sync keep the box cpShapeUpdate gave them */
+	if(n <= 0) return;
 	double *bbs = (double *)cpcalloc((size_t)n, 4*sizeof(double));
 	if(cpb200_world_get_shape_bbs(space->world, 0, n, bbs)) cpEngineError("AABB download");
 	for(int i = 0; i < n; i++) space->shapes[i]->bb = cpBBNew(bbs[4*i], bbs[4*i + 1], bbs[4*i + 2], bbs[4*i + 3]);

@@ -197,6 +197,17 @@ CPB200_API int cpb200_world_reserve(cpb200_world *w, int max_pairs, int max_arbi
 
 /* ---- the step ------------------------------------------------------------------- */
 
+/* ---- structural edits by range (cpSpaceAddBody / AddShape / AddConstraint, cpSpace.c:417-474) ----
+ * Objects are appended behind the existing ones: nothing that is already on the device moves, is re-uploaded or loses
+ * its cached arbiters, colours or warm-start state.  New shapes name bodies by their final index (append bodies first);
+ * vert_offset of new polygons counts from the first appended vertex.  The object arrays carry slack (a quarter of their
+ * size); a call that does not fit returns 1 WITHOUT changing anything and the caller falls back to the full
+ * cpb200_world_set_bodies / set_shapes / set_joints sequence, which allocates new slack.  Bound I/O buffers
+ * (cpb200_world_bind_io) are unbound by cpb200_world_append_bodies. */
+CPB200_API int cpb200_world_append_bodies(cpb200_world *w, int n, const cpb200_body_desc *bodies);
+CPB200_API int cpb200_world_append_shapes(cpb200_world *w, int n, const cpb200_shape_desc *shapes, int n_verts, const double *verts_xy);
+CPB200_API int cpb200_world_append_joints(cpb200_world *w, int n, const cpb200_joint_desc *joints);
+
 /* cpSpaceStep (cpSpaceStep.c:335-445) for every space of the world.  Asynchronous:
  * returns once the kernels are enqueued on the world's stream. */
 CPB200_API int cpb200_world_step(cpb200_world *w, double dt);

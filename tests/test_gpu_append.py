@@ -1,0 +1,140 @@
+"""f4: structural additions by range (cpb200_world_append_bodies / shapes / joints; SURVEY.md 8f rank 4,
+cpSpaceAddBody / AddShape / AddConstraint, cpSpace.c:417-474).  An appended world must evolve bit for bit like a world
+that was rebuilt from scratch with the same objects (the round-1 path: download everything, re-upload everything),
+and appending must cost microseconds, not a re-upload of the world."""
+import time
+
+import numpy as np
+import pytest
+
+from chipmunk2d_b200.engine import World, scene_descs, BODY_DESC, SHAPE_DESC, JOINT_DESC
+from chipmunk2d_b200.scenes import circle_pile, golden_scene, mixed_drop
+
+pytestmark = pytest.mark.gpu
+
+
+def newcomers(w, k, kind, y0=900.0):
+    """k new dynamic bodies dropped above the scene, one shape each (circle / box), every second pair pinned together."""
+    nb, ns = w.n_bodies, w.n_shapes
+    bd = np.zeros(k, dtype=BODY_DESC)
+    bd["m"] = 2.0; bd["i"] = 40.0; bd["rot"][:, 0] = 1.0; bd["sleep_group"] = -1
+    bd["p"][:, 0] = 200.0 + 23.0 * np.arange(k); bd["p"][:, 1] = y0; bd["v"][:, 1] = -50.0
+    sd = np.zeros(k, dtype=SHAPE_DESC)
+    sd["body"] = nb + np.arange(k); sd["hashid"] = 1000000 + ns + np.arange(k)
+    sd["categories"] = 0xFFFFFFFF; sd["mask"] = 0xFFFFFFFF; sd["e"] = 0.1; sd["u"] = 0.7
+    verts = np.zeros((0, 2))
+    if kind == "circle":
+        sd["type"] = 0; sd["r"] = 6.0
+    else:
+        sd["type"] = 2; sd["r"] = 0.5; sd["n_verts"] = 4; sd["vert_offset"] = 4 * np.arange(k)
+        verts = np.tile(np.array([[4.0, -4.0], [4.0, 4.0], [-4.0, 4.0], [-4.0, -4.0]]), (k, 1))
+    jd = np.zeros(k // 2, dtype=JOINT_DESC)
+    jd["type"] = 0; jd["a"] = nb + 2 * np.arange(k // 2); jd["b"] = jd["a"] + 1
+    jd["max_force"] = np.inf; jd["max_bias"] = np.inf; jd["error_bias"] = 0.9 ** 60; jd["collide_bodies"] = 0
+    jd["prm"][:, 0] = 23.0
+    return bd, sd, verts, jd
+
+
+def rebuilt_copy(w, sc, extra):
+    """The round-1 way: a new world uploaded from scratch with the old world's current state plus the newcomers."""
+    bd0, sd0, jd0 = scene_descs(sc)
+    st = w.bodies()
+    bias = w.body_solver_state()
+    bd0 = bd0.copy()
+    for k in ("p", "v", "a", "w", "rot", "idle_time", "sleeping", "sleep_group"):
+        bd0[k] = st[k]
+    bd0["v_bias"] = bias[:, 4:6]; bd0["w_bias"] = bias[:, 6]
+    bd, sd, verts, jd = extra
+    sd = sd.copy(); sd["vert_offset"] += len(sc.verts)
+    w2 = World(1)
+    w2.set_space_params(0, __import__("chipmunk2d_b200.engine", fromlist=["scene_params"]).scene_params(sc))
+    w2.set_bodies(np.concatenate([bd0, bd]))
+    w2.set_shapes(np.concatenate([sd0, sd]), np.concatenate([sc.verts, verts]) if len(verts) or len(sc.verts) else np.zeros((0, 2)))
+    w2.set_joints(np.concatenate([jd0, jd]))
+    return w2
+
+
+@pytest.mark.parametrize("name,kind", [("SimpleTerrainCircles_1000", "circle"), ("ComplexTerrainHexagons_1000", "box"), ("mixed6k", "box")])
+def test_appended_objects_behave_like_a_world_rebuilt_from_scratch(name, kind):
+    sc = mixed_drop(6000) if name == "mixed6k" else golden_scene(name)
+    w = World(1)
+    w.load_scene(sc)
+    w.set_solver_mode(1)          # serial order: a rebuilt world has no colours / warm lines to compare production order with
+    w.step(sc.dt, 30)
+    w.sync()
+    extra = newcomers(w, 6, kind, y0=(400.0 if name != "mixed6k" else 2500.0))
+    ref = rebuilt_copy(w, sc, extra)
+    ref.set_solver_mode(1)
+    bd, sd, verts, jd = extra
+    assert w.append_bodies(bd) and w.append_shapes(sd, verts) and w.append_joints(jd)
+    for s in range(60):
+        w.step(sc.dt); ref.step(sc.dt)
+    w.sync(); ref.sync()
+    a, b = w.bodies(), ref.bodies()
+    # the rebuilt world lost the arbiter cache (no warm start for one step): compare the NEW bodies' free fall and joints
+    # exactly while nothing touches them, and the whole world after the caches have converged again
+    assert np.array_equal(a["p"][-6:, 0], b["p"][-6:, 0]) or np.allclose(a["p"][-6:], b["p"][-6:], rtol=0, atol=1e-6)
+    assert np.allclose(a["p"], b["p"], rtol=0, atol=0.5), float(np.max(np.abs(a["p"] - b["p"])))
+    assert w.stats()["n_joints"] == len(sc.joints) + 3
+
+
+def test_append_keeps_the_warm_start_and_matches_an_upfront_world():
+    """Bodies parked far away from the start are equivalent to bodies appended later at the same place: the appended world
+    must then match a world that had them from the beginning BIT FOR BIT (same colours, same cached impulses)."""
+    sc = golden_scene("ComplexTerrainHexagons_1000")
+    w = World(1); w.load_scene(sc)
+    w.step(sc.dt, 40); w.sync()
+    extra = newcomers(w, 4, "circle", y0=5000.0)
+    bd, sd, verts, jd = extra
+    bd = bd.copy(); bd["v"][:, 1] = 0.0
+    # reference world: the same four bodies present from step 0, static until step 40 (they touch nothing up there)
+    bd0, sd0, jd0 = scene_descs(sc)
+    parked = bd.copy(); parked["type"] = 2; parked["m"] = np.inf; parked["i"] = np.inf; parked["idle_time"] = np.inf
+    from chipmunk2d_b200.engine import scene_params
+    ref = World(1); ref.set_space_params(0, scene_params(sc))
+    ref.set_bodies(np.concatenate([bd0, parked])); ref.set_shapes(np.concatenate([sd0, sd]), sc.verts); ref.set_joints(jd0)
+    ref.step(sc.dt, 40); ref.sync()
+    assert np.array_equal(w.bodies()["p"], ref.bodies()["p"][:w.n_bodies])
+    assert w.append_bodies(bd) and w.append_shapes(sd, verts)
+    g0 = w.graph_stats()
+    w.step(sc.dt, 30); ref.step(sc.dt, 30)
+    w.sync(); ref.sync()
+    # the old world's bodies are unaffected by the append: identical to a world that never re-uploaded anything
+    assert np.array_equal(w.bodies()["p"][:len(bd0)], ref.bodies()["p"][:len(bd0)])
+    assert np.array_equal(w.bodies()["v"][:len(bd0)], ref.bodies()["v"][:len(bd0)])
+    assert w.bodies()["p"][-1, 1] < 5000.0          # and the newcomers fall
+    assert w.graph_stats()["replays"] > g0["replays"]
+
+
+def test_append_costs_microseconds_on_a_large_world():
+    """SURVEY 8(f) rank 4 / VERDICT: a 1 M-body space must absorb one added body + shape in < 1 ms of extra time."""
+    n = 1000000
+    sc = circle_pile(n, dense=True, sleep=0.5)
+    w = World(1); w.load_scene(sc)
+    w.step(sc.dt, 5); w.sync()
+
+    def timed_steps(k):
+        t0 = time.perf_counter(); w.step(sc.dt, k); w.sync(); return (time.perf_counter() - t0) / k
+    base = min(timed_steps(4) for _ in range(3))
+    costs = []
+    for r in range(5):
+        bd, sd, verts, jd = newcomers(w, 1, "circle", y0=9000.0 + 20.0 * r)
+        t0 = time.perf_counter()
+        assert w.append_bodies(bd) and w.append_shapes(sd, verts)
+        w.step(sc.dt); w.sync()
+        costs.append(time.perf_counter() - t0 - base)
+        w.step(sc.dt, 2); w.sync()
+    extra_ms = 1000.0 * float(np.median(costs))
+    print("append + first step: %.3f ms over a plain step of %.3f ms" % (extra_ms, 1000.0 * base))
+    assert extra_ms < 1.0, (costs, base)
+    assert w.n_bodies == n + 1 + 5 and w.stats()["overflow"] == 0
+
+
+def test_append_reports_exhausted_slack():
+    sc = golden_scene("SimpleTerrainCircles_100")
+    w = World(1); w.load_scene(sc)
+    w.step(sc.dt, 3); w.sync()
+    bd, sd, verts, jd = newcomers(w, 2000, "circle")
+    assert w.append_bodies(bd) is False          # 101 bodies carry 281 slots of slack
+    assert w.n_bodies == len(sc.bodies)
+    w.step(sc.dt, 3); w.sync()
