@@ -37,6 +37,7 @@ struct DBodies {
 	int *space;
 	int *sleeping;  // 0 awake, 1 asleep
 	int *sgroup;    // sleeping component id (root body index) or -1
+	int *custom;    // CPB200_BODY_HOST_POSITION | CPB200_BODY_HOST_VELOCITY: a host callback integrates this body
 };
 
 // ---- shapes (cpShape + cpCircleShape/cpSegmentShape/cpPolyShape) ----
@@ -150,7 +151,7 @@ struct DJoints {
 	V2 *bias;              // scalar joints use .x
 	V2 *acc;               // jnAcc / jAcc
 	double *aux0, *aux1;   // spring: target_vrn, v_coef | ratchet: angle
-	V2 *jspring;           // impulse applied by damped springs in preStep (cpDampedSpring.c:49-52)
+	V2 *jspring;           // (value, 1.0) = the spring force / torque a host callback returned for the next prestep; (., 0) = default law
 	int *colour;
 	int *row;              // colour-sorted order: row -> joint index
 	uint64_t *pri;         // colouring priority: hash of the space-local joint index

@@ -10,6 +10,7 @@ __global__ void k_integrate_pos(DBodies B, double dt)
 	int i = CPB_TID;
 	if(i >= B.n) return;
 	if(B.type[i] == CPB200_BODY_STATIC || B.sleeping[i]) return;
+	if(B.custom[i] & CPB200_BODY_HOST_POSITION) return;   // the host ran this body's position_func and uploaded the result
 	double4 V = B.V[i], VB = B.VB[i];
 	V2 p = vadd(B.pos[i], vmul(vadd(v2(V.x, V.y), v2(VB.x, VB.y)), dt));
 	double a = B.ang[i] + (V.z + VB.z)*dt;
@@ -89,6 +90,7 @@ __global__ void k_integrate_vel(DBodies B, const DSpace *__restrict__ spaces, do
 	if(i >= B.n) return;
 	claim[i] = 0ull; bmask[i] = 0ull;
 	if(B.type[i] != CPB200_BODY_DYNAMIC || B.sleeping[i]) return;
+	if(B.custom[i] & CPB200_BODY_HOST_VELOCITY) return;   // the host runs this body's velocity_func between prestep and solver
 	DSpace sp = spaces[B.space[i]];
 	double4 V = B.V[i];
 	V2 mi = B.MI[i];

@@ -138,7 +138,9 @@ __global__ void k_joint_prestep(DJoints J, DBodies B, double dt)
 		J.nmass[j] = 1.0/k;
 		J.aux0[j] = 0.0;                                  // target_vrn
 		J.aux1[j] = 1.0 - exp(-prm.z*dt*k);               // v_coef
-		double f_spring = (prm.x - dist)*prm.y;           // defaultSpringForce (cpDampedSpring.c:24-27)
+		V2 fc = J.jspring[j];                            // a host springForceFunc's answer for this step, if any
+		double f_spring = (fc.y != 0.0 ? fc.x : (prm.x - dist)*prm.y);   // defaultSpringForce (cpDampedSpring.c:24-27)
+		J.jspring[j] = v2(0.0, 0.0);
 		double j_spring = f_spring*dt;
 		J.acc[j] = v2(j_spring, 0.0);
 		V2 imp = vmul(n, j_spring);
@@ -158,7 +160,9 @@ __global__ void k_joint_prestep(DJoints J, DBodies B, double dt)
 		J.nmass[j] = 1.0/moment;                          // iSum
 		J.aux1[j] = 1.0 - exp(-prm.z*dt*moment);          // w_coef
 		J.aux0[j] = 0.0;                                  // target_wrn
-		double j_spring = ((B.ang[a] - B.ang[b]) - prm.x)*prm.y*dt;
+		V2 fc = J.jspring[j];                            // a host springTorqueFunc's answer for this step, if any
+		J.jspring[j] = v2(0.0, 0.0);
+		double j_spring = (fc.y != 0.0 ? fc.x : ((B.ang[a] - B.ang[b]) - prm.x)*prm.y)*dt;
 		J.acc[j] = v2(j_spring, 0.0);
 		if(mia.y != 0.0) atomic_add_d(&B.V[a].z, -(j_spring*mia.y));
 		if(mib.y != 0.0) atomic_add_d(&B.V[b].z, j_spring*mib.y);

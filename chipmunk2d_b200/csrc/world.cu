@@ -420,7 +420,7 @@ __global__ void k_unpack_bodies(DBodies B, const cpb200_body_desc *__restrict__ 
 	B.MI[i] = v2(dyn ? 1.0/d.m : 0.0, dyn ? 1.0/d.i : 0.0);
 	B.M[i] = v2(d.m, d.i);
 	B.force[i] = v2(d.f[0], d.f[1]); B.torque[i] = d.t; B.idle[i] = d.idle_time;
-	B.type[i] = d.type; B.space[i] = d.space; B.sleeping[i] = d.sleeping; B.sgroup[i] = d.sleep_group;
+	B.type[i] = d.type; B.space[i] = d.space; B.sleeping[i] = d.sleeping; B.sgroup[i] = d.sleep_group; B.custom[i] = d.custom;
 	// translation part of SetTransform from the host-supplied rotation (cpBody.c:347-357)
 	V2 p = v2(d.p[0], d.p[1]), rot = v2(d.rot[0], d.rot[1]), cg = v2(d.cog[0], d.cog[1]);
 	B.txy[i] = v2(p.x - (cg.x*rot.x - cg.y*rot.y), p.y - (cg.x*rot.y + cg.y*rot.x));
@@ -467,7 +467,7 @@ extern "C" int cpb200_world_set_bodies(cpb200_world *w, int n, const cpb200_body
 	DA(w->gB, B.pos, cap); DA(w->gB, B.ang, cap); DA(w->gB, B.rot, cap); DA(w->gB, B.txy, cap); DA(w->gB, B.cog, cap);
 	DA(w->gB, B.V, cap); DA(w->gB, B.VB, cap); DA(w->gB, B.MI, cap); DA(w->gB, B.M, cap); DA(w->gB, B.force, cap);
 	DA(w->gB, B.torque, cap); DA(w->gB, B.idle, cap); DA(w->gB, B.type, cap); DA(w->gB, B.space, cap);
-	DA(w->gB, B.sleeping, cap); DA(w->gB, B.sgroup, cap);
+	DA(w->gB, B.sleeping, cap); DA(w->gB, B.sgroup, cap); DA(w->gB, B.custom, cap);
 	w->gK.release();
 	DA(w->gK, w->K.claim, cap); DA(w->gK, w->K.bmask, cap);
 	DA(w->gK, w->K.ccount, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.cstart, CPB_MAX_COLOURS + 1); DA(w->gK, w->K.ccursor, CPB_MAX_COLOURS + 1);
@@ -619,6 +619,87 @@ extern "C" int cpb200_world_bind_io(cpb200_world *w, const double *forces_fxyt, 
 	}
 	w->io_src = forces_fxyt; w->io_sink = state_out;
 	return 0;
+}
+
+// ---- host callbacks in the middle of a step (custom integrators, spring force functions) ----
+__global__ void k_pack_body_state_indexed(DBodies B, cpb200_body_state *__restrict__ dst, const int *__restrict__ idx, int n)
+{
+	int k = CPB_TID;
+	if(k >= n) return;
+	int i = idx[k];
+	cpb200_body_state o;
+	memset(&o, 0, sizeof(o));
+	if(i >= 0 && i < B.n){
+		V2 p = B.pos[i], rot = B.rot[i]; double4 V = B.V[i];
+		o.p[0] = p.x; o.p[1] = p.y; o.v[0] = V.x; o.v[1] = V.y; o.a = B.ang[i]; o.w = V.z;
+		o.rot[0] = rot.x; o.rot[1] = rot.y; o.idle_time = B.idle[i]; o.sleeping = B.sleeping[i]; o.sleep_group = B.sgroup[i];
+	}
+	dst[k] = o;
+}
+
+__global__ void k_set_velocities_indexed(DBodies B, const int *__restrict__ idx, const double *__restrict__ vxyw, int n)
+{
+	int k = CPB_TID;
+	if(k >= n) return;
+	int i = idx[k];
+	if(i < 0 || i >= B.n) return;
+	double4 V = B.V[i];
+	B.V[i] = make_double4(vxyw[3*k], vxyw[3*k + 1], vxyw[3*k + 2], V.w);
+	B.force[i] = v2(0.0, 0.0); B.torque[i] = 0.0;
+}
+
+__global__ void k_set_spring_forces(DJoints J, const int *__restrict__ idx, const double *__restrict__ f, int n)
+{
+	int k = CPB_TID;
+	if(k >= n) return;
+	int j = idx[k];
+	if(j >= 0 && j < J.n) J.jspring[j] = v2(f[k], 1.0);
+}
+
+// [indices | payload] in one staging buffer: returns the device payload pointer
+static int stage_indexed(cpb200_world *w, int n, const int32_t *indices, const void *payload, size_t payload_bytes, const int **d_idx, void **d_payload)
+{
+	size_t ib = (sizeof(int32_t)*(size_t)n + 63) & ~(size_t)63;
+	if(stage_reserve(w, ib + payload_bytes + 64)) return -1;
+	CPB_CHECK(cudaMemcpyAsync(w->d_stage, indices, sizeof(int32_t)*(size_t)n, cudaMemcpyHostToDevice, w->stream));
+	*d_idx = (const int *)w->d_stage;
+	*d_payload = (char *)w->d_stage + ib;
+	if(payload && payload_bytes) CPB_CHECK(cudaMemcpyAsync(*d_payload, payload, payload_bytes, cudaMemcpyHostToDevice, w->stream));
+	return 0;
+}
+
+extern "C" int cpb200_world_get_bodies_indexed(cpb200_world *w, int n, const int32_t *indices, cpb200_body_state *out)
+{
+	if(!w || n < 0 || (n > 0 && (!indices || !out))){ cpb_set_error("bad arguments"); return -1; }
+	if(n == 0) return 0;
+	cudaSetDevice(w->device);
+	const int *d_idx; void *d_out;
+	if(stage_indexed(w, n, indices, NULL, sizeof(cpb200_body_state)*(size_t)n, &d_idx, &d_out)) return -1;
+	LAUNCH(k_pack_body_state_indexed, grid_for(n, 128), 128, w->stream, w->B, (cpb200_body_state *)d_out, d_idx, n);
+	CPB_CHECK(cudaMemcpyAsync(out, d_out, sizeof(cpb200_body_state)*(size_t)n, cudaMemcpyDeviceToHost, w->stream));
+	return world_sync(w);
+}
+
+extern "C" int cpb200_world_set_body_velocities_indexed(cpb200_world *w, int n, const int32_t *indices, const double *vxyw)
+{
+	if(!w || n < 0 || (n > 0 && (!indices || !vxyw))){ cpb_set_error("bad arguments"); return -1; }
+	if(n == 0) return 0;
+	cudaSetDevice(w->device);
+	const int *d_idx; void *d_v;
+	if(stage_indexed(w, n, indices, vxyw, sizeof(double)*3*(size_t)n, &d_idx, &d_v)) return -1;
+	LAUNCH(k_set_velocities_indexed, grid_for(n, 128), 128, w->stream, w->B, d_idx, (const double *)d_v, n);
+	return world_sync(w);
+}
+
+extern "C" int cpb200_world_set_spring_forces(cpb200_world *w, int n, const int32_t *joints, const double *f)
+{
+	if(!w || n < 0 || (n > 0 && (!joints || !f))){ cpb_set_error("bad arguments"); return -1; }
+	if(n == 0) return 0;
+	cudaSetDevice(w->device);
+	const int *d_idx; void *d_f;
+	if(stage_indexed(w, n, joints, f, sizeof(double)*(size_t)n, &d_idx, &d_f)) return -1;
+	LAUNCH(k_set_spring_forces, grid_for(n, 128), 128, w->stream, w->J, d_idx, (const double *)d_f, n);
+	return world_sync(w);
 }
 
 extern "C" int cpb200_world_reserve(cpb200_world *w, int max_pairs, int max_arbiters)

@@ -44,7 +44,7 @@ SPACE_PARAMS = np.dtype([
 BODY_DESC = np.dtype([
     ("p", "<f8", 2), ("v", "<f8", 2), ("f", "<f8", 2), ("a", "<f8"), ("w", "<f8"), ("t", "<f8"), ("rot", "<f8", 2),
     ("m", "<f8"), ("i", "<f8"), ("cog", "<f8", 2), ("v_bias", "<f8", 2), ("w_bias", "<f8"), ("idle_time", "<f8"),
-    ("type", "<i4"), ("space", "<i4"), ("sleeping", "<i4"), ("sleep_group", "<i4")], align=True)
+    ("type", "<i4"), ("space", "<i4"), ("sleeping", "<i4"), ("sleep_group", "<i4"), ("custom", "<i4"), ("pad_", "<i4")], align=True)
 SHAPE_DESC = np.dtype([
     ("type", "<i4"), ("body", "<i4"), ("hashid", "<u4"), ("sensor", "<i4"), ("categories", "<u4"), ("mask", "<u4"),
     ("group", "<u8"), ("collision_type", "<u8"), ("e", "<f8"), ("u", "<f8"), ("surface_v", "<f8", 2), ("r", "<f8"),

@@ -255,21 +255,22 @@ void cpBodySetTorque(cpBody *body, cpFloat torque){ cpBodyActivate(body); touch_
 cpDataPointer cpBodyGetUserData(const cpBody *body){ return body->userData; }
 void cpBodySetUserData(cpBody *body, cpDataPointer userData){ body->userData = userData; }
 
-/* The device integrates every body with the reference's default integrators (K1/K9).  Custom
- * per-body integrators would need a host round trip in the middle of the step (SURVEY.md 8b
- * fast-path predicate); they are rejected loudly instead of being silently ignored. */
+/* The device integrates every body with the reference's default integrators (K1 / K9).  A body with a user-supplied
+ * integrator (cpBody.c:482-491; demo/Planet.c) is skipped by those kernels: the host layer runs the callback on the
+ * body's mirror at the point of the step where the reference calls it and moves the result to the device (cpSpaceStep's
+ * slow path in cp_space.c).  Everything else about the body -- collisions, contacts, the solver -- stays on the device. */
 void
 cpBodySetVelocityUpdateFunc(cpBody *body, cpBodyVelocityFunc velocityFunc)
 {
-	cpAssertHard(velocityFunc == cpBodyUpdateVelocity, "Custom velocity update functions are not supported by the B200 step path.");
-	body->velocity_func = velocityFunc;
+	body->velocity_func = (velocityFunc ? velocityFunc : cpBodyUpdateVelocity);
+	if(body->space){ if(body->velocity_func != cpBodyUpdateVelocity) body->space->anyCustom = cpTrue; cpSpaceMarkBodyDirtyB200(body); }
 }
 
 void
 cpBodySetPositionUpdateFunc(cpBody *body, cpBodyPositionFunc positionFunc)
 {
-	cpAssertHard(positionFunc == cpBodyUpdatePosition, "Custom position update functions are not supported by the B200 step path.");
-	body->position_func = positionFunc;
+	body->position_func = (positionFunc ? positionFunc : cpBodyUpdatePosition);
+	if(body->space){ if(body->position_func != cpBodyUpdatePosition) body->space->anyCustom = cpTrue; cpSpaceMarkBodyDirtyB200(body); }
 }
 
 /* Host versions of the integrators for bodies the user steps by hand (cpBody.c:493-522). */

@@ -169,10 +169,10 @@ cpDampedSpringForceFunc cpDampedSpringGetSpringForceFunc(const cpConstraint *con
 void
 cpDampedSpringSetSpringForceFunc(cpConstraint *constraint, cpDampedSpringForceFunc springForceFunc)
 {
-	/* the device evaluates the default linear spring (cpDampedSpring.c:24-27); a host callback per spring
-	 * per step is outside the all-device fast path */
-	cpAssertHard(springForceFunc == NULL, "Custom spring force functions are not supported by the B200 step path.");
+	/* the device evaluates the default linear spring (cpDampedSpring.c:24-27); a user function is called by the host
+	 * layer between the collision phase and the prestep (slow path of cpSpaceStep in cp_space.c; demo/Springies.c) */
 	constraint->forceFunc = (void *)springForceFunc;
+	if(springForceFunc && constraint->space) constraint->space->anyCustom = cpTrue;
 }
 
 /* ---- damped rotary spring (cpDampedRotarySpring.c:90-178): prm = restAngle, stiffness, damping ---- */
@@ -192,8 +192,8 @@ cpDampedRotarySpringTorqueFunc cpDampedRotarySpringGetSpringTorqueFunc(const cpC
 void
 cpDampedRotarySpringSetSpringTorqueFunc(cpConstraint *constraint, cpDampedRotarySpringTorqueFunc springTorqueFunc)
 {
-	cpAssertHard(springTorqueFunc == NULL, "Custom spring torque functions are not supported by the B200 step path.");
 	constraint->forceFunc = (void *)springTorqueFunc;
+	if(springTorqueFunc && constraint->space) constraint->space->anyCustom = cpTrue;
 }
 
 /* ---- rotary limit (cpRotaryLimitJoint.c:104-160): prm = min, max ---- */

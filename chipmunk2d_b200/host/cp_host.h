@@ -171,6 +171,7 @@ struct cpSpace {
 	/* bodies / shapes / constraints added since the last sync sit behind the uploaded ones (slots >= n...OnDevice) and
 	 * reach the device as appended ranges (cpb200_world_append_*): nothing else is re-uploaded.  Any removal or edit of
 	 * an object that IS on the device sets topologyDirty instead (full re-upload). */
+	cpBool anyCustom;          /* some body / spring of this space has (had) a user callback: steps scan for them (slow path) */
 	cpBool appendDirty;
 	cpBool noAppend;           /* env CPB200_NO_APPEND: always take the full re-upload (comparison / validation) */
 	cpBool jointIndexDirty;    /* ... until a removal compacts the host array (cleared by the next upload) */

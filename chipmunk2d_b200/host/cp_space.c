@@ -236,6 +236,7 @@ cpSpaceAddBody(cpSpace *space, cpBody *body)
 	space->bodies[space->nBodies++] = body;
 	body->space = space;
 	if(append) space->appendDirty = cpTrue; else space->topologyDirty = cpTrue;
+	if(body->position_func != cpBodyUpdatePosition || body->velocity_func != cpBodyUpdateVelocity) space->anyCustom = cpTrue;
 	return body;
 }
 
@@ -283,6 +284,7 @@ cpSpaceAddConstraint(cpSpace *space, cpConstraint *constraint)
 	cpBodyAddConstraint(b, constraint);
 	constraint->space = space;
 	if(can_append(space)) space->appendDirty = cpTrue; else space->topologyDirty = cpTrue;
+	if(constraint->forceFunc) space->anyCustom = cpTrue;
 	return constraint;
 }
 
@@ -454,6 +456,7 @@ fill_body_desc(cpb200_body_desc *d, const cpBody *b)
 	d->space = 0;
 	d->sleeping = (b->sleepRoot != NULL);
 	d->sleep_group = (b->sleepRoot ? b->sleepRoot->index : -1);
+	d->custom = (b->position_func != cpBodyUpdatePosition ? CPB200_BODY_HOST_POSITION : 0) | (b->velocity_func != cpBodyUpdateVelocity ? CPB200_BODY_HOST_VELOCITY : 0);
 }
 
 static void
@@ -939,6 +942,125 @@ run_separate_postsolve_callbacks(cpSpace *space)
 	}
 }
 
+/* ---- user callbacks inside the step (slow path) ----
+ * Bodies with a custom position_func / velocity_func and springs with a custom force function are few (demo/Planet.c,
+ * demo/Springies.c); the step of such a space is split at the points where the reference makes those calls
+ * (cpSpaceStep.c:362-367 position, cpDampedSpring.c:50 inside the constraint prestep, cpSpaceStep.c:398-404 velocity)
+ * and only the flagged objects make the round trip through the host. */
+typedef struct cpCustomWork { int nPos, nVel, nSpring; int32_t *pos, *vel, *spring; } cpCustomWork;
+
+static void
+custom_collect(cpSpace *space, cpCustomWork *cw)
+{
+	memset(cw, 0, sizeof(*cw));
+	if(!space->anyCustom) return;
+	cw->pos = (int32_t *)cpcalloc((size_t)space->nBodies + 1, sizeof(int32_t));
+	cw->vel = (int32_t *)cpcalloc((size_t)space->nBodies + 1, sizeof(int32_t));
+	cw->spring = (int32_t *)cpcalloc((size_t)space->nConstraints + 1, sizeof(int32_t));
+	for(int i = 0; i < space->nBodies; i++){
+		cpBody *b = space->bodies[i];
+		if(b->idleTime == INFINITY) continue;                                     /* static: never integrated (cpSpace.c:447) */
+		if(b->position_func != cpBodyUpdatePosition) cw->pos[cw->nPos++] = i;
+		if(b->velocity_func != cpBodyUpdateVelocity && b->m != INFINITY) cw->vel[cw->nVel++] = i;
+	}
+	for(int i = 0; i < space->nConstraints; i++){
+		cpConstraint *c = space->constraints[i];
+		if(c->forceFunc && (c->klass == CPB200_JOINT_DAMPED_SPRING || c->klass == CPB200_JOINT_DAMPED_ROTARY_SPRING)) cw->spring[cw->nSpring++] = i;
+	}
+}
+
+static void custom_free(cpCustomWork *cw){ cpfree(cw->pos); cpfree(cw->vel); cpfree(cw->spring); }
+
+/* mirrors of the listed bodies from the device, forces untouched (the step has not consumed them yet) */
+static void
+custom_fetch_bodies(cpSpace *space, int n, const int32_t *idx)
+{
+	if(n == 0) return;
+	cpb200_body_state *st = (cpb200_body_state *)cpcalloc((size_t)n, sizeof(cpb200_body_state));
+	if(cpb200_world_get_bodies_indexed(space->world, n, idx, st)) cpEngineError("body download (custom integrator)");
+	for(int k = 0; k < n; k++){
+		cpBody *b = space->bodies[idx[k]];
+		const cpb200_body_state *s = &st[k];
+		b->p = cpv(s->p[0], s->p[1]); b->v = cpv(s->v[0], s->v[1]); b->a = s->a; b->w = s->w;
+		cpVect rot = cpv(s->rot[0], s->rot[1]), c = b->cog;
+		b->transform = cpTransformNewTranspose(rot.x, -rot.y, b->p.x - (c.x*rot.x - c.y*rot.y), rot.y, rot.x, b->p.y - (c.x*rot.y + c.y*rot.x));
+		b->sleepRoot = (s->sleeping && s->sleep_group >= 0 && s->sleep_group < space->nBodies ? space->bodies[s->sleep_group] : NULL);
+		b->fetchStamp = space->fetchStamp;
+	}
+	cpfree(st);
+}
+
+/* cpSpaceStep.c:362-367: position_func of every awake body, before anything else */
+static void
+custom_positions(cpSpace *space, cpCustomWork *cw, cpFloat dt)
+{
+	if(cw->nPos == 0 || !space->world || space->topologyDirty) {
+		/* first step (nothing on the device yet) or a pending re-upload: the mirrors are the state */
+		if(cw->nPos == 0) return;
+	} else {
+		cpSpaceFetchBodiesB200(space);
+		cpSpaceFetchBiasB200(space);
+	}
+	space->locked++;
+	for(int k = 0; k < cw->nPos; k++){
+		cpBody *b = space->bodies[cw->pos[k]];
+		if(b->sleepRoot) continue;
+		b->position_func(b, dt);
+	}
+	space->locked--;
+	space->bodiesDirty = cpTrue;     /* the integrated mirrors travel with the ordinary body upload */
+}
+
+/* cpDampedSpring.c:36-52 / cpDampedRotarySpring.c:36-48: the argument the reference hands to the user's function */
+static void
+custom_springs(cpSpace *space, cpCustomWork *cw)
+{
+	if(cw->nSpring == 0) return;
+	int nb = 0;
+	int32_t *bidx = (int32_t *)cpcalloc((size_t)2*cw->nSpring, sizeof(int32_t));
+	for(int k = 0; k < cw->nSpring; k++){ cpConstraint *c = space->constraints[cw->spring[k]]; bidx[nb++] = c->a->index; bidx[nb++] = c->b->index; }
+	custom_fetch_bodies(space, nb, bidx);           /* positions after this step's position update */
+	cpfree(bidx);
+	double *f = (double *)cpcalloc((size_t)cw->nSpring, sizeof(double));
+	space->locked++;
+	for(int k = 0; k < cw->nSpring; k++){
+		cpConstraint *c = space->constraints[cw->spring[k]];
+		cpBody *a = c->a, *b = c->b;
+		if(c->klass == CPB200_JOINT_DAMPED_SPRING){
+			cpVect r1 = cpTransformVect(a->transform, cpvsub(c->anchorA, a->cog));
+			cpVect r2 = cpTransformVect(b->transform, cpvsub(c->anchorB, b->cog));
+			cpFloat dist = cpvlength(cpvsub(cpvadd(b->p, r2), cpvadd(a->p, r1)));
+			f[k] = ((cpDampedSpringForceFunc)c->forceFunc)(c, dist);
+		} else {
+			f[k] = ((cpDampedRotarySpringTorqueFunc)c->forceFunc)(c, a->a - b->a);
+		}
+	}
+	space->locked--;
+	if(cpb200_world_set_spring_forces(space->world, cw->nSpring, cw->spring, f)) cpEngineError("spring force upload");
+	cpfree(f);
+}
+
+/* cpSpaceStep.c:398-404: velocity_func(body, gravity, damping^dt, dt) between the prestep and the solver */
+static void
+custom_velocities(cpSpace *space, cpCustomWork *cw, cpFloat dt)
+{
+	if(cw->nVel == 0) return;
+	custom_fetch_bodies(space, cw->nVel, cw->vel);
+	const cpFloat damping = cpfpow(space->damping, dt);
+	double *v = (double *)cpcalloc((size_t)cw->nVel, 3*sizeof(double));
+	const cpBool dirty = space->bodiesDirty, forces = space->forcesDirty;
+	space->locked++;
+	for(int k = 0; k < cw->nVel; k++){
+		cpBody *b = space->bodies[cw->vel[k]];
+		if(!b->sleepRoot) b->velocity_func(b, space->gravity, damping, dt);
+		v[3*k] = b->v.x; v[3*k + 1] = b->v.y; v[3*k + 2] = b->w;
+	}
+	space->locked--;
+	space->bodiesDirty = dirty; space->forcesDirty = forces;   /* the result goes straight to the device below */
+	if(cpb200_world_set_body_velocities_indexed(space->world, cw->nVel, cw->vel, v)) cpEngineError("velocity upload (custom integrator)");
+	cpfree(v);
+}
+
 /* ---- the step ---- */
 static void
 step_once(cpSpace *space, cpFloat dt, cpBool callbacks)
@@ -951,23 +1073,35 @@ step_once(cpSpace *space, cpFloat dt, cpBool callbacks)
 		}
 		space->locked--;
 	}
+	cpCustomWork cw;
+	custom_collect(space, &cw);
+	custom_positions(space, &cw, dt);
 	sync_to_device(space);
 	const cpBool handlers = space_has_collision_callbacks(space);
-	if(handlers){
+	const cpBool midstep = (cw.nSpring > 0 || cw.nVel > 0);
+	if(handlers || midstep){
 		/* split step: the handlers' return values and edits take effect in THIS step, like the reference */
 		if(cpb200_world_step_collide(space->world, dt)) cpEngineError("cpSpaceStep (collision phase)");
 		space->stamp++;
 		space->curr_dt = dt;
 		space->hostStale = cpTrue; space->bbStale = cpTrue; space->arbStale = cpTrue;
-		space->locked++;
-		run_begin_presolve_callbacks(space);
-		space->locked--;
+		if(handlers){
+			space->locked++;
+			run_begin_presolve_callbacks(space);
+			space->locked--;
+		}
+		if(midstep){
+			custom_springs(space, &cw);
+			if(cpb200_world_step_presolve(space->world)) cpEngineError("cpSpaceStep (prestep phase)");
+			custom_velocities(space, &cw, dt);
+		}
 		if(cpb200_world_step_finish(space->world)) cpEngineError("cpSpaceStep (solver phase)");
 	} else {
 		if(cpb200_world_step(space->world, dt)) cpEngineError("cpSpaceStep");
 		space->stamp++;
 		space->curr_dt = dt;
 	}
+	if(space->anyCustom) custom_free(&cw);
 	space->hostStale = cpTrue;
 	space->biasStale = cpTrue;
 	space->bbStale = cpTrue;

@@ -73,7 +73,14 @@ typedef struct cpb200_body_desc {
 	int32_t space;                /* index of the owning space within the world */
 	int32_t sleeping;             /* 1 = body is asleep (sleeping.root != NULL) */
 	int32_t sleep_group;          /* bodies asleep together share a group id (component root); -1 when awake */
+	int32_t custom;               /* CPB200_BODY_HOST_POSITION | CPB200_BODY_HOST_VELOCITY: integrated by a host callback */
+	int32_t pad_;
 } cpb200_body_desc;
+/* Bodies with a user-supplied position_func / velocity_func (cpBody.c:482-491): the device skips its own integrator for
+ * them (K1 / K9) and the host layer runs the callback on its mirror at the point of the step where the reference calls it
+ * (cpSpaceStep.c:362-367, 398-404), through the split step. */
+#define CPB200_BODY_HOST_POSITION 1
+#define CPB200_BODY_HOST_VELOCITY 2
 
 /* struct cpShape + cpCircleShape / cpSegmentShape / cpPolyShape (chipmunk_structs.h:177-236). */
 typedef struct cpb200_shape_desc {
@@ -290,6 +297,18 @@ CPB200_API int cpb200_world_set_solver_grid(cpb200_world *w, int blocks);
  * space->constraints (sleeping reorders that array); joints not listed follow in upload order.
  * Applies to the next step only. */
 CPB200_API int cpb200_world_set_joint_order(cpb200_world *w, int n, const int32_t *order);
+/* ---- host callbacks in the middle of a step (custom integrators / spring force functions; SURVEY.md 8b slow path) ----
+ * All three are meant for the gaps of the split step: positions are final after cpb200_world_step_collide, velocities
+ * are integrated (for bodies without CPB200_BODY_HOST_VELOCITY) by cpb200_world_step_presolve. */
+/* state of the listed bodies (any order) */
+CPB200_API int cpb200_world_get_bodies_indexed(cpb200_world *w, int n, const int32_t *indices, cpb200_body_state *out);
+/* vxyw[n][3] = v.x v.y w of the listed bodies (what a custom velocity_func left in the cpBody); their forces are cleared */
+CPB200_API int cpb200_world_set_body_velocities_indexed(cpb200_world *w, int n, const int32_t *indices, const double *vxyw);
+/* f[n] = the value springForceFunc(spring, dist) / springTorqueFunc(spring, relativeAngle) returned for the listed damped
+ * (rotary) springs: the NEXT prestep uses it instead of the default linear law (cpDampedSpring.c:24-27, 50;
+ * cpDampedRotarySpring.c:24-27, 48).  Applies to one prestep only. */
+CPB200_API int cpb200_world_set_spring_forces(cpb200_world *w, int n, const int32_t *joints, const double *f);
+
 /* ---- the PRODUCTION solver order, pinned against the oracle (tests/test_gpu_production_order.py) ----
  * A split step can also stop right before the solver: step_collide -> step_presolve (islands, cache ageing,
  * prestep, velocity integration: everything of cpSpaceStep.c:335-404) -> [read the solver's inputs] ->
