@@ -214,6 +214,15 @@ static int upload(cpb200_world *w, T *dst, const std::vector<T> &src)
 	return 0;
 }
 
+// the same without the wait: for a batch of small uploads from vectors that outlive the batch (one sync at its end)
+template <typename T>
+static int upload_nowait(cpb200_world *w, T *dst, const std::vector<T> &src)
+{
+	if(src.empty()) return 0;
+	CPB_CHECK(cudaMemcpyAsync(dst, src.data(), sizeof(T)*src.size(), cudaMemcpyHostToDevice, w->stream));
+	return 0;
+}
+
 template <typename T>
 static int download(cpb200_world *w, std::vector<T> &dst, const T *src, size_t n)
 {
@@ -942,11 +951,12 @@ extern "C" int cpb200_world_append_shapes(cpb200_world *w, int n, const cpb200_s
 		mat[i] = make_double4(e[i], u[i], surfv[i].x, surfv[i].y); ids[i].x = hashid[i]; ids[i].y = hlocal[i];
 	}
 	if(world_sync(w)) return -1;
-	if(upload(w, S.type + s0, type) || upload(w, S.body + s0, body) || upload(w, S.hashid + s0, hashid) || upload(w, S.hlocal + s0, hlocal) || upload(w, S.sensor + s0, sensor) ||
-	   upload(w, S.cat + s0, cat) || upload(w, S.mask + s0, mask) || upload(w, S.group + s0, group) || upload(w, S.ctype + s0, ctype) || upload(w, S.e + s0, e) || upload(w, S.u + s0, u) ||
-	   upload(w, S.r + s0, r) || upload(w, S.surfv + s0, surfv) || upload(w, S.la + s0, la) || upload(w, S.lb + s0, lb) || upload(w, S.ln + s0, ln) || upload(w, S.atan + s0, atan_) ||
-	   upload(w, S.btan + s0, btan_) || upload(w, S.mat + s0, mat) || upload(w, S.ids + s0, ids) || upload(w, S.filt + s0, filt) || upload(w, S.pcount + s0, pcount) ||
-	   upload(w, S.poff + s0, poff) || upload(w, S.lpv + v0, lpv) || upload(w, S.lpn + v0, lpn)) return -1;
+	if(upload_nowait(w, S.type + s0, type) || upload_nowait(w, S.body + s0, body) || upload_nowait(w, S.hashid + s0, hashid) || upload_nowait(w, S.hlocal + s0, hlocal) || upload_nowait(w, S.sensor + s0, sensor) ||
+	   upload_nowait(w, S.cat + s0, cat) || upload_nowait(w, S.mask + s0, mask) || upload_nowait(w, S.group + s0, group) || upload_nowait(w, S.ctype + s0, ctype) || upload_nowait(w, S.e + s0, e) || upload_nowait(w, S.u + s0, u) ||
+	   upload_nowait(w, S.r + s0, r) || upload_nowait(w, S.surfv + s0, surfv) || upload_nowait(w, S.la + s0, la) || upload_nowait(w, S.lb + s0, lb) || upload_nowait(w, S.ln + s0, ln) || upload_nowait(w, S.atan + s0, atan_) ||
+	   upload_nowait(w, S.btan + s0, btan_) || upload_nowait(w, S.mat + s0, mat) || upload_nowait(w, S.ids + s0, ids) || upload_nowait(w, S.filt + s0, filt) || upload_nowait(w, S.pcount + s0, pcount) ||
+	   upload_nowait(w, S.poff + s0, poff) || upload_nowait(w, S.lpv + v0, lpv) || upload_nowait(w, S.lpn + v0, lpn)) return -1;
+	if(world_sync(w)) return -1;       // the vectors above are locals
 	w->space_base = base;
 	S.n += n; S.nv += n_verts;
 	w->bvh.n = S.n;
@@ -1083,9 +1093,10 @@ extern "C" int cpb200_world_append_joints(cpb200_world *w, int n, const cpb200_j
 	}
 	if(world_sync(w)) return -1;
 	// (colour / hint = -1: a new joint has no colour to keep; the colouring puts it on its worklist)
-	if(upload(w, J.type + j0, type) || upload(w, J.a + j0, a) || upload(w, J.b + j0, b) || upload(w, J.max_force + j0, max_force) || upload(w, J.max_bias + j0, max_bias) ||
-	   upload(w, J.anchor_a + j0, anchor_a) || upload(w, J.anchor_b + j0, anchor_b) || upload(w, J.prm + j0, prm) || upload(w, J.acc + j0, acc) || upload(w, J.aux0 + j0, aux0) ||
-	   upload(w, J.pri + j0, jpri) || upload(w, J.colour + j0, colour) || upload(w, J.hint + j0, hint)) return -1;
+	if(upload_nowait(w, J.type + j0, type) || upload_nowait(w, J.a + j0, a) || upload_nowait(w, J.b + j0, b) || upload_nowait(w, J.max_force + j0, max_force) || upload_nowait(w, J.max_bias + j0, max_bias) ||
+	   upload_nowait(w, J.anchor_a + j0, anchor_a) || upload_nowait(w, J.anchor_b + j0, anchor_b) || upload_nowait(w, J.prm + j0, prm) || upload_nowait(w, J.acc + j0, acc) || upload_nowait(w, J.aux0 + j0, aux0) ||
+	   upload_nowait(w, J.pri + j0, jpri) || upload_nowait(w, J.colour + j0, colour) || upload_nowait(w, J.hint + j0, hint)) return -1;
+	if(world_sync(w)) return -1;       // the vectors above are locals
 	if(new_nocollide){
 		std::sort(nocollide.begin(), nocollide.end());
 		nocollide.erase(std::unique(nocollide.begin(), nocollide.end()), nocollide.end());
@@ -1174,6 +1185,7 @@ static int sl_refresh(cpb200_world *w)
 	w->gSL.release(); memset(&w->SL, 0, sizeof(w->SL)); w->sl_tmp = NULL;
 	const int ns = w->n_spaces, nb = w->B.n;
 	if(w->sl_disabled || nb == 0 || (int)w->body_space.size() != nb) return 0;
+	if((size_t)cpb_div_up(nb, ns)*64 > CPB_SL_MAX_SMEM) return 0;   // the average space is already too large for a CTA: skip the scan (1 M bodies)
 	std::vector<int> first((size_t)ns, -1), count((size_t)ns, 0);
 	for(int i = 0; i < nb; i++){
 		int sp = w->body_space[(size_t)i];

@@ -971,23 +971,18 @@ custom_collect(cpSpace *space, cpCustomWork *cw)
 
 static void custom_free(cpCustomWork *cw){ cpfree(cw->pos); cpfree(cw->vel); cpfree(cw->spring); }
 
-/* mirrors of the listed bodies from the device, forces untouched (the step has not consumed them yet) */
+/* Every mirror current with the device (the user's callback may read any body), the listed bodies' forces untouched:
+ * an ordinary download assumes the step has consumed them (cpBodyUnpackB200), here the step is still in progress. */
 static void
 custom_fetch_bodies(cpSpace *space, int n, const int32_t *idx)
 {
 	if(n == 0) return;
-	cpb200_body_state *st = (cpb200_body_state *)cpcalloc((size_t)n, sizeof(cpb200_body_state));
-	if(cpb200_world_get_bodies_indexed(space->world, n, idx, st)) cpEngineError("body download (custom integrator)");
-	for(int k = 0; k < n; k++){
-		cpBody *b = space->bodies[idx[k]];
-		const cpb200_body_state *s = &st[k];
-		b->p = cpv(s->p[0], s->p[1]); b->v = cpv(s->v[0], s->v[1]); b->a = s->a; b->w = s->w;
-		cpVect rot = cpv(s->rot[0], s->rot[1]), c = b->cog;
-		b->transform = cpTransformNewTranspose(rot.x, -rot.y, b->p.x - (c.x*rot.x - c.y*rot.y), rot.y, rot.x, b->p.y - (c.x*rot.y + c.y*rot.x));
-		b->sleepRoot = (s->sleeping && s->sleep_group >= 0 && s->sleep_group < space->nBodies ? space->bodies[s->sleep_group] : NULL);
-		b->fetchStamp = space->fetchStamp;
-	}
-	cpfree(st);
+	double *keep = (double *)cpcalloc((size_t)n, 3*sizeof(double));
+	for(int k = 0; k < n; k++){ const cpBody *b = space->bodies[idx[k]]; keep[3*k] = b->f.x; keep[3*k + 1] = b->f.y; keep[3*k + 2] = b->t; }
+	space->hostStale = cpTrue;
+	cpSpaceFetchBodiesB200(space);
+	for(int k = 0; k < n; k++){ cpBody *b = space->bodies[idx[k]]; b->f = cpv(keep[3*k], keep[3*k + 1]); b->t = keep[3*k + 2]; }
+	cpfree(keep);
 }
 
 /* cpSpaceStep.c:362-367: position_func of every awake body, before anything else */

@@ -539,6 +539,101 @@ static void arbiter_accessors(void)
 	cpShapeFree(bs); cpBodyFree(ball); cpShapeFree(g); cpSpaceFree(space);
 }
 
+/* 25. demo/Planet.c: a custom velocity function (gravity towards the origin, cpBodyUpdateVelocity with it) on bodies that
+ * orbit a static planet and never touch anything; one body keeps the default integrator in the same space */
+static void planet_gravity(cpBody *body, cpVect gravity, cpFloat damping, cpFloat dt)
+{
+	cpVect p = cpBodyGetPosition(body);
+	cpFloat sqdist = cpvlengthsq(p);
+	cpVect g = cpvmult(p, -5.0e6/(sqdist*cpfsqrt(sqdist)));
+	cpBodyUpdateVelocity(body, g, damping, dt);
+}
+
+static void custom_velocity_func(void)
+{
+	cpSpace *space = cpSpaceNew();
+	cpSpaceSetGravity(space, cpv(0, -10));
+	cpSpaceSetDamping(space, 0.99);
+	cpBody *b[4];
+	for(int i = 0; i < 4; i++){
+		cpFloat r = 200.0 + 60.0*i;
+		b[i] = cpSpaceAddBody(space, cpBodyNew(1.0 + i, 10.0 + i));
+		cpBodySetPosition(b[i], cpv(r, 10.0*i));
+		cpBodySetVelocity(b[i], cpv(0.0, cpfsqrt(5.0e6/r)));
+		cpBodySetAngularVelocity(b[i], 0.1*i);
+		if(i < 3) cpBodySetVelocityUpdateFunc(b[i], planet_gravity);
+		cpShape *s = cpSpaceAddShape(space, cpCircleShapeNew(b[i], 4.0, cpvzero));
+		cpShapeSetFriction(s, 0.5);
+	}
+	for(int k = 0; k < 40; k++){
+		if(k == 10) cpBodySetForce(b[1], cpv(30.0, -20.0));     /* consumed by the custom function's cpBodyUpdateVelocity */
+		if(k == 20) cpBodySetVelocityUpdateFunc(b[2], cpBodyUpdateVelocity);   /* back to the default */
+		cpSpaceStep(space, 1.0/60.0);
+		if(k % 13 == 0 || k == 39) for(int i = 0; i < 4; i++){ char n[48]; sprintf(n, "custom_velocity_%d_%d", k, i); body_line(n, "A", b[i]); }
+	}
+	cpSpaceFree(space);
+}
+
+/* 26. a custom position function (wraps x into [0, 100) after the default update) next to default bodies */
+static void wrap_position(cpBody *body, cpFloat dt)
+{
+	cpBodyUpdatePosition(body, dt);
+	cpVect p = cpBodyGetPosition(body);
+	if(p.x >= 100.0) cpBodySetPosition(body, cpv(p.x - 100.0, p.y));
+}
+
+static void custom_position_func(void)
+{
+	cpShape *g; cpSpace *space = ground_space(&g);
+	cpBody *a = add_ball(space, cpv(90.0, 30.0), 5.0, 1.0, NULL), *b = add_ball(space, cpv(20.0, 4.95), 5.0, 1.0, NULL);
+	cpBodySetVelocity(a, cpv(120.0, 0.0));
+	cpBodySetPositionUpdateFunc(a, wrap_position);
+	for(int k = 0; k < 30; k++){
+		cpSpaceStep(space, 1.0/60.0);
+		if(k % 7 == 0 || k == 29){ char n[48]; sprintf(n, "custom_position_%d_a", k); body_line(n, "A", a); sprintf(n, "custom_position_%d_b", k); body_line(n, "A", b); }
+	}
+	cpSpaceFree(space);
+}
+
+/* 27. demo/Springies.c: a clamped spring force function, and a custom torque function on a rotary spring */
+static cpFloat clamped_spring_force(cpConstraint *spring, cpFloat dist)
+{
+	cpFloat clamp = 20.0;
+	return cpfclamp(cpDampedSpringGetRestLength(spring) - dist, -clamp, clamp)*cpDampedSpringGetStiffness(spring);
+}
+static cpFloat cubic_spring_torque(cpConstraint *spring, cpFloat relativeAngle)
+{
+	cpFloat d = relativeAngle - cpDampedRotarySpringGetRestAngle(spring);
+	return d*d*d*cpDampedRotarySpringGetStiffness(spring);
+}
+
+static void custom_spring_funcs(void)
+{
+	cpSpace *space = cpSpaceNew();
+	cpSpaceSetGravity(space, cpv(0, -30));
+	cpBody *a = cpSpaceAddBody(space, cpBodyNew(1.0, 20.0)), *b = cpSpaceAddBody(space, cpBodyNew(2.0, 30.0));
+	cpBody *c = cpSpaceAddBody(space, cpBodyNew(1.5, 25.0)), *d = cpSpaceAddBody(space, cpBodyNew(1.0, 15.0));
+	cpBodySetPosition(a, cpv(0, 0)); cpBodySetPosition(b, cpv(90, 10)); cpBodySetPosition(c, cpv(0, 200)); cpBodySetPosition(d, cpv(50, 200));
+	cpBodySetAngle(c, 0.9); cpBodySetAngularVelocity(d, 2.0);
+	cpConstraint *s1 = cpSpaceAddConstraint(space, cpDampedSpringNew(a, b, cpv(1, 0), cpv(-1, 0), 40.0, 15.0, 0.8));
+	cpDampedSpringSetSpringForceFunc(s1, clamped_spring_force);
+	cpConstraint *s2 = cpSpaceAddConstraint(space, cpDampedRotarySpringNew(c, d, 0.2, 120.0, 4.0));
+	cpDampedRotarySpringSetSpringTorqueFunc(s2, cubic_spring_torque);
+	/* default law in the same space; through c's centre of gravity it only touches c's linear velocity, the rotary spring
+	 * only its angular velocity: the two commute exactly, so the solver's order cannot show */
+	cpConstraint *s3 = cpSpaceAddConstraint(space, cpDampedSpringNew(cpSpaceGetStaticBody(space), c, cpv(0, 320), cpv(0, 0), 100.0, 8.0, 0.3));
+	for(int k = 0; k < 45; k++){
+		cpSpaceStep(space, 1.0/60.0);
+		if(k % 11 == 0 || k == 44){
+			char n[48];
+			sprintf(n, "custom_spring_%d_a", k); body_line(n, "A", a); sprintf(n, "custom_spring_%d_b", k); body_line(n, "A", b);
+			sprintf(n, "custom_spring_%d_c", k); body_line(n, "A", c); sprintf(n, "custom_spring_%d_d", k); body_line(n, "A", d);
+			printf("custom_spring_%d_impulse A %a %a %a\n", k, cpConstraintGetImpulse(s1), cpConstraintGetImpulse(s2), cpConstraintGetImpulse(s3));
+		}
+	}
+	cpSpaceFree(space);
+}
+
 int main(void)
 {
 	empty_space();
@@ -565,5 +660,8 @@ int main(void)
 	idle_timer_reset();
 	query_after_edit();
 	arbiter_accessors();
+	custom_velocity_func();
+	custom_position_func();
+	custom_spring_funcs();
 	return 0;
 }
