@@ -874,17 +874,22 @@ extern "C" int cpb200_world_set_shapes(cpb200_world *w, int n, const cpb200_shap
 		if(world_sync(w)) return -1;
 		n_rec = std::min(n_rec, A.cap);
 		if(n_rec > 0){
-			uint32_t max_hash = 0;
-			for(size_t i = 0; i < N; i++) max_hash = std::max(max_hash, hashid[i]);
-			std::vector<int> by_hash((size_t)max_hash + 1, -1);
-			for(size_t i = 0; i < N; i++) by_hash[hashid[i]] = (int)i;
+			// new index of every live hashid: a sorted (hashid, index) list, searched per record (hashids come from a counter
+			// that only grows, so a table indexed by hashid would cost as much as every shape the space ever had)
+			std::vector<std::pair<uint32_t, int> > by_hash(N);
+			for(size_t i = 0; i < N; i++) by_hash[i] = std::make_pair(hashid[i], (int)i);
+			std::sort(by_hash.begin(), by_hash.end());
+			auto find_new = [&](uint32_t h) -> int {
+				auto it = std::lower_bound(by_hash.begin(), by_hash.end(), std::make_pair(h, -1));
+				return (it != by_hash.end() && it->first == h ? it->second : -1);
+			};
 			std::vector<int> sa, sb, ba, bb; std::vector<uint64_t> key;
 			if(download(w, sa, A.sa, (size_t)n_rec) || download(w, sb, A.sb, (size_t)n_rec) || download(w, key, A.key, (size_t)n_rec) || world_sync(w)) return -1;
 			ba.resize((size_t)n_rec); bb.resize((size_t)n_rec);
 			for(int i = 0; i < n_rec; i++){
 				int na = -1, nb = -1;
-				if(sa[i] >= 0 && (size_t)sa[i] < old_hashid.size() && old_hashid[sa[i]] <= max_hash) na = by_hash[old_hashid[sa[i]]];
-				if(sb[i] >= 0 && (size_t)sb[i] < old_hashid.size() && old_hashid[sb[i]] <= max_hash) nb = by_hash[old_hashid[sb[i]]];
+				if(sa[i] >= 0 && (size_t)sa[i] < old_hashid.size()) na = find_new(old_hashid[sa[i]]);
+				if(sb[i] >= 0 && (size_t)sb[i] < old_hashid.size()) nb = find_new(old_hashid[sb[i]]);
 				if(na < 0 || nb < 0){ key[i] = ~0ull; sa[i] = sb[i] = 0; ba[i] = bb[i] = 0; } // a shape was removed: record dies in the next carry pass
 				else { sa[i] = na; sb[i] = nb; ba[i] = body[(size_t)na]; bb[i] = body[(size_t)nb]; }
 			}

@@ -175,6 +175,10 @@ struct cpSpace {
 	cpBool appendDirty;
 	cpBool noAppend;           /* env CPB200_NO_APPEND: always take the full re-upload (comparison / validation) */
 	cpBool jointIndexDirty;    /* ... until a removal compacts the host array (cleared by the next upload) */
+	cpBool shapeIndexDirty;    /* a removal compacted space->shapes / bodies: device records can no longer be mapped to host objects,
+	                              the arbiter mirrors fetched BEFORE that removal stay in use until the next step */
+	cpBool jointsDirty;        /* only constraint parameters changed: the joints are re-uploaded, nothing else */
+	cpBool shapesDirty;        /* only shape parameters changed: the shapes are re-uploaded, nothing else */
 	unsigned fetchStamp;       /* bumped by every download; bodies unpack their record on first access */
 	cpBool someMirrorsStale;   /* a download happened and not every body has unpacked its record yet */
 	cpBool bbStale, arbStale, jointStale;

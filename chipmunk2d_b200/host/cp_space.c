@@ -123,14 +123,16 @@ cpBool cpSpaceIsLocked(cpSpace *space){ return (space->locked > 0); }
 void cpSpaceMarkTopologyDirty(cpSpace *space){ space->topologyDirty = cpTrue; }
 /* a re-parameterised object forces the full re-upload only if the device already holds it: one that was added since the
  * last sync is still waiting for its (first) upload as part of an appended range */
-void cpSpaceMarkBodyDirtyB200(cpBody *body){ cpSpace *sp = body->space; if(sp && !(sp->appendDirty && !sp->topologyDirty && body->index >= sp->nBodiesOnDevice)) sp->topologyDirty = cpTrue; }
-void cpSpaceMarkShapeDirtyB200(cpShape *shape){ cpSpace *sp = shape->space; if(sp && !(sp->appendDirty && !sp->topologyDirty && shape->index >= sp->nShapesOnDevice)) sp->topologyDirty = cpTrue; }
-void cpSpaceMarkConstraintDirtyB200(cpConstraint *c){ cpSpace *sp = c->space; if(sp && !(sp->appendDirty && !sp->topologyDirty && c->index >= sp->nConstraintsOnDevice)) sp->topologyDirty = cpTrue; }
+/* (mass, moment, type, centre of gravity and integrator changes travel with the ordinary body upload; parameter changes of
+ * shapes / constraints re-upload that object class only -- a per-frame cpSimpleMotorSetRate must not re-upload the world) */
+void cpSpaceMarkBodyDirtyB200(cpBody *body){ cpSpace *sp = body->space; if(sp && !(sp->appendDirty && !sp->topologyDirty && body->index >= sp->nBodiesOnDevice)) sp->bodiesDirty = cpTrue; }
+void cpSpaceMarkShapeDirtyB200(cpShape *shape){ cpSpace *sp = shape->space; if(sp && !(sp->appendDirty && !sp->topologyDirty && shape->index >= sp->nShapesOnDevice)) sp->shapesDirty = cpTrue; }
+void cpSpaceMarkConstraintDirtyB200(cpConstraint *c){ cpSpace *sp = c->space; if(sp && !(sp->appendDirty && !sp->topologyDirty && c->index >= sp->nConstraintsOnDevice)) sp->jointsDirty = cpTrue; }
 /* an addition keeps the device's objects where they are if nothing else is pending */
 static cpBool
 can_append(const cpSpace *space)
 {
-	return space->world != NULL && !space->topologyDirty && !space->noAppend && space->locked == 0;
+	return space->world != NULL && !space->topologyDirty && !space->shapesDirty && !space->jointsDirty && !space->noAppend && space->locked == 0;
 }
 void cpSpaceSetSolverModeB200(cpSpace *space, int mode){ space->solverMode = mode; space->paramsDirty = cpTrue; }
 
@@ -296,7 +298,30 @@ sync_before_edit(cpSpace *space)
 	cpSpaceFetchBodiesB200(space);
 	cpSpaceFetchBiasB200(space);
 	if(space->jointStale) cpSpaceFetchJointsB200(space);
-	space->arbStale = cpTrue;
+}
+
+/* The arbiter mirrors of the last step stay in use across host-side edits (cpBodyEachArbiter, the getters, separate
+ * callbacks of later removals): before a removal compacts the host arrays they are fetched while device records can still
+ * be mapped to host objects, and the mirrors that touch the removed shape are dropped afterwards. */
+static void
+drop_arbiters_of_shape(cpSpace *space, cpShape *shape)
+{
+	int m = 0;
+	for(int i = 0; i < space->nBodies; i++) space->bodies[i]->firstArb = -1;
+	for(int k = 0; k < space->nArbs; k++){
+		cpArbiter *arb = &space->arbs[k];
+		if(arb->a == shape || arb->b == shape) continue;
+		if(m != k) space->arbs[m] = *arb;
+		arb = &space->arbs[m];
+		arb->next_a = arb->next_b = -1;
+		/* (the same rule cpSpaceFetchArbitersB200 threads by) */
+		if(arb->active || (arb->count > 0 && arb->state != CP_ARBITER_STATE_CACHED && (arb->body_a->sleepRoot || arb->body_b->sleepRoot))){
+			arb->next_a = arb->body_a->firstArb; arb->body_a->firstArb = m;
+			arb->next_b = arb->body_b->firstArb; arb->body_b->firstArb = m;
+		}
+		m++;
+	}
+	space->nArbs = m;
 }
 
 void
@@ -304,18 +329,22 @@ cpSpaceRemoveShape(cpSpace *space, cpShape *shape)
 {
 	cpAssertHard(cpSpaceContainsShape(space, shape), "Cannot remove a shape that was not added to the space. (Removed twice maybe?)");
 	cpAssertSpaceUnlocked(space);
-	if((space->nHandlers > 0 || space->hasDefaultHandler) && space->world && !space->topologyDirty){
-		/* arbiters of the removed shape separate now (cpSpaceFilterArbiters, cpSpace.c:482-511) */
+	if(space->world && shape->index < space->nShapesOnDevice){
+		/* arbiters of the removed shape separate now (cpSpaceFilterArbiters, cpSpace.c:482-511) -- on EVERY removal, also the
+		 * second one inside the same post-step callback */
 		if(space->arbStale) cpSpaceFetchArbitersB200(space);
-		space->locked++;
-		for(int k = 0; k < space->nArbs; k++){
-			cpArbiter *arb = &space->arbs[k];
-			if((arb->a == shape || arb->b == shape) && arb->state != CP_ARBITER_STATE_CACHED && arb->stamp == space->stamp){
-				arb->state = CP_ARBITER_STATE_INVALIDATED;
-				arb->handler->separateFunc(arb, space, arb->handler->userData);
+		if(space->nHandlers > 0 || space->hasDefaultHandler){
+			space->locked++;
+			for(int k = 0; k < space->nArbs; k++){
+				cpArbiter *arb = &space->arbs[k];
+				if((arb->a == shape || arb->b == shape) && arb->state != CP_ARBITER_STATE_CACHED && arb->stamp == space->stamp){
+					arb->state = CP_ARBITER_STATE_INVALIDATED;
+					arb->handler->separateFunc(arb, space, arb->handler->userData);
+				}
 			}
+			space->locked--;
 		}
-		space->locked--;
+		drop_arbiters_of_shape(space, shape);
 	}
 	sync_before_edit(space);
 	cpBody *body = shape->body;
@@ -326,6 +355,7 @@ cpSpaceRemoveShape(cpSpace *space, cpShape *shape)
 	shape->space = NULL;
 	shape->index = -1;
 	space->topologyDirty = cpTrue;
+	space->shapeIndexDirty = cpTrue;
 }
 
 void
@@ -650,6 +680,15 @@ sync_to_device(cpSpace *space)
 		space->topologyDirty = cpFalse;
 		space->bodiesDirty = cpFalse;
 		space->forcesDirty = cpFalse;
+		space->shapesDirty = space->jointsDirty = cpFalse;
+		space->shapeIndexDirty = cpFalse;
+	} else if(space->shapesDirty || space->jointsDirty){
+		/* parameters of shapes / constraints only (host slots still equal device indices: removals set topologyDirty) */
+		if(space->bodiesDirty){ cpSpaceFetchBodiesB200(space); cpSpaceFetchBiasB200(space); upload_bodies(space, cpFalse); }
+		else if(space->forcesDirty){ cpSpaceUnpackAllB200(space); upload_forces(space); }
+		if(space->shapesDirty) upload_shapes(space);
+		if(space->jointsDirty){ if(space->jointStale) cpSpaceFetchJointsB200(space); upload_joints(space); }
+		space->bodiesDirty = space->forcesDirty = space->shapesDirty = space->jointsDirty = cpFalse;
 	} else if(space->bodiesDirty){
 		cpSpaceFetchBodiesB200(space);
 		cpSpaceFetchBiasB200(space);
@@ -796,6 +835,7 @@ void
 cpSpaceFetchArbitersB200(cpSpace *space)
 {
 	space->arbStale = cpFalse;
+	if(space->shapeIndexDirty) return;   /* device records cannot be mapped to host objects any more: the mirrors fetched before the removal stay */
 	/* remember the user data of the outgoing mirrors */
 	space->nArbData = 0;
 	for(int i = 0; i < space->nArbs; i++){
@@ -808,7 +848,7 @@ cpSpaceFetchArbitersB200(cpSpace *space)
 	}
 	for(int i = 0; i < space->nBodies; i++) space->bodies[i]->firstArb = -1;
 	space->nArbs = 0;
-	if(!space->world || space->topologyDirty) return;
+	if(!space->world) return;
 	/* everything in the cache: active, dormant (sleeping) and cached-for-persistence records */
 	int n = cpb200_world_get_arbiters(space->world, 0, NULL, 0);
 	if(n < 0) cpEngineError("arbiter download");
@@ -820,7 +860,7 @@ cpSpaceFetchArbitersB200(cpSpace *space)
 	cpSpaceFetchBodiesB200(space);
 	for(int i = 0; i < n; i++){
 		const cpb200_arbiter *r = &recs[i];
-		if(r->shape_a < 0 || r->shape_a >= space->nShapes || r->shape_b < 0 || r->shape_b >= space->nShapes) continue;
+		if(r->shape_a < 0 || r->shape_a >= space->nShapesOnDevice || r->shape_a >= space->nShapes || r->shape_b < 0 || r->shape_b >= space->nShapesOnDevice || r->shape_b >= space->nShapes) continue;
 		cpArbiter *arb = &space->arbs[space->nArbs];
 		memset(arb, 0, sizeof(*arb));
 		arb->space = space;

@@ -634,6 +634,38 @@ static void custom_spring_funcs(void)
 	cpSpaceFree(space);
 }
 
+/* 28. two touching shapes removed inside ONE post-step callback: separate must fire for every arbiter of both
+ * (cpSpaceRemoveShape -> cpSpaceFilterArbiters, cpSpace.c:482-511), and cpBodyEachArbiter keeps working between edits */
+static int g_separates = 0, g_each = 0;
+static void count_separate(cpArbiter *arb, cpSpace *space, cpDataPointer data){ g_separates++; }
+static void count_each(cpBody *body, cpArbiter *arb, void *data){ g_each++; }
+static cpShape *g_rm[2]; static cpBody *g_rb[2];
+static void remove_both(cpSpace *space, void *key, void *data)
+{
+	cpSpaceRemoveShape(space, g_rm[0]);
+	g_each = 0; cpBodyEachArbiter(g_rb[1], count_each, NULL);      /* the other ball still sees its arbiters after the first edit */
+	printf("remove_two_between E %a %a\n", (double)g_separates, (double)g_each);
+	cpSpaceRemoveShape(space, g_rm[1]);
+	printf("remove_two_after E %a\n", (double)g_separates);
+}
+static void remove_two_in_one_callback(void)
+{
+	cpShape *g; cpSpace *space = ground_space(&g);
+	cpCollisionHandler *h = cpSpaceAddDefaultCollisionHandler(space);
+	h->separateFunc = count_separate;
+	g_rb[0] = add_ball(space, cpv(0.0, 4.95), 5.0, 1.0, &g_rm[0]);
+	g_rb[1] = add_ball(space, cpv(9.9, 4.95), 5.0, 1.0, &g_rm[1]);
+	g_separates = 0;
+	for(int k = 0; k < 5; k++) cpSpaceStep(space, 1.0/60.0);
+	g_each = 0; cpBodyEachArbiter(g_rb[0], count_each, NULL);
+	printf("remove_two_before E %a %a\n", (double)g_separates, (double)g_each);
+	cpSpaceAddPostStepCallback(space, remove_both, (void *)&g_rm, NULL);
+	cpSpaceStep(space, 1.0/60.0);
+	cpSpaceStep(space, 1.0/60.0);
+	printf("remove_two_end E %a\n", (double)g_separates);
+	cpSpaceFree(space);
+}
+
 int main(void)
 {
 	empty_space();
@@ -663,5 +695,6 @@ int main(void)
 	custom_velocity_func();
 	custom_position_func();
 	custom_spring_funcs();
+	remove_two_in_one_callback();
 	return 0;
 }
