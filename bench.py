@@ -43,7 +43,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_PILE = 1000000
-N_BATCH = 4096
+N_BATCH = int(os.environ.get("CPB200_BENCH_SPACES", "4096"))   # (override: per-GPU tuning runs of the batched workload)
 CPU_SAMPLE_PILE = 100000      # cpu_baseline leg of the GPU arm: a bounded sample (about 10-20 s of host work)
 CPU_SAMPLE_MIXED = 20000
 SETTLE = {"pile1m": 20, "pile1m_nosleep": 20, "pile1m_shallow": 600, "batch": 300, "batch_sharded": 300, "c1": 300, "c2": 300, "mixed100k": 120}
@@ -188,7 +188,30 @@ def _ref_penetration(rs):
     return pen
 
 
-def reference_run(workload, steps, warmup, settle, sample=None, hasty=False, threads=0):
+def reference_run(*args, **kw):
+    """reference_run_ on a thread with a 1 GB stack: cpSpaceProcessComponents flood-fills the contact graph recursively
+    (FloodFillComponent, cpSpaceComponent.c:168-198), and a 500 000-body pile with sleeping enabled overflows the default
+    8 MB stack of the unmodified reference (segmentation fault inside cpSpaceStep; 300 000 bodies still fit)."""
+    box = {}
+
+    def work():
+        try:
+            box["r"] = reference_run_(*args, **kw)
+        except BaseException as exc:      # noqa: BLE001 -- re-raised on the caller's thread
+            box["e"] = exc
+    old = threading.stack_size(1 << 30)
+    try:
+        t = threading.Thread(target=work)
+        t.start()
+        t.join()
+    finally:
+        threading.stack_size(old)
+    if "e" in box:
+        raise box["e"]
+    return box.get("r")
+
+
+def reference_run_(workload, steps, warmup, settle, sample=None, hasty=False, threads=0):
     """The unmodified reference (oracle/_ref) stepping `workload` (or a bounded sample of its generator) on the host.
     A single space runs cpSpaceStep on one thread (or cpHastySpaceStep on its solver threads); independent spaces (the
     batched workload) run one cpSpace per host core over all cores -- ctypes releases the GIL inside the library."""
@@ -268,7 +291,8 @@ def run_reference(args):
         emit({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"})
         return
     if not args.workload.startswith("batch"):
-        h = reference_run(args.workload, steps, warm, settle, sample=sample, hasty=True, threads=0)
+        big = args.workload.startswith("pile1m")
+        h = reference_run(args.workload, (2 if big else steps), (1 if big else warm), (2 if big and args.workload != "pile1m_shallow" else settle), sample=sample, hasty=True, threads=0)
         if h:
             base["hasty"] = {k: h[k] for k in ("value", "unit", "cores", "ms_per_step", "sample")}
     line = {"impl": "reference", "metric": "body_steps_per_sec", "value": base["value"], "unit": "body-steps/s", "n_gpus": args.gpus,

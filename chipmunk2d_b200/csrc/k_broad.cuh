@@ -191,10 +191,15 @@ __global__ void k_bvh_refit(DBvh T)
 	if(i >= n || n < 2) return;
 	int cur = T.parent[(n - 1) + i];
 	while(cur >= 0){
-		__threadfence();
+		// one acquire-release atomic instead of fence + atomic + fence: the first child to arrive releases the box it wrote,
+		// the second acquires it (the stand-alone fences were most of this kernel's 20-level latency chain)
+#ifndef CPB_EMU
+		int old;
+		asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(&T.flags[cur]) : "memory");
+#else
 		int old = atomicAdd(&T.flags[cur], 1);
+#endif
 		if(old == 0) return; // first child to arrive: the sibling's thread finishes this node
-		__threadfence();
 		int l = T.left[cur], r = T.right[cur];
 		// children were written by other threads (possibly other SMs): read through L2
 		double4 a = ld_cg4(&T.nbb[l]);
