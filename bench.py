@@ -460,7 +460,7 @@ def roofline_of(rec, workload):
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     loc = rec["_local"]
     st2, iterations, nb = loc["st2"], loc["iterations"], loc["nb"]
-    solve_us = rec["stage_us"].get("colour_solve", 0.0)
+    solve_us = rec["stage_us"].get("solve", 0.0)
     alg = algorithmic_bytes_solver(st2["n_contacts"], st2["n_joints"], iterations)
     achieved = alg / (solve_us * 1e-6) / 1e9 if solve_us > 0 else 0.0
     traffic = None
@@ -474,7 +474,7 @@ def roofline_of(rec, workload):
         dram_frac = float(traffic) / (solve_us * 1e-6) / 1e9 / peak
     whole = 264.0 * nb + 108.0 * nb + 32.0 * st2["n_shapes"] + (8.0 + 170.0) * st2["n_pairs"] + 64.0 * st2["n_arbiters"] + 400.0 * st2["n_contacts"] + 384.0 * iterations * st2["n_contacts"]
     step_s = loc["ms_local"] / rec["steps"] * 1e-3
-    out = {"bound": "hbm", "kernel": "k_colour_solve (persistent colouring + warm start + %d Gauss-Seidel iterations)" % iterations,
+    out = {"bound": "hbm", "kernel": "k_colour_solve<..., PHASE 2> (persistent: warm start + %d Gauss-Seidel iterations + write-back; the colouring + row build is a launch of its own, stage colour_rows)" % iterations,
            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
            "frac_on_dram_bytes": dram_frac,
            "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg, "launch_us": solve_us,

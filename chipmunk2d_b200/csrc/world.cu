@@ -81,11 +81,11 @@ extern "C" int cpb200_device_available(void)
 // ------------------------------------------------------------------ stages (profiling)
 enum {
 	ST_INTEGRATE_POS, ST_SHAPE_CACHE, ST_BVH_KEYS, ST_BVH_SORT, ST_BVH_BUILD, ST_BVH_PAIRS,
-	ST_COLLIDE, ST_ISLANDS, ST_CARRY, ST_PRESTEP, ST_INTEGRATE_VEL, ST_SOLVE, ST_COUNT
+	ST_COLLIDE, ST_ISLANDS, ST_CARRY, ST_PRESTEP, ST_INTEGRATE_VEL, ST_COLOUR, ST_SOLVE, ST_COUNT
 };
 static const char *g_stage_names[ST_COUNT] = {
 	"integrate_pos", "shape_cache", "bvh_keys", "bvh_sort", "bvh_build", "bvh_pairs",
-	"collide", "islands", "arbiter_carry", "prestep", "integrate_vel", "colour_solve"
+	"collide", "islands", "arbiter_carry", "prestep", "integrate_vel", "colour_rows", "solve"
 };
 extern "C" const char *cpb200_stage_name(int i){ return (i >= 0 && i < ST_COUNT) ? g_stage_names[i] : ""; }
 
@@ -1476,6 +1476,7 @@ static int step_phase_b2(cpb200_world *w)
 	const int nb = B.n;
 	const int wide = w->sm_count*8;
 	w->mid_solve = false;
+	STAGE_END(w, ST_COLOUR);   // (re-recorded after the colouring kernel on the production path)
 
 	if(w->solver_mode == 1){
 		int need = Ac.cap;
@@ -1517,6 +1518,7 @@ static int step_phase_b2(cpb200_world *w)
 			void *k_colour = space_local ? (void *)k_colour_solve<true, true, true, 1, 2> : (void *)k_colour_solve<false, true, true, 1, 2>;
 			CPB_CHECK(cudaLaunchCooperativeKernel(k_colour, dim3(blocks), dim3(256), args, 0, st));
 			g_cpb_launches++;
+			STAGE_END(w, ST_COLOUR);
 			if(!space_local){
 				const int m3 = (w->solve_minb == 3 ? 1 : 0);
 				static void *const k_iterate[2][2][2] = {   // [stream_rows][joints][min blocks 2 | 3]

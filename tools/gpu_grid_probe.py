@@ -12,5 +12,5 @@ for name, sc, warm in (("mixed100k", mixed_drop(100000), 120), ("pile100k", circ
         w.set_profiling(True)
         for _ in range(3): w.step(sc.dt)
         sp = w.solver_profile(); st = w.stage_times()
-        print("%-10s grid %3d  %.3f ms/step  solve %.0f us (colour %.0f rows %.0f warm %.0f iterate %.0f)" % (name, g, ms, st["colour_solve"], sp["colour_us"], sp["rows_us"], sp["warm_us"], sp["iterate_us"]), flush=True)
+        print("%-10s grid %3d  %.3f ms/step  solve %.0f us (colour %.0f rows %.0f warm %.0f iterate %.0f)" % (name, g, ms, st["solve"], sp["colour_us"], sp["rows_us"], sp["warm_us"], sp["iterate_us"]), flush=True)
         w.close()

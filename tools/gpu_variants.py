@@ -30,5 +30,5 @@ if __name__ == "__main__":
         if only and name not in only.split(","): continue
         for lib in libs:
             ms, sp, st = run(os.path.join(ROOT, "chipmunk2d_b200/lib", lib), sc, warm, steps)
-            print("%-10s %-22s %.3f ms/step  solve %.0f us (colour %.0f rows %.0f warm %.0f iterate %.0f) colours %d" % (name, lib, ms, st["colour_solve"], sp["colour_us"], sp["rows_us"], sp["warm_us"], sp["iterate_us"], sp["n_colours"]), flush=True)
+            print("%-10s %-22s %.3f ms/step  solve %.0f us (colour %.0f rows %.0f warm %.0f iterate %.0f) colours %d" % (name, lib, ms, st["solve"], sp["colour_us"], sp["rows_us"], sp["warm_us"], sp["iterate_us"], sp["n_colours"]), flush=True)
             if os.environ.get("STAGES"): print("      " + "  ".join("%s %.0f" % (k, v) for k, v in st.items()), flush=True)
