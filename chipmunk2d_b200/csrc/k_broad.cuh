@@ -442,14 +442,15 @@ struct DSpaceShapes { const int *shape0, *nshape; };   // contiguous shape range
 // are dealt out to the threads one each: the expensive part -- filter gathers, constraint lookup, list append --
 // runs with full, converged warps, 32 pairs per ballot and global atomic.  (Doing (2) inside (1) ran the
 // expensive path once per hit with 14 of 32 lanes active on average and waited for a global atomic each time.)
-#define CPB_SLP_CAND 2048
-__global__ void k_sl_pairs(DSpaceShapes SS, DShapes S, DBodies B, DPairs P, const uint64_t *__restrict__ nocollide, int n_nocollide, int *overflow)
+// (cand_cap candidates per CTA, sized by the host: 2048 for the batched demo spaces, 4 x shapes for one larger space)
+__global__ void k_sl_pairs(DSpaceShapes SS, DShapes S, DBodies B, DPairs P, const uint64_t *__restrict__ nocollide, int n_nocollide, int *overflow, int max_nshape, int cand_cap)
 {
-	extern __shared__ double4 s_bb[];                 // [n] AABBs, then [n] ints: active flags
-	__shared__ unsigned s_cand[CPB_SLP_CAND];
+	extern __shared__ double4 s_bb[];                 // [max_nshape] AABBs, then [max_nshape] ints: active flags, then [cand_cap] candidates
 	__shared__ int s_ncand;
 	const int sp = blockIdx.x, s0 = SS.shape0[sp], n = SS.nshape[sp];
-	int *s_act = (int *)(s_bb + n);
+	int *s_act = (int *)(s_bb + max_nshape);
+	unsigned *s_cand = (unsigned *)(s_act + max_nshape);
+	const int CPB_SLP_CAND = cand_cap;
 	if(threadIdx.x == 0) s_ncand = 0;
 	for(int k = threadIdx.x; k < n; k += blockDim.x){
 		s_bb[k] = S.bb[s0 + k];

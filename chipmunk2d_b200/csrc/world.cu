@@ -32,7 +32,8 @@ unsigned long long g_cpb_launches = 0;
 #ifndef CPB_CARRY_CTAS
 #define CPB_CARRY_CTAS 16
 #endif
-#define CPB_SL_MAX_SHAPES 512          // a space up to this many shapes is broadphased all-pairs in one CTA (k_sl_pairs)
+#define CPB_SL_MAX_SHAPES 2048         // a space up to this many shapes is broadphased all-pairs in one CTA (k_sl_pairs): a 1000-body
+                                       // scene is ~1 M box tests from shared memory, ten microseconds, instead of the LBVH's 17 launches
 #define CPB_SL_MAX_SMEM (200*1024)   // shared memory a space's velocity sectors may take in k_sl_solve
 
 // ------------------------------------------------------------------ errors
@@ -290,7 +291,7 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 		{ const char *e = getenv("CPB200_SOLVE_MINB"); w->solve_minb = (e && atoi(e) == 3 ? 3 : 2); }
 		cudaFuncSetAttribute(k_sl_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CPB_SL_MAX_SMEM);
 		cudaFuncSetAttribute(k_sl_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CPB_SL_MAX_SMEM);
-		cudaFuncSetAttribute(k_sl_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, CPB_SL_MAX_SHAPES*(int)(sizeof(double4) + sizeof(int)));
+		cudaFuncSetAttribute(k_sl_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, CPB_SL_MAX_SHAPES*(int)(sizeof(double4) + sizeof(int) + 4*sizeof(unsigned)));
 	}
 #endif
 	cpb200_space_params def;
@@ -1319,9 +1320,11 @@ static int step_phase_a(cpb200_world *w, double dt)
 	if(sl_broad){
 #ifndef CPB_EMU
 		STAGE_END(w, ST_BVH_KEYS); STAGE_END(w, ST_BVH_SORT); STAGE_END(w, ST_BVH_BUILD);
-		int threads = 32; while(threads < 256 && threads < w->sl_max_nshape) threads *= 2;
-		size_t smem = (size_t)w->sl_max_nshape*(sizeof(double4) + sizeof(int));
-		LAUNCH_SMEM(k_sl_pairs, w->n_spaces, threads, smem, st, w->SS, S, B, w->P, (const uint64_t *)w->d_nocollide, w->n_nocollide, &w->C->overflow);
+		int threads = 32; while(threads < 1024 && threads < w->sl_max_nshape) threads *= 2;
+		if(w->n_spaces > 1 && threads > 256) threads = 256;   // many spaces: more resident CTAs beat wider ones
+		const int cand_cap = std::max(2048, 4*w->sl_max_nshape);
+		size_t smem = (size_t)w->sl_max_nshape*(sizeof(double4) + sizeof(int)) + sizeof(unsigned)*(size_t)cand_cap;
+		LAUNCH_SMEM(k_sl_pairs, w->n_spaces, threads, smem, st, w->SS, S, B, w->P, (const uint64_t *)w->d_nocollide, w->n_nocollide, &w->C->overflow, w->sl_max_nshape, cand_cap);
 		STAGE_END(w, ST_BVH_PAIRS);
 #endif
 	} else if(ns >= 2){
