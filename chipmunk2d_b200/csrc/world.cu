@@ -32,8 +32,8 @@ unsigned long long g_cpb_launches = 0;
 #ifndef CPB_CARRY_CTAS
 #define CPB_CARRY_CTAS 16
 #endif
-#define CPB_SL_MAX_SHAPES 2048         // a space up to this many shapes is broadphased all-pairs in one CTA (k_sl_pairs): a 1000-body
-                                       // scene is ~1 M box tests from shared memory, ten microseconds, instead of the LBVH's 17 launches
+#define CPB_SL_MAX_SHAPES 512          // a space up to this many shapes is broadphased all-pairs in one CTA (k_sl_pairs).  (2048 was tried for
+                                       // the 1000-body Bench scenes: one CTA needs 166 us for their 1.1 M box tests, the LBVH's 17 launches 80 us.)
 #define CPB_SL_MAX_SMEM (200*1024)   // shared memory a space's velocity sectors may take in k_sl_solve
 
 // ------------------------------------------------------------------ errors
