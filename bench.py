@@ -441,7 +441,8 @@ def measure(workload, args, ctx, full):
            "contacts_solved_per_sec": total_contacts * steps / t_max,
            "contact_iterations_per_sec": total_contacts * iterations * steps / t_max,
            "per_step": {"bodies": total_bodies, "spaces": total_spaces, "pairs": total_pairs, "arbiters": total_arbs, "contacts": total_contacts, "colours": st["n_colours"],
-                        "awake_bodies": total_awake, "max_penetration": float(mx[0]), "kinetic_energy": total_ke},
+                        "awake_bodies": total_awake, "max_penetration": float(mx[0]), "kinetic_energy": total_ke,
+                        "idle_row_fraction": (st["n_row_idle"] / st["n_row_solves"] if st["n_row_solves"] else None)},
            "gpu_launches": int(launches), "e2e": e2e, "stage_us": acc, "solver_us": sp}
     if e2e_api is not None:
         rec["e2e_per_body_api"] = e2e_api

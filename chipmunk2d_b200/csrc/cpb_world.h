@@ -197,7 +197,8 @@ struct DCounters {
 	int n_cached;
 	uint32_t stamp;        // space->stamp (cpSpaceStep.c:349): advanced on the device by k_reset_step, so a captured step graph replays it
 	int no_gjk_stage;      // experiment switch (env CPB200_NO_GJK_STAGE): k_collide<2> reads polygon vertices from global memory
-	int pad[2];
+	int n_row_solves;      // rows x iterations the world-wide solver visited this step ...
+	int n_row_idle;        // ... and how many of those changed neither body (clamped impulses: all four scatters skipped)
 };
 
 #define CPB_MAX_COLOURS 64

@@ -446,10 +446,11 @@ template<bool STREAM> struct RowContact {
 // one colour-sorted row: mode 0 = warm start, 1 = iteration
 // (ba, bb, cnt) are passed in: the persistent kernel fetches them for a thread's next row while the previous
 // phase is still draining, so that after the barrier the velocity gathers do not wait for an index load
-template<class VS> CPB_DEVICE void solve_row_idx(const VS &vs, const DBodies &B, const DRows &R, int r, int ba, int bb, int cnt, int mode, double dt_coef){
+// returns true if the row changed a body (iteration passes; warm start always counts as changed)
+template<class VS> CPB_DEVICE bool solve_row_idx(const VS &vs, const DBodies &B, const DRows &R, int r, int ba, int bb, int cnt, int mode, double dt_coef){
 	bool first = (cnt < 0);
 	if(first) cnt = -cnt;
-	if(mode == 0 && first) return;
+	if(mode == 0 && first) return true;
 	double4 Va = vs.ldV(ba), Vb = vs.ldV(bb);
 	V2 n = row_ld<VS::STREAM>(&R.n[r]);
 	if(mode == 0){
@@ -461,7 +462,7 @@ template<class VS> CPB_DEVICE void solve_row_idx(const VS &vs, const DBodies &B,
 		}
 		if(dyn_a) vs.stV(ba, Va);
 		if(dyn_b) vs.stV(bb, Vb);
-		return;
+		return true;
 	}
 	double4 VBa = vs.ldVB(ba), VBb = vs.ldVB(bb);
 	// (m_inv, i_inv) ride in the spare lanes of the two velocity sectors
@@ -484,6 +485,7 @@ template<class VS> CPB_DEVICE void solve_row_idx(const VS &vs, const DBodies &B,
 	if(dyn_a){ vs.stV(ba, Va); vs.stVB(ba, VBa); }
 	if(dyn_b){ vs.stV(bb, Vb); vs.stVB(bb, VBb); }
 #endif
+	return dirty.va || dirty.vb || dirty.vba || dirty.vbb;
 }
 
 CPB_DEVICE void solve_row(const DBodies &B, const DRows &R, int r, int mode, double dt_coef){
@@ -808,6 +810,7 @@ template<bool SPACE_LOCAL, bool STREAM_ROWS, bool JOINTS, int PHASE, int MINB> _
 	const int jtid = nth - 1 - tid;
 	const VelGlobalT<STREAM_ROWS> vg = {B.V, B.VB};
 	const bool PHASE_PREFETCH = (STREAM_ROWS && (use_hints & 2) == 0);   // bit 1 of use_hints: experiment switch, prefetch off
+	int n_solves = 0, n_idle = 0;                // step statistics: row visits of the iteration passes / visits that changed nothing
 	int pr = -1, pba = 0, pbb = 0, pcnt = 0;     // prefetched row
 	int pq = -1, pj = 0, pja = 0, pjb = 0;       // prefetched joint
 	#define PREFETCH_PHASE(c_) do { \
@@ -822,7 +825,8 @@ template<bool SPACE_LOCAL, bool STREAM_ROWS, bool JOINTS, int PHASE, int MINB> _
 				int r = pr, ba = pba, bb = pbb, cnt = pcnt;
 				pr += nth;
 				if(pr < r1){ pba = row_ld<STREAM_ROWS>(&R.ba[pr]); pbb = row_ld<STREAM_ROWS>(&R.bb[pr]); pcnt = row_ld<STREAM_ROWS>(&R.cnt[pr]); row_prefetch(R, pr); } else pr = -1;
-				solve_row_idx(vg, B, R, r, ba, bb, cnt, mode, dt_coef);
+				const bool moved = solve_row_idx(vg, B, R, r, ba, bb, cnt, mode, dt_coef);
+				if(mode){ n_solves++; n_idle += (moved ? 0 : 1); }
 			}
 			while(JOINTS && pq >= 0){
 				int j = pj, a = pja, b = pjb;
@@ -841,6 +845,10 @@ template<bool SPACE_LOCAL, bool STREAM_ROWS, bool JOINTS, int PHASE, int MINB> _
 		if(pass == 0) PROF(3);
 	}
 	#undef PREFETCH_PHASE
+	{
+		n_solves = __reduce_add_sync(0xffffffffu, n_solves); n_idle = __reduce_add_sync(0xffffffffu, n_idle);
+		if((threadIdx.x & 31) == 0 && n_solves){ atomicAdd(&C->n_row_solves, n_solves); atomicAdd(&C->n_row_idle, n_idle); }
+	}
 	PROF(4);
 	int n_rows = K.cstart[CPB_MAX_COLOURS];
 	rows_writeback(A, R, n_rows, tid, nth);

@@ -1147,7 +1147,7 @@ __global__ void k_reset_step(DCounters *C, int *pair_count, int *cur_count, int 
 	if(CPB_TID != 0) return;
 	C->stamp++;            // cpSpaceStep.c:349
 	C->n_pairs[0] = C->n_pairs[1] = C->n_pairs[2] = 0;
-	C->n_contacts = 0; C->n_active = 0; C->n_colours = 0; C->n_cached = 0;
+	C->n_contacts = 0; C->n_active = 0; C->n_colours = 0; C->n_cached = 0; C->n_row_solves = 0; C->n_row_idle = 0;
 	C->colour_remaining[0] = C->colour_remaining[1] = 0; C->colour_rounds = 0; C->n_overflow_colour = 0;
 	pair_count[0] = pair_count[1] = pair_count[2] = pair_count[3] = 0;
 	*cur_count = 0;
@@ -2006,6 +2006,7 @@ extern "C" int cpb200_world_get_stats(cpb200_world *w, cpb200_stats *out)
 	out->n_arbiters = (uint32_t)w->hC->n_active; out->n_contacts = (uint32_t)w->hC->n_contacts;
 	out->n_cached = (uint32_t)w->hC->n_cached; out->n_colours = (uint32_t)w->hC->n_colours; out->overflow = (uint32_t)w->hC->overflow;
 	out->kinetic_energy = w->h_scratch[0]; out->max_penetration = w->h_scratch[1];
+	out->n_row_solves = (uint32_t)w->hC->n_row_solves; out->n_row_idle = (uint32_t)w->hC->n_row_idle;
 	return 0;
 }
 

@@ -67,7 +67,7 @@ JOINT_STATE = np.dtype([("acc", "<f8", 2), ("impulse", "<f8"), ("aux", "<f8")], 
 STATS = np.dtype([
     ("steps", "<u8"), ("n_bodies", "<u4"), ("n_awake", "<u4"), ("n_shapes", "<u4"), ("n_joints", "<u4"), ("n_pairs", "<u4"),
     ("n_arbiters", "<u4"), ("n_contacts", "<u4"), ("n_cached", "<u4"), ("n_colours", "<u4"), ("overflow", "<u4"),
-    ("kinetic_energy", "<f8"), ("max_penetration", "<f8")], align=True)
+    ("kinetic_energy", "<f8"), ("max_penetration", "<f8"), ("n_row_solves", "<u4"), ("n_row_idle", "<u4")], align=True)
 
 
 class EngineError(RuntimeError):

@@ -162,6 +162,8 @@ typedef struct cpb200_stats {
 	uint32_t overflow;            /* non-zero: a device buffer was too small; results of that step are invalid */
 	double kinetic_energy;        /* sum over dynamic bodies of m*v^2 + i*w^2 (cpBody.c:581-588, not halved) */
 	double max_penetration;       /* max over active contacts of -dist (>= 0) */
+	uint32_t n_row_solves;        /* world-wide solver: contact rows x iterations visited in the last step ... */
+	uint32_t n_row_idle;          /* ... of which this many left both bodies bit-identical (clamped impulses): their scatters were skipped */
 } cpb200_stats;
 
 /* ---- lifetime ------------------------------------------------------------------ */
