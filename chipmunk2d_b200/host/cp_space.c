@@ -1100,20 +1100,16 @@ custom_velocities(cpSpace *space, cpCustomWork *cw, cpFloat dt)
 static void
 step_once(cpSpace *space, cpFloat dt, cpBool callbacks)
 {
-	if(callbacks){
-		space->locked++;
-		for(int i = 0; i < space->nConstraints; i++){
-			cpConstraint *c = space->constraints[i];
-			if(c->preSolve) c->preSolve(c, space);
-		}
-		space->locked--;
-	}
+	/* constraint preSolve callbacks run after the collision phase and the islands pass, before the prestep
+	 * (cpSpaceStep.c:389-396): a space that has one steps in parts */
+	cpBool constraintPreSolve = cpFalse;
+	if(callbacks){ for(int i = 0; i < space->nConstraints; i++){ if(space->constraints[i]->preSolve){ constraintPreSolve = cpTrue; break; } } }
 	cpCustomWork cw;
 	custom_collect(space, &cw);
 	custom_positions(space, &cw, dt);
 	sync_to_device(space);
 	const cpBool handlers = space_has_collision_callbacks(space);
-	const cpBool midstep = (cw.nSpring > 0 || cw.nVel > 0);
+	const cpBool midstep = (cw.nSpring > 0 || cw.nVel > 0 || constraintPreSolve);
 	if(handlers || midstep){
 		/* split step: the handlers' return values and edits take effect in THIS step, like the reference */
 		if(cpb200_world_step_collide(space->world, dt)) cpEngineError("cpSpaceStep (collision phase)");
@@ -1126,6 +1122,18 @@ step_once(cpSpace *space, cpFloat dt, cpBool callbacks)
 			space->locked--;
 		}
 		if(midstep){
+			if(constraintPreSolve){
+				space->locked++;
+				for(int i = 0; i < space->nConstraints; i++){
+					cpConstraint *c = space->constraints[i];
+					if(c->preSolve) c->preSolve(c, space);
+				}
+				space->locked--;
+				/* what the callback changed (cpSimpleMotorSetRate, cpConstraintSetMaxForce, ...) must reach this step's prestep */
+				if(space->jointsDirty){ if(space->jointStale) cpSpaceFetchJointsB200(space); upload_joints(space); space->jointsDirty = cpFalse; }
+				if(space->bodiesDirty){ cpSpaceFetchBodiesB200(space); upload_bodies(space, cpFalse); space->bodiesDirty = space->forcesDirty = cpFalse; }
+				else if(space->forcesDirty){ cpSpaceUnpackAllB200(space); upload_forces(space); space->forcesDirty = cpFalse; }
+			}
 			custom_springs(space, &cw);
 			if(cpb200_world_step_presolve(space->world)) cpEngineError("cpSpaceStep (prestep phase)");
 			custom_velocities(space, &cw, dt);

@@ -5,10 +5,12 @@
  * value), the part of the reference's public API that sits on or next to the cpSpaceStep hot
  * path (reference headers under include/chipmunk; SURVEY.md 8b "minimum set"):
  *   spaces, bodies, circle/segment/poly shapes, the ten joint classes, arbiters, collision
- *   handlers, post-step callbacks, iterators, cpHastySpace (chipmunk/cpHastySpace.h), the
- *   moment/area/hull helpers and the inline cpVect / cpBB / cpTransform math.
- * Not provided (out of the hot-path scope): spatial-index classes, space queries,
- * debug draw, autogeometry (cpMarch/cpPolyline), struct layouts (chipmunk_structs.h).
+ *   handlers, post-step callbacks, iterators, cpHastySpace (chipmunk/cpHastySpace.h), space and
+ *   shape queries (point / segment / bb / shape, as device scans), custom body integrators and
+ *   spring force functions (host callbacks through a split step), the moment/area/hull helpers
+ *   and the inline cpVect / cpBB / cpTransform math.
+ * Not provided (out of the hot-path scope): spatial-index classes, debug draw,
+ * autogeometry (cpMarch/cpPolyline), struct layouts (chipmunk_structs.h).
  *
  * A cpSpace created here lives on a B200: cpSpaceStep() runs every stage of the step as CUDA
  * kernels through the C ABI in include/cpb200.h.  Object state read through the getters below

@@ -666,6 +666,31 @@ static void remove_two_in_one_callback(void)
 	cpSpaceFree(space);
 }
 
+/* 29. a constraint preSolve callback (cpSpaceStep.c:389-396) that re-parameterises its joint every step: the new rate
+ * must act in the SAME step, and the callback sees this step's positions (it runs after the position update) */
+static int g_presolve_calls = 0; static double g_seen_angle = 0.0;
+static void motor_presolve(cpConstraint *c, cpSpace *space)
+{
+	g_presolve_calls++;
+	g_seen_angle = cpBodyGetAngle(cpConstraintGetBodyB(c));
+	cpSimpleMotorSetRate(c, (g_presolve_calls % 2) ? 3.0 : -1.5);
+	if(g_presolve_calls == 6) cpConstraintSetMaxForce(c, 50.0);
+}
+static void constraint_presolve_callback(void)
+{
+	cpSpace *space = cpSpaceNew();
+	cpBody *wheel = cpSpaceAddBody(space, cpBodyNew(2.0, 8.0));
+	cpBodySetPosition(wheel, cpv(3, 4));
+	cpConstraint *m = cpSpaceAddConstraint(space, cpSimpleMotorNew(cpSpaceGetStaticBody(space), wheel, 1.0));
+	cpConstraintSetPreSolveFunc(m, motor_presolve);
+	g_presolve_calls = 0;
+	for(int k = 0; k < 10; k++){
+		cpSpaceStep(space, 1.0/60.0);
+		printf("constraint_presolve_%d A %a %a %a %a\n", k, (double)g_presolve_calls, g_seen_angle, cpBodyGetAngularVelocity(wheel), cpConstraintGetImpulse(m));
+	}
+	cpSpaceFree(space);
+}
+
 int main(void)
 {
 	empty_space();
@@ -696,5 +721,6 @@ int main(void)
 	custom_position_func();
 	custom_spring_funcs();
 	remove_two_in_one_callback();
+	constraint_presolve_callback();
 	return 0;
 }
