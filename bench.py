@@ -434,6 +434,30 @@ def measure(workload, args, ctx, full):
             api.space = None
         except Exception as exc:
             e2e_api = {"value": None, "unit": "body-steps/s", "error": str(exc)}
+    append_cost = None
+    if full and len(scenes) == 1 and workload.startswith("pile1m"):
+        # f4: what one cpSpaceAddBody + cpSpaceAddShape costs on the running space -- the appended range,
+        # the first step after it (kernel by kernel: the step graph is re-captured) -- over a plain step
+        try:
+            from chipmunk2d_b200.engine import BODY_DESC, SHAPE_DESC
+            def one_step():
+                t0 = time.perf_counter(); w.step(dt); w.sync(); return time.perf_counter() - t0
+            plain = min(one_step() for _ in range(5))
+            costs = []
+            for r in range(5):
+                bd = np.zeros(1, dtype=BODY_DESC); bd["m"] = 1.0; bd["i"] = 12.5; bd["rot"][:, 0] = 1.0; bd["sleep_group"] = -1
+                bd["p"] = (50.0 + 20.0 * r, 20000.0)
+                sd = np.zeros(1, dtype=SHAPE_DESC); sd["body"] = w.n_bodies; sd["hashid"] = 10000000 + r; sd["r"] = 5.0
+                sd["categories"] = 0xFFFFFFFF; sd["mask"] = 0xFFFFFFFF; sd["u"] = 0.9
+                t0 = time.perf_counter()
+                ok = w.append_bodies(bd) and w.append_shapes(sd)
+                w.step(dt); w.sync()
+                costs.append(time.perf_counter() - t0 - plain)
+                w.step(dt, 2); w.sync()
+            append_cost = {"extra_ms_per_added_body_and_shape": 1000.0 * float(np.median(costs)), "plain_step_ms": 1000.0 * plain, "appended_in_place": bool(ok),
+                           "what": "cpb200_world_append_bodies(1) + cpb200_world_append_shapes(1) + the first step after them, minus a plain step (host clock, median of 5)"}
+        except Exception as exc:
+            append_cost = {"error": str(exc)}
     w.close()
 
     rec = {"config": cfg, "value": total_bodies * steps / t_max, "unit": "body-steps/s", "steps": steps, "warmup": warm,
@@ -446,6 +470,8 @@ def measure(workload, args, ctx, full):
            "gpu_launches": int(launches), "e2e": e2e, "stage_us": acc, "solver_us": sp}
     if e2e_api is not None:
         rec["e2e_per_body_api"] = e2e_api
+    if append_cost is not None:
+        rec["append_cost"] = append_cost
     rec["_local"] = {"iterations": iterations, "nb": nb, "st2": st2, "clocks": clocks, "ms_local": ms, "n_scenes": len(scenes)}
     return rec
 
@@ -552,6 +578,7 @@ def run_ours(args):
         "per_step": main["per_step"], "clocks": loc["clocks"], "gpu_launches": main["gpu_launches"],
         "e2e": main["e2e"], "e2e_per_body_api": main.get("e2e_per_body_api"),
         "roofline": roof, "stage_us": main["stage_us"], "solver_us": main["solver_us"],
+        "append_cost": main.get("append_cost"),
         "cpu_baseline": cpu, "sub_records": subs,
     }
     emit(line)

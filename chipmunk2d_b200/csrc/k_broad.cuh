@@ -15,6 +15,9 @@
 #include "cpb_world.h"
 #include "prims.cuh"
 
+// Deferred nodes of the depth-first traversal: at most one per level.  The depth of the radix tree is bounded by the number of
+// distinct prefix lengths of its keys: 32 Morton bits + the space-id bits (<= 12 for 4096 spaces) + the index bits that break
+// ties between equal keys (<= 31) = 75 < 96, so the overflow flag (bit 3) cannot be raised by any input; it stays as a guard.
 #define CPB_BVH_STACK 96
 
 CPB_DEVICE bool shape_is_active(const DBodies &B, int body){
