@@ -132,6 +132,7 @@ struct cpb200_world {
 	std::vector<uint32_t> space_base;     // lowest shape hashid of every space (hlocal = hashid - base)
 	std::vector<int> joint_base;          // first joint index of every space (colouring priorities)
 	std::vector<uint64_t> nocollide_keys; // sorted body pairs joined by a constraint with collideBodies == 0
+	std::vector<uint64_t> joint_nocollide; // per joint: its body-pair key + 1 if collideBodies == 0, else 0
 	int user_cap_pairs, user_cap_arbs;
 
 	uint32_t stamp;
@@ -1007,7 +1008,7 @@ extern "C" int cpb200_world_set_joints(cpb200_world *w, int n, const cpb200_join
 	std::vector<double> max_force(N), max_bias(N), aux0(N, 0.0);
 	std::vector<V2> anchor_a(N), anchor_b(N), acc(N);
 	std::vector<double4> prm(N);
-	std::vector<uint64_t> nocollide, jpri(N);
+	std::vector<uint64_t> nocollide, jpri(N), jnc(N);
 	std::vector<int> body_space;
 	if(download(w, body_space, w->B.space, (size_t)w->B.n) || world_sync(w)) return -1;
 	std::vector<int> joint_base((size_t)w->n_spaces, -1);
@@ -1031,11 +1032,14 @@ extern "C" int cpb200_world_set_joints(cpb200_world *w, int n, const cpb200_join
 			V2 gn = vperp(vnormalize(vsub(v2(d.prm[0], d.prm[1]), anchor_a[i])));
 			prm[i].z = gn.x; prm[i].w = gn.y;
 		}
+		jnc[i] = 0;
 		if(!d.collide_bodies){
 			uint64_t lo = (uint64_t)(uint32_t)std::min(d.a, d.b), hi = (uint64_t)(uint32_t)std::max(d.a, d.b);
 			nocollide.push_back((lo << 32) | hi);
+			jnc[i] = ((lo << 32) | hi) + 1ull;
 		}
 	}
+	w->joint_nocollide = jnc;
 	std::sort(nocollide.begin(), nocollide.end());
 	nocollide.erase(std::unique(nocollide.begin(), nocollide.end()), nocollide.end());
 	w->gJ.release();
@@ -1065,7 +1069,7 @@ extern "C" int cpb200_world_append_joints(cpb200_world *w, int n, const cpb200_j
 	if(n == 0) return 0;
 	if(w->mid_step || w->mid_solve){ cpb_set_error("structural edit inside a split step"); return -1; }
 	DJoints &J = w->J;
-	if(J.n + n > w->cap_joints || (int)w->joint_base.size() != w->n_spaces || (int)w->body_space.size() != w->B.n || w->joint_error_bias.size() != (size_t)J.n) return 1;
+	if(J.n + n > w->cap_joints || (int)w->joint_base.size() != w->n_spaces || (int)w->body_space.size() != w->B.n || w->joint_error_bias.size() != (size_t)J.n || w->joint_nocollide.size() != (size_t)J.n) return 1;
 	cudaSetDevice(w->device);
 	const size_t N = (size_t)n;
 	const int j0 = J.n;
@@ -1073,7 +1077,7 @@ extern "C" int cpb200_world_append_joints(cpb200_world *w, int n, const cpb200_j
 	std::vector<double> max_force(N), max_bias(N), aux0(N, 0.0);
 	std::vector<V2> anchor_a(N), anchor_b(N), acc(N);
 	std::vector<double4> prm(N);
-	std::vector<uint64_t> jpri(N), nocollide = w->nocollide_keys;
+	std::vector<uint64_t> jpri(N), nocollide = w->nocollide_keys, jnc_new;
 	std::vector<int> base = w->joint_base;
 	bool new_nocollide = false;
 	for(size_t i = 0; i < N; i++){
@@ -1092,9 +1096,11 @@ extern "C" int cpb200_world_append_joints(cpb200_world *w, int n, const cpb200_j
 			V2 gn = vperp(vnormalize(vsub(v2(d.prm[0], d.prm[1]), anchor_a[i])));          // cpGrooveJoint.c:128
 			prm[i].z = gn.x; prm[i].w = gn.y;
 		}
+		jnc_new.push_back(0);
 		if(!d.collide_bodies){
 			uint64_t lo = (uint64_t)(uint32_t)std::min(d.a, d.b), hi = (uint64_t)(uint32_t)std::max(d.a, d.b);
 			nocollide.push_back((lo << 32) | hi); new_nocollide = true;
+			jnc_new.back() = ((lo << 32) | hi) + 1ull;
 		}
 	}
 	if(world_sync(w)) return -1;
@@ -1109,11 +1115,150 @@ extern "C" int cpb200_world_append_joints(cpb200_world *w, int n, const cpb200_j
 		if(upload_nocollide(w, nocollide)) return -1;
 	}
 	for(size_t i = 0; i < N; i++) w->joint_error_bias.push_back(joints[i].error_bias);
+	w->joint_nocollide.insert(w->joint_nocollide.end(), jnc_new.begin(), jnc_new.end());
 	w->joint_base = base;
 	J.n += n;
 	w->joint_body.insert(w->joint_body.end(), a.begin(), a.end());
 	w->sl_dirty = true;
 	w->joints_dt = 0.0;   // bias coefficients of all joints are refreshed at the next step (one small upload)
+	return world_sync(w);
+}
+
+// ---- f4: removal in place.  The last object of the class moves into the hole (the host registries do the same swap, so
+// host slot == device index stays true); everything that names the moved object by index is re-pointed on the device.
+__global__ void k_move_shape(DShapes S, int dst, int src)
+{
+	if(CPB_TID != 0) return;
+	#define MV(a) S.a[dst] = S.a[src]
+	MV(type); MV(body); MV(hashid); MV(hlocal); MV(sensor); MV(cat); MV(mask); MV(group); MV(ctype); MV(e); MV(u); MV(r); MV(surfv);
+	MV(la); MV(lb); MV(ln); MV(atan); MV(btan); MV(pcount); MV(poff); MV(wa); MV(wb); MV(wn); MV(bb); MV(mat); MV(ids); MV(filt);
+	#undef MV
+	S.circ[2*(size_t)dst] = S.circ[2*(size_t)src]; S.circ[2*(size_t)dst + 1] = S.circ[2*(size_t)src + 1];
+}
+
+// records of the removed shape die (their key can never be looked up again: hashids are not reused), records of the
+// moved shape follow it
+__global__ void k_arb_remap_shape(DArbs A, int removed, int moved)
+{
+	int n = *A.count_ptr; if(n > A.cap) n = A.cap;
+	for(int i = CPB_TID; i < n; i += CPB_NTHREADS){
+		int sa = A.sa[i], sb = A.sb[i];
+		if(sa == removed || sb == removed){ A.key[i] = ~0ull; A.active[i] = 0; A.sa[i] = 0; A.sb[i] = 0; A.ba[i] = 0; A.bb[i] = 0; continue; }
+		if(sa == moved) A.sa[i] = removed;
+		if(sb == moved) A.sb[i] = removed;
+	}
+}
+
+extern "C" int cpb200_world_remove_shape(cpb200_world *w, int index)
+{
+	if(!w || index < 0 || index >= w->S.n){ cpb_set_error("shape index out of range"); return -1; }
+	if(w->mid_step || w->mid_solve){ cpb_set_error("structural edit inside a split step"); return -1; }
+	if((int)w->shape_body.size() != w->S.n) return 1;
+	cudaSetDevice(w->device);
+	const int last = w->S.n - 1;
+	if(index != last) LAUNCH(k_move_shape, 1, 32, w->stream, w->S, index, last);
+	if(w->cap_arbs > 0) LAUNCH(k_arb_remap_shape, std::min(grid_for(w->A[w->cur].cap, 256), w->sm_count*8), 256, w->stream, w->A[w->cur], index, (index != last ? last : -1));
+	w->shape_body[(size_t)index] = w->shape_body[(size_t)last];
+	w->shape_body.pop_back();
+	w->S.n = last; w->bvh.n = last;
+	w->sl_dirty = true;
+	return world_sync(w);
+}
+
+__global__ void k_move_joint(DJoints J, int dst, int src, unsigned long long pri)
+{
+	if(CPB_TID != 0) return;
+	#define MV(a) J.a[dst] = J.a[src]
+	J.type[dst] = J.type[src]; J.a[dst] = J.a[src]; J.b[dst] = J.b[src];
+	MV(max_force); MV(max_bias); MV(bias_coef); MV(anchor_a); MV(anchor_b); MV(prm); MV(r1); MV(r2); MV(nrm); MV(nmass); MV(k); MV(bias); MV(acc);
+	MV(aux0); MV(aux1); MV(jspring); MV(colour); MV(hint);
+	#undef MV
+	J.pri[dst] = pri;     // priorities must stay unique among the live joints: the one of its new index
+}
+
+extern "C" int cpb200_world_remove_joint(cpb200_world *w, int index)
+{
+	if(!w || index < 0 || index >= w->J.n){ cpb_set_error("joint index out of range"); return -1; }
+	if(w->mid_step || w->mid_solve){ cpb_set_error("structural edit inside a split step"); return -1; }
+	if((int)w->joint_body.size() != w->J.n || w->joint_error_bias.size() != (size_t)w->J.n || w->joint_nocollide.size() != (size_t)w->J.n ||
+	   (int)w->joint_base.size() != w->n_spaces || (int)w->body_space.size() != w->B.n) return 1;
+	cudaSetDevice(w->device);
+	const int last = w->J.n - 1;
+	if(index != last){
+		int jb = w->joint_base[(size_t)w->body_space[(size_t)w->joint_body[(size_t)last]]];
+		if(jb < 0) jb = 0;
+		LAUNCH(k_move_joint, 1, 32, w->stream, w->J, index, last, (unsigned long long)(mix64(0x9e3779b97f4a7c15ull ^ (uint64_t)(index - jb)) >> 8));
+	}
+	const bool had_nocollide = (w->joint_nocollide[(size_t)index] != 0);
+	w->joint_body[(size_t)index] = w->joint_body[(size_t)last]; w->joint_body.pop_back();
+	w->joint_error_bias[(size_t)index] = w->joint_error_bias[(size_t)last]; w->joint_error_bias.pop_back();
+	w->joint_nocollide[(size_t)index] = w->joint_nocollide[(size_t)last]; w->joint_nocollide.pop_back();
+	w->J.n = last;
+	if(had_nocollide){
+		std::vector<uint64_t> keys;
+		for(uint64_t k : w->joint_nocollide) if(k) keys.push_back(k - 1);
+		std::sort(keys.begin(), keys.end());
+		keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+		if(upload_nocollide(w, keys)) return -1;
+	}
+	w->sl_dirty = true;
+	// (last step's colours of the remaining constraints stay valid: removing an edge cannot create a conflict)
+	return world_sync(w);
+}
+
+__global__ void k_move_body(DBodies B, int dst, int src)
+{
+	if(CPB_TID != 0) return;
+	#define MV(a) B.a[dst] = B.a[src]
+	MV(pos); MV(ang); MV(rot); MV(txy); MV(cog); MV(V); MV(VB); MV(MI); MV(M); MV(force); MV(torque); MV(idle); MV(type); MV(space); MV(sleeping); MV(sgroup); MV(custom);
+	#undef MV
+}
+
+// every index that named body `moved` now names `dst`; sleeping groups are named by their root body as well
+__global__ void k_remap_body(DBodies B, DShapes S, DJoints J, DArbs A, int dst, int moved)
+{
+	const int tid = CPB_TID, nth = CPB_NTHREADS;
+	for(int i = tid; i < B.n; i += nth){ if(B.sgroup[i] == moved) B.sgroup[i] = dst; }
+	for(int s = tid; s < S.n; s += nth){
+		if(S.body[s] != moved) continue;
+		S.body[s] = dst;
+		unsigned long long x = (unsigned long long)__double_as_longlong(S.filt[s].x);
+		x = (x & 0xffffffff00000000ull) | (unsigned long long)(uint32_t)dst;
+		S.filt[s].x = __longlong_as_double((long long)x);
+	}
+	for(int j = tid; j < J.n; j += nth){ if(J.a[j] == moved) J.a[j] = dst; if(J.b[j] == moved) J.b[j] = dst; }
+	int n = *A.count_ptr; if(n > A.cap) n = A.cap;
+	for(int i = tid; i < n; i += nth){ if(A.ba[i] == moved) A.ba[i] = dst; if(A.bb[i] == moved) A.bb[i] = dst; }
+}
+
+/* The body must not be named by any shape or joint any more (remove those first); returns 1 otherwise, or when the
+ * engine's host-side bookkeeping cannot follow (the caller then re-uploads). */
+extern "C" int cpb200_world_remove_body(cpb200_world *w, int index)
+{
+	if(!w || index < 0 || index >= w->B.n){ cpb_set_error("body index out of range"); return -1; }
+	if(w->mid_step || w->mid_solve){ cpb_set_error("structural edit inside a split step"); return -1; }
+	if((int)w->body_space.size() != w->B.n || (int)w->shape_body.size() != w->S.n || (int)w->joint_body.size() != w->J.n) return 1;
+	for(int b : w->shape_body) if(b == index) return 1;
+	for(int b : w->joint_body) if(b == index) return 1;
+	cudaSetDevice(w->device);
+	std::vector<int> jb;
+	if(w->J.n){ if(download(w, jb, w->J.b, (size_t)w->J.n) || world_sync(w)) return -1; for(int b : jb) if(b == index) return 1; }
+	const int last = w->B.n - 1;
+	if(index != last){
+		LAUNCH(k_move_body, 1, 32, w->stream, w->B, index, last);
+		w->B.n = last;      // (the remap below must not walk over the vacated slot)
+		DArbs dummy = w->A[w->cur];
+		if(w->cap_arbs == 0){ cpb_set_error("internal: arbiter buffers missing"); return -1; }
+		LAUNCH(k_remap_body, std::min(grid_for(std::max(std::max(w->B.n, w->S.n), dummy.cap), 256), w->sm_count*8), 256, w->stream, w->B, w->S, w->J, dummy, index, last);
+		for(int &b : w->shape_body) if(b == last) b = index;
+		for(int &b : w->joint_body) if(b == last) b = index;
+		w->body_space[(size_t)index] = w->body_space[(size_t)last];
+	}
+	w->B.n = last;
+	w->body_space.pop_back();
+	w->io_src = NULL; w->io_sink = NULL;
+	w->sl_dirty = true;
+	w->cache_dirty = true;      // the packed circle lines carry the body index: rewritten for every shape by the next cache pass
 	return world_sync(w);
 }
 

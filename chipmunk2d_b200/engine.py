@@ -130,6 +130,9 @@ def load_engine(path=None):
     lib.cpb200_world_append_bodies.argtypes = [vp, ci, vp]
     lib.cpb200_world_append_shapes.argtypes = [vp, ci, vp, ci, vp]
     lib.cpb200_world_append_joints.argtypes = [vp, ci, vp]
+    lib.cpb200_world_remove_shape.argtypes = [vp, ci]
+    lib.cpb200_world_remove_body.argtypes = [vp, ci]
+    lib.cpb200_world_remove_joint.argtypes = [vp, ci]
     lib.cpb200_world_get_graph_stats.argtypes = [vp, vp]
     lib.cpb200_world_graph_error.restype = C.c_char_p
     lib.cpb200_world_graph_error.argtypes = [vp]
@@ -335,6 +338,24 @@ class World:
         rc = self._ck(self.lib.cpb200_world_append_joints(self.w, len(jd), jd.ctypes.data))
         if rc == 0:
             self.n_joints += len(jd)
+        return rc == 0
+
+    def remove_shape(self, index):
+        rc = self._ck(self.lib.cpb200_world_remove_shape(self.w, int(index)))
+        if rc == 0:
+            self.n_shapes -= 1
+        return rc == 0
+
+    def remove_body(self, index):
+        rc = self._ck(self.lib.cpb200_world_remove_body(self.w, int(index)))
+        if rc == 0:
+            self.n_bodies -= 1
+        return rc == 0
+
+    def remove_joint(self, index):
+        rc = self._ck(self.lib.cpb200_world_remove_joint(self.w, int(index)))
+        if rc == 0:
+            self.n_joints -= 1
         return rc == 0
 
     def reserve(self, max_pairs=0, max_arbiters=0):

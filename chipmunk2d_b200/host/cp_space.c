@@ -290,6 +290,21 @@ cpSpaceAddConstraint(cpSpace *space, cpConstraint *constraint)
 	return constraint;
 }
 
+/* f4: a removal is done in place on the device (the engine moves its last object into the hole, exactly like the
+ * registries below) when nothing else is pending; additions that have not travelled yet go first, so that "last" means
+ * the same object on both sides.  Returns cpFalse if the removal has to take the full re-upload instead. */
+static cpBool append_to_device(cpSpace *space);
+static cpBool
+flush_appends_for_removal(cpSpace *space)
+{
+	if(!can_append(space)) return cpFalse;
+	if(space->appendDirty){
+		if(!append_to_device(space)){ space->topologyDirty = cpTrue; return cpFalse; }
+		space->appendDirty = cpFalse;
+	}
+	return cpTrue;
+}
+
 /* before a structural edit the mirrors must hold the device's latest state, because the edit forces a
  * full re-upload from them */
 static void
@@ -346,7 +361,13 @@ cpSpaceRemoveShape(cpSpace *space, cpShape *shape)
 		}
 		drop_arbiters_of_shape(space, shape);
 	}
-	sync_before_edit(space);
+	cpBool inPlace = cpFalse;
+	if(flush_appends_for_removal(space) && shape->index < space->nShapesOnDevice){
+		int rc = cpb200_world_remove_shape(space->world, shape->index);
+		if(rc < 0) cpEngineError("shape removal");
+		inPlace = (rc == 0);
+	}
+	if(!inPlace) sync_before_edit(space);
 	cpBody *body = shape->body;
 	cpBodyActivate(body);
 	cpBodyRemoveShape(body, shape);
@@ -354,8 +375,8 @@ cpSpaceRemoveShape(cpSpace *space, cpShape *shape)
 	if(i != last){ space->shapes[i] = space->shapes[last]; space->shapes[i]->index = i; }
 	shape->space = NULL;
 	shape->index = -1;
-	space->topologyDirty = cpTrue;
-	space->shapeIndexDirty = cpTrue;
+	if(inPlace){ space->nShapesOnDevice--; space->bbStale = cpTrue; }
+	else { space->topologyDirty = cpTrue; space->shapeIndexDirty = cpTrue; }
 }
 
 void
@@ -364,14 +385,23 @@ cpSpaceRemoveBody(cpSpace *space, cpBody *body)
 	cpAssertHard(body != cpSpaceGetStaticBody(space), "Cannot remove the designated static body for the space.");
 	cpAssertHard(cpSpaceContainsBody(space, body), "Cannot remove a body that was not added to the space. (Removed twice maybe?)");
 	cpAssertSpaceUnlocked(space);
-	sync_before_edit(space);
+	cpBool inPlace = cpFalse;
+	if(body->shapeList == NULL && body->constraintList == NULL && flush_appends_for_removal(space) && body->index < space->nBodiesOnDevice){
+		/* every mirror takes its record of the last download first: the records are addressed by the OLD slots */
+		cpSpaceFetchBodiesB200(space);
+		cpSpaceFetchBiasB200(space);
+		int rc = cpb200_world_remove_body(space->world, body->index);
+		if(rc < 0) cpEngineError("body removal");
+		inPlace = (rc == 0);
+	}
+	if(!inPlace) sync_before_edit(space);
 	cpBodyActivate(body);
 	int i = body->index, last = --space->nBodies;
 	if(i != last){ space->bodies[i] = space->bodies[last]; space->bodies[i]->index = i; }
 	body->space = NULL;
 	body->index = -1;
 	body->sleepRoot = NULL;
-	space->topologyDirty = cpTrue;
+	if(inPlace) space->nBodiesOnDevice--; else space->topologyDirty = cpTrue;
 }
 
 void
@@ -379,17 +409,24 @@ cpSpaceRemoveConstraint(cpSpace *space, cpConstraint *constraint)
 {
 	cpAssertHard(cpSpaceContainsConstraint(space, constraint), "Cannot remove a constraint that was not added to the space. (Removed twice maybe?)");
 	cpAssertSpaceUnlocked(space);
-	sync_before_edit(space);
+	cpBool inPlace = cpFalse;
+	if(flush_appends_for_removal(space) && constraint->index < space->nConstraintsOnDevice){
+		if(space->jointStale) cpSpaceFetchJointsB200(space);     /* the removed joint keeps its last impulse for cpConstraintGetImpulse */
+		int rc = cpb200_world_remove_joint(space->world, constraint->index);
+		if(rc < 0) cpEngineError("constraint removal");
+		inPlace = (rc == 0);
+	}
+	if(!inPlace) sync_before_edit(space);
 	cpBodyActivate(constraint->a);
 	cpBodyActivate(constraint->b);
 	cpBodyRemoveConstraint(constraint->a, constraint);
 	cpBodyRemoveConstraint(constraint->b, constraint);
 	int i = constraint->index, last = --space->nConstraints;
 	if(i != last){ space->constraints[i] = space->constraints[last]; space->constraints[i]->index = i; }
-	space->jointIndexDirty = cpTrue;   /* host slots no longer match device indices until the next upload */
 	constraint->space = NULL;
 	constraint->index = -1;
-	space->topologyDirty = cpTrue;
+	if(inPlace) space->nConstraintsOnDevice--;
+	else { space->jointIndexDirty = cpTrue;   /* host slots no longer match device indices until the next upload */ space->topologyDirty = cpTrue; }
 }
 
 cpBool cpSpaceContainsShape(cpSpace *space, cpShape *shape){ return (shape->space == space); }

@@ -216,6 +216,14 @@ CPB200_API int cpb200_world_reserve(cpb200_world *w, int max_pairs, int max_arbi
 CPB200_API int cpb200_world_append_bodies(cpb200_world *w, int n, const cpb200_body_desc *bodies);
 CPB200_API int cpb200_world_append_shapes(cpb200_world *w, int n, const cpb200_shape_desc *shapes, int n_verts, const double *verts_xy);
 CPB200_API int cpb200_world_append_joints(cpb200_world *w, int n, const cpb200_joint_desc *joints);
+/* cpSpaceRemoveShape / RemoveBody / RemoveConstraint (cpSpace.c:476-571) in place: the LAST object of the class moves
+ * into the hole -- a host that keeps its registries dense the same way (swap with last) keeps slot == index -- and every
+ * index that named the moved object is re-pointed on the device (arbiter records, shapes' body indices, joints, sleeping
+ * groups).  Arbiter records of a removed shape die.  A body can only be removed once no shape or joint names it.
+ * Returns 1 (nothing changed) when the engine's bookkeeping cannot follow; the caller then re-uploads. */
+CPB200_API int cpb200_world_remove_shape(cpb200_world *w, int index);
+CPB200_API int cpb200_world_remove_body(cpb200_world *w, int index);
+CPB200_API int cpb200_world_remove_joint(cpb200_world *w, int index);
 
 /* cpSpaceStep (cpSpaceStep.c:335-445) for every space of the world.  Asynchronous:
  * returns once the kernels are enqueued on the world's stream. */

@@ -146,3 +146,53 @@ def test_append_reports_exhausted_slack():
     assert w.append_bodies(bd) is False          # 101 bodies carry 281 slots of slack
     assert w.n_bodies == len(sc.bodies)
     w.step(sc.dt, 3); w.sync()
+
+
+@pytest.mark.parametrize("name", ["SimpleTerrainCircles_1000", "mixed6k"])
+def test_removal_in_place_equals_reuploading_the_world_without_the_object(name, monkeypatch):
+    """cpb200_world_remove_shape / remove_joint / remove_body (swap with last + re-pointing on the device) against a
+    re-upload of the world without the object, in the same slot order: identical evolution afterwards."""
+    from chipmunk2d_b200.engine import scene_descs
+    sc = mixed_drop(6000) if name == "mixed6k" else golden_scene(name)
+    monkeypatch.setenv("CPB200_NO_HINTS", "1")
+    a, b = World(1), World(1)
+    for w in (a, b):
+        w.reserve(max_pairs=400000, max_arbiters=200000)
+        w.load_scene(sc)
+        w.step(sc.dt, 40)
+        w.sync()
+    bd0, sd0, jd0 = scene_descs(sc)
+    nb, ns, nj = len(bd0), len(sd0), len(jd0)
+    victims = [nb // 2, 7, nb - 1]                                   # a middle body, an early one, the last one
+    # host-side model of the registries: current slot -> original index
+    body_slot, shape_slot, joint_slot = list(range(nb)), list(range(ns)), list(range(nj))
+    for v in victims:
+        k = body_slot.index(v)                                       # where that body sits now
+        for q in sorted([i for i, j in enumerate(joint_slot) if jd0["a"][j] == v or jd0["b"][j] == v], reverse=True):
+            assert a.remove_joint(q); joint_slot[q] = joint_slot[-1]; joint_slot.pop()
+        for q in sorted([i for i, s_ in enumerate(shape_slot) if sd0["body"][s_] == v], reverse=True):
+            assert a.remove_shape(q); shape_slot[q] = shape_slot[-1]; shape_slot.pop()
+        assert a.remove_body(k); body_slot[k] = body_slot[-1]; body_slot.pop()
+    assert (a.n_bodies, a.n_shapes, a.n_joints) == (len(body_slot), len(shape_slot), len(joint_slot))
+    # world b: the same registries uploaded from scratch (state read back first)
+    st = b.bodies(); bias = b.body_solver_state()
+    bd = bd0.copy()
+    for key in ("p", "v", "a", "w", "rot", "idle_time", "sleeping", "sleep_group"):
+        bd[key] = st[key]
+    bd["v_bias"] = bias[:, 4:6]; bd["w_bias"] = bias[:, 6]
+    new_body = {orig: slot for slot, orig in enumerate(body_slot)}
+    bd = bd[body_slot]
+    sd = sd0[shape_slot].copy(); sd["body"] = [new_body[int(x)] for x in sd["body"]]
+    jd = jd0[joint_slot].copy()
+    if nj:
+        jd["acc"] = b.joints()["acc"][joint_slot]
+        jd["a"] = [new_body[int(x)] for x in jd["a"]]; jd["b"] = [new_body[int(x)] for x in jd["b"]]
+    b.set_bodies(bd); b.set_shapes(sd, sc.verts); b.set_joints(jd)
+    for s in range(50):
+        a.step(sc.dt); b.step(sc.dt)
+    a.sync(); b.sync()
+    x, y = a.bodies(), b.bodies()
+    for key in ("p", "v", "a", "w"):
+        assert np.array_equal(x[key], y[key]), (name, key, float(np.max(np.abs(x[key] - y[key]))))
+    assert np.array_equal(a.pairs(), b.pairs())
+    assert a.stats()["overflow"] == 0
