@@ -21,6 +21,7 @@
 #include "prims.cuh"
 
 #define CPB_OVERFLOW_COLOUR (CPB_MAX_COLOURS - 1)
+
 #define CPB_MAX_COLOUR_ROUNDS 200
 
 struct DColour {
@@ -244,10 +245,17 @@ CPB_DEVICE void write_row_packed(const DArbs &A, const DRows &R, int i, int r){
 // scnt/sbase: per-CTA shared scratch [CPB_MAX_COLOURS] (NULL in the emulation build): a CTA counts its
 // rows per colour, reserves one contiguous range per colour with a single global atomic, then hands the
 // slots out with shared-memory atomics.
-CPB_DEVICE void build_rows(const DArbs &A, const DJoints &J, const DRows &R, const DColour &K, int *scnt, int *sbase, int nA, int tid, int nth){
+CPB_DEVICE void build_rows(const DArbs &A, const DJoints &J, const DRows &R, const DColour &K, int *scnt, int *sbase, int nA, int tid, int nth, bool chunked){
 #ifndef CPB_EMU
 	if(scnt){
-		for(int i = tid; i < nA; i += nth){
+		// every CTA takes ONE contiguous chunk of the records (they were appended in pair-list order, i.e. along the
+		// broadphase's Morton order): the rows it reserves per colour then come from one neighbourhood of the scene, and a warp
+		// of the iteration loop gathers body sectors that lie close together.  (Strided over the whole record range, 256
+		// records at a time, the same loop interleaved ~40 distant neighbourhoods inside every CTA's slice of a colour.)
+		const int per = (nA + (int)gridDim.x - 1)/(int)gridDim.x;
+		const int i0 = (chunked ? (int)blockIdx.x*per + (int)threadIdx.x : tid), i1 = (chunked ? min(nA, ((int)blockIdx.x + 1)*per) : nA);
+		const int istep = (chunked ? (int)blockDim.x : nth);
+		for(int i = i0; i < i1; i += istep){
 			if(A.active[i] != 1) continue;
 			int col = A.colour[i];
 			if(col >= 0) atomicAdd(&scnt[col], 1);
@@ -259,7 +267,7 @@ CPB_DEVICE void build_rows(const DArbs &A, const DJoints &J, const DRows &R, con
 			scnt[threadIdx.x] = 0;
 		}
 		__syncthreads();
-		for(int i = tid; i < nA; i += nth){
+		for(int i = i0; i < i1; i += istep){
 			if(A.active[i] != 1) continue;
 			int col = A.colour[i];
 			if(col < 0) continue;
@@ -791,7 +799,7 @@ template<bool SPACE_LOCAL, bool STREAM_ROWS, bool JOINTS, int PHASE, int MINB> _
 		return;
 	}
 	GRID_SYNC();
-	build_rows(A, J, R, K, s_hist, s_base, nA, tid, nth);
+	build_rows(A, J, R, K, s_hist, s_base, nA, tid, nth, (use_hints & 4) == 0);   // bit 2 of use_hints: experiment switch, strided records
 	if(PHASE == 1){ __syncthreads(); PROF(2); return; }
 	GRID_SYNC();
 	PROF(2);
@@ -872,7 +880,7 @@ __global__ void k_colour_finish(DArbs A, DJoints J, DRows R, DColour K, DCounter
 	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
 	if(stage == 2){ colour_leftover(A, J, K, (int *)NULL, nA, CPB_MAX_COLOUR_ROUNDS, CPB_TID, CPB_NTHREADS); return; }
 	if(stage == 0){ if(CPB_TID == 0) colour_starts(K, C); }
-	else build_rows(A, J, R, K, (int *)NULL, (int *)NULL, nA, CPB_TID, CPB_NTHREADS);
+	else build_rows(A, J, R, K, (int *)NULL, (int *)NULL, nA, CPB_TID, CPB_NTHREADS, true);
 }
 __global__ void k_solve_colour(DBodies B, DRows R, DJoints J, DColour K, int colour, int mode, double dt, double dt_coef){
 	if(colour == CPB_OVERFLOW_COLOUR){ if(CPB_TID == 0) solve_overflow<true>(B, R, J, K, mode, dt, dt_coef); }

@@ -174,6 +174,7 @@ struct cpb200_world {
 	bool hints_valid;       // last step's colours may seed this step's colouring
 	bool no_hints;          // validation hook (env CPB200_NO_HINTS): colour from scratch every step
 	bool no_phase_prefetch; // experiment switch (env CPB200_NO_PHASE_PREFETCH)
+	bool rows_strided;      // experiment switch (env CPB200_ROWS_STRIDED): round 1's strided record assignment in the row build
 	int wl_cap; AllocGroup gW;
 	int force_blocks;       // validation hook: fixed persistent grid size (0 = automatic)
 	int last_active;        // active arbiters seen at the last host read-back (grid sizing hint)
@@ -321,7 +322,7 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	if(w->C && getenv("CPB200_NO_GJK_STAGE")){ int one = 1; cudaMemcpyAsync(&w->C->no_gjk_stage, &one, sizeof(int), cudaMemcpyHostToDevice, w->stream); cudaStreamSynchronize(w->stream); }
 	cudaMallocHost(&p, sizeof(DCounters)); w->hC = (DCounters *)p; memset(w->hC, 0, sizeof(DCounters));
 	cudaMalloc(&p, sizeof(unsigned)*64); w->d_barrier = (unsigned *)p; cudaMemsetAsync(w->d_barrier, 0, sizeof(unsigned)*64, w->stream);
-	w->no_hints = (getenv("CPB200_NO_HINTS") != NULL); w->no_phase_prefetch = (getenv("CPB200_NO_PHASE_PREFETCH") != NULL);
+	w->no_hints = (getenv("CPB200_NO_HINTS") != NULL); w->no_phase_prefetch = (getenv("CPB200_NO_PHASE_PREFETCH") != NULL); w->rows_strided = (getenv("CPB200_ROWS_STRIDED") != NULL);
 	w->d_query = NULL; w->query_bytes = 0;
 	w->mid_solve = false; w->solver_variant = 0; w->last_solver_path = 0;
 	memset(w->graph, 0, sizeof(w->graph)); w->graph_gen = 1; w->graph_last_sig[0] = w->graph_last_sig[1] = 0; w->graph_replays = w->graph_captures = 0;
@@ -1646,6 +1647,7 @@ static int step_phase_b2(cpb200_world *w)
 		if(ensure_worklists(w, Ac.cap + J.n + 64)) return -1;
 		int use_hints = (w->hints_valid && !w->no_hints ? 1 : 0);
 		if(w->no_phase_prefetch) use_hints |= 2;
+		if(w->rows_strided) use_hints |= 4;
 		w->hints_valid = true;
 #ifndef CPB_EMU
 		{
