@@ -1066,10 +1066,9 @@ custom_fetch_bodies(cpSpace *space, int n, const int32_t *idx)
 static void
 custom_positions(cpSpace *space, cpCustomWork *cw, cpFloat dt)
 {
-	if(cw->nPos == 0 || !space->world || space->topologyDirty) {
-		/* first step (nothing on the device yet) or a pending re-upload: the mirrors are the state */
-		if(cw->nPos == 0) return;
-	} else {
+	if(cw->nPos == 0) return;
+	if(space->world){
+		/* the callbacks integrate the mirrors: those must hold the device's latest state, pending bias velocities included */
 		cpSpaceFetchBodiesB200(space);
 		cpSpaceFetchBiasB200(space);
 	}
