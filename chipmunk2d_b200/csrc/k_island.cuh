@@ -22,17 +22,25 @@ struct DIslands {
 	int *woken;         // per body: woke up this step
 	int *touch;         // per body: idle long enough itself, but joined to an awake body that is not
 	int *any_woken;     // [1] some body woke up this step
+	int *flags;         // [2][4] per step parity: (some awake body has idled long enough, some body sleeps, some body is kinematic, -)
+	                    // written by k_sleep_idle; in a live pile all three are 0 and the passes over the arbiters return at once
 };
+#define ISL_IDLE 0
+#define ISL_SLEEPING 1
+#define ISL_KINEMATIC 2
 
 CPB_DEVICE bool space_sleeps(const DSpace &sp){ return sp.sleep_threshold != INFINITY; }
 
 // idle timers (cpSpaceComponent.c:237-250)
-__global__ void k_sleep_idle(DBodies B, DIslands I, const DSpace *__restrict__ spaces, double dt)
+__global__ void k_sleep_idle(DBodies B, DIslands I, const DSpace *__restrict__ spaces, double dt, int par)
 {
 	int i = CPB_TID;
 	if(i >= B.n) return;
 	I.parent[i] = i; I.wake[i] = 0; I.comp_active[i] = 0; I.woken[i] = 0; I.touch[i] = 0;
-	if(i == 0) *I.any_woken = 0;
+	if(i == 0){ *I.any_woken = 0; int *nf = I.flags + 4*(par ^ 1); nf[0] = nf[1] = nf[2] = nf[3] = 0; }   // the NEXT step's flags
+	int *fl = I.flags + 4*par;
+	if(B.type[i] == CPB200_BODY_KINEMATIC && !fl[ISL_KINEMATIC]) fl[ISL_KINEMATIC] = 1;
+	if(B.sleeping[i] && !fl[ISL_SLEEPING]) fl[ISL_SLEEPING] = 1;
 	if(B.type[i] != CPB200_BODY_DYNAMIC || B.sleeping[i]) return;
 	DSpace sp = spaces[B.space[i]];
 	if(!space_sleeps(sp)) return;
@@ -43,12 +51,16 @@ __global__ void k_sleep_idle(DBodies B, DIslands I, const DSpace *__restrict__ s
 	double keThreshold = (dvsq ? M.x*dvsq : 0.0);
 	double vsq = V.x*V.x + V.y*V.y, wsq = V.z*V.z;
 	double ke = (vsq ? vsq*M.x : 0.0) + (wsq ? wsq*M.y : 0.0);
-	B.idle[i] = (ke > keThreshold ? 0.0 : B.idle[i] + dt);
+	const double idle = (ke > keThreshold ? 0.0 : B.idle[i] + dt);
+	B.idle[i] = idle;
+	if(idle >= sp.sleep_threshold && !fl[ISL_IDLE]) fl[ISL_IDLE] = 1;
 }
 
 // wake marks from this step's active arbiters and from joints (cpSpaceComponent.c:253-278)
-__global__ void k_sleep_wake_mark(DBodies B, DIslands I, DArbs A, DJoints J, const DSpace *__restrict__ spaces)
+__global__ void k_sleep_wake_mark(DBodies B, DIslands I, DArbs A, DJoints J, const DSpace *__restrict__ spaces, int par)
 {
+	// only a sleeping body can be woken and only a kinematic one resets its partner's timer
+	if(!I.flags[4*par + ISL_SLEEPING] && !I.flags[4*par + ISL_KINEMATIC]) return;
 	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
 	int total = nA + J.n;
 	for(int c = CPB_TID; c < total; c += CPB_NTHREADS){
@@ -70,8 +82,9 @@ __global__ void k_sleep_wake_mark(DBodies B, DIslands I, DArbs A, DJoints J, con
 	}
 }
 
-__global__ void k_sleep_wake_apply(DBodies B, DIslands I)
+__global__ void k_sleep_wake_apply(DBodies B, DIslands I, int par)
 {
+	if(!I.flags[4*par + ISL_SLEEPING]) return;
 	int i = CPB_TID;
 	if(i >= B.n || !B.sleeping[i]) return;
 	int g = B.sgroup[i];
@@ -116,8 +129,9 @@ __global__ void k_sleep_woken_reset(DBodies B, DIslands I, DArbs A, DJoints J)
 // "idle subgraph" with no edge to a body that has not: such edges only mark their idle endpoint.  While a pile
 // is still settling no body qualifies and the pass is a streaming read; the full union-find over millions of
 // edges of one giant component runs only in the step in which that component actually falls asleep.
-__global__ void k_sleep_union(DBodies B, DIslands I, DArbs A, DJoints J, const DSpace *__restrict__ spaces)
+__global__ void k_sleep_union(DBodies B, DIslands I, DArbs A, DJoints J, const DSpace *__restrict__ spaces, int par)
 {
+	if(!I.flags[4*par + ISL_IDLE]) return;      // nobody has idled long enough: no component can fall asleep this step
 	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
 	int total = nA + J.n;
 	for(int c = CPB_TID; c < total; c += CPB_NTHREADS){
@@ -146,8 +160,9 @@ __global__ void k_sleep_union(DBodies B, DIslands I, DArbs A, DJoints J, const D
 	}
 }
 
-__global__ void k_sleep_components(DBodies B, DIslands I, const DSpace *__restrict__ spaces)
+__global__ void k_sleep_components(DBodies B, DIslands I, const DSpace *__restrict__ spaces, int par)
 {
+	if(!I.flags[4*par + ISL_IDLE]) return;
 	int i = CPB_TID;
 	if(i >= B.n) return;
 	if(B.type[i] != CPB200_BODY_DYNAMIC || B.sleeping[i]) return;
@@ -157,8 +172,9 @@ __global__ void k_sleep_components(DBodies B, DIslands I, const DSpace *__restri
 	if(!space_sleeps(sp) || B.idle[i] < sp.sleep_threshold || I.touch[i]) I.comp_active[r] = 1;
 }
 
-__global__ void k_sleep_apply(DBodies B, DIslands I)
+__global__ void k_sleep_apply(DBodies B, DIslands I, int par)
 {
+	if(!I.flags[4*par + ISL_IDLE]) return;      // (and k_sleep_components did not mark anything)
 	int i = CPB_TID;
 	if(i >= B.n) return;
 	if(B.type[i] != CPB200_BODY_DYNAMIC || B.sleeping[i]) return;
@@ -169,8 +185,10 @@ __global__ void k_sleep_apply(DBodies B, DIslands I)
 }
 
 // arbiters whose bodies all rest leave the solver but keep their contacts (cpSpaceComponent.c:94-105)
-__global__ void k_sleep_arbs(DBodies B, DArbs A, DCounters *C)
+__global__ void k_sleep_arbs(DBodies B, DIslands I, DArbs A, DCounters *C, int par)
 {
+	// an arbiter goes dormant only if a body of it sleeps: one that slept before this step or one that fell asleep in it
+	if(!I.flags[4*par + ISL_SLEEPING] && !I.flags[4*par + ISL_IDLE]) return;
 	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
 	for(int i = CPB_TID; i < nA; i += CPB_NTHREADS){
 		if(A.active[i] != 1) continue;
@@ -184,19 +202,19 @@ __global__ void k_sleep_arbs(DBodies B, DArbs A, DCounters *C)
 	}
 }
 
-static int islands_step(DIslands &I, DBodies &B, DShapes &S, DJoints &J, DArbs &Ap, DArbs &Ac, DTable &Tc, const DSpace *spaces, double dt, uint32_t stamp, DCounters *C, int sm_count, cudaStream_t st)
+static int islands_step(DIslands &I, DBodies &B, DShapes &S, DJoints &J, DArbs &Ap, DArbs &Ac, DTable &Tc, const DSpace *spaces, double dt, int par, DCounters *C, int sm_count, cudaStream_t st)
 {
-	(void)S; (void)Ap; (void)Tc; (void)stamp;
+	(void)S; (void)Ap; (void)Tc;
 	if(B.n == 0) return 0;
 	int gb = cpb_div_up(B.n, 256);
 	int ge = std::min(cpb_div_up(Ac.cap + J.n + 1, 256), sm_count*8);
-	LAUNCH(k_sleep_idle, gb, 256, st, B, I, spaces, dt);
-	LAUNCH(k_sleep_wake_mark, ge, 256, st, B, I, Ac, J, spaces);
-	LAUNCH(k_sleep_wake_apply, gb, 256, st, B, I);
+	LAUNCH(k_sleep_idle, gb, 256, st, B, I, spaces, dt, par);
+	LAUNCH(k_sleep_wake_mark, ge, 256, st, B, I, Ac, J, spaces, par);
+	LAUNCH(k_sleep_wake_apply, gb, 256, st, B, I, par);
 	LAUNCH(k_sleep_woken_reset, ge, 256, st, B, I, Ac, J);
-	LAUNCH(k_sleep_union, ge, 256, st, B, I, Ac, J, spaces);
-	LAUNCH(k_sleep_components, gb, 256, st, B, I, spaces);
-	LAUNCH(k_sleep_apply, gb, 256, st, B, I);
-	LAUNCH(k_sleep_arbs, ge, 256, st, B, Ac, C);
+	LAUNCH(k_sleep_union, ge, 256, st, B, I, Ac, J, spaces, par);
+	LAUNCH(k_sleep_components, gb, 256, st, B, I, spaces, par);
+	LAUNCH(k_sleep_apply, gb, 256, st, B, I, par);
+	LAUNCH(k_sleep_arbs, ge, 256, st, B, I, Ac, C, par);
 	return 0;
 }

@@ -489,7 +489,7 @@ extern "C" int cpb200_world_set_bodies(cpb200_world *w, int n, const cpb200_body
 	w->io_src = NULL; w->io_sink = NULL;   // bound host buffers were sized for the old body count: bind again
 	w->body_space.clear(); w->sl_dirty = true;
 	w->gI.release();
-	DA(w->gI, w->I.parent, cap); DA(w->gI, w->I.wake, cap); DA(w->gI, w->I.comp_active, cap); DA(w->gI, w->I.woken, cap); DA(w->gI, w->I.touch, cap); DA(w->gI, w->I.any_woken, 4);
+	DA(w->gI, w->I.parent, cap); DA(w->gI, w->I.wake, cap); DA(w->gI, w->I.comp_active, cap); DA(w->gI, w->I.woken, cap); DA(w->gI, w->I.touch, cap); DA(w->gI, w->I.any_woken, 4); DA(w->gI, w->I.flags, 8);
 	int r = cpb200_world_update_bodies(w, 0, n, bodies);
 	w->cache_dirty = true;
 	return r;
@@ -1535,7 +1535,7 @@ static int step_phase_b1(cpb200_world *w)
 
 	// K7: islands / sleeping (cpSpaceProcessComponents) -- before the cache filter, like the reference
 	if(w->any_sleep_enabled){
-		if(islands_step(w->I, B, S, J, Ap, Ac, Tc, w->d_spaces, dt, w->stamp, w->C, w->sm_count, st)) return -1;
+		if(islands_step(w->I, B, S, J, Ap, Ac, Tc, w->d_spaces, dt, w->cur & 1, w->C, w->sm_count, st)) return -1;
 	}
 	STAGE_END(w, ST_ISLANDS);
 
