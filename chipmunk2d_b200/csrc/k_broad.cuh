@@ -144,10 +144,12 @@ __global__ void k_bvh_build(DBvh T)
 	if(i == 0) T.parent[0] = -1;
 }
 
-__global__ void k_bvh_leaves(DBvh T, DShapes S, DBodies B)
+// reset_flags: a step that keeps the tree's topology (no k_morton pass) clears the refit's arrival counters here
+__global__ void k_bvh_leaves(DBvh T, DShapes S, DBodies B, int reset_flags)
 {
 	int i = CPB_TID;
 	if(i >= T.n) return;
+	if(reset_flags) T.flags[i] = 0;
 	int s = T.leaf_shape[i];
 	T.nbb[(T.n - 1) + i] = S.bb[s];
 	int body = S.body[s];

@@ -159,10 +159,14 @@ struct cpb200_world {
 	// A step whose launch sequence is fixed (no collision handlers, no profiling, same dt, same buffers) is captured once
 	// into a CUDA graph per arbiter-buffer parity and replayed with one launch: a 1000-body scene is ~35 kernels of a few
 	// microseconds each, and their launch gaps were most of its step time.  Every counter a kernel needs lives on the device.
-	struct StepGraph { cudaGraphExec_t exec; unsigned long long sig; int launches; int solver_path; } graph[2];
+	// (one graph per arbiter-buffer parity and per kind of broadphase step: tree rebuilt / tree topology kept)
+	struct StepGraph { cudaGraphExec_t exec; unsigned long long sig; int launches; int solver_path; } graph[4];
 	unsigned long long graph_gen;       // bumped by every upload / setting that can change the launch sequence
-	unsigned long long graph_last_sig[2];  // signature of the previous step of the same parity (a graph is captured when it repeats;
-	                                       // the radix sort's ping-pong buffers make odd and even steps differ)
+	unsigned long long graph_last_sig[4];  // signature of the previous step of the same slot (a graph is captured when it repeats)
+	// The LBVH's topology (leaf order + Karras hierarchy) is kept for bvh_period steps and only refitted in between: a
+	// refitted tree is an exact bounding hierarchy whatever its age, so the pair set does not depend on this; only the
+	// traversal gets dearer as the boxes of an old topology spread.  Structural edits rebuild at once.
+	bool bvh_valid; int bvh_age, bvh_period;
 	bool graph_enabled;
 	// per-step host I/O bound to the world (cpb200_world_bind_io): page-locked host buffers, device staging, a side stream
 	const double *io_src; double *io_sink;
@@ -325,14 +329,16 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	w->no_hints = (getenv("CPB200_NO_HINTS") != NULL); w->no_phase_prefetch = (getenv("CPB200_NO_PHASE_PREFETCH") != NULL); w->rows_strided = (getenv("CPB200_ROWS_STRIDED") != NULL);
 	w->d_query = NULL; w->query_bytes = 0;
 	w->mid_solve = false; w->solver_variant = 0; w->last_solver_path = 0;
-	memset(w->graph, 0, sizeof(w->graph)); w->graph_gen = 1; w->graph_last_sig[0] = w->graph_last_sig[1] = 0; w->graph_replays = w->graph_captures = 0;
+	memset(w->graph, 0, sizeof(w->graph)); w->graph_gen = 1; memset(w->graph_last_sig, 0, sizeof(w->graph_last_sig)); w->graph_replays = w->graph_captures = 0;
+	w->bvh_valid = false; w->bvh_age = 0; w->bvh_period = 8;
+	{ const char *e = getenv("CPB200_BVH_PERIOD"); if(e && atoi(e) >= 1) w->bvh_period = atoi(e); }
 	w->graph_enabled = (getenv("CPB200_NO_GRAPH") == NULL); w->graph_error[0] = 0;
 	w->io_src = NULL; w->io_sink = NULL; w->d_io_force = w->d_io_pos = w->d_io_vel = NULL; w->io_cap = 0;
 	cudaStreamCreate(&w->stream_io);
 	cudaEventCreateWithFlags(&w->ev_io_begin, cudaEventDisableTiming); cudaEventCreateWithFlags(&w->ev_io_forces, cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&w->ev_io_pos, cudaEventDisableTiming); cudaEventCreateWithFlags(&w->ev_io_join, cudaEventDisableTiming);
 	w->mid_step = false; w->step_dt = 0.0; w->step_dt_coef = 0.0; w->step_iterations = 0;
-	w->sl_dirty = true; w->sl_ok = false; w->sl_disabled = (getenv("CPB200_NO_SPACE_LOCAL") != NULL); w->sl_max_nbody = 0;
+	w->sl_dirty = true; w->bvh_valid = false; w->sl_ok = false; w->sl_disabled = (getenv("CPB200_NO_SPACE_LOCAL") != NULL); w->sl_max_nbody = 0;
 	memset(&w->SL, 0, sizeof(w->SL)); w->sl_tmp = NULL;
 	memset(&w->SS, 0, sizeof(w->SS)); w->sl_shapes_ok = false; w->sl_max_nshape = 0;
 	w->d_sl_plain = w->d_sl_jointed = NULL; w->n_sl_plain = w->n_sl_jointed = 0;
@@ -349,7 +355,7 @@ extern "C" void cpb200_world_destroy(cpb200_world *w)
 	cudaSetDevice(w->device);
 	cudaStreamSynchronize(w->stream);
 #ifndef CPB_EMU
-	for(int k = 0; k < 2; k++) if(w->graph[k].exec) cudaGraphExecDestroy(w->graph[k].exec);
+	for(int k = 0; k < 4; k++) if(w->graph[k].exec) cudaGraphExecDestroy(w->graph[k].exec);
 #endif
 	w->gB.release(); w->gS.release(); w->gJ.release(); w->gA.release(); w->gK.release(); w->gV.release(); w->gP.release(); w->gI.release(); w->gW.release();
 	cudaFree(w->d_barrier);
@@ -487,7 +493,7 @@ extern "C" int cpb200_world_set_bodies(cpb200_world *w, int n, const cpb200_body
 	DA(w->gK, w->K.wl_n, CPB_MAX_COLOUR_ROUNDS + 2); DA(w->gK, w->K.prof, 8);
 	w->hints_valid = false; // body types / masses may have changed: colour from scratch once
 	w->io_src = NULL; w->io_sink = NULL;   // bound host buffers were sized for the old body count: bind again
-	w->body_space.clear(); w->sl_dirty = true;
+	w->body_space.clear(); w->sl_dirty = true; w->bvh_valid = false;
 	w->gI.release();
 	DA(w->gI, w->I.parent, cap); DA(w->gI, w->I.wake, cap); DA(w->gI, w->I.comp_active, cap); DA(w->gI, w->I.woken, cap); DA(w->gI, w->I.touch, cap); DA(w->gI, w->I.any_woken, 4); DA(w->gI, w->I.flags, 8);
 	int r = cpb200_world_update_bodies(w, 0, n, bodies);
@@ -526,9 +532,9 @@ static int upload_body_range(cpb200_world *w, int first, int n, const cpb200_bod
 	if(n == 0) return 0;
 	cudaSetDevice(w->device);
 	size_t bytes = sizeof(cpb200_body_desc)*(size_t)n;
-	if((int)w->body_space.size() != w->B.n){ w->body_space.assign((size_t)w->B.n, 0); w->sl_dirty = true; }
+	if((int)w->body_space.size() != w->B.n){ w->body_space.assign((size_t)w->B.n, 0); w->sl_dirty = true; w->bvh_valid = false; }
 	for(int i = 0; i < n; i++){
-		if(w->body_space[(size_t)(first + i)] != (int)bodies[i].space){ w->body_space[(size_t)(first + i)] = (int)bodies[i].space; w->sl_dirty = true; }
+		if(w->body_space[(size_t)(first + i)] != (int)bodies[i].space){ w->body_space[(size_t)(first + i)] = (int)bodies[i].space; w->sl_dirty = true; w->bvh_valid = false; }
 	}
 	if(stage_reserve(w, bytes + 64)) return -1;
 	int *bad = (int *)((char *)w->d_stage + ((bytes + 15) & ~(size_t)15));
@@ -851,7 +857,7 @@ extern "C" int cpb200_world_set_shapes(cpb200_world *w, int n, const cpb200_shap
 	   upload(w, S.surfv, surfv) || upload(w, S.la, la) || upload(w, S.lb, lb) || upload(w, S.ln, ln) || upload(w, S.atan, atan_) || upload(w, S.btan, btan_) ||
 	   upload(w, S.mat, mat) || upload(w, S.ids, ids) || upload(w, S.filt, filt) || upload(w, S.pcount, pcount) || upload(w, S.poff, poff) || upload(w, S.lpv, lpv) || upload(w, S.lpn, lpn)) return -1;
 
-	w->shape_body = body; w->sl_dirty = true;
+	w->shape_body = body; w->sl_dirty = true; w->bvh_valid = false;
 
 	// broadphase scratch (sized for the capacity: appended shapes need no reallocation)
 	w->gV.release();
@@ -969,7 +975,7 @@ extern "C" int cpb200_world_append_shapes(cpb200_world *w, int n, const cpb200_s
 	S.n += n; S.nv += n_verts;
 	w->bvh.n = S.n;
 	w->shape_body.insert(w->shape_body.end(), body.begin(), body.end());
-	w->sl_dirty = true;
+	w->sl_dirty = true; w->bvh_valid = false;
 	w->cache_dirty = true;      // the world cache of the new shapes (and nothing else changes: same bodies, same transforms)
 	return 0;
 }
@@ -1056,7 +1062,7 @@ extern "C" int cpb200_world_set_joints(cpb200_world *w, int n, const cpb200_join
 	if(upload(w, J.type, type) || upload(w, J.a, a) || upload(w, J.b, b) || upload(w, J.max_force, max_force) || upload(w, J.max_bias, max_bias) ||
 	   upload(w, J.anchor_a, anchor_a) || upload(w, J.anchor_b, anchor_b) || upload(w, J.prm, prm) || upload(w, J.acc, acc) || upload(w, J.aux0, aux0) || upload(w, J.pri, jpri)) return -1;
 	if(upload_nocollide(w, nocollide)) return -1;
-	w->joint_body = a; w->sl_dirty = true;
+	w->joint_body = a; w->sl_dirty = true; w->bvh_valid = false;
 	w->joints_dt = 0.0; // force bias_coef refresh
 	w->hints_valid = false;
 	return world_sync(w);
@@ -1120,7 +1126,7 @@ extern "C" int cpb200_world_append_joints(cpb200_world *w, int n, const cpb200_j
 	w->joint_base = base;
 	J.n += n;
 	w->joint_body.insert(w->joint_body.end(), a.begin(), a.end());
-	w->sl_dirty = true;
+	w->sl_dirty = true; w->bvh_valid = false;
 	w->joints_dt = 0.0;   // bias coefficients of all joints are refreshed at the next step (one small upload)
 	return world_sync(w);
 }
@@ -1162,7 +1168,7 @@ extern "C" int cpb200_world_remove_shape(cpb200_world *w, int index)
 	w->shape_body[(size_t)index] = w->shape_body[(size_t)last];
 	w->shape_body.pop_back();
 	w->S.n = last; w->bvh.n = last;
-	w->sl_dirty = true;
+	w->sl_dirty = true; w->bvh_valid = false;
 	return world_sync(w);
 }
 
@@ -1202,7 +1208,7 @@ extern "C" int cpb200_world_remove_joint(cpb200_world *w, int index)
 		keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
 		if(upload_nocollide(w, keys)) return -1;
 	}
-	w->sl_dirty = true;
+	w->sl_dirty = true; w->bvh_valid = false;
 	// (last step's colours of the remaining constraints stay valid: removing an edge cannot create a conflict)
 	return world_sync(w);
 }
@@ -1258,7 +1264,7 @@ extern "C" int cpb200_world_remove_body(cpb200_world *w, int index)
 	w->B.n = last;
 	w->body_space.pop_back();
 	w->io_src = NULL; w->io_sink = NULL;
-	w->sl_dirty = true;
+	w->sl_dirty = true; w->bvh_valid = false;
 	w->cache_dirty = true;      // the packed circle lines carry the body index: rewritten for every shape by the next cache pass
 	return world_sync(w);
 }
@@ -1404,6 +1410,16 @@ static int sl_refresh(cpb200_world *w)
 // up to the point where the reference calls the begin/preSolve collision handlers, cpSpaceStep.c:234-290).
 // Phase B: islands, cache ageing, prestep, velocities, solver.  cpb200_world_step runs both back to back;
 // the host layer of a space WITH collision handlers calls them separately and edits arbiters in between.
+// does this step rebuild the LBVH (bounds, Morton keys, sort, hierarchy) or only refit the one it has?
+static bool bvh_in_use(const cpb200_world *w)
+{
+#ifndef CPB_EMU
+	if(w->sl_shapes_ok && w->sl_max_nshape <= CPB_SL_MAX_SHAPES && w->S.n >= 2) return false;
+#endif
+	return w->S.n >= 2;
+}
+static bool bvh_rebuild_due(const cpb200_world *w){ return !w->bvh_valid || w->bvh_age >= w->bvh_period; }
+
 static int step_phase_a(cpb200_world *w, double dt)
 {
 	cudaSetDevice(w->device);
@@ -1475,21 +1491,34 @@ static int step_phase_a(cpb200_world *w, double dt)
 #endif
 	} else if(ns >= 2){
 		DBvh &T = w->bvh;
-		LAUNCH(k_bounds_init, 1, 32, st, T.bounds);
-		LAUNCH(k_bounds, std::min(grid_for(ns, 256), wide), 256, st, S, T.bounds);
-		// Morton bits: log2(shapes) + 4 (sixteen cells per shape), in whole radix digits
-		int want_bits = 4; while((1 << (want_bits - 4)) < ns && want_bits < 32) want_bits++;
-		want_bits = std::min(32, std::max(16, (want_bits + 7) & ~7));
-		const int drop_bits = 32 - want_bits;
-		LAUNCH(k_morton, grid_for(ns, 256), 256, st, S, B, (const double *)T.bounds, T.keys, T.leaf_shape, drop_bits, T.flags);
-		STAGE_END(w, ST_BVH_KEYS);
-		int space_bits = 0; while((1 << space_bits) < w->n_spaces) space_bits++;
-		int bits = 32 + space_bits;
-		int where = cpb_radix_sort(T.keys, T.leaf_shape, w->keys_b, w->vals_b, ns, bits, w->sort_tmp, st, drop_bits);
-		if(where){ std::swap(T.keys, w->keys_b); std::swap(T.leaf_shape, w->vals_b); }
-		STAGE_END(w, ST_BVH_SORT);
-		LAUNCH(k_bvh_build, grid_for(ns - 1, 256), 256, st, T);
-		LAUNCH(k_bvh_leaves, grid_for(ns, 256), 256, st, T, S, B);
+		const bool rebuild = bvh_rebuild_due(w);
+		if(rebuild){
+			LAUNCH(k_bounds_init, 1, 32, st, T.bounds);
+			LAUNCH(k_bounds, std::min(grid_for(ns, 256), wide), 256, st, S, T.bounds);
+			// Morton bits: log2(shapes) + 4 (sixteen cells per shape), in whole radix digits
+			int want_bits = 4; while((1 << (want_bits - 4)) < ns && want_bits < 32) want_bits++;
+			want_bits = std::min(32, std::max(16, (want_bits + 7) & ~7));
+			const int drop_bits = 32 - want_bits;
+			LAUNCH(k_morton, grid_for(ns, 256), 256, st, S, B, (const double *)T.bounds, T.keys, T.leaf_shape, drop_bits, T.flags);
+			STAGE_END(w, ST_BVH_KEYS);
+			int space_bits = 0; while((1 << space_bits) < w->n_spaces) space_bits++;
+			int bits = 32 + space_bits;
+			int where = cpb_radix_sort(T.keys, T.leaf_shape, w->keys_b, w->vals_b, ns, bits, w->sort_tmp, st, drop_bits);
+			if(where){
+				if(w->bvh_period > 1){
+					// the leaf order outlives this step (and the graphs that replay the steps in between name T.leaf_shape): bring it home
+					CPB_CHECK(cudaMemcpyAsync(T.keys, w->keys_b, sizeof(uint64_t)*(size_t)ns, cudaMemcpyDeviceToDevice, st));
+					CPB_CHECK(cudaMemcpyAsync(T.leaf_shape, w->vals_b, sizeof(int)*(size_t)ns, cudaMemcpyDeviceToDevice, st));
+				} else { std::swap(T.keys, w->keys_b); std::swap(T.leaf_shape, w->vals_b); }
+			}
+			STAGE_END(w, ST_BVH_SORT);
+			LAUNCH(k_bvh_build, grid_for(ns - 1, 256), 256, st, T);
+			w->bvh_valid = true; w->bvh_age = 1;
+		} else {
+			STAGE_END(w, ST_BVH_KEYS); STAGE_END(w, ST_BVH_SORT);
+			w->bvh_age++;
+		}
+		LAUNCH(k_bvh_leaves, grid_for(ns, 256), 256, st, T, S, B, (int)!rebuild);
 		LAUNCH(k_bvh_refit, grid_for(ns, 256), 256, st, T);
 		LAUNCH(k_bvh_pack, grid_for(ns - 1, 256), 256, st, T);
 		STAGE_END(w, ST_BVH_BUILD);
@@ -1744,10 +1773,11 @@ static unsigned long long sig_ptr(unsigned long long h, const void *p){ return s
 
 // Everything the launch sequence of a production step depends on: buffer addresses and sizes (kernel arguments are
 // captured by value), dt and the iteration count, and the launch plan of the solver.
-static unsigned long long step_signature(cpb200_world *w, double dt, int iterations, const SolvePlan &plan)
+static unsigned long long step_signature(cpb200_world *w, double dt, int iterations, const SolvePlan &plan, bool rebuild)
 {
 	unsigned long long h = 0xcbf29ce484222325ull, d;
 	memcpy(&d, &dt, 8);
+	h = sig_mix(h, rebuild ? 2ull : 1ull); h = sig_mix(h, (unsigned long long)(w->bvh_period > 1 ? 1 : 0));
 	h = sig_mix(h, d); h = sig_mix(h, (unsigned long long)iterations);
 	h = sig_mix(h, (unsigned long long)w->B.n); h = sig_mix(h, (unsigned long long)w->S.n); h = sig_mix(h, (unsigned long long)w->S.nv); h = sig_mix(h, (unsigned long long)w->J.n);
 	h = sig_mix(h, (unsigned long long)w->cap_arbs); h = sig_mix(h, (unsigned long long)w->cap_pairs); h = sig_mix(h, (unsigned long long)w->n_spaces);
@@ -1767,8 +1797,9 @@ static unsigned long long step_signature(cpb200_world *w, double dt, int iterati
 }
 
 // host-side effects of step_phase_a + step_phase_b, for a replayed graph
-static void step_bookkeeping(cpb200_world *w, double dt, int iterations, int solver_path, int launches)
+static void step_bookkeeping(cpb200_world *w, double dt, int iterations, int solver_path, int launches, bool rebuild)
 {
+	if(bvh_in_use(w)){ if(rebuild){ w->bvh_valid = true; w->bvh_age = 1; } else w->bvh_age++; }
 	w->stamp++;
 	w->curr_dt = dt;
 	w->cur ^= 1;
@@ -1792,28 +1823,31 @@ static int step_graphed(cpb200_world *w, double dt)
 	               (w->J.n == 0 || w->joints_dt == dt) && !w->sl_dirty && w->wl_cap >= w->A[0].cap + w->J.n + 64 &&
 	               !(w->solver_variant == 3 && !w->sl_ok) && w->B.n > 0);
 	if(!steady){
-		w->graph_last_sig[0] = w->graph_last_sig[1] = 0;
+		memset(w->graph_last_sig, 0, sizeof(w->graph_last_sig));
 		if(step_phase_a(w, dt)) return -1;
 		return step_phase_b(w);
 	}
 	const SolvePlan plan = plan_solver(w);
-	const unsigned long long sig = step_signature(w, dt, iterations, plan);
-	cpb200_world::StepGraph &G = w->graph[w->cur & 1];
+	const bool rebuild = bvh_in_use(w) && bvh_rebuild_due(w);
+	const unsigned long long sig = step_signature(w, dt, iterations, plan, rebuild);
+	const int slot = (w->cur & 1)*2 + (rebuild ? 1 : 0);
+	cpb200_world::StepGraph &G = w->graph[slot];
 	if(G.exec && G.sig == sig){
-		step_bookkeeping(w, dt, iterations, G.solver_path, G.launches);
+		step_bookkeeping(w, dt, iterations, G.solver_path, G.launches, rebuild);
 		CPB_CHECK(cudaGraphLaunch(G.exec, st));
 		w->graph_replays++;
 		return 0;
 	}
-	if(w->graph_last_sig[w->cur & 1] != sig){
-		// first step with this signature: run it as it is; if the next one of this parity looks the same it is captured
-		w->graph_last_sig[w->cur & 1] = sig;
+	if(w->graph_last_sig[slot] != sig){
+		// first step with this signature: run it as it is; if the next one of this slot looks the same it is captured
+		w->graph_last_sig[slot] = sig;
 		if(step_phase_a(w, dt)) return -1;
 		return step_phase_b(w);
 	}
 	// capture: the step functions enqueue into the capturing stream; nothing executes until the graph is launched
 	const uint32_t s_stamp = w->stamp; const double s_curr_dt = w->curr_dt; const int s_cur = w->cur; const uint64_t s_steps = w->steps;
 	const bool s_hints = w->hints_valid; const unsigned long long s_launches = g_cpb_launches; const int s_path = w->last_solver_path;
+	const bool s_bvh_valid = w->bvh_valid; const int s_bvh_age = w->bvh_age;
 	if(G.exec){ cudaGraphExecDestroy(G.exec); G.exec = NULL; }
 	cudaGraph_t graph = NULL;
 	int rc = -1;
@@ -1835,7 +1869,7 @@ static int step_graphed(cpb200_world *w, double dt)
 		// this world's step cannot be captured (driver limitation): undo the host bookkeeping and run it the ordinary way from now on
 		cudaGetLastError();
 		w->stamp = s_stamp; w->curr_dt = s_curr_dt; w->cur = s_cur; w->steps = s_steps; w->hints_valid = s_hints; g_cpb_launches = s_launches;
-		w->last_solver_path = s_path; w->mid_step = false; w->mid_solve = false;
+		w->last_solver_path = s_path; w->mid_step = false; w->mid_solve = false; w->bvh_valid = s_bvh_valid; w->bvh_age = s_bvh_age;
 		w->graph_enabled = false;
 		if(step_phase_a(w, dt)) return -1;
 		return step_phase_b(w);
