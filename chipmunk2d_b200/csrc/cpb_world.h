@@ -199,6 +199,7 @@ struct DCounters {
 	int no_gjk_stage;      // experiment switch (env CPB200_NO_GJK_STAGE): k_collide<2> reads polygon vertices from global memory
 	int n_row_solves;      // rows x iterations the world-wide solver visited this step ...
 	int n_row_idle;        // ... and how many of those changed neither body (clamped impulses: all four scatters skipped)
+	unsigned bvh_visits, bvh_queries;   // tree nodes visited / query leaves, sampled (every 16th CTA of k_bvh_pairs): the host's measure of how far an aged topology has degraded
 };
 
 #define CPB_MAX_COLOURS 64

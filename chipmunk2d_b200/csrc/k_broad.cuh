@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(128) k_pair_filter(DShapes S, DPairs P, const 
 }
 #endif
 
-__global__ void __launch_bounds__(128) k_bvh_pairs(DBvh T, DShapes S, DBodies B, DPairs P, const uint64_t *__restrict__ nocollide, int n_nocollide, int multi_space, int *overflow)
+__global__ void __launch_bounds__(128) k_bvh_pairs(DBvh T, DShapes S, DBodies B, DPairs P, const uint64_t *__restrict__ nocollide, int n_nocollide, int multi_space, int *overflow, unsigned *visits)
 {
 	int i = CPB_TID;
 	int n = T.n;
@@ -388,11 +388,18 @@ __global__ void __launch_bounds__(128) k_bvh_pairs(DBvh T, DShapes S, DBodies B,
 	int stack[CPB_BVH_STACK];
 	int sp = 0;
 	int node = 0;
+#ifndef CPB_EMU
+	const bool sampled = ((blockIdx.x & 15) == 0);
+	unsigned n_visit = 0, n_query = (done ? 0u : 1u);
+#endif
 	for(;;){
 #ifndef CPB_EMU
 		if(!__any_sync(0xffffffffu, !done)) break;
 #endif
 		if(!done){
+#ifndef CPB_EMU
+			n_visit++;
+#endif
 			int4 ci = T.cinfo[node];
 			double4 box[2] = {ld4_nc(&T.cbox[2*node]), ld4_nc(&T.cbox[2*node + 1])};
 			int4 cs = make_int4(0, 0, 0, 0);
@@ -430,6 +437,11 @@ __global__ void __launch_bounds__(128) k_bvh_pairs(DBvh T, DShapes S, DBodies B,
 	}
 #ifndef CPB_EMU
 	pairs_flush(s_cand[wid], &s_n[wid], lane, P, overflow);
+	if(sampled){
+		// tree quality sample for the host (DCounters::bvh_visits / bvh_queries)
+		n_visit = __reduce_add_sync(0xffffffffu, n_visit); n_query = __reduce_add_sync(0xffffffffu, n_query);
+		if(lane == 0 && n_query){ atomicAdd(&visits[0], n_visit); atomicAdd(&visits[1], n_query); }
+	}
 #endif
 }
 

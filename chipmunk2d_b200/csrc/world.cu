@@ -161,12 +161,13 @@ struct cpb200_world {
 	// microseconds each, and their launch gaps were most of its step time.  Every counter a kernel needs lives on the device.
 	// (one graph per arbiter-buffer parity and per kind of broadphase step: tree rebuilt / tree topology kept)
 	struct StepGraph { cudaGraphExec_t exec; unsigned long long sig; int launches; int solver_path; } graph[4];
-	unsigned long long graph_gen;       // bumped by every upload / setting that can change the launch sequence
 	unsigned long long graph_last_sig[4];  // signature of the previous step of the same slot (a graph is captured when it repeats)
 	// The LBVH's topology (leaf order + Karras hierarchy) is kept for bvh_period steps and only refitted in between: a
 	// refitted tree is an exact bounding hierarchy whatever its age, so the pair set does not depend on this; only the
 	// traversal gets dearer as the boxes of an old topology spread.  Structural edits rebuild at once.
 	bool bvh_valid; int bvh_age, bvh_period;
+	bool bvh_no_valve;          // env CPB200_BVH_NO_VALVE (measurement switch)
+	double bvh_fresh_visits;    // visits per query right after a rebuild (0 = not measured): cpb200_world_sync rebuilds early when an aged tree needs 1.5x that
 	bool graph_enabled;
 	// per-step host I/O bound to the world (cpb200_world_bind_io): page-locked host buffers, device staging, a side stream
 	const double *io_src; double *io_sink;
@@ -329,8 +330,8 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	w->no_hints = (getenv("CPB200_NO_HINTS") != NULL); w->no_phase_prefetch = (getenv("CPB200_NO_PHASE_PREFETCH") != NULL); w->rows_strided = (getenv("CPB200_ROWS_STRIDED") != NULL);
 	w->d_query = NULL; w->query_bytes = 0;
 	w->mid_solve = false; w->solver_variant = 0; w->last_solver_path = 0;
-	memset(w->graph, 0, sizeof(w->graph)); w->graph_gen = 1; memset(w->graph_last_sig, 0, sizeof(w->graph_last_sig)); w->graph_replays = w->graph_captures = 0;
-	w->bvh_valid = false; w->bvh_age = 0; w->bvh_period = 8;
+	memset(w->graph, 0, sizeof(w->graph)); memset(w->graph_last_sig, 0, sizeof(w->graph_last_sig)); w->graph_replays = w->graph_captures = 0;
+	w->bvh_valid = false; w->bvh_age = 0; w->bvh_period = 8; w->bvh_fresh_visits = 0.0; w->bvh_no_valve = (getenv("CPB200_BVH_NO_VALVE") != NULL);
 	{ const char *e = getenv("CPB200_BVH_PERIOD"); if(e && atoi(e) >= 1) w->bvh_period = atoi(e); }
 	w->graph_enabled = (getenv("CPB200_NO_GRAPH") == NULL); w->graph_error[0] = 0;
 	w->io_src = NULL; w->io_sink = NULL; w->d_io_force = w->d_io_pos = w->d_io_vel = NULL; w->io_cap = 0;
@@ -1299,7 +1300,7 @@ __global__ void k_reset_step(DCounters *C, int *pair_count, int *cur_count, int 
 	if(CPB_TID != 0) return;
 	C->stamp++;            // cpSpaceStep.c:349
 	C->n_pairs[0] = C->n_pairs[1] = C->n_pairs[2] = 0;
-	C->n_contacts = 0; C->n_active = 0; C->n_colours = 0; C->n_cached = 0; C->n_row_solves = 0; C->n_row_idle = 0;
+	C->n_contacts = 0; C->n_active = 0; C->n_colours = 0; C->n_cached = 0; C->n_row_solves = 0; C->n_row_idle = 0; C->bvh_visits = 0; C->bvh_queries = 0;
 	C->colour_remaining[0] = C->colour_remaining[1] = 0; C->colour_rounds = 0; C->n_overflow_colour = 0;
 	pair_count[0] = pair_count[1] = pair_count[2] = pair_count[3] = 0;
 	*cur_count = 0;
@@ -1522,7 +1523,7 @@ static int step_phase_a(cpb200_world *w, double dt)
 		LAUNCH(k_bvh_refit, grid_for(ns, 256), 256, st, T);
 		LAUNCH(k_bvh_pack, grid_for(ns - 1, 256), 256, st, T);
 		STAGE_END(w, ST_BVH_BUILD);
-		LAUNCH(k_bvh_pairs, grid_for(ns, 128), 128, st, T, S, B, w->P, (const uint64_t *)w->d_nocollide, w->n_nocollide, (int)(w->n_spaces > 1), &w->C->overflow);
+		LAUNCH(k_bvh_pairs, grid_for(ns, 128), 128, st, T, S, B, w->P, (const uint64_t *)w->d_nocollide, w->n_nocollide, (int)(w->n_spaces > 1), &w->C->overflow, &w->C->bvh_visits);
 #ifndef CPB_EMU
 		LAUNCH(k_pair_filter, std::min(grid_for(w->P.cap, 128*CPB_FILTER_ROUNDS), wide), 128, st, S, w->P, (const uint64_t *)w->d_nocollide, w->n_nocollide, &w->C->overflow);
 #endif
@@ -2007,6 +2008,13 @@ extern "C" int cpb200_world_time_steps(cpb200_world *w, double dt, int n, float 
 static int counters_check(cpb200_world *w)
 {
 	w->last_active = w->hC->n_active;
+	// the counters are those of the last step: how many nodes its tree traversal visited per query.  Measured on a fresh
+	// tree it is the yardstick; an aged topology that needs half as much again is rebuilt at the next step.
+	if(w->bvh_valid && w->hC->bvh_queries > 64 && !w->bvh_no_valve){
+		const double v = (double)w->hC->bvh_visits/(double)w->hC->bvh_queries;
+		if(w->bvh_age <= 1) w->bvh_fresh_visits = v;
+		else if(w->bvh_fresh_visits > 0.0 && v > 1.5*w->bvh_fresh_visits){ w->bvh_valid = false; w->bvh_fresh_visits = 0.0; }
+	}
 	if(w->hC->overflow){
 		cpb_set_error("device buffer overflow (flags 0x%x: 1 pairs, 2 arbiters, 4 table, 8 bvh stack): collisions of the last step were dropped; "
 			"call cpb200_world_reserve with larger capacities (in use: %d pair candidates, %d arbiter records)", w->hC->overflow, w->cap_pairs, w->cap_arbs);
