@@ -1425,7 +1425,7 @@ static int step_phase_a(cpb200_world *w, double dt)
 {
 	cudaSetDevice(w->device);
 	cudaStream_t st = w->stream;
-	DBodies &B = w->B; DShapes &S = w->S; DJoints &J = w->J;
+	DBodies &B = w->B; DShapes &S = w->S;
 	if(S.n > 0 && w->cap_arbs == 0){ cpb_set_error("internal: arbiter buffers missing"); return -1; }
 	if(w->cap_arbs == 0){ if(alloc_arbs(w, 1024) || alloc_pairs(w, 1024)) return -1; }
 
@@ -1446,7 +1446,7 @@ static int step_phase_a(cpb200_world *w, double dt)
 	// swap arbiter buffers: last step's records become "prev"
 	int prv = w->cur; w->cur ^= 1;
 	DArbs &Ap = w->A[prv]; DArbs &Ac = w->A[w->cur];
-	DTable &Tp = w->T[prv]; DTable &Tc = w->T[w->cur];
+	DTable &Tp = w->T[prv];
 	LAUNCH(k_reset_step, 1, 32, st, w->C, w->P.count, Ac.count_ptr, w->K.ccount, w->K.jcount, w->K.wl_n, w->d_barrier);
 
 	const int nb = B.n, ns = S.n;
