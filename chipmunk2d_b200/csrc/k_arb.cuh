@@ -375,38 +375,55 @@ CPB_DEVICE double k_scalar_body(V2 mi, V2 r, V2 n){
 	return mi.x + mi.y*rcn*rcn;
 }
 
-__global__ void k_arb_prestep(DBodies B, DArbs A, const DSpace *__restrict__ spaces, double dt, DCounters *C, double *max_pen)
+// cpArbiterPreStep for one contact (cpArbiter.c:416-439).  Shared by the stand-alone K8 kernel and by the solver's row
+// build (which computes the same numbers on the fly in a production step): one body of code, one operation order.
+struct PrestepBodies { V2 mia, mib; double4 Va, Vb; V2 body_delta; };
+CPB_DEVICE PrestepBodies prestep_bodies(const DBodies &B, int ba, int bb){
+	PrestepBodies pb;
+	pb.mia = B.MI[ba]; pb.mib = B.MI[bb];
+	pb.Va = B.V[ba]; pb.Vb = B.V[bb];
+	pb.body_delta = vsub(B.pos[bb], B.pos[ba]);
+	return pb;
+}
+CPB_DEVICE void prestep_contact(const PrestepBodies &pb, V2 n_, double e, double bias_coef, double slop, double dt, V2 r1, V2 r2,
+	double &nmass, double &tmass, double &bias, double &bounce)
+{
+	nmass = 1.0/(k_scalar_body(pb.mia, r1, n_) + k_scalar_body(pb.mib, r2, n_));
+	V2 t = vperp(n_);
+	tmass = 1.0/(k_scalar_body(pb.mia, r1, t) + k_scalar_body(pb.mib, r2, t));
+	double dist = vdot(vadd(vsub(r2, r1), pb.body_delta), n_);
+	bias = -bias_coef*fmin_cp(0.0, dist + slop)/dt;
+	// normal_relative_velocity (chipmunk_private.h:172-183)
+	V2 v1 = vadd(v2(pb.Va.x, pb.Va.y), vmul(vperp(r1), pb.Va.z));
+	V2 v2_ = vadd(v2(pb.Vb.x, pb.Vb.y), vmul(vperp(r2), pb.Vb.z));
+	bounce = vdot(vsub(v2_, v1), n_)*e;
+}
+
+// derived_only: refresh nMass / tMass / bias of the active records for a read-back after a production step (whose row
+// build computed them on the fly and never stored them); bounce needs the velocities from before the step and the bias
+// impulse belongs to the solver by then: both are left alone.
+__global__ void k_arb_prestep(DBodies B, DArbs A, const DSpace *__restrict__ spaces, double dt, int derived_only)
 {
 	int n = *A.count_ptr; if(n > A.cap) n = A.cap;
 	for(int i = CPB_TID; i < n; i += CPB_NTHREADS){
 	if(A.active[i] != 1){
-		if(A.active[i] == 0 && A.state[i] == CPB200_ARB_FIRST_COLLISION) A.state[i] = CPB200_ARB_NORMAL;   // cpSpaceStep.c:283
+		if(!derived_only && A.active[i] == 0 && A.state[i] == CPB200_ARB_FIRST_COLLISION) A.state[i] = CPB200_ARB_NORMAL;   // cpSpaceStep.c:283
 		continue;
 	}
 	int ba = A.ba[i], bb = A.bb[i];
 	DSpace sp = spaces[B.space[ba]];
 	V2 n_ = A.n[i];
-	V2 mia = B.MI[ba], mib = B.MI[bb];
-	double4 Va = B.V[ba], Vb = B.V[bb];
-	V2 body_delta = vsub(B.pos[bb], B.pos[ba]);
+	const PrestepBodies pb = prestep_bodies(B, ba, bb);
 	double e = A.e[i];
 	int cnt = A.cnt[i];
 	for(int k = 0; k < cnt; k++){
 		int c = CIDX(A, i, k);
-		V2 r1 = A.r1[c], r2 = A.r2[c];
-		A.nmass[c] = 1.0/(k_scalar_body(mia, r1, n_) + k_scalar_body(mib, r2, n_));
-		V2 t = vperp(n_);
-		A.tmass[c] = 1.0/(k_scalar_body(mia, r1, t) + k_scalar_body(mib, r2, t));
-		double dist = vdot(vadd(vsub(r2, r1), body_delta), n_);
-		A.bias[c] = -sp.bias_coef*fmin_cp(0.0, dist + sp.slop)/dt;
-		A.jb[c] = 0.0;
-		// normal_relative_velocity (chipmunk_private.h:172-183)
-		V2 v1 = vadd(v2(Va.x, Va.y), vmul(vperp(r1), Va.z));
-		V2 v2_ = vadd(v2(Vb.x, Vb.y), vmul(vperp(r2), Vb.z));
-		A.bounce[c] = vdot(vsub(v2_, v1), n_)*e;
+		double nm, tm, bi, bo;
+		prestep_contact(pb, n_, e, sp.bias_coef, sp.slop, dt, A.r1[c], A.r2[c], nm, tm, bi, bo);
+		A.nmass[c] = nm; A.tmass[c] = tm; A.bias[c] = bi;
+		if(!derived_only){ A.jb[c] = 0.0; A.bounce[c] = bo; }
 	}
 	}
-	(void)C; (void)max_pen;
 }
 
 // validation hook: narrowphase of one pair (cpShapesCollide, cpShape.c:259-283)

@@ -5,10 +5,12 @@
 
 // K1: cpBodyUpdatePosition + SetTransform (cpBody.c:511-522, 347-357) for every body of the
 // reference's dynamicBodies array: awake dynamic AND kinematic bodies (cpSpace.c:447).
-__global__ void k_integrate_pos(DBodies B, double dt)
+// (also clears the per-body scratch words of this step's graph colouring)
+__global__ void k_integrate_pos(DBodies B, double dt, unsigned long long *claim, unsigned long long *bmask)
 {
 	int i = CPB_TID;
 	if(i >= B.n) return;
+	claim[i] = 0ull; bmask[i] = 0ull;
 	if(B.type[i] == CPB200_BODY_STATIC || B.sleeping[i]) return;
 	if(B.custom[i] & CPB200_BODY_HOST_POSITION) return;   // the host ran this body's position_func and uploaded the result
 	double4 V = B.V[i], VB = B.VB[i];
@@ -84,11 +86,10 @@ __global__ void k_shape_cache(DShapes S, DBodies B, int all)
 
 // K9: cpBodyUpdateVelocity (cpBody.c:493-509); kinematic bodies are skipped, forces reset.
 // Also clears the two per-body words of the colouring that follows (one launch instead of two memsets).
-__global__ void k_integrate_vel(DBodies B, const DSpace *__restrict__ spaces, double dt, unsigned long long *claim, unsigned long long *bmask)
+__global__ void k_integrate_vel(DBodies B, const DSpace *__restrict__ spaces, double dt)
 {
 	int i = CPB_TID;
 	if(i >= B.n) return;
-	claim[i] = 0ull; bmask[i] = 0ull;
 	if(B.type[i] != CPB200_BODY_DYNAMIC || B.sleeping[i]) return;
 	if(B.custom[i] & CPB200_BODY_HOST_VELOCITY) return;   // the host runs this body's velocity_func between prestep and solver
 	DSpace sp = spaces[B.space[i]];

@@ -178,7 +178,13 @@ CPB_DEVICE void colour_starts(const DColour &K, DCounters *C){
 	C->n_colours = ncol;
 }
 
-CPB_DEVICE void write_row(const DArbs &A, const DRows &R, int i, int r){
+// A production step folds K8 (cpArbiterPreStep) into the row build: the row build reads every active record anyway, so
+// nMass / tMass / bias / bounce go straight from registers into the row instead of through five record arrays and back
+// (k_arb_prestep's round trip: 5 doubles per contact written, then gathered again 0.3 ms later).  on == 0: the numbers
+// are in the records already (split steps -- collision handlers, validation hooks --, the serial solver, the emulator).
+struct DPrestep { const DSpace *spaces; double dt; int on; };
+
+CPB_DEVICE void write_row(const DBodies &B, const DPrestep &P, const DArbs &A, const DRows &R, int i, int r){
 	if(r >= R.cap) return;
 	// gather everything first, then scatter: the record and row arrays may alias as far as the compiler knows, so
 	// interleaved copies would serialise into load -> store -> load chains (one memory latency per field)
@@ -187,12 +193,21 @@ CPB_DEVICE void write_row(const DArbs &A, const DRows &R, int i, int r){
 	const double u = A.u[i];
 	const int s0 = CIDX(A, i, 0), s1 = CIDX(A, i, 1);
 	const V2 r1a = A.r1[s0], r2a = A.r2[s0];
-	const double nma = A.nmass[s0], tma = A.tmass[s0], boa = A.bounce[s0], bia = A.bias[s0], jna = A.jn[s0], jta = A.jt[s0], jba = A.jb[s0];
+	double nma, tma, boa, bia, jba;
+	const double jna = A.jn[s0], jta = A.jt[s0];
 	V2 r1b = r1a, r2b = r2a;
 	double nmb = 0.0, tmb = 0.0, bob = 0.0, bib = 0.0, jnb = 0.0, jtb = 0.0, jbb = 0.0;
-	if(cnt == 2){
-		r1b = A.r1[s1]; r2b = A.r2[s1];
-		nmb = A.nmass[s1]; tmb = A.tmass[s1]; bob = A.bounce[s1]; bib = A.bias[s1]; jnb = A.jn[s1]; jtb = A.jt[s1]; jbb = A.jb[s1];
+	if(cnt == 2){ r1b = A.r1[s1]; r2b = A.r2[s1]; jnb = A.jn[s1]; jtb = A.jt[s1]; }
+	if(P.on){
+		const DSpace sp = P.spaces[B.space[ba]];
+		const PrestepBodies pb = prestep_bodies(B, ba, bb);
+		const double e = A.e[i];
+		prestep_contact(pb, n, e, sp.bias_coef, sp.slop, P.dt, r1a, r2a, nma, tma, bia, boa);
+		jba = 0.0;
+		if(cnt == 2) prestep_contact(pb, n, e, sp.bias_coef, sp.slop, P.dt, r1b, r2b, nmb, tmb, bib, bob);
+	} else {
+		nma = A.nmass[s0]; tma = A.tmass[s0]; boa = A.bounce[s0]; bia = A.bias[s0]; jba = A.jb[s0];
+		if(cnt == 2){ nmb = A.nmass[s1]; tmb = A.tmass[s1]; bob = A.bounce[s1]; bib = A.bias[s1]; jbb = A.jb[s1]; }
 	}
 	R.arb[r] = i; R.ba[r] = ba; R.bb[r] = bb;
 	// first-collision arbiters skip the warm start (cpArbiter.c:444): flag in the sign of cnt
@@ -212,19 +227,28 @@ CPB_DEVICE void write_row(const DArbs &A, const DRows &R, int i, int r){
 }
 
 // the same row in the packed layout of the space-local solver
-CPB_DEVICE void write_row_packed(const DArbs &A, const DRows &R, int i, int r){
+CPB_DEVICE void write_row_packed(const DBodies &B, const DPrestep &P, const DArbs &A, const DRows &R, int i, int r){
 	if(r >= R.cap) return;
 	const int ba = A.ba[i], bb = A.bb[i], cnt = A.cnt[i], state = A.state[i];
 	const V2 n = A.n[i], svr = A.svr[i];
 	const double u = A.u[i];
 	const int s0 = CIDX(A, i, 0), s1 = CIDX(A, i, 1);
 	const V2 r1a = A.r1[s0], r2a = A.r2[s0];
-	const double nma = A.nmass[s0], tma = A.tmass[s0], boa = A.bounce[s0], bia = A.bias[s0], jna = A.jn[s0], jta = A.jt[s0], jba = A.jb[s0];
+	double nma, tma, boa, bia, jba;
+	const double jna = A.jn[s0], jta = A.jt[s0];
 	V2 r1b = r1a, r2b = r2a;
 	double nmb = 0.0, tmb = 0.0, bob = 0.0, bib = 0.0, jnb = 0.0, jtb = 0.0, jbb = 0.0;
-	if(cnt == 2){
-		r1b = A.r1[s1]; r2b = A.r2[s1];
-		nmb = A.nmass[s1]; tmb = A.tmass[s1]; bob = A.bounce[s1]; bib = A.bias[s1]; jnb = A.jn[s1]; jtb = A.jt[s1]; jbb = A.jb[s1];
+	if(cnt == 2){ r1b = A.r1[s1]; r2b = A.r2[s1]; jnb = A.jn[s1]; jtb = A.jt[s1]; }
+	if(P.on){
+		const DSpace sp = P.spaces[B.space[ba]];
+		const PrestepBodies pb = prestep_bodies(B, ba, bb);
+		const double e = A.e[i];
+		prestep_contact(pb, n, e, sp.bias_coef, sp.slop, P.dt, r1a, r2a, nma, tma, bia, boa);
+		jba = 0.0;
+		if(cnt == 2) prestep_contact(pb, n, e, sp.bias_coef, sp.slop, P.dt, r1b, r2b, nmb, tmb, bib, bob);
+	} else {
+		nma = A.nmass[s0]; tma = A.tmass[s0]; boa = A.bounce[s0]; bia = A.bias[s0]; jba = A.jb[s0];
+		if(cnt == 2){ nmb = A.nmass[s1]; tmb = A.tmass[s1]; bob = A.bounce[s1]; bib = A.bias[s1]; jbb = A.jb[s1]; }
 	}
 	R.hdr[r] = make_int4(ba, bb, (state == CPB200_ARB_FIRST_COLLISION ? -cnt : cnt), i);
 	R.nsv[r] = make_double4(n.x, n.y, svr.x, svr.y);
@@ -245,7 +269,7 @@ CPB_DEVICE void write_row_packed(const DArbs &A, const DRows &R, int i, int r){
 // scnt/sbase: per-CTA shared scratch [CPB_MAX_COLOURS] (NULL in the emulation build): a CTA counts its
 // rows per colour, reserves one contiguous range per colour with a single global atomic, then hands the
 // slots out with shared-memory atomics.
-CPB_DEVICE void build_rows(const DArbs &A, const DJoints &J, const DRows &R, const DColour &K, int *scnt, int *sbase, int nA, int tid, int nth, bool chunked){
+CPB_DEVICE void build_rows(const DBodies &B, const DPrestep &P, const DArbs &A, const DJoints &J, const DRows &R, const DColour &K, int *scnt, int *sbase, int nA, int tid, int nth, bool chunked){
 #ifndef CPB_EMU
 	if(scnt){
 		// every CTA takes ONE contiguous chunk of the records (they were appended in pair-list order, i.e. along the
@@ -268,10 +292,14 @@ CPB_DEVICE void build_rows(const DArbs &A, const DJoints &J, const DRows &R, con
 		}
 		__syncthreads();
 		for(int i = i0; i < i1; i += istep){
-			if(A.active[i] != 1) continue;
+			if(A.active[i] != 1){
+				// (the stand-alone K8 kernel's other duty, cpSpaceStep.c:283)
+				if(P.on && A.active[i] == 0 && A.state[i] == CPB200_ARB_FIRST_COLLISION) A.state[i] = CPB200_ARB_NORMAL;
+				continue;
+			}
 			int col = A.colour[i];
 			if(col < 0) continue;
-			write_row(A, R, i, K.cstart[col] + sbase[col] + atomicAdd(&scnt[col], 1));
+			write_row(B, P, A, R, i, K.cstart[col] + sbase[col] + atomicAdd(&scnt[col], 1));
 		}
 		__syncthreads();
 		if(threadIdx.x < CPB_MAX_COLOURS) scnt[threadIdx.x] = 0;
@@ -279,10 +307,13 @@ CPB_DEVICE void build_rows(const DArbs &A, const DJoints &J, const DRows &R, con
 #endif
 	{
 		for(int i = tid; i < nA; i += nth){
-			if(A.active[i] != 1) continue;
+			if(A.active[i] != 1){
+				if(P.on && A.active[i] == 0 && A.state[i] == CPB200_ARB_FIRST_COLLISION) A.state[i] = CPB200_ARB_NORMAL;
+				continue;
+			}
 			int col = A.colour[i];
 			if(col < 0) continue;
-			write_row(A, R, i, K.cstart[col] + atomicAdd(&K.ccursor[col], 1));
+			write_row(B, P, A, R, i, K.cstart[col] + atomicAdd(&K.ccursor[col], 1));
 		}
 	}
 	for(int j = tid; j < J.n; j += nth){
@@ -622,16 +653,19 @@ CPB_DEVICE void sl_count(const DBodies &B, const DArbs &A, const DJoints &J, con
 	}
 }
 
-__global__ void k_sl_rows(DBodies B, DArbs A, DJoints J, DRows R, DSpaceLocal SL)
+__global__ void k_sl_rows(DBodies B, DArbs A, DJoints J, DRows R, DSpaceLocal SL, DPrestep P)
 {
 	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
 	const int tid = CPB_TID, nth = CPB_NTHREADS;
 	const int jbase = (int)SL.start[SL.n_spaces*CPB_MAX_COLOURS];   // sentinel: never incremented
 	for(int i = tid; i < nA; i += nth){
-		if(A.active[i] != 1) continue;
+		if(A.active[i] != 1){
+			if(P.on && A.active[i] == 0 && A.state[i] == CPB200_ARB_FIRST_COLLISION) A.state[i] = CPB200_ARB_NORMAL;
+			continue;
+		}
 		int col = A.colour[i];
 		if(col < 0) continue;
-		write_row_packed(A, R, i, (int)atomicAdd(&SL.start[sl_arb_bucket(B.space[A.ba[i]], col)], 1u));
+		write_row_packed(B, P, A, R, i, (int)atomicAdd(&SL.start[sl_arb_bucket(B.space[A.ba[i]], col)], 1u));
 	}
 	for(int j = tid; j < J.n; j += nth){
 		int col = J.colour[j];
@@ -756,7 +790,7 @@ __device__ __forceinline__ unsigned long long global_ns(){ unsigned long long t;
 // allocation of a kernel is the maximum over its phases -- the row build holds a whole arbiter record in registers
 // (gather, then scatter) and would cap the occupancy of the iteration loop, which is the part that needs warps to
 // hide its gathers.  (PHASE 0 = both in one launch, kept for comparison.)
-template<bool SPACE_LOCAL, bool STREAM_ROWS, bool JOINTS, int PHASE, int MINB> __global__ void __launch_bounds__(256, MINB) k_colour_solve(DBodies B, DArbs A, DJoints J, DRows R, DColour K, DCounters *C, unsigned *bar, DSpaceLocal SL, int use_hints, int iterations, double dt, double dt_coef)
+template<bool SPACE_LOCAL, bool STREAM_ROWS, bool JOINTS, int PHASE, int MINB> __global__ void __launch_bounds__(256, MINB) k_colour_solve(DBodies B, DArbs A, DJoints J, DRows R, DColour K, DCounters *C, unsigned *bar, DSpaceLocal SL, int use_hints, int iterations, double dt, double dt_coef, DPrestep P)
 {
 	__shared__ int s_hist[2*CPB_MAX_COLOURS];
 	__shared__ int s_base[CPB_MAX_COLOURS];
@@ -799,7 +833,7 @@ template<bool SPACE_LOCAL, bool STREAM_ROWS, bool JOINTS, int PHASE, int MINB> _
 		return;
 	}
 	GRID_SYNC();
-	build_rows(A, J, R, K, s_hist, s_base, nA, tid, nth, (use_hints & 4) == 0);   // bit 2 of use_hints: experiment switch, strided records
+	build_rows(B, P, A, J, R, K, s_hist, s_base, nA, tid, nth, (use_hints & 4) == 0);   // bit 2 of use_hints: experiment switch, strided records
 	if(PHASE == 1){ __syncthreads(); PROF(2); return; }
 	GRID_SYNC();
 	PROF(2);
@@ -880,7 +914,7 @@ __global__ void k_colour_finish(DArbs A, DJoints J, DRows R, DColour K, DCounter
 	int nA = *A.count_ptr; if(nA > A.cap) nA = A.cap;
 	if(stage == 2){ colour_leftover(A, J, K, (int *)NULL, nA, CPB_MAX_COLOUR_ROUNDS, CPB_TID, CPB_NTHREADS); return; }
 	if(stage == 0){ if(CPB_TID == 0) colour_starts(K, C); }
-	else build_rows(A, J, R, K, (int *)NULL, (int *)NULL, nA, CPB_TID, CPB_NTHREADS, true);
+	else { DPrestep P = {NULL, 0.0, 0}; DBodies B = {}; build_rows(B, P, A, J, R, K, (int *)NULL, (int *)NULL, nA, CPB_TID, CPB_NTHREADS, true); }
 }
 __global__ void k_solve_colour(DBodies B, DRows R, DJoints J, DColour K, int colour, int mode, double dt, double dt_coef){
 	if(colour == CPB_OVERFLOW_COLOUR){ if(CPB_TID == 0) solve_overflow<true>(B, R, J, K, mode, dt, dt_coef); }

@@ -82,11 +82,11 @@ extern "C" int cpb200_device_available(void)
 // ------------------------------------------------------------------ stages (profiling)
 enum {
 	ST_INTEGRATE_POS, ST_SHAPE_CACHE, ST_BVH_KEYS, ST_BVH_SORT, ST_BVH_BUILD, ST_BVH_PAIRS,
-	ST_COLLIDE, ST_ISLANDS, ST_CARRY, ST_PRESTEP, ST_INTEGRATE_VEL, ST_COLOUR, ST_SOLVE, ST_COUNT
+	ST_COLLIDE, ST_ISLANDS, ST_CARRY, ST_PRESTEP, ST_COLOUR, ST_INTEGRATE_VEL, ST_SOLVE, ST_COUNT
 };
 static const char *g_stage_names[ST_COUNT] = {
 	"integrate_pos", "shape_cache", "bvh_keys", "bvh_sort", "bvh_build", "bvh_pairs",
-	"collide", "islands", "arbiter_carry", "prestep", "integrate_vel", "colour_rows", "solve"
+	"collide", "islands", "arbiter_carry", "prestep", "colour_rows", "integrate_vel", "solve"
 };
 extern "C" const char *cpb200_stage_name(int i){ return (i >= 0 && i < ST_COUNT) ? g_stage_names[i] : ""; }
 
@@ -166,6 +166,7 @@ struct cpb200_world {
 	// refitted tree is an exact bounding hierarchy whatever its age, so the pair set does not depend on this; only the
 	// traversal gets dearer as the boxes of an old topology spread.  Structural edits rebuild at once.
 	bool bvh_valid; int bvh_age, bvh_period;
+	bool arb_derived_stale[2];  // per arbiter buffer: the last step computed nMass / tMass / bias inside its row build; a read-back recomputes them
 	bool bvh_no_valve;          // env CPB200_BVH_NO_VALVE (measurement switch)
 	double bvh_fresh_visits;    // visits per query right after a rebuild (0 = not measured): cpb200_world_sync rebuilds early when an aged tree needs 1.5x that
 	bool graph_enabled;
@@ -331,6 +332,7 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	w->d_query = NULL; w->query_bytes = 0;
 	w->mid_solve = false; w->solver_variant = 0; w->last_solver_path = 0;
 	memset(w->graph, 0, sizeof(w->graph)); memset(w->graph_last_sig, 0, sizeof(w->graph_last_sig)); w->graph_replays = w->graph_captures = 0;
+	w->arb_derived_stale[0] = w->arb_derived_stale[1] = false;
 	w->bvh_valid = false; w->bvh_age = 0; w->bvh_period = 8; w->bvh_fresh_visits = 0.0; w->bvh_no_valve = (getenv("CPB200_BVH_NO_VALVE") != NULL);
 	{ const char *e = getenv("CPB200_BVH_PERIOD"); if(e && atoi(e) >= 1) w->bvh_period = atoi(e); }
 	w->graph_enabled = (getenv("CPB200_NO_GRAPH") == NULL); w->graph_error[0] = 0;
@@ -1447,6 +1449,7 @@ static int step_phase_a(cpb200_world *w, double dt)
 	int prv = w->cur; w->cur ^= 1;
 	DArbs &Ap = w->A[prv]; DArbs &Ac = w->A[w->cur];
 	DTable &Tp = w->T[prv];
+	w->arb_derived_stale[w->cur] = false;
 	LAUNCH(k_reset_step, 1, 32, st, w->C, w->P.count, Ac.count_ptr, w->K.ccount, w->K.jcount, w->K.wl_n, w->d_barrier);
 
 	const int nb = B.n, ns = S.n;
@@ -1463,7 +1466,7 @@ static int step_phase_a(cpb200_world *w, double dt)
 			CPB_CHECK(cudaEventRecord(w->ev_io_forces, w->stream_io));
 		}
 	}
-	if(nb) LAUNCH(k_integrate_pos, grid_for(nb, 256), 256, st, B, dt);
+	if(nb) LAUNCH(k_integrate_pos, grid_for(nb, 256), 256, st, B, dt, w->K.claim, w->K.bmask);
 	if(io && w->io_sink){
 		LAUNCH(k_pack_pos, grid_for(nb, 256), 256, st, B, w->d_io_pos);
 		CPB_CHECK(cudaEventRecord(w->ev_io_pos, st)); CPB_CHECK(cudaStreamWaitEvent(w->stream_io, w->ev_io_pos, 0));
@@ -1546,10 +1549,26 @@ static int step_phase_a(cpb200_world *w, double dt)
 	return 0;
 }
 
-static int step_phase_b2(cpb200_world *w);
+static int step_phase_b2(cpb200_world *w, bool fused);
+
+// K9 (with the forces of a bound host buffer)
+static int launch_integrate_vel(cpb200_world *w)
+{
+	cudaStream_t st = w->stream;
+	const int nb = w->B.n;
+	if(w->io_src && nb > 0 && w->io_cap >= nb){
+		CPB_CHECK(cudaStreamWaitEvent(st, w->ev_io_forces, 0));
+		LAUNCH(k_set_forces, grid_for(nb, 256), 256, st, w->B, (const double *)w->d_io_force, 0, nb);
+	}
+	if(nb) LAUNCH(k_integrate_vel, grid_for(nb, 256), 256, st, w->B, (const DSpace *)w->d_spaces, w->step_dt);
+	return 0;
+}
 
 // Phase B up to the solver: islands, cache ageing + table, prestep, velocity integration.
-static int step_phase_b1(cpb200_world *w)
+// fused (a production step that nothing interrupts between the collision phase and the solver): the arbiters' prestep
+// is folded into the solver's row build and the velocity integration follows it -- cpArbiterPreStep must see the
+// velocities from before cpBodyUpdateVelocity (bounce, cpArbiter.c:436) -- see step_phase_b2.
+static int step_phase_b1(cpb200_world *w, bool fused)
 {
 	cudaSetDevice(w->device);
 	cudaStream_t st = w->stream;
@@ -1559,7 +1578,6 @@ static int step_phase_b1(cpb200_world *w)
 	const int prv = w->cur ^ 1;
 	DArbs &Ap = w->A[prv]; DArbs &Ac = w->A[w->cur];
 	DTable &Tc = w->T[w->cur];
-	const int nb = B.n;
 	const int wide = w->sm_count*8;
 	w->mid_step = false;
 
@@ -1587,26 +1605,29 @@ static int step_phase_b1(cpb200_world *w)
 	// K8
 	{
 		int g = std::min(grid_for(Ac.cap, 128), wide);
-		LAUNCH(k_arb_prestep, g, 128, st, B, Ac, (const DSpace *)w->d_spaces, dt, w->C, (double *)NULL);
+		if(!fused) LAUNCH(k_arb_prestep, g, 128, st, B, Ac, (const DSpace *)w->d_spaces, dt, 0);
 		if(J.n) LAUNCH(k_joint_prestep, grid_for(J.n, 128), 128, st, J, B, dt);
 	}
+	w->arb_derived_stale[w->cur] = fused;
 	STAGE_END(w, ST_PRESTEP);
-
-	// K9
-	if(w->io_src && nb > 0 && w->io_cap >= nb){
-		CPB_CHECK(cudaStreamWaitEvent(st, w->ev_io_forces, 0));
-		LAUNCH(k_set_forces, grid_for(nb, 256), 256, st, B, (const double *)w->d_io_force, 0, nb);
+	if(!fused){
+		// K9 (stage order of the profile: colour_rows closes empty here, the colouring is timed with the solver)
+		STAGE_END(w, ST_COLOUR);
+		if(launch_integrate_vel(w)) return -1;
+		STAGE_END(w, ST_INTEGRATE_VEL);
 	}
-	if(nb) LAUNCH(k_integrate_vel, grid_for(nb, 256), 256, st, B, (const DSpace *)w->d_spaces, dt, w->K.claim, w->K.bmask);
-	STAGE_END(w, ST_INTEGRATE_VEL);
 	w->mid_solve = true;
 	return 0;
 }
 
-static int step_phase_b(cpb200_world *w)
+static int step_phase_b(cpb200_world *w, bool fused)
 {
-	if(step_phase_b1(w)) return -1;
-	return step_phase_b2(w);
+#ifdef CPB_EMU
+	fused = false;
+#endif
+	if(w->solver_mode == 1) fused = false;   // the serial validation solver reads the records
+	if(step_phase_b1(w, fused)) return -1;
+	return step_phase_b2(w, fused);
 }
 
 // How the coloured solver is launched this step: grid of the persistent kernel, kernel family, CTA width of the
@@ -1643,7 +1664,7 @@ static SolvePlan plan_solver(cpb200_world *w)
 }
 
 // K10 + K11 and the end of the step
-static int step_phase_b2(cpb200_world *w)
+static int step_phase_b2(cpb200_world *w, bool fused)
 {
 	cudaSetDevice(w->device);
 	cudaStream_t st = w->stream;
@@ -1655,7 +1676,6 @@ static int step_phase_b2(cpb200_world *w)
 	const int nb = B.n;
 	const int wide = w->sm_count*8;
 	w->mid_solve = false;
-	STAGE_END(w, ST_COLOUR);   // (re-recorded after the colouring kernel on the production path)
 
 	if(w->solver_mode == 1){
 		int need = Ac.cap;
@@ -1692,13 +1712,18 @@ static int step_phase_b2(cpb200_world *w)
 			if(!space_local) SL.start = NULL;
 			size_t nbuckets = 2*(size_t)w->n_spaces*CPB_MAX_COLOURS + 2;
 			if(space_local) cudaMemsetAsync(SL.start, 0, sizeof(uint32_t)*nbuckets, st);
-			void *args[] = {&B, &Ac, &J, &R, &K, &C, &bar, &SL, &use_hints, &iterations, &dt, &dt_coef};
+			DPrestep P = {(const DSpace *)w->d_spaces, dt, fused ? 1 : 0};
+			void *args[] = {&B, &Ac, &J, &R, &K, &C, &bar, &SL, &use_hints, &iterations, &dt, &dt_coef, &P};
 			const bool joints = (J.n > 0);
 			// colouring (+ row build) and the iteration loop are separate cooperative launches: each gets its own register budget
 			void *k_colour = space_local ? (void *)k_colour_solve<true, true, true, 1, 2> : (void *)k_colour_solve<false, true, true, 1, 2>;
 			CPB_CHECK(cudaLaunchCooperativeKernel(k_colour, dim3(blocks), dim3(256), args, 0, st));
 			g_cpb_launches++;
-			STAGE_END(w, ST_COLOUR);
+			if(fused && !space_local){
+				STAGE_END(w, ST_COLOUR);
+				if(launch_integrate_vel(w)) return -1;
+				STAGE_END(w, ST_INTEGRATE_VEL);
+			}
 			if(!space_local){
 				const int m3 = (w->solve_minb == 3 ? 1 : 0);
 				static void *const k_iterate[2][2][2] = {   // [stream_rows][joints][min blocks 2 | 3]
@@ -1713,7 +1738,12 @@ static int step_phase_b2(cpb200_world *w)
 			if(space_local){
 				cpb_exclusive_scan(SL.start, SL.start, (int)nbuckets, w->sl_tmp, st);
 				int g = std::min(grid_for(Ac.cap + J.n, 256), wide);
-				LAUNCH(k_sl_rows, g, 256, st, B, Ac, J, R, SL);
+				LAUNCH(k_sl_rows, g, 256, st, B, Ac, J, R, SL, P);
+				if(fused){
+					STAGE_END(w, ST_COLOUR);
+					if(launch_integrate_vel(w)) return -1;
+					STAGE_END(w, ST_INTEGRATE_VEL);
+				}
 				const int threads = plan.threads;
 				size_t smem = (size_t)w->sl_max_nbody*64;
 				const bool fork = (w->n_sl_plain > 0 && w->n_sl_jointed > 0);
@@ -1804,6 +1834,7 @@ static void step_bookkeeping(cpb200_world *w, double dt, int iterations, int sol
 	w->stamp++;
 	w->curr_dt = dt;
 	w->cur ^= 1;
+	w->arb_derived_stale[w->cur] = true;   // graphs hold production steps only (prestep folded into the row build)
 	w->step_dt = dt; w->step_dt_coef = 1.0; w->step_iterations = iterations;
 	w->mid_step = false; w->mid_solve = false;
 	w->hints_valid = true;
@@ -1826,7 +1857,7 @@ static int step_graphed(cpb200_world *w, double dt)
 	if(!steady){
 		memset(w->graph_last_sig, 0, sizeof(w->graph_last_sig));
 		if(step_phase_a(w, dt)) return -1;
-		return step_phase_b(w);
+		return step_phase_b(w, true);
 	}
 	const SolvePlan plan = plan_solver(w);
 	const bool rebuild = bvh_in_use(w) && bvh_rebuild_due(w);
@@ -1843,7 +1874,7 @@ static int step_graphed(cpb200_world *w, double dt)
 		// first step with this signature: run it as it is; if the next one of this slot looks the same it is captured
 		w->graph_last_sig[slot] = sig;
 		if(step_phase_a(w, dt)) return -1;
-		return step_phase_b(w);
+		return step_phase_b(w, true);
 	}
 	// capture: the step functions enqueue into the capturing stream; nothing executes until the graph is launched
 	const uint32_t s_stamp = w->stamp; const double s_curr_dt = w->curr_dt; const int s_cur = w->cur; const uint64_t s_steps = w->steps;
@@ -1856,7 +1887,7 @@ static int step_graphed(cpb200_world *w, double dt)
 	const char *where = "cudaStreamBeginCapture";
 	if(ce == cudaSuccess){
 		rc = step_phase_a(w, dt);
-		if(!rc) rc = step_phase_b(w);
+		if(!rc) rc = step_phase_b(w, true);
 		if(rc){ where = "enqueue under capture"; snprintf(w->graph_error, sizeof(w->graph_error), "%s", cpb200_last_error()); }
 		ce = cudaStreamEndCapture(st, &graph);
 		if(ce != cudaSuccess || !graph){ if(!rc) where = "cudaStreamEndCapture"; rc = -1; }
@@ -1873,7 +1904,7 @@ static int step_graphed(cpb200_world *w, double dt)
 		w->last_solver_path = s_path; w->mid_step = false; w->mid_solve = false; w->bvh_valid = s_bvh_valid; w->bvh_age = s_bvh_age;
 		w->graph_enabled = false;
 		if(step_phase_a(w, dt)) return -1;
-		return step_phase_b(w);
+		return step_phase_b(w, true);
 	}
 	G.exec = exec; G.sig = sig; G.launches = (int)(g_cpb_launches - s_launches); G.solver_path = w->last_solver_path;
 	w->graph_captures++;
@@ -1891,7 +1922,7 @@ extern "C" int cpb200_world_step(cpb200_world *w, double dt)
 	if(w->graph_enabled && w->solver_mode == 0 && !w->profiling) return step_graphed(w, dt);
 #endif
 	if(step_phase_a(w, dt)) return -1;
-	return step_phase_b(w);
+	return step_phase_b(w, true);
 }
 
 /* Validation hook: replay the captured step graph (1, default unless CPB200_NO_GRAPH is set) or launch every kernel (0). */
@@ -1922,16 +1953,16 @@ extern "C" int cpb200_world_step_collide(cpb200_world *w, double dt)
 extern "C" int cpb200_world_step_finish(cpb200_world *w)
 {
 	if(!w){ cpb_set_error("null world"); return -1; }
-	if(w->mid_solve) return step_phase_b2(w);
+	if(w->mid_solve) return step_phase_b2(w, false);
 	if(!w->mid_step){ cpb_set_error("cpb200_world_step_finish without cpb200_world_step_collide"); return -1; }
-	return step_phase_b(w);
+	return step_phase_b(w, false);
 }
 
 extern "C" int cpb200_world_step_presolve(cpb200_world *w)
 {
 	if(!w){ cpb_set_error("null world"); return -1; }
 	if(!w->mid_step){ cpb_set_error("cpb200_world_step_presolve without cpb200_world_step_collide"); return -1; }
-	return step_phase_b1(w);
+	return step_phase_b1(w, false);
 }
 
 // Host decisions of the begin/preSolve handlers applied to this step's records (cpSpaceStep.c:257-285,
@@ -2094,6 +2125,11 @@ extern "C" int cpb200_world_get_arbiters(cpb200_world *w, int cap, cpb200_arbite
 	if(world_sync(w)) return -1;
 	if(counters_check(w)) return -2;   // a host that reads arbiters (collision handlers) must not see a truncated list silently
 	if(n > A.cap) n = A.cap;
+	if(w->arb_derived_stale[w->cur] && out && n > 0){
+		// the last step was a production step: nMass / tMass / bias lived in the solver's rows only (step_phase_b1)
+		LAUNCH(k_arb_prestep, std::min(grid_for(A.cap, 128), w->sm_count*8), 128, w->stream, w->B, A, (const DSpace *)w->d_spaces, w->step_dt, 1);
+		w->arb_derived_stale[w->cur] = false;
+	}
 	size_t N = (size_t)n;
 	std::vector<int> sa, sb, ba, bb, cnt, state, active; std::vector<uint32_t> stamp; std::vector<V2> nn, svr, r1, r2;
 	std::vector<double> e, u, nmass, tmass, bounce, bias, jn, jt, jb; std::vector<uint64_t> hash;

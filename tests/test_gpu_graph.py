@@ -88,3 +88,35 @@ def test_bound_io_equals_blocking_uploads_and_downloads(name):
     assert np.array_equal(a.bodies()["p"], b.bodies()["p"])
     with pytest.raises(Exception):
         a.bind_io(np.zeros((n, 3)), None)          # pageable memory is refused
+
+
+@pytest.mark.parametrize("name", ["ComplexTerrainHexagons_1000", "PyramidStack", "Chains", "mixed6k", "pile20k", "batch8"])
+def test_production_step_equals_split_step(name):
+    """A production step folds cpArbiterPreStep into the solver's row build and integrates the velocities after it
+    (cpArbiterPreStep reads the velocities from before cpBodyUpdateVelocity); a split step -- collision handlers, the
+    validation hooks of the oracle replay -- runs the stand-alone kernels in the reference's order.  Same arithmetic on
+    the same inputs: identical bits, in the bodies and in the arbiters (nMass / tMass / bias are recomputed on read-back
+    after a production step)."""
+    scenes = {"batch8": lambda: batched_demo_scenes(8), "pile20k": lambda: [circle_pile(20000, dense=True, sleep=0.5)],
+              "mixed6k": lambda: [mixed_drop(6000)]}.get(name, lambda: [golden_scene(name)])()
+    a, b = World(len(scenes)), World(len(scenes))
+    a.load_scenes(scenes); b.load_scenes(scenes)
+    dt = scenes[0].dt
+    steps = 320 if name in ("PyramidStack", "batch8") else 80
+    for s in range(steps):
+        a.step(dt)
+        b.step_collide(dt); b.step_presolve(); b.step_finish()
+        if s % 20 == 19 or s == steps - 1:
+            a.sync(); b.sync()
+            assert same(a, b), (name, s)
+            ra, rb = a.arbiters(active_only=True), b.arbiters(active_only=True)
+            assert len(ra) == len(rb)
+            oa, ob = np.argsort(ra["shape_a"].astype(np.int64) << 32 | ra["shape_b"]), np.argsort(rb["shape_a"].astype(np.int64) << 32 | rb["shape_b"])
+            ra, rb = ra[oa], rb[ob]
+            for f in ("shape_a", "shape_b", "count", "n", "e", "u"):
+                assert np.array_equal(ra[f], rb[f]), (name, s, f)
+            for k in range(2):
+                m = ra["count"] > k
+                for f in ("r1", "r2", "n_mass", "t_mass", "bias", "jn_acc", "jt_acc", "j_bias"):
+                    assert np.array_equal(ra["contacts"][f][m, k], rb["contacts"][f][m, k]), (name, s, k, f)
+    assert a.stats()["n_arbiters"] > 0
