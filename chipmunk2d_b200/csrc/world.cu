@@ -193,6 +193,7 @@ struct cpb200_world {
 	DSpaceShapes SS; bool sl_shapes_ok; int sl_max_nshape;
 	std::vector<int> joint_body;   // host copy: body a of every joint (its space has constraints)
 	int *d_sl_plain, *d_sl_jointed; int n_sl_plain, n_sl_jointed;
+	cudaEvent_t ev_fork_a, ev_join_a;   // k_pack_warm runs beside the broadphase (stream2)
 	cudaStream_t stream2; cudaEvent_t ev_fork, ev_join;   // the two k_sl_solve launches touch disjoint spaces: run them side by side   // spaces without / with joints (k_sl_solve launches)
 	uint32_t *sl_tmp;
 	void *d_query; size_t query_bytes;   // device buffer for query hits (+ counters in its first 64 bytes)
@@ -285,6 +286,7 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	cudaStreamCreate(&w->stream);
 	cudaStreamCreate(&w->stream2);
 	cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&w->ev_fork_a, cudaEventDisableTiming); cudaEventCreateWithFlags(&w->ev_join_a, cudaEventDisableTiming);
 	w->sm_count = 148;
 	w->coop_blocks = 148; w->solve_minb = 2;
 #ifndef CPB_EMU
@@ -370,7 +372,7 @@ extern "C" void cpb200_world_destroy(cpb200_world *w)
 	if(w->d_joint_order) cudaFree(w->d_joint_order);
 	if(w->d_nocollide) cudaFree(w->d_nocollide);
 	for(int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(w->ev[i]);
-	cudaStreamDestroy(w->stream2); cudaEventDestroy(w->ev_fork); cudaEventDestroy(w->ev_join);
+	cudaStreamDestroy(w->stream2); cudaEventDestroy(w->ev_fork); cudaEventDestroy(w->ev_join); cudaEventDestroy(w->ev_fork_a); cudaEventDestroy(w->ev_join_a);
 	cudaStreamDestroy(w->stream_io); cudaEventDestroy(w->ev_io_begin); cudaEventDestroy(w->ev_io_forces); cudaEventDestroy(w->ev_io_pos); cudaEventDestroy(w->ev_io_join);
 	if(w->d_io_force) cudaFree(w->d_io_force);
 	if(w->d_io_pos) cudaFree(w->d_io_pos);
@@ -1476,6 +1478,18 @@ static int step_phase_a(cpb200_world *w, double dt)
 	if(ns) LAUNCH(k_shape_cache, grid_for(ns, 128), 128, st, S, B, 0);
 	STAGE_END(w, ST_SHAPE_CACHE);
 
+	// The warm-start lines of last step's records (what the narrowphase looks up) depend on nothing this step does: the
+	// pass that packs them runs on a second stream, one CTA per SM, beside the tree build / refit, and joins in front of
+	// the collide kernels.  Worth 1 % of the 1 M step.  Measured alternatives: beside the integrators (bandwidth-bound
+	// themselves) it gains nothing; with a full grid it crowds the refit's warps out and slows that atomic chain down
+	// by what it saves; beside the traversal it costs more (0.24 -> 0.34 ms) than it saves.
+#ifndef CPB_EMU
+	CPB_CHECK(cudaEventRecord(w->ev_fork_a, st)); CPB_CHECK(cudaStreamWaitEvent(w->stream2, w->ev_fork_a, 0));
+	LAUNCH(k_pack_warm, std::min(grid_for(Ap.cap, 256), w->sm_count), 256, w->stream2, Ap);
+	CPB_CHECK(cudaEventRecord(w->ev_join_a, w->stream2));
+#endif
+
+
 	// K3: space-local all-pairs broadphase for worlds of small spaces, else the LBVH
 	if(w->sl_dirty && sl_refresh(w)) return -1;
 #ifndef CPB_EMU
@@ -1538,7 +1552,11 @@ static int step_phase_a(cpb200_world *w, double dt)
 	// K5 + K6
 	{
 		int g = std::min(grid_for(w->P.cap, 128), w->sm_count*CPB_COLLIDE_CTAS);
+#ifndef CPB_EMU
+		CPB_CHECK(cudaStreamWaitEvent(st, w->ev_join_a, 0));
+#else
 		LAUNCH(k_pack_warm, std::min(grid_for(Ap.cap, 256), wide), 256, st, Ap);
+#endif
 		LAUNCH(k_collide<0>, g, 128, st, S, B, (const int *)w->P.a[0], (const int *)w->P.b[0], (const int *)&w->P.count[0], w->P.cap, Ap, Tp, Ac, w->C);
 		LAUNCH(k_collide<1>, g, 128, st, S, B, (const int *)w->P.a[1], (const int *)w->P.b[1], (const int *)&w->P.count[1], w->P.cap, Ap, Tp, Ac, w->C);
 		LAUNCH(k_collide<2>, g, 128, st, S, B, (const int *)w->P.a[2], (const int *)w->P.b[2], (const int *)&w->P.count[2], w->P.cap, Ap, Tp, Ac, w->C);
