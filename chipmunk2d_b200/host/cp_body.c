@@ -6,9 +6,19 @@
  * accumulation :206-239, setters :241-467, integrators :493-522) and the sleep API of
  * src/cpSpaceComponent.c:113-349.
  */
+#include <stdlib.h>
+#include <string.h>
 #include "cp_host.h"
 
-cpBody *cpBodyAlloc(void){ return (cpBody *)cpcalloc(1, sizeof(cpBody)); }
+/* 64-byte aligned, so that the struct's "lines" (cp_host.h) are cache lines; released with cpfree like any other object */
+cpBody *
+cpBodyAlloc(void)
+{
+	void *mem = NULL;
+	if(posix_memalign(&mem, 64, (sizeof(cpBody) + 63) & ~(size_t)63)) return NULL;
+	memset(mem, 0, sizeof(cpBody));
+	return (cpBody *)mem;
+}
 
 static void
 touch(cpBody *body)

@@ -32,20 +32,20 @@ struct cpBody {
 	cpBody *sleepRoot;         /* non-NULL <=> asleep; all members of a sleeping component share it */
 	cpFloat m;
 	cpVect f;
-	cpFloat t;
+	cpDataPointer userData;    /* (callbacks of cpSpaceEachBody usually start by asking for it) */
 	cpBool idleReset;          /* activated while awake since the last upload: the device restarts its idle timer */
 	unsigned fetchStamp;       /* == space->fetchStamp <=> this mirror holds the state of the last download */
 	/* second line: what the getters read */
 	cpTransform transform;
 	cpVect p;
 	/* the rest */
+	cpFloat t;
 	cpVect v;
 	cpFloat a, w;
 	cpFloat m_inv, i, i_inv;
 	cpVect cog;
 	cpVect v_bias;
 	cpFloat w_bias;
-	cpDataPointer userData;
 	cpBodyVelocityFunc velocity_func;
 	cpBodyPositionFunc position_func;
 	cpShape *shapeList;
