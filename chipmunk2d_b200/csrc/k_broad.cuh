@@ -113,6 +113,8 @@ CPB_DEVICE int bvh_delta(const uint64_t *__restrict__ keys, int n, int i, int j)
 	return __clzll((long long)(a ^ b));
 }
 
+#define CPB_REFIT_WIN 256
+#define CPB_BVH_LOCAL 0x40000000
 __global__ void k_bvh_build(DBvh T)
 {
 	int i = CPB_TID;
@@ -140,7 +142,10 @@ __global__ void k_bvh_build(DBvh T)
 	int left = (lo == gamma ? (n - 1) + gamma : gamma);
 	int right = (hi == gamma + 1 ? (n - 1) + gamma + 1 : gamma + 1);
 	T.left[i] = left; T.right[i] = right;
-	T.parent[left] = i; T.parent[right] = i;
+	// the parent word also says whether that parent's leaf range [lo, hi] lies inside one window of CPB_REFIT_WIN leaves:
+	// such nodes (255 of 256) are refitted from shared memory by the CTA that owns the window (k_bvh_refit_fused)
+	const int up = i | ((lo/CPB_REFIT_WIN == hi/CPB_REFIT_WIN) ? CPB_BVH_LOCAL : 0);
+	T.parent[left] = up; T.parent[right] = up;
 	if(i == 0) T.parent[0] = -1;
 }
 
@@ -196,6 +201,7 @@ __global__ void k_bvh_refit(DBvh T)
 	if(i >= n || n < 2) return;
 	int cur = T.parent[(n - 1) + i];
 	while(cur >= 0){
+		cur &= (CPB_BVH_LOCAL - 1);
 		// one acquire-release atomic instead of fence + atomic + fence: the first child to arrive releases the box it wrote,
 		// the second acquires it (the stand-alone fences were most of this kernel's 20-level latency chain)
 #ifndef CPB_EMU
@@ -217,6 +223,88 @@ __global__ void k_bvh_refit(DBvh T)
 		cur = T.parent[cur];
 	}
 }
+
+#ifndef CPB_EMU
+// Leaves + refit + traversal layout in one pass (the production path; the three kernels above are what the emulation build
+// runs).  A CTA owns a window of CPB_REFIT_WIN consecutive leaves.  Every internal node whose leaf range lies inside the
+// window -- its id does too, an internal node's id is one end of its range -- is refitted from shared memory: arrival
+// counters, child boxes and child links never leave the SM, so the bottom eight levels of the tree (255 of 256 nodes)
+// cost shared-memory latencies instead of an L2 atomic and two L2 loads per level.  The thread that completes the last
+// local node of its path goes on through the upper levels with the acquire-release protocol of k_bvh_refit.  Whoever
+// completes a node holds both children in registers and writes the node's traversal record (k_bvh_pack's job) right
+// there; node boxes go to global memory only where a non-local parent will read them.  The second arrival clears the
+// global counter it used, so no pass has to reset them for the next step.
+__device__ __forceinline__ void bvh_node_finish(const DBvh &T, int cur, int l, int r, double4 a, double4 b, int2 sa, int2 sb, int ka, int kb,
+	double4 &box, int2 &sp, int &skip)
+{
+	T.cbox[2*cur] = a; T.cbox[2*cur + 1] = b;
+	T.cinfo[cur] = make_int4(l, r, ka, kb);
+	T.cspace[cur] = make_int4(sa.x, sa.y, sb.x, sb.y);
+	box = make_double4(fmin(a.x, b.x), fmin(a.y, b.y), fmax(a.z, b.z), fmax(a.w, b.w));
+	sp = make_int2(sa.x < sb.x ? sa.x : sb.x, sa.y > sb.y ? sa.y : sb.y);
+	skip = (ka > kb ? ka : kb);
+}
+
+__global__ void __launch_bounds__(CPB_REFIT_WIN) k_bvh_refit_fused(DBvh T, DShapes S, DBodies B)
+{
+	__shared__ double4 s_box[2*CPB_REFIT_WIN];      // [0, WIN) internal nodes by id - base, [WIN, 2 WIN) leaves by position - base
+	__shared__ int2 s_sp[2*CPB_REFIT_WIN];
+	__shared__ int s_skip[2*CPB_REFIT_WIN];
+	__shared__ int s_left[CPB_REFIT_WIN], s_right[CPB_REFIT_WIN], s_parent[CPB_REFIT_WIN], s_flag[CPB_REFIT_WIN];
+	const int n = T.n, t = threadIdx.x, base = blockIdx.x*CPB_REFIT_WIN, i = base + t;
+	s_flag[t] = 0;
+	if(i < n - 1){ s_left[t] = T.left[i]; s_right[t] = T.right[i]; s_parent[t] = T.parent[i]; }
+	__syncthreads();
+	if(i >= n || n < 2) return;
+	// the leaf (k_bvh_leaves)
+	double4 box; int2 sp; int skip;
+	{
+		const int s = T.leaf_shape[i];
+		box = S.bb[s];
+		const int body = S.body[s];
+		const int space = B.space[body];
+		sp = make_int2(space, space);
+		skip = (shape_is_active(B, body) ? i : 0x7fffffff);
+	}
+	int me = (n - 1) + i;
+	s_box[CPB_REFIT_WIN + t] = box; s_sp[CPB_REFIT_WIN + t] = sp; s_skip[CPB_REFIT_WIN + t] = skip;
+	int up = T.parent[me];
+	// inside the window: shared memory only
+	while(up >= 0 && (up & CPB_BVH_LOCAL)){
+		const int cur = up & (CPB_BVH_LOCAL - 1), slot = cur - base;
+		__threadfence_block();
+		if(atomicAdd(&s_flag[slot], 1) == 0) return;   // first child to arrive: the sibling's thread finishes this node
+		__threadfence_block();
+		const int l = s_left[slot], r = s_right[slot];
+		const int il = (l >= n - 1 ? CPB_REFIT_WIN + (l - (n - 1)) - base : l - base);
+		const int ir = (r >= n - 1 ? CPB_REFIT_WIN + (r - (n - 1)) - base : r - base);
+		const double4 a = s_box[il], b = s_box[ir];
+		const int2 sa = s_sp[il], sb = s_sp[ir];
+		const int ka = s_skip[il], kb = s_skip[ir];
+		bvh_node_finish(T, cur, l, r, a, b, sa, sb, ka, kb, box, sp, skip);
+		s_box[slot] = box; s_sp[slot] = sp; s_skip[slot] = skip;
+		me = cur;
+		up = s_parent[slot];
+	}
+	if(up < 0) return;   // (the root of a tree that fits one window)
+	// the node this thread completed last is the child of a node outside the window: publish it
+	T.nbb[me] = box; T.nsp[me] = sp; T.nskip[me] = skip;
+	while(up >= 0){
+		const int cur = up & (CPB_BVH_LOCAL - 1);
+		int old;
+		asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(&T.flags[cur]) : "memory");
+		if(old == 0) return;
+		T.flags[cur] = 0;
+		const int l = T.left[cur], r = T.right[cur];
+		const double4 a = ld_cg4(&T.nbb[l]), b = ld_cg4(&T.nbb[r]);
+		const int2 sa = ld_cg_i2(&T.nsp[l]), sb = ld_cg_i2(&T.nsp[r]);
+		const int ka = ld_cg_i(&T.nskip[l]), kb = ld_cg_i(&T.nskip[r]);
+		bvh_node_finish(T, cur, l, r, a, b, sa, sb, ka, kb, box, sp, skip);
+		T.nbb[cur] = box; T.nsp[cur] = sp; T.nskip[cur] = skip;
+		up = T.parent[cur];
+	}
+}
+#endif
 
 // ---- K4 rules ----
 CPB_DEVICE bool bb_intersects(double4 a, double4 b){

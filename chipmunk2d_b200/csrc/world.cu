@@ -167,6 +167,8 @@ struct cpb200_world {
 	// traversal gets dearer as the boxes of an old topology spread.  Structural edits rebuild at once.
 	bool bvh_valid; int bvh_age, bvh_period;
 	bool arb_derived_stale[2];  // per arbiter buffer: the last step computed nMass / tMass / bias inside its row build; a read-back recomputes them
+	int pack_ctas;              // CTAs per SM of the side-stream k_pack_warm (env CPB200_PACK_CTAS)
+	bool refit_unfused;         // env CPB200_REFIT_UNFUSED (measurement switch): k_bvh_leaves + k_bvh_refit + k_bvh_pack instead of the fused kernel
 	bool bvh_no_valve;          // env CPB200_BVH_NO_VALVE (measurement switch)
 	double bvh_fresh_visits;    // visits per query right after a rebuild (0 = not measured): cpb200_world_sync rebuilds early when an aged tree needs 1.5x that
 	bool graph_enabled;
@@ -335,7 +337,8 @@ extern "C" cpb200_world *cpb200_world_create(int device, int n_spaces)
 	w->mid_solve = false; w->solver_variant = 0; w->last_solver_path = 0;
 	memset(w->graph, 0, sizeof(w->graph)); memset(w->graph_last_sig, 0, sizeof(w->graph_last_sig)); w->graph_replays = w->graph_captures = 0;
 	w->arb_derived_stale[0] = w->arb_derived_stale[1] = false;
-	w->bvh_valid = false; w->bvh_age = 0; w->bvh_period = 8; w->bvh_fresh_visits = 0.0; w->bvh_no_valve = (getenv("CPB200_BVH_NO_VALVE") != NULL);
+	w->bvh_valid = false; w->bvh_age = 0; w->bvh_period = 8; w->bvh_fresh_visits = 0.0; w->bvh_no_valve = (getenv("CPB200_BVH_NO_VALVE") != NULL); w->refit_unfused = (getenv("CPB200_REFIT_UNFUSED") != NULL);
+	w->pack_ctas = 3; { const char *e = getenv("CPB200_PACK_CTAS"); if(e && atoi(e) >= 1) w->pack_ctas = atoi(e); }
 	{ const char *e = getenv("CPB200_BVH_PERIOD"); if(e && atoi(e) >= 1) w->bvh_period = atoi(e); }
 	w->graph_enabled = (getenv("CPB200_NO_GRAPH") == NULL); w->graph_error[0] = 0;
 	w->io_src = NULL; w->io_sink = NULL; w->d_io_force = w->d_io_pos = w->d_io_vel = NULL; w->io_cap = 0;
@@ -1479,13 +1482,14 @@ static int step_phase_a(cpb200_world *w, double dt)
 	STAGE_END(w, ST_SHAPE_CACHE);
 
 	// The warm-start lines of last step's records (what the narrowphase looks up) depend on nothing this step does: the
-	// pass that packs them runs on a second stream, one CTA per SM, beside the tree build / refit, and joins in front of
-	// the collide kernels.  Worth 1 % of the 1 M step.  Measured alternatives: beside the integrators (bandwidth-bound
-	// themselves) it gains nothing; with a full grid it crowds the refit's warps out and slows that atomic chain down
-	// by what it saves; beside the traversal it costs more (0.24 -> 0.34 ms) than it saves.
+	// pass that packs them runs on a second stream, three CTAs per SM, beside the tree build / refit, and joins in front
+	// of the collide kernels.  Worth 2 % of the 1 M step together with the shared-memory refit.  Measured alternatives:
+	// beside the integrators (bandwidth-bound themselves) it gains nothing; beside the old refit (a 20-level chain of L2
+	// atomics) anything wider than one CTA per SM slowed that chain down by what it saved; beside the traversal it costs
+	// more (0.24 -> 0.34 ms) than it saves.
 #ifndef CPB_EMU
 	CPB_CHECK(cudaEventRecord(w->ev_fork_a, st)); CPB_CHECK(cudaStreamWaitEvent(w->stream2, w->ev_fork_a, 0));
-	LAUNCH(k_pack_warm, std::min(grid_for(Ap.cap, 256), w->sm_count), 256, w->stream2, Ap);
+	LAUNCH(k_pack_warm, std::min(grid_for(Ap.cap, 256), w->sm_count*w->pack_ctas), 256, w->stream2, Ap);
 	CPB_CHECK(cudaEventRecord(w->ev_join_a, w->stream2));
 #endif
 
@@ -1536,9 +1540,15 @@ static int step_phase_a(cpb200_world *w, double dt)
 			STAGE_END(w, ST_BVH_KEYS); STAGE_END(w, ST_BVH_SORT);
 			w->bvh_age++;
 		}
-		LAUNCH(k_bvh_leaves, grid_for(ns, 256), 256, st, T, S, B, (int)!rebuild);
-		LAUNCH(k_bvh_refit, grid_for(ns, 256), 256, st, T);
-		LAUNCH(k_bvh_pack, grid_for(ns - 1, 256), 256, st, T);
+#ifndef CPB_EMU
+		if(!w->refit_unfused) LAUNCH(k_bvh_refit_fused, grid_for(ns, CPB_REFIT_WIN), CPB_REFIT_WIN, st, T, S, B);
+		else
+#endif
+		{
+			LAUNCH(k_bvh_leaves, grid_for(ns, 256), 256, st, T, S, B, 1);
+			LAUNCH(k_bvh_refit, grid_for(ns, 256), 256, st, T);
+			LAUNCH(k_bvh_pack, grid_for(ns - 1, 256), 256, st, T);
+		}
 		STAGE_END(w, ST_BVH_BUILD);
 		LAUNCH(k_bvh_pairs, grid_for(ns, 128), 128, st, T, S, B, w->P, (const uint64_t *)w->d_nocollide, w->n_nocollide, (int)(w->n_spaces > 1), &w->C->overflow, &w->C->bvh_visits);
 #ifndef CPB_EMU
