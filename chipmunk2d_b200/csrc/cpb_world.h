@@ -174,6 +174,10 @@ struct DBvh {
 	double4 *cbox;         // [2(n-1)] boxes of the two children of internal node i at [2i], [2i+1]
 	int4 *cinfo;           // [n-1] (left, right, left skip key, right skip key)
 	int4 *cspace;          // [n-1] (left space min, max, right space min, max)
+	// nodes (leaves or internal) whose own leaf range lies inside one refit window while their parent's does not: where the
+	// shared-memory refit hands over to the pass through L2.  Listed by k_bvh_build, valid as long as the topology is.
+	int *top_list;         // [n]
+	int *top_count;        // [1]
 };
 
 // pair lists by class: 0 circle-circle, 1 circle-segment, 2 everything that needs GJK

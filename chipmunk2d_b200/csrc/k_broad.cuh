@@ -40,9 +40,9 @@ static inline void atomic_min_double(double *addr, double v){ if(v < *addr) *add
 static inline void atomic_max_double(double *addr, double v){ if(v > *addr) *addr = v; }
 #endif
 
-__global__ void k_bounds_init(double *bounds)
+__global__ void k_bounds_init(double *bounds, int *top_count)
 {
-	if(CPB_TID == 0){ bounds[0] = INFINITY; bounds[1] = INFINITY; bounds[2] = -INFINITY; bounds[3] = -INFINITY; }
+	if(CPB_TID == 0){ bounds[0] = INFINITY; bounds[1] = INFINITY; bounds[2] = -INFINITY; bounds[3] = -INFINITY; *top_count = 0; }
 }
 
 __global__ void k_bounds(DShapes S, double *bounds)
@@ -144,9 +144,15 @@ __global__ void k_bvh_build(DBvh T)
 	T.left[i] = left; T.right[i] = right;
 	// the parent word also says whether that parent's leaf range [lo, hi] lies inside one window of CPB_REFIT_WIN leaves:
 	// such nodes (255 of 256) are refitted from shared memory by the CTA that owns the window (k_bvh_refit_fused)
-	const int up = i | ((lo/CPB_REFIT_WIN == hi/CPB_REFIT_WIN) ? CPB_BVH_LOCAL : 0);
+	const bool local = (lo/CPB_REFIT_WIN == hi/CPB_REFIT_WIN);
+	const int up = i | (local ? CPB_BVH_LOCAL : 0);
 	T.parent[left] = up; T.parent[right] = up;
 	if(i == 0) T.parent[0] = -1;
+	// children that are the top of a window-local subtree (or a lone leaf) under a node that is not: k_bvh_refit_top starts there
+	if(!local){
+		if(lo/CPB_REFIT_WIN == gamma/CPB_REFIT_WIN){ int k = atomicAdd(T.top_count, 1); if(k < n) T.top_list[k] = left; }
+		if((gamma + 1)/CPB_REFIT_WIN == hi/CPB_REFIT_WIN){ int k = atomicAdd(T.top_count, 1); if(k < n) T.top_list[k] = right; }
+	}
 }
 
 // reset_flags: a step that keeps the tree's topology (no k_morton pass) clears the refit's arrival counters here
@@ -229,8 +235,8 @@ __global__ void k_bvh_refit(DBvh T)
 // runs).  A CTA owns a window of CPB_REFIT_WIN consecutive leaves.  Every internal node whose leaf range lies inside the
 // window -- its id does too, an internal node's id is one end of its range -- is refitted from shared memory: arrival
 // counters, child boxes and child links never leave the SM, so the bottom eight levels of the tree (255 of 256 nodes)
-// cost shared-memory latencies instead of an L2 atomic and two L2 loads per level.  The thread that completes the last
-// local node of its path goes on through the upper levels with the acquire-release protocol of k_bvh_refit.  Whoever
+// cost shared-memory latencies instead of an L2 atomic and two L2 loads per level.  The upper levels are a second, small
+// launch (k_bvh_refit_top) with the acquire-release protocol of k_bvh_refit.  Whoever
 // completes a node holds both children in registers and writes the node's traversal record (k_bvh_pack's job) right
 // there; node boxes go to global memory only where a non-local parent will read them.  The second arrival clears the
 // global counter it used, so no pass has to reset them for the next step.
@@ -286,22 +292,32 @@ __global__ void __launch_bounds__(CPB_REFIT_WIN) k_bvh_refit_fused(DBvh T, DShap
 		me = cur;
 		up = s_parent[slot];
 	}
-	if(up < 0) return;   // (the root of a tree that fits one window)
-	// the node this thread completed last is the child of a node outside the window: publish it
-	T.nbb[me] = box; T.nsp[me] = sp; T.nskip[me] = skip;
-	while(up >= 0){
-		const int cur = up & (CPB_BVH_LOCAL - 1);
-		int old;
-		asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(&T.flags[cur]) : "memory");
-		if(old == 0) return;
-		T.flags[cur] = 0;
-		const int l = T.left[cur], r = T.right[cur];
-		const double4 a = ld_cg4(&T.nbb[l]), b = ld_cg4(&T.nbb[r]);
-		const int2 sa = ld_cg_i2(&T.nsp[l]), sb = ld_cg_i2(&T.nsp[r]);
-		const int ka = ld_cg_i(&T.nskip[l]), kb = ld_cg_i(&T.nskip[r]);
-		bvh_node_finish(T, cur, l, r, a, b, sa, sb, ka, kb, box, sp, skip);
-		T.nbb[cur] = box; T.nsp[cur] = sp; T.nskip[cur] = skip;
-		up = T.parent[cur];
+	// the node this thread completed last is the child of a node outside the window (or the root): publish it for k_bvh_refit_top
+	if(up >= 0){ T.nbb[me] = box; T.nsp[me] = sp; T.nskip[me] = skip; }
+}
+
+// The levels above the windows: one thread per window-top node (T.top_list, a few thousand at a million leaves -- all
+// resident at once, where the leaf-parallel kernel kept every CTA alive for as long as its one surviving thread climbed).
+__global__ void __launch_bounds__(128) k_bvh_refit_top(DBvh T)
+{
+	const int count = min(*T.top_count, T.n);
+	for(int k = CPB_TID; k < count; k += CPB_NTHREADS){
+		int up = T.parent[T.top_list[k]];
+		while(up >= 0){
+			const int cur = up & (CPB_BVH_LOCAL - 1);
+			int old;
+			asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(&T.flags[cur]) : "memory");
+			if(old == 0) break;      // first child to arrive: the sibling's thread finishes this node
+			T.flags[cur] = 0;        // both children are in: the counter is ready for the next step
+			const int l = T.left[cur], r = T.right[cur];
+			const double4 a = ld_cg4(&T.nbb[l]), b = ld_cg4(&T.nbb[r]);
+			const int2 sa = ld_cg_i2(&T.nsp[l]), sb = ld_cg_i2(&T.nsp[r]);
+			const int ka = ld_cg_i(&T.nskip[l]), kb = ld_cg_i(&T.nskip[r]);
+			double4 box; int2 sp; int skip;
+			bvh_node_finish(T, cur, l, r, a, b, sa, sb, ka, kb, box, sp, skip);
+			T.nbb[cur] = box; T.nsp[cur] = sp; T.nskip[cur] = skip;
+			up = T.parent[cur];
+		}
 	}
 }
 #endif

@@ -93,7 +93,9 @@ extern "C" const char *cpb200_stage_name(int i){ return (i >= 0 && i < ST_COUNT)
 // ------------------------------------------------------------------ world
 struct AllocGroup {
 	std::vector<void *> ptrs;
-	void release(){ for(void *p : ptrs) cudaFree(p); ptrs.clear(); }
+	unsigned long long gen = 0;   // bumped by every allocation and release: part of the step graph's signature, so a graph never
+	                              // outlives a buffer it names (a freed and re-allocated array may or may not get its old address)
+	void release(){ for(void *p : ptrs) cudaFree(p); ptrs.clear(); gen++; }
 };
 
 struct cpb200_world {
@@ -212,6 +214,7 @@ static int dalloc(AllocGroup &g, T *&p, size_t n)
 	if(e != cudaSuccess){ cpb_set_error("cudaMalloc(%zu bytes) failed: %s", sizeof(T)*n, cudaGetErrorString(e)); p = NULL; return -1; }
 	cudaMemsetAsync(q, 0, sizeof(T)*n, 0);
 	g.ptrs.push_back(q);
+	g.gen++;
 	p = (T *)q;
 	return 0;
 }
@@ -873,7 +876,7 @@ extern "C" int cpb200_world_set_shapes(cpb200_world *w, int n, const cpb200_shap
 	T.n = n;
 	int nn = cap;
 	DA(w->gV, T.keys, nn); DA(w->gV, T.leaf_shape, nn); DA(w->gV, T.left, nn); DA(w->gV, T.right, nn); DA(w->gV, T.parent, 2*nn);
-	DA(w->gV, T.nbb, 2*nn); DA(w->gV, T.nsp, 2*nn); DA(w->gV, T.flags, nn); DA(w->gV, T.bounds, 4);
+	DA(w->gV, T.nbb, 2*nn); DA(w->gV, T.nsp, 2*nn); DA(w->gV, T.flags, nn); DA(w->gV, T.bounds, 4); DA(w->gV, T.top_list, nn); DA(w->gV, T.top_count, 4);
 	DA(w->gV, T.nskip, 2*nn); DA(w->gV, T.cbox, 2*nn); DA(w->gV, T.cinfo, nn); DA(w->gV, T.cspace, nn);
 	DA(w->gV, w->keys_b, nn); DA(w->gV, w->vals_b, nn);
 	DA(w->gV, w->sort_tmp, cpb_sort_tmp_elems(nn) + 16);
@@ -1515,7 +1518,7 @@ static int step_phase_a(cpb200_world *w, double dt)
 		DBvh &T = w->bvh;
 		const bool rebuild = bvh_rebuild_due(w);
 		if(rebuild){
-			LAUNCH(k_bounds_init, 1, 32, st, T.bounds);
+			LAUNCH(k_bounds_init, 1, 32, st, T.bounds, T.top_count);
 			LAUNCH(k_bounds, std::min(grid_for(ns, 256), wide), 256, st, S, T.bounds);
 			// Morton bits: log2(shapes) + 4 (sixteen cells per shape), in whole radix digits
 			int want_bits = 4; while((1 << (want_bits - 4)) < ns && want_bits < 32) want_bits++;
@@ -1541,8 +1544,10 @@ static int step_phase_a(cpb200_world *w, double dt)
 			w->bvh_age++;
 		}
 #ifndef CPB_EMU
-		if(!w->refit_unfused) LAUNCH(k_bvh_refit_fused, grid_for(ns, CPB_REFIT_WIN), CPB_REFIT_WIN, st, T, S, B);
-		else
+		if(!w->refit_unfused){
+			LAUNCH(k_bvh_refit_fused, grid_for(ns, CPB_REFIT_WIN), CPB_REFIT_WIN, st, T, S, B);
+			LAUNCH(k_bvh_refit_top, std::min(grid_for(ns/16 + 128, 128), wide), 128, st, T);
+		} else
 #endif
 		{
 			LAUNCH(k_bvh_leaves, grid_for(ns, 256), 256, st, T, S, B, 1);
@@ -1837,6 +1842,9 @@ static unsigned long long step_signature(cpb200_world *w, double dt, int iterati
 	unsigned long long h = 0xcbf29ce484222325ull, d;
 	memcpy(&d, &dt, 8);
 	h = sig_mix(h, rebuild ? 2ull : 1ull); h = sig_mix(h, (unsigned long long)(w->bvh_period > 1 ? 1 : 0));
+	// every group of device arrays: their generation counters (the pointers hashed below are a sample, not all of them)
+	h = sig_mix(h, w->gB.gen); h = sig_mix(h, w->gS.gen); h = sig_mix(h, w->gJ.gen); h = sig_mix(h, w->gA.gen); h = sig_mix(h, w->gK.gen);
+	h = sig_mix(h, w->gV.gen); h = sig_mix(h, w->gP.gen); h = sig_mix(h, w->gI.gen); h = sig_mix(h, w->gW.gen); h = sig_mix(h, w->gSL.gen);
 	h = sig_mix(h, d); h = sig_mix(h, (unsigned long long)iterations);
 	h = sig_mix(h, (unsigned long long)w->B.n); h = sig_mix(h, (unsigned long long)w->S.n); h = sig_mix(h, (unsigned long long)w->S.nv); h = sig_mix(h, (unsigned long long)w->J.n);
 	h = sig_mix(h, (unsigned long long)w->cap_arbs); h = sig_mix(h, (unsigned long long)w->cap_pairs); h = sig_mix(h, (unsigned long long)w->n_spaces);
