@@ -120,3 +120,29 @@ def test_production_step_equals_split_step(name):
                 for f in ("r1", "r2", "n_mass", "t_mass", "bias", "jn_acc", "jt_acc", "j_bias"):
                     assert np.array_equal(ra["contacts"][f][m, k], rb["contacts"][f][m, k]), (name, s, k, f)
     assert a.stats()["n_arbiters"] > 0
+
+
+def test_graph_is_recaptured_after_structural_edits_reallocate_device_tables():
+    """Appending / removing objects re-allocates the space-local tables (and, beyond the slack, the object arrays).  A
+    freed array may or may not get its old address back, so equal pointers prove nothing: the graph signature carries
+    the allocation generation of every group of device arrays, and a graph captured before the edit is never replayed
+    after it.  Other worlds are created in between to stir the device allocator."""
+    from tests.test_gpu_append import newcomers
+    sc = golden_scene("PyramidStack")
+    a, b = pair([sc])
+    dt = sc.dt
+    a.step(dt, 40); b.step(dt, 40)
+    bd, sd, verts, _jd = newcomers(a, 2, "circle", y0=300.0)
+    junk = []
+    for w in (a, b):
+        w.append_bodies(bd); w.append_shapes(sd, verts)
+        junk.append(World(1)); junk[-1].load_scene(golden_scene("Chains"))
+        w.step(dt, 40)
+        w.remove_shape(w.n_shapes - 1)                   # the shape count of two edits ago: same sizes, new tables
+        junk.append(World(1)); junk[-1].load_scene(sc)
+        w.step(dt, 40)
+        w.remove_shape(w.n_shapes - 1)
+        w.step(dt, 40)
+    a.sync(); b.sync()
+    assert same(a, b)
+    assert a.stats()["overflow"] == 0 and a.graph_stats()["replays"] > 60, a.graph_stats()
