@@ -305,18 +305,20 @@ __global__ void __launch_bounds__(128) k_bvh_refit_top(DBvh T)
 		int up = T.parent[T.top_list[k]];
 		while(up >= 0){
 			const int cur = up & (CPB_BVH_LOCAL - 1);
+			// the links are topology (constant while the tree is refitted): fetched beside the arrival atomic, not behind it --
+			// two dependent L2 round trips per level (atomic, child data) instead of four
+			const int l = __ldg(&T.left[cur]), r = __ldg(&T.right[cur]), next = __ldg(&T.parent[cur]);
 			int old;
 			asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(&T.flags[cur]) : "memory");
 			if(old == 0) break;      // first child to arrive: the sibling's thread finishes this node
 			T.flags[cur] = 0;        // both children are in: the counter is ready for the next step
-			const int l = T.left[cur], r = T.right[cur];
 			const double4 a = ld_cg4(&T.nbb[l]), b = ld_cg4(&T.nbb[r]);
 			const int2 sa = ld_cg_i2(&T.nsp[l]), sb = ld_cg_i2(&T.nsp[r]);
 			const int ka = ld_cg_i(&T.nskip[l]), kb = ld_cg_i(&T.nskip[r]);
 			double4 box; int2 sp; int skip;
 			bvh_node_finish(T, cur, l, r, a, b, sa, sb, ka, kb, box, sp, skip);
 			T.nbb[cur] = box; T.nsp[cur] = sp; T.nskip[cur] = skip;
-			up = T.parent[cur];
+			up = next;
 		}
 	}
 }
